@@ -1,0 +1,153 @@
+/* platanus3_b200.h — C ABI of the B200-native k-mer-to-graph hot path.
+ *
+ * Drop-in boundary for platanus3's Load -> CountShortKmer -> MakeBF -> DeBruijnGraph
+ * neighbour-query stage. The reference has no FFI of its own (one C++ translation unit,
+ * reference main.cpp:1-9); every entry point below names the reference function it replaces.
+ * Plain pointers and sizes only. All functions return P3_OK (0) or a negative P3_ERR_* code;
+ * p3_last_error() gives the message. There is NO CPU fallback: every compute entry point
+ * fails with P3_ERR_CUDA when no sm_100 device is usable.
+ *
+ * k-mer words: W = ceil(2k/64) little-endian uint64 words holding the same 2k-bit integer as
+ * the reference's std::bitset<2k> (first base in the most significant 2 bits, A=0 C=1 G=2 T=3;
+ * reference src/BitCalc.cpp:8-19). This build supports 21 <= k <= 32 on the device (W = 1).
+ *
+ * 2-bit staging layout ("packed reads"): all reads back to back, 32 bases per uint64 word,
+ * base j of the stream in word j/32 at bits [63-2(j%32)-1, 63-2(j%32)] (MSB first), zero
+ * padded, plus read offsets off[0..n_reads] in bases. p3_packed_words() words are required
+ * (one halo word included). An optional "non-ACGT" plane (uint32 per word, bit 31-(j%32))
+ * reproduces the reference reading such characters as code 0 on both strands
+ * (reference src/common.h:32-33 operator[] default-insert).
+ */
+#ifndef PLATANUS3_B200_H
+#define PLATANUS3_B200_H
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define P3_OK 0
+#define P3_ERR_CUDA (-1)       /* no device / CUDA runtime error */
+#define P3_ERR_ARG (-2)        /* bad argument (unsupported k, null pointer, ...) */
+#define P3_ERR_TABLE_FULL (-3) /* a hash table overflowed its capacity (after auto-grow) */
+#define P3_ERR_STATE (-4)      /* stage called out of order */
+#define P3_ERR_NOMEM (-5)
+#define P3_ERR_IO (-6)
+
+#define P3_SHORTK 21        /* reference src/Options.cpp:14 shortk_length */
+#define P3_COV_THRESHOLD 2  /* reference src/MakeBloomFilter.cpp:28 cov_threshold */
+#define P3_MIN_K 21
+#define P3_MAX_K 32
+
+typedef struct p3_ctx p3_ctx;
+
+const char *p3_last_error(void);
+int p3_version(void);
+int p3_device_count(void);
+
+/* ---- host-only helpers (no GPU needed) --------------------------------------------------- */
+
+/* Options::EstimateBloomfilter, reference src/Options.cpp:50-60 (the filter_size==0 branch).
+ * Fails with P3_ERR_ARG when the estimate degenerates (item_number == 0), where the reference
+ * divides by zero. */
+int p3_estimate_bloomfilter(uint64_t all_bases, uint32_t k, uint64_t *filter_size, uint32_t *num_hashes);
+
+/* number of uint64 words of 2-bit staging for total_bases bases (incl. one halo word) */
+uint64_t p3_packed_words(uint64_t total_bases);
+
+/* GetFirstKmerForward's base coding (reference src/BitCalc.cpp:8-19) applied to whole reads:
+ * ASCII reads seq[off[i]..off[i+1]) -> 2-bit staging. nmask may be NULL; *has_non_acgt tells
+ * whether any character outside ACGT was seen (then the nmask plane is required for parity). */
+int p3_pack_reads(const char *seq, const uint64_t *off, uint64_t n_reads, uint64_t *packed,
+                  uint32_t *nmask, int *has_non_acgt);
+
+/* pinned host staging buffers (cudaHostAlloc) */
+void *p3_host_alloc(size_t bytes);
+void p3_host_free(void *p);
+
+/* ---- context ------------------------------------------------------------------------------ */
+
+/* One context per GPU. stream: a cudaStream_t to launch on, or NULL for a private stream. */
+p3_ctx *p3_create(int device, void *stream);
+void p3_destroy(p3_ctx *ctx);
+int p3_synchronize(p3_ctx *ctx);
+
+/* ---- reads (ReadFile::reads, reference src/Load.cpp:8) ----------------------------------- */
+
+/* host staging -> device (async H2D on the context stream; buffers should be pinned) */
+int p3_reads_upload(p3_ctx *ctx, const uint64_t *h_packed, uint64_t total_bases,
+                    const uint64_t *h_off, uint64_t n_reads, const uint32_t *h_nmask);
+/* device-resident staging owned by the caller (zero copy); must stay alive while attached */
+int p3_reads_attach(p3_ctx *ctx, const uint64_t *d_packed, uint64_t total_bases,
+                    const uint64_t *d_off, uint64_t n_reads, const uint32_t *d_nmask);
+
+/* ---- stage A: ReadFile::CountShortKmer, reference src/Load.cpp:105-127 -------------------- */
+
+/* Counts every canonical 21-mer of every read into the device count table.
+ * table_slots: capacity in 8-byte slots (0 = auto from the number of 21-mer positions). */
+int p3_count_short_kmers(p3_ctx *ctx, uint64_t table_slots);
+int p3_short_kmer_stats(p3_ctx *ctx, uint64_t *n_positions, uint64_t *n_distinct);
+/* shortk_database as (key,count) pairs in table order (unsorted). cap = array capacity. */
+int p3_short_kmer_export(p3_ctx *ctx, uint64_t *h_keys, uint64_t *h_counts, uint64_t cap, uint64_t *n);
+/* KC[key] for a batch of canonical 21-mers (0 when absent) */
+int p3_short_kmer_lookup(p3_ctx *ctx, const uint64_t *h_keys, uint64_t n, uint64_t *h_counts);
+
+/* ---- stage B: MakeBF, reference src/MakeBloomFilter.cpp:25-89 ----------------------------- */
+
+/* 21-mer coverage -> window minimum (RMQ) >= cov_threshold -> BF.add(canonical k-mer) and the
+ * first such k-mer of each read as seed. solid_slots: capacity of the distinct-solid-k-mer
+ * set (0 = auto, grows on overflow). */
+int p3_make_bf(p3_ctx *ctx, uint32_t k, uint64_t filter_size, uint32_t num_hashes,
+               uint32_t cov_threshold, uint64_t solid_slots);
+int p3_make_bf_stats(p3_ctx *ctx, uint64_t *n_adds, uint64_t *n_distinct_solid);
+/* BF::m_bits (reference src/bloomfilter.cpp:28): (filter_size+7)/8 bytes, bit i = byte i>>3 bit i&7 */
+int p3_bf_export(p3_ctx *ctx, uint8_t *h_bits);
+/* install a filter from host bits (for stand-alone add / query use) */
+int p3_bf_import(p3_ctx *ctx, uint32_t k, uint64_t filter_size, uint32_t num_hashes, const uint8_t *h_bits);
+/* seed_kmer: position in read r of its first solid k-mer, or -1 (MakeBloomFilter.cpp:79-83) */
+int p3_seed_export(p3_ctx *ctx, int64_t *h_seed_pos);
+/* one bit per stream position (uint32 per 32 bases, MSB first): k-mer starting there was added */
+int p3_solid_flags_export(p3_ctx *ctx, uint32_t *h_bitmap);
+/* BF<Key>::add / possiblyContains, reference src/bloomfilter.cpp:69-86, batched over
+ * already-canonical k-mers (n*W words) */
+int p3_bf_add(p3_ctx *ctx, const uint64_t *h_kmers, uint64_t n);
+int p3_bf_possibly_contains(p3_ctx *ctx, const uint64_t *h_kmers, uint64_t n, uint8_t *h_out);
+/* GetDoubleHash_64bit, reference src/MyHash.cpp:22-35, over canonical k-mers: out = n*2 words */
+int p3_double_hash(p3_ctx *ctx, uint32_t k, const uint64_t *h_kmers, uint64_t n, uint64_t *h_out);
+
+/* ---- stage C: DeBruijnGraph::CheckDirections, reference src/DeBruijnGraph.cpp:326-345 ----- */
+
+/* For every distinct solid k-mer (canonical orientation) the 8 neighbour queries of
+ * CheckDirections/IsRecorded (:318-323): bit i of the adjacency byte = direction i recorded
+ * (0-3 left extension by A,C,G,T; 4-7 right extension). */
+int p3_dbg_adjacency(p3_ctx *ctx);
+int p3_dbg_stats(p3_ctx *ctx, uint64_t *n_kmers, uint64_t *n_edges);
+/* distinct solid k-mers (n*W words, unsorted) and their adjacency bytes */
+int p3_dbg_export(p3_ctx *ctx, uint64_t *h_kmers, uint8_t *h_adj, uint64_t cap, uint64_t *n);
+/* CheckDirections on arbitrary ORIENTED k-mers (ignored_direction = -1) */
+int p3_check_directions(p3_ctx *ctx, const uint64_t *h_kmers, uint64_t n, uint8_t *h_mask);
+
+/* ---- whole path ---------------------------------------------------------------------------- */
+
+/* Assemble<>, reference src/Assemble.cpp:7-21, up to the neighbour queries MakeDBG issues:
+ * upload + stages A, B, C in one call on host staging buffers. filter_size == 0 runs
+ * p3_estimate_bloomfilter(all_bases, k) first, as main.cpp:23 does. Results stay on the device
+ * for the export calls above. */
+int p3_assemble_hot_path(p3_ctx *ctx, const uint64_t *h_packed, uint64_t total_bases,
+                         const uint64_t *h_off, uint64_t n_reads, const uint32_t *h_nmask,
+                         uint64_t all_bases, uint32_t k, uint64_t filter_size, uint32_t num_hashes,
+                         uint64_t table_slots, uint64_t solid_slots);
+
+/* device milliseconds of the last run of each stage (CUDA events on the context stream):
+ * ms[0]=count21 ms[1]=coverage flags ms[2]=solid+bloom ms[3]=seeds ms[4]=adjacency */
+int p3_stage_ms(p3_ctx *ctx, float ms[5]);
+/* kernels launched by this context since creation (for bench.py's gpu_launches) */
+uint64_t p3_launch_count(p3_ctx *ctx);
+/* filter parameters in effect */
+int p3_bf_params(p3_ctx *ctx, uint64_t *filter_size, uint32_t *num_hashes, uint32_t *k);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -206,6 +206,13 @@ void p3ref_add_read(void *h, const char *name, const char *seq, uint64_t len) {
         r->rf->all_bases += len;
     }
 }
+// batch form: reads seq[off[i]..off[i+1]) named ">r<i>"
+void p3ref_add_reads(void *h, const char *seq, const uint64_t *off, uint64_t n) {
+    for (uint64_t i = 0; i < n; i++) {
+        std::string name = ">r" + std::to_string(i);
+        p3ref_add_read(h, name.c_str(), seq + off[i], off[i + 1] - off[i]);
+    }
+}
 uint64_t p3ref_all_bases(void *h) { return ((RefRun *)h)->rf->all_bases; }
 uint64_t p3ref_n_reads(void *h) { return ((RefRun *)h)->rf->reads.size(); }
 // dump reads (sorted by name for determinism): lens[i], then concatenated into seq
@@ -282,6 +289,13 @@ void p3ref_bf_add(void *h, const char *kmer) { ((RefRun *)h)->st->bf_add(kmer); 
 int p3ref_check_directions(void *h, const char *kmer, int ignored) {
     RefRun *r = (RefRun *)h; if (!r->st->lgp) r->st->lgp = &r->lg;
     return r->st->check_directions(kmer, ignored);
+}
+// CheckDirections over n ORIENTED k-mers given as n*k characters (the per-k-mer neighbour
+// queries MakeDBG issues, DeBruijnGraph.cpp:164,232,269, without the walk around them)
+void p3ref_check_directions_batch(void *h, const char *kmers, uint64_t n, uint8_t *out) {
+    RefRun *r = (RefRun *)h; if (!r->st->lgp) r->st->lgp = &r->lg;
+    int k = (int)r->opt.kmer_length;
+    for (uint64_t i = 0; i < n; i++) out[i] = (uint8_t)r->st->check_directions(kmers + i * k, -1);
 }
 int p3ref_is_recorded(void *h, const char *kmer) {
     RefRun *r = (RefRun *)h; if (!r->st->lgp) r->st->lgp = &r->lg;

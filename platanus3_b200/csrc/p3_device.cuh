@@ -1,0 +1,274 @@
+// p3_device.cuh — device-side building blocks of the k-mer-to-graph hot path (sm_100a).
+//
+// Everything here is integer/byte work bound by HBM random access, so the design rules are:
+// coalesced 2-bit read staging, one 256-bit load per 32-byte hash bucket, 64-bit atomics that
+// stay in L2, and no per-read rolling state (each k-mer is cut straight out of two packed
+// words with a funnel shift, so positions are independent and map 1:1 onto threads).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace p3 {
+
+constexpr int kShortK = 21;                        // reference src/Options.cpp:14
+constexpr uint64_t kKey42 = (1ULL << 42) - 1;      // canonical 21-mer = 42 bits
+constexpr uint64_t kCntOne = 1ULL << 42;           // count lives in slot bits 42..63
+constexpr uint64_t kCntFieldMax = 0x3FFFFFULL;     // 22-bit count field
+constexpr uint64_t kEmpty = ~0ULL;                 // all-T is never canonical (rc = all-A = 0 is smaller)
+constexpr int kOvfCap = 1024;                      // overflow side table (counts >= 2^22)
+
+struct Stats {
+    unsigned long long n_pos21;           // valid 21-mer positions counted
+    unsigned long long n_distinct21;      // distinct canonical 21-mers
+    unsigned long long n_adds;            // BF.add calls the reference would make
+    unsigned long long n_distinct_solid;  // distinct canonical solid k-mers
+    unsigned long long n_edges;           // adjacency bits set
+    unsigned long long n_good21;          // distinct 21-mers with count >= threshold
+    unsigned long long n_export;          // scratch counter for export kernels
+    unsigned int err_table_full;
+    unsigned int err_ovf_full;
+    unsigned int n_overflow;              // entries in the overflow table
+    unsigned int pad;
+};
+
+struct FastMod {  // x % d for a run-time invariant d (filter_size), reference bloomfilter.cpp:65
+    uint64_t d, M;
+};
+__host__ __device__ inline FastMod make_fastmod(uint64_t d) {
+    FastMod f; f.d = d; f.M = d ? (~0ULL / d) : 0; return f;
+}
+__device__ __forceinline__ uint64_t fastmod(uint64_t x, const FastMod &f) {
+    uint64_t q = __umul64hi(x, f.M);     // q <= x/d, off by at most 2
+    uint64_t r = x - q * f.d;
+    while (r >= f.d) r -= f.d;
+    return r;
+}
+
+// ---- hashing --------------------------------------------------------------------------------
+// reference src/MyHash.cpp:12-19
+__device__ __forceinline__ uint64_t fmix64(uint64_t k) {
+    k ^= k >> 33; k *= 0xff51afd7ed558ccdULL; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL; k ^= k >> 33;
+    return k;
+}
+__device__ __forceinline__ uint64_t shift_mix(uint64_t v) { return v ^ (v >> 47); }
+// std::hash<std::bitset<2k>> for 2k <= 64: libstdc++ _Hash_bytes over ceil(2k/8) bytes with seed
+// 0xc70f6907 (what reference src/MyHash.cpp:25 calls). One 8-byte block when nbytes == 8, else
+// only the tail step (the tail bytes ARE the little-endian value of the k-mer).
+__device__ __forceinline__ uint64_t std_hash_kmer1(uint64_t w, int nbytes) {
+    const uint64_t mul = 0xc6a4a7935bd1e995ULL;
+    uint64_t hash = 0xc70f6907ULL ^ ((uint64_t)nbytes * mul);
+    if (nbytes == 8) {
+        uint64_t data = shift_mix(w * mul) * mul;
+        hash ^= data; hash *= mul;
+    } else {
+        hash ^= w; hash *= mul;
+    }
+    hash = shift_mix(hash) * mul;
+    hash = shift_mix(hash);
+    return hash;
+}
+__device__ __forceinline__ uint64_t rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
+// reference src/MyHash.cpp:22-35
+__device__ __forceinline__ void double_hash(uint64_t h0, uint64_t &h1, uint64_t &h2) {
+    const uint64_t c1 = 0x87c37b91114253d5ULL, c2 = 0x4cf5ad432745937fULL;
+    h1 = h0; h2 = h1 ^ c2;
+    h2 = rotl64(h2, 31); h1 ^= c1; h1 = rotl64(h1, 33);
+    h1 += h2; h2 += h1; h1 ^= c2; h2 ^= c1;
+    h1 = fmix64(h1); h2 = fmix64(h2);
+    h1 += h2; h2 += h1;
+}
+
+// ---- 2-bit k-mers ----------------------------------------------------------------------------
+// reverse the order of the 32 two-bit groups of v
+__device__ __forceinline__ uint64_t rev2(uint64_t v) {
+    v = __brevll(v);
+    return ((v >> 1) & 0x5555555555555555ULL) | ((v & 0x5555555555555555ULL) << 1);
+}
+// duplicate every bit of m: bit i -> bits 2i, 2i+1
+__device__ __forceinline__ uint64_t spread32(uint32_t m) {
+    uint64_t s = m;
+    s = (s | (s << 16)) & 0x0000FFFF0000FFFFULL;
+    s = (s | (s << 8)) & 0x00FF00FF00FF00FFULL;
+    s = (s | (s << 4)) & 0x0F0F0F0F0F0F0F0FULL;
+    s = (s | (s << 2)) & 0x3333333333333333ULL;
+    s = (s | (s << 1)) & 0x5555555555555555ULL;
+    return s | (s << 1);
+}
+// 64-bit window starting `o` bases into hi (hand-off of the neighbouring packed word)
+__device__ __forceinline__ uint64_t window(uint64_t hi, uint64_t lo, int o) {
+    return o ? ((hi << (2 * o)) | (lo >> (64 - 2 * o))) : hi;
+}
+__device__ __forceinline__ uint64_t kmask(int k) { return k >= 32 ? ~0ULL : ((1ULL << (2 * k)) - 1); }
+// canonical k-mer (CompareBit(Fw,Bw), reference src/BitCalc.cpp:48-54) from a left-aligned
+// window x; m2 = spread non-ACGT plane of the same window (0 when the reads are clean): those
+// bases read as code 0 on the reverse strand too (reference src/common.h:32-33 quirk).
+__device__ __forceinline__ uint64_t canonical_from_window(uint64_t x, uint64_t m2, int k) {
+    uint64_t f = x >> (64 - 2 * k);
+    uint64_t r = rev2(~x & ~m2) & kmask(k);
+    return f <= r ? f : r;
+}
+// GetComplementKmer (reference src/BitCalc.cpp:36-45) on a right-aligned k-mer
+__device__ __forceinline__ uint64_t revcomp(uint64_t v, int k) { return rev2(~v) >> (64 - 2 * k); }
+
+// ---- 32-byte bucket load ----------------------------------------------------------------------
+__device__ __forceinline__ void ld_bucket(const uint64_t *p, uint64_t s[4]) {
+    asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];"
+                 : "=l"(s[0]), "=l"(s[1]), "=l"(s[2]), "=l"(s[3]) : "l"(p));
+}
+__device__ __forceinline__ unsigned long long *ull(uint64_t *p) { return reinterpret_cast<unsigned long long *>(p); }
+
+// ---- overflow side table (counts that do not fit 22 bits) --------------------------------------
+struct Ovf {
+    uint64_t *keys;                  // kOvfCap, kEmpty when free
+    unsigned long long *wraps;       // number of 2^22 wrap-arounds
+};
+__device__ inline void ovf_add(const Ovf &o, uint64_t key, Stats *st) {
+    unsigned h = (unsigned)(fmix64(key) % kOvfCap);
+    for (int i = 0; i < kOvfCap; i++) {
+        unsigned s = (h + i) % kOvfCap;
+        uint64_t cur = o.keys[s];
+        if (cur == kEmpty) {
+            cur = atomicCAS(ull(o.keys + s), kEmpty, key);
+            if (cur == kEmpty) { atomicAdd(&st->n_overflow, 1u); cur = key; }
+        }
+        if (cur == key) { atomicAdd(o.wraps + s, 1ULL); return; }
+    }
+    atomicExch(&st->err_ovf_full, 1u);
+}
+__device__ inline uint64_t ovf_get(const Ovf &o, uint64_t key) {
+    unsigned h = (unsigned)(fmix64(key) % kOvfCap);
+    for (int i = 0; i < kOvfCap; i++) {
+        unsigned s = (h + i) % kOvfCap;
+        uint64_t cur = o.keys[s];
+        if (cur == key) return o.wraps[s];
+        if (cur == kEmpty) return 0;
+    }
+    return 0;
+}
+
+// ---- count table: [count:22 | key:42] slots, 4 per 32-byte bucket, linear bucket probing ------
+// (the "MyHash" count table of BASELINE.json's north_star; replaces the reference's
+//  std::unordered_map<std::bitset<42>,uint64_t> KmerCount, src/common.h:26)
+__device__ __forceinline__ void count_bump(uint64_t *slot, uint64_t seen, uint64_t key, const Ovf &ovf, Stats *st) {
+    if ((seen >> 42) < 0x200000ULL) {
+        atomicAdd(ull(slot), kCntOne);  // RED: fewer than 2^21 adds can be in flight, cannot wrap
+    } else {
+        uint64_t old = atomicAdd(ull(slot), kCntOne);
+        if ((old >> 42) == kCntFieldMax) ovf_add(ovf, key, st);  // field wrapped to 0
+    }
+}
+// Returns the count the key is KNOWN to have reached after this insert (a lower bound on the
+// final count, because counts only grow): 1 when this call created the key, seen+1 otherwise.
+// count21 uses it to prove "count >= 2" for every position but the first occurrence of a key,
+// so the coverage pass only revisits those. *created tells the caller to bump n_distinct.
+__device__ __forceinline__ uint64_t count_insert(uint64_t *table, uint64_t nb, uint64_t key, const Ovf &ovf, Stats *st, bool *created) {
+    uint64_t b = __umul64hi(fmix64(key), nb);
+    *created = false;
+    for (uint64_t probe = 0; probe < nb; probe++) {
+        uint64_t *bp = table + 4 * b;
+        uint64_t s[4];
+        ld_bucket(bp, s);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            uint64_t v = s[i];
+            if ((v & kKey42) == key) { count_bump(bp + i, v, key, ovf, st); return (v >> 42) + 1; }
+            if (v == kEmpty) {
+                uint64_t old = atomicCAS(ull(bp + i), kEmpty, key | kCntOne);
+                if (old == kEmpty) { *created = true; return 1; }
+                if ((old & kKey42) == key) { count_bump(bp + i, old, key, ovf, st); return (old >> 42) + 1; }
+            }
+        }
+        b = (b + 1 == nb) ? 0 : b + 1;
+    }
+    atomicExch(&st->err_table_full, 1u);
+    return 0;
+}
+// KC[key] (0 when absent)
+__device__ __forceinline__ uint64_t count_lookup(const uint64_t *table, uint64_t nb, uint64_t key, const Ovf &ovf, unsigned n_overflow) {
+    uint64_t b = __umul64hi(fmix64(key), nb);
+    for (uint64_t probe = 0; probe < nb; probe++) {
+        uint64_t s[4];
+        ld_bucket(table + 4 * b, s);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            uint64_t v = s[i];
+            if ((v & kKey42) == key) {
+                uint64_t c = v >> 42;
+                if (n_overflow) c += ovf_get(ovf, key) << 22;
+                return c;
+            }
+            if (v == kEmpty) return 0;
+        }
+        b = (b + 1 == nb) ? 0 : b + 1;
+    }
+    return 0;
+}
+
+// ---- solid k-mer set: 64-bit keys, 4 per bucket --------------------------------------------------
+// returns 1 = inserted now, 0 = already present, -1 = table full
+__device__ __forceinline__ int set_insert(uint64_t *table, uint64_t nb, uint64_t key) {
+    uint64_t b = __umul64hi(fmix64(key), nb);
+    for (uint64_t probe = 0; probe < nb; probe++) {
+        uint64_t *bp = table + 4 * b;
+        uint64_t s[4];
+        ld_bucket(bp, s);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            uint64_t v = s[i];
+            if (v == key) return 0;
+            if (v == kEmpty) {
+                uint64_t old = atomicCAS(ull(bp + i), kEmpty, key);
+                if (old == kEmpty) return 1;
+                if (old == key) return 0;
+            }
+        }
+        b = (b + 1 == nb) ? 0 : b + 1;
+    }
+    return -1;
+}
+
+// ---- Bloom filter, reference src/bloomfilter.cpp ---------------------------------------------------
+struct Bloom {
+    uint32_t *bits;   // bit i = word i>>5 bit i&31 (== byte i>>3 bit i&7 of std::vector<bool> order)
+    FastMod fm;       // filter_size
+    int nh;           // num_hashes
+    int nbytes;       // ceil(2k/8)
+};
+// BF::add, reference src/bloomfilter.cpp:69-74
+__device__ __forceinline__ void bloom_add(const Bloom &bf, uint64_t canon) {
+    uint64_t h1, h2;
+    double_hash(std_hash_kmer1(canon, bf.nbytes), h1, h2);
+    uint64_t x = h1;
+    for (int n = 0; n < bf.nh; n++, x += h2) {
+        uint64_t bit = fastmod(x, bf.fm);
+        uint32_t m = 1u << (bit & 31);
+        uint32_t *wp = bf.bits + (bit >> 5);
+        if (!(__ldcg(wp) & m)) atomicOr(wp, m);   // bits only ever go 0->1, a stale 1 is still a 1
+    }
+}
+// BF::possiblyContains, reference src/bloomfilter.cpp:77-86
+__device__ __forceinline__ bool bloom_query(const Bloom &bf, uint64_t canon) {
+    uint64_t h1, h2;
+    double_hash(std_hash_kmer1(canon, bf.nbytes), h1, h2);
+    uint64_t x = h1;
+    for (int n = 0; n < bf.nh; n++, x += h2) {
+        uint64_t bit = fastmod(x, bf.fm);
+        if (!((__ldg(bf.bits + (bit >> 5)) >> (bit & 31)) & 1u)) return false;
+    }
+    return true;
+}
+// IsRecorded, reference src/DeBruijnGraph.cpp:318-323 (oriented k-mer in, canonicalised here)
+__device__ __forceinline__ bool is_recorded(const Bloom &bf, uint64_t kmer, int k) {
+    uint64_t rc = revcomp(kmer, k);
+    return bloom_query(bf, kmer <= rc ? kmer : rc);
+}
+// neighbour d of an oriented k-mer, reference src/DeBruijnGraph.cpp:327-339
+__device__ __forceinline__ uint64_t neighbour(uint64_t kmer, int d, int k) {
+    return d < 4 ? ((kmer >> 2) | ((uint64_t)d << (2 * k - 2))) : (((kmer << 2) | (uint64_t)(d - 4)) & kmask(k));
+}
+
+__device__ __forceinline__ unsigned long long warp_sum(unsigned v) {
+    return __reduce_add_sync(0xffffffffu, v);
+}
+
+}  // namespace p3

@@ -1,0 +1,820 @@
+// p3_gpu.cu — kernels and the C ABI (include/platanus3_b200.h) of the B200-native
+// k-mer-to-graph hot path: CountShortKmer -> MakeBF -> CheckDirections.
+//
+// Thread mapping for the three streaming kernels: one thread per packed word (32 consecutive
+// k-mer start positions). A warp reads 32 consecutive words (256 B, coalesced) plus the next
+// word as hand-off, so every k-mer is two registers and a funnel shift away; there is no
+// rolling state to carry along a read and no divergence on read boundaries (a read-end bit
+// plane turns "k-mer crosses a read end" into one AND per position).
+#include "../../include/platanus3_b200.h"
+#include "p3_device.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace p3;
+
+// ------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------
+
+// read-end plane: bit (31 - j%32) of rend[j/32] set iff stream position j is the last base of a
+// read or lies in the zero padding. "k-mer at p is inside one read" == no end bit in [p, p+k-2].
+__global__ void rend_kernel(const uint64_t *__restrict__ off, uint64_t n_reads, uint64_t total_bases,
+                            uint64_t n_bits, uint32_t *__restrict__ rend) {
+    uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    uint64_t stride = gridDim.x * (uint64_t)blockDim.x;
+    for (uint64_t r = t; r < n_reads; r += stride) {
+        uint64_t e = off[r + 1];
+        if (e == 0) continue;
+        uint64_t p = e - 1;
+        atomicOr(rend + (p >> 5), 0x80000000u >> (p & 31));
+    }
+    for (uint64_t p = total_bases + t; p < n_bits; p += stride) atomicOr(rend + (p >> 5), 0x80000000u >> (p & 31));
+}
+
+template <bool HAS_MASK>
+__global__ void __launch_bounds__(256)
+count21_kernel(const uint64_t *__restrict__ packed, const uint32_t *__restrict__ rend,
+               const uint32_t *__restrict__ nmask, uint64_t n_words, uint64_t *table, uint64_t nb,
+               Ovf ovf, Stats *st, uint32_t *__restrict__ proven2) {
+    const uint64_t W21 = ~0ULL << (64 - (kShortK - 1));  // positions p .. p+19
+    unsigned n_pos = 0, n_new = 0;
+    uint64_t stride = gridDim.x * (uint64_t)blockDim.x;
+    for (uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < n_words; w += stride) {
+        uint64_t hi = __ldg(packed + w), lo = __ldg(packed + w + 1);
+        uint64_t E = ((uint64_t)__ldg(rend + w) << 32) | __ldg(rend + w + 1);
+        uint64_t mhi = 0, mlo = 0;
+        if (HAS_MASK) { mhi = spread32(__ldg(nmask + w)); mlo = spread32(__ldg(nmask + w + 1)); }
+        uint32_t g = 0;
+#pragma unroll 4
+        for (int o = 0; o < 32; o++) {
+            if (((E << o) & W21) != 0) continue;
+            uint64_t x = window(hi, lo, o);
+            uint64_t m2 = HAS_MASK ? window(mhi, mlo, o) : 0;
+            uint64_t key = canonical_from_window(x, m2, kShortK);
+            bool created;
+            uint64_t reached = count_insert(table, nb, key, ovf, st, &created);
+            n_pos++;
+            n_new += created ? 1u : 0u;
+            if (reached >= 2) g |= 0x80000000u >> o;
+        }
+        proven2[w] = g;  // bit set: this 21-mer's final count is certainly >= 2
+    }
+    unsigned long long a = warp_sum(n_pos), b = warp_sum(n_new);
+    if ((threadIdx.x & 31) == 0) {
+        if (a) atomicAdd(&st->n_pos21, a);
+        if (b) atomicAdd(&st->n_distinct21, b);
+    }
+}
+
+// shortk_cov >= threshold per position (reference src/MakeBloomFilter.cpp:52-58), one bit each
+template <bool HAS_MASK>
+__global__ void __launch_bounds__(256)
+flags21_kernel(const uint64_t *__restrict__ packed, const uint32_t *__restrict__ rend,
+               const uint32_t *__restrict__ nmask, uint64_t n_words, const uint64_t *__restrict__ table,
+               uint64_t nb, Ovf ovf, const Stats *st, uint64_t thr, const uint32_t *__restrict__ proven2,
+               uint32_t *__restrict__ good21) {
+    const uint64_t W21 = ~0ULL << (64 - (kShortK - 1));
+    const unsigned n_overflow = st->n_overflow;
+    uint64_t stride = gridDim.x * (uint64_t)blockDim.x;
+    for (uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < n_words; w += stride) {
+        uint64_t hi = __ldg(packed + w), lo = __ldg(packed + w + 1);
+        uint64_t E = ((uint64_t)__ldg(rend + w) << 32) | __ldg(rend + w + 1);
+        uint64_t mhi = 0, mlo = 0;
+        if (HAS_MASK) { mhi = spread32(__ldg(nmask + w)); mlo = spread32(__ldg(nmask + w + 1)); }
+        uint32_t valid = 0;
+#pragma unroll
+        for (int o = 0; o < 32; o++) valid |= (((E << o) & W21) == 0) ? (0x80000000u >> o) : 0u;
+        // positions count21 already proved (count >= 2) need no second table access
+        uint32_t g = proven2 ? (__ldg(proven2 + w) & valid) : 0u;
+        uint32_t need = valid & ~g;
+        while (need) {
+            int o = __clz(need);
+            need &= ~(0x80000000u >> o);
+            uint64_t x = window(hi, lo, o);
+            uint64_t m2 = HAS_MASK ? window(mhi, mlo, o) : 0;
+            uint64_t key = canonical_from_window(x, m2, kShortK);
+            if (count_lookup(table, nb, key, ovf, n_overflow) >= thr) g |= 0x80000000u >> o;
+        }
+        good21[w] = g;
+    }
+}
+
+// RMQ window minimum >= threshold  <=>  every 21-mer flag in the window is set
+// (reference src/MakeBloomFilter.cpp:62,75). Window length x = k-20 <= 12 for k <= 32.
+__device__ __forceinline__ uint32_t solid_bits(uint32_t g0, uint32_t g1, int x) {
+    uint64_t a = ((uint64_t)g0 << 32) | g1;
+    int w = 1;
+    while (2 * w <= x) { a &= a << w; w *= 2; }
+    a &= a << (x - w);
+    return (uint32_t)(a >> 32);
+}
+
+// pass 1: solid-position bit plane + number of BF.add calls
+__global__ void __launch_bounds__(256)
+solid_kernel(const uint32_t *__restrict__ good21, uint64_t n_words, int k, uint32_t *__restrict__ solid, Stats *st) {
+    unsigned n = 0;
+    uint64_t stride = gridDim.x * (uint64_t)blockDim.x;
+    for (uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < n_words; w += stride) {
+        uint32_t s = solid_bits(__ldg(good21 + w), __ldg(good21 + w + 1), k - kShortK + 1);
+        solid[w] = s;
+        n += __popc(s);
+    }
+    unsigned long long a = warp_sum(n);
+    if ((threadIdx.x & 31) == 0 && a) atomicAdd(&st->n_adds, a);
+}
+
+// pass 2: BF.add for every solid position (reference src/MakeBloomFilter.cpp:75-77). Positions of
+// the same canonical k-mer set identical bits, so each distinct k-mer is added once: the solid
+// set de-duplicates and its insertion winner does the num_hashes atomicOr's.
+template <bool HAS_MASK>
+__global__ void __launch_bounds__(256)
+makebf_kernel(const uint64_t *__restrict__ packed, const uint32_t *__restrict__ nmask,
+              const uint32_t *__restrict__ solid, uint64_t n_words, int k, uint64_t *set, uint64_t nbs,
+              uint64_t *__restrict__ list, uint64_t list_cap, Bloom bf, Stats *st) {
+    uint64_t stride = gridDim.x * (uint64_t)blockDim.x;
+    for (uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < n_words; w += stride) {
+        uint32_t s = __ldg(solid + w);
+        if (!s) continue;
+        uint64_t hi = __ldg(packed + w), lo = __ldg(packed + w + 1);
+        uint64_t mhi = 0, mlo = 0;
+        if (HAS_MASK) { mhi = spread32(__ldg(nmask + w)); mlo = spread32(__ldg(nmask + w + 1)); }
+        while (s) {
+            int o = __clz(s);
+            s &= ~(0x80000000u >> o);
+            uint64_t x = window(hi, lo, o);
+            uint64_t m2 = HAS_MASK ? window(mhi, mlo, o) : 0;
+            uint64_t c = canonical_from_window(x, m2, k);
+            int r = set_insert(set, nbs, c);
+            if (r > 0) {
+                unsigned long long idx = atomicAdd(&st->n_distinct_solid, 1ULL);
+                if (idx < list_cap) list[idx] = c;
+                bloom_add(bf, c);
+            } else if (r < 0) {
+                atomicExch(&st->err_table_full, 1u);
+            }
+        }
+    }
+}
+
+// first solid k-mer of each read (reference src/MakeBloomFilter.cpp:79-83)
+__global__ void seeds_kernel(const uint64_t *__restrict__ off, uint64_t n_reads, const uint32_t *__restrict__ solid,
+                             int k, int64_t *__restrict__ seed_pos) {
+    uint64_t stride = gridDim.x * (uint64_t)blockDim.x;
+    for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < n_reads; r += stride) {
+        uint64_t s = off[r], e = off[r + 1];
+        int64_t found = -1;
+        if (e - s >= (uint64_t)k) {
+            uint64_t last = e - k;
+            for (uint64_t w = s >> 5; w <= (last >> 5); w++) {
+                uint32_t v = __ldg(solid + w);
+                if (w == (s >> 5)) v &= 0xFFFFFFFFu >> (s & 31);
+                if (v) {
+                    uint64_t p = (w << 5) + __clz(v);
+                    if (p <= last) found = (int64_t)(p - s);
+                    break;
+                }
+            }
+        }
+        seed_pos[r] = found;
+    }
+}
+
+// CheckDirections (reference src/DeBruijnGraph.cpp:326-345): 8 lanes per k-mer, one direction each
+__global__ void __launch_bounds__(256)
+adjacency_kernel(const uint64_t *__restrict__ kmers, uint64_t n, int k, Bloom bf, uint8_t *__restrict__ adj, Stats *st) {
+    const int lane = threadIdx.x & 31;
+    const int d = lane & 7, g = lane >> 3;
+    uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+    uint64_t n_warps = (gridDim.x * (uint64_t)blockDim.x) >> 5;
+    unsigned edges = 0;
+    for (uint64_t base = warp * 4; base < n; base += n_warps * 4) {
+        uint64_t i = base + g;
+        bool rec = false;
+        if (i < n) rec = is_recorded(bf, neighbour(__ldg(kmers + i), d, k), k);
+        unsigned m = __ballot_sync(0xffffffffu, rec);
+        if (d == 0 && i < n) {
+            unsigned byte = (m >> (8 * g)) & 0xFFu;
+            adj[i] = (uint8_t)byte;
+            edges += __popc(byte);
+        }
+    }
+    unsigned long long e = warp_sum(edges);
+    if (lane == 0 && e && st) atomicAdd(&st->n_edges, e);
+}
+
+// ---- small batch / export kernels -------------------------------------------------------------------
+__global__ void export_counts_kernel(const uint64_t *__restrict__ table, uint64_t n_slots, Ovf ovf, Stats *st,
+                                     uint64_t thr, uint64_t *keys, uint64_t *counts, uint64_t cap) {
+    uint64_t stride = gridDim.x * (uint64_t)blockDim.x;
+    const unsigned n_overflow = st->n_overflow;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_slots; i += stride) {
+        uint64_t v = table[i];
+        if (v == kEmpty) continue;
+        uint64_t key = v & kKey42, c = v >> 42;
+        if (n_overflow) c += ovf_get(ovf, key) << 22;
+        if (keys) {
+            unsigned long long idx = atomicAdd(&st->n_export, 1ULL);
+            if (idx < cap) { keys[idx] = key; counts[idx] = c; }
+        } else if (c >= thr) {
+            atomicAdd(&st->n_good21, 1ULL);
+        }
+    }
+}
+__global__ void lookup_counts_kernel(const uint64_t *__restrict__ table, uint64_t nb, Ovf ovf, const Stats *st,
+                                     const uint64_t *__restrict__ keys, uint64_t n, uint64_t *counts) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i < n) counts[i] = count_lookup(table, nb, keys[i], ovf, st->n_overflow);
+}
+__global__ void bf_add_kernel(Bloom bf, const uint64_t *__restrict__ kmers, uint64_t n) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i < n) bloom_add(bf, kmers[i]);
+}
+__global__ void bf_query_kernel(Bloom bf, const uint64_t *__restrict__ kmers, uint64_t n, uint8_t *out) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = bloom_query(bf, kmers[i]) ? 1 : 0;
+}
+__global__ void double_hash_kernel(int nbytes, const uint64_t *__restrict__ kmers, uint64_t n, uint64_t *out) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i < n) {
+        uint64_t h1, h2;
+        double_hash(std_hash_kmer1(kmers[i], nbytes), h1, h2);
+        out[2 * i] = h1; out[2 * i + 1] = h2;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side: context + C ABI
+// ------------------------------------------------------------------------------------------------
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) { g_err = msg; return code; }
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(P3_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));          \
+    } while (0)
+
+struct p3_ctx {
+    int device = 0;
+    int n_sm = 148;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    uint64_t launches = 0;
+    // reads
+    const uint64_t *d_packed = nullptr; const uint64_t *d_off = nullptr; const uint32_t *d_nmask = nullptr;
+    uint64_t *own_packed = nullptr; uint64_t *own_off = nullptr; uint32_t *own_nmask = nullptr;
+    uint64_t cap_packed = 0, cap_off = 0, cap_nmask = 0, cap_rend = 0, cap_planes = 0, cap_seed = 0;  // bytes
+    uint64_t total_bases = 0, n_reads = 0, n_words = 0;
+    uint32_t *d_rend = nullptr;
+    bool have_reads = false;
+    // count table
+    uint64_t *d_table = nullptr; uint64_t nb = 0;
+    uint64_t *d_ovf_keys = nullptr; unsigned long long *d_ovf_wraps = nullptr;
+    bool have_counts = false;
+    // make_bf
+    uint32_t *d_good21 = nullptr, *d_solid = nullptr;
+    uint32_t *d_proven2 = nullptr; uint64_t cap_proven = 0;
+    uint64_t *d_set = nullptr; uint64_t nbs = 0;
+    uint64_t *d_list = nullptr; uint64_t list_cap = 0;
+    uint32_t *d_bloom = nullptr; uint64_t bloom_words = 0;
+    int64_t *d_seed = nullptr;
+    uint64_t filter_size = 0; uint32_t num_hashes = 0; uint32_t k = 0;
+    bool have_bf = false, have_solid = false;
+    // adjacency
+    uint8_t *d_adj = nullptr; uint64_t adj_cap = 0; bool have_adj = false;
+    Stats *d_stats = nullptr; Stats h_stats;
+    cudaEvent_t ev[10];
+    float ms[5] = {0, 0, 0, 0, 0};
+    Ovf ovf() const { Ovf o; o.keys = d_ovf_keys; o.wraps = d_ovf_wraps; return o; }
+    Bloom bloom() const {
+        Bloom b; b.bits = d_bloom; b.fm = make_fastmod(filter_size); b.nh = (int)num_hashes; b.nbytes = (int)((2 * k + 7) / 8);
+        return b;
+    }
+    int grid(int blocks_per_sm = 8) const { return n_sm * blocks_per_sm; }
+};
+
+template <typename T> static void dfree(T *&p) { if (p) { cudaFree((void *)p); p = nullptr; } }
+// grow-only device buffer: reallocates only when the request exceeds the capacity, so repeated
+// runs on same-sized inputs never touch cudaMalloc/cudaFree (both synchronise the device)
+template <typename T> static cudaError_t ensure(T *&p, uint64_t &cap_bytes, uint64_t need_bytes) {
+    if (p && cap_bytes >= need_bytes) return cudaSuccess;
+    dfree(p); cap_bytes = 0;
+    cudaError_t e = cudaMalloc((void **)&p, need_bytes ? need_bytes : 1);
+    if (e == cudaSuccess) cap_bytes = need_bytes;
+    return e;
+}
+
+static int pull_stats(p3_ctx *c) {
+    CU(cudaMemcpyAsync(&c->h_stats, c->d_stats, sizeof(Stats), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return P3_OK;
+}
+
+extern "C" {
+
+const char *p3_last_error(void) { return g_err.c_str(); }
+int p3_version(void) { return 100; }
+int p3_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+void *p3_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void p3_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+p3_ctx *p3_create(int device, void *stream) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        fail(P3_ERR_CUDA, "p3_create: no CUDA device (this library has no CPU fallback)");
+        return nullptr;
+    }
+    if (device < 0 || device >= n) { fail(P3_ERR_ARG, "p3_create: bad device index"); return nullptr; }
+    if (cudaSetDevice(device) != cudaSuccess) { fail(P3_ERR_CUDA, "cudaSetDevice failed"); return nullptr; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { fail(P3_ERR_CUDA, "cudaGetDeviceProperties failed"); return nullptr; }
+    if (prop.major < 10) { fail(P3_ERR_CUDA, "p3_create: device is not sm_100 (B200) class"); return nullptr; }
+    if (const char *g = getenv("P3_L2_FETCH_GRANULARITY")) {  // experiment knob: 32/64/128-byte L2 miss fetch
+        cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g));
+        cudaGetLastError();
+    }
+    p3_ctx *c = new p3_ctx();
+    c->device = device;
+    c->n_sm = prop.multiProcessorCount;
+    if (stream) { c->stream = (cudaStream_t)stream; }
+    else {
+        if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; fail(P3_ERR_CUDA, "cudaStreamCreate failed"); return nullptr; }
+        c->own_stream = true;
+    }
+    for (auto &e : c->ev) cudaEventCreate(&e);
+    if (cudaMalloc(&c->d_stats, sizeof(Stats)) != cudaSuccess ||
+        cudaMalloc(&c->d_ovf_keys, sizeof(uint64_t) * kOvfCap) != cudaSuccess ||
+        cudaMalloc(&c->d_ovf_wraps, sizeof(unsigned long long) * kOvfCap) != cudaSuccess) {
+        fail(P3_ERR_NOMEM, "p3_create: cudaMalloc failed"); delete c; return nullptr;
+    }
+    cudaMemsetAsync(c->d_stats, 0, sizeof(Stats), c->stream);
+    memset(&c->h_stats, 0, sizeof(Stats));
+    return c;
+}
+
+static void free_reads(p3_ctx *c) {
+    dfree(c->own_packed); dfree(c->own_off); dfree(c->own_nmask); dfree(c->d_rend);
+    c->cap_packed = c->cap_off = c->cap_nmask = c->cap_rend = 0;
+    c->d_packed = nullptr; c->d_off = nullptr; c->d_nmask = nullptr; c->have_reads = false;
+}
+static void free_bf(p3_ctx *c) {
+    dfree(c->d_good21); dfree(c->d_solid); dfree(c->d_set); dfree(c->d_list); dfree(c->d_bloom);
+    dfree(c->d_seed); dfree(c->d_adj); c->adj_cap = 0; c->cap_planes = c->cap_seed = 0;
+    c->nbs = 0; c->bloom_words = 0;
+    c->have_bf = c->have_solid = c->have_adj = false;
+}
+
+void p3_destroy(p3_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    free_reads(c); free_bf(c);
+    dfree(c->d_table); dfree(c->d_proven2); dfree(c->d_ovf_keys); dfree(c->d_ovf_wraps); dfree(c->d_stats);
+    for (auto &e : c->ev) cudaEventDestroy(e);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int p3_synchronize(p3_ctx *c) {
+    if (!c) return fail(P3_ERR_ARG, "null ctx");
+    CU(cudaStreamSynchronize(c->stream));
+    return P3_OK;
+}
+
+static int finish_reads(p3_ctx *c) {
+    // read-end plane, built on the device from the offsets
+    uint64_t plane_words = c->n_words + 1;
+    CU(ensure(c->d_rend, c->cap_rend, sizeof(uint32_t) * plane_words));
+    CU(cudaMemsetAsync(c->d_rend, 0, sizeof(uint32_t) * plane_words, c->stream));
+    rend_kernel<<<c->grid(4), 256, 0, c->stream>>>(c->d_off, c->n_reads, c->total_bases, plane_words * 32, c->d_rend);
+    c->launches++;
+    CU(cudaGetLastError());
+    c->have_reads = true; c->have_counts = false;
+    c->have_bf = c->have_solid = c->have_adj = false;
+    return P3_OK;
+}
+
+int p3_reads_upload(p3_ctx *c, const uint64_t *h_packed, uint64_t total_bases, const uint64_t *h_off,
+                    uint64_t n_reads, const uint32_t *h_nmask) {
+    if (!c || !h_packed || !h_off) return fail(P3_ERR_ARG, "p3_reads_upload: null argument");
+    CU(cudaSetDevice(c->device));
+    c->have_reads = false;
+    c->total_bases = total_bases; c->n_reads = n_reads; c->n_words = (total_bases + 31) / 32;
+    uint64_t pw = c->n_words + 1;
+    CU(ensure(c->own_packed, c->cap_packed, sizeof(uint64_t) * pw));
+    CU(ensure(c->own_off, c->cap_off, sizeof(uint64_t) * (n_reads + 1)));
+    CU(cudaMemcpyAsync(c->own_packed, h_packed, sizeof(uint64_t) * pw, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->own_off, h_off, sizeof(uint64_t) * (n_reads + 1), cudaMemcpyHostToDevice, c->stream));
+    if (h_nmask) {
+        CU(ensure(c->own_nmask, c->cap_nmask, sizeof(uint32_t) * pw));
+        CU(cudaMemcpyAsync(c->own_nmask, h_nmask, sizeof(uint32_t) * pw, cudaMemcpyHostToDevice, c->stream));
+    }
+    c->d_packed = c->own_packed; c->d_off = c->own_off; c->d_nmask = h_nmask ? c->own_nmask : nullptr;
+    return finish_reads(c);
+}
+
+int p3_reads_attach(p3_ctx *c, const uint64_t *d_packed, uint64_t total_bases, const uint64_t *d_off,
+                    uint64_t n_reads, const uint32_t *d_nmask) {
+    if (!c || !d_packed || !d_off) return fail(P3_ERR_ARG, "p3_reads_attach: null argument");
+    CU(cudaSetDevice(c->device));
+    c->have_reads = false;
+    c->total_bases = total_bases; c->n_reads = n_reads; c->n_words = (total_bases + 31) / 32;
+    c->d_packed = d_packed; c->d_off = d_off; c->d_nmask = d_nmask;
+    return finish_reads(c);
+}
+
+// ---- stage A -----------------------------------------------------------------------------------
+int p3_count_short_kmers(p3_ctx *c, uint64_t table_slots) {
+    if (!c) return fail(P3_ERR_ARG, "null ctx");
+    if (!c->have_reads) return fail(P3_ERR_STATE, "p3_count_short_kmers: no reads attached");
+    CU(cudaSetDevice(c->device));
+    uint64_t upper = c->total_bases > (kShortK - 1) * c->n_reads ? c->total_bases - (kShortK - 1) * c->n_reads : 0;
+    if (table_slots == 0) {
+        table_slots = std::max<uint64_t>(2 * upper, 1024);
+        size_t fr = 0, tot = 0;
+        CU(cudaMemGetInfo(&fr, &tot));
+        uint64_t lim = (uint64_t)(0.6 * (double)(fr + (c->d_table ? c->nb * 32 : 0))) / 8;
+        if (table_slots > lim) table_slots = lim;
+    }
+    uint64_t nb = (table_slots + 3) / 4;
+    if (nb == 0) nb = 1;
+    if (!c->d_table || c->nb != nb) {
+        dfree(c->d_table);
+        if (cudaMalloc(&c->d_table, nb * 32) != cudaSuccess) { cudaGetLastError(); return fail(P3_ERR_NOMEM, "count table allocation failed"); }
+        c->nb = nb;
+    }
+    CU(cudaMemsetAsync(c->d_table, 0xFF, nb * 32, c->stream));
+    CU(cudaMemsetAsync(c->d_ovf_keys, 0xFF, sizeof(uint64_t) * kOvfCap, c->stream));
+    CU(cudaMemsetAsync(c->d_ovf_wraps, 0, sizeof(unsigned long long) * kOvfCap, c->stream));
+    CU(cudaMemsetAsync(c->d_stats, 0, sizeof(Stats), c->stream));
+    CU(ensure(c->d_proven2, c->cap_proven, sizeof(uint32_t) * (c->n_words + 1)));
+    CU(cudaEventRecord(c->ev[0], c->stream));
+    if (c->d_nmask)
+        count21_kernel<true><<<c->grid(), 256, 0, c->stream>>>(c->d_packed, c->d_rend, c->d_nmask, c->n_words, c->d_table, nb, c->ovf(), c->d_stats, c->d_proven2);
+    else
+        count21_kernel<false><<<c->grid(), 256, 0, c->stream>>>(c->d_packed, c->d_rend, nullptr, c->n_words, c->d_table, nb, c->ovf(), c->d_stats, c->d_proven2);
+    c->launches++;
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(c->ev[1], c->stream));
+    int rc = pull_stats(c);
+    if (rc) return rc;
+    CU(cudaEventElapsedTime(&c->ms[0], c->ev[0], c->ev[1]));
+    if (c->h_stats.err_table_full) return fail(P3_ERR_TABLE_FULL, "21-mer count table full: raise table_slots");
+    if (c->h_stats.err_ovf_full) return fail(P3_ERR_TABLE_FULL, "count overflow side table full");
+    c->have_counts = true;
+    c->have_bf = c->have_solid = c->have_adj = false;  // buffers are kept for reuse
+    return P3_OK;
+}
+
+int p3_short_kmer_stats(p3_ctx *c, uint64_t *n_positions, uint64_t *n_distinct) {
+    if (!c || !c->have_counts) return fail(P3_ERR_STATE, "no counts");
+    if (n_positions) *n_positions = c->h_stats.n_pos21;
+    if (n_distinct) *n_distinct = c->h_stats.n_distinct21;
+    return P3_OK;
+}
+
+int p3_short_kmer_export(p3_ctx *c, uint64_t *h_keys, uint64_t *h_counts, uint64_t cap, uint64_t *n) {
+    if (!c || !c->have_counts || !h_keys || !h_counts) return fail(P3_ERR_STATE, "p3_short_kmer_export: no counts / null output");
+    CU(cudaSetDevice(c->device));
+    uint64_t nd = c->h_stats.n_distinct21;
+    if (n) *n = nd;
+    if (cap < nd) return fail(P3_ERR_ARG, "p3_short_kmer_export: capacity too small");
+    if (nd == 0) return P3_OK;
+    uint64_t *dk = nullptr, *dc = nullptr;
+    CU(cudaMalloc(&dk, sizeof(uint64_t) * nd));
+    CU(cudaMalloc(&dc, sizeof(uint64_t) * nd));
+    CU(cudaMemsetAsync(&c->d_stats->n_export, 0, sizeof(unsigned long long), c->stream));
+    export_counts_kernel<<<c->grid(), 256, 0, c->stream>>>(c->d_table, c->nb * 4, c->ovf(), c->d_stats, 0, dk, dc, nd);
+    c->launches++;
+    CU(cudaMemcpyAsync(h_keys, dk, sizeof(uint64_t) * nd, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(h_counts, dc, sizeof(uint64_t) * nd, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    cudaFree(dk); cudaFree(dc);
+    return P3_OK;
+}
+
+int p3_short_kmer_lookup(p3_ctx *c, const uint64_t *h_keys, uint64_t n, uint64_t *h_counts) {
+    if (!c || !c->have_counts) return fail(P3_ERR_STATE, "no counts");
+    if (n == 0) return P3_OK;
+    CU(cudaSetDevice(c->device));
+    uint64_t *dk = nullptr, *dc = nullptr;
+    CU(cudaMalloc(&dk, sizeof(uint64_t) * n));
+    CU(cudaMalloc(&dc, sizeof(uint64_t) * n));
+    CU(cudaMemcpyAsync(dk, h_keys, sizeof(uint64_t) * n, cudaMemcpyHostToDevice, c->stream));
+    lookup_counts_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->d_table, c->nb, c->ovf(), c->d_stats, dk, n, dc);
+    c->launches++;
+    CU(cudaMemcpyAsync(h_counts, dc, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    cudaFree(dk); cudaFree(dc);
+    return P3_OK;
+}
+
+// ---- stage B -----------------------------------------------------------------------------------
+static int alloc_bloom(p3_ctx *c, uint32_t k, uint64_t filter_size, uint32_t num_hashes) {
+    if (k < P3_MIN_K || k > P3_MAX_K) return fail(P3_ERR_ARG, "k outside [21,32] is not supported by this build");
+    if (filter_size == 0) return fail(P3_ERR_ARG, "filter_size == 0 (the reference divides by zero here)");
+    if (num_hashes > 255) return fail(P3_ERR_ARG, "num_hashes > 255 (uint8_t in the reference)");
+    uint64_t words = (filter_size + 31) / 32;
+    if (!c->d_bloom || c->bloom_words != words) {
+        dfree(c->d_bloom);
+        if (cudaMalloc(&c->d_bloom, sizeof(uint32_t) * words) != cudaSuccess) { cudaGetLastError(); return fail(P3_ERR_NOMEM, "bloom allocation failed"); }
+        c->bloom_words = words;
+    }
+    c->k = k; c->filter_size = filter_size; c->num_hashes = num_hashes;
+    return P3_OK;
+}
+
+int p3_make_bf(p3_ctx *c, uint32_t k, uint64_t filter_size, uint32_t num_hashes, uint32_t cov_threshold,
+               uint64_t solid_slots) {
+    if (!c) return fail(P3_ERR_ARG, "null ctx");
+    if (!c->have_counts) return fail(P3_ERR_STATE, "p3_make_bf: run p3_count_short_kmers first");
+    CU(cudaSetDevice(c->device));
+    int rc = alloc_bloom(c, k, filter_size, num_hashes);
+    if (rc) return rc;
+    uint64_t pw = c->n_words + 1;
+    if (!c->d_good21 || !c->d_solid || c->cap_planes < sizeof(uint32_t) * pw) {
+        dfree(c->d_good21); dfree(c->d_solid);
+        CU(cudaMalloc(&c->d_good21, sizeof(uint32_t) * pw));
+        CU(cudaMalloc(&c->d_solid, sizeof(uint32_t) * pw));
+        c->cap_planes = sizeof(uint32_t) * pw;
+    }
+    CU(ensure(c->d_seed, c->cap_seed, sizeof(int64_t) * std::max<uint64_t>(c->n_reads, 1)));
+    // reset the stage-B part of the stats
+    CU(cudaMemsetAsync(&c->d_stats->n_adds, 0, sizeof(unsigned long long) * 5, c->stream));
+    CU(cudaMemsetAsync(c->d_good21 + c->n_words, 0, sizeof(uint32_t), c->stream));
+
+    // B1: coverage flags
+    CU(cudaEventRecord(c->ev[2], c->stream));
+    if (c->d_nmask)
+        flags21_kernel<true><<<c->grid(), 256, 0, c->stream>>>(c->d_packed, c->d_rend, c->d_nmask, c->n_words, c->d_table, c->nb, c->ovf(), c->d_stats, cov_threshold, cov_threshold == 2 ? c->d_proven2 : nullptr, c->d_good21);
+    else
+        flags21_kernel<false><<<c->grid(), 256, 0, c->stream>>>(c->d_packed, c->d_rend, nullptr, c->n_words, c->d_table, c->nb, c->ovf(), c->d_stats, cov_threshold, cov_threshold == 2 ? c->d_proven2 : nullptr, c->d_good21);
+    c->launches++;
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(c->ev[3], c->stream));
+
+    // B2a: solid plane + n_adds; number of distinct good 21-mers sizes the solid set
+    solid_kernel<<<c->grid(), 256, 0, c->stream>>>(c->d_good21, c->n_words, (int)k, c->d_solid, c->d_stats);
+    c->launches++;
+    if (solid_slots == 0) {
+        export_counts_kernel<<<c->grid(), 256, 0, c->stream>>>(c->d_table, c->nb * 4, c->ovf(), c->d_stats, cov_threshold, nullptr, nullptr, 0);
+        c->launches++;
+    }
+    rc = pull_stats(c);
+    if (rc) return rc;
+    if (solid_slots == 0) {
+        uint64_t est = std::min<uint64_t>(c->h_stats.n_adds, (uint64_t)(1.25 * (double)c->h_stats.n_good21) + 1024);
+        solid_slots = std::max<uint64_t>(2 * est, 1024);
+    }
+    // B2b: de-duplicated BF.add; grows the solid set on overflow
+    for (int attempt = 0;; attempt++) {
+        uint64_t nbs = (solid_slots + 3) / 4;
+        if (!c->d_set || c->nbs != nbs) {
+            dfree(c->d_set); dfree(c->d_list);
+            if (cudaMalloc(&c->d_set, nbs * 32) != cudaSuccess || cudaMalloc(&c->d_list, nbs * 32) != cudaSuccess) {
+                cudaGetLastError();
+                return fail(P3_ERR_NOMEM, "solid k-mer set allocation failed");
+            }
+            c->nbs = nbs; c->list_cap = nbs * 4;
+        }
+        CU(cudaMemsetAsync(c->d_set, 0xFF, nbs * 32, c->stream));
+        CU(cudaMemsetAsync(c->d_bloom, 0, sizeof(uint32_t) * c->bloom_words, c->stream));
+        CU(cudaMemsetAsync(&c->d_stats->n_distinct_solid, 0, sizeof(unsigned long long), c->stream));
+        CU(cudaMemsetAsync(&c->d_stats->err_table_full, 0, sizeof(unsigned), c->stream));
+        CU(cudaEventRecord(c->ev[4], c->stream));
+        if (c->d_nmask)
+            makebf_kernel<true><<<c->grid(), 256, 0, c->stream>>>(c->d_packed, c->d_nmask, c->d_solid, c->n_words, (int)k, c->d_set, nbs, c->d_list, c->list_cap, c->bloom(), c->d_stats);
+        else
+            makebf_kernel<false><<<c->grid(), 256, 0, c->stream>>>(c->d_packed, nullptr, c->d_solid, c->n_words, (int)k, c->d_set, nbs, c->d_list, c->list_cap, c->bloom(), c->d_stats);
+        c->launches++;
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(c->ev[5], c->stream));
+        seeds_kernel<<<c->grid(4), 256, 0, c->stream>>>(c->d_off, c->n_reads, c->d_solid, (int)k, c->d_seed);
+        c->launches++;
+        CU(cudaEventRecord(c->ev[6], c->stream));
+        rc = pull_stats(c);
+        if (rc) return rc;
+        if (!c->h_stats.err_table_full) break;
+        if (attempt >= 16) return fail(P3_ERR_TABLE_FULL, "solid k-mer set full after growing");
+        solid_slots = std::max<uint64_t>(solid_slots * 4, 1024);
+    }
+    CU(cudaEventElapsedTime(&c->ms[1], c->ev[2], c->ev[3]));
+    CU(cudaEventElapsedTime(&c->ms[2], c->ev[4], c->ev[5]));
+    CU(cudaEventElapsedTime(&c->ms[3], c->ev[5], c->ev[6]));
+    c->have_bf = true; c->have_solid = true; c->have_adj = false;
+    return P3_OK;
+}
+
+int p3_make_bf_stats(p3_ctx *c, uint64_t *n_adds, uint64_t *n_distinct_solid) {
+    if (!c || !c->have_solid) return fail(P3_ERR_STATE, "no make_bf result");
+    if (n_adds) *n_adds = c->h_stats.n_adds;
+    if (n_distinct_solid) *n_distinct_solid = c->h_stats.n_distinct_solid;
+    return P3_OK;
+}
+
+int p3_bf_export(p3_ctx *c, uint8_t *h_bits) {
+    if (!c || !c->have_bf || !h_bits) return fail(P3_ERR_STATE, "p3_bf_export: no filter");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(h_bits, c->d_bloom, (c->filter_size + 7) / 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return P3_OK;
+}
+
+int p3_bf_import(p3_ctx *c, uint32_t k, uint64_t filter_size, uint32_t num_hashes, const uint8_t *h_bits) {
+    if (!c) return fail(P3_ERR_ARG, "null ctx");
+    CU(cudaSetDevice(c->device));
+    int rc = alloc_bloom(c, k, filter_size, num_hashes);
+    if (rc) return rc;
+    CU(cudaMemsetAsync(c->d_bloom, 0, sizeof(uint32_t) * c->bloom_words, c->stream));
+    if (h_bits) CU(cudaMemcpyAsync(c->d_bloom, h_bits, (filter_size + 7) / 8, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->have_bf = true;
+    return P3_OK;
+}
+
+int p3_seed_export(p3_ctx *c, int64_t *h_seed_pos) {
+    if (!c || !c->have_solid || !h_seed_pos) return fail(P3_ERR_STATE, "p3_seed_export: no make_bf result");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(h_seed_pos, c->d_seed, sizeof(int64_t) * c->n_reads, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return P3_OK;
+}
+
+int p3_solid_flags_export(p3_ctx *c, uint32_t *h_bitmap) {
+    if (!c || !c->have_solid || !h_bitmap) return fail(P3_ERR_STATE, "p3_solid_flags_export: no make_bf result");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(h_bitmap, c->d_solid, sizeof(uint32_t) * c->n_words, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return P3_OK;
+}
+
+static int with_kmers(p3_ctx *c, const uint64_t *h_kmers, uint64_t n, uint64_t **dk) {
+    CU(cudaMalloc(dk, sizeof(uint64_t) * n));
+    CU(cudaMemcpyAsync(*dk, h_kmers, sizeof(uint64_t) * n, cudaMemcpyHostToDevice, c->stream));
+    return P3_OK;
+}
+
+int p3_bf_add(p3_ctx *c, const uint64_t *h_kmers, uint64_t n) {
+    if (!c || !c->have_bf) return fail(P3_ERR_STATE, "p3_bf_add: no filter");
+    if (n == 0) return P3_OK;
+    CU(cudaSetDevice(c->device));
+    uint64_t *dk = nullptr;
+    int rc = with_kmers(c, h_kmers, n, &dk);
+    if (rc) return rc;
+    bf_add_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->bloom(), dk, n);
+    c->launches++;
+    CU(cudaStreamSynchronize(c->stream));
+    cudaFree(dk);
+    return P3_OK;
+}
+
+int p3_bf_possibly_contains(p3_ctx *c, const uint64_t *h_kmers, uint64_t n, uint8_t *h_out) {
+    if (!c || !c->have_bf) return fail(P3_ERR_STATE, "p3_bf_possibly_contains: no filter");
+    if (n == 0) return P3_OK;
+    CU(cudaSetDevice(c->device));
+    uint64_t *dk = nullptr; uint8_t *dout = nullptr;
+    int rc = with_kmers(c, h_kmers, n, &dk);
+    if (rc) return rc;
+    CU(cudaMalloc(&dout, n));
+    bf_query_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->bloom(), dk, n, dout);
+    c->launches++;
+    CU(cudaMemcpyAsync(h_out, dout, n, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    cudaFree(dk); cudaFree(dout);
+    return P3_OK;
+}
+
+int p3_double_hash(p3_ctx *c, uint32_t k, const uint64_t *h_kmers, uint64_t n, uint64_t *h_out) {
+    if (!c) return fail(P3_ERR_ARG, "null ctx");
+    if (k < 1 || k > 32) return fail(P3_ERR_ARG, "p3_double_hash: k must be <= 32");
+    if (n == 0) return P3_OK;
+    CU(cudaSetDevice(c->device));
+    uint64_t *dk = nullptr, *dout = nullptr;
+    int rc = with_kmers(c, h_kmers, n, &dk);
+    if (rc) return rc;
+    CU(cudaMalloc(&dout, sizeof(uint64_t) * 2 * n));
+    double_hash_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>((int)((2 * k + 7) / 8), dk, n, dout);
+    c->launches++;
+    CU(cudaMemcpyAsync(h_out, dout, sizeof(uint64_t) * 2 * n, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    cudaFree(dk); cudaFree(dout);
+    return P3_OK;
+}
+
+// ---- stage C -----------------------------------------------------------------------------------
+int p3_dbg_adjacency(p3_ctx *c) {
+    if (!c || !c->have_solid) return fail(P3_ERR_STATE, "p3_dbg_adjacency: run p3_make_bf first");
+    CU(cudaSetDevice(c->device));
+    uint64_t n = c->h_stats.n_distinct_solid;
+    if (!c->d_adj || c->adj_cap < n) {
+        dfree(c->d_adj);
+        c->adj_cap = std::max<uint64_t>(c->list_cap, std::max<uint64_t>(n, 1));
+        CU(cudaMalloc(&c->d_adj, c->adj_cap));
+    }
+    CU(cudaMemsetAsync(&c->d_stats->n_edges, 0, sizeof(unsigned long long), c->stream));
+    CU(cudaEventRecord(c->ev[7], c->stream));
+    if (n) {
+        adjacency_kernel<<<c->grid(), 256, 0, c->stream>>>(c->d_list, n, (int)c->k, c->bloom(), c->d_adj, c->d_stats);
+        c->launches++;
+        CU(cudaGetLastError());
+    }
+    CU(cudaEventRecord(c->ev[8], c->stream));
+    int rc = pull_stats(c);
+    if (rc) return rc;
+    CU(cudaEventElapsedTime(&c->ms[4], c->ev[7], c->ev[8]));
+    c->have_adj = true;
+    return P3_OK;
+}
+
+int p3_dbg_stats(p3_ctx *c, uint64_t *n_kmers, uint64_t *n_edges) {
+    if (!c || !c->have_adj) return fail(P3_ERR_STATE, "no adjacency result");
+    if (n_kmers) *n_kmers = c->h_stats.n_distinct_solid;
+    if (n_edges) *n_edges = c->h_stats.n_edges;
+    return P3_OK;
+}
+
+int p3_dbg_export(p3_ctx *c, uint64_t *h_kmers, uint8_t *h_adj, uint64_t cap, uint64_t *n) {
+    if (!c || !c->have_solid) return fail(P3_ERR_STATE, "p3_dbg_export: no make_bf result");
+    CU(cudaSetDevice(c->device));
+    uint64_t nd = c->h_stats.n_distinct_solid;
+    if (n) *n = nd;
+    if (cap < nd) return fail(P3_ERR_ARG, "p3_dbg_export: capacity too small");
+    if (nd == 0) return P3_OK;
+    if (h_kmers) CU(cudaMemcpyAsync(h_kmers, c->d_list, sizeof(uint64_t) * nd, cudaMemcpyDeviceToHost, c->stream));
+    if (h_adj) {
+        if (!c->have_adj) return fail(P3_ERR_STATE, "p3_dbg_export: run p3_dbg_adjacency first");
+        CU(cudaMemcpyAsync(h_adj, c->d_adj, nd, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    return P3_OK;
+}
+
+int p3_check_directions(p3_ctx *c, const uint64_t *h_kmers, uint64_t n, uint8_t *h_mask) {
+    if (!c || !c->have_bf) return fail(P3_ERR_STATE, "p3_check_directions: no filter");
+    if (n == 0) return P3_OK;
+    CU(cudaSetDevice(c->device));
+    uint64_t *dk = nullptr; uint8_t *dout = nullptr;
+    int rc = with_kmers(c, h_kmers, n, &dk);
+    if (rc) return rc;
+    CU(cudaMalloc(&dout, n));
+    uint64_t warps = (n + 3) / 4;
+    unsigned blocks = (unsigned)std::min<uint64_t>((warps + 7) / 8, (uint64_t)c->grid());
+    adjacency_kernel<<<blocks, 256, 0, c->stream>>>(dk, n, (int)c->k, c->bloom(), dout, nullptr);
+    c->launches++;
+    CU(cudaMemcpyAsync(h_mask, dout, n, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    cudaFree(dk); cudaFree(dout);
+    return P3_OK;
+}
+
+// ---- whole path ----------------------------------------------------------------------------------
+int p3_assemble_hot_path(p3_ctx *c, const uint64_t *h_packed, uint64_t total_bases, const uint64_t *h_off,
+                         uint64_t n_reads, const uint32_t *h_nmask, uint64_t all_bases, uint32_t k,
+                         uint64_t filter_size, uint32_t num_hashes, uint64_t table_slots, uint64_t solid_slots) {
+    if (!c) return fail(P3_ERR_ARG, "null ctx");
+    if (filter_size == 0) {
+        int rc = p3_estimate_bloomfilter(all_bases, k, &filter_size, &num_hashes);
+        if (rc) return rc;
+    }
+    int rc = p3_reads_upload(c, h_packed, total_bases, h_off, n_reads, h_nmask);
+    if (rc) return rc;
+    rc = p3_count_short_kmers(c, table_slots);
+    if (rc) return rc;
+    rc = p3_make_bf(c, k, filter_size, num_hashes, P3_COV_THRESHOLD, solid_slots);
+    if (rc) return rc;
+    return p3_dbg_adjacency(c);
+}
+
+int p3_stage_ms(p3_ctx *c, float ms[5]) {
+    if (!c) return fail(P3_ERR_ARG, "null ctx");
+    for (int i = 0; i < 5; i++) ms[i] = c->ms[i];
+    return P3_OK;
+}
+uint64_t p3_launch_count(p3_ctx *c) { return c ? c->launches : 0; }
+int p3_bf_params(p3_ctx *c, uint64_t *filter_size, uint32_t *num_hashes, uint32_t *k) {
+    if (!c) return fail(P3_ERR_ARG, "null ctx");
+    if (filter_size) *filter_size = c->filter_size;
+    if (num_hashes) *num_hashes = c->num_hashes;
+    if (k) *k = c->k;
+    return P3_OK;
+}
+
+}  // extern "C"

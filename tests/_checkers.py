@@ -189,6 +189,8 @@ class Ref:
         L.p3ref_num_hashes.argtypes = [C.c_void_p]
         L.p3ref_num_hashes.restype = C.c_int
         L.p3ref_add_read.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_uint64]
+        L.p3ref_add_reads.argtypes = [C.c_void_p, u8p, u64p, C.c_uint64]
+        L.p3ref_check_directions_batch.argtypes = [C.c_void_p, u8p, C.c_uint64, u8p]
         L.p3ref_reads_export.restype = C.c_uint64
         L.p3ref_reads_export.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.p3ref_estimate_only.argtypes = [C.c_uint64, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_int)]
@@ -229,6 +231,14 @@ class Ref:
         for i, r in enumerate(reads):
             b = r.encode() if isinstance(r, str) else bytes(r)
             self.L.p3ref_add_read(self.h, (">r%d" % i).encode(), b, len(b))
+
+    def add_reads_arrays(self, seq, off):
+        self.L.p3ref_add_reads(self.h, np.ascontiguousarray(seq, np.uint8), np.ascontiguousarray(off, np.uint64), len(off) - 1)
+
+    def check_directions_batch(self, kmers_ascii, n):
+        out = np.zeros(max(n, 1), np.uint8)
+        self.L.p3ref_check_directions_batch(self.h, np.ascontiguousarray(kmers_ascii, np.uint8), n, out)
+        return out[:n]
 
     def reads(self):
         n = self.n_reads

@@ -1,0 +1,232 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the oracle
+(bit-exact: integer/byte work) and against the golden fixtures from the reference build."""
+import numpy as np
+import pytest
+
+from _checkers import Oracle, kmer_str_to_words, reads_to_arrays
+from platanus3_b200 import _lib, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = _lib.Context(0)
+    yield c
+    c.close()
+
+
+def _dataset(seed, genome, cov, rl, err):
+    g = synth.random_genome(genome, seed)
+    return synth.reads_as_bytes(synth.simulate_reads(g, cov, rl, err, seed + 1))
+
+
+def _full_check(ctx, oracle, reads, k, m=0, n_adj=3000, table_slots=0, solid_slots=0):
+    seq, off = reads_to_arrays(reads)
+    if m:
+        fs, nh = m, 10
+    else:
+        fs, nh = _lib.estimate_bloomfilter(int(off[-1]), k)
+        assert (fs, nh) == oracle.estimate_bloomfilter(int(off[-1]), k)
+    ctx.load_ascii(seq, off)
+    n_pos, n_distinct = ctx.count_short_kmers(table_slots)
+    keys, counts = ctx.short_kmer_export()
+    okeys, ocounts = oracle.count_short_kmers(seq, off)
+    assert n_pos == int(ocounts.sum()) and n_distinct == len(okeys)
+    assert np.array_equal(keys, okeys)
+    assert np.array_equal(counts, ocounts)
+
+    n_adds, n_solid = ctx.make_bf(k, fs, nh, solid_slots=solid_slots)
+    obits, oseeds, osolid_flags, oadds = oracle.make_bf(seq, off, k, okeys, ocounts, fs, nh, want_solid=True)
+    assert n_adds == oadds
+    assert np.array_equal(ctx.bf_export(), obits)
+    assert np.array_equal(ctx.seed_export(), oseeds)
+    assert np.array_equal(ctx.solid_flags_export(), osolid_flags)
+
+    n_kmers, n_edges = ctx.dbg_adjacency()
+    kmers, adj = ctx.dbg_export()
+    osolid = oracle.solid_kmers(seq, off, k, okeys, ocounts)[:, 0]
+    assert n_kmers == n_solid == len(osolid)
+    assert np.array_equal(kmers, osolid)
+    assert n_edges == int(np.unpackbits(adj).sum())
+    step = max(1, len(osolid) // n_adj)
+    for i in range(0, len(osolid), step):
+        assert adj[i] == oracle.check_directions(obits, fs, nh, osolid[i:i + 1], k), (i, hex(int(osolid[i])))
+    return dict(keys=okeys, bits=obits, fs=fs, nh=nh, solid=osolid)
+
+
+@pytest.mark.parametrize("k", [21, 22, 25, 27, 28, 29, 31, 32])
+def test_pipeline_small(ctx, oracle, k):
+    reads = _dataset(k, genome=5000, cov=15, rl=90, err=0.01)
+    _full_check(ctx, oracle, reads, k)
+
+
+def test_pipeline_error_free(ctx, oracle):
+    """configs[0] shape in miniature: error-free reads, every k-mer solid"""
+    reads = _dataset(77, genome=20000, cov=30, rl=150, err=0.0)
+    _full_check(ctx, oracle, reads, 32)
+
+
+def test_pipeline_medium_with_errors(ctx, oracle):
+    """configs[1] shape in miniature: 1% substitutions, Bloom screening of error k-mers"""
+    reads = _dataset(78, genome=200000, cov=50, rl=150, err=0.01)
+    _full_check(ctx, oracle, reads, 32, n_adj=5000)
+
+
+def test_pipeline_m_option(ctx, oracle):
+    reads = _dataset(5, genome=4000, cov=12, rl=80, err=0.02)
+    _full_check(ctx, oracle, reads, 25, m=100003)
+
+
+def test_ragged_reads_and_non_acgt(ctx, oracle):
+    """reads of many lengths (one exactly k), N / lower-case bases (reference quirk: code 0 on
+    both strands), read ends at every word phase"""
+    k = 25
+    rng = np.random.default_rng(3)
+    g = synth.random_genome(3000, 11)
+    reads = []
+    for i in range(700):
+        L = int(rng.integers(k, 140)) if i else k
+        s = int(rng.integers(0, len(g) - L))
+        r = bytearray(synth.codes_to_ascii(g[s:s + L]).tobytes())
+        if i % 7 == 0:
+            r[int(rng.integers(0, L))] = ord("N")
+        if i % 11 == 0:
+            r[int(rng.integers(0, L))] = ord("a")
+        reads.append(bytes(r))
+    _full_check(ctx, oracle, reads, k, m=70001)
+
+
+def test_long_reads(ctx, oracle):
+    reads = _dataset(21, genome=30000, cov=12, rl=5000, err=0.01)
+    _full_check(ctx, oracle, reads, 32)
+
+
+def test_tight_tables_grow_or_fail_loudly(ctx, oracle):
+    reads = _dataset(9, genome=5000, cov=15, rl=90, err=0.01)
+    seq, off = reads_to_arrays(reads)
+    ctx.load_ascii(seq, off)
+    with pytest.raises(_lib.P3Error) as e:
+        ctx.count_short_kmers(table_slots=64)
+    assert e.value.code == -3
+    # high load factor still exact; tiny solid set grows by itself
+    okeys, _ = oracle.count_short_kmers(seq, off)
+    _full_check(ctx, oracle, reads, 32, table_slots=int(len(okeys) * 1.05), solid_slots=16)
+
+
+def test_repeats_and_homopolymers(ctx, oracle):
+    """hot keys: poly-A / poly-T reads (canonical 0), tandem repeats, palindromic k-mers"""
+    k = 22
+    reads = [b"A" * 200, b"T" * 180, b"AC" * 100, b"ACGT" * 60, b"GAATTC" * 40] * 30
+    reads += _dataset(4, genome=2000, cov=10, rl=100, err=0.0)
+    _full_check(ctx, oracle, reads, k, m=40009)
+
+
+def test_count_overflow_side_table(ctx, oracle):
+    """counts beyond the 22-bit slot field stay exact (overflow side table)"""
+    n = 5_000_000
+    seq = np.full(n, ord("A"), np.uint8)
+    off = np.array([0, n], np.uint64)
+    ctx.load_ascii(seq, off)
+    n_pos, n_distinct = ctx.count_short_kmers(4096)
+    keys, counts = ctx.short_kmer_export()
+    assert n_distinct == 1 and keys[0] == 0
+    assert counts[0] == n - 20 == n_pos and counts[0] > (1 << 22)
+    assert ctx.short_kmer_lookup(np.array([0, 5], np.uint64)).tolist() == [n - 20, 0]
+    n_adds, n_solid = ctx.make_bf(32, 10007, 10)
+    assert n_adds == n - 31 and n_solid == 1
+
+
+def test_bf_primitives(ctx, oracle):
+    """BF::add / possiblyContains / GetDoubleHash_64bit batched over canonical k-mers"""
+    rng = np.random.default_rng(8)
+    for k in (21, 25, 28, 29, 32):
+        fs, nh = 50021, 7
+        kmers = np.array([oracle.canonical_words("".join("ACGT"[i] for i in rng.integers(0, 4, k)), k)[0]
+                          for _ in range(400)], np.uint64)
+        dh = ctx.double_hash(k, kmers)
+        for i in range(0, 400, 13):
+            assert tuple(int(x) for x in dh[i]) == oracle.double_hash(oracle.std_hash_kmer(kmers[i:i + 1], k))
+        ctx.bf_import(k, fs, nh, None)
+        ctx.bf_add(kmers[:200])
+        obits = np.zeros((fs + 7) // 8, np.uint8)
+        for i in range(200):
+            oracle.bf_add(obits, fs, nh, kmers[i:i + 1], k)
+        assert np.array_equal(ctx.bf_export(), obits)
+        got = ctx.bf_possibly_contains(kmers)
+        want = np.array([oracle.L.p3o_bf_possibly_contains(obits, fs, nh, kmers[i:i + 1], k) for i in range(400)], np.uint8)
+        assert np.array_equal(got, want) and got[:200].all()
+
+
+def test_check_directions_oriented(ctx, oracle):
+    """CheckDirections on oriented (non-canonical) k-mers, incl. k-mers that are not in the set"""
+    k = 31
+    reads = _dataset(31, genome=4000, cov=12, rl=100, err=0.005)
+    info = _full_check(ctx, oracle, reads, k)
+    rng = np.random.default_rng(2)
+    probes = [kmer_str_to_words(r[p:p + k].decode(), k)[0] for r in reads[:50] for p in range(0, 60, 9)]
+    probes += [int(x) for x in rng.integers(0, 1 << 62, 200)]
+    probes = np.array(probes, np.uint64)
+    got = ctx.check_directions(probes)
+    want = np.array([oracle.check_directions(info["bits"], info["fs"], info["nh"], probes[i:i + 1], k) for i in range(len(probes))], np.uint8)
+    assert np.array_equal(got, want)
+
+
+def test_whole_path_entry_point(ctx, oracle):
+    """p3_assemble_hot_path on host staging buffers == staged calls"""
+    k = 32
+    reads = _dataset(12, genome=8000, cov=20, rl=120, err=0.01)
+    seq, off = reads_to_arrays(reads)
+    packed, nmask = _lib.pack_reads(seq, off)
+    ctx.assemble_hot_path(packed, off, k, nmask)
+    fs, nh = oracle.estimate_bloomfilter(int(off[-1]), k)
+    assert (ctx.filter_size, ctx.num_hashes) == (fs, nh)
+    okeys, ocounts = oracle.count_short_kmers(seq, off)
+    obits, oseeds, _, _ = oracle.make_bf(seq, off, k, okeys, ocounts, fs, nh)
+    assert np.array_equal(ctx.bf_export(), obits)
+    assert np.array_equal(ctx.seed_export(), oseeds)
+    kmers, adj = ctx.dbg_export()
+    assert np.array_equal(kmers, oracle.solid_kmers(seq, off, k, okeys, ocounts)[:, 0])
+
+
+def test_properties_at_scale(ctx):
+    """size-independent properties on a workload too big for the oracle: counts sum to the
+    number of positions, every solid k-mer answers possiblyContains, adjacency is symmetric
+    (a right edge K->N implies N, re-oriented, has the left edge back to K)"""
+    k = 32
+    g = synth.random_genome(2_000_000, 5)
+    codes = synth.simulate_reads(g, 30, 150, 0.01, 6)
+    seq = synth.codes_to_ascii(codes).reshape(-1)
+    off = (np.arange(codes.shape[0] + 1, dtype=np.uint64) * np.uint64(150))
+    ctx.load_ascii(seq, off)
+    n_pos, n_distinct = ctx.count_short_kmers()
+    assert n_pos == codes.shape[0] * 130
+    keys, counts = ctx.short_kmer_export()
+    assert int(counts.sum()) == n_pos and len(np.unique(keys)) == len(keys) == n_distinct
+    fs, nh = _lib.estimate_bloomfilter(int(off[-1]), k)
+    n_adds, n_solid = ctx.make_bf(k, fs, nh)
+    ctx.dbg_adjacency()
+    kmers, adj = ctx.dbg_export()
+    assert len(np.unique(kmers)) == len(kmers) == n_solid
+    assert ctx.bf_possibly_contains(kmers).all()
+    # genome k-mers are (almost all) solid at 30x
+    gk = 0
+    sel = np.arange(0, len(g) - k, 997)
+    win = g[sel[:, None] + np.arange(k)[None, :]].astype(np.uint64)
+    f = np.zeros(len(sel), np.uint64)
+    r = np.zeros(len(sel), np.uint64)
+    for j in range(k):
+        f = (f << np.uint64(2)) | win[:, j]
+        r = r | ((np.uint64(3) - win[:, j]) << np.uint64(2 * j))
+    canon = np.minimum(f, r)
+    assert np.isin(canon, kmers).mean() > 0.99
+    # edge symmetry through the oriented query entry point
+    sub = kmers[:: max(1, len(kmers) // 20000)]
+    a = ctx.check_directions(sub)
+    mask = np.uint64(0xFFFFFFFFFFFFFFFF)
+    for d in range(4, 8):
+        has = (a >> d) & 1 == 1
+        nbr = ((sub[has] << np.uint64(2)) | np.uint64(d - 4)) & mask
+        back = ctx.check_directions(nbr)
+        left_base = (sub[has] >> np.uint64(2 * k - 2)).astype(np.int64)
+        assert np.all((back >> left_base.astype(np.uint8)) & 1 == 1)
