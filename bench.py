@@ -205,7 +205,6 @@ def main():
     # pinned host staging for the e2e leg
     h_packed = wl["packed"].cpu().pin_memory()
     h_off = wl["off"].cpu().pin_memory()
-    ctx2 = _lib.Context(local, ctypes.c_void_p(stream.cuda_stream))
     out_bits = torch.empty((fs + 7) // 8, dtype=torch.uint8).pin_memory()
     out_seeds = torch.empty(n_reads, dtype=torch.int64).pin_memory()
     out_kmers = torch.empty(solid_slots, dtype=torch.int64).pin_memory()
@@ -236,7 +235,7 @@ def main():
     sampler = ClockSampler(local)
     sampler.start()
     l0 = ctx.launch_count()
-    count_ms, stage_acc = [], {}
+    count_ms, stage_acc, sub_acc = [], {}, {}
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -246,6 +245,8 @@ def main():
         count_ms.append(ms["count21"])
         for kk, v in ms.items():
             stage_acc[kk] = stage_acc.get(kk, 0.0) + v
+        for kk, v in ctx.count_substage_ms().items():
+            sub_acc[kk] = sub_acc.get(kk, 0.0) + v
     e1.record(stream)
     torch.cuda.synchronize()
     total_ms = e0.elapsed_time(e1)
@@ -254,7 +255,9 @@ def main():
     st = ctx.stats()
     assert st["n_positions"] == n_pos, (st, n_pos)
 
-    # e2e leg
+    # e2e leg (its own context; the resident one is released first so both fit in HBM)
+    ctx.close()
+    ctx2 = _lib.Context(local, ctypes.c_void_p(stream.cuda_stream))
     step_e2e()
     n_solid = 0
     torch.cuda.synchronize()
@@ -281,9 +284,11 @@ def main():
                    "bf_adds": st["n_adds"], "solid_kmers": st["n_distinct_solid"], "dbg_edges": st["n_edges"],
                    "filter_size_bits": fs, "num_hashes": nh},
         "stage_ms": {kk: v / args.steps for kk, v in stage_acc.items()},
+        "count_substage": {kk: v / args.steps for kk, v in sub_acc.items()},
         "roofline": {"kernel": "count21_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                      "algorithmic_bytes_per_kmer": ALGO_BYTES_PER_KMER, "kernel_ms": k_ms},
+        "count_mode": os.environ.get("P3_COUNT_MODE", "binned"),
         "e2e": {"value": n_pos / (e2e_ms / args.steps * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches, "clocks": clocks,
@@ -291,7 +296,7 @@ def main():
     if genome != GENOME:
         result["config"]["workload"] += " [DEBUG OVERRIDE genome=%d: not the headline config]" % genome
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        ctx.close(); ctx2.close()
+        ctx2.close()
         result["cpu_baseline"] = cpu_baseline()
     if rank == 0:
         print(json.dumps(result))

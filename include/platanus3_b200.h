@@ -142,6 +142,10 @@ int p3_assemble_hot_path(p3_ctx *ctx, const uint64_t *h_packed, uint64_t total_b
 /* device milliseconds of the last run of each stage (CUDA events on the context stream):
  * ms[0]=count21 ms[1]=coverage flags ms[2]=solid+bloom ms[3]=seeds ms[4]=adjacency */
 int p3_stage_ms(p3_ctx *ctx, float ms[5]);
+/* finer timing: ms[0]=histogram+scan ms[1]=scatter into partition bins ms[2]=insert sweep of the last
+ * p3_count_short_kmers call (0 in direct mode), ms[3]=dense BF.add passes of the last p3_make_bf
+ * (part of p3_stage_ms[2]); *parts = table partitions, *chunks = read chunks (0 = direct mode) */
+int p3_count_substage_ms(p3_ctx *ctx, float ms[4], uint32_t *parts, uint64_t *chunks);
 /* kernels launched by this context since creation (for bench.py's gpu_launches) */
 uint64_t p3_launch_count(p3_ctx *ctx);
 /* filter parameters in effect */

@@ -20,7 +20,7 @@ SYMBOLS = [
     "p3_short_kmer_export", "p3_short_kmer_lookup", "p3_make_bf", "p3_make_bf_stats", "p3_bf_export",
     "p3_bf_import", "p3_seed_export", "p3_solid_flags_export", "p3_bf_add", "p3_bf_possibly_contains",
     "p3_double_hash", "p3_dbg_adjacency", "p3_dbg_stats", "p3_dbg_export", "p3_check_directions",
-    "p3_assemble_hot_path", "p3_stage_ms", "p3_launch_count", "p3_bf_params",
+    "p3_assemble_hot_path", "p3_stage_ms", "p3_count_substage_ms", "p3_launch_count", "p3_bf_params",
 ]
 
 
@@ -75,6 +75,7 @@ def lib():
         L.p3_check_directions.argtypes = [vp, vp, u64, vp]
         L.p3_assemble_hot_path.argtypes = [vp, vp, u64, vp, u64, vp, u64, u32, u64, u32, u64, u64]
         L.p3_stage_ms.argtypes = [vp, C.POINTER(C.c_float)]
+        L.p3_count_substage_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(u32), C.POINTER(u64)]
         L.p3_launch_count.restype = u64
         L.p3_launch_count.argtypes = [vp]
         L.p3_bf_params.argtypes = [vp, C.POINTER(u64), C.POINTER(u32), C.POINTER(u32)]
@@ -276,6 +277,13 @@ class Context:
         ms = (C.c_float * 5)()
         check(self.L.p3_stage_ms(self.h, ms))
         return dict(zip(("count21", "flags21", "makebf", "seeds", "adjacency"), [float(x) for x in ms]))
+
+    def count_substage_ms(self):
+        ms = (C.c_float * 4)()
+        parts, chunks = C.c_uint32(), C.c_uint64()
+        check(self.L.p3_count_substage_ms(self.h, ms, C.byref(parts), C.byref(chunks)))
+        return {"hist": float(ms[0]), "scatter": float(ms[1]), "insert": float(ms[2]), "bloom_add": float(ms[3]),
+                "parts": parts.value, "chunks": chunks.value}
 
     def launch_count(self):
         return int(self.L.p3_launch_count(self.h))

@@ -25,6 +25,8 @@ struct Stats {
     unsigned long long n_edges;           // adjacency bits set
     unsigned long long n_good21;          // distinct 21-mers with count >= threshold
     unsigned long long n_export;          // scratch counter for export kernels
+    unsigned long long n_cand;            // first-occurrence candidates logged by the binned count
+    unsigned long long work;              // dynamic work counter of the sweep kernels
     unsigned int err_table_full;
     unsigned int err_ovf_full;
     unsigned int n_overflow;              // entries in the overflow table
@@ -157,15 +159,31 @@ __device__ __forceinline__ void count_bump(uint64_t *slot, uint64_t seen, uint64
         if ((old >> 42) == kCntFieldMax) ovf_add(ovf, key, st);  // field wrapped to 0
     }
 }
-// Returns the count the key is KNOWN to have reached after this insert (a lower bound on the
-// final count, because counts only grow): 1 when this call created the key, seen+1 otherwise.
-// count21 uses it to prove "count >= 2" for every position but the first occurrence of a key,
-// so the coverage pass only revisits those. *created tells the caller to bump n_distinct.
-__device__ __forceinline__ uint64_t count_insert(uint64_t *table, uint64_t nb, uint64_t key, const Ovf &ovf, Stats *st, bool *created) {
-    uint64_t b = __umul64hi(fmix64(key), nb);
-    *created = false;
-    for (uint64_t probe = 0; probe < nb; probe++) {
-        uint64_t *bp = table + 4 * b;
+// Table addressing. The table is split into P equal partitions of nbp buckets; a key lives in
+// partition part(h) (top bits of h = fmix64(key)) and probes linearly INSIDE its partition
+// starting at a bucket chosen from the low 32 bits of h. P = 1 is the plain table. With P > 1
+// a sweep over records binned by partition touches one partition at a time, which then stays
+// L2 resident (profiles/r01_randacc.md: 62-77 G inserts/s instead of 17.4 G/s from DRAM).
+constexpr int kMaxParts = 1024;
+struct Table {
+    uint64_t *slots;
+    uint64_t nbp;   // buckets per partition (< 2^32)
+    uint32_t P;     // partitions
+};
+__device__ __forceinline__ uint32_t part_of(uint64_t h, uint32_t P) { return (uint32_t)__umul64hi(h, (uint64_t)P); }
+__device__ __forceinline__ uint64_t sub_of(uint64_t h, uint64_t nbp) { return ((h & 0xFFFFFFFFULL) * nbp) >> 32; }
+
+// Inserts one occurrence of key. Returns the count the key is KNOWN to have reached after this
+// insert (a lower bound on the final count, because counts only grow): 1 when this call created
+// the key, seen+1 otherwise; 0 on table-full. *created_slot = global slot index when this call
+// created the key, else ~0.
+__device__ __forceinline__ uint64_t count_insert(const Table &t, uint64_t key, const Ovf &ovf, Stats *st, uint64_t *created_slot) {
+    const uint64_t h = fmix64(key);
+    const uint64_t base = (uint64_t)part_of(h, t.P) * t.nbp;
+    uint64_t b = sub_of(h, t.nbp);
+    *created_slot = ~0ULL;
+    for (uint64_t probe = 0; probe < t.nbp; probe++) {
+        uint64_t *bp = t.slots + 4 * (base + b);
         uint64_t s[4];
         ld_bucket(bp, s);
 #pragma unroll
@@ -174,21 +192,23 @@ __device__ __forceinline__ uint64_t count_insert(uint64_t *table, uint64_t nb, u
             if ((v & kKey42) == key) { count_bump(bp + i, v, key, ovf, st); return (v >> 42) + 1; }
             if (v == kEmpty) {
                 uint64_t old = atomicCAS(ull(bp + i), kEmpty, key | kCntOne);
-                if (old == kEmpty) { *created = true; return 1; }
+                if (old == kEmpty) { *created_slot = 4 * (base + b) + i; return 1; }
                 if ((old & kKey42) == key) { count_bump(bp + i, old, key, ovf, st); return (old >> 42) + 1; }
             }
         }
-        b = (b + 1 == nb) ? 0 : b + 1;
+        b = (b + 1 == t.nbp) ? 0 : b + 1;
     }
     atomicExch(&st->err_table_full, 1u);
     return 0;
 }
 // KC[key] (0 when absent)
-__device__ __forceinline__ uint64_t count_lookup(const uint64_t *table, uint64_t nb, uint64_t key, const Ovf &ovf, unsigned n_overflow) {
-    uint64_t b = __umul64hi(fmix64(key), nb);
-    for (uint64_t probe = 0; probe < nb; probe++) {
+__device__ __forceinline__ uint64_t count_lookup(const Table &t, uint64_t key, const Ovf &ovf, unsigned n_overflow) {
+    const uint64_t h = fmix64(key);
+    const uint64_t base = (uint64_t)part_of(h, t.P) * t.nbp;
+    uint64_t b = sub_of(h, t.nbp);
+    for (uint64_t probe = 0; probe < t.nbp; probe++) {
         uint64_t s[4];
-        ld_bucket(table + 4 * b, s);
+        ld_bucket(t.slots + 4 * (base + b), s);
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             uint64_t v = s[i];
@@ -199,7 +219,7 @@ __device__ __forceinline__ uint64_t count_lookup(const uint64_t *table, uint64_t
             }
             if (v == kEmpty) return 0;
         }
-        b = (b + 1 == nb) ? 0 : b + 1;
+        b = (b + 1 == t.nbp) ? 0 : b + 1;
     }
     return 0;
 }
@@ -225,6 +245,22 @@ __device__ __forceinline__ int set_insert(uint64_t *table, uint64_t nb, uint64_t
         b = (b + 1 == nb) ? 0 : b + 1;
     }
     return -1;
+}
+
+// membership only (read-only table)
+__device__ __forceinline__ bool set_contains(const uint64_t *table, uint64_t nb, uint64_t key) {
+    uint64_t b = __umul64hi(fmix64(key), nb);
+    for (uint64_t probe = 0; probe < nb; probe++) {
+        uint64_t s[4];
+        ld_bucket(table + 4 * b, s);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            if (s[i] == key) return true;
+            if (s[i] == kEmpty) return false;
+        }
+        b = (b + 1 == nb) ? 0 : b + 1;
+    }
+    return false;
 }
 
 // ---- Bloom filter, reference src/bloomfilter.cpp ---------------------------------------------------

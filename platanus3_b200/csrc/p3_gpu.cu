@@ -37,10 +37,11 @@ __global__ void rend_kernel(const uint64_t *__restrict__ off, uint64_t n_reads, 
     for (uint64_t p = total_bases + t; p < n_bits; p += stride) atomicOr(rend + (p >> 5), 0x80000000u >> (p & 31));
 }
 
+// ---- direct count (P3_COUNT_MODE=direct): every position goes straight to the DRAM-resident table
 template <bool HAS_MASK>
 __global__ void __launch_bounds__(256)
 count21_kernel(const uint64_t *__restrict__ packed, const uint32_t *__restrict__ rend,
-               const uint32_t *__restrict__ nmask, uint64_t n_words, uint64_t *table, uint64_t nb,
+               const uint32_t *__restrict__ nmask, uint64_t n_words, Table table,
                Ovf ovf, Stats *st, uint32_t *__restrict__ proven2) {
     const uint64_t W21 = ~0ULL << (64 - (kShortK - 1));  // positions p .. p+19
     unsigned n_pos = 0, n_new = 0;
@@ -57,10 +58,10 @@ count21_kernel(const uint64_t *__restrict__ packed, const uint32_t *__restrict__
             uint64_t x = window(hi, lo, o);
             uint64_t m2 = HAS_MASK ? window(mhi, mlo, o) : 0;
             uint64_t key = canonical_from_window(x, m2, kShortK);
-            bool created;
-            uint64_t reached = count_insert(table, nb, key, ovf, st, &created);
+            uint64_t created;
+            uint64_t reached = count_insert(table, key, ovf, st, &created);
             n_pos++;
-            n_new += created ? 1u : 0u;
+            n_new += (created != ~0ULL) ? 1u : 0u;
             if (reached >= 2) g |= 0x80000000u >> o;
         }
         proven2[w] = g;  // bit set: this 21-mer's final count is certainly >= 2
@@ -76,8 +77,8 @@ count21_kernel(const uint64_t *__restrict__ packed, const uint32_t *__restrict__
 template <bool HAS_MASK>
 __global__ void __launch_bounds__(256)
 flags21_kernel(const uint64_t *__restrict__ packed, const uint32_t *__restrict__ rend,
-               const uint32_t *__restrict__ nmask, uint64_t n_words, const uint64_t *__restrict__ table,
-               uint64_t nb, Ovf ovf, const Stats *st, uint64_t thr, const uint32_t *__restrict__ proven2,
+               const uint32_t *__restrict__ nmask, uint64_t n_words, Table table,
+               Ovf ovf, const Stats *st, uint64_t thr, const uint32_t *__restrict__ proven2,
                uint32_t *__restrict__ good21) {
     const uint64_t W21 = ~0ULL << (64 - (kShortK - 1));
     const unsigned n_overflow = st->n_overflow;
@@ -99,9 +100,238 @@ flags21_kernel(const uint64_t *__restrict__ packed, const uint32_t *__restrict__
             uint64_t x = window(hi, lo, o);
             uint64_t m2 = HAS_MASK ? window(mhi, mlo, o) : 0;
             uint64_t key = canonical_from_window(x, m2, kShortK);
-            if (count_lookup(table, nb, key, ovf, n_overflow) >= thr) g |= 0x80000000u >> o;
+            if (count_lookup(table, key, ovf, n_overflow) >= thr) g |= 0x80000000u >> o;
         }
         good21[w] = g;
+    }
+}
+
+// ---- binned count (default): bin -> L2-resident insert sweep -> first-occurrence candidates ----------
+//
+// K1 hist21:    per-partition record counts of a chunk of words (smem histogram per block)
+// K2 scan:      exclusive scan -> bin bases / cursors
+// K3 scatter21: block-local counting sort of a 4096-position tile by partition, then coalesced
+//               runs into the bins. Record = [o:5 | key:42] (uint64) + word index (uint32).
+// K4 insert_bins: grid-stride sweep over the binned records. Records are ordered by partition, so
+//               the whole grid works inside one ~25 MB table partition at a time (L2 resident).
+//               The inserting thread that CREATES a key logs (slot, position): a key with final
+//               count 1 has exactly one occurrence, the one that created it.
+// K5 cand_check: for every candidate whose final count < 2, clear its bit in the coverage plane.
+constexpr int kTileWords = 128;                 // words per scatter tile = threads per block
+constexpr int kTilePos = kTileWords * 32;       // 4096 positions
+
+template <bool HAS_MASK>
+__global__ void __launch_bounds__(256)
+hist21_kernel(const uint64_t *__restrict__ packed, const uint32_t *__restrict__ rend,
+              const uint32_t *__restrict__ nmask, uint64_t w0, uint64_t w1, uint32_t P,
+              unsigned long long *__restrict__ ghist) {
+    __shared__ unsigned int sh[kMaxParts];
+    const uint64_t W21 = ~0ULL << (64 - (kShortK - 1));
+    for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    uint64_t stride = gridDim.x * (uint64_t)blockDim.x;
+    for (uint64_t w = w0 + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < w1; w += stride) {
+        uint64_t hi = __ldg(packed + w), lo = __ldg(packed + w + 1);
+        uint64_t E = ((uint64_t)__ldg(rend + w) << 32) | __ldg(rend + w + 1);
+        uint64_t mhi = 0, mlo = 0;
+        if (HAS_MASK) { mhi = spread32(__ldg(nmask + w)); mlo = spread32(__ldg(nmask + w + 1)); }
+#pragma unroll 4
+        for (int o = 0; o < 32; o++) {
+            if (((E << o) & W21) != 0) continue;
+            uint64_t key = canonical_from_window(window(hi, lo, o), HAS_MASK ? window(mhi, mlo, o) : 0, kShortK);
+            atomicAdd(&sh[part_of(fmix64(key), P)], 1u);
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < P; i += blockDim.x)
+        if (sh[i]) atomicAdd(&ghist[i], (unsigned long long)sh[i]);
+}
+
+// one block: cursor[p] = exclusive prefix of ghist; ghist[P] receives the total
+__global__ void scan_parts_kernel(const unsigned long long *__restrict__ ghist, uint32_t P,
+                                  unsigned long long *__restrict__ cursor, unsigned long long *__restrict__ total) {
+    __shared__ unsigned long long s[kMaxParts];
+    for (uint32_t i = threadIdx.x; i < kMaxParts; i += blockDim.x) s[i] = i < P ? ghist[i] : 0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long acc = 0;
+        for (uint32_t i = 0; i < P; i++) { unsigned long long v = s[i]; s[i] = acc; acc += v; }
+        *total = acc;
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) cursor[i] = s[i];
+}
+
+struct ScatterSmem {
+    uint64_t key[kTilePos];               // 32 KB  records sorted by partition
+    uint16_t part[kTilePos];              //  8 KB
+    uint16_t loc[kTilePos];               //  8 KB  word-in-tile of each sorted record
+    uint16_t rank[32][kTileWords];        //  8 KB  arrival rank of (offset, thread) inside its partition
+    uint32_t hist[kMaxParts];             //  4 KB
+    uint32_t offs[kMaxParts];             //  4 KB
+    unsigned long long gbase[kMaxParts];  //  8 KB
+    uint32_t warp_tot[kTileWords / 32];
+    uint32_t total;
+};
+
+template <bool HAS_MASK>
+__global__ void __launch_bounds__(kTileWords)
+scatter21_kernel(const uint64_t *__restrict__ packed, const uint32_t *__restrict__ rend,
+                 const uint32_t *__restrict__ nmask, uint64_t w0, uint64_t w1, uint32_t P,
+                 unsigned long long *cursor, uint64_t *__restrict__ bkeys, uint32_t *__restrict__ bword,
+                 uint32_t *__restrict__ valid_plane) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ScatterSmem &sm = *reinterpret_cast<ScatterSmem *>(smem_raw);
+    const uint64_t W21 = ~0ULL << (64 - (kShortK - 1));
+    const int tid = threadIdx.x;
+    const uint64_t n_tiles = (w1 - w0 + kTileWords - 1) / kTileWords;
+    const uint32_t per_thread = (P + kTileWords - 1) / kTileWords;  // hist entries scanned per thread (<= 8)
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (uint32_t i = tid; i < P; i += kTileWords) sm.hist[i] = 0;
+        __syncthreads();
+        const uint64_t w = w0 + tile * kTileWords + tid;
+        uint64_t hi = 0, lo = 0, mhi = 0, mlo = 0;
+        uint32_t valid = 0;
+        if (w < w1) {
+            hi = __ldg(packed + w); lo = __ldg(packed + w + 1);
+            uint64_t E = ((uint64_t)__ldg(rend + w) << 32) | __ldg(rend + w + 1);
+            if (HAS_MASK) { mhi = spread32(__ldg(nmask + w)); mlo = spread32(__ldg(nmask + w + 1)); }
+#pragma unroll
+            for (int o = 0; o < 32; o++) valid |= (((E << o) & W21) == 0) ? (0x80000000u >> o) : 0u;
+            valid_plane[w] = valid;
+        }
+        // pass 1: arrival rank inside (tile, partition)
+#pragma unroll 4
+        for (int o = 0; o < 32; o++) {
+            if (!(valid & (0x80000000u >> o))) continue;
+            uint64_t key = canonical_from_window(window(hi, lo, o), HAS_MASK ? window(mhi, mlo, o) : 0, kShortK);
+            sm.rank[o][tid] = (uint16_t)atomicAdd(&sm.hist[part_of(fmix64(key), P)], 1u);
+        }
+        __syncthreads();
+        // exclusive scan of hist[0..P) : thread t owns entries [t*per_thread, (t+1)*per_thread)
+        {
+            uint32_t local = 0;
+            const uint32_t b0 = tid * per_thread;
+            for (uint32_t j = 0; j < per_thread; j++) { uint32_t i = b0 + j; if (i < P) local += sm.hist[i]; }
+            uint32_t incl = local;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, d); if ((tid & 31) >= d) incl += v; }
+            if ((tid & 31) == 31) sm.warp_tot[tid >> 5] = incl;
+            __syncthreads();
+            uint32_t wbase = 0;
+            for (int q = 0; q < (tid >> 5); q++) wbase += sm.warp_tot[q];
+            uint32_t run = wbase + incl - local;
+            for (uint32_t j = 0; j < per_thread; j++) {
+                uint32_t i = b0 + j;
+                if (i < P) {
+                    uint32_t h = sm.hist[i];
+                    sm.offs[i] = run;
+                    if (h) sm.gbase[i] = atomicAdd(&cursor[i], (unsigned long long)h);
+                    run += h;
+                }
+            }
+            if (tid == kTileWords - 1) sm.total = wbase + incl;
+        }
+        __syncthreads();
+        // pass 2: place records sorted by partition
+#pragma unroll 4
+        for (int o = 0; o < 32; o++) {
+            if (!(valid & (0x80000000u >> o))) continue;
+            uint64_t key = canonical_from_window(window(hi, lo, o), HAS_MASK ? window(mhi, mlo, o) : 0, kShortK);
+            uint32_t pt = part_of(fmix64(key), P);
+            uint32_t idx = sm.offs[pt] + sm.rank[o][tid];
+            sm.key[idx] = key | ((uint64_t)o << 42);
+            sm.part[idx] = (uint16_t)pt;
+            sm.loc[idx] = (uint16_t)tid;
+        }
+        __syncthreads();
+        const uint32_t total = sm.total;
+        const uint64_t tile_w0 = w0 + tile * kTileWords;
+        for (uint32_t i = tid; i < total; i += kTileWords) {
+            uint32_t pt = sm.part[i];
+            unsigned long long dst = sm.gbase[pt] + (i - sm.offs[pt]);
+            bkeys[dst] = sm.key[i];
+            bword[dst] = (uint32_t)(tile_w0 + sm.loc[i]);
+        }
+        __syncthreads();
+    }
+}
+
+// Work is handed out in chunks from ONE global counter instead of a static grid-stride loop:
+// blocks run at different speeds, and with a static assignment the fast ones drift many
+// partitions ahead, so that several hundred MB of table are live at once and L2 thrashes
+// (measured: 22 G rec/s). With the shared counter all in-flight chunks lie within
+// gridDim * kSweepChunk records of each other, i.e. inside one or two partitions.
+constexpr int kSweepChunk = 2048;   // records per block per grab (8 per thread)
+constexpr int kSweepPer = kSweepChunk / 256;
+__global__ void __launch_bounds__(256)
+insert_bins_kernel(const uint64_t *__restrict__ bkeys, const uint32_t *__restrict__ bword, uint64_t n,
+                   Table table, Ovf ovf, Stats *st, uint64_t *__restrict__ cand_slot,
+                   uint64_t *__restrict__ cand_pos, uint64_t cand_cap) {
+    __shared__ unsigned long long s_base, s_cand;
+    __shared__ unsigned s_wtot[8];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_base = atomicAdd(&st->work, (unsigned long long)kSweepChunk);
+        __syncthreads();
+        const uint64_t cbase = s_base;
+        if (cbase >= n) break;
+        uint64_t rec[kSweepPer];
+        uint32_t wd[kSweepPer];
+#pragma unroll
+        for (int it = 0; it < kSweepPer; it++) {   // the whole chunk's records first: 8 independent coalesced loads
+            uint64_t i = cbase + it * 256 + threadIdx.x;
+            rec[it] = i < n ? __ldcs(bkeys + i) : ~0ULL;
+            wd[it] = i < n ? __ldcs(bword + i) : 0u;
+        }
+        uint64_t created[kSweepPer];
+        unsigned mine = 0;
+#pragma unroll
+        for (int it = 0; it < kSweepPer; it++) {
+            created[it] = ~0ULL;
+            if (rec[it] != ~0ULL) count_insert(table, rec[it] & kKey42, ovf, st, &created[it]);
+            mine += created[it] != ~0ULL;
+        }
+        // one global atomic per block per chunk for the candidate list (a per-warp atomic on the
+        // single list cursor serialises in L2 and was the whole kernel time)
+        unsigned incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { unsigned v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
+        if (lane == 31) s_wtot[wid] = incl;
+        __syncthreads();
+        unsigned wbase = 0, total = 0;
+#pragma unroll
+        for (int q = 0; q < 8; q++) { unsigned t = s_wtot[q]; if (q < wid) wbase += t; total += t; }
+        if (threadIdx.x == 0 && total) s_cand = atomicAdd(&st->n_cand, (unsigned long long)total);
+        __syncthreads();
+        if (mine) {
+            unsigned long long j = s_cand + wbase + incl - mine;
+#pragma unroll
+            for (int it = 0; it < kSweepPer; it++) {
+                if (created[it] != ~0ULL) {
+                    if (j < cand_cap) { cand_slot[j] = created[it]; cand_pos[j] = (uint64_t)wd[it] * 32 + ((rec[it] >> 42) & 31); }
+                    j++;
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+cand_check_kernel(const uint64_t *__restrict__ slots, const uint64_t *__restrict__ cand_slot,
+                  const uint64_t *__restrict__ cand_pos, uint64_t n_cand, uint64_t thr, Ovf ovf,
+                  const Stats *st, uint32_t *good21) {
+    const unsigned n_overflow = st->n_overflow;
+    uint64_t stride = gridDim.x * (uint64_t)blockDim.x;
+    for (uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; j < n_cand; j += stride) {
+        uint64_t v = __ldcg(slots + __ldcs(cand_slot + j));
+        uint64_t c = v >> 42;
+        if (c < thr && n_overflow) c += ovf_get(ovf, v & kKey42) << 22;
+        if (c < thr) {
+            uint64_t pos = __ldcs(cand_pos + j);
+            atomicAnd(good21 + (pos >> 5), ~(0x80000000u >> (pos & 31)));
+        }
     }
 }
 
@@ -136,8 +366,9 @@ template <bool HAS_MASK>
 __global__ void __launch_bounds__(256)
 makebf_kernel(const uint64_t *__restrict__ packed, const uint32_t *__restrict__ nmask,
               const uint32_t *__restrict__ solid, uint64_t n_words, int k, uint64_t *set, uint64_t nbs,
-              uint64_t *__restrict__ list, uint64_t list_cap, Bloom bf, Stats *st) {
+              Stats *st) {
     uint64_t stride = gridDim.x * (uint64_t)blockDim.x;
+    bool full = false;
     for (uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < n_words; w += stride) {
         uint32_t s = __ldg(solid + w);
         if (!s) continue;
@@ -149,15 +380,59 @@ makebf_kernel(const uint64_t *__restrict__ packed, const uint32_t *__restrict__ 
             s &= ~(0x80000000u >> o);
             uint64_t x = window(hi, lo, o);
             uint64_t m2 = HAS_MASK ? window(mhi, mlo, o) : 0;
-            uint64_t c = canonical_from_window(x, m2, k);
-            int r = set_insert(set, nbs, c);
-            if (r > 0) {
-                unsigned long long idx = atomicAdd(&st->n_distinct_solid, 1ULL);
-                if (idx < list_cap) list[idx] = c;
-                bloom_add(bf, c);
-            } else if (r < 0) {
-                atomicExch(&st->err_table_full, 1u);
-            }
+            if (set_insert(set, nbs, canonical_from_window(x, m2, k)) < 0) full = true;
+        }
+    }
+    if (full) atomicExch(&st->err_table_full, 1u);
+}
+
+// distinct solid k-mers = occupied slots of the set, compacted into a dense list. One global
+// atomic per block-iteration (a per-winner atomic on one list cursor serialises in L2).
+__global__ void __launch_bounds__(256)
+compact_set_kernel(const uint64_t *__restrict__ set, uint64_t n_slots, uint64_t *__restrict__ list,
+                   uint64_t list_cap, Stats *st) {
+    __shared__ unsigned s_wtot[8];
+    __shared__ unsigned long long s_base;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint64_t stride = gridDim.x * (uint64_t)blockDim.x;
+    uint64_t n_round = (n_slots + stride - 1) / stride;
+    for (uint64_t r = 0; r < n_round; r++) {
+        uint64_t i = r * stride + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+        uint64_t v = i < n_slots ? __ldcs(set + i) : kEmpty;
+        unsigned m = __ballot_sync(0xffffffffu, v != kEmpty);
+        if (lane == 0) s_wtot[wid] = __popc(m);
+        __syncthreads();
+        unsigned wbase = 0, total = 0;
+#pragma unroll
+        for (int q = 0; q < 8; q++) { unsigned t = s_wtot[q]; if (q < wid) wbase += t; total += t; }
+        if (threadIdx.x == 0 && total) s_base = atomicAdd(&st->n_distinct_solid, (unsigned long long)total);
+        __syncthreads();
+        if (v != kEmpty) {
+            unsigned long long j = s_base + wbase + __popc(m & ((1u << lane) - 1));
+            if (j < list_cap) list[j] = v;
+        }
+        __syncthreads();
+    }
+}
+
+// BF.add (reference src/bloomfilter.cpp:69-74) for every distinct solid k-mer, dense over the list.
+// The filter is usually larger than L2, so it is processed in `n_seg` passes over segments of
+// seg_bits bits (<= ~24 MB): each pass recomputes the num_hashes bit indices (a few dozen ALU ops
+// each) and only sets the bits that fall into its segment, so the atomics of a pass all hit an
+// L2-resident window instead of DRAM (random RED from DRAM: 21.8 G/s, from L2: ~215 G/s).
+__global__ void __launch_bounds__(256)
+bloom_list_kernel(const uint64_t *__restrict__ kmers, uint64_t n, Bloom bf, uint64_t seg_lo, uint64_t seg_hi) {
+    uint64_t stride = gridDim.x * (uint64_t)blockDim.x;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint64_t h1, h2;
+        double_hash(std_hash_kmer1(__ldg(kmers + i), bf.nbytes), h1, h2);
+        uint64_t x = h1;
+        for (int q = 0; q < bf.nh; q++, x += h2) {
+            uint64_t bit = fastmod(x, bf.fm);
+            if (bit < seg_lo || bit >= seg_hi) continue;
+            uint32_t m = 1u << (bit & 31);
+            uint32_t *wp = bf.bits + (bit >> 5);
+            atomicOr(wp, m);   // RED.OR: the segment is L2 resident, a test-load first would only add a dependent trip
         }
     }
 }
@@ -186,8 +461,12 @@ __global__ void seeds_kernel(const uint64_t *__restrict__ off, uint64_t n_reads,
 }
 
 // CheckDirections (reference src/DeBruijnGraph.cpp:326-345): 8 lanes per k-mer, one direction each
+// `set` (may be null): the distinct solid k-mers. Every member was added to the filter, so
+// possiblyContains is certainly true for it and its num_hashes probes are skipped; only
+// non-members (which mostly fail after a few probes) walk the filter.
 __global__ void __launch_bounds__(256)
-adjacency_kernel(const uint64_t *__restrict__ kmers, uint64_t n, int k, Bloom bf, uint8_t *__restrict__ adj, Stats *st) {
+adjacency_kernel(const uint64_t *__restrict__ kmers, uint64_t n, int k, Bloom bf, const uint64_t *__restrict__ set,
+                 uint64_t nbs, uint8_t *__restrict__ adj, Stats *st) {
     const int lane = threadIdx.x & 31;
     const int d = lane & 7, g = lane >> 3;
     uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
@@ -196,7 +475,12 @@ adjacency_kernel(const uint64_t *__restrict__ kmers, uint64_t n, int k, Bloom bf
     for (uint64_t base = warp * 4; base < n; base += n_warps * 4) {
         uint64_t i = base + g;
         bool rec = false;
-        if (i < n) rec = is_recorded(bf, neighbour(__ldg(kmers + i), d, k), k);
+        if (i < n) {
+            uint64_t nb = neighbour(__ldg(kmers + i), d, k);
+            uint64_t rc = revcomp(nb, k);
+            uint64_t c = nb <= rc ? nb : rc;   // IsRecorded canonicalises (DeBruijnGraph.cpp:320-321)
+            rec = (set && set_contains(set, nbs, c)) || bloom_query(bf, c);
+        }
         unsigned m = __ballot_sync(0xffffffffu, rec);
         if (d == 0 && i < n) {
             unsigned byte = (m >> (8 * g)) & 0xFFu;
@@ -226,10 +510,10 @@ __global__ void export_counts_kernel(const uint64_t *__restrict__ table, uint64_
         }
     }
 }
-__global__ void lookup_counts_kernel(const uint64_t *__restrict__ table, uint64_t nb, Ovf ovf, const Stats *st,
+__global__ void lookup_counts_kernel(Table table, Ovf ovf, const Stats *st,
                                      const uint64_t *__restrict__ keys, uint64_t n, uint64_t *counts) {
     uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (i < n) counts[i] = count_lookup(table, nb, keys[i], ovf, st->n_overflow);
+    if (i < n) counts[i] = count_lookup(table, keys[i], ovf, st->n_overflow);
 }
 __global__ void bf_add_kernel(Bloom bf, const uint64_t *__restrict__ kmers, uint64_t n) {
     uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
@@ -276,13 +560,24 @@ struct p3_ctx {
     uint32_t *d_rend = nullptr;
     bool have_reads = false;
     // count table
-    uint64_t *d_table = nullptr; uint64_t nb = 0;
+    uint64_t *d_table = nullptr; uint64_t nb = 0;     // nb = total buckets = P * nbp
+    uint32_t parts = 1; uint64_t nbp = 0;
+    bool binned = true;                                // P3_COUNT_MODE=direct switches it off
+    uint64_t *d_bkeys = nullptr; uint32_t *d_bword = nullptr; uint64_t cap_bkeys = 0, cap_bword = 0;
+    uint32_t *d_valid = nullptr; uint64_t cap_valid = 0;
+    uint64_t *d_cand_slot = nullptr, *d_cand_pos = nullptr; uint64_t cap_cand_slot = 0, cap_cand_pos = 0, cand_cap = 0;
+    unsigned long long *d_ghist = nullptr, *d_cursor = nullptr;
+    float ms_sub[4] = {0, 0, 0, 0};
+    float ms_bloom = 0;                    // hist, scatter, insert, cand_check
+    uint64_t n_chunks = 0, binned_pos = 0;
+    Table table() const { Table t; t.slots = d_table; t.nbp = nbp; t.P = parts; return t; }
     uint64_t *d_ovf_keys = nullptr; unsigned long long *d_ovf_wraps = nullptr;
     bool have_counts = false;
     // make_bf
     uint32_t *d_good21 = nullptr, *d_solid = nullptr;
     uint32_t *d_proven2 = nullptr; uint64_t cap_proven = 0;
     uint64_t *d_set = nullptr; uint64_t nbs = 0;
+    bool set_valid = false;   // d_set holds a subset of what the current filter contains
     uint64_t *d_list = nullptr; uint64_t list_cap = 0;
     uint32_t *d_bloom = nullptr; uint64_t bloom_words = 0;
     int64_t *d_seed = nullptr;
@@ -291,7 +586,7 @@ struct p3_ctx {
     // adjacency
     uint8_t *d_adj = nullptr; uint64_t adj_cap = 0; bool have_adj = false;
     Stats *d_stats = nullptr; Stats h_stats;
-    cudaEvent_t ev[10];
+    cudaEvent_t ev[16];
     float ms[5] = {0, 0, 0, 0, 0};
     Ovf ovf() const { Ovf o; o.keys = d_ovf_keys; o.wraps = d_ovf_wraps; return o; }
     Bloom bloom() const {
@@ -315,6 +610,10 @@ template <typename T> static cudaError_t ensure(T *&p, uint64_t &cap_bytes, uint
 static int pull_stats(p3_ctx *c) {
     CU(cudaMemcpyAsync(&c->h_stats, c->d_stats, sizeof(Stats), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    if (c->binned) {  // the binned count keeps its position total on the host; distinct keys == candidates
+        c->h_stats.n_pos21 = c->binned_pos;
+        c->h_stats.n_distinct21 = c->h_stats.n_cand;
+    }
     return P3_OK;
 }
 
@@ -387,7 +686,8 @@ void p3_destroy(p3_ctx *c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     free_reads(c); free_bf(c);
-    dfree(c->d_table); dfree(c->d_proven2); dfree(c->d_ovf_keys); dfree(c->d_ovf_wraps); dfree(c->d_stats);
+    dfree(c->d_table); dfree(c->d_proven2); dfree(c->d_bkeys); dfree(c->d_bword); dfree(c->d_valid);
+    dfree(c->d_cand_slot); dfree(c->d_cand_pos); dfree(c->d_ghist); dfree(c->d_cursor); dfree(c->d_ovf_keys); dfree(c->d_ovf_wraps); dfree(c->d_stats);
     for (auto &e : c->ev) cudaEventDestroy(e);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -442,43 +742,134 @@ int p3_reads_attach(p3_ctx *c, const uint64_t *d_packed, uint64_t total_bases, c
 }
 
 // ---- stage A -----------------------------------------------------------------------------------
+static int count_direct(p3_ctx *c) {
+    CU(ensure(c->d_proven2, c->cap_proven, sizeof(uint32_t) * (c->n_words + 1)));
+    CU(cudaEventRecord(c->ev[0], c->stream));
+    if (c->d_nmask)
+        count21_kernel<true><<<c->grid(), 256, 0, c->stream>>>(c->d_packed, c->d_rend, c->d_nmask, c->n_words, c->table(), c->ovf(), c->d_stats, c->d_proven2);
+    else
+        count21_kernel<false><<<c->grid(), 256, 0, c->stream>>>(c->d_packed, c->d_rend, nullptr, c->n_words, c->table(), c->ovf(), c->d_stats, c->d_proven2);
+    c->launches++;
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(c->ev[1], c->stream));
+    return P3_OK;
+}
+
+static int count_binned(p3_ctx *c, uint64_t upper) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        CU(cudaFuncSetAttribute(scatter21_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem)));
+        CU(cudaFuncSetAttribute(scatter21_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem)));
+        attr_set = true;
+    }
+    const uint32_t P = c->parts;
+    if (!c->d_ghist) {
+        CU(cudaMalloc(&c->d_ghist, sizeof(unsigned long long) * (kMaxParts + 1)));
+        CU(cudaMalloc(&c->d_cursor, sizeof(unsigned long long) * (kMaxParts + 1)));
+    }
+    CU(ensure(c->d_valid, c->cap_valid, sizeof(uint32_t) * (c->n_words + 1)));
+    // candidates: one per distinct key, never more than slots or positions
+    c->cand_cap = std::min<uint64_t>(c->nb * 4, std::max<uint64_t>(upper, 1));
+    CU(ensure(c->d_cand_slot, c->cap_cand_slot, sizeof(uint64_t) * c->cand_cap));
+    CU(ensure(c->d_cand_pos, c->cap_cand_pos, sizeof(uint64_t) * c->cand_cap));
+    // chunk the words so that the bins (12 B per position) fit the memory budget
+    size_t fr = 0, tot = 0;
+    CU(cudaMemGetInfo(&fr, &tot));
+    uint64_t have = c->cap_bkeys + c->cap_bword;
+    uint64_t budget = (uint64_t)(0.7 * (double)(fr + have));
+    if (const char *e = getenv("P3_BIN_BUDGET_BYTES")) budget = strtoull(e, nullptr, 10);
+    uint64_t chunk_words = std::max<uint64_t>(budget / (12 * 32), kTileWords);
+    chunk_words = std::min<uint64_t>(chunk_words / kTileWords * kTileWords, (c->n_words + kTileWords - 1) / kTileWords * kTileWords);
+    if (chunk_words == 0) chunk_words = kTileWords;
+    uint64_t rec_cap = chunk_words * 32;
+    CU(ensure(c->d_bkeys, c->cap_bkeys, sizeof(uint64_t) * rec_cap));
+    CU(ensure(c->d_bword, c->cap_bword, sizeof(uint32_t) * rec_cap));
+    c->n_chunks = 0; c->binned_pos = 0;
+    for (int i = 0; i < 4; i++) c->ms_sub[i] = 0;
+    CU(cudaEventRecord(c->ev[0], c->stream));
+    for (uint64_t w0 = 0; w0 < c->n_words; w0 += chunk_words) {
+        uint64_t w1 = std::min<uint64_t>(w0 + chunk_words, c->n_words);
+        CU(cudaMemsetAsync(c->d_ghist, 0, sizeof(unsigned long long) * (kMaxParts + 1), c->stream));
+        CU(cudaEventRecord(c->ev[10], c->stream));
+        if (c->d_nmask) hist21_kernel<true><<<c->grid(), 256, 0, c->stream>>>(c->d_packed, c->d_rend, c->d_nmask, w0, w1, P, c->d_ghist);
+        else hist21_kernel<false><<<c->grid(), 256, 0, c->stream>>>(c->d_packed, c->d_rend, nullptr, w0, w1, P, c->d_ghist);
+        scan_parts_kernel<<<1, 256, 0, c->stream>>>(c->d_ghist, P, c->d_cursor, c->d_ghist + kMaxParts);
+        CU(cudaEventRecord(c->ev[11], c->stream));
+        unsigned sblocks = (unsigned)std::min<uint64_t>((w1 - w0 + kTileWords - 1) / kTileWords, (uint64_t)c->n_sm * 3);
+        if (c->d_nmask) scatter21_kernel<true><<<sblocks, kTileWords, sizeof(ScatterSmem), c->stream>>>(c->d_packed, c->d_rend, c->d_nmask, w0, w1, P, c->d_cursor, c->d_bkeys, c->d_bword, c->d_valid);
+        else scatter21_kernel<false><<<sblocks, kTileWords, sizeof(ScatterSmem), c->stream>>>(c->d_packed, c->d_rend, nullptr, w0, w1, P, c->d_cursor, c->d_bkeys, c->d_bword, c->d_valid);
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(c->ev[12], c->stream));
+        unsigned long long n_rec = 0;
+        CU(cudaMemcpyAsync(&n_rec, c->d_ghist + kMaxParts, sizeof(n_rec), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        if (n_rec) {
+            CU(cudaMemsetAsync(&c->d_stats->work, 0, sizeof(unsigned long long), c->stream));
+            insert_bins_kernel<<<c->grid(), 256, 0, c->stream>>>(c->d_bkeys, c->d_bword, n_rec, c->table(), c->ovf(), c->d_stats, c->d_cand_slot, c->d_cand_pos, c->cand_cap);
+            CU(cudaGetLastError());
+            c->launches++;
+        }
+        CU(cudaEventRecord(c->ev[13], c->stream));
+        CU(cudaEventSynchronize(c->ev[13]));
+        {
+            float a = 0, b = 0, d = 0;
+            cudaEventElapsedTime(&a, c->ev[10], c->ev[11]);
+            cudaEventElapsedTime(&b, c->ev[11], c->ev[12]);
+            cudaEventElapsedTime(&d, c->ev[12], c->ev[13]);
+            c->ms_sub[0] += a; c->ms_sub[1] += b; c->ms_sub[2] += d;
+        }
+        c->launches += 3;
+        c->binned_pos += n_rec;        // accumulated on the host (records == valid positions)
+        c->n_chunks++;
+    }
+    CU(cudaEventRecord(c->ev[1], c->stream));
+    return P3_OK;
+}
+
 int p3_count_short_kmers(p3_ctx *c, uint64_t table_slots) {
     if (!c) return fail(P3_ERR_ARG, "null ctx");
     if (!c->have_reads) return fail(P3_ERR_STATE, "p3_count_short_kmers: no reads attached");
     CU(cudaSetDevice(c->device));
+    const char *mode = getenv("P3_COUNT_MODE");
+    c->binned = !(mode && strcmp(mode, "direct") == 0);
     uint64_t upper = c->total_bases > (kShortK - 1) * c->n_reads ? c->total_bases - (kShortK - 1) * c->n_reads : 0;
     if (table_slots == 0) {
         table_slots = std::max<uint64_t>(2 * upper, 1024);
         size_t fr = 0, tot = 0;
         CU(cudaMemGetInfo(&fr, &tot));
-        uint64_t lim = (uint64_t)(0.6 * (double)(fr + (c->d_table ? c->nb * 32 : 0))) / 8;
+        uint64_t lim = (uint64_t)(0.25 * (double)(fr + (c->d_table ? c->nb * 32 : 0))) / 8;
         if (table_slots > lim) table_slots = lim;
     }
-    uint64_t nb = (table_slots + 3) / 4;
-    if (nb == 0) nb = 1;
+    // partitions: ~24 MB of table each so that one partition plus the streaming bins stay in L2
+    uint32_t P = 1;
+    if (c->binned) {
+        uint64_t want = (table_slots * 8 + (24ull << 20) - 1) / (24ull << 20);
+        if (const char *e = getenv("P3_PARTS")) want = strtoull(e, nullptr, 10);
+        P = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(want, 1), kMaxParts);
+    }
+    uint64_t nbp = ((table_slots + 3) / 4 + P - 1) / P;
+    if (nbp == 0) nbp = 1;
+    if (nbp >= (1ull << 32)) return fail(P3_ERR_ARG, "count table partition too large");
+    uint64_t nb = nbp * P;
     if (!c->d_table || c->nb != nb) {
         dfree(c->d_table);
         if (cudaMalloc(&c->d_table, nb * 32) != cudaSuccess) { cudaGetLastError(); return fail(P3_ERR_NOMEM, "count table allocation failed"); }
         c->nb = nb;
     }
+    c->parts = P; c->nbp = nbp;
     CU(cudaMemsetAsync(c->d_table, 0xFF, nb * 32, c->stream));
     CU(cudaMemsetAsync(c->d_ovf_keys, 0xFF, sizeof(uint64_t) * kOvfCap, c->stream));
     CU(cudaMemsetAsync(c->d_ovf_wraps, 0, sizeof(unsigned long long) * kOvfCap, c->stream));
     CU(cudaMemsetAsync(c->d_stats, 0, sizeof(Stats), c->stream));
-    CU(ensure(c->d_proven2, c->cap_proven, sizeof(uint32_t) * (c->n_words + 1)));
-    CU(cudaEventRecord(c->ev[0], c->stream));
-    if (c->d_nmask)
-        count21_kernel<true><<<c->grid(), 256, 0, c->stream>>>(c->d_packed, c->d_rend, c->d_nmask, c->n_words, c->d_table, nb, c->ovf(), c->d_stats, c->d_proven2);
-    else
-        count21_kernel<false><<<c->grid(), 256, 0, c->stream>>>(c->d_packed, c->d_rend, nullptr, c->n_words, c->d_table, nb, c->ovf(), c->d_stats, c->d_proven2);
-    c->launches++;
-    CU(cudaGetLastError());
-    CU(cudaEventRecord(c->ev[1], c->stream));
-    int rc = pull_stats(c);
+    memset(&c->h_stats, 0, sizeof(Stats));
+    int rc = c->binned ? count_binned(c, upper) : count_direct(c);
+    if (rc) return rc;
+    rc = pull_stats(c);
     if (rc) return rc;
     CU(cudaEventElapsedTime(&c->ms[0], c->ev[0], c->ev[1]));
     if (c->h_stats.err_table_full) return fail(P3_ERR_TABLE_FULL, "21-mer count table full: raise table_slots");
     if (c->h_stats.err_ovf_full) return fail(P3_ERR_TABLE_FULL, "count overflow side table full");
+    if (c->binned && c->h_stats.n_cand > c->cand_cap) return fail(P3_ERR_TABLE_FULL, "candidate list overflow");
     c->have_counts = true;
     c->have_bf = c->have_solid = c->have_adj = false;  // buffers are kept for reuse
     return P3_OK;
@@ -519,7 +910,7 @@ int p3_short_kmer_lookup(p3_ctx *c, const uint64_t *h_keys, uint64_t n, uint64_t
     CU(cudaMalloc(&dk, sizeof(uint64_t) * n));
     CU(cudaMalloc(&dc, sizeof(uint64_t) * n));
     CU(cudaMemcpyAsync(dk, h_keys, sizeof(uint64_t) * n, cudaMemcpyHostToDevice, c->stream));
-    lookup_counts_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->d_table, c->nb, c->ovf(), c->d_stats, dk, n, dc);
+    lookup_counts_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->table(), c->ovf(), c->d_stats, dk, n, dc);
     c->launches++;
     CU(cudaMemcpyAsync(h_counts, dc, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
@@ -547,6 +938,7 @@ int p3_make_bf(p3_ctx *c, uint32_t k, uint64_t filter_size, uint32_t num_hashes,
     if (!c) return fail(P3_ERR_ARG, "null ctx");
     if (!c->have_counts) return fail(P3_ERR_STATE, "p3_make_bf: run p3_count_short_kmers first");
     CU(cudaSetDevice(c->device));
+    c->set_valid = false;
     int rc = alloc_bloom(c, k, filter_size, num_hashes);
     if (rc) return rc;
     uint64_t pw = c->n_words + 1;
@@ -563,11 +955,22 @@ int p3_make_bf(p3_ctx *c, uint32_t k, uint64_t filter_size, uint32_t num_hashes,
 
     // B1: coverage flags
     CU(cudaEventRecord(c->ev[2], c->stream));
-    if (c->d_nmask)
-        flags21_kernel<true><<<c->grid(), 256, 0, c->stream>>>(c->d_packed, c->d_rend, c->d_nmask, c->n_words, c->d_table, c->nb, c->ovf(), c->d_stats, cov_threshold, cov_threshold == 2 ? c->d_proven2 : nullptr, c->d_good21);
-    else
-        flags21_kernel<false><<<c->grid(), 256, 0, c->stream>>>(c->d_packed, c->d_rend, nullptr, c->n_words, c->d_table, c->nb, c->ovf(), c->d_stats, cov_threshold, cov_threshold == 2 ? c->d_proven2 : nullptr, c->d_good21);
-    c->launches++;
+    if (c->binned && cov_threshold == 2) {
+        // every valid position is good unless it is the single occurrence of a count-1 key
+        CU(cudaMemcpyAsync(c->d_good21, c->d_valid, sizeof(uint32_t) * c->n_words, cudaMemcpyDeviceToDevice, c->stream));
+        uint64_t nc = c->h_stats.n_cand;
+        if (nc) {
+            cand_check_kernel<<<c->grid(), 256, 0, c->stream>>>(c->d_table, c->d_cand_slot, c->d_cand_pos, nc, cov_threshold, c->ovf(), c->d_stats, c->d_good21);
+            c->launches++;
+        }
+    } else {
+        const uint32_t *proven = (!c->binned && cov_threshold == 2) ? c->d_proven2 : nullptr;
+        if (c->d_nmask)
+            flags21_kernel<true><<<c->grid(), 256, 0, c->stream>>>(c->d_packed, c->d_rend, c->d_nmask, c->n_words, c->table(), c->ovf(), c->d_stats, cov_threshold, proven, c->d_good21);
+        else
+            flags21_kernel<false><<<c->grid(), 256, 0, c->stream>>>(c->d_packed, c->d_rend, nullptr, c->n_words, c->table(), c->ovf(), c->d_stats, cov_threshold, proven, c->d_good21);
+        c->launches++;
+    }
     CU(cudaGetLastError());
     CU(cudaEventRecord(c->ev[3], c->stream));
 
@@ -601,25 +1004,45 @@ int p3_make_bf(p3_ctx *c, uint32_t k, uint64_t filter_size, uint32_t num_hashes,
         CU(cudaMemsetAsync(&c->d_stats->err_table_full, 0, sizeof(unsigned), c->stream));
         CU(cudaEventRecord(c->ev[4], c->stream));
         if (c->d_nmask)
-            makebf_kernel<true><<<c->grid(), 256, 0, c->stream>>>(c->d_packed, c->d_nmask, c->d_solid, c->n_words, (int)k, c->d_set, nbs, c->d_list, c->list_cap, c->bloom(), c->d_stats);
+            makebf_kernel<true><<<c->grid(), 256, 0, c->stream>>>(c->d_packed, c->d_nmask, c->d_solid, c->n_words, (int)k, c->d_set, nbs, c->d_stats);
         else
-            makebf_kernel<false><<<c->grid(), 256, 0, c->stream>>>(c->d_packed, nullptr, c->d_solid, c->n_words, (int)k, c->d_set, nbs, c->d_list, c->list_cap, c->bloom(), c->d_stats);
-        c->launches++;
+            makebf_kernel<false><<<c->grid(), 256, 0, c->stream>>>(c->d_packed, nullptr, c->d_solid, c->n_words, (int)k, c->d_set, nbs, c->d_stats);
+        compact_set_kernel<<<c->grid(), 256, 0, c->stream>>>(c->d_set, nbs * 4, c->d_list, c->list_cap, c->d_stats);
+        c->launches += 2;
         CU(cudaGetLastError());
+        rc = pull_stats(c);
+        if (rc) return rc;
+        if (c->h_stats.err_table_full) {
+            if (attempt >= 16) return fail(P3_ERR_TABLE_FULL, "solid k-mer set full after growing");
+            solid_slots = std::max<uint64_t>(solid_slots * 4, 1024);
+            continue;
+        }
+        {   // dense BF.add over the distinct k-mers, one pass per L2-sized filter segment
+            uint64_t nd = c->h_stats.n_distinct_solid;
+            uint64_t seg_bits = 40ull << 23;                       // 40 MB of filter per pass
+            uint64_t n_seg = (filter_size + seg_bits - 1) / seg_bits;
+            if (n_seg > 16 || nd * num_hashes < (1u << 22)) { n_seg = 1; seg_bits = filter_size; }   // huge filter / tiny job: one pass
+            else seg_bits = ((filter_size + n_seg - 1) / n_seg + 31) / 32 * 32;
+            CU(cudaEventRecord(c->ev[14], c->stream));
+            for (uint64_t sg = 0; sg < n_seg && nd; sg++) {
+                bloom_list_kernel<<<c->grid(), 256, 0, c->stream>>>(c->d_list, nd, c->bloom(), sg * seg_bits, std::min<uint64_t>((sg + 1) * seg_bits, filter_size));
+                c->launches++;
+            }
+            CU(cudaGetLastError());
+            CU(cudaEventRecord(c->ev[15], c->stream));
+        }
         CU(cudaEventRecord(c->ev[5], c->stream));
         seeds_kernel<<<c->grid(4), 256, 0, c->stream>>>(c->d_off, c->n_reads, c->d_solid, (int)k, c->d_seed);
         c->launches++;
         CU(cudaEventRecord(c->ev[6], c->stream));
-        rc = pull_stats(c);
-        if (rc) return rc;
-        if (!c->h_stats.err_table_full) break;
-        if (attempt >= 16) return fail(P3_ERR_TABLE_FULL, "solid k-mer set full after growing");
-        solid_slots = std::max<uint64_t>(solid_slots * 4, 1024);
+        CU(cudaStreamSynchronize(c->stream));
+        break;
     }
+    CU(cudaEventElapsedTime(&c->ms_bloom, c->ev[14], c->ev[15]));
     CU(cudaEventElapsedTime(&c->ms[1], c->ev[2], c->ev[3]));
     CU(cudaEventElapsedTime(&c->ms[2], c->ev[4], c->ev[5]));
     CU(cudaEventElapsedTime(&c->ms[3], c->ev[5], c->ev[6]));
-    c->have_bf = true; c->have_solid = true; c->have_adj = false;
+    c->have_bf = true; c->have_solid = true; c->have_adj = false; c->set_valid = true;
     return P3_OK;
 }
 
@@ -643,6 +1066,7 @@ int p3_bf_import(p3_ctx *c, uint32_t k, uint64_t filter_size, uint32_t num_hashe
     CU(cudaSetDevice(c->device));
     int rc = alloc_bloom(c, k, filter_size, num_hashes);
     if (rc) return rc;
+    c->set_valid = false; c->have_solid = false; c->have_adj = false;
     CU(cudaMemsetAsync(c->d_bloom, 0, sizeof(uint32_t) * c->bloom_words, c->stream));
     if (h_bits) CU(cudaMemcpyAsync(c->d_bloom, h_bits, (filter_size + 7) / 8, cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));
@@ -732,7 +1156,7 @@ int p3_dbg_adjacency(p3_ctx *c) {
     CU(cudaMemsetAsync(&c->d_stats->n_edges, 0, sizeof(unsigned long long), c->stream));
     CU(cudaEventRecord(c->ev[7], c->stream));
     if (n) {
-        adjacency_kernel<<<c->grid(), 256, 0, c->stream>>>(c->d_list, n, (int)c->k, c->bloom(), c->d_adj, c->d_stats);
+        adjacency_kernel<<<c->grid(), 256, 0, c->stream>>>(c->d_list, n, (int)c->k, c->bloom(), c->set_valid ? c->d_set : nullptr, c->nbs, c->d_adj, c->d_stats);
         c->launches++;
         CU(cudaGetLastError());
     }
@@ -777,7 +1201,7 @@ int p3_check_directions(p3_ctx *c, const uint64_t *h_kmers, uint64_t n, uint8_t 
     CU(cudaMalloc(&dout, n));
     uint64_t warps = (n + 3) / 4;
     unsigned blocks = (unsigned)std::min<uint64_t>((warps + 7) / 8, (uint64_t)c->grid());
-    adjacency_kernel<<<blocks, 256, 0, c->stream>>>(dk, n, (int)c->k, c->bloom(), dout, nullptr);
+    adjacency_kernel<<<blocks, 256, 0, c->stream>>>(dk, n, (int)c->k, c->bloom(), c->set_valid ? c->d_set : nullptr, c->nbs, dout, nullptr);
     c->launches++;
     CU(cudaMemcpyAsync(h_mask, dout, n, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
@@ -803,6 +1227,14 @@ int p3_assemble_hot_path(p3_ctx *c, const uint64_t *h_packed, uint64_t total_bas
     return p3_dbg_adjacency(c);
 }
 
+int p3_count_substage_ms(p3_ctx *c, float ms[4], uint32_t *parts, uint64_t *chunks) {
+    if (!c) return fail(P3_ERR_ARG, "null ctx");
+    for (int i = 0; i < 3; i++) ms[i] = c->binned ? c->ms_sub[i] : 0.f;
+    ms[3] = c->ms_bloom;
+    if (parts) *parts = c->parts;
+    if (chunks) *chunks = c->binned ? c->n_chunks : 0;
+    return P3_OK;
+}
 int p3_stage_ms(p3_ctx *c, float ms[5]) {
     if (!c) return fail(P3_ERR_ARG, "null ctx");
     for (int i = 0; i < 5; i++) ms[i] = c->ms[i];

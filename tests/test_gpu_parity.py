@@ -61,6 +61,42 @@ def test_pipeline_small(ctx, oracle, k):
     _full_check(ctx, oracle, reads, k)
 
 
+@pytest.mark.parametrize("env", [
+    {"P3_COUNT_MODE": "direct"},
+    {"P3_PARTS": "1"},
+    {"P3_PARTS": "7"},
+    {"P3_PARTS": "1024", "P3_BIN_BUDGET_BYTES": "200000"},   # many partitions, many chunks
+    {"P3_PARTS": "3", "P3_BIN_BUDGET_BYTES": "1"},            # one tile per chunk
+])
+def test_count_modes(ctx, oracle, env, monkeypatch):
+    """direct table vs binned/partitioned count (any partition count, any chunking) are all exact"""
+    for k_, v_ in env.items():
+        monkeypatch.setenv(k_, v_)
+    reads = _dataset(61, genome=6000, cov=14, rl=110, err=0.01)
+    _full_check(ctx, oracle, reads, 32)
+    _full_check(ctx, oracle, [b"A" * 300, b"T" * 250, b"ACGT" * 50] * 20 + reads[:200], 25, m=30011)
+
+
+def test_threshold_other_than_two(ctx, oracle):
+    """cov_threshold != 2 takes the full-lookup path; 1 makes every k-mer solid, 3 fewer"""
+    reads = _dataset(62, genome=3000, cov=12, rl=90, err=0.01)
+    seq, off = reads_to_arrays(reads)
+    ctx.load_ascii(seq, off)
+    ctx.count_short_kmers()
+    a1, _ = ctx.make_bf(25, 50021, 10, cov_threshold=1)
+    assert a1 == sum(len(r) - 24 for r in reads)
+    a2, _ = ctx.make_bf(25, 50021, 10, cov_threshold=2)
+    a3, _ = ctx.make_bf(25, 50021, 10, cov_threshold=3)
+    assert a1 > a2 > a3 > 0
+    okeys, ocounts = oracle.count_short_kmers(seq, off)
+    _, _, _, oadds = oracle.make_bf(seq, off, 25, okeys, ocounts, 50021, 10)
+    assert a2 == oadds
+    # threshold 3 == oracle with every count-2 key demoted to 1
+    dem = ocounts.copy(); dem[dem == 2] = 1
+    _, _, _, oadds3 = oracle.make_bf(seq, off, 25, okeys, dem, 50021, 10)
+    assert a3 == oadds3
+
+
 def test_pipeline_error_free(ctx, oracle):
     """configs[0] shape in miniature: error-free reads, every k-mer solid"""
     reads = _dataset(77, genome=20000, cov=30, rl=150, err=0.0)
