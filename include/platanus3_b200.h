@@ -123,6 +123,13 @@ int p3_double_hash(p3_ctx *ctx, uint32_t k, const uint64_t *h_kmers, uint64_t n,
  * (0-3 left extension by A,C,G,T; 4-7 right extension). */
 int p3_dbg_adjacency(p3_ctx *ctx);
 int p3_dbg_stats(p3_ctx *ctx, uint64_t *n_kmers, uint64_t *n_edges);
+/* Closes the k-mer table under recorded neighbours so that a host walk (DeBruijnGraph::MakeDBG,
+ * reference src/DeBruijnGraph.cpp:94-297) never needs a k-mer the table lacks: neighbours that
+ * answer possiblyContains but are not solid (Bloom false positives) are added with their own
+ * adjacency, to a fixed point. h_roots (optional): oriented k-mers the walk starts from (the seeds),
+ * which get an entry even when they are not solid (a seed with a non-ACGT base is recorded in
+ * forward orientation only). p3_dbg_export then returns solid + root + added k-mers. */
+int p3_dbg_close(p3_ctx *ctx, const uint64_t *h_roots, uint64_t n_roots, uint64_t *n_total);
 /* distinct solid k-mers (n*W words, unsorted) and their adjacency bytes */
 int p3_dbg_export(p3_ctx *ctx, uint64_t *h_kmers, uint8_t *h_adj, uint64_t cap, uint64_t *n);
 /* CheckDirections on arbitrary ORIENTED k-mers (ignored_direction = -1) */
@@ -138,6 +145,32 @@ int p3_assemble_hot_path(p3_ctx *ctx, const uint64_t *h_packed, uint64_t total_b
                          const uint64_t *h_off, uint64_t n_reads, const uint32_t *h_nmask,
                          uint64_t all_bases, uint32_t k, uint64_t filter_size, uint32_t num_hashes,
                          uint64_t table_slots, uint64_t solid_slots);
+
+/* ---- host side of the drop-in (row f: callers / formats either side of the path) ------------- */
+
+/* ReadFile::LoadFile / LoadFasta / LoadFastq, reference src/Load.cpp:32-103: FASTA or single-line
+ * FASTQ chosen by the first byte, reads shorter than k dropped, records with the same name line
+ * collapse to the last one while all_bases counts every record. The reads come back as ASCII,
+ * offsets and (pinned, when a GPU is present) 2-bit staging ready for p3_reads_upload. */
+typedef struct p3_reads p3_reads;
+int p3_load_file(const char *path, uint32_t k, p3_reads **out);
+void p3_reads_free(p3_reads *r);
+uint64_t p3_reads_count(const p3_reads *r);
+uint64_t p3_reads_all_bases(const p3_reads *r);
+uint64_t p3_reads_total_bases(const p3_reads *r);
+const uint64_t *p3_reads_offsets(const p3_reads *r);
+const uint64_t *p3_reads_packed(const p3_reads *r);
+const uint32_t *p3_reads_nmask(const p3_reads *r);   /* NULL when every base is ACGT */
+const char *p3_reads_ascii(const p3_reads *r);
+
+/* main() + Assemble<>, reference main.cpp:11-31 and src/Assemble.cpp:7-28, for one read file:
+ * Load, filter sizing, the GPU hot path, then on the host the unitig walk (MakeDBG with the
+ * reference's -t 1 order), CountNodeCoverage and PrintGraph. Writes the GFA to gfa_path and the
+ * reference's milestone log lines to log_path (either may be NULL). stats (optional, 8 values):
+ * reads, all_bases, distinct 21-mers, solid k-mers, table k-mers after closure, junctions, joints,
+ * straights. */
+int p3_assemble_file(const char *read_path, uint32_t k, uint64_t m, int threads, int device,
+                     const char *gfa_path, const char *log_path, uint64_t *stats);
 
 /* device milliseconds of the last run of each stage (CUDA events on the context stream):
  * ms[0]=count21 ms[1]=coverage flags ms[2]=solid+bloom ms[3]=seeds ms[4]=adjacency */

@@ -19,7 +19,9 @@ SYMBOLS = [
     "p3_reads_upload", "p3_reads_attach", "p3_count_short_kmers", "p3_short_kmer_stats",
     "p3_short_kmer_export", "p3_short_kmer_lookup", "p3_make_bf", "p3_make_bf_stats", "p3_bf_export",
     "p3_bf_import", "p3_seed_export", "p3_solid_flags_export", "p3_bf_add", "p3_bf_possibly_contains",
-    "p3_double_hash", "p3_dbg_adjacency", "p3_dbg_stats", "p3_dbg_export", "p3_check_directions",
+    "p3_double_hash", "p3_dbg_adjacency", "p3_dbg_stats", "p3_dbg_close", "p3_dbg_export", "p3_check_directions",
+    "p3_load_file", "p3_reads_free", "p3_reads_count", "p3_reads_all_bases", "p3_reads_total_bases",
+    "p3_reads_offsets", "p3_reads_packed", "p3_reads_nmask", "p3_reads_ascii", "p3_assemble_file",
     "p3_assemble_hot_path", "p3_stage_ms", "p3_count_substage_ms", "p3_launch_count", "p3_bf_params",
 ]
 
@@ -71,9 +73,19 @@ def lib():
         L.p3_double_hash.argtypes = [vp, u32, vp, u64, vp]
         L.p3_dbg_adjacency.argtypes = [vp]
         L.p3_dbg_stats.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
+        L.p3_dbg_close.argtypes = [vp, vp, u64, C.POINTER(u64)]
         L.p3_dbg_export.argtypes = [vp, vp, vp, u64, C.POINTER(u64)]
         L.p3_check_directions.argtypes = [vp, vp, u64, vp]
         L.p3_assemble_hot_path.argtypes = [vp, vp, u64, vp, u64, vp, u64, u32, u64, u32, u64, u64]
+        L.p3_load_file.argtypes = [C.c_char_p, u32, C.POINTER(vp)]
+        L.p3_reads_free.argtypes = [vp]
+        for nm in ("p3_reads_count", "p3_reads_all_bases", "p3_reads_total_bases"):
+            getattr(L, nm).restype = u64
+            getattr(L, nm).argtypes = [vp]
+        for nm in ("p3_reads_offsets", "p3_reads_packed", "p3_reads_nmask", "p3_reads_ascii"):
+            getattr(L, nm).restype = vp
+            getattr(L, nm).argtypes = [vp]
+        L.p3_assemble_file.argtypes = [C.c_char_p, u32, u64, i32, i32, C.c_char_p, C.c_char_p, C.POINTER(u64)]
         L.p3_stage_ms.argtypes = [vp, C.POINTER(C.c_float)]
         L.p3_count_substage_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(u32), C.POINTER(u64)]
         L.p3_launch_count.restype = u64
@@ -115,6 +127,35 @@ def pack_reads(seq, off, want_mask=True):
     bad = C.c_int(0)
     check(lib().p3_pack_reads(_ptr(seq) if total else None, _ptr(off), n_reads, _ptr(packed), _ptr(nmask), C.byref(bad)))
     return packed, (nmask if (bad.value and want_mask) else None)
+
+
+def load_file(path, k):
+    """ReadFile::LoadFile (reference src/Load.cpp:32) -> dict(seq uint8, off uint64, all_bases, packed, nmask)"""
+    h = C.c_void_p()
+    check(lib().p3_load_file(path.encode(), k, C.byref(h)))
+    L = lib()
+    try:
+        n = L.p3_reads_count(h)
+        total = L.p3_reads_total_bases(h)
+        off = np.ctypeslib.as_array(C.cast(L.p3_reads_offsets(h), C.POINTER(C.c_uint64)), (n + 1,)).copy()
+        seq = np.ctypeslib.as_array(C.cast(L.p3_reads_ascii(h), C.POINTER(C.c_uint8)), (max(total, 1),))[:total].copy()
+        words = L.p3_packed_words(total)
+        packed = np.ctypeslib.as_array(C.cast(L.p3_reads_packed(h), C.POINTER(C.c_uint64)), (words,)).copy()
+        nm = L.p3_reads_nmask(h)
+        nmask = np.ctypeslib.as_array(C.cast(nm, C.POINTER(C.c_uint32)), (words,)).copy() if nm else None
+        return dict(seq=seq, off=off, all_bases=L.p3_reads_all_bases(h), packed=packed, nmask=nmask)
+    finally:
+        L.p3_reads_free(h)
+
+
+def assemble_file(path, k, m=0, threads=1, device=0, gfa_path=None, log_path=None):
+    """main() + Assemble<> for one read file; returns the 8 run statistics"""
+    st = (C.c_uint64 * 8)()
+    check(lib().p3_assemble_file(path.encode(), k, m, threads, device,
+                                 gfa_path.encode() if gfa_path else None,
+                                 log_path.encode() if log_path else None, st))
+    names = ("reads", "all_bases", "distinct_21mers", "solid_kmers", "table_kmers", "junctions", "joints", "straights")
+    return dict(zip(names, [int(x) for x in st]))
 
 
 class Context:
@@ -239,12 +280,17 @@ class Context:
         check(self.L.p3_dbg_stats(self.h, C.byref(a), C.byref(b)))
         return a.value, b.value
 
-    def dbg_export(self, sort=True):
-        a, b = C.c_uint64(), C.c_uint64()
-        check(self.L.p3_make_bf_stats(self.h, C.byref(a), C.byref(b)))
-        kmers = np.zeros(max(b.value, 1), np.uint64)
-        adj = np.zeros(max(b.value, 1), np.uint8)
+    def dbg_close(self, roots=None):
         n = C.c_uint64()
+        roots = None if roots is None else np.ascontiguousarray(roots, np.uint64)
+        check(self.L.p3_dbg_close(self.h, _ptr(roots), 0 if roots is None else len(roots), C.byref(n)))
+        return n.value
+
+    def dbg_export(self, sort=True):
+        n = C.c_uint64()
+        self.L.p3_dbg_export(self.h, None, None, 0, C.byref(n))   # size query (capacity error ignored)
+        kmers = np.zeros(max(n.value, 1), np.uint64)
+        adj = np.zeros(max(n.value, 1), np.uint8)
         check(self.L.p3_dbg_export(self.h, _ptr(kmers), _ptr(adj), len(kmers), C.byref(n)))
         kmers, adj = kmers[: n.value], adj[: n.value]
         if sort:

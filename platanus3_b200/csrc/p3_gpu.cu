@@ -492,6 +492,69 @@ adjacency_kernel(const uint64_t *__restrict__ kmers, uint64_t n, int k, Bloom bf
     if (lane == 0 && e && st) atomicAdd(&st->n_edges, e);
 }
 
+// Closure of the k-mer set under recorded neighbours (for the host unitig walk): the walk only
+// ever moves to a neighbour that CheckDirections reported, i.e. one whose possiblyContains is true.
+// Solid k-mers are in the set already; a reported neighbour that is NOT in the set is a Bloom
+// false positive ("phantom"). Phantoms are inserted and appended to the list so that the next
+// adjacency pass covers them too; iterating to a fixed point gives the walk a table that answers
+// every CheckDirections it can possibly ask, with the reference's false positives included.
+__global__ void __launch_bounds__(256)
+closure_kernel(uint64_t *list, const uint8_t *__restrict__ adj, uint64_t lo, uint64_t hi, int k,
+               uint64_t *set, uint64_t nbs, uint64_t list_cap, Stats *st) {
+    __shared__ unsigned s_wtot[8];
+    __shared__ unsigned long long s_base;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint64_t stride = gridDim.x * (uint64_t)blockDim.x;
+    uint64_t n_round = (hi - lo + stride - 1) / stride;
+    for (uint64_t r = 0; r < n_round; r++) {
+        uint64_t i = lo + r * stride + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+        uint64_t fresh[8];
+        unsigned mine = 0;
+        if (i < hi) {
+            uint64_t km = list[i];
+            unsigned a = adj[i];
+            while (a) {
+                int d = __ffs(a) - 1;
+                a &= a - 1;
+                uint64_t nb = neighbour(km, d, k);
+                uint64_t rc = revcomp(nb, k);
+                uint64_t c = nb <= rc ? nb : rc;
+                int ins = set_insert(set, nbs, c);
+                if (ins > 0) fresh[mine++] = c;
+                else if (ins < 0) atomicExch(&st->err_table_full, 1u);
+            }
+        }
+        unsigned incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { unsigned v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
+        if (lane == 31) s_wtot[wid] = incl;
+        __syncthreads();
+        unsigned wbase = 0, total = 0;
+#pragma unroll
+        for (int q = 0; q < 8; q++) { unsigned t = s_wtot[q]; if (q < wid) wbase += t; total += t; }
+        if (threadIdx.x == 0 && total) s_base = atomicAdd(&st->n_distinct_solid, (unsigned long long)total);
+        __syncthreads();
+        unsigned long long j = s_base + wbase + incl - mine;
+        for (unsigned q = 0; q < mine; q++, j++)
+            if (j < list_cap) list[j] = fresh[q];
+        __syncthreads();
+    }
+}
+
+// walk roots (seed k-mers, oriented): make sure their canonical form has a table entry
+__global__ void roots_kernel(const uint64_t *__restrict__ roots, uint64_t n, int k, uint64_t *set, uint64_t nbs,
+                             uint64_t *list, uint64_t list_cap, Stats *st) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t km = roots[i], rc = revcomp(km, k);
+    uint64_t c = km <= rc ? km : rc;
+    int ins = set_insert(set, nbs, c);
+    if (ins > 0) {
+        unsigned long long j = atomicAdd(&st->n_distinct_solid, 1ULL);
+        if (j < list_cap) list[j] = c;
+    } else if (ins < 0) atomicExch(&st->err_table_full, 1u);
+}
+
 // ---- small batch / export kernels -------------------------------------------------------------------
 __global__ void export_counts_kernel(const uint64_t *__restrict__ table, uint64_t n_slots, Ovf ovf, Stats *st,
                                      uint64_t thr, uint64_t *keys, uint64_t *counts, uint64_t cap) {
@@ -585,6 +648,7 @@ struct p3_ctx {
     bool have_bf = false, have_solid = false;
     // adjacency
     uint8_t *d_adj = nullptr; uint64_t adj_cap = 0; bool have_adj = false;
+    uint64_t n_solid = 0, n_closed = 0; bool closed = false;
     Stats *d_stats = nullptr; Stats h_stats;
     cudaEvent_t ev[16];
     float ms[5] = {0, 0, 0, 0, 0};
@@ -620,6 +684,7 @@ static int pull_stats(p3_ctx *c) {
 extern "C" {
 
 const char *p3_last_error(void) { return g_err.c_str(); }
+void p3_internal_set_error(const char *msg) { g_err = msg ? msg : ""; }
 int p3_version(void) { return 100; }
 int p3_device_count(void) {
     int n = 0;
@@ -1165,12 +1230,69 @@ int p3_dbg_adjacency(p3_ctx *c) {
     if (rc) return rc;
     CU(cudaEventElapsedTime(&c->ms[4], c->ev[7], c->ev[8]));
     c->have_adj = true;
+    c->n_solid = n; c->n_closed = n; c->closed = false;
+    return P3_OK;
+}
+
+// fixed point of "add every recorded neighbour" (see closure_kernel), seeded with the solid k-mers
+// and the given walk roots; *n_total = solid + root + phantom k-mers
+int p3_dbg_close(p3_ctx *c, const uint64_t *h_roots, uint64_t n_roots, uint64_t *n_total) {
+    if (!c || !c->have_adj) return fail(P3_ERR_STATE, "p3_dbg_close: run p3_dbg_adjacency first");
+    CU(cudaSetDevice(c->device));
+    // from here on the set also holds k-mers that need not answer possiblyContains (roots), so it
+    // must not short-cut Bloom queries any more
+    c->set_valid = false;
+    auto adjacency_range = [&](uint64_t from, uint64_t to) -> int {
+        if (to <= from) return P3_OK;
+        uint64_t nn = to - from, warps = (nn + 3) / 4;
+        unsigned blocks = (unsigned)std::min<uint64_t>((warps + 7) / 8, (uint64_t)c->grid());
+        adjacency_kernel<<<blocks, 256, 0, c->stream>>>(c->d_list + from, nn, (int)c->k, c->bloom(), nullptr, 0, c->d_adj + from, nullptr);
+        c->launches++;
+        CU(cudaGetLastError());
+        return P3_OK;
+    };
+    auto check_full = [&](uint64_t n2) -> int {
+        if (c->h_stats.err_table_full || n2 > c->list_cap || n2 > c->adj_cap)
+            return fail(P3_ERR_TABLE_FULL, "p3_dbg_close: k-mer set full (false-positive closure too large; raise solid_slots or -m)");
+        return P3_OK;
+    };
+    uint64_t hi = c->n_closed;
+    if (h_roots && n_roots) {
+        uint64_t *dr = nullptr;
+        CU(cudaMalloc(&dr, sizeof(uint64_t) * n_roots));
+        CU(cudaMemcpyAsync(dr, h_roots, sizeof(uint64_t) * n_roots, cudaMemcpyHostToDevice, c->stream));
+        roots_kernel<<<(unsigned)((n_roots + 255) / 256), 256, 0, c->stream>>>(dr, n_roots, (int)c->k, c->d_set, c->nbs, c->d_list, c->list_cap, c->d_stats);
+        c->launches++;
+        int rc = pull_stats(c);
+        cudaFree(dr);
+        if (rc) return rc;
+        uint64_t n1 = c->h_stats.n_distinct_solid;
+        if ((rc = check_full(n1))) return rc;
+        if ((rc = adjacency_range(hi, n1))) return rc;
+        hi = n1;
+    }
+    uint64_t lo = c->closed ? c->n_closed : 0;
+    for (int round = 0; lo < hi; round++) {
+        if (round > 200) return fail(P3_ERR_TABLE_FULL, "p3_dbg_close: no fixed point (filter saturated: the reference walk would not terminate either)");
+        closure_kernel<<<c->grid(), 256, 0, c->stream>>>(c->d_list, c->d_adj, lo, hi, (int)c->k, c->d_set, c->nbs, c->list_cap, c->d_stats);
+        c->launches++;
+        CU(cudaGetLastError());
+        int rc = pull_stats(c);
+        if (rc) return rc;
+        uint64_t n2 = c->h_stats.n_distinct_solid;
+        if ((rc = check_full(n2))) return rc;
+        if ((rc = adjacency_range(hi, n2))) return rc;
+        lo = hi; hi = n2;
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    c->n_closed = hi; c->closed = true;
+    if (n_total) *n_total = hi;
     return P3_OK;
 }
 
 int p3_dbg_stats(p3_ctx *c, uint64_t *n_kmers, uint64_t *n_edges) {
     if (!c || !c->have_adj) return fail(P3_ERR_STATE, "no adjacency result");
-    if (n_kmers) *n_kmers = c->h_stats.n_distinct_solid;
+    if (n_kmers) *n_kmers = c->n_solid;
     if (n_edges) *n_edges = c->h_stats.n_edges;
     return P3_OK;
 }
@@ -1178,7 +1300,7 @@ int p3_dbg_stats(p3_ctx *c, uint64_t *n_kmers, uint64_t *n_edges) {
 int p3_dbg_export(p3_ctx *c, uint64_t *h_kmers, uint8_t *h_adj, uint64_t cap, uint64_t *n) {
     if (!c || !c->have_solid) return fail(P3_ERR_STATE, "p3_dbg_export: no make_bf result");
     CU(cudaSetDevice(c->device));
-    uint64_t nd = c->h_stats.n_distinct_solid;
+    uint64_t nd = c->have_adj ? c->n_closed : c->h_stats.n_distinct_solid;
     if (n) *n = nd;
     if (cap < nd) return fail(P3_ERR_ARG, "p3_dbg_export: capacity too small");
     if (nd == 0) return P3_OK;

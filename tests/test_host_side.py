@@ -1,0 +1,122 @@
+"""Host side of the drop-in: Load parity on CPU; the whole run (GPU hot path + host walk +
+coverage + GFA) against the golden fixtures made from the reference with -t 1."""
+import glob
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from platanus3_b200 import _lib, synth
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLD, "*.npz")))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _load(name):
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    return g, os.path.join(GOLD, str(g["read_file"]))
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_load_file_matches_oracle(oracle, name):
+    """ReadFile::LoadFile: same reads, same all_bases, 2-bit staging == p3_pack_reads of them"""
+    g, path = _load(name)
+    k = int(g["k"])
+    mine = _lib.load_file(path, k)
+    seq, off, all_bases = oracle.load_reads(path, k)
+    assert mine["all_bases"] == all_bases == int(g["all_bases"])
+    assert len(mine["off"]) - 1 == int(g["n_reads"])
+    a = sorted(mine["seq"][int(mine["off"][i]):int(mine["off"][i + 1])].tobytes() for i in range(len(mine["off"]) - 1))
+    b = sorted(seq[int(off[i]):int(off[i + 1])].tobytes() for i in range(len(off) - 1))
+    assert a == b
+    packed, nmask = _lib.pack_reads(mine["seq"], mine["off"])
+    assert np.array_equal(packed, mine["packed"])
+    assert (nmask is None) == (mine["nmask"] is None)
+    if nmask is not None:
+        assert np.array_equal(nmask, mine["nmask"])
+
+
+def test_load_file_edge_cases(tmp_path):
+    p = tmp_path / "empty.fasta"
+    p.write_bytes(b"")
+    assert len(_lib.load_file(str(p), 21)["off"]) == 1
+    p = tmp_path / "noheader.fasta"
+    p.write_bytes(b"ACGTACGTACGTACGTACGTACGTACGT\n")
+    assert len(_lib.load_file(str(p), 21)["off"]) == 1          # first byte is neither '>' nor '@'
+    p = tmp_path / "crlf_.fasta"
+    p.write_bytes(b">a\r\nACGTACGTACGTACGTACGTACGT\r\n")
+    r = _lib.load_file(str(p), 21)                                # '\r' stays in the read, like std::getline
+    assert r["seq"].tobytes() == b"ACGTACGTACGTACGTACGTACGT\r" and r["nmask"] is not None
+    with pytest.raises(_lib.P3Error):
+        _lib.load_file("a.fa", 21)                                 # name shorter than 5 (Load.cpp:26)
+    with pytest.raises(_lib.P3Error):
+        _lib.load_file(str(tmp_path / "missing.fasta"), 21)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", CASES)
+def test_assemble_file_matches_reference_gfa(name, tmp_path):
+    """GFA (as a set of lines), node counts and seed count equal the reference's -t 1 run"""
+    g, path = _load(name)
+    gfa, log = str(tmp_path / "out.gfa"), str(tmp_path / "out.log")
+    st = _lib.assemble_file(path, int(g["k"]), m=int(g["m"]), threads=1, gfa_path=gfa, log_path=log)
+    assert (st["junctions"], st["joints"], st["straights"]) == (int(g["n_junctions"]), int(g["n_joints"]), int(g["n_straights"]))
+    assert st["reads"] == int(g["n_reads"]) and st["all_bases"] == int(g["all_bases"])
+    assert st["distinct_21mers"] == len(g["keys"])
+    assert sorted(open(gfa).read().splitlines()) == [str(x) for x in g["gfa"]]
+    lines = open(log).read().splitlines()
+    assert "seed kmer num= %d" % len(g["seeds"]) in lines
+    assert "filter_size : %d" % int(g["filter_size"]) in lines and "num_hashes : %d" % int(g["num_hashes"]) in lines
+    assert lines[-1] == "finish"
+
+
+@pytest.mark.gpu
+def test_cli_drop_in(tmp_path):
+    """platanus3-compatible command line: -i -k -t [-m], ./platanus3.log and ./de_bruijn_graph.gfa in cwd"""
+    g, path = _load("k25_err")
+    exe = os.path.join(ROOT, "platanus3_b200", "platanus3_b200")
+    r = subprocess.run([exe, "-i", path, "-k", "25", "-t", "4"], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert sorted((tmp_path / "de_bruijn_graph.gfa").read_text().splitlines()) == [str(x) for x in g["gfa"]]
+    assert (tmp_path / "platanus3.log").read_text().splitlines()[-1] == "finish"
+    r = subprocess.run([exe], cwd=tmp_path, capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and r.stdout.startswith("Usage: platanus3 -i")      # main.cpp:16-19
+    r = subprocess.run([exe, "-i", path, "-k", "63"], cwd=tmp_path, capture_output=True, text=True, timeout=60)
+    assert r.returncode == 1 and "not supported" in r.stderr
+
+
+@pytest.mark.gpu
+def test_closure_covers_every_reported_neighbour(oracle):
+    """after p3_dbg_close every neighbour the table reports is itself in the table"""
+    from _checkers import reads_to_arrays
+    k = 27
+    gnm = synth.random_genome(8000, 9)
+    reads = synth.reads_as_bytes(synth.simulate_reads(gnm, 30, 100, 0.01, 10))
+    seq, off = reads_to_arrays(reads)
+    fs, nh = _lib.estimate_bloomfilter(int(off[-1]), k)
+    with _lib.Context(0) as ctx:
+        ctx.load_ascii(seq, off)
+        ctx.count_short_kmers()
+        ctx.make_bf(k, fs, nh)
+        n_solid, _ = ctx.dbg_adjacency()
+        n_total = ctx.dbg_close()
+        kmers, adj = ctx.dbg_export()
+        assert len(kmers) == n_total >= n_solid
+        assert np.array_equal(adj, ctx.check_directions(kmers))
+        table = set(int(x) for x in kmers)
+        mask = (1 << (2 * k)) - 1
+
+        def canon(v):
+            r = 0
+            x = v
+            for _ in range(k):
+                r = (r << 2) | (3 - (x & 3))
+                x >>= 2
+            return min(v, r)
+        for km, a in list(zip(kmers.tolist(), adj.tolist()))[:: max(1, len(kmers) // 3000)]:
+            for d in range(8):
+                if (a >> d) & 1:
+                    nb = (km >> 2) | (d << (2 * k - 2)) if d < 4 else ((km << 2) | (d - 4)) & mask
+                    assert canon(nb) in table
