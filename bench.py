@@ -156,6 +156,116 @@ def cpu_baseline():
         return {"value": None, "unit": UNIT, "cores": 1, "kind": "unavailable", "sample": "failed: %r" % (e,)}
 
 
+def main_multi(args, rank, world, local, dev):
+    """N > 1: one rank per GPU; k-mers hash-partitioned by owner, NCCL all-to-all (platanus3_b200/dist.py).
+    Weak scaling: the genome grows with N (N x 100 Mbp at 50x), every rank parses the same number of
+    reads as the single-GPU run."""
+    import torch
+    import torch.distributed as dist
+    from platanus3_b200 import _lib, workload, dist as pdist
+    dist.init_process_group("nccl", device_id=dev)
+    comm = pdist.TorchDistComm()
+    genome = args.genome * world
+    wl = workload.make_reads(genome, COVERAGE / world, READ_LEN, ERR, 1234, dev, read_seed=5678 + rank)
+    torch.cuda.synchronize()
+    n_reads, total = wl["n_reads"], wl["total_bases"]
+    n_pos_local = n_reads * (READ_LEN - 20)
+    tot = comm.all_sum([total, n_pos_local])
+    all_bases, n_pos = tot
+    fs, nh = _lib.estimate_bloomfilter(all_bases, K)
+    distinct21 = genome + int(all_bases * ERR * 21 * 1.05)
+    table_slots = int(distinct21 / world / 0.55)
+    owned_slots = int(genome * 1.2 / world / 0.5)
+    solid_slots = int(min(genome, total) * 1.2 / 0.5)
+    chunk_words = 1 << 25
+    stream = torch.cuda.current_stream()
+    ctx = _lib.Context(local, ctypes.c_void_p(stream.cuda_stream))
+    ctx.attach(wl["packed"].data_ptr(), total, wl["off"].data_ptr(), n_reads, None, keep=wl)
+
+    def step():
+        return pdist.run_hot_path([ctx], comm, K, fs, nh, table_slots, solid_slots, owned_slots, chunk_words, dev)[0]
+
+    def timed(fn, steps):
+        dist.barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        out = None
+        for _ in range(steps):
+            out = fn()
+        e1.record(stream)
+        dist.barrier(); torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), out
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = ctx.launch_count()
+    total_ms, st = timed(step, args.steps)
+    launches = ctx.launch_count() - l0
+    clocks = sampler.summary()
+    sums = comm.all_sum([st["owned_distinct21"], st["n_adds"], st["owned_solid"], st["owned_edges"], st["owned_positions"], launches])
+    assert sums[4] == n_pos, (sums, n_pos)
+
+    # e2e: pinned host staging -> upload -> distributed pass -> results back to the host
+    h_packed, h_off = wl["packed"].cpu().pin_memory(), wl["off"].cpu().pin_memory()
+    ctx.close()
+    del wl
+    ctx2 = _lib.Context(local, ctypes.c_void_p(stream.cuda_stream))
+    out_bits = torch.empty((fs + 7) // 8, dtype=torch.uint8).pin_memory()
+    out_seeds = torch.empty(n_reads, dtype=torch.int64).pin_memory()
+    out_kmers = torch.empty(owned_slots, dtype=torch.int64).pin_memory()
+    out_adj = torch.empty(owned_slots, dtype=torch.uint8).pin_memory()
+    L = _lib.lib()
+    got = [0]
+
+    def step_e2e():
+        _lib.check(L.p3_reads_upload(ctx2.h, h_packed.data_ptr(), total, h_off.data_ptr(), n_reads, None))
+        ctx2.n_reads, ctx2.total_bases = n_reads, total
+        pdist.run_hot_path([ctx2], comm, K, fs, nh, table_slots, solid_slots, owned_slots, chunk_words, dev)
+        _lib.check(L.p3_bf_export(ctx2.h, out_bits.data_ptr()))
+        _lib.check(L.p3_seed_export(ctx2.h, out_seeds.data_ptr()))
+        n = ctypes.c_uint64()
+        _lib.check(L.p3_dbg_export(ctx2.h, out_kmers.data_ptr(), out_adj.data_ptr(), owned_slots, ctypes.byref(n)))
+        got[0] = n.value
+
+    step_e2e()
+    e2e_ms, _ = timed(step_e2e, args.steps)
+    h2d = h_packed.numel() * 8 + h_off.numel() * 8
+    d2h = out_bits.numel() + out_seeds.numel() * 8 + got[0] * 9
+    io = comm.all_sum([h2d, d2h])
+
+    ms_per_step = total_ms / args.steps
+    peak, peak_src = measured_peak()
+    count_ms = st["stage_ms"]["count"]
+    achieved = ALGO_BYTES_PER_KMER * (n_pos / world) / (count_ms * 1e-3) / 1e9
+    if rank == 0:
+        cfg = workload_config(world)
+        cfg["workload"] = "configs[1] scaled weakly: synthetic %d Mbp genome, %dx reads of %d bp, %.0f%% substitution errors, k=%d, %d ranks" % (
+            genome // 10 ** 6, COVERAGE, READ_LEN, ERR * 100, K, world)
+        cfg["genome_bp"] = genome
+        cfg["parallelism"] = "%d GPUs: k-mers hash-partitioned by owner, NCCL all-to-all of binned 21-mers / k-mers, filter OR-reduce" % world
+        print(json.dumps({
+            "metric": METRIC, "value": n_pos / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64", "data": "synthetic", "config": cfg,
+            "dbg_edges_per_s": sums[3] / (ms_per_step * 1e-3),
+            "counts": {"kmer_positions": n_pos, "distinct_21mers": sums[0], "bf_adds": sums[1], "solid_kmers": sums[2],
+                       "dbg_edges": sums[3], "filter_size_bits": fs, "num_hashes": nh},
+            "stage_ms": st["stage_ms"],
+            "roofline": {"kernel": "count stage (owner binning + all-to-all + L2-resident insert), rank 0", "bound": "hbm",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": peak_src, "algorithmic_bytes_per_kmer": ALGO_BYTES_PER_KMER, "kernel_ms": count_ms},
+            "e2e": {"value": n_pos / (e2e_ms / args.steps * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
+                    "h2d_bytes_per_step": io[0], "d2h_bytes_per_step": io[1]},
+            "gpu_launches": sums[5], "clocks": clocks,
+        }))
+    ctx2.close()
+    dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -174,13 +284,10 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        raise SystemExit("multi-GPU bench lands with the hash-partitioned path (DESIGN.md row e)")
+        return main_multi(args, rank, world, local, dev)
 
     genome = args.genome
     wl = workload.make_reads(genome, COVERAGE, READ_LEN, ERR, 1234 + rank, dev)

@@ -146,6 +146,40 @@ int p3_assemble_hot_path(p3_ctx *ctx, const uint64_t *h_packed, uint64_t total_b
                          uint64_t all_bases, uint32_t k, uint64_t filter_size, uint32_t num_hashes,
                          uint64_t table_slots, uint64_t solid_slots);
 
+/* ---- multi-GPU building blocks (one process per GPU; the caller moves the buffers with NCCL) -------
+ *
+ * Canonical k-mers are hash-partitioned over the ranks: the OWNER of a key counts it / de-duplicates
+ * it. Every entry point works on device pointers so that torch.distributed (or NCCL directly) can
+ * all-to-all them in place. Order of use: see platanus3_b200/dist.py or csrc/p3_multi.inc.cu.
+ * Count record = uint64 [rank:8 @47 | offset-in-word:5 @42 | canonical 21-mer:42] + uint32 word
+ * index; position record = uint64 [rank:8 @56 | stream position:56]. */
+uint32_t p3_owner_of_key(uint64_t key, uint32_t n_ranks);
+/* 21-mer positions of words [w0,w1) per owner rank (h_counts[n_ranks]); then the records themselves,
+ * grouped by owner in rank order, into caller buffers of sum(h_counts) entries */
+int p3_mg_owner_hist(p3_ctx *ctx, uint32_t n_ranks, uint64_t w0, uint64_t w1, uint64_t *h_counts);
+int p3_mg_owner_scatter(p3_ctx *ctx, uint32_t n_ranks, uint32_t my_rank, uint64_t w0, uint64_t w1,
+                        uint64_t *d_keys, uint32_t *d_words);
+/* owner side of CountShortKmer: table of table_slots 8-byte slots, then any number of record
+ * batches (each <= max_records_per_call), then _end */
+int p3_mg_count_begin(p3_ctx *ctx, uint64_t table_slots, uint64_t max_records_per_call);
+int p3_mg_count_records(p3_ctx *ctx, const uint64_t *d_keys, const uint32_t *d_words, uint64_t n);
+int p3_mg_count_end(p3_ctx *ctx);
+/* owned keys with final count < 2: their (rank, position) records grouped by source rank */
+int p3_mg_singletons(p3_ctx *ctx, uint32_t n_ranks, uint64_t *h_counts, const uint64_t **d_pos);
+/* source side of MakeBF's coverage test: plane := valid positions, minus the received positions */
+int p3_mg_cover_begin(p3_ctx *ctx);
+int p3_mg_cover_clear(p3_ctx *ctx, const uint64_t *d_pos, uint64_t n);
+/* solid plane, seeds and the locally distinct solid k-mers (solid_slots 0 = auto) */
+int p3_mg_solid_local(p3_ctx *ctx, uint32_t k, uint64_t solid_slots, uint64_t *n_adds, uint64_t *n_local);
+int p3_mg_kmer_owner_hist(p3_ctx *ctx, uint32_t n_ranks, uint64_t *h_counts);
+int p3_mg_kmer_owner_scatter(p3_ctx *ctx, uint32_t n_ranks, uint64_t *d_out);
+/* owner side of MakeBF: de-duplicate received k-mers; _end makes them this context's k-mer list,
+ * clears its filter copy and BF.adds them (then OR-reduce the copies, then p3_dbg_adjacency) */
+int p3_mg_owned_begin(p3_ctx *ctx, uint64_t owned_slots);
+int p3_mg_owned_insert(p3_ctx *ctx, const uint64_t *d_kmers, uint64_t n);
+int p3_mg_owned_end(p3_ctx *ctx, uint32_t k, uint64_t filter_size, uint32_t num_hashes, uint64_t *n_owned);
+int p3_mg_filter(p3_ctx *ctx, uint32_t **d_bits, uint64_t *n_words);
+
 /* ---- host side of the drop-in (row f: callers / formats either side of the path) ------------- */
 
 /* ReadFile::LoadFile / LoadFasta / LoadFastq, reference src/Load.cpp:32-103: FASTA or single-line

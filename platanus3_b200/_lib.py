@@ -20,6 +20,10 @@ SYMBOLS = [
     "p3_short_kmer_export", "p3_short_kmer_lookup", "p3_make_bf", "p3_make_bf_stats", "p3_bf_export",
     "p3_bf_import", "p3_seed_export", "p3_solid_flags_export", "p3_bf_add", "p3_bf_possibly_contains",
     "p3_double_hash", "p3_dbg_adjacency", "p3_dbg_stats", "p3_dbg_close", "p3_dbg_export", "p3_check_directions",
+    "p3_owner_of_key", "p3_mg_owner_hist", "p3_mg_owner_scatter", "p3_mg_count_begin", "p3_mg_count_records",
+    "p3_mg_count_end", "p3_mg_singletons", "p3_mg_cover_begin", "p3_mg_cover_clear", "p3_mg_solid_local",
+    "p3_mg_kmer_owner_hist", "p3_mg_kmer_owner_scatter", "p3_mg_owned_begin", "p3_mg_owned_insert",
+    "p3_mg_owned_end", "p3_mg_filter",
     "p3_load_file", "p3_reads_free", "p3_reads_count", "p3_reads_all_bases", "p3_reads_total_bases",
     "p3_reads_offsets", "p3_reads_packed", "p3_reads_nmask", "p3_reads_ascii", "p3_assemble_file",
     "p3_assemble_hot_path", "p3_stage_ms", "p3_count_substage_ms", "p3_launch_count", "p3_bf_params",
@@ -77,6 +81,23 @@ def lib():
         L.p3_dbg_export.argtypes = [vp, vp, vp, u64, C.POINTER(u64)]
         L.p3_check_directions.argtypes = [vp, vp, u64, vp]
         L.p3_assemble_hot_path.argtypes = [vp, vp, u64, vp, u64, vp, u64, u32, u64, u32, u64, u64]
+        L.p3_owner_of_key.restype = u32
+        L.p3_owner_of_key.argtypes = [u64, u32]
+        L.p3_mg_owner_hist.argtypes = [vp, u32, u64, u64, vp]
+        L.p3_mg_owner_scatter.argtypes = [vp, u32, u32, u64, u64, vp, vp]
+        L.p3_mg_count_begin.argtypes = [vp, u64, u64]
+        L.p3_mg_count_records.argtypes = [vp, vp, vp, u64]
+        L.p3_mg_count_end.argtypes = [vp]
+        L.p3_mg_singletons.argtypes = [vp, u32, vp, C.POINTER(vp)]
+        L.p3_mg_cover_begin.argtypes = [vp]
+        L.p3_mg_cover_clear.argtypes = [vp, vp, u64]
+        L.p3_mg_solid_local.argtypes = [vp, u32, u64, C.POINTER(u64), C.POINTER(u64)]
+        L.p3_mg_kmer_owner_hist.argtypes = [vp, u32, vp]
+        L.p3_mg_kmer_owner_scatter.argtypes = [vp, u32, vp]
+        L.p3_mg_owned_begin.argtypes = [vp, u64]
+        L.p3_mg_owned_insert.argtypes = [vp, vp, u64]
+        L.p3_mg_owned_end.argtypes = [vp, u32, u64, u32, C.POINTER(u64)]
+        L.p3_mg_filter.argtypes = [vp, C.POINTER(vp), C.POINTER(u64)]
         L.p3_load_file.argtypes = [C.c_char_p, u32, C.POINTER(vp)]
         L.p3_reads_free.argtypes = [vp]
         for nm in ("p3_reads_count", "p3_reads_all_bases", "p3_reads_total_bases"):

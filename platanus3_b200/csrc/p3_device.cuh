@@ -171,6 +171,27 @@ struct Table {
     uint32_t P;     // partitions
 };
 __device__ __forceinline__ uint32_t part_of(uint64_t h, uint32_t P) { return (uint32_t)__umul64hi(h, (uint64_t)P); }
+// owner GPU of a key (21-mer or k-mer) among n ranks: a hash independent of the table hash, so
+// that the keys one rank owns still spread over all of its table partitions and buckets
+__host__ __device__ inline uint64_t owner_mix(uint64_t k) {
+    k ^= 0x5bd1e9955bd1e995ULL;
+    k ^= k >> 33; k *= 0xff51afd7ed558ccdULL; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL; k ^= k >> 33;
+    return k;
+}
+__device__ __forceinline__ uint32_t owner_of(uint64_t key, uint32_t n) { return (uint32_t)__umul64hi(owner_mix(key), (uint64_t)n); }
+// record layouts
+//   count record   : [rank:8 @47 | offset-in-word:5 @42 | key:42]  + uint32 word index
+//   position record: [rank:8 @56 | stream position:56]
+constexpr int kRecOffShift = 42, kRecRankShift = 47, kPosRankShift = 56;
+// partition function of the tile-sort scatter kernels
+//   0 = table partition of a count record   1 = owner of a count record
+//   2 = rank field of a position record     3 = owner of a full 64-bit k-mer
+template <int PMODE> __device__ __forceinline__ uint32_t pid_of(uint64_t rec, uint32_t P) {
+    if (PMODE == 0) return part_of(fmix64(rec & kKey42), P);
+    if (PMODE == 1) return owner_of(rec & kKey42, P);
+    if (PMODE == 2) return (uint32_t)(rec >> kPosRankShift);
+    return owner_of(rec, P);
+}
 __device__ __forceinline__ uint64_t sub_of(uint64_t h, uint64_t nbp) { return ((h & 0xFFFFFFFFULL) * nbp) >> 32; }
 
 // Inserts one occurrence of key. Returns the count the key is KNOWN to have reached after this

@@ -14,6 +14,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 using namespace p3;
@@ -120,7 +121,7 @@ flags21_kernel(const uint64_t *__restrict__ packed, const uint32_t *__restrict__
 constexpr int kTileWords = 128;                 // words per scatter tile = threads per block
 constexpr int kTilePos = kTileWords * 32;       // 4096 positions
 
-template <bool HAS_MASK>
+template <bool HAS_MASK, int PMODE>
 __global__ void __launch_bounds__(256)
 hist21_kernel(const uint64_t *__restrict__ packed, const uint32_t *__restrict__ rend,
               const uint32_t *__restrict__ nmask, uint64_t w0, uint64_t w1, uint32_t P,
@@ -139,7 +140,7 @@ hist21_kernel(const uint64_t *__restrict__ packed, const uint32_t *__restrict__ 
         for (int o = 0; o < 32; o++) {
             if (((E << o) & W21) != 0) continue;
             uint64_t key = canonical_from_window(window(hi, lo, o), HAS_MASK ? window(mhi, mlo, o) : 0, kShortK);
-            atomicAdd(&sh[part_of(fmix64(key), P)], 1u);
+            atomicAdd(&sh[pid_of<PMODE>(key, P)], 1u);
         }
     }
     __syncthreads();
@@ -174,18 +175,44 @@ struct ScatterSmem {
     uint32_t total;
 };
 
-template <bool HAS_MASK>
+// exclusive scan of sm.hist[0..P) into sm.offs, one global claim per non-empty partition into
+// sm.gbase, total into sm.total. Called by all kTileWords threads between two __syncthreads().
+__device__ __forceinline__ void tile_scan_and_claim(ScatterSmem &sm, uint32_t P, unsigned long long *cursor, int tid) {
+    const uint32_t per_thread = (P + kTileWords - 1) / kTileWords;   // <= 8
+    uint32_t local = 0;
+    const uint32_t b0 = tid * per_thread;
+    for (uint32_t j = 0; j < per_thread; j++) { uint32_t i = b0 + j; if (i < P) local += sm.hist[i]; }
+    uint32_t incl = local;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, d); if ((tid & 31) >= d) incl += v; }
+    if ((tid & 31) == 31) sm.warp_tot[tid >> 5] = incl;
+    __syncthreads();
+    uint32_t wbase = 0;
+    for (int q = 0; q < (tid >> 5); q++) wbase += sm.warp_tot[q];
+    uint32_t run = wbase + incl - local;
+    for (uint32_t j = 0; j < per_thread; j++) {
+        uint32_t i = b0 + j;
+        if (i < P) {
+            uint32_t h = sm.hist[i];
+            sm.offs[i] = run;
+            if (h) sm.gbase[i] = atomicAdd(&cursor[i], (unsigned long long)h);
+            run += h;
+        }
+    }
+    if (tid == kTileWords - 1) sm.total = wbase + incl;
+}
+
+template <bool HAS_MASK, int PMODE>
 __global__ void __launch_bounds__(kTileWords)
 scatter21_kernel(const uint64_t *__restrict__ packed, const uint32_t *__restrict__ rend,
                  const uint32_t *__restrict__ nmask, uint64_t w0, uint64_t w1, uint32_t P,
                  unsigned long long *cursor, uint64_t *__restrict__ bkeys, uint32_t *__restrict__ bword,
-                 uint32_t *__restrict__ valid_plane) {
+                 uint32_t *__restrict__ valid_plane, uint64_t tag) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ScatterSmem &sm = *reinterpret_cast<ScatterSmem *>(smem_raw);
     const uint64_t W21 = ~0ULL << (64 - (kShortK - 1));
     const int tid = threadIdx.x;
     const uint64_t n_tiles = (w1 - w0 + kTileWords - 1) / kTileWords;
-    const uint32_t per_thread = (P + kTileWords - 1) / kTileWords;  // hist entries scanned per thread (<= 8)
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         for (uint32_t i = tid; i < P; i += kTileWords) sm.hist[i] = 0;
         __syncthreads();
@@ -205,42 +232,19 @@ scatter21_kernel(const uint64_t *__restrict__ packed, const uint32_t *__restrict
         for (int o = 0; o < 32; o++) {
             if (!(valid & (0x80000000u >> o))) continue;
             uint64_t key = canonical_from_window(window(hi, lo, o), HAS_MASK ? window(mhi, mlo, o) : 0, kShortK);
-            sm.rank[o][tid] = (uint16_t)atomicAdd(&sm.hist[part_of(fmix64(key), P)], 1u);
+            sm.rank[o][tid] = (uint16_t)atomicAdd(&sm.hist[pid_of<PMODE>(key, P)], 1u);
         }
         __syncthreads();
-        // exclusive scan of hist[0..P) : thread t owns entries [t*per_thread, (t+1)*per_thread)
-        {
-            uint32_t local = 0;
-            const uint32_t b0 = tid * per_thread;
-            for (uint32_t j = 0; j < per_thread; j++) { uint32_t i = b0 + j; if (i < P) local += sm.hist[i]; }
-            uint32_t incl = local;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, d); if ((tid & 31) >= d) incl += v; }
-            if ((tid & 31) == 31) sm.warp_tot[tid >> 5] = incl;
-            __syncthreads();
-            uint32_t wbase = 0;
-            for (int q = 0; q < (tid >> 5); q++) wbase += sm.warp_tot[q];
-            uint32_t run = wbase + incl - local;
-            for (uint32_t j = 0; j < per_thread; j++) {
-                uint32_t i = b0 + j;
-                if (i < P) {
-                    uint32_t h = sm.hist[i];
-                    sm.offs[i] = run;
-                    if (h) sm.gbase[i] = atomicAdd(&cursor[i], (unsigned long long)h);
-                    run += h;
-                }
-            }
-            if (tid == kTileWords - 1) sm.total = wbase + incl;
-        }
+        tile_scan_and_claim(sm, P, cursor, tid);
         __syncthreads();
         // pass 2: place records sorted by partition
 #pragma unroll 4
         for (int o = 0; o < 32; o++) {
             if (!(valid & (0x80000000u >> o))) continue;
             uint64_t key = canonical_from_window(window(hi, lo, o), HAS_MASK ? window(mhi, mlo, o) : 0, kShortK);
-            uint32_t pt = part_of(fmix64(key), P);
+            uint32_t pt = pid_of<PMODE>(key, P);
             uint32_t idx = sm.offs[pt] + sm.rank[o][tid];
-            sm.key[idx] = key | ((uint64_t)o << 42);
+            sm.key[idx] = key | ((uint64_t)o << kRecOffShift) | tag;
             sm.part[idx] = (uint16_t)pt;
             sm.loc[idx] = (uint16_t)tid;
         }
@@ -252,6 +256,71 @@ scatter21_kernel(const uint64_t *__restrict__ packed, const uint32_t *__restrict
             unsigned long long dst = sm.gbase[pt] + (i - sm.offs[pt]);
             bkeys[dst] = sm.key[i];
             bword[dst] = (uint32_t)(tile_w0 + sm.loc[i]);
+        }
+        __syncthreads();
+    }
+}
+
+// the same tile sort for records that already sit in an array (received from other ranks, k-mer
+// lists, position lists): 4096 records per tile, thread t takes records j*128+t (coalesced)
+template <int PMODE>
+__global__ void __launch_bounds__(256)
+hist_rec_kernel(const uint64_t *__restrict__ in, uint64_t n, uint32_t P, unsigned long long *__restrict__ ghist) {
+    __shared__ unsigned int sh[kMaxParts];
+    for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    uint64_t stride = gridDim.x * (uint64_t)blockDim.x;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += stride)
+        atomicAdd(&sh[pid_of<PMODE>(__ldcs(in + i), P)], 1u);
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < P; i += blockDim.x)
+        if (sh[i]) atomicAdd(&ghist[i], (unsigned long long)sh[i]);
+}
+
+template <int PMODE, bool HAS_AUX>
+__global__ void __launch_bounds__(kTileWords)
+scatter_rec_kernel(const uint64_t *__restrict__ in, const uint32_t *__restrict__ aux_in, uint64_t n, uint32_t P,
+                   unsigned long long *cursor, uint64_t *__restrict__ out, uint32_t *__restrict__ aux_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ScatterSmem &sm = *reinterpret_cast<ScatterSmem *>(smem_raw);
+    const int tid = threadIdx.x;
+    const uint64_t n_tiles = (n + kTilePos - 1) / kTilePos;
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (uint32_t i = tid; i < P; i += kTileWords) sm.hist[i] = 0;
+        __syncthreads();
+        const uint64_t t0 = tile * kTilePos;
+        uint64_t rec[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+            uint64_t i = t0 + j * kTileWords + tid;
+            rec[j] = i < n ? __ldcs(in + i) : 0;
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+            uint64_t i = t0 + j * kTileWords + tid;
+            if (i < n) sm.rank[j][tid] = (uint16_t)atomicAdd(&sm.hist[pid_of<PMODE>(rec[j], P)], 1u);
+        }
+        __syncthreads();
+        tile_scan_and_claim(sm, P, cursor, tid);
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+            uint64_t i = t0 + j * kTileWords + tid;
+            if (i < n) {
+                uint32_t pt = pid_of<PMODE>(rec[j], P);
+                uint32_t idx = sm.offs[pt] + sm.rank[j][tid];
+                sm.key[idx] = rec[j];
+                sm.part[idx] = (uint16_t)pt;
+                sm.loc[idx] = (uint16_t)(j * kTileWords + tid);
+            }
+        }
+        __syncthreads();
+        const uint32_t total = sm.total;
+        for (uint32_t i = tid; i < total; i += kTileWords) {
+            uint32_t pt = sm.part[i];
+            unsigned long long dst = sm.gbase[pt] + (i - sm.offs[pt]);
+            out[dst] = sm.key[i];
+            if (HAS_AUX) aux_out[dst] = __ldg(aux_in + t0 + sm.loc[i]);
         }
         __syncthreads();
     }
@@ -310,7 +379,10 @@ insert_bins_kernel(const uint64_t *__restrict__ bkeys, const uint32_t *__restric
 #pragma unroll
             for (int it = 0; it < kSweepPer; it++) {
                 if (created[it] != ~0ULL) {
-                    if (j < cand_cap) { cand_slot[j] = created[it]; cand_pos[j] = (uint64_t)wd[it] * 32 + ((rec[it] >> 42) & 31); }
+                    if (j < cand_cap) {
+                        cand_slot[j] = created[it];
+                        cand_pos[j] = ((uint64_t)wd[it] * 32 + ((rec[it] >> kRecOffShift) & 31)) | (((rec[it] >> kRecRankShift) & 0xFF) << kPosRankShift);
+                    }
                     j++;
                 }
             }
@@ -329,7 +401,7 @@ cand_check_kernel(const uint64_t *__restrict__ slots, const uint64_t *__restrict
         uint64_t c = v >> 42;
         if (c < thr && n_overflow) c += ovf_get(ovf, v & kKey42) << 22;
         if (c < thr) {
-            uint64_t pos = __ldcs(cand_pos + j);
+            uint64_t pos = __ldcs(cand_pos + j) & ((1ULL << kPosRankShift) - 1);
             atomicAnd(good21 + (pos >> 5), ~(0x80000000u >> (pos & 31)));
         }
     }
@@ -660,6 +732,7 @@ struct p3_ctx {
     int grid(int blocks_per_sm = 8) const { return n_sm * blocks_per_sm; }
 };
 
+static void mg_release(struct p3_ctx *c);   // p3_multi.inc.cu
 template <typename T> static void dfree(T *&p) { if (p) { cudaFree((void *)p); p = nullptr; } }
 // grow-only device buffer: reallocates only when the request exceeds the capacity, so repeated
 // runs on same-sized inputs never touch cudaMalloc/cudaFree (both synchronise the device)
@@ -750,6 +823,7 @@ void p3_destroy(p3_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    mg_release(c);
     free_reads(c); free_bf(c);
     dfree(c->d_table); dfree(c->d_proven2); dfree(c->d_bkeys); dfree(c->d_bword); dfree(c->d_valid);
     dfree(c->d_cand_slot); dfree(c->d_cand_pos); dfree(c->d_ghist); dfree(c->d_cursor); dfree(c->d_ovf_keys); dfree(c->d_ovf_wraps); dfree(c->d_stats);
@@ -820,13 +894,25 @@ static int count_direct(p3_ctx *c) {
     return P3_OK;
 }
 
+// the tile-sort kernels need > 48 KB of dynamic shared memory
+static int scatter_attrs() {
+    static bool done = false;
+    if (done) return P3_OK;
+    const int sz = (int)sizeof(ScatterSmem);
+    CU(cudaFuncSetAttribute(scatter21_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz));
+    CU(cudaFuncSetAttribute(scatter21_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz));
+    CU(cudaFuncSetAttribute(scatter21_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz));
+    CU(cudaFuncSetAttribute(scatter21_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz));
+    CU(cudaFuncSetAttribute(scatter_rec_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz));
+    CU(cudaFuncSetAttribute(scatter_rec_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz));
+    CU(cudaFuncSetAttribute(scatter_rec_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz));
+    done = true;
+    return P3_OK;
+}
+
 static int count_binned(p3_ctx *c, uint64_t upper) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        CU(cudaFuncSetAttribute(scatter21_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem)));
-        CU(cudaFuncSetAttribute(scatter21_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem)));
-        attr_set = true;
-    }
+    int rc0 = scatter_attrs();
+    if (rc0) return rc0;
     const uint32_t P = c->parts;
     if (!c->d_ghist) {
         CU(cudaMalloc(&c->d_ghist, sizeof(unsigned long long) * (kMaxParts + 1)));
@@ -856,13 +942,13 @@ static int count_binned(p3_ctx *c, uint64_t upper) {
         uint64_t w1 = std::min<uint64_t>(w0 + chunk_words, c->n_words);
         CU(cudaMemsetAsync(c->d_ghist, 0, sizeof(unsigned long long) * (kMaxParts + 1), c->stream));
         CU(cudaEventRecord(c->ev[10], c->stream));
-        if (c->d_nmask) hist21_kernel<true><<<c->grid(), 256, 0, c->stream>>>(c->d_packed, c->d_rend, c->d_nmask, w0, w1, P, c->d_ghist);
-        else hist21_kernel<false><<<c->grid(), 256, 0, c->stream>>>(c->d_packed, c->d_rend, nullptr, w0, w1, P, c->d_ghist);
+        if (c->d_nmask) hist21_kernel<true, 0><<<c->grid(), 256, 0, c->stream>>>(c->d_packed, c->d_rend, c->d_nmask, w0, w1, P, c->d_ghist);
+        else hist21_kernel<false, 0><<<c->grid(), 256, 0, c->stream>>>(c->d_packed, c->d_rend, nullptr, w0, w1, P, c->d_ghist);
         scan_parts_kernel<<<1, 256, 0, c->stream>>>(c->d_ghist, P, c->d_cursor, c->d_ghist + kMaxParts);
         CU(cudaEventRecord(c->ev[11], c->stream));
         unsigned sblocks = (unsigned)std::min<uint64_t>((w1 - w0 + kTileWords - 1) / kTileWords, (uint64_t)c->n_sm * 3);
-        if (c->d_nmask) scatter21_kernel<true><<<sblocks, kTileWords, sizeof(ScatterSmem), c->stream>>>(c->d_packed, c->d_rend, c->d_nmask, w0, w1, P, c->d_cursor, c->d_bkeys, c->d_bword, c->d_valid);
-        else scatter21_kernel<false><<<sblocks, kTileWords, sizeof(ScatterSmem), c->stream>>>(c->d_packed, c->d_rend, nullptr, w0, w1, P, c->d_cursor, c->d_bkeys, c->d_bword, c->d_valid);
+        if (c->d_nmask) scatter21_kernel<true, 0><<<sblocks, kTileWords, sizeof(ScatterSmem), c->stream>>>(c->d_packed, c->d_rend, c->d_nmask, w0, w1, P, c->d_cursor, c->d_bkeys, c->d_bword, c->d_valid, 0);
+        else scatter21_kernel<false, 0><<<sblocks, kTileWords, sizeof(ScatterSmem), c->stream>>>(c->d_packed, c->d_rend, nullptr, w0, w1, P, c->d_cursor, c->d_bkeys, c->d_bword, c->d_valid, 0);
         CU(cudaGetLastError());
         CU(cudaEventRecord(c->ev[12], c->stream));
         unsigned long long n_rec = 0;
@@ -891,21 +977,9 @@ static int count_binned(p3_ctx *c, uint64_t upper) {
     return P3_OK;
 }
 
-int p3_count_short_kmers(p3_ctx *c, uint64_t table_slots) {
-    if (!c) return fail(P3_ERR_ARG, "null ctx");
-    if (!c->have_reads) return fail(P3_ERR_STATE, "p3_count_short_kmers: no reads attached");
-    CU(cudaSetDevice(c->device));
-    const char *mode = getenv("P3_COUNT_MODE");
-    c->binned = !(mode && strcmp(mode, "direct") == 0);
-    uint64_t upper = c->total_bases > (kShortK - 1) * c->n_reads ? c->total_bases - (kShortK - 1) * c->n_reads : 0;
-    if (table_slots == 0) {
-        table_slots = std::max<uint64_t>(2 * upper, 1024);
-        size_t fr = 0, tot = 0;
-        CU(cudaMemGetInfo(&fr, &tot));
-        uint64_t lim = (uint64_t)(0.25 * (double)(fr + (c->d_table ? c->nb * 32 : 0))) / 8;
-        if (table_slots > lim) table_slots = lim;
-    }
-    // partitions: ~24 MB of table each so that one partition plus the streaming bins stay in L2
+// allocate (or reuse) and clear the count table: partitions of ~24 MB each in binned mode so that
+// one partition plus the streaming bins stay in L2
+static int setup_table(p3_ctx *c, uint64_t table_slots) {
     uint32_t P = 1;
     if (c->binned) {
         uint64_t want = (table_slots * 8 + (24ull << 20) - 1) / (24ull << 20);
@@ -927,7 +1001,26 @@ int p3_count_short_kmers(p3_ctx *c, uint64_t table_slots) {
     CU(cudaMemsetAsync(c->d_ovf_wraps, 0, sizeof(unsigned long long) * kOvfCap, c->stream));
     CU(cudaMemsetAsync(c->d_stats, 0, sizeof(Stats), c->stream));
     memset(&c->h_stats, 0, sizeof(Stats));
-    int rc = c->binned ? count_binned(c, upper) : count_direct(c);
+    return P3_OK;
+}
+
+int p3_count_short_kmers(p3_ctx *c, uint64_t table_slots) {
+    if (!c) return fail(P3_ERR_ARG, "null ctx");
+    if (!c->have_reads) return fail(P3_ERR_STATE, "p3_count_short_kmers: no reads attached");
+    CU(cudaSetDevice(c->device));
+    const char *mode = getenv("P3_COUNT_MODE");
+    c->binned = !(mode && strcmp(mode, "direct") == 0);
+    uint64_t upper = c->total_bases > (kShortK - 1) * c->n_reads ? c->total_bases - (kShortK - 1) * c->n_reads : 0;
+    if (table_slots == 0) {
+        table_slots = std::max<uint64_t>(2 * upper, 1024);
+        size_t fr = 0, tot = 0;
+        CU(cudaMemGetInfo(&fr, &tot));
+        uint64_t lim = (uint64_t)(0.25 * (double)(fr + (c->d_table ? c->nb * 32 : 0))) / 8;
+        if (table_slots > lim) table_slots = lim;
+    }
+    int rc = setup_table(c, table_slots);
+    if (rc) return rc;
+    rc = c->binned ? count_binned(c, upper) : count_direct(c);
     if (rc) return rc;
     rc = pull_stats(c);
     if (rc) return rc;
@@ -998,6 +1091,51 @@ static int alloc_bloom(p3_ctx *c, uint32_t k, uint64_t filter_size, uint32_t num
     return P3_OK;
 }
 
+// distinct canonical k-mers of the solid positions -> c->d_set / c->d_list (grows on overflow);
+// leaves n_distinct_solid in h_stats
+static int dedupe_solid_positions(p3_ctx *c, uint32_t k, uint64_t solid_slots) {
+    for (int attempt = 0;; attempt++) {
+        uint64_t nbs = (solid_slots + 3) / 4;
+        if (!c->d_set || c->nbs != nbs) {
+            dfree(c->d_set); dfree(c->d_list);
+            if (cudaMalloc(&c->d_set, nbs * 32) != cudaSuccess || cudaMalloc(&c->d_list, nbs * 32) != cudaSuccess) {
+                cudaGetLastError();
+                return fail(P3_ERR_NOMEM, "solid k-mer set allocation failed");
+            }
+            c->nbs = nbs; c->list_cap = nbs * 4;
+        }
+        CU(cudaMemsetAsync(c->d_set, 0xFF, nbs * 32, c->stream));
+        CU(cudaMemsetAsync(&c->d_stats->n_distinct_solid, 0, sizeof(unsigned long long), c->stream));
+        CU(cudaMemsetAsync(&c->d_stats->err_table_full, 0, sizeof(unsigned), c->stream));
+        if (c->d_nmask)
+            makebf_kernel<true><<<c->grid(), 256, 0, c->stream>>>(c->d_packed, c->d_nmask, c->d_solid, c->n_words, (int)k, c->d_set, nbs, c->d_stats);
+        else
+            makebf_kernel<false><<<c->grid(), 256, 0, c->stream>>>(c->d_packed, nullptr, c->d_solid, c->n_words, (int)k, c->d_set, nbs, c->d_stats);
+        compact_set_kernel<<<c->grid(), 256, 0, c->stream>>>(c->d_set, nbs * 4, c->d_list, c->list_cap, c->d_stats);
+        c->launches += 2;
+        CU(cudaGetLastError());
+        int rc = pull_stats(c);
+        if (rc) return rc;
+        if (!c->h_stats.err_table_full) return P3_OK;
+        if (attempt >= 16) return fail(P3_ERR_TABLE_FULL, "solid k-mer set full after growing");
+        solid_slots = std::max<uint64_t>(solid_slots * 4, 1024);
+    }
+}
+
+// dense BF.add over the first nd k-mers of c->d_list, one pass per L2-sized filter segment
+static int bloom_add_list(p3_ctx *c, uint64_t nd) {
+    uint64_t seg_bits = 40ull << 23;                       // 40 MB of filter per pass
+    uint64_t n_seg = (c->filter_size + seg_bits - 1) / seg_bits;
+    if (n_seg > 16 || nd * c->num_hashes < (1u << 22)) { n_seg = 1; seg_bits = c->filter_size; }   // huge filter / tiny job: one pass
+    else seg_bits = ((c->filter_size + n_seg - 1) / n_seg + 31) / 32 * 32;
+    for (uint64_t sg = 0; sg < n_seg && nd; sg++) {
+        bloom_list_kernel<<<c->grid(), 256, 0, c->stream>>>(c->d_list, nd, c->bloom(), sg * seg_bits, std::min<uint64_t>((sg + 1) * seg_bits, c->filter_size));
+        c->launches++;
+    }
+    CU(cudaGetLastError());
+    return P3_OK;
+}
+
 int p3_make_bf(p3_ctx *c, uint32_t k, uint64_t filter_size, uint32_t num_hashes, uint32_t cov_threshold,
                uint64_t solid_slots) {
     if (!c) return fail(P3_ERR_ARG, "null ctx");
@@ -1052,57 +1190,20 @@ int p3_make_bf(p3_ctx *c, uint32_t k, uint64_t filter_size, uint32_t num_hashes,
         uint64_t est = std::min<uint64_t>(c->h_stats.n_adds, (uint64_t)(1.25 * (double)c->h_stats.n_good21) + 1024);
         solid_slots = std::max<uint64_t>(2 * est, 1024);
     }
-    // B2b: de-duplicated BF.add; grows the solid set on overflow
-    for (int attempt = 0;; attempt++) {
-        uint64_t nbs = (solid_slots + 3) / 4;
-        if (!c->d_set || c->nbs != nbs) {
-            dfree(c->d_set); dfree(c->d_list);
-            if (cudaMalloc(&c->d_set, nbs * 32) != cudaSuccess || cudaMalloc(&c->d_list, nbs * 32) != cudaSuccess) {
-                cudaGetLastError();
-                return fail(P3_ERR_NOMEM, "solid k-mer set allocation failed");
-            }
-            c->nbs = nbs; c->list_cap = nbs * 4;
-        }
-        CU(cudaMemsetAsync(c->d_set, 0xFF, nbs * 32, c->stream));
-        CU(cudaMemsetAsync(c->d_bloom, 0, sizeof(uint32_t) * c->bloom_words, c->stream));
-        CU(cudaMemsetAsync(&c->d_stats->n_distinct_solid, 0, sizeof(unsigned long long), c->stream));
-        CU(cudaMemsetAsync(&c->d_stats->err_table_full, 0, sizeof(unsigned), c->stream));
-        CU(cudaEventRecord(c->ev[4], c->stream));
-        if (c->d_nmask)
-            makebf_kernel<true><<<c->grid(), 256, 0, c->stream>>>(c->d_packed, c->d_nmask, c->d_solid, c->n_words, (int)k, c->d_set, nbs, c->d_stats);
-        else
-            makebf_kernel<false><<<c->grid(), 256, 0, c->stream>>>(c->d_packed, nullptr, c->d_solid, c->n_words, (int)k, c->d_set, nbs, c->d_stats);
-        compact_set_kernel<<<c->grid(), 256, 0, c->stream>>>(c->d_set, nbs * 4, c->d_list, c->list_cap, c->d_stats);
-        c->launches += 2;
-        CU(cudaGetLastError());
-        rc = pull_stats(c);
-        if (rc) return rc;
-        if (c->h_stats.err_table_full) {
-            if (attempt >= 16) return fail(P3_ERR_TABLE_FULL, "solid k-mer set full after growing");
-            solid_slots = std::max<uint64_t>(solid_slots * 4, 1024);
-            continue;
-        }
-        {   // dense BF.add over the distinct k-mers, one pass per L2-sized filter segment
-            uint64_t nd = c->h_stats.n_distinct_solid;
-            uint64_t seg_bits = 40ull << 23;                       // 40 MB of filter per pass
-            uint64_t n_seg = (filter_size + seg_bits - 1) / seg_bits;
-            if (n_seg > 16 || nd * num_hashes < (1u << 22)) { n_seg = 1; seg_bits = filter_size; }   // huge filter / tiny job: one pass
-            else seg_bits = ((filter_size + n_seg - 1) / n_seg + 31) / 32 * 32;
-            CU(cudaEventRecord(c->ev[14], c->stream));
-            for (uint64_t sg = 0; sg < n_seg && nd; sg++) {
-                bloom_list_kernel<<<c->grid(), 256, 0, c->stream>>>(c->d_list, nd, c->bloom(), sg * seg_bits, std::min<uint64_t>((sg + 1) * seg_bits, filter_size));
-                c->launches++;
-            }
-            CU(cudaGetLastError());
-            CU(cudaEventRecord(c->ev[15], c->stream));
-        }
-        CU(cudaEventRecord(c->ev[5], c->stream));
-        seeds_kernel<<<c->grid(4), 256, 0, c->stream>>>(c->d_off, c->n_reads, c->d_solid, (int)k, c->d_seed);
-        c->launches++;
-        CU(cudaEventRecord(c->ev[6], c->stream));
-        CU(cudaStreamSynchronize(c->stream));
-        break;
-    }
+    // B2b: de-duplicate the solid positions into the set/list, then dense BF.add over the list
+    CU(cudaEventRecord(c->ev[4], c->stream));
+    rc = dedupe_solid_positions(c, k, solid_slots);
+    if (rc) return rc;
+    CU(cudaMemsetAsync(c->d_bloom, 0, sizeof(uint32_t) * c->bloom_words, c->stream));
+    CU(cudaEventRecord(c->ev[14], c->stream));
+    rc = bloom_add_list(c, c->h_stats.n_distinct_solid);
+    if (rc) return rc;
+    CU(cudaEventRecord(c->ev[15], c->stream));
+    CU(cudaEventRecord(c->ev[5], c->stream));
+    seeds_kernel<<<c->grid(4), 256, 0, c->stream>>>(c->d_off, c->n_reads, c->d_solid, (int)k, c->d_seed);
+    c->launches++;
+    CU(cudaEventRecord(c->ev[6], c->stream));
+    CU(cudaStreamSynchronize(c->stream));
     CU(cudaEventElapsedTime(&c->ms_bloom, c->ev[14], c->ev[15]));
     CU(cudaEventElapsedTime(&c->ms[1], c->ev[2], c->ev[3]));
     CU(cudaEventElapsedTime(&c->ms[2], c->ev[4], c->ev[5]));
@@ -1372,3 +1473,5 @@ int p3_bf_params(p3_ctx *c, uint64_t *filter_size, uint32_t *num_hashes, uint32_
 }
 
 }  // extern "C"
+
+#include "p3_multi.inc.cu"

@@ -1,0 +1,373 @@
+// p3_multi.inc.cu — multi-GPU building blocks (DESIGN.md row e), part of the p3_gpu.cu translation
+// unit. One process per GPU; the exchanges themselves (all-to-all, filter OR-reduce) are done by
+// the caller with torch.distributed/NCCL on the device buffers these entry points fill or read:
+//
+//   every rank : bin its 21-mers by OWNER rank          p3_mg_owner_hist / p3_mg_owner_scatter
+//   all-to-all of the count records (12 B each)
+//   owner      : binned, L2-resident insert             p3_mg_count_begin / _records / _end
+//   owner      : singleton verdicts by source rank      p3_mg_singletons
+//   all-to-all of the positions (8 B each)
+//   every rank : coverage plane, solid plane, seeds,    p3_mg_cover_begin / _clear, p3_mg_solid_local
+//                locally distinct solid k-mers
+//   every rank : bin those k-mers by owner              p3_mg_kmer_owner_hist / _scatter
+//   all-to-all of the k-mers (8 B each)
+//   owner      : de-duplicate, BF.add into its copy     p3_mg_owned_begin / _insert / _end
+//   OR-reduce of the filter copies                      p3_mg_filter gives the buffer
+//   owner      : CheckDirections of its k-mers          p3_dbg_adjacency (filter is complete & local)
+
+__global__ void __launch_bounds__(256)
+singleton_list_kernel(const uint64_t *__restrict__ slots, const uint64_t *__restrict__ cand_slot,
+                      const uint64_t *__restrict__ cand_pos, uint64_t n_cand, uint64_t thr, Ovf ovf,
+                      Stats *st, uint64_t *__restrict__ out) {
+    __shared__ unsigned s_wtot[8];
+    __shared__ unsigned long long s_base;
+    const unsigned n_overflow = st->n_overflow;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint64_t stride = gridDim.x * (uint64_t)blockDim.x;
+    uint64_t n_round = (n_cand + stride - 1) / stride;
+    for (uint64_t r = 0; r < n_round; r++) {
+        uint64_t j = r * stride + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+        bool single = false;
+        uint64_t pos = 0;
+        if (j < n_cand) {
+            uint64_t v = __ldcg(slots + __ldcs(cand_slot + j));
+            uint64_t c = v >> 42;
+            if (c < thr && n_overflow) c += ovf_get(ovf, v & kKey42) << 22;
+            single = c < thr;
+            if (single) pos = __ldcs(cand_pos + j);
+        }
+        unsigned m = __ballot_sync(0xffffffffu, single);
+        if (lane == 0) s_wtot[wid] = __popc(m);
+        __syncthreads();
+        unsigned wbase = 0, total = 0;
+#pragma unroll
+        for (int q = 0; q < 8; q++) { unsigned t = s_wtot[q]; if (q < wid) wbase += t; total += t; }
+        if (threadIdx.x == 0 && total) s_base = atomicAdd(&st->n_export, (unsigned long long)total);
+        __syncthreads();
+        if (single) out[s_base + wbase + __popc(m & ((1u << lane) - 1))] = pos;
+        __syncthreads();
+    }
+}
+
+__global__ void clear_positions_kernel(const uint64_t *__restrict__ pos, uint64_t n, uint32_t *good21) {
+    uint64_t stride = gridDim.x * (uint64_t)blockDim.x;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint64_t p = __ldcs(pos + i) & ((1ULL << kPosRankShift) - 1);
+        atomicAnd(good21 + (p >> 5), ~(0x80000000u >> (p & 31)));
+    }
+}
+
+__global__ void set_insert_list_kernel(const uint64_t *__restrict__ kmers, uint64_t n, uint64_t *set, uint64_t nbs, Stats *st) {
+    uint64_t stride = gridDim.x * (uint64_t)blockDim.x;
+    bool full = false;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += stride)
+        if (set_insert(set, nbs, __ldcs(kmers + i)) < 0) full = true;
+    if (full) atomicExch(&st->err_table_full, 1u);
+}
+
+// host-side copy of owner_of (for tests and for callers that route on the host)
+static inline uint32_t owner_of_host(uint64_t key, uint32_t n) {
+    return (uint32_t)(((unsigned __int128)owner_mix(key) * n) >> 64);
+}
+
+struct MgState {   // extra per-context state of the multi-GPU path
+    uint64_t *d_sing = nullptr, *d_sing2 = nullptr; uint64_t cap_sing = 0, cap_sing2 = 0;
+    uint64_t *d_set2 = nullptr, *d_list2 = nullptr; uint64_t nbs2 = 0;
+    uint64_t rec_cap = 0;
+    uint64_t n_local = 0;
+};
+static std::unordered_map<p3_ctx *, MgState> g_mg;   // keyed by context (p3_ctx layout stays private to p3_gpu.cu)
+
+static void mg_release(p3_ctx *c) {
+    auto it = g_mg.find(c);
+    if (it == g_mg.end()) return;
+    MgState &m = it->second;
+    dfree(m.d_sing); dfree(m.d_sing2); dfree(m.d_set2); dfree(m.d_list2);
+    g_mg.erase(it);
+}
+
+static int mg_scan(p3_ctx *c, uint32_t P, uint64_t *h_counts) {
+    scan_parts_kernel<<<1, 256, 0, c->stream>>>(c->d_ghist, P, c->d_cursor, c->d_ghist + kMaxParts);
+    c->launches++;
+    if (h_counts) {
+        std::vector<unsigned long long> h(P);
+        CU(cudaMemcpyAsync(h.data(), c->d_ghist, sizeof(unsigned long long) * P, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        for (uint32_t i = 0; i < P; i++) h_counts[i] = h[i];
+    }
+    return P3_OK;
+}
+static int mg_hist_buffers(p3_ctx *c) {
+    if (!c->d_ghist) {
+        CU(cudaMalloc(&c->d_ghist, sizeof(unsigned long long) * (kMaxParts + 1)));
+        CU(cudaMalloc(&c->d_cursor, sizeof(unsigned long long) * (kMaxParts + 1)));
+    }
+    return scatter_attrs();
+}
+
+extern "C" {
+
+uint32_t p3_owner_of_key(uint64_t key, uint32_t n_ranks) { return n_ranks ? owner_of_host(key, n_ranks) : 0; }
+
+int p3_mg_owner_hist(p3_ctx *c, uint32_t n_ranks, uint64_t w0, uint64_t w1, uint64_t *h_counts) {
+    if (!c || !c->have_reads) return fail(P3_ERR_STATE, "p3_mg_owner_hist: no reads attached");
+    if (n_ranks == 0 || n_ranks > 256 || w1 > c->n_words || w0 > w1) return fail(P3_ERR_ARG, "p3_mg_owner_hist: bad arguments");
+    CU(cudaSetDevice(c->device));
+    int rc = mg_hist_buffers(c);
+    if (rc) return rc;
+    CU(cudaMemsetAsync(c->d_ghist, 0, sizeof(unsigned long long) * (kMaxParts + 1), c->stream));
+    if (c->d_nmask) hist21_kernel<true, 1><<<c->grid(), 256, 0, c->stream>>>(c->d_packed, c->d_rend, c->d_nmask, w0, w1, n_ranks, c->d_ghist);
+    else hist21_kernel<false, 1><<<c->grid(), 256, 0, c->stream>>>(c->d_packed, c->d_rend, nullptr, w0, w1, n_ranks, c->d_ghist);
+    c->launches++;
+    CU(cudaGetLastError());
+    return mg_scan(c, n_ranks, h_counts);
+}
+
+// must follow p3_mg_owner_hist with the same arguments (it consumes the cursors that call set up)
+int p3_mg_owner_scatter(p3_ctx *c, uint32_t n_ranks, uint32_t my_rank, uint64_t w0, uint64_t w1,
+                        uint64_t *d_keys, uint32_t *d_words) {
+    if (!c || !c->have_reads || !d_keys || !d_words) return fail(P3_ERR_STATE, "p3_mg_owner_scatter: no reads / null buffers");
+    if (my_rank >= n_ranks || n_ranks > 256) return fail(P3_ERR_ARG, "p3_mg_owner_scatter: bad rank");
+    CU(cudaSetDevice(c->device));
+    CU(ensure(c->d_valid, c->cap_valid, sizeof(uint32_t) * (c->n_words + 1)));
+    unsigned sblocks = (unsigned)std::min<uint64_t>(std::max<uint64_t>((w1 - w0 + kTileWords - 1) / kTileWords, 1), (uint64_t)c->n_sm * 3);
+    const uint64_t tag = (uint64_t)my_rank << kRecRankShift;
+    if (c->d_nmask) scatter21_kernel<true, 1><<<sblocks, kTileWords, sizeof(ScatterSmem), c->stream>>>(c->d_packed, c->d_rend, c->d_nmask, w0, w1, n_ranks, c->d_cursor, d_keys, d_words, c->d_valid, tag);
+    else scatter21_kernel<false, 1><<<sblocks, kTileWords, sizeof(ScatterSmem), c->stream>>>(c->d_packed, c->d_rend, nullptr, w0, w1, n_ranks, c->d_cursor, d_keys, d_words, c->d_valid, tag);
+    c->launches++;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));
+    return P3_OK;
+}
+
+int p3_mg_count_begin(p3_ctx *c, uint64_t table_slots, uint64_t max_records_per_call) {
+    if (!c) return fail(P3_ERR_ARG, "null ctx");
+    if (table_slots == 0) return fail(P3_ERR_ARG, "p3_mg_count_begin: table_slots required");
+    CU(cudaSetDevice(c->device));
+    int rc = mg_hist_buffers(c);
+    if (rc) return rc;
+    c->binned = true;
+    rc = setup_table(c, table_slots);
+    if (rc) return rc;
+    MgState &m = g_mg[c];
+    m.rec_cap = std::max<uint64_t>(max_records_per_call, 1);
+    CU(ensure(c->d_bkeys, c->cap_bkeys, sizeof(uint64_t) * m.rec_cap));
+    CU(ensure(c->d_bword, c->cap_bword, sizeof(uint32_t) * m.rec_cap));
+    c->cand_cap = c->nb * 4;
+    CU(ensure(c->d_cand_slot, c->cap_cand_slot, sizeof(uint64_t) * c->cand_cap));
+    CU(ensure(c->d_cand_pos, c->cap_cand_pos, sizeof(uint64_t) * c->cand_cap));
+    c->binned_pos = 0; c->n_chunks = 0;
+    c->have_counts = false;
+    return P3_OK;
+}
+
+int p3_mg_count_records(p3_ctx *c, const uint64_t *d_keys, const uint32_t *d_words, uint64_t n) {
+    if (!c) return fail(P3_ERR_ARG, "null ctx");
+    if (n == 0) return P3_OK;
+    CU(cudaSetDevice(c->device));
+    CU(ensure(c->d_bkeys, c->cap_bkeys, sizeof(uint64_t) * n));   // local bins grow with the largest batch
+    CU(ensure(c->d_bword, c->cap_bword, sizeof(uint32_t) * n));
+    const uint32_t P = c->parts;
+    CU(cudaMemsetAsync(c->d_ghist, 0, sizeof(unsigned long long) * (kMaxParts + 1), c->stream));
+    hist_rec_kernel<0><<<c->grid(), 256, 0, c->stream>>>(d_keys, n, P, c->d_ghist);
+    int rc = mg_scan(c, P, nullptr);
+    if (rc) return rc;
+    unsigned sblocks = (unsigned)std::min<uint64_t>((n + kTilePos - 1) / kTilePos, (uint64_t)c->n_sm * 3);
+    scatter_rec_kernel<0, true><<<sblocks, kTileWords, sizeof(ScatterSmem), c->stream>>>(d_keys, d_words, n, P, c->d_cursor, c->d_bkeys, c->d_bword);
+    CU(cudaMemsetAsync(&c->d_stats->work, 0, sizeof(unsigned long long), c->stream));
+    insert_bins_kernel<<<c->grid(), 256, 0, c->stream>>>(c->d_bkeys, c->d_bword, n, c->table(), c->ovf(), c->d_stats, c->d_cand_slot, c->d_cand_pos, c->cand_cap);
+    c->launches += 3;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));
+    c->binned_pos += n; c->n_chunks++;
+    return P3_OK;
+}
+
+int p3_mg_count_end(p3_ctx *c) {
+    if (!c) return fail(P3_ERR_ARG, "null ctx");
+    CU(cudaSetDevice(c->device));
+    int rc = pull_stats(c);
+    if (rc) return rc;
+    if (c->h_stats.err_table_full) return fail(P3_ERR_TABLE_FULL, "21-mer count table full: raise table_slots");
+    if (c->h_stats.err_ovf_full) return fail(P3_ERR_TABLE_FULL, "count overflow side table full");
+    if (c->h_stats.n_cand > c->cand_cap) return fail(P3_ERR_TABLE_FULL, "candidate list overflow");
+    c->have_counts = true;
+    c->have_bf = c->have_solid = c->have_adj = false;
+    return P3_OK;
+}
+
+// positions (with their source rank in the top byte) of every key this rank owns whose final
+// count is below the reference's cov_threshold of 2, grouped by source rank
+int p3_mg_singletons(p3_ctx *c, uint32_t n_ranks, uint64_t *h_counts, const uint64_t **d_pos) {
+    if (!c || !c->have_counts) return fail(P3_ERR_STATE, "p3_mg_singletons: no counts");
+    CU(cudaSetDevice(c->device));
+    MgState &m = g_mg[c];
+    uint64_t nc = c->h_stats.n_cand;
+    CU(ensure(m.d_sing, m.cap_sing, sizeof(uint64_t) * std::max<uint64_t>(nc, 1)));
+    CU(ensure(m.d_sing2, m.cap_sing2, sizeof(uint64_t) * std::max<uint64_t>(nc, 1)));
+    CU(cudaMemsetAsync(&c->d_stats->n_export, 0, sizeof(unsigned long long), c->stream));
+    if (nc) {
+        singleton_list_kernel<<<c->grid(), 256, 0, c->stream>>>(c->d_table, c->d_cand_slot, c->d_cand_pos, nc, P3_COV_THRESHOLD, c->ovf(), c->d_stats, m.d_sing);
+        c->launches++;
+    }
+    int rc = pull_stats(c);
+    if (rc) return rc;
+    uint64_t ns = c->h_stats.n_export;
+    CU(cudaMemsetAsync(c->d_ghist, 0, sizeof(unsigned long long) * (kMaxParts + 1), c->stream));
+    if (ns) hist_rec_kernel<2><<<c->grid(), 256, 0, c->stream>>>(m.d_sing, ns, n_ranks, c->d_ghist);
+    rc = mg_scan(c, n_ranks, h_counts);
+    if (rc) return rc;
+    if (ns) {
+        unsigned sblocks = (unsigned)std::min<uint64_t>((ns + kTilePos - 1) / kTilePos, (uint64_t)c->n_sm * 3);
+        scatter_rec_kernel<2, false><<<sblocks, kTileWords, sizeof(ScatterSmem), c->stream>>>(m.d_sing, nullptr, ns, n_ranks, c->d_cursor, m.d_sing2, nullptr);
+        c->launches += 2;
+    }
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));
+    if (d_pos) *d_pos = m.d_sing2;
+    return P3_OK;
+}
+
+static int ensure_planes(p3_ctx *c) {
+    uint64_t pw = c->n_words + 1;
+    if (!c->d_good21 || !c->d_solid || c->cap_planes < sizeof(uint32_t) * pw) {
+        dfree(c->d_good21); dfree(c->d_solid);
+        CU(cudaMalloc(&c->d_good21, sizeof(uint32_t) * pw));
+        CU(cudaMalloc(&c->d_solid, sizeof(uint32_t) * pw));
+        c->cap_planes = sizeof(uint32_t) * pw;
+    }
+    CU(ensure(c->d_seed, c->cap_seed, sizeof(int64_t) * std::max<uint64_t>(c->n_reads, 1)));
+    return P3_OK;
+}
+
+// coverage plane := every valid 21-mer position (p3_mg_owner_scatter filled the valid plane)
+int p3_mg_cover_begin(p3_ctx *c) {
+    if (!c || !c->have_reads || !c->d_valid) return fail(P3_ERR_STATE, "p3_mg_cover_begin: run p3_mg_owner_scatter first");
+    CU(cudaSetDevice(c->device));
+    int rc = ensure_planes(c);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(c->d_good21, c->d_valid, sizeof(uint32_t) * c->n_words, cudaMemcpyDeviceToDevice, c->stream));
+    CU(cudaMemsetAsync(c->d_good21 + c->n_words, 0, sizeof(uint32_t), c->stream));
+    return P3_OK;
+}
+int p3_mg_cover_clear(p3_ctx *c, const uint64_t *d_pos, uint64_t n) {
+    if (!c || !c->d_good21) return fail(P3_ERR_STATE, "p3_mg_cover_clear: run p3_mg_cover_begin first");
+    if (n == 0) return P3_OK;
+    CU(cudaSetDevice(c->device));
+    clear_positions_kernel<<<c->grid(), 256, 0, c->stream>>>(d_pos, n, c->d_good21);
+    c->launches++;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));
+    return P3_OK;
+}
+
+// solid plane (window AND of the coverage plane), seeds, and the locally distinct solid k-mers
+int p3_mg_solid_local(p3_ctx *c, uint32_t k, uint64_t solid_slots, uint64_t *n_adds, uint64_t *n_local) {
+    if (!c || !c->d_good21) return fail(P3_ERR_STATE, "p3_mg_solid_local: run p3_mg_cover_begin first");
+    if (k < P3_MIN_K || k > P3_MAX_K) return fail(P3_ERR_ARG, "k outside [21,32] is not supported by this build");
+    CU(cudaSetDevice(c->device));
+    c->k = k; c->set_valid = false;
+    CU(cudaMemsetAsync(&c->d_stats->n_adds, 0, sizeof(unsigned long long) * 5, c->stream));
+    solid_kernel<<<c->grid(), 256, 0, c->stream>>>(c->d_good21, c->n_words, (int)k, c->d_solid, c->d_stats);
+    c->launches++;
+    int rc = pull_stats(c);
+    if (rc) return rc;
+    if (solid_slots == 0) solid_slots = std::max<uint64_t>(2 * std::min<uint64_t>(c->h_stats.n_adds, 1ull << 26), 1024);
+    rc = dedupe_solid_positions(c, k, solid_slots);
+    if (rc) return rc;
+    seeds_kernel<<<c->grid(4), 256, 0, c->stream>>>(c->d_off, c->n_reads, c->d_solid, (int)k, c->d_seed);
+    c->launches++;
+    CU(cudaStreamSynchronize(c->stream));
+    g_mg[c].n_local = c->h_stats.n_distinct_solid;
+    c->have_solid = true;
+    if (n_adds) *n_adds = c->h_stats.n_adds;
+    if (n_local) *n_local = c->h_stats.n_distinct_solid;
+    return P3_OK;
+}
+
+int p3_mg_kmer_owner_hist(p3_ctx *c, uint32_t n_ranks, uint64_t *h_counts) {
+    if (!c || !c->have_solid) return fail(P3_ERR_STATE, "p3_mg_kmer_owner_hist: run p3_mg_solid_local first");
+    CU(cudaSetDevice(c->device));
+    uint64_t n = g_mg[c].n_local;
+    CU(cudaMemsetAsync(c->d_ghist, 0, sizeof(unsigned long long) * (kMaxParts + 1), c->stream));
+    if (n) { hist_rec_kernel<3><<<c->grid(), 256, 0, c->stream>>>(c->d_list, n, n_ranks, c->d_ghist); c->launches++; }
+    CU(cudaGetLastError());
+    return mg_scan(c, n_ranks, h_counts);
+}
+int p3_mg_kmer_owner_scatter(p3_ctx *c, uint32_t n_ranks, uint64_t *d_out) {
+    if (!c || !c->have_solid || !d_out) return fail(P3_ERR_STATE, "p3_mg_kmer_owner_scatter: bad state");
+    CU(cudaSetDevice(c->device));
+    uint64_t n = g_mg[c].n_local;
+    if (n) {
+        unsigned sblocks = (unsigned)std::min<uint64_t>((n + kTilePos - 1) / kTilePos, (uint64_t)c->n_sm * 3);
+        scatter_rec_kernel<3, false><<<sblocks, kTileWords, sizeof(ScatterSmem), c->stream>>>(c->d_list, nullptr, n, n_ranks, c->d_cursor, d_out, nullptr);
+        c->launches++;
+    }
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));
+    return P3_OK;
+}
+
+int p3_mg_owned_begin(p3_ctx *c, uint64_t owned_slots) {
+    if (!c) return fail(P3_ERR_ARG, "null ctx");
+    CU(cudaSetDevice(c->device));
+    MgState &m = g_mg[c];
+    uint64_t nbs = (std::max<uint64_t>(owned_slots, 1024) + 3) / 4;
+    if (!m.d_set2 || m.nbs2 != nbs) {
+        dfree(m.d_set2); dfree(m.d_list2);
+        if (cudaMalloc(&m.d_set2, nbs * 32) != cudaSuccess || cudaMalloc(&m.d_list2, nbs * 32) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(P3_ERR_NOMEM, "owned k-mer set allocation failed");
+        }
+        m.nbs2 = nbs;
+    }
+    CU(cudaMemsetAsync(m.d_set2, 0xFF, nbs * 32, c->stream));
+    CU(cudaMemsetAsync(&c->d_stats->err_table_full, 0, sizeof(unsigned), c->stream));
+    return P3_OK;
+}
+int p3_mg_owned_insert(p3_ctx *c, const uint64_t *d_kmers, uint64_t n) {
+    if (!c) return fail(P3_ERR_ARG, "null ctx");
+    if (n == 0) return P3_OK;
+    CU(cudaSetDevice(c->device));
+    MgState &m = g_mg[c];
+    set_insert_list_kernel<<<c->grid(), 256, 0, c->stream>>>(d_kmers, n, m.d_set2, m.nbs2, c->d_stats);
+    c->launches++;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));
+    return P3_OK;
+}
+
+// the owned set becomes THE set/list of this context; the filter copy is cleared and receives
+// BF.add of every owned k-mer (the caller then OR-reduces the copies across ranks)
+int p3_mg_owned_end(p3_ctx *c, uint32_t k, uint64_t filter_size, uint32_t num_hashes, uint64_t *n_owned) {
+    if (!c) return fail(P3_ERR_ARG, "null ctx");
+    CU(cudaSetDevice(c->device));
+    MgState &m = g_mg[c];
+    if (!m.d_set2) return fail(P3_ERR_STATE, "p3_mg_owned_end: run p3_mg_owned_begin first");
+    int rc = alloc_bloom(c, k, filter_size, num_hashes);
+    if (rc) return rc;
+    std::swap(c->d_set, m.d_set2); std::swap(c->d_list, m.d_list2); std::swap(c->nbs, m.nbs2);
+    c->list_cap = c->nbs * 4;
+    CU(cudaMemsetAsync(&c->d_stats->n_distinct_solid, 0, sizeof(unsigned long long), c->stream));
+    compact_set_kernel<<<c->grid(), 256, 0, c->stream>>>(c->d_set, c->nbs * 4, c->d_list, c->list_cap, c->d_stats);
+    c->launches++;
+    rc = pull_stats(c);
+    if (rc) return rc;
+    if (c->h_stats.err_table_full) return fail(P3_ERR_TABLE_FULL, "owned k-mer set full: raise owned_slots");
+    CU(cudaMemsetAsync(c->d_bloom, 0, sizeof(uint32_t) * c->bloom_words, c->stream));
+    rc = bloom_add_list(c, c->h_stats.n_distinct_solid);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(c->stream));
+    c->have_bf = true; c->have_solid = true; c->have_adj = false; c->set_valid = true;
+    if (n_owned) *n_owned = c->h_stats.n_distinct_solid;
+    return P3_OK;
+}
+
+int p3_mg_filter(p3_ctx *c, uint32_t **d_bits, uint64_t *n_words) {
+    if (!c || !c->d_bloom) return fail(P3_ERR_STATE, "p3_mg_filter: no filter");
+    if (d_bits) *d_bits = c->d_bloom;
+    if (n_words) *n_words = c->bloom_words;
+    return P3_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,244 @@
+"""Multi-GPU hot path: canonical k-mers hash-partitioned by owner rank, exchanged with all-to-all.
+
+One process per GPU (torch.distributed / NCCL). All heavy work is in the CUDA library
+(csrc/p3_multi.inc.cu); this module only sequences the stages and moves the device buffers:
+
+  A   every rank bins its 21-mers by owner -> all-to-all (12 B records) -> owner counts them
+  B1  owner lists its count-1 keys' (rank, position) -> all-to-all -> ranks clear coverage bits
+  B2  ranks build solid planes/seeds and their locally distinct solid k-mers -> all-to-all by
+      owner -> owner de-duplicates and BF.adds into its filter copy -> OR-reduce of the copies
+  C   owner runs CheckDirections for its k-mers against the (now complete, local) filter
+
+The same driver runs over an emulated communicator (several contexts of one process on one GPU),
+which is how the parity tests exercise the distributed algorithm on a single-GPU box.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+class _DevView:
+    """torch view of a raw device pointer via __cuda_array_interface__"""
+
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def dev_tensor(ptr, n, dtype, device):
+    if n == 0 or not ptr:
+        return torch.empty(0, dtype=dtype, device=device)
+    typestr = {torch.int64: "<i8", torch.int32: "<i4", torch.uint8: "|u1"}[dtype]
+    return torch.as_tensor(_DevView(ptr, n, typestr), device=device)
+
+
+# ---------------------------------------------------------------------------- communicators
+class TorchDistComm:
+    """all-to-all with variable splits and bitwise-OR reduction over torch.distributed"""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist, self.group = dist, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.local_ranks = [self.rank]
+
+    def exchange(self, sends):
+        """sends: [(tensors, counts)] for the one local rank -> [(recv_tensors, recv_counts)]"""
+        (tensors, counts), = sends
+        dev = tensors[0].device
+        sc = torch.tensor(counts, dtype=torch.int64, device=dev)
+        rc = torch.empty_like(sc)
+        self.dist.all_to_all_single(rc, sc, group=self.group)
+        rcounts = [int(x) for x in rc.tolist()]
+        outs = []
+        for t in tensors:
+            out = torch.empty(sum(rcounts), dtype=t.dtype, device=dev)
+            self.dist.all_to_all_single(out, t, output_split_sizes=rcounts, input_split_sizes=[int(c) for c in counts], group=self.group)
+            outs.append(out)
+        return [(outs, rcounts)]
+
+    def or_reduce(self, filters):
+        """bitwise OR of the int32 filter copies of all ranks, in place: all-to-all of shards, local OR,
+        all-gather (NCCL has no bitwise-or reduction op)"""
+        f, = filters
+        n, w = f.numel(), self.world
+        if w == 1:
+            return
+        shard = (n + w - 1) // w
+        buf = torch.zeros(shard * w, dtype=f.dtype, device=f.device)
+        buf[:n] = f
+        recv = torch.empty_like(buf)
+        self.dist.all_to_all_single(recv, buf, group=self.group)
+        acc = recv[:shard].clone()
+        for i in range(1, w):
+            torch.bitwise_or(acc, recv[i * shard:(i + 1) * shard], out=acc)
+        self.dist.all_gather_into_tensor(buf, acc, group=self.group)
+        f.copy_(buf[:n])
+
+    def all_sum(self, values):
+        t = torch.tensor(values, dtype=torch.int64, device="cuda" if torch.cuda.is_available() and self.dist.get_backend(self.group) == "nccl" else "cpu")
+        self.dist.all_reduce(t, group=self.group)
+        return [int(x) for x in t.tolist()]
+
+
+class EmulatedComm:
+    """all ranks live in this process (one context each); exchanges are slicing and concatenation"""
+
+    def __init__(self, world):
+        self.world = world
+        self.local_ranks = list(range(world))
+
+    def exchange(self, sends):
+        w = self.world
+        offs = [np.concatenate([[0], np.cumsum(counts)]).astype(np.int64) for _, counts in sends]
+        out = []
+        for j in range(w):
+            rcounts = [int(sends[i][1][j]) for i in range(w)]
+            outs = []
+            for ti in range(len(sends[0][0])):
+                parts = [sends[i][0][ti][int(offs[i][j]):int(offs[i][j + 1])] for i in range(w)]
+                outs.append(torch.cat(parts) if parts else sends[0][0][ti][:0])
+            out.append((outs, rcounts))
+        return out
+
+    def or_reduce(self, filters):
+        acc = filters[0].clone()
+        for f in filters[1:]:
+            torch.bitwise_or(acc, f, out=acc)
+        for f in filters:
+            f.copy_(acc)
+
+    def all_sum(self, values_per_rank):
+        return [int(sum(v)) for v in zip(*values_per_rank)]
+
+
+# ---------------------------------------------------------------------------- driver
+def _check(rc):
+    _lib.check(rc)
+
+
+def _exchange(comm, sends):
+    """all-to-all, then wait for it: the library launches on its context's stream, which need not be
+    the torch stream NCCL synchronises with (every p3_mg_* call itself returns synchronised)"""
+    out = comm.exchange(sends)
+    torch.cuda.synchronize()
+    return out
+
+
+def run_hot_path(ctxs, comm, k, filter_size, num_hashes, table_slots, solid_slots=0, owned_slots=0,
+                 chunk_words=None, device=None):
+    """ctxs: the Context of every LOCAL rank (reads already attached/uploaded), in comm.local_ranks
+    order. table_slots: per-rank count-table capacity. Returns one stats dict per local rank; the
+    results stay in the contexts (owned 21-mer counts, owned k-mers + adjacency, local seeds, the
+    complete filter)."""
+    L = _lib.lib()
+    w = comm.world
+    device = device or torch.device("cuda", torch.cuda.current_device())
+    stats = [dict(rank=r) for r in comm.local_ranks]
+    marks = []
+
+    def mark(name):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        marks.append((name, e))
+    mark("start")
+    n_words = [(c.total_bases + 31) // 32 for c in ctxs]
+    cw = chunk_words or max(max(n_words), 1)
+    n_chunks = max((nw + cw - 1) // cw for nw in n_words) if n_words else 0
+    if hasattr(comm, "dist"):   # ranks may hold different amounts of reads: agree on the chunk count
+        t = torch.tensor([n_chunks], dtype=torch.int64, device=device)
+        comm.dist.all_reduce(t, op=comm.dist.ReduceOp.MAX, group=comm.group)
+        n_chunks = int(t.item())
+
+    # ---- A: count ------------------------------------------------------------------------------
+    for c in ctxs:
+        _check(L.p3_mg_count_begin(c.h, table_slots, 1))
+    for ch in range(n_chunks):
+        sends = []
+        for c, r, nw in zip(ctxs, comm.local_ranks, n_words):
+            w0, w1 = min(ch * cw, nw), min((ch + 1) * cw, nw)
+            counts = (C.c_uint64 * w)()
+            _check(L.p3_mg_owner_hist(c.h, w, w0, w1, counts))
+            counts = [int(x) for x in counts]
+            tot = sum(counts)
+            keys = torch.empty(max(tot, 1), dtype=torch.int64, device=device)
+            words = torch.empty(max(tot, 1), dtype=torch.int32, device=device)
+            _check(L.p3_mg_owner_scatter(c.h, w, r, w0, w1, keys.data_ptr(), words.data_ptr()))
+            sends.append(([keys[:tot], words[:tot]], counts))
+        recvs = _exchange(comm, sends)
+        del sends
+        for c, (tensors, rcounts) in zip(ctxs, recvs):
+            n = sum(rcounts)
+            if n:
+                _check(L.p3_mg_count_records(c.h, tensors[0].data_ptr(), tensors[1].data_ptr(), n))
+        del recvs
+    for c, st in zip(ctxs, stats):
+        _check(L.p3_mg_count_end(c.h))
+        a, b = C.c_uint64(), C.c_uint64()
+        _check(L.p3_short_kmer_stats(c.h, C.byref(a), C.byref(b)))
+        st.update(owned_positions=a.value, owned_distinct21=b.value)
+
+    mark("count")
+    # ---- B1: singleton verdicts back to the reads ----------------------------------------------------
+    sends = []
+    for c in ctxs:
+        counts = (C.c_uint64 * w)()
+        ptr = C.c_void_p()
+        _check(L.p3_mg_singletons(c.h, w, counts, C.byref(ptr)))
+        counts = [int(x) for x in counts]
+        sends.append(([dev_tensor(ptr.value, sum(counts), torch.int64, device)], counts))
+    recvs = _exchange(comm, sends)
+    for c, (tensors, rcounts) in zip(ctxs, recvs):
+        _check(L.p3_mg_cover_begin(c.h))
+        n = sum(rcounts)
+        if n:
+            t = tensors[0].contiguous()
+            _check(L.p3_mg_cover_clear(c.h, t.data_ptr(), n))
+    del sends, recvs
+
+    mark("coverage")
+    # ---- B2: solid k-mers to their owners ---------------------------------------------------------------
+    sends = []
+    for c, st in zip(ctxs, stats):
+        a, b = C.c_uint64(), C.c_uint64()
+        _check(L.p3_mg_solid_local(c.h, k, solid_slots, C.byref(a), C.byref(b)))
+        st.update(n_adds=a.value, local_distinct_solid=b.value)
+        counts = (C.c_uint64 * w)()
+        _check(L.p3_mg_kmer_owner_hist(c.h, w, counts))
+        counts = [int(x) for x in counts]
+        buf = torch.empty(max(sum(counts), 1), dtype=torch.int64, device=device)
+        _check(L.p3_mg_kmer_owner_scatter(c.h, w, buf.data_ptr()))
+        sends.append(([buf[:sum(counts)]], counts))
+    recvs = _exchange(comm, sends)
+    del sends
+    filters = []
+    for c, st, (tensors, rcounts) in zip(ctxs, stats, recvs):
+        n = sum(rcounts)
+        _check(L.p3_mg_owned_begin(c.h, owned_slots or max(2 * n, 1024)))
+        if n:
+            t = tensors[0].contiguous()
+            _check(L.p3_mg_owned_insert(c.h, t.data_ptr(), n))
+        no = C.c_uint64()
+        _check(L.p3_mg_owned_end(c.h, k, filter_size, num_hashes, C.byref(no)))
+        st.update(owned_solid=no.value)
+        c.k, c.filter_size, c.num_hashes = k, filter_size, num_hashes
+        ptr, nwords = C.c_void_p(), C.c_uint64()
+        _check(L.p3_mg_filter(c.h, C.byref(ptr), C.byref(nwords)))
+        filters.append(dev_tensor(ptr.value, nwords.value, torch.int32, device))
+    del recvs
+    comm.or_reduce(filters)
+    torch.cuda.synchronize()
+
+    mark("makebf")
+    # ---- C: adjacency of the owned k-mers ---------------------------------------------------------------------
+    for c, st in zip(ctxs, stats):
+        nk, ne = c.dbg_adjacency()
+        st.update(owned_kmers=nk, owned_edges=ne)
+    mark("adjacency")
+    torch.cuda.synchronize()
+    ms = {marks[i][0]: marks[i - 1][1].elapsed_time(marks[i][1]) for i in range(1, len(marks))}
+    for st in stats:
+        st["stage_ms"] = ms
+    return stats

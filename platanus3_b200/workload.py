@@ -16,7 +16,7 @@ def pack_codes(codes_flat):
 
 
 def make_reads(genome_bases, coverage, read_len, error_rate, seed, device, chunk_reads=1 << 20,
-               return_codes=False):
+               return_codes=False, read_seed=None):
     """Uniform shotgun reads from a random genome, both strands, substitution errors.
 
     Returns dict(packed=int64[n_words+1], off=int64[n_reads+1], total_bases, n_reads[, codes]).
@@ -27,6 +27,8 @@ def make_reads(genome_bases, coverage, read_len, error_rate, seed, device, chunk
     gen = torch.Generator(device=device)
     gen.manual_seed(seed)
     genome = torch.randint(0, 4, (genome_bases,), generator=gen, device=device, dtype=torch.uint8)
+    if read_seed is not None:   # same genome on every rank, different reads
+        gen.manual_seed(read_seed)
     n_reads = max(16, int(round(genome_bases * coverage / read_len)) // 16 * 16)
     total = n_reads * read_len
     n_words = total // 32

@@ -1,0 +1,142 @@
+"""Multi-GPU path. CPU: the communicator (variable all-to-all, OR-reduce) over gloo with
+world_size 2, and the owner function. GPU: the whole distributed algorithm with R ranks emulated
+as R contexts on one device, bit-exact against the oracle."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+from _checkers import reads_to_arrays
+from platanus3_b200 import _lib, dist as pdist, synth
+
+
+def test_owner_function_is_a_stable_uniform_partition():
+    L = _lib.lib()
+    rng = np.random.default_rng(0)
+    keys = rng.integers(0, 1 << 42, 40000, dtype=np.uint64)
+    for n in (1, 2, 3, 8):
+        own = np.array([L.p3_owner_of_key(int(x), n) for x in keys])
+        assert own.min() >= 0 and own.max() < n
+        assert np.array_equal(own, np.array([L.p3_owner_of_key(int(x), n) for x in keys]))
+        frac = np.bincount(own, minlength=n) / len(keys)
+        assert np.all(np.abs(frac - 1.0 / n) < 0.02)
+    assert L.p3_owner_of_key(12345, 1) == 0
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        comm = pdist.TorchDistComm()
+        # variable all-to-all: rank r sends (r+1)*(j+2) records to rank j, values encode (src, dst, i)
+        counts = [(rank + 1) * (j + 2) for j in range(world)]
+        a = torch.cat([torch.arange(c, dtype=torch.int64) + 1000 * rank + 100000 * j for j, c in enumerate(counts)])
+        b = (a % 97).to(torch.int32)
+        (outs, rcounts), = comm.exchange([([a, b], counts)])
+        want_counts = [(i + 1) * (rank + 2) for i in range(world)]
+        want = torch.cat([torch.arange(c, dtype=torch.int64) + 1000 * i + 100000 * rank for i, c in enumerate(want_counts)])
+        ok = rcounts == want_counts and torch.equal(outs[0], want) and torch.equal(outs[1], (want % 97).to(torch.int32))
+        # OR-reduce of filter copies whose length is not a multiple of the world size
+        g = torch.Generator().manual_seed(5)
+        full = [torch.randint(-2 ** 31, 2 ** 31 - 1, (1001,), generator=g, dtype=torch.int64).to(torch.int32) for _ in range(world)]
+        mine = full[rank].clone()
+        comm.or_reduce([mine])
+        acc = full[0].clone()
+        for f in full[1:]:
+            acc |= f
+        ok = ok and torch.equal(mine, acc)
+        ok = ok and comm.all_sum([rank + 1, 10]) == [sum(range(1, world + 1)), 10 * world]
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_comm_over_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(60)
+    assert res == [(0, True), (1, True)]
+
+
+def test_emulated_comm_matches_definition():
+    comm = pdist.EmulatedComm(3)
+    sends = []
+    for r in range(3):
+        counts = [r + j + 1 for j in range(3)]
+        t = torch.cat([torch.full((c,), 10 * r + j, dtype=torch.int64) for j, c in enumerate(counts)])
+        sends.append(([t], counts))
+    recvs = comm.exchange(sends)
+    for j, (outs, rcounts) in enumerate(recvs):
+        assert rcounts == [i + j + 1 for i in range(3)]
+        assert outs[0].tolist() == sum(([10 * i + j] * (i + j + 1) for i in range(3)), [])
+    fs = [torch.tensor([1, 0, 4], dtype=torch.int32), torch.tensor([2, 0, 4], dtype=torch.int32)]
+    pdist.EmulatedComm(2).or_reduce(fs)
+    assert fs[0].tolist() == fs[1].tolist() == [3, 0, 4]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world,chunk", [(1, None), (2, None), (3, 512), (8, 4096)])
+def test_distributed_hot_path_emulated(oracle, world, chunk):
+    """R ranks as R contexts on one GPU: counts, filter, solid k-mers, adjacency and seeds equal the
+    single-node oracle"""
+    k = 32
+    g = synth.random_genome(12000, 17)
+    reads = synth.reads_as_bytes(synth.simulate_reads(g, 30, 120, 0.01, 18))
+    reads[3] = reads[3][:40] + b"N" + reads[3][41:]
+    seq, off = reads_to_arrays(reads)
+    fs, nh = _lib.estimate_bloomfilter(int(off[-1]), k)
+    okeys, ocounts = oracle.count_short_kmers(seq, off)
+    obits, oseeds, _, oadds = oracle.make_bf(seq, off, k, okeys, ocounts, fs, nh)
+    osolid = oracle.solid_kmers(seq, off, k, okeys, ocounts)[:, 0]
+
+    bounds = np.linspace(0, len(reads), world + 1).astype(int)
+    ctxs = []
+    for r in range(world):
+        s, o = reads_to_arrays(reads[bounds[r]:bounds[r + 1]])
+        c = _lib.Context(0)
+        c.load_ascii(s, o)
+        ctxs.append(c)
+    try:
+        stats = pdist.run_hot_path(ctxs, pdist.EmulatedComm(world), k, fs, nh, table_slots=max(2 * len(okeys) // world, 4096),
+                                   chunk_words=chunk)
+        assert sum(s["owned_positions"] for s in stats) == int(ocounts.sum())
+        assert sum(s["owned_distinct21"] for s in stats) == len(okeys)
+        assert sum(s["n_adds"] for s in stats) == oadds
+        keys = np.concatenate([c.short_kmer_export()[0] for c in ctxs])
+        counts = np.concatenate([c.short_kmer_export()[1] for c in ctxs])
+        o = np.argsort(keys)
+        assert np.array_equal(keys[o], okeys) and np.array_equal(counts[o], ocounts)
+        L = _lib.lib()
+        for r, c in enumerate(ctxs):   # every key sits on its owner
+            kk = c.short_kmer_export()[0]
+            assert all(L.p3_owner_of_key(int(x), world) == r for x in kk[:: max(1, len(kk) // 200)])
+            assert np.array_equal(c.bf_export(), obits)
+            assert np.array_equal(c.seed_export(), oseeds[bounds[r]:bounds[r + 1]])
+        kmers = np.concatenate([c.dbg_export(sort=False)[0] for c in ctxs])
+        adj = np.concatenate([c.dbg_export(sort=False)[1] for c in ctxs])
+        o = np.argsort(kmers)
+        kmers, adj = kmers[o], adj[o]
+        assert np.array_equal(kmers, osolid)
+        for i in range(0, len(osolid), max(1, len(osolid) // 1500)):
+            assert adj[i] == oracle.check_directions(obits, fs, nh, osolid[i:i + 1], k)
+    finally:
+        for c in ctxs:
+            c.close()
