@@ -538,7 +538,7 @@ __global__ void seeds_kernel(const uint64_t *__restrict__ off, uint64_t n_reads,
 // non-members (which mostly fail after a few probes) walk the filter.
 __global__ void __launch_bounds__(256)
 adjacency_kernel(const uint64_t *__restrict__ kmers, uint64_t n, int k, Bloom bf, const uint64_t *__restrict__ set,
-                 uint64_t nbs, uint8_t *__restrict__ adj, Stats *st) {
+                 uint64_t nbs, const uint64_t *__restrict__ set_b, uint64_t nbs_b, uint8_t *__restrict__ adj, Stats *st) {
     const int lane = threadIdx.x & 31;
     const int d = lane & 7, g = lane >> 3;
     uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
@@ -551,7 +551,8 @@ adjacency_kernel(const uint64_t *__restrict__ kmers, uint64_t n, int k, Bloom bf
             uint64_t nb = neighbour(__ldg(kmers + i), d, k);
             uint64_t rc = revcomp(nb, k);
             uint64_t c = nb <= rc ? nb : rc;   // IsRecorded canonicalises (DeBruijnGraph.cpp:320-321)
-            rec = (set && set_contains(set, nbs, c)) || bloom_query(bf, c);
+            // set_b (multi-GPU): the rank's locally seen solid k-mers, which their owners added
+            rec = (set && set_contains(set, nbs, c)) || (set_b && set_contains(set_b, nbs_b, c)) || bloom_query(bf, c);
         }
         unsigned m = __ballot_sync(0xffffffffu, rec);
         if (d == 0 && i < n) {
@@ -713,6 +714,7 @@ struct p3_ctx {
     uint32_t *d_proven2 = nullptr; uint64_t cap_proven = 0;
     uint64_t *d_set = nullptr; uint64_t nbs = 0;
     bool set_valid = false;   // d_set holds a subset of what the current filter contains
+    const uint64_t *d_set_b = nullptr; uint64_t nbs_b = 0;   // multi-GPU: second (locally seen) solid set, not owned here
     uint64_t *d_list = nullptr; uint64_t list_cap = 0;
     uint32_t *d_bloom = nullptr; uint64_t bloom_words = 0;
     int64_t *d_seed = nullptr;
@@ -1209,6 +1211,7 @@ int p3_make_bf(p3_ctx *c, uint32_t k, uint64_t filter_size, uint32_t num_hashes,
     CU(cudaEventElapsedTime(&c->ms[2], c->ev[4], c->ev[5]));
     CU(cudaEventElapsedTime(&c->ms[3], c->ev[5], c->ev[6]));
     c->have_bf = true; c->have_solid = true; c->have_adj = false; c->set_valid = true;
+    c->d_set_b = nullptr; c->nbs_b = 0;
     return P3_OK;
 }
 
@@ -1322,7 +1325,7 @@ int p3_dbg_adjacency(p3_ctx *c) {
     CU(cudaMemsetAsync(&c->d_stats->n_edges, 0, sizeof(unsigned long long), c->stream));
     CU(cudaEventRecord(c->ev[7], c->stream));
     if (n) {
-        adjacency_kernel<<<c->grid(), 256, 0, c->stream>>>(c->d_list, n, (int)c->k, c->bloom(), c->set_valid ? c->d_set : nullptr, c->nbs, c->d_adj, c->d_stats);
+        adjacency_kernel<<<c->grid(), 256, 0, c->stream>>>(c->d_list, n, (int)c->k, c->bloom(), c->set_valid ? c->d_set : nullptr, c->nbs, c->set_valid ? c->d_set_b : nullptr, c->nbs_b, c->d_adj, c->d_stats);
         c->launches++;
         CU(cudaGetLastError());
     }
@@ -1347,7 +1350,7 @@ int p3_dbg_close(p3_ctx *c, const uint64_t *h_roots, uint64_t n_roots, uint64_t 
         if (to <= from) return P3_OK;
         uint64_t nn = to - from, warps = (nn + 3) / 4;
         unsigned blocks = (unsigned)std::min<uint64_t>((warps + 7) / 8, (uint64_t)c->grid());
-        adjacency_kernel<<<blocks, 256, 0, c->stream>>>(c->d_list + from, nn, (int)c->k, c->bloom(), nullptr, 0, c->d_adj + from, nullptr);
+        adjacency_kernel<<<blocks, 256, 0, c->stream>>>(c->d_list + from, nn, (int)c->k, c->bloom(), nullptr, 0, nullptr, 0, c->d_adj + from, nullptr);
         c->launches++;
         CU(cudaGetLastError());
         return P3_OK;
@@ -1424,7 +1427,7 @@ int p3_check_directions(p3_ctx *c, const uint64_t *h_kmers, uint64_t n, uint8_t 
     CU(cudaMalloc(&dout, n));
     uint64_t warps = (n + 3) / 4;
     unsigned blocks = (unsigned)std::min<uint64_t>((warps + 7) / 8, (uint64_t)c->grid());
-    adjacency_kernel<<<blocks, 256, 0, c->stream>>>(dk, n, (int)c->k, c->bloom(), c->set_valid ? c->d_set : nullptr, c->nbs, dout, nullptr);
+    adjacency_kernel<<<blocks, 256, 0, c->stream>>>(dk, n, (int)c->k, c->bloom(), c->set_valid ? c->d_set : nullptr, c->nbs, c->set_valid ? c->d_set_b : nullptr, c->nbs_b, dout, nullptr);
     c->launches++;
     CU(cudaMemcpyAsync(h_mask, dout, n, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));

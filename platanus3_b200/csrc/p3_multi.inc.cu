@@ -75,6 +75,7 @@ struct MgState {   // extra per-context state of the multi-GPU path
     uint64_t *d_set2 = nullptr, *d_list2 = nullptr; uint64_t nbs2 = 0;
     uint64_t rec_cap = 0;
     uint64_t n_local = 0;
+    bool swapped = false;   // c->d_set/d_list currently hold the OWNED set (p3_mg_owned_end swapped them in)
 };
 static std::unordered_map<p3_ctx *, MgState> g_mg;   // keyed by context (p3_ctx layout stays private to p3_gpu.cu)
 
@@ -266,7 +267,15 @@ int p3_mg_solid_local(p3_ctx *c, uint32_t k, uint64_t solid_slots, uint64_t *n_a
     if (!c || !c->d_good21) return fail(P3_ERR_STATE, "p3_mg_solid_local: run p3_mg_cover_begin first");
     if (k < P3_MIN_K || k > P3_MAX_K) return fail(P3_ERR_ARG, "k outside [21,32] is not supported by this build");
     CU(cudaSetDevice(c->device));
-    c->k = k; c->set_valid = false;
+    c->k = k; c->set_valid = false; c->d_set_b = nullptr; c->nbs_b = 0;
+    {   // give the local-set buffers of the previous run back to their role so that they are reused
+        MgState &m = g_mg[c];
+        if (m.swapped) {
+            std::swap(c->d_set, m.d_set2); std::swap(c->d_list, m.d_list2); std::swap(c->nbs, m.nbs2);
+            c->list_cap = c->nbs * 4;
+            m.swapped = false;
+        }
+    }
     CU(cudaMemsetAsync(&c->d_stats->n_adds, 0, sizeof(unsigned long long) * 5, c->stream));
     solid_kernel<<<c->grid(), 256, 0, c->stream>>>(c->d_good21, c->n_words, (int)k, c->d_solid, c->d_stats);
     c->launches++;
@@ -312,6 +321,7 @@ int p3_mg_owned_begin(p3_ctx *c, uint64_t owned_slots) {
     if (!c) return fail(P3_ERR_ARG, "null ctx");
     CU(cudaSetDevice(c->device));
     MgState &m = g_mg[c];
+    if (m.swapped) return fail(P3_ERR_STATE, "p3_mg_owned_begin: run p3_mg_solid_local first");
     uint64_t nbs = (std::max<uint64_t>(owned_slots, 1024) + 3) / 4;
     if (!m.d_set2 || m.nbs2 != nbs) {
         dfree(m.d_set2); dfree(m.d_list2);
@@ -348,6 +358,7 @@ int p3_mg_owned_end(p3_ctx *c, uint32_t k, uint64_t filter_size, uint32_t num_ha
     if (rc) return rc;
     std::swap(c->d_set, m.d_set2); std::swap(c->d_list, m.d_list2); std::swap(c->nbs, m.nbs2);
     c->list_cap = c->nbs * 4;
+    m.swapped = true;
     CU(cudaMemsetAsync(&c->d_stats->n_distinct_solid, 0, sizeof(unsigned long long), c->stream));
     compact_set_kernel<<<c->grid(), 256, 0, c->stream>>>(c->d_set, c->nbs * 4, c->d_list, c->list_cap, c->d_stats);
     c->launches++;
@@ -359,6 +370,7 @@ int p3_mg_owned_end(p3_ctx *c, uint32_t k, uint64_t filter_size, uint32_t num_ha
     if (rc) return rc;
     CU(cudaStreamSynchronize(c->stream));
     c->have_bf = true; c->have_solid = true; c->have_adj = false; c->set_valid = true;
+    c->d_set_b = m.d_set2; c->nbs_b = m.nbs2;   // after the swap: the locally seen solid k-mers
     if (n_owned) *n_owned = c->h_stats.n_distinct_solid;
     return P3_OK;
 }

@@ -152,10 +152,13 @@ def run_hot_path(ctxs, comm, k, filter_size, num_hashes, table_slots, solid_slot
         comm.dist.all_reduce(t, op=comm.dist.ReduceOp.MAX, group=comm.group)
         n_chunks = int(t.item())
 
+    import time
+    sub = dict(bin=0.0, exchange=0.0, insert=0.0)
     # ---- A: count ------------------------------------------------------------------------------
     for c in ctxs:
         _check(L.p3_mg_count_begin(c.h, table_slots, 1))
     for ch in range(n_chunks):
+        t0 = time.perf_counter()
         sends = []
         for c, r, nw in zip(ctxs, comm.local_ranks, n_words):
             w0, w1 = min(ch * cw, nw), min((ch + 1) * cw, nw)
@@ -167,13 +170,17 @@ def run_hot_path(ctxs, comm, k, filter_size, num_hashes, table_slots, solid_slot
             words = torch.empty(max(tot, 1), dtype=torch.int32, device=device)
             _check(L.p3_mg_owner_scatter(c.h, w, r, w0, w1, keys.data_ptr(), words.data_ptr()))
             sends.append(([keys[:tot], words[:tot]], counts))
+        t1 = time.perf_counter()
         recvs = _exchange(comm, sends)
         del sends
+        t2 = time.perf_counter()
         for c, (tensors, rcounts) in zip(ctxs, recvs):
             n = sum(rcounts)
             if n:
                 _check(L.p3_mg_count_records(c.h, tensors[0].data_ptr(), tensors[1].data_ptr(), n))
         del recvs
+        t3 = time.perf_counter()
+        sub["bin"] += 1e3 * (t1 - t0); sub["exchange"] += 1e3 * (t2 - t1); sub["insert"] += 1e3 * (t3 - t2)
     for c, st in zip(ctxs, stats):
         _check(L.p3_mg_count_end(c.h))
         a, b = C.c_uint64(), C.c_uint64()
@@ -241,4 +248,5 @@ def run_hot_path(ctxs, comm, k, filter_size, num_hashes, table_slots, solid_slot
     ms = {marks[i][0]: marks[i - 1][1].elapsed_time(marks[i][1]) for i in range(1, len(marks))}
     for st in stats:
         st["stage_ms"] = ms
+        st["count_sub_ms"] = sub
     return stats
