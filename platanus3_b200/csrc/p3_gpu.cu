@@ -171,14 +171,15 @@ struct ScatterSmem {
     uint32_t hist[kMaxParts];             //  4 KB
     uint32_t offs[kMaxParts];             //  4 KB
     unsigned long long gbase[kMaxParts];  //  8 KB
-    uint32_t warp_tot[kTileWords / 32];
+    uint32_t warp_tot[8];
     uint32_t total;
 };
 
 // exclusive scan of sm.hist[0..P) into sm.offs, one global claim per non-empty partition into
-// sm.gbase, total into sm.total. Called by all kTileWords threads between two __syncthreads().
+// sm.gbase, total into sm.total. Called by all NT threads of the block between two __syncthreads().
+template <int NT>
 __device__ __forceinline__ void tile_scan_and_claim(ScatterSmem &sm, uint32_t P, unsigned long long *cursor, int tid) {
-    const uint32_t per_thread = (P + kTileWords - 1) / kTileWords;   // <= 8
+    const uint32_t per_thread = (P + NT - 1) / NT;
     uint32_t local = 0;
     const uint32_t b0 = tid * per_thread;
     for (uint32_t j = 0; j < per_thread; j++) { uint32_t i = b0 + j; if (i < P) local += sm.hist[i]; }
@@ -199,11 +200,14 @@ __device__ __forceinline__ void tile_scan_and_claim(ScatterSmem &sm, uint32_t P,
             run += h;
         }
     }
-    if (tid == kTileWords - 1) sm.total = wbase + incl;
+    if (tid == NT - 1) sm.total = wbase + incl;
 }
 
+// 256 threads per 128-word tile: thread t handles 16 of the 32 offsets of word t>>1, so the tile's
+// shared memory is covered by 8 warps instead of 4 (occupancy was 18 % with 4)
+constexpr int kScatterThreads = 2 * kTileWords;
 template <bool HAS_MASK, int PMODE>
-__global__ void __launch_bounds__(kTileWords)
+__global__ void __launch_bounds__(kScatterThreads)
 scatter21_kernel(const uint64_t *__restrict__ packed, const uint32_t *__restrict__ rend,
                  const uint32_t *__restrict__ nmask, uint64_t w0, uint64_t w1, uint32_t P,
                  unsigned long long *cursor, uint64_t *__restrict__ bkeys, uint32_t *__restrict__ bword,
@@ -212,11 +216,13 @@ scatter21_kernel(const uint64_t *__restrict__ packed, const uint32_t *__restrict
     ScatterSmem &sm = *reinterpret_cast<ScatterSmem *>(smem_raw);
     const uint64_t W21 = ~0ULL << (64 - (kShortK - 1));
     const int tid = threadIdx.x;
+    const int wt = tid >> 1;            // word of the tile
+    const int o0 = (tid & 1) * 16;      // first offset this thread handles
     const uint64_t n_tiles = (w1 - w0 + kTileWords - 1) / kTileWords;
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        for (uint32_t i = tid; i < P; i += kTileWords) sm.hist[i] = 0;
+        for (uint32_t i = tid; i < P; i += kScatterThreads) sm.hist[i] = 0;
         __syncthreads();
-        const uint64_t w = w0 + tile * kTileWords + tid;
+        const uint64_t w = w0 + tile * kTileWords + wt;
         uint64_t hi = 0, lo = 0, mhi = 0, mlo = 0;
         uint32_t valid = 0;
         if (w < w1) {
@@ -225,33 +231,41 @@ scatter21_kernel(const uint64_t *__restrict__ packed, const uint32_t *__restrict
             if (HAS_MASK) { mhi = spread32(__ldg(nmask + w)); mlo = spread32(__ldg(nmask + w + 1)); }
 #pragma unroll
             for (int o = 0; o < 32; o++) valid |= (((E << o) & W21) == 0) ? (0x80000000u >> o) : 0u;
-            valid_plane[w] = valid;
+            if ((tid & 1) == 0) valid_plane[w] = valid;
         }
-        // pass 1: arrival rank inside (tile, partition)
-#pragma unroll 4
-        for (int o = 0; o < 32; o++) {
-            if (!(valid & (0x80000000u >> o))) continue;
-            uint64_t key = canonical_from_window(window(hi, lo, o), HAS_MASK ? window(mhi, mlo, o) : 0, kShortK);
-            sm.rank[o][tid] = (uint16_t)atomicAdd(&sm.hist[pid_of<PMODE>(key, P)], 1u);
+        // pass 1: canonical key + partition id once per position, kept in registers as
+        // [pid:12 @52 | key:42]; arrival rank inside (tile, partition) from the shared histogram
+        uint64_t kp[16];
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+            const int o = o0 + q;
+            kp[q] = ~0ULL;
+            if (valid & (0x80000000u >> o)) {
+                uint64_t key = canonical_from_window(window(hi, lo, o), HAS_MASK ? window(mhi, mlo, o) : 0, kShortK);
+                uint32_t pt = pid_of<PMODE>(key, P);
+                kp[q] = key | ((uint64_t)pt << 52);
+                sm.rank[o][wt] = (uint16_t)atomicAdd(&sm.hist[pt], 1u);
+            }
         }
         __syncthreads();
-        tile_scan_and_claim(sm, P, cursor, tid);
+        tile_scan_and_claim<kScatterThreads>(sm, P, cursor, tid);
         __syncthreads();
         // pass 2: place records sorted by partition
-#pragma unroll 4
-        for (int o = 0; o < 32; o++) {
-            if (!(valid & (0x80000000u >> o))) continue;
-            uint64_t key = canonical_from_window(window(hi, lo, o), HAS_MASK ? window(mhi, mlo, o) : 0, kShortK);
-            uint32_t pt = pid_of<PMODE>(key, P);
-            uint32_t idx = sm.offs[pt] + sm.rank[o][tid];
-            sm.key[idx] = key | ((uint64_t)o << kRecOffShift) | tag;
-            sm.part[idx] = (uint16_t)pt;
-            sm.loc[idx] = (uint16_t)tid;
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+            const int o = o0 + q;
+            if (kp[q] != ~0ULL) {
+                uint32_t pt = (uint32_t)(kp[q] >> 52);
+                uint32_t idx = sm.offs[pt] + sm.rank[o][wt];
+                sm.key[idx] = (kp[q] & kKey42) | ((uint64_t)o << kRecOffShift) | tag;
+                sm.part[idx] = (uint16_t)pt;
+                sm.loc[idx] = (uint16_t)wt;
+            }
         }
         __syncthreads();
         const uint32_t total = sm.total;
         const uint64_t tile_w0 = w0 + tile * kTileWords;
-        for (uint32_t i = tid; i < total; i += kTileWords) {
+        for (uint32_t i = tid; i < total; i += kScatterThreads) {
             uint32_t pt = sm.part[i];
             unsigned long long dst = sm.gbase[pt] + (i - sm.offs[pt]);
             bkeys[dst] = sm.key[i];
@@ -301,7 +315,7 @@ scatter_rec_kernel(const uint64_t *__restrict__ in, const uint32_t *__restrict__
             if (i < n) sm.rank[j][tid] = (uint16_t)atomicAdd(&sm.hist[pid_of<PMODE>(rec[j], P)], 1u);
         }
         __syncthreads();
-        tile_scan_and_claim(sm, P, cursor, tid);
+        tile_scan_and_claim<kTileWords>(sm, P, cursor, tid);
         __syncthreads();
 #pragma unroll
         for (int j = 0; j < 32; j++) {
@@ -333,7 +347,7 @@ scatter_rec_kernel(const uint64_t *__restrict__ in, const uint32_t *__restrict__
 // gridDim * kSweepChunk records of each other, i.e. inside one or two partitions.
 constexpr int kSweepChunk = 2048;   // records per block per grab (8 per thread)
 constexpr int kSweepPer = kSweepChunk / 256;
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 insert_bins_kernel(const uint64_t *__restrict__ bkeys, const uint32_t *__restrict__ bword, uint64_t n,
                    Table table, Ovf ovf, Stats *st, uint64_t *__restrict__ cand_slot,
                    uint64_t *__restrict__ cand_pos, uint64_t cand_cap) {
@@ -949,8 +963,8 @@ static int count_binned(p3_ctx *c, uint64_t upper) {
         scan_parts_kernel<<<1, 256, 0, c->stream>>>(c->d_ghist, P, c->d_cursor, c->d_ghist + kMaxParts);
         CU(cudaEventRecord(c->ev[11], c->stream));
         unsigned sblocks = (unsigned)std::min<uint64_t>((w1 - w0 + kTileWords - 1) / kTileWords, (uint64_t)c->n_sm * 3);
-        if (c->d_nmask) scatter21_kernel<true, 0><<<sblocks, kTileWords, sizeof(ScatterSmem), c->stream>>>(c->d_packed, c->d_rend, c->d_nmask, w0, w1, P, c->d_cursor, c->d_bkeys, c->d_bword, c->d_valid, 0);
-        else scatter21_kernel<false, 0><<<sblocks, kTileWords, sizeof(ScatterSmem), c->stream>>>(c->d_packed, c->d_rend, nullptr, w0, w1, P, c->d_cursor, c->d_bkeys, c->d_bword, c->d_valid, 0);
+        if (c->d_nmask) scatter21_kernel<true, 0><<<sblocks, kScatterThreads, sizeof(ScatterSmem), c->stream>>>(c->d_packed, c->d_rend, c->d_nmask, w0, w1, P, c->d_cursor, c->d_bkeys, c->d_bword, c->d_valid, 0);
+        else scatter21_kernel<false, 0><<<sblocks, kScatterThreads, sizeof(ScatterSmem), c->stream>>>(c->d_packed, c->d_rend, nullptr, w0, w1, P, c->d_cursor, c->d_bkeys, c->d_bword, c->d_valid, 0);
         CU(cudaGetLastError());
         CU(cudaEventRecord(c->ev[12], c->stream));
         unsigned long long n_rec = 0;

@@ -133,8 +133,8 @@ int p3_mg_owner_scatter(p3_ctx *c, uint32_t n_ranks, uint32_t my_rank, uint64_t 
     CU(ensure(c->d_valid, c->cap_valid, sizeof(uint32_t) * (c->n_words + 1)));
     unsigned sblocks = (unsigned)std::min<uint64_t>(std::max<uint64_t>((w1 - w0 + kTileWords - 1) / kTileWords, 1), (uint64_t)c->n_sm * 3);
     const uint64_t tag = (uint64_t)my_rank << kRecRankShift;
-    if (c->d_nmask) scatter21_kernel<true, 1><<<sblocks, kTileWords, sizeof(ScatterSmem), c->stream>>>(c->d_packed, c->d_rend, c->d_nmask, w0, w1, n_ranks, c->d_cursor, d_keys, d_words, c->d_valid, tag);
-    else scatter21_kernel<false, 1><<<sblocks, kTileWords, sizeof(ScatterSmem), c->stream>>>(c->d_packed, c->d_rend, nullptr, w0, w1, n_ranks, c->d_cursor, d_keys, d_words, c->d_valid, tag);
+    if (c->d_nmask) scatter21_kernel<true, 1><<<sblocks, kScatterThreads, sizeof(ScatterSmem), c->stream>>>(c->d_packed, c->d_rend, c->d_nmask, w0, w1, n_ranks, c->d_cursor, d_keys, d_words, c->d_valid, tag);
+    else scatter21_kernel<false, 1><<<sblocks, kScatterThreads, sizeof(ScatterSmem), c->stream>>>(c->d_packed, c->d_rend, nullptr, w0, w1, n_ranks, c->d_cursor, d_keys, d_words, c->d_valid, tag);
     c->launches++;
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(c->stream));
