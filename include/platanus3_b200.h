@@ -9,7 +9,8 @@
  *
  * k-mer words: W = ceil(2k/64) little-endian uint64 words holding the same 2k-bit integer as
  * the reference's std::bitset<2k> (first base in the most significant 2 bits, A=0 C=1 G=2 T=3;
- * reference src/BitCalc.cpp:8-19). This build supports 21 <= k <= 32 on the device (W = 1).
+ * reference src/BitCalc.cpp:8-19). The device path supports 21 <= k <= 3001; the host walk
+ * (p3_dbg_close, p3_assemble_file) is limited to k <= 32 (W = 1) in this build.
  *
  * 2-bit staging layout ("packed reads"): all reads back to back, 32 bases per uint64 word,
  * base j of the stream in word j/32 at bits [63-2(j%32)-1, 63-2(j%32)] (MSB first), zero
@@ -38,7 +39,8 @@ extern "C" {
 #define P3_SHORTK 21        /* reference src/Options.cpp:14 shortk_length */
 #define P3_COV_THRESHOLD 2  /* reference src/MakeBloomFilter.cpp:28 cov_threshold */
 #define P3_MIN_K 21
-#define P3_MAX_K 32
+#define P3_MAX_K 3001      /* device path: any k in [21,3001] (the reference's largest bitset) */
+#define P3_MAX_K_WALK 32   /* host unitig walk / p3_dbg_close / p3_assemble_file: single-word k-mers */
 
 typedef struct p3_ctx p3_ctx;
 

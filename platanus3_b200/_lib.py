@@ -279,6 +279,7 @@ class Context:
         return bits[: self.total_bases]
 
     def bf_add(self, kmers):
+        """kmers: uint64[n] (k <= 32) or uint64[n, W]"""
         kmers = np.ascontiguousarray(kmers, np.uint64)
         check(self.L.p3_bf_add(self.h, _ptr(kmers), len(kmers)))
 
@@ -308,8 +309,19 @@ class Context:
         return n.value
 
     def dbg_export(self, sort=True):
+        """distinct k-mers and adjacency bytes; k <= 32: kmers is uint64[n], else uint64[n, W] (little-endian words)"""
         n = C.c_uint64()
         self.L.p3_dbg_export(self.h, None, None, 0, C.byref(n))   # size query (capacity error ignored)
+        W = (2 * self.k + 63) // 64
+        if W > 1:
+            kmers = np.zeros((max(n.value, 1), W), np.uint64)
+            adj = np.zeros(max(n.value, 1), np.uint8)
+            check(self.L.p3_dbg_export(self.h, _ptr(kmers), _ptr(adj), len(adj), C.byref(n)))
+            kmers, adj = kmers[: n.value], adj[: n.value]
+            if sort and len(kmers):
+                o = np.lexsort(tuple(kmers[:, j] for j in range(W)))   # last key (top word) is primary
+                kmers, adj = kmers[o], adj[o]
+            return kmers, adj
         kmers = np.zeros(max(n.value, 1), np.uint64)
         adj = np.zeros(max(n.value, 1), np.uint8)
         check(self.L.p3_dbg_export(self.h, _ptr(kmers), _ptr(adj), len(kmers), C.byref(n)))

@@ -425,7 +425,7 @@ int p3_assemble_file(const char *read_path, uint32_t k, uint64_t m, int threads,
                      const char *gfa_path, const char *log_path, uint64_t *stats) {
     (void)threads;
     Log log; log.path = log_path ? log_path : "";
-    if (k < P3_MIN_K || k > P3_MAX_K) { g_host_err = "k outside [21,32] is not supported by this build"; return P3_ERR_ARG; }
+    if (k < P3_MIN_K || k > P3_MAX_K_WALK) { g_host_err = "k outside [21,32] is not supported by the host walk of this build"; return P3_ERR_ARG; }
     p3_reads *rd = nullptr;
     int rc = p3_load_file(read_path, k, &rd);
     if (rc) return rc;

@@ -749,6 +749,11 @@ struct p3_ctx {
 };
 
 static void mg_release(struct p3_ctx *c);   // p3_multi.inc.cu
+static void long_release(struct p3_ctx *c); // p3_long.inc.cu
+static int make_bf_long(struct p3_ctx *c, uint32_t k, uint64_t solid_slots);
+static int adjacency_long(struct p3_ctx *c, const uint64_t *d_words, uint64_t n, uint8_t *d_adj, struct p3::Stats *st);
+static const uint64_t *long_words(struct p3_ctx *c);
+static int long_batch(struct p3_ctx *c, int op, uint32_t k, const uint64_t *h_kmers, uint64_t n, void *h_out);
 template <typename T> static void dfree(T *&p) { if (p) { cudaFree((void *)p); p = nullptr; } }
 // grow-only device buffer: reallocates only when the request exceeds the capacity, so repeated
 // runs on same-sized inputs never touch cudaMalloc/cudaFree (both synchronise the device)
@@ -840,6 +845,7 @@ void p3_destroy(p3_ctx *c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     mg_release(c);
+    long_release(c);
     free_reads(c); free_bf(c);
     dfree(c->d_table); dfree(c->d_proven2); dfree(c->d_bkeys); dfree(c->d_bword); dfree(c->d_valid);
     dfree(c->d_cand_slot); dfree(c->d_cand_pos); dfree(c->d_ghist); dfree(c->d_cursor); dfree(c->d_ovf_keys); dfree(c->d_ovf_wraps); dfree(c->d_stats);
@@ -1094,7 +1100,7 @@ int p3_short_kmer_lookup(p3_ctx *c, const uint64_t *h_keys, uint64_t n, uint64_t
 
 // ---- stage B -----------------------------------------------------------------------------------
 static int alloc_bloom(p3_ctx *c, uint32_t k, uint64_t filter_size, uint32_t num_hashes) {
-    if (k < P3_MIN_K || k > P3_MAX_K) return fail(P3_ERR_ARG, "k outside [21,32] is not supported by this build");
+    if (k < P3_MIN_K || k > P3_MAX_K) return fail(P3_ERR_ARG, "k outside [21,3001] is not supported");
     if (filter_size == 0) return fail(P3_ERR_ARG, "filter_size == 0 (the reference divides by zero here)");
     if (num_hashes > 255) return fail(P3_ERR_ARG, "num_hashes > 255 (uint8_t in the reference)");
     uint64_t words = (filter_size + 31) / 32;
@@ -1193,6 +1199,17 @@ int p3_make_bf(p3_ctx *c, uint32_t k, uint64_t filter_size, uint32_t num_hashes,
     CU(cudaGetLastError());
     CU(cudaEventRecord(c->ev[3], c->stream));
 
+    if (k > 32) {   // multi-word k-mers: p3_long.inc.cu
+        rc = make_bf_long(c, k, solid_slots);
+        if (rc) return rc;
+        CU(cudaEventElapsedTime(&c->ms_bloom, c->ev[14], c->ev[15]));
+        CU(cudaEventElapsedTime(&c->ms[1], c->ev[2], c->ev[3]));
+        CU(cudaEventElapsedTime(&c->ms[2], c->ev[4], c->ev[5]));
+        CU(cudaEventElapsedTime(&c->ms[3], c->ev[5], c->ev[6]));
+        c->have_bf = true; c->have_solid = true; c->have_adj = false; c->set_valid = false;
+        c->d_set_b = nullptr; c->nbs_b = 0;
+        return P3_OK;
+    }
     // B2a: solid plane + n_adds; number of distinct good 21-mers sizes the solid set
     solid_kernel<<<c->grid(), 256, 0, c->stream>>>(c->d_good21, c->n_words, (int)k, c->d_solid, c->d_stats);
     c->launches++;
@@ -1282,6 +1299,7 @@ static int with_kmers(p3_ctx *c, const uint64_t *h_kmers, uint64_t n, uint64_t *
 int p3_bf_add(p3_ctx *c, const uint64_t *h_kmers, uint64_t n) {
     if (!c || !c->have_bf) return fail(P3_ERR_STATE, "p3_bf_add: no filter");
     if (n == 0) return P3_OK;
+    if (c->k > 32) return long_batch(c, 0, c->k, h_kmers, n, nullptr);
     CU(cudaSetDevice(c->device));
     uint64_t *dk = nullptr;
     int rc = with_kmers(c, h_kmers, n, &dk);
@@ -1296,6 +1314,7 @@ int p3_bf_add(p3_ctx *c, const uint64_t *h_kmers, uint64_t n) {
 int p3_bf_possibly_contains(p3_ctx *c, const uint64_t *h_kmers, uint64_t n, uint8_t *h_out) {
     if (!c || !c->have_bf) return fail(P3_ERR_STATE, "p3_bf_possibly_contains: no filter");
     if (n == 0) return P3_OK;
+    if (c->k > 32) return long_batch(c, 1, c->k, h_kmers, n, h_out);
     CU(cudaSetDevice(c->device));
     uint64_t *dk = nullptr; uint8_t *dout = nullptr;
     int rc = with_kmers(c, h_kmers, n, &dk);
@@ -1311,8 +1330,9 @@ int p3_bf_possibly_contains(p3_ctx *c, const uint64_t *h_kmers, uint64_t n, uint
 
 int p3_double_hash(p3_ctx *c, uint32_t k, const uint64_t *h_kmers, uint64_t n, uint64_t *h_out) {
     if (!c) return fail(P3_ERR_ARG, "null ctx");
-    if (k < 1 || k > 32) return fail(P3_ERR_ARG, "p3_double_hash: k must be <= 32");
+    if (k < 1 || k > P3_MAX_K) return fail(P3_ERR_ARG, "p3_double_hash: k must be <= 3001");
     if (n == 0) return P3_OK;
+    if (k > 32) return long_batch(c, 2, k, h_kmers, n, h_out);
     CU(cudaSetDevice(c->device));
     uint64_t *dk = nullptr, *dout = nullptr;
     int rc = with_kmers(c, h_kmers, n, &dk);
@@ -1338,7 +1358,10 @@ int p3_dbg_adjacency(p3_ctx *c) {
     }
     CU(cudaMemsetAsync(&c->d_stats->n_edges, 0, sizeof(unsigned long long), c->stream));
     CU(cudaEventRecord(c->ev[7], c->stream));
-    if (n) {
+    if (n && c->k > 32) {
+        int rcl = adjacency_long(c, long_words(c), n, c->d_adj, c->d_stats);
+        if (rcl) return rcl;
+    } else if (n) {
         adjacency_kernel<<<c->grid(), 256, 0, c->stream>>>(c->d_list, n, (int)c->k, c->bloom(), c->set_valid ? c->d_set : nullptr, c->nbs, c->set_valid ? c->d_set_b : nullptr, c->nbs_b, c->d_adj, c->d_stats);
         c->launches++;
         CU(cudaGetLastError());
@@ -1356,6 +1379,7 @@ int p3_dbg_adjacency(p3_ctx *c) {
 // and the given walk roots; *n_total = solid + root + phantom k-mers
 int p3_dbg_close(p3_ctx *c, const uint64_t *h_roots, uint64_t n_roots, uint64_t *n_total) {
     if (!c || !c->have_adj) return fail(P3_ERR_STATE, "p3_dbg_close: run p3_dbg_adjacency first");
+    if (c->k > 32) return fail(P3_ERR_ARG, "p3_dbg_close: k > 32 is not supported yet (the host walk is single-word)");
     CU(cudaSetDevice(c->device));
     // from here on the set also holds k-mers that need not answer possiblyContains (roots), so it
     // must not short-cut Bloom queries any more
@@ -1422,7 +1446,8 @@ int p3_dbg_export(p3_ctx *c, uint64_t *h_kmers, uint8_t *h_adj, uint64_t cap, ui
     if (n) *n = nd;
     if (cap < nd) return fail(P3_ERR_ARG, "p3_dbg_export: capacity too small");
     if (nd == 0) return P3_OK;
-    if (h_kmers) CU(cudaMemcpyAsync(h_kmers, c->d_list, sizeof(uint64_t) * nd, cudaMemcpyDeviceToHost, c->stream));
+    const uint64_t W = (2 * (uint64_t)c->k + 63) / 64;
+    if (h_kmers) CU(cudaMemcpyAsync(h_kmers, c->k > 32 ? long_words(c) : c->d_list, sizeof(uint64_t) * nd * W, cudaMemcpyDeviceToHost, c->stream));
     if (h_adj) {
         if (!c->have_adj) return fail(P3_ERR_STATE, "p3_dbg_export: run p3_dbg_adjacency first");
         CU(cudaMemcpyAsync(h_adj, c->d_adj, nd, cudaMemcpyDeviceToHost, c->stream));
@@ -1434,6 +1459,7 @@ int p3_dbg_export(p3_ctx *c, uint64_t *h_kmers, uint8_t *h_adj, uint64_t cap, ui
 int p3_check_directions(p3_ctx *c, const uint64_t *h_kmers, uint64_t n, uint8_t *h_mask) {
     if (!c || !c->have_bf) return fail(P3_ERR_STATE, "p3_check_directions: no filter");
     if (n == 0) return P3_OK;
+    if (c->k > 32) return long_batch(c, 3, c->k, h_kmers, n, h_mask);
     CU(cudaSetDevice(c->device));
     uint64_t *dk = nullptr; uint8_t *dout = nullptr;
     int rc = with_kmers(c, h_kmers, n, &dk);
@@ -1491,4 +1517,5 @@ int p3_bf_params(p3_ctx *c, uint64_t *filter_size, uint32_t *num_hashes, uint32_
 
 }  // extern "C"
 
+#include "p3_long.inc.cu"
 #include "p3_multi.inc.cu"

@@ -265,7 +265,7 @@ int p3_mg_cover_clear(p3_ctx *c, const uint64_t *d_pos, uint64_t n) {
 // solid plane (window AND of the coverage plane), seeds, and the locally distinct solid k-mers
 int p3_mg_solid_local(p3_ctx *c, uint32_t k, uint64_t solid_slots, uint64_t *n_adds, uint64_t *n_local) {
     if (!c || !c->d_good21) return fail(P3_ERR_STATE, "p3_mg_solid_local: run p3_mg_cover_begin first");
-    if (k < P3_MIN_K || k > P3_MAX_K) return fail(P3_ERR_ARG, "k outside [21,32] is not supported by this build");
+    if (k < P3_MIN_K || k > 32) return fail(P3_ERR_ARG, "multi-GPU path: k outside [21,32] is not supported yet");
     CU(cudaSetDevice(c->device));
     c->k = k; c->set_valid = false; c->d_set_b = nullptr; c->nbs_b = 0;
     {   // give the local-set buffers of the previous run back to their role so that they are reused

@@ -32,6 +32,9 @@ CASES = [
     ("k32_err", 32, 0, 1500, 50, 100, 0.01, "fastq"),
     ("k32_m", 32, 200003, 2000, 10, 90, 0.02, "fasta"),
     ("k25_quirks", 25, 60013, 1500, 10, 70, 0.005, "fasta"),
+    # multi-word k-mers, two of the values the reference's own Assemble_k offers (Assemble.cpp:38-41)
+    ("k63_err", 63, 0, 1500, 50, 150, 0.005, "fasta"),
+    ("k101_m", 101, 300007, 1500, 30, 250, 0.003, "fastq"),
 ]
 
 

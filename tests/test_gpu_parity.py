@@ -266,3 +266,84 @@ def test_properties_at_scale(ctx):
         back = ctx.check_directions(nbr)
         left_base = (sub[has] >> np.uint64(2 * k - 2)).astype(np.int64)
         assert np.all((back >> left_base.astype(np.uint8)) & 1 == 1)
+
+
+# ---------------------------------------------------------------- multi-word k (33 <= k <= 3001)
+def _long_check(ctx, oracle, reads, k, m=0, n_adj=400):
+    from _checkers import nwords
+    W = nwords(k)
+    seq, off = reads_to_arrays(reads)
+    fs, nh = (m, 10) if m else _lib.estimate_bloomfilter(int(off[-1]), k)
+    ctx.load_ascii(seq, off)
+    ctx.count_short_kmers()
+    okeys, ocounts = oracle.count_short_kmers(seq, off)
+    n_adds, n_solid = ctx.make_bf(k, fs, nh)
+    obits, oseeds, osolid_flags, oadds = oracle.make_bf(seq, off, k, okeys, ocounts, fs, nh, want_solid=True)
+    assert n_adds == oadds
+    assert np.array_equal(ctx.solid_flags_export(), osolid_flags)
+    assert np.array_equal(ctx.seed_export(), oseeds)
+    assert np.array_equal(ctx.bf_export(), obits)
+    osolid = oracle.solid_kmers(seq, off, k, okeys, ocounts)
+    n_kmers, n_edges = ctx.dbg_adjacency()
+    kmers, adj = ctx.dbg_export()
+    assert n_kmers == n_solid == len(osolid)
+    assert kmers.shape == (len(osolid), W) and np.array_equal(kmers, osolid)
+    assert n_edges == int(np.unpackbits(adj).sum())
+    for i in range(0, len(osolid), max(1, len(osolid) // n_adj)):
+        assert adj[i] == oracle.check_directions(obits, fs, nh, osolid[i], k), (k, i)
+    return dict(bits=obits, fs=fs, nh=nh, solid=osolid)
+
+
+@pytest.mark.parametrize("k,rl", [(33, 100), (47, 120), (63, 150), (64, 150), (65, 150), (96, 200), (101, 250)])
+def test_long_k_pipeline(ctx, oracle, k, rl):
+    reads = _dataset(300 + k, genome=4000, cov=40, rl=rl, err=0.003)
+    _long_check(ctx, oracle, reads, k)
+
+
+def test_long_k_quirks_and_m(ctx, oracle):
+    """k = 63 with ragged reads (one exactly k long), non-ACGT bases, homopolymers, explicit -m"""
+    k = 63
+    rng = np.random.default_rng(4)
+    g = synth.random_genome(3000, 12)
+    reads = [b"A" * 200, b"T" * 150, b"AC" * 90]
+    for i in range(500):
+        L = int(rng.integers(k, 260)) if i else k
+        s0 = int(rng.integers(0, len(g) - L))
+        r = bytearray(synth.codes_to_ascii(g[s0:s0 + L]).tobytes())
+        if i % 9 == 0:
+            r[int(rng.integers(0, L))] = ord("N")
+        reads.append(bytes(r))
+    _long_check(ctx, oracle, reads, k, m=90001)
+
+
+def test_very_long_k(ctx, oracle):
+    """k = 501 and the reference's maximum k = 3001 on long error-free reads"""
+    g = synth.random_genome(9000, 21)
+    for k, rl in ((501, 2000), (3001, 6000)):
+        reads = synth.reads_as_bytes(synth.simulate_reads(g, 12, rl, 0.0, 22 + k))
+        _long_check(ctx, oracle, reads, k, m=200003, n_adj=60)
+
+
+def test_long_k_batch_primitives(ctx, oracle):
+    """BF.add / possiblyContains / GetDoubleHash_64bit / CheckDirections on explicit W-word k-mers"""
+    from _checkers import nwords
+    rng = np.random.default_rng(6)
+    for k in (33, 63, 64, 101, 1001):
+        W = nwords(k)
+        fs, nh = 70001, 9
+        kmers = np.stack([oracle.canonical_words("".join("ACGT"[i] for i in rng.integers(0, 4, k)), k) for _ in range(120)])
+        dh = ctx.double_hash(k, kmers)
+        for i in range(0, 120, 7):
+            assert tuple(int(x) for x in dh[i]) == oracle.double_hash(oracle.std_hash_kmer(kmers[i], k))
+        ctx.bf_import(k, fs, nh, None)
+        ctx.bf_add(kmers[:60])
+        obits = np.zeros((fs + 7) // 8, np.uint8)
+        for i in range(60):
+            oracle.bf_add(obits, fs, nh, kmers[i], k)
+        assert np.array_equal(ctx.bf_export(), obits)
+        got = ctx.bf_possibly_contains(kmers)
+        want = np.array([oracle.L.p3o_bf_possibly_contains(obits, fs, nh, np.ascontiguousarray(kmers[i]), k) for i in range(120)], np.uint8)
+        assert np.array_equal(got, want) and got[:60].all()
+        masks = ctx.check_directions(kmers)
+        for i in range(0, 120, 5):
+            assert masks[i] == oracle.check_directions(obits, fs, nh, kmers[i], k)
