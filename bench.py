@@ -34,9 +34,13 @@ READ_LEN = 150
 GENOME = 100_000_000
 COVERAGE = 50
 ERR = 0.01
-# count21's algorithmic bytes per 21-mer occurrence (DESIGN.md "Roofline"): 2 bits of read
+# count stage's algorithmic bytes per 21-mer occurrence (DESIGN.md "Roofline"): 2 bits of read
 # staging in, one 8-byte table slot read and written back
 ALGO_BYTES_PER_KMER = 0.25 + 8 + 8
+# DRAM bytes of the count stage's kernels for ONE step of configs[1] on one B200, from
+# `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` (profiles/r01e_traffic_full_workload.csv):
+# hist21 1.88 + scatter21 60.66 + insert_bins 102.11 GB
+COUNT_STAGE_TRAFFIC_BYTES = 164.65e9
 SAMPLE_GENOME = 200_000  # cpu_baseline / reference arm: same generator, 500x smaller genome
 
 
@@ -394,8 +398,13 @@ def main():
                    "filter_size_bits": fs, "num_hashes": nh},
         "stage_ms": {kk: v / args.steps for kk, v in stage_acc.items()},
         "count_substage": {kk: v / args.steps for kk, v in sub_acc.items()},
-        "roofline": {"kernel": "count21_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        "roofline": {"kernel": "count stage = hist21 + scatter21 + insert_bins (dominant: insert_bins_kernel)"
+                               if os.environ.get("P3_COUNT_MODE", "binned") != "direct" else "count21_kernel",
+                     "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak,
+                     "traffic": COUNT_STAGE_TRAFFIC_BYTES if (genome == GENOME and os.environ.get("P3_COUNT_MODE", "binned") != "direct") else None,
+                     "traffic_source": "profiles/r01e_traffic_full_workload.csv (ncu dram__bytes_read+write of the three kernels, one step)",
+                     "peak_source": peak_src,
                      "algorithmic_bytes_per_kmer": ALGO_BYTES_PER_KMER, "kernel_ms": k_ms},
         "count_mode": os.environ.get("P3_COUNT_MODE", "binned"),
         "e2e": {"value": n_pos / (e2e_ms / args.steps * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms / args.steps,

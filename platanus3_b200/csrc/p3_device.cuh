@@ -117,6 +117,18 @@ __device__ __forceinline__ void ld_bucket(const uint64_t *p, uint64_t s[4]) {
     asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];"
                  : "=l"(s[0]), "=l"(s[1]), "=l"(s[2]), "=l"(s[3]) : "l"(p));
 }
+// same, but an L2 miss fills only the 64-byte half line that holds the bucket (default: all 128 B).
+// For tables that stay DRAM resident (solid set, Bloom filter) the unused half is pure traffic:
+// ncu showed makebf/adjacency byte-bound at 4.4-5.0 TB/s with 128-byte fills.
+__device__ __forceinline__ void ld_bucket64(const uint64_t *p, uint64_t s[4]) {
+    asm volatile("ld.global.cg.L2::64B.v4.u64 {%0,%1,%2,%3}, [%4];"
+                 : "=l"(s[0]), "=l"(s[1]), "=l"(s[2]), "=l"(s[3]) : "l"(p));
+}
+__device__ __forceinline__ uint32_t ld_word64(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.global.nc.L2::64B.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
 __device__ __forceinline__ unsigned long long *ull(uint64_t *p) { return reinterpret_cast<unsigned long long *>(p); }
 
 // ---- overflow side table (counts that do not fit 22 bits) --------------------------------------
@@ -252,7 +264,7 @@ __device__ __forceinline__ int set_insert(uint64_t *table, uint64_t nb, uint64_t
     for (uint64_t probe = 0; probe < nb; probe++) {
         uint64_t *bp = table + 4 * b;
         uint64_t s[4];
-        ld_bucket(bp, s);
+        ld_bucket64(bp, s);
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             uint64_t v = s[i];
@@ -273,7 +285,7 @@ __device__ __forceinline__ bool set_contains(const uint64_t *table, uint64_t nb,
     uint64_t b = __umul64hi(fmix64(key), nb);
     for (uint64_t probe = 0; probe < nb; probe++) {
         uint64_t s[4];
-        ld_bucket(table + 4 * b, s);
+        ld_bucket64(table + 4 * b, s);
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             if (s[i] == key) return true;
@@ -310,7 +322,7 @@ __device__ __forceinline__ bool bloom_query(const Bloom &bf, uint64_t canon) {
     uint64_t x = h1;
     for (int n = 0; n < bf.nh; n++, x += h2) {
         uint64_t bit = fastmod(x, bf.fm);
-        if (!((__ldg(bf.bits + (bit >> 5)) >> (bit & 31)) & 1u)) return false;
+        if (!((ld_word64(bf.bits + (bit >> 5)) >> (bit & 31)) & 1u)) return false;
     }
     return true;
 }
