@@ -199,6 +199,13 @@ const uint64_t *p3_reads_packed(const p3_reads *r);
 const uint32_t *p3_reads_nmask(const p3_reads *r);   /* NULL when every base is ACGT */
 const char *p3_reads_ascii(const p3_reads *r);
 
+/* DeBruijnGraph::CountNodeCoverage, reference src/DeBruijnGraph.cpp:394-449, over the reads attached
+ * to ctx: h_junctions / h_joints are the ORIENTED node k-mers (k <= 32) as the walk recorded them;
+ * h_jcov receives 9 counters per junction [coverage, left_kmers_cov[4], right_kmers_cov[4]],
+ * h_tcov one coverage counter per joint. */
+int p3_node_coverage(p3_ctx *ctx, uint32_t k, const uint64_t *h_junctions, uint64_t nj,
+                     const uint64_t *h_joints, uint64_t nt, int32_t *h_jcov, int32_t *h_tcov);
+
 /* main() + Assemble<>, reference main.cpp:11-31 and src/Assemble.cpp:7-28, for one read file:
  * Load, filter sizing, the GPU hot path, then on the host the unitig walk (MakeDBG with the
  * reference's -t 1 order), CountNodeCoverage and PrintGraph. Writes the GFA to gfa_path and the

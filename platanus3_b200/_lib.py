@@ -25,7 +25,7 @@ SYMBOLS = [
     "p3_mg_kmer_owner_hist", "p3_mg_kmer_owner_scatter", "p3_mg_owned_begin", "p3_mg_owned_insert",
     "p3_mg_owned_end", "p3_mg_filter",
     "p3_load_file", "p3_reads_free", "p3_reads_count", "p3_reads_all_bases", "p3_reads_total_bases",
-    "p3_reads_offsets", "p3_reads_packed", "p3_reads_nmask", "p3_reads_ascii", "p3_assemble_file",
+    "p3_reads_offsets", "p3_reads_packed", "p3_reads_nmask", "p3_reads_ascii", "p3_assemble_file", "p3_node_coverage",
     "p3_assemble_hot_path", "p3_stage_ms", "p3_count_substage_ms", "p3_launch_count", "p3_bf_params",
 ]
 
@@ -106,6 +106,7 @@ def lib():
         for nm in ("p3_reads_offsets", "p3_reads_packed", "p3_reads_nmask", "p3_reads_ascii"):
             getattr(L, nm).restype = vp
             getattr(L, nm).argtypes = [vp]
+        L.p3_node_coverage.argtypes = [vp, u32, vp, u64, vp, u64, vp, vp]
         L.p3_assemble_file.argtypes = [C.c_char_p, u32, u64, i32, i32, C.c_char_p, C.c_char_p, C.POINTER(u64)]
         L.p3_stage_ms.argtypes = [vp, C.POINTER(C.c_float)]
         L.p3_count_substage_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(u32), C.POINTER(u64)]

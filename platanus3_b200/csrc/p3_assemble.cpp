@@ -315,48 +315,28 @@ struct Walker {
         }
         return 0;
     }
-    void add_node_coverage(uint64_t km) {   // :442-449
-        auto j = junctions.find(km); if (j != junctions.end()) j->second.coverage++;
-        auto t = joints.find(km); if (t != joints.end()) t->second.coverage++;
-    }
 };
 
 inline int fcode(unsigned char c) { return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : 0; }
-inline int rcode(unsigned char c) { return c == 'A' ? 3 : c == 'C' ? 2 : c == 'G' ? 1 : c == 'T' ? 0 : 0; }   // base_to_bit[trans_base[c]]
 
-// CountNodeCoverage, reference src/DeBruijnGraph.cpp:394-439 (sums only: read order is irrelevant)
-void count_node_coverage(Walker &w, const p3_reads &rd) {
-    const int k = w.k;
-    if (w.junctions.empty() && w.joints.empty()) return;
-    for (size_t r = 0; r + 1 < rd.off.size(); r++) {
-        const unsigned char *s = (const unsigned char *)rd.seq.data() + rd.off[r];
-        size_t len = rd.off[r + 1] - rd.off[r];
-        uint64_t fw = 0, bw = 0;
-        for (int i = 0; i < k; i++) fw = ((fw << 2) | (uint64_t)fcode(s[i])) & w.kmask;
-        for (int i = k - 1; i >= 0; i--) bw = ((bw << 2) | (uint64_t)rcode(s[i])) & w.kmask;
-        w.add_node_coverage(fw); w.add_node_coverage(bw);
-        // target_read[kmer_length]: for a read of exactly k bases std::string yields '\0' -> code 0
-        unsigned char nxt = len > (size_t)k ? s[k] : 0;
-        auto jf = w.junctions.find(fw);
-        if (jf != w.junctions.end()) jf->second.right_cov[fcode(nxt)]++;
-        else { auto jb = w.junctions.find(bw); if (jb != w.junctions.end()) jb->second.left_cov[rcode(nxt)]++; }
-        for (size_t i = k; i < len; i++) {
-            fw = ((fw << 2) | (uint64_t)fcode(s[i])) & w.kmask;
-            bw = (bw >> 2) | ((uint64_t)rcode(s[i]) << (2 * k - 2));
-            w.add_node_coverage(fw); w.add_node_coverage(bw);
-            auto f = w.junctions.find(fw);
-            if (f != w.junctions.end()) {
-                f->second.left_cov[fcode(s[i - k])]++;
-                if (i < len - 1) f->second.right_cov[fcode(s[i + 1])]++;
-            } else {
-                auto b = w.junctions.find(bw);
-                if (b != w.junctions.end()) {
-                    b->second.right_cov[rcode(s[i - k])]++;
-                    if (i < len - 1) b->second.left_cov[rcode(s[i + 1])]++;
-                }
-            }
-        }
+// CountNodeCoverage (reference src/DeBruijnGraph.cpp:394-439) runs on the GPU (p3_node_coverage):
+// the node k-mers go down in id order, the counters come back into the maps.
+int count_node_coverage(Walker &w, p3_ctx *ctx) {
+    std::vector<uint64_t> jk(w.junctions.size()), tk;
+    std::vector<uint64_t> tkeys;
+    for (auto &kv : w.junctions) jk[kv.second.id - 1] = kv.first;   // ids are 1..n without gaps
+    tkeys.reserve(w.joints.size());
+    for (auto &kv : w.joints) tkeys.push_back(kv.first);
+    std::vector<int32_t> jc(9 * jk.size() + 1), tc(tkeys.size() + 1);
+    int rc = p3_node_coverage(ctx, (uint32_t)w.k, jk.data(), jk.size(), tkeys.data(), tkeys.size(), jc.data(), tc.data());
+    if (rc) return rc;
+    for (size_t i = 0; i < jk.size(); i++) {
+        Junction &J = w.junctions[jk[i]];
+        J.coverage = jc[9 * i];
+        for (int b = 0; b < 4; b++) { J.left_cov[b] = jc[9 * i + 1 + b]; J.right_cov[b] = jc[9 * i + 5 + b]; }
     }
+    for (size_t i = 0; i < tkeys.size(); i++) w.joints[tkeys[i]].coverage = tc[i];
+    return P3_OK;
 }
 
 // PrintGraph, reference src/DeBruijnGraph.cpp:452-544. The reference iterates unordered_maps, so its
@@ -490,7 +470,6 @@ int p3_assemble_file(const char *read_path, uint32_t k, uint64_t m, int threads,
     rc = p3_dbg_export(ctx, kmers.data(), adjb.data(), kmers.size(), &got);
     if (rc) return bail(rc);
     kmers.resize(got); adjb.resize(got);
-    p3_destroy(ctx);
 
     log.line("start graph extention");
     AdjTable table; table.build(kmers, adjb);
@@ -498,11 +477,14 @@ int p3_assemble_file(const char *read_path, uint32_t k, uint64_t m, int threads,
     Walker w((int)k, table);
     if (w.make_dbg(seeds, /*node_limit*/ 4 * (got + 16)) != 0 || w.missing) {
         g_host_err = w.missing ? "internal: walk left the closed adjacency table" : "walk did not terminate";
+        p3_destroy(ctx);
         p3_reads_free(rd);
         return P3_ERR_STATE;
     }
     log.line("de bruijn graph loaded");
-    count_node_coverage(w, *rd);
+    rc = count_node_coverage(w, ctx);
+    if (rc) return bail(rc);
+    p3_destroy(ctx);
     log.line("count node coverage");
     rc = gfa_path ? print_graph(w, gfa_path) : P3_OK;
     if (stats) {

@@ -1518,4 +1518,5 @@ int p3_bf_params(p3_ctx *c, uint64_t *filter_size, uint32_t *num_hashes, uint32_
 }  // extern "C"
 
 #include "p3_long.inc.cu"
+#include "p3_cover.inc.cu"
 #include "p3_multi.inc.cu"
