@@ -161,6 +161,18 @@ uint32_t p3_owner_of_key(uint64_t key, uint32_t n_ranks);
 int p3_mg_owner_hist(p3_ctx *ctx, uint32_t n_ranks, uint64_t w0, uint64_t w1, uint64_t *h_counts);
 int p3_mg_owner_scatter(p3_ctx *ctx, uint32_t n_ranks, uint32_t my_rank, uint64_t w0, uint64_t w1,
                         uint64_t *d_keys, uint32_t *d_words);
+/* fused bin + exchange: owner j's records are stored straight into keys_base[j] / words_base[j],
+ * device addresses (as integers) inside rank j's receive buffer that are mapped into this process
+ * over NVLink peer memory, already offset to the region reserved for this source rank (n_ranks <= 16).
+ * The caller barriers all ranks before the owners consume their buffers. */
+int p3_mg_owner_scatter_peer(p3_ctx *ctx, uint32_t n_ranks, uint32_t my_rank, uint64_t w0, uint64_t w1,
+                             const uint64_t *keys_base, const uint64_t *words_base);
+/* the receive buffers peers store into (grow-only; exported with p3_ipc_export), and CUDA IPC
+ * plumbing: a 64-byte handle of a buffer of this process / a mapping of another process's buffer */
+int p3_mg_recv_buffers(p3_ctx *ctx, uint64_t n_records, uint64_t **d_keys, uint32_t **d_words);
+int p3_ipc_export(const void *d_ptr, uint8_t handle[64]);
+int p3_ipc_open(int device, const uint8_t handle[64], void **d_ptr);
+int p3_ipc_close(int device, void *d_ptr);
 /* owner side of CountShortKmer: table of table_slots 8-byte slots, then any number of record
  * batches (each <= max_records_per_call), then _end */
 int p3_mg_count_begin(p3_ctx *ctx, uint64_t table_slots, uint64_t max_records_per_call);
@@ -171,6 +183,11 @@ int p3_mg_singletons(p3_ctx *ctx, uint32_t n_ranks, uint64_t *h_counts, const ui
 /* source side of MakeBF's coverage test: plane := valid positions, minus the received positions */
 int p3_mg_cover_begin(p3_ctx *ctx);
 int p3_mg_cover_clear(p3_ctx *ctx, const uint64_t *d_pos, uint64_t n);
+/* fused alternative to p3_mg_singletons + all-to-all + p3_mg_cover_clear: the owner clears the bits
+ * of its count-1 keys directly in the source ranks' planes (planes[j] = rank j's p3_mg_cover_plane as
+ * mapped into this process; RED.AND over NVLink). Ranks synchronise before and after. */
+int p3_mg_cover_plane(p3_ctx *ctx, uint32_t **d_plane);
+int p3_mg_cover_peer(p3_ctx *ctx, uint32_t n_ranks, const uint64_t *planes);
 /* solid plane, seeds and the locally distinct solid k-mers (solid_slots 0 = auto) */
 int p3_mg_solid_local(p3_ctx *ctx, uint32_t k, uint64_t solid_slots, uint64_t *n_adds, uint64_t *n_local);
 int p3_mg_kmer_owner_hist(p3_ctx *ctx, uint32_t n_ranks, uint64_t *h_counts);

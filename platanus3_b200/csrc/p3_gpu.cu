@@ -203,15 +203,22 @@ __device__ __forceinline__ void tile_scan_and_claim(ScatterSmem &sm, uint32_t P,
     if (tid == NT - 1) sm.total = wbase + incl;
 }
 
+// PEER mode (multi-GPU): partition p's records go to a DIFFERENT buffer per partition — the
+// receive buffer of owner rank p, mapped into this process through NVLink peer memory (CUDA IPC,
+// p3_ipc_open). The tile's runs are stored there directly, so the exchange happens inside the
+// binning kernel, tile by tile, instead of as a separate all-to-all over a send buffer.
+constexpr int kMaxPeers = 16;
+struct PeerOut { uint64_t *keys[kMaxPeers]; uint32_t *words[kMaxPeers]; };
+
 // 256 threads per 128-word tile: thread t handles 16 of the 32 offsets of word t>>1, so the tile's
 // shared memory is covered by 8 warps instead of 4 (occupancy was 18 % with 4)
 constexpr int kScatterThreads = 2 * kTileWords;
-template <bool HAS_MASK, int PMODE>
+template <bool HAS_MASK, int PMODE, bool PEER = false>
 __global__ void __launch_bounds__(kScatterThreads)
 scatter21_kernel(const uint64_t *__restrict__ packed, const uint32_t *__restrict__ rend,
                  const uint32_t *__restrict__ nmask, uint64_t w0, uint64_t w1, uint32_t P,
                  unsigned long long *cursor, uint64_t *__restrict__ bkeys, uint32_t *__restrict__ bword,
-                 uint32_t *__restrict__ valid_plane, uint64_t tag) {
+                 uint32_t *__restrict__ valid_plane, uint64_t tag, PeerOut peer = PeerOut()) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ScatterSmem &sm = *reinterpret_cast<ScatterSmem *>(smem_raw);
     const uint64_t W21 = ~0ULL << (64 - (kShortK - 1));
@@ -268,8 +275,13 @@ scatter21_kernel(const uint64_t *__restrict__ packed, const uint32_t *__restrict
         for (uint32_t i = tid; i < total; i += kScatterThreads) {
             uint32_t pt = sm.part[i];
             unsigned long long dst = sm.gbase[pt] + (i - sm.offs[pt]);
-            bkeys[dst] = sm.key[i];
-            bword[dst] = (uint32_t)(tile_w0 + sm.loc[i]);
+            if (PEER) {   // remote (or local) stores over NVLink into owner pt's receive buffer
+                peer.keys[pt][dst] = sm.key[i];
+                peer.words[pt][dst] = (uint32_t)(tile_w0 + sm.loc[i]);
+            } else {
+                bkeys[dst] = sm.key[i];
+                bword[dst] = (uint32_t)(tile_w0 + sm.loc[i]);
+            }
         }
         __syncthreads();
     }
@@ -925,6 +937,8 @@ static int scatter_attrs() {
     CU(cudaFuncSetAttribute(scatter21_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz));
     CU(cudaFuncSetAttribute(scatter21_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz));
     CU(cudaFuncSetAttribute(scatter21_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz));
+    CU(cudaFuncSetAttribute(scatter21_kernel<true, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz));
+    CU(cudaFuncSetAttribute(scatter21_kernel<false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz));
     CU(cudaFuncSetAttribute(scatter_rec_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz));
     CU(cudaFuncSetAttribute(scatter_rec_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz));
     CU(cudaFuncSetAttribute(scatter_rec_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz));

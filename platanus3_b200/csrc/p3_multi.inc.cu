@@ -57,6 +57,29 @@ __global__ void clear_positions_kernel(const uint64_t *__restrict__ pos, uint64_
     }
 }
 
+// Coverage verdicts without a list, a sort and an all-to-all: the owner looks at each of its
+// first-occurrence candidates and, when the key's final count stayed below the threshold, clears the
+// position's bit straight in the SOURCE rank's coverage plane (RED.AND over NVLink peer memory; the
+// rank is the top byte of the position record).
+struct PeerPlanes { uint32_t *p[kMaxPeers]; };
+__global__ void __launch_bounds__(256)
+cand_check_peer_kernel(const uint64_t *__restrict__ slots, const uint64_t *__restrict__ cand_slot,
+                       const uint64_t *__restrict__ cand_pos, uint64_t n_cand, uint64_t thr, Ovf ovf,
+                       const Stats *st, PeerPlanes planes) {
+    const unsigned n_overflow = st->n_overflow;
+    uint64_t stride = gridDim.x * (uint64_t)blockDim.x;
+    for (uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; j < n_cand; j += stride) {
+        uint64_t v = __ldcg(slots + __ldcs(cand_slot + j));
+        uint64_t c = v >> 42;
+        if (c < thr && n_overflow) c += ovf_get(ovf, v & kKey42) << 22;
+        if (c < thr) {
+            uint64_t rec = __ldcs(cand_pos + j);
+            uint64_t pos = rec & ((1ULL << kPosRankShift) - 1);
+            atomicAnd(planes.p[(rec >> kPosRankShift) & (kMaxPeers - 1)] + (pos >> 5), ~(0x80000000u >> (pos & 31)));
+        }
+    }
+}
+
 __global__ void set_insert_list_kernel(const uint64_t *__restrict__ kmers, uint64_t n, uint64_t *set, uint64_t nbs, Stats *st) {
     uint64_t stride = gridDim.x * (uint64_t)blockDim.x;
     bool full = false;
@@ -75,6 +98,9 @@ struct MgState {   // extra per-context state of the multi-GPU path
     uint64_t *d_set2 = nullptr, *d_list2 = nullptr; uint64_t nbs2 = 0;
     uint64_t rec_cap = 0;
     uint64_t n_local = 0;
+    // receive buffers of the fused bin + exchange (peers store into them over NVLink); plain
+    // cudaMalloc allocations so that cudaIpcGetMemHandle can export them to the other processes
+    uint64_t *d_rkeys = nullptr; uint32_t *d_rwords = nullptr; uint64_t cap_rkeys = 0, cap_rwords = 0;
     bool swapped = false;   // c->d_set/d_list currently hold the OWNED set (p3_mg_owned_end swapped them in)
 };
 static std::unordered_map<p3_ctx *, MgState> g_mg;   // keyed by context (p3_ctx layout stays private to p3_gpu.cu)
@@ -83,7 +109,7 @@ static void mg_release(p3_ctx *c) {
     auto it = g_mg.find(c);
     if (it == g_mg.end()) return;
     MgState &m = it->second;
-    dfree(m.d_sing); dfree(m.d_sing2); dfree(m.d_set2); dfree(m.d_list2);
+    dfree(m.d_sing); dfree(m.d_sing2); dfree(m.d_set2); dfree(m.d_list2); dfree(m.d_rkeys); dfree(m.d_rwords);
     g_mg.erase(it);
 }
 
@@ -138,6 +164,74 @@ int p3_mg_owner_scatter(p3_ctx *c, uint32_t n_ranks, uint32_t my_rank, uint64_t 
     c->launches++;
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(c->stream));
+    return P3_OK;
+}
+
+// Fused bin + exchange: like p3_mg_owner_scatter, but owner j's records are stored straight to
+// keys_base[j] / words_base[j] — device pointers into rank j's receive buffer that are mapped into
+// this process (NVLink peer memory: p3_ipc_open of the owner's p3_mg_recv_buffers), already offset to
+// the region reserved for this source rank (sizes from the all-gathered p3_mg_owner_hist counts). The
+// caller synchronises all ranks before the owners read their buffers.
+int p3_mg_owner_scatter_peer(p3_ctx *c, uint32_t n_ranks, uint32_t my_rank, uint64_t w0, uint64_t w1,
+                             const uint64_t *keys_base, const uint64_t *words_base) {
+    if (!c || !c->have_reads || !keys_base || !words_base) return fail(P3_ERR_STATE, "p3_mg_owner_scatter_peer: no reads / null buffers");
+    if (my_rank >= n_ranks || n_ranks > kMaxPeers) return fail(P3_ERR_ARG, "p3_mg_owner_scatter_peer: at most 16 ranks");
+    CU(cudaSetDevice(c->device));
+    CU(ensure(c->d_valid, c->cap_valid, sizeof(uint32_t) * (c->n_words + 1)));
+    PeerOut po;
+    for (uint32_t j = 0; j < (uint32_t)kMaxPeers; j++) {
+        po.keys[j] = j < n_ranks ? (uint64_t *)(uintptr_t)keys_base[j] : nullptr;
+        po.words[j] = j < n_ranks ? (uint32_t *)(uintptr_t)words_base[j] : nullptr;
+    }
+    // positions inside each destination region are relative: cursors start at zero
+    CU(cudaMemsetAsync(c->d_cursor, 0, sizeof(unsigned long long) * (kMaxParts + 1), c->stream));
+    unsigned sblocks = (unsigned)std::min<uint64_t>(std::max<uint64_t>((w1 - w0 + kTileWords - 1) / kTileWords, 1), (uint64_t)c->n_sm * 3);
+    const uint64_t tag = (uint64_t)my_rank << kRecRankShift;
+    if (c->d_nmask) scatter21_kernel<true, 1, true><<<sblocks, kScatterThreads, sizeof(ScatterSmem), c->stream>>>(c->d_packed, c->d_rend, c->d_nmask, w0, w1, n_ranks, c->d_cursor, nullptr, nullptr, c->d_valid, tag, po);
+    else scatter21_kernel<false, 1, true><<<sblocks, kScatterThreads, sizeof(ScatterSmem), c->stream>>>(c->d_packed, c->d_rend, nullptr, w0, w1, n_ranks, c->d_cursor, nullptr, nullptr, c->d_valid, tag, po);
+    c->launches++;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));
+    return P3_OK;
+}
+
+// receive buffers for n_records count records (grow-only; a grown buffer is a NEW allocation, whose
+// handle has to be exported again)
+int p3_mg_recv_buffers(p3_ctx *c, uint64_t n_records, uint64_t **d_keys, uint32_t **d_words) {
+    if (!c) return fail(P3_ERR_ARG, "null ctx");
+    CU(cudaSetDevice(c->device));
+    MgState &m = g_mg[c];
+    n_records = std::max<uint64_t>(n_records, 1);
+    CU(ensure(m.d_rkeys, m.cap_rkeys, sizeof(uint64_t) * n_records));
+    CU(ensure(m.d_rwords, m.cap_rwords, sizeof(uint32_t) * n_records));
+    if (d_keys) *d_keys = m.d_rkeys;
+    if (d_words) *d_words = m.d_rwords;
+    return P3_OK;
+}
+
+// CUDA IPC plumbing for the peer buffers (one process per GPU): export a cudaMalloc'ed buffer of this
+// process as a 64-byte handle / map another process's buffer into this one (NVLink peer access is
+// enabled on first use)
+int p3_ipc_export(const void *d_ptr, uint8_t handle[64]) {
+    if (!d_ptr || !handle) return fail(P3_ERR_ARG, "p3_ipc_export: null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, const_cast<void *>(d_ptr)));
+    memcpy(handle, &h, 64);
+    return P3_OK;
+}
+int p3_ipc_open(int device, const uint8_t handle[64], void **d_ptr) {
+    if (!handle || !d_ptr) return fail(P3_ERR_ARG, "p3_ipc_open: null argument");
+    CU(cudaSetDevice(device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CU(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return P3_OK;
+}
+int p3_ipc_close(int device, void *d_ptr) {
+    if (!d_ptr) return P3_OK;
+    CU(cudaSetDevice(device));
+    CU(cudaIpcCloseMemHandle(d_ptr));
     return P3_OK;
 }
 
@@ -258,6 +352,30 @@ int p3_mg_cover_clear(p3_ctx *c, const uint64_t *d_pos, uint64_t n) {
     clear_positions_kernel<<<c->grid(), 256, 0, c->stream>>>(d_pos, n, c->d_good21);
     c->launches++;
     CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));
+    return P3_OK;
+}
+
+int p3_mg_cover_plane(p3_ctx *c, uint32_t **d_plane) {
+    if (!c || !c->d_good21) return fail(P3_ERR_STATE, "p3_mg_cover_plane: run p3_mg_cover_begin first");
+    if (d_plane) *d_plane = c->d_good21;
+    return P3_OK;
+}
+// owner side, fused with the exchange: clear the bits of this rank's count-1 keys directly in the
+// source ranks' planes (planes[j] = rank j's p3_mg_cover_plane, mapped into this process). All ranks
+// must have run p3_mg_cover_begin before any rank calls this, and must synchronise afterwards.
+int p3_mg_cover_peer(p3_ctx *c, uint32_t n_ranks, const uint64_t *planes) {
+    if (!c || !c->have_counts || !planes) return fail(P3_ERR_STATE, "p3_mg_cover_peer: no counts / null planes");
+    if (n_ranks == 0 || n_ranks > kMaxPeers) return fail(P3_ERR_ARG, "p3_mg_cover_peer: at most 16 ranks");
+    CU(cudaSetDevice(c->device));
+    PeerPlanes pp;
+    for (uint32_t j = 0; j < (uint32_t)kMaxPeers; j++) pp.p[j] = (uint32_t *)(uintptr_t)planes[j < n_ranks ? j : 0];
+    uint64_t nc = c->h_stats.n_cand;
+    if (nc) {
+        cand_check_peer_kernel<<<c->grid(), 256, 0, c->stream>>>(c->d_table, c->d_cand_slot, c->d_cand_pos, nc, P3_COV_THRESHOLD, c->ovf(), c->d_stats, pp);
+        c->launches++;
+        CU(cudaGetLastError());
+    }
     CU(cudaStreamSynchronize(c->stream));
     return P3_OK;
 }

@@ -77,10 +77,63 @@ class TorchDistComm:
         self.dist.all_gather_into_tensor(buf, acc, group=self.group)
         f.copy_(buf[:n])
 
+    def _dev(self):
+        return "cuda" if torch.cuda.is_available() and self.dist.get_backend(self.group) == "nccl" else "cpu"
+
     def all_sum(self, values):
-        t = torch.tensor(values, dtype=torch.int64, device="cuda" if torch.cuda.is_available() and self.dist.get_backend(self.group) == "nccl" else "cpu")
+        t = torch.tensor(values, dtype=torch.int64, device=self._dev())
         self.dist.all_reduce(t, group=self.group)
         return [int(x) for x in t.tolist()]
+
+    def all_gather(self, rows):
+        """rows: [list of ints] of the one local rank (same length on every rank) -> [world][len]"""
+        (row,) = rows
+        t = torch.tensor(row, dtype=torch.int64, device=self._dev())
+        out = torch.empty(self.world * max(t.numel(), 1), dtype=torch.int64, device=t.device)[: self.world * t.numel()]
+        if t.numel():
+            self.dist.all_gather_into_tensor(out, t, group=self.group)
+        return out.view(self.world, -1).tolist()
+
+    def barrier(self):
+        torch.cuda.synchronize()
+        self.dist.barrier(group=self.group)
+
+    def share(self, ptr_rows, device_index):
+        """ptr_rows: [[device pointers of cudaMalloc'ed buffers]] of the one local rank -> the same
+        buffers of EVERY rank as pointers valid in this process ([world][n]): CUDA IPC handles are
+        all-gathered and opened once (peer access over NVLink); the mappings are cached by handle."""
+        L = _lib.lib()
+        (ptrs,) = ptr_rows
+        handles = []
+        for p in ptrs:
+            h = (C.c_uint8 * 64)()
+            _check(L.p3_ipc_export(C.c_void_p(p), h))
+            handles.append(bytes(h))
+        gathered = [None] * self.world
+        self.dist.all_gather_object(gathered, handles, group=self.group)
+        if not hasattr(self, "_mapped"):
+            self._mapped = {}
+        table = []
+        for r in range(self.world):
+            if r == self.rank:
+                table.append(list(ptrs))
+                continue
+            row = []
+            for h in gathered[r]:
+                if h not in self._mapped:
+                    out = C.c_void_p()
+                    _check(L.p3_ipc_open(device_index, (C.c_uint8 * 64).from_buffer_copy(h), C.byref(out)))
+                    self._mapped[h] = (out.value, device_index)
+                row.append(self._mapped[h][0])
+            table.append(row)
+        return table
+
+    def close_shared(self):
+        """unmap every peer buffer (call on all ranks BEFORE the owners free their buffers)"""
+        L = _lib.lib()
+        for ptr, dev in getattr(self, "_mapped", {}).values():
+            L.p3_ipc_close(dev, C.c_void_p(ptr))
+        self._mapped = {}
 
 
 class EmulatedComm:
@@ -112,6 +165,18 @@ class EmulatedComm:
 
     def all_sum(self, values_per_rank):
         return [int(sum(v)) for v in zip(*values_per_rank)]
+
+    def all_gather(self, rows):
+        return [list(r) for r in rows]
+
+    def barrier(self):
+        torch.cuda.synchronize()
+
+    def share(self, ptr_rows, device_index):
+        return [list(r) for r in ptr_rows]   # one process: every rank's pointers are valid as they are
+
+    def close_shared(self):
+        pass
 
 
 # ---------------------------------------------------------------------------- driver
@@ -152,16 +217,66 @@ def run_hot_path(ctxs, comm, k, filter_size, num_hashes, table_slots, solid_slot
         comm.dist.all_reduce(t, op=comm.dist.ReduceOp.MAX, group=comm.group)
         n_chunks = int(t.item())
 
+    import os
     import time
+    peer = os.environ.get("P3_MG_EXCHANGE", "peer") != "nccl" and w <= 16
+    dev_index = device.index if device.index is not None else torch.cuda.current_device()
+    u64a = C.c_uint64 * w
     sub = dict(bin=0.0, exchange=0.0, insert=0.0)
     # ---- A: count ------------------------------------------------------------------------------
     for c in ctxs:
         _check(L.p3_mg_count_begin(c.h, table_slots, 1))
-    for ch in range(n_chunks):
+
+    def chunk_range(ch, nw):
+        return min(ch * cw, nw), min((ch + 1) * cw, nw)
+
+    if peer:
+        # Fused bin + exchange (csrc: scatter21_kernel<.., PEER>): every rank stores owner j's records
+        # straight into rank j's receive buffer over NVLink, tile by tile, while it bins. Needs the
+        # per-chunk owner histograms of all ranks first (where each source's region starts).
+        t0 = time.perf_counter()
+        rows = []
+        for c, nw in zip(ctxs, n_words):
+            row = []
+            for ch in range(n_chunks):
+                w0, w1 = chunk_range(ch, nw)
+                counts = u64a()
+                _check(L.p3_mg_owner_hist(c.h, w, w0, w1, counts))
+                row += [int(x) for x in counts]
+            rows.append(row)
+        hist = np.array(comm.all_gather(rows), dtype=np.int64).reshape(w, n_chunks, w)   # [source][chunk][owner]
+        cap = hist.sum(axis=0).max(axis=0) if n_chunks else np.zeros(w, np.int64)        # per owner
+        ptr_rows = []
+        for c, r in zip(ctxs, comm.local_ranks):
+            pk, pw = C.c_void_p(), C.c_void_p()
+            _check(L.p3_mg_recv_buffers(c.h, int(cap[r]), C.byref(pk), C.byref(pw)))
+            ptr_rows.append([pk.value, pw.value])
+        table = comm.share(ptr_rows, dev_index)     # [rank][0 = keys, 1 = words]
+        comm.barrier()
+        sub["bin"] += 1e3 * (time.perf_counter() - t0)
+        for ch in range(n_chunks):
+            t0 = time.perf_counter()
+            before = np.cumsum(hist[:, ch, :], axis=0) - hist[:, ch, :]   # [source][owner]: records of lower sources
+            for c, r, nw in zip(ctxs, comm.local_ranks, n_words):
+                w0, w1 = chunk_range(ch, nw)
+                kb = u64a(*[table[j][0] + 8 * int(before[r, j]) for j in range(w)])
+                wb = u64a(*[table[j][1] + 4 * int(before[r, j]) for j in range(w)])
+                _check(L.p3_mg_owner_scatter_peer(c.h, w, r, w0, w1, kb, wb))
+            t1 = time.perf_counter()
+            comm.barrier()      # every source's stores have landed
+            t2 = time.perf_counter()
+            for c, r, row in zip(ctxs, comm.local_ranks, ptr_rows):
+                n = int(hist[:, ch, r].sum())
+                if n:
+                    _check(L.p3_mg_count_records(c.h, row[0], row[1], n))
+            comm.barrier()      # the buffers may be overwritten by the next chunk
+            t3 = time.perf_counter()
+            sub["bin"] += 1e3 * (t1 - t0); sub["exchange"] += 1e3 * (t2 - t1); sub["insert"] += 1e3 * (t3 - t2)
+    for ch in range(n_chunks if not peer else 0):
         t0 = time.perf_counter()
         sends = []
         for c, r, nw in zip(ctxs, comm.local_ranks, n_words):
-            w0, w1 = min(ch * cw, nw), min((ch + 1) * cw, nw)
+            w0, w1 = chunk_range(ch, nw)
             counts = (C.c_uint64 * w)()
             _check(L.p3_mg_owner_hist(c.h, w, w0, w1, counts))
             counts = [int(x) for x in counts]
@@ -185,25 +300,40 @@ def run_hot_path(ctxs, comm, k, filter_size, num_hashes, table_slots, solid_slot
         _check(L.p3_mg_count_end(c.h))
         a, b = C.c_uint64(), C.c_uint64()
         _check(L.p3_short_kmer_stats(c.h, C.byref(a), C.byref(b)))
-        st.update(owned_positions=a.value, owned_distinct21=b.value)
+        st.update(owned_positions=a.value, owned_distinct21=b.value, exchange="peer" if peer else "nccl")
 
     mark("count")
     # ---- B1: singleton verdicts back to the reads ----------------------------------------------------
-    sends = []
-    for c in ctxs:
-        counts = (C.c_uint64 * w)()
-        ptr = C.c_void_p()
-        _check(L.p3_mg_singletons(c.h, w, counts, C.byref(ptr)))
-        counts = [int(x) for x in counts]
-        sends.append(([dev_tensor(ptr.value, sum(counts), torch.int64, device)], counts))
-    recvs = _exchange(comm, sends)
-    for c, (tensors, rcounts) in zip(ctxs, recvs):
-        _check(L.p3_mg_cover_begin(c.h))
-        n = sum(rcounts)
-        if n:
-            t = tensors[0].contiguous()
-            _check(L.p3_mg_cover_clear(c.h, t.data_ptr(), n))
-    del sends, recvs
+    if peer and os.environ.get("P3_MG_COVER", "peer") != "nccl":
+        # owners clear the bits of their count-1 keys directly in the source ranks' planes (NVLink RED.AND)
+        ptr_rows = []
+        for c in ctxs:
+            _check(L.p3_mg_cover_begin(c.h))
+            pp = C.c_void_p()
+            _check(L.p3_mg_cover_plane(c.h, C.byref(pp)))
+            ptr_rows.append([pp.value])
+        planes = comm.share(ptr_rows, dev_index)
+        comm.barrier()
+        pl = u64a(*[planes[j][0] for j in range(w)])
+        for c in ctxs:
+            _check(L.p3_mg_cover_peer(c.h, w, pl))
+        comm.barrier()
+    else:
+        sends = []
+        for c in ctxs:
+            counts = (C.c_uint64 * w)()
+            ptr = C.c_void_p()
+            _check(L.p3_mg_singletons(c.h, w, counts, C.byref(ptr)))
+            counts = [int(x) for x in counts]
+            sends.append(([dev_tensor(ptr.value, sum(counts), torch.int64, device)], counts))
+        recvs = _exchange(comm, sends)
+        for c, (tensors, rcounts) in zip(ctxs, recvs):
+            _check(L.p3_mg_cover_begin(c.h))
+            n = sum(rcounts)
+            if n:
+                t = tensors[0].contiguous()
+                _check(L.p3_mg_cover_clear(c.h, t.data_ptr(), n))
+        del sends, recvs
 
     mark("coverage")
     # ---- B2: solid k-mers to their owners ---------------------------------------------------------------

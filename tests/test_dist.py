@@ -57,6 +57,8 @@ def _gloo_worker(rank, world, port, q):
             acc |= f
         ok = ok and torch.equal(mine, acc)
         ok = ok and comm.all_sum([rank + 1, 10]) == [sum(range(1, world + 1)), 10 * world]
+        ok = ok and comm.all_gather([[rank, 7 * rank + 1, 3]]) == [[r, 7 * r + 1, 3] for r in range(world)]
+        ok = ok and comm.all_gather([[]]) == [[] for _ in range(world)]
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
@@ -93,10 +95,13 @@ def test_emulated_comm_matches_definition():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("exchange", ["peer", "nccl"])
 @pytest.mark.parametrize("world,chunk", [(1, None), (2, None), (3, 512), (8, 4096)])
-def test_distributed_hot_path_emulated(oracle, world, chunk):
+def test_distributed_hot_path_emulated(oracle, world, chunk, exchange, monkeypatch):
     """R ranks as R contexts on one GPU: counts, filter, solid k-mers, adjacency and seeds equal the
-    single-node oracle"""
+    single-node oracle. exchange = "peer": the fused bin + exchange (sources store into the owners'
+    receive buffers / coverage planes directly); "nccl": the all-to-all path"""
+    monkeypatch.setenv("P3_MG_EXCHANGE", exchange)
     k = 32
     g = synth.random_genome(12000, 17)
     reads = synth.reads_as_bytes(synth.simulate_reads(g, 30, 120, 0.01, 18))
@@ -117,6 +122,7 @@ def test_distributed_hot_path_emulated(oracle, world, chunk):
     try:
         stats = pdist.run_hot_path(ctxs, pdist.EmulatedComm(world), k, fs, nh, table_slots=max(2 * len(okeys) // world, 4096),
                                    chunk_words=chunk)
+        assert all(s["exchange"] == exchange for s in stats)
         assert sum(s["owned_positions"] for s in stats) == int(ocounts.sum())
         assert sum(s["owned_distinct21"] for s in stats) == len(okeys)
         assert sum(s["n_adds"] for s in stats) == oadds
@@ -140,3 +146,72 @@ def test_distributed_hot_path_emulated(oracle, world, chunk):
     finally:
         for c in ctxs:
             c.close()
+
+
+def _nccl_worker(rank, world, port, tmp, exchange):
+    """one real rank: its slice of the reads on its own GPU, results to an .npz for the parent"""
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), P3_MG_EXCHANGE=exchange)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        d = np.load(os.path.join(tmp, "in_%d.npz" % rank))
+        comm = pdist.TorchDistComm()
+        with _lib.Context(rank) as c:
+            c.load_ascii(d["seq"], d["off"])
+            for _ in range(2):   # twice: buffers and peer mappings are reused
+                st = pdist.run_hot_path([c], comm, int(d["k"]), int(d["fs"]), int(d["nh"]), table_slots=int(d["slots"]),
+                                        chunk_words=int(d["chunk"]), device=torch.device("cuda", rank))[0]
+            keys, counts = c.short_kmer_export()
+            kmers, adj = c.dbg_export(sort=False)
+            np.savez(os.path.join(tmp, "out_%d.npz" % rank), keys=keys, counts=counts, bits=c.bf_export(), seeds=c.seed_export(),
+                     kmers=kmers, adj=adj, n_adds=st["n_adds"], exchange=st["exchange"])
+            comm.barrier()
+            comm.close_shared()
+            comm.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("exchange", ["peer", "nccl"])
+def test_distributed_hot_path_two_real_gpus(oracle, tmp_path, exchange):
+    """two processes on two GPUs over NCCL + CUDA IPC peer buffers (skipped on a single-GPU box)"""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    world, k = 2, 32
+    g = synth.random_genome(30000, 21)
+    reads = synth.reads_as_bytes(synth.simulate_reads(g, 30, 120, 0.01, 22))
+    seq, off = reads_to_arrays(reads)
+    fs, nh = _lib.estimate_bloomfilter(int(off[-1]), k)
+    okeys, ocounts = oracle.count_short_kmers(seq, off)
+    obits, oseeds, _, oadds = oracle.make_bf(seq, off, k, okeys, ocounts, fs, nh)
+    osolid = oracle.solid_kmers(seq, off, k, okeys, ocounts)[:, 0]
+    bounds = np.linspace(0, len(reads), world + 1).astype(int)
+    for r in range(world):
+        s, o = reads_to_arrays(reads[bounds[r]:bounds[r + 1]])
+        np.savez(tmp_path / ("in_%d.npz" % r), seq=s, off=o, k=k, fs=fs, nh=nh, slots=max(2 * len(okeys) // world, 4096), chunk=2048)
+    ctx = mp.get_context("spawn")
+    port = _free_port()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, world, port, str(tmp_path), exchange)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    outs = [np.load(tmp_path / ("out_%d.npz" % r)) for r in range(world)]
+    assert all(str(o["exchange"]) == exchange for o in outs)
+    keys = np.concatenate([o["keys"] for o in outs]); counts = np.concatenate([o["counts"] for o in outs])
+    order = np.argsort(keys)
+    assert np.array_equal(keys[order], okeys) and np.array_equal(counts[order], ocounts)
+    assert sum(int(o["n_adds"]) for o in outs) == oadds
+    for r, o in enumerate(outs):
+        assert np.array_equal(o["bits"], obits)
+        assert np.array_equal(o["seeds"], oseeds[bounds[r]:bounds[r + 1]])
+    kmers = np.concatenate([o["kmers"] for o in outs]); adj = np.concatenate([o["adj"] for o in outs])
+    order = np.argsort(kmers)
+    kmers, adj = kmers[order], adj[order]
+    assert np.array_equal(kmers, osolid)
+    for i in range(0, len(osolid), max(1, len(osolid) // 500)):
+        assert adj[i] == oracle.check_directions(obits, fs, nh, osolid[i:i + 1], k)
