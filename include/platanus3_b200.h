@@ -198,6 +198,21 @@ int p3_mg_owned_begin(p3_ctx *ctx, uint64_t owned_slots);
 int p3_mg_owned_insert(p3_ctx *ctx, const uint64_t *d_kmers, uint64_t n);
 int p3_mg_owned_end(p3_ctx *ctx, uint32_t k, uint64_t filter_size, uint32_t num_hashes, uint64_t *n_owned);
 int p3_mg_filter(p3_ctx *ctx, uint32_t **d_bits, uint64_t *n_words);
+/* Sharded BF.add (reference src/bloomfilter.cpp:69-74) instead of replicated adds + OR-reduce: the
+ * filter is cut into segments of p3_bloom_seg_bits() bits, dealt out to the ranks in contiguous
+ * shards. p3_mg_owned_list = p3_mg_owned_end without the adds (filter allocation of at least
+ * filter_words_cap words, cleared). p3_mg_bloom_bin computes every owned k-mer's num_hashes bit
+ * indices once, sorts them by segment and stores segment s's 4-byte in-segment offsets to
+ * h_segbase[s] (device addresses, normally inside the shard owner's p3_mg_bloom_buffer mapped over
+ * NVLink peer memory; cap records each); h_counts[s] = records written. The owner ORs them in with
+ * p3_mg_bloom_apply (h_ptr/h_n: [n_local][n_src] regions), then the shards are all-gathered.
+ * p3_mg_bloom_direct is the fallback (adds into the local full copy; OR-reduce afterwards). */
+uint64_t p3_bloom_seg_bits(void);
+int p3_mg_owned_list(p3_ctx *ctx, uint32_t k, uint64_t filter_size, uint32_t num_hashes, uint64_t filter_words_cap, uint64_t *n_owned);
+int p3_mg_bloom_buffer(p3_ctx *ctx, uint64_t n_u32, uint32_t **d_buf);
+int p3_mg_bloom_bin(p3_ctx *ctx, uint32_t n_seg, const uint64_t *h_segbase, uint64_t cap, uint64_t *h_counts);
+int p3_mg_bloom_apply(p3_ctx *ctx, uint64_t seg_first, uint32_t n_local, uint32_t n_src, const uint64_t *h_ptr, const uint64_t *h_n);
+int p3_mg_bloom_direct(p3_ctx *ctx);
 
 /* ---- host side of the drop-in (row f: callers / formats either side of the path) ------------- */
 

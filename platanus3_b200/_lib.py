@@ -23,7 +23,8 @@ SYMBOLS = [
     "p3_owner_of_key", "p3_mg_owner_hist", "p3_mg_owner_scatter", "p3_mg_owner_scatter_peer", "p3_mg_recv_buffers", "p3_ipc_export", "p3_ipc_open", "p3_ipc_close", "p3_mg_cover_plane", "p3_mg_cover_peer", "p3_mg_count_begin", "p3_mg_count_records",
     "p3_mg_count_end", "p3_mg_singletons", "p3_mg_cover_begin", "p3_mg_cover_clear", "p3_mg_solid_local",
     "p3_mg_kmer_owner_hist", "p3_mg_kmer_owner_scatter", "p3_mg_owned_begin", "p3_mg_owned_insert",
-    "p3_mg_owned_end", "p3_mg_filter",
+    "p3_mg_owned_end", "p3_mg_filter", "p3_bloom_seg_bits", "p3_mg_owned_list", "p3_mg_bloom_buffer", "p3_mg_bloom_bin",
+    "p3_mg_bloom_apply", "p3_mg_bloom_direct",
     "p3_load_file", "p3_reads_free", "p3_reads_count", "p3_reads_all_bases", "p3_reads_total_bases",
     "p3_reads_offsets", "p3_reads_packed", "p3_reads_nmask", "p3_reads_ascii", "p3_assemble_file", "p3_node_coverage",
     "p3_assemble_hot_path", "p3_stage_ms", "p3_count_substage_ms", "p3_launch_count", "p3_bf_params",
@@ -105,6 +106,13 @@ def lib():
         L.p3_mg_owned_insert.argtypes = [vp, vp, u64]
         L.p3_mg_owned_end.argtypes = [vp, u32, u64, u32, C.POINTER(u64)]
         L.p3_mg_filter.argtypes = [vp, C.POINTER(vp), C.POINTER(u64)]
+        L.p3_bloom_seg_bits.restype = u64
+        L.p3_bloom_seg_bits.argtypes = []
+        L.p3_mg_owned_list.argtypes = [vp, u32, u64, u32, u64, C.POINTER(u64)]
+        L.p3_mg_bloom_buffer.argtypes = [vp, u64, C.POINTER(vp)]
+        L.p3_mg_bloom_bin.argtypes = [vp, u32, vp, u64, vp]
+        L.p3_mg_bloom_apply.argtypes = [vp, u64, u32, u32, vp, vp]
+        L.p3_mg_bloom_direct.argtypes = [vp]
         L.p3_load_file.argtypes = [C.c_char_p, u32, C.POINTER(vp)]
         L.p3_reads_free.argtypes = [vp]
         for nm in ("p3_reads_count", "p3_reads_all_bases", "p3_reads_total_bases"):

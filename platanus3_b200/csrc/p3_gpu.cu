@@ -762,6 +762,8 @@ struct p3_ctx {
 
 static void mg_release(struct p3_ctx *c);   // p3_multi.inc.cu
 static void long_release(struct p3_ctx *c); // p3_long.inc.cu
+static void bloom_release(struct p3_ctx *c);                                  // p3_bloom.inc.cu
+static int bloom_add_binned(struct p3_ctx *c, uint64_t n, bool *done);
 static int make_bf_long(struct p3_ctx *c, uint32_t k, uint64_t solid_slots);
 static int adjacency_long(struct p3_ctx *c, const uint64_t *d_words, uint64_t n, uint8_t *d_adj, struct p3::Stats *st);
 static const uint64_t *long_words(struct p3_ctx *c);
@@ -858,6 +860,7 @@ void p3_destroy(p3_ctx *c) {
     cudaStreamSynchronize(c->stream);
     mg_release(c);
     long_release(c);
+    bloom_release(c);
     free_reads(c); free_bf(c);
     dfree(c->d_table); dfree(c->d_proven2); dfree(c->d_bkeys); dfree(c->d_bword); dfree(c->d_valid);
     dfree(c->d_cand_slot); dfree(c->d_cand_pos); dfree(c->d_ghist); dfree(c->d_cursor); dfree(c->d_ovf_keys); dfree(c->d_ovf_wraps); dfree(c->d_stats);
@@ -1113,11 +1116,11 @@ int p3_short_kmer_lookup(p3_ctx *c, const uint64_t *h_keys, uint64_t n, uint64_t
 }
 
 // ---- stage B -----------------------------------------------------------------------------------
-static int alloc_bloom(p3_ctx *c, uint32_t k, uint64_t filter_size, uint32_t num_hashes) {
+static int alloc_bloom(p3_ctx *c, uint32_t k, uint64_t filter_size, uint32_t num_hashes, uint64_t min_words = 0) {
     if (k < P3_MIN_K || k > P3_MAX_K) return fail(P3_ERR_ARG, "k outside [21,3001] is not supported");
     if (filter_size == 0) return fail(P3_ERR_ARG, "filter_size == 0 (the reference divides by zero here)");
     if (num_hashes > 255) return fail(P3_ERR_ARG, "num_hashes > 255 (uint8_t in the reference)");
-    uint64_t words = (filter_size + 31) / 32;
+    uint64_t words = std::max<uint64_t>((filter_size + 31) / 32, min_words);   // min_words: room for whole shards (multi-GPU)
     if (!c->d_bloom || c->bloom_words != words) {
         dfree(c->d_bloom);
         if (cudaMalloc(&c->d_bloom, sizeof(uint32_t) * words) != cudaSuccess) { cudaGetLastError(); return fail(P3_ERR_NOMEM, "bloom allocation failed"); }
@@ -1158,8 +1161,12 @@ static int dedupe_solid_positions(p3_ctx *c, uint32_t k, uint64_t solid_slots) {
     }
 }
 
-// dense BF.add over the first nd k-mers of c->d_list, one pass per L2-sized filter segment
+// dense BF.add over the first nd k-mers of c->d_list: binned by filter segment (p3_bloom.inc.cu);
+// tiny jobs and single-segment filters take the direct kernel, one pass per L2-sized segment
 static int bloom_add_list(p3_ctx *c, uint64_t nd) {
+    bool done = false;
+    int rcb = bloom_add_binned(c, nd, &done);
+    if (rcb || done) return rcb;
     uint64_t seg_bits = 40ull << 23;                       // 40 MB of filter per pass
     uint64_t n_seg = (c->filter_size + seg_bits - 1) / seg_bits;
     if (n_seg > 16 || nd * c->num_hashes < (1u << 22)) { n_seg = 1; seg_bits = c->filter_size; }   // huge filter / tiny job: one pass
@@ -1532,5 +1539,6 @@ int p3_bf_params(p3_ctx *c, uint64_t *filter_size, uint32_t *num_hashes, uint32_
 }  // extern "C"
 
 #include "p3_long.inc.cu"
+#include "p3_bloom.inc.cu"
 #include "p3_cover.inc.cu"
 #include "p3_multi.inc.cu"

@@ -293,6 +293,11 @@ static void long_release(p3_ctx *c) {
 }
 
 static int bloom_add_words(p3_ctx *c, const uint64_t *d_words, uint64_t n) {
+    if (d_words == g_long[c].d_words) {   // the context's own k-mer list: binned adds (p3_bloom.inc.cu)
+        bool done = false;
+        int rcb = bloom_add_binned(c, n, &done);
+        if (rcb || done) return rcb;
+    }
     LongK L = make_longk(c->k);
     uint64_t seg_bits = 40ull << 23;
     uint64_t n_seg = (c->filter_size + seg_bits - 1) / seg_bits;

@@ -465,14 +465,15 @@ int p3_mg_owned_insert(p3_ctx *c, const uint64_t *d_kmers, uint64_t n) {
     return P3_OK;
 }
 
-// the owned set becomes THE set/list of this context; the filter copy is cleared and receives
-// BF.add of every owned k-mer (the caller then OR-reduces the copies across ranks)
-int p3_mg_owned_end(p3_ctx *c, uint32_t k, uint64_t filter_size, uint32_t num_hashes, uint64_t *n_owned) {
+// the owned set becomes THE set/list of this context; the filter copy (at least min_words words) is
+// cleared and, with do_adds, receives BF.add of every owned k-mer
+static int owned_finish(p3_ctx *c, uint32_t k, uint64_t filter_size, uint32_t num_hashes, uint64_t min_words,
+                        bool do_adds, uint64_t *n_owned) {
     if (!c) return fail(P3_ERR_ARG, "null ctx");
     CU(cudaSetDevice(c->device));
     MgState &m = g_mg[c];
     if (!m.d_set2) return fail(P3_ERR_STATE, "p3_mg_owned_end: run p3_mg_owned_begin first");
-    int rc = alloc_bloom(c, k, filter_size, num_hashes);
+    int rc = alloc_bloom(c, k, filter_size, num_hashes, min_words);
     if (rc) return rc;
     std::swap(c->d_set, m.d_set2); std::swap(c->d_list, m.d_list2); std::swap(c->nbs, m.nbs2);
     c->list_cap = c->nbs * 4;
@@ -484,12 +485,83 @@ int p3_mg_owned_end(p3_ctx *c, uint32_t k, uint64_t filter_size, uint32_t num_ha
     if (rc) return rc;
     if (c->h_stats.err_table_full) return fail(P3_ERR_TABLE_FULL, "owned k-mer set full: raise owned_slots");
     CU(cudaMemsetAsync(c->d_bloom, 0, sizeof(uint32_t) * c->bloom_words, c->stream));
-    rc = bloom_add_list(c, c->h_stats.n_distinct_solid);
-    if (rc) return rc;
+    if (do_adds) {
+        rc = bloom_add_list(c, c->h_stats.n_distinct_solid);
+        if (rc) return rc;
+    }
     CU(cudaStreamSynchronize(c->stream));
     c->have_bf = true; c->have_solid = true; c->have_adj = false; c->set_valid = true;
     c->d_set_b = m.d_set2; c->nbs_b = m.nbs2;   // after the swap: the locally seen solid k-mers
     if (n_owned) *n_owned = c->h_stats.n_distinct_solid;
+    return P3_OK;
+}
+// replicated-filter variant: adds into this rank's full copy (the caller then OR-reduces the copies)
+int p3_mg_owned_end(p3_ctx *c, uint32_t k, uint64_t filter_size, uint32_t num_hashes, uint64_t *n_owned) {
+    return owned_finish(c, k, filter_size, num_hashes, 0, true, n_owned);
+}
+// sharded-filter variant: list only; the adds follow as p3_mg_bloom_bin / _apply (or _direct)
+int p3_mg_owned_list(p3_ctx *c, uint32_t k, uint64_t filter_size, uint32_t num_hashes, uint64_t filter_words_cap, uint64_t *n_owned) {
+    return owned_finish(c, k, filter_size, num_hashes, filter_words_cap, false, n_owned);
+}
+
+uint64_t p3_bloom_seg_bits(void) { return 1ull << bloom_seg_shift(); }
+
+// buffer that receives the binned bit indices of the segments this rank owns (peers store into it;
+// export with p3_ipc_export). Grow-only; an outgrown buffer is kept until the context is destroyed
+// because peers may still have it mapped.
+int p3_mg_bloom_buffer(p3_ctx *c, uint64_t n_u32, uint32_t **d_buf) {
+    if (!c) return fail(P3_ERR_ARG, "null ctx");
+    CU(cudaSetDevice(c->device));
+    BloomBinState &b = g_bbin[c];
+    uint64_t need = sizeof(uint32_t) * std::max<uint64_t>(n_u32, 1);
+    if (!b.d_bins || b.cap_bins < need) {
+        if (b.d_bins) b.graveyard.push_back(b.d_bins);
+        b.d_bins = nullptr; b.cap_bins = 0;
+        if (cudaMalloc((void **)&b.d_bins, need) != cudaSuccess) { cudaGetLastError(); return fail(P3_ERR_NOMEM, "bloom bin buffer allocation failed"); }
+        b.cap_bins = need;
+    }
+    if (d_buf) *d_buf = b.d_bins;
+    return P3_OK;
+}
+// source side: the num_hashes bit indices of every owned k-mer, binned by filter segment and stored to
+// h_segbase[s] (device addresses, possibly peer memory; cap records each). h_counts[s] = records
+// written (a count above cap means that segment overflowed: use p3_mg_bloom_direct on all ranks).
+int p3_mg_bloom_bin(p3_ctx *c, uint32_t n_seg, const uint64_t *h_segbase, uint64_t cap, uint64_t *h_counts) {
+    if (!c || !c->have_bf || !h_segbase || !h_counts) return fail(P3_ERR_STATE, "p3_mg_bloom_bin: run p3_mg_owned_list first");
+    if (n_seg == 0 || n_seg > (uint32_t)kMaxParts || c->num_hashes > (uint32_t)kBinMaxHashes)
+        return fail(P3_ERR_ARG, "p3_mg_bloom_bin: too many segments / hash functions for the binned path");
+    CU(cudaSetDevice(c->device));
+    uint64_t n = c->h_stats.n_distinct_solid;
+    uint64_t *d_hh = nullptr;
+    int rc = bloom_hash_list(c, n, &d_hh);
+    if (rc) return rc;
+    return bloom_bin_launch(c, d_hh, n, n_seg, bloom_seg_shift(), h_segbase, cap, h_counts);
+}
+// owner side: OR the received records of local segments [seg_first, seg_first + n_local) into this
+// context's filter; h_ptr / h_n [n_local][n_src] = where source r's records of the segment are and how many
+int p3_mg_bloom_apply(p3_ctx *c, uint64_t seg_first, uint32_t n_local, uint32_t n_src, const uint64_t *h_ptr, const uint64_t *h_n) {
+    if (!c || !c->have_bf) return fail(P3_ERR_STATE, "p3_mg_bloom_apply: no filter");
+    if (n_src > (uint32_t)kMaxRegions) return fail(P3_ERR_ARG, "p3_mg_bloom_apply: at most 16 sources");
+    CU(cudaSetDevice(c->device));
+    const int shift = bloom_seg_shift();
+    for (uint32_t s = 0; s < n_local; s++) {
+        if (((seg_first + s + 1) << (shift - 5)) > c->bloom_words) return fail(P3_ERR_ARG, "p3_mg_bloom_apply: segment outside the filter allocation");
+        ApplyRegions rg; rg.count = (int)n_src;
+        for (uint32_t r = 0; r < n_src; r++) { rg.ptr[r] = (const uint32_t *)(uintptr_t)h_ptr[s * n_src + r]; rg.n[r] = h_n[s * n_src + r]; }
+        int rc = bloom_apply_launch(c, seg_first + s, shift, rg);
+        if (rc) return rc;
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    return P3_OK;
+}
+// fallback of the sharded adds: every owned k-mer straight into this rank's full copy (then OR-reduce)
+int p3_mg_bloom_direct(p3_ctx *c) {
+    if (!c || !c->have_bf) return fail(P3_ERR_STATE, "p3_mg_bloom_direct: no filter");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemsetAsync(c->d_bloom, 0, sizeof(uint32_t) * c->bloom_words, c->stream));
+    int rc = bloom_add_list(c, c->h_stats.n_distinct_solid);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(c->stream));
     return P3_OK;
 }
 

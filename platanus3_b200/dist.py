@@ -80,6 +80,13 @@ class TorchDistComm:
     def _dev(self):
         return "cuda" if torch.cuda.is_available() and self.dist.get_backend(self.group) == "nccl" else "cpu"
 
+    def all_gather_shards(self, filters, shard):
+        """filters: the one local filter tensor of world*shard words whose shard `rank` is final ->
+        every shard final on every rank (in-place all-gather)"""
+        f, = filters
+        if self.world > 1:
+            self.dist.all_gather_into_tensor(f[: self.world * shard], f[self.rank * shard:(self.rank + 1) * shard], group=self.group)
+
     def all_sum(self, values):
         t = torch.tensor(values, dtype=torch.int64, device=self._dev())
         self.dist.all_reduce(t, group=self.group)
@@ -162,6 +169,12 @@ class EmulatedComm:
             torch.bitwise_or(acc, f, out=acc)
         for f in filters:
             f.copy_(acc)
+
+    def all_gather_shards(self, filters, shard):
+        for r, f in enumerate(filters):
+            for o, g in enumerate(filters):
+                if o != r:
+                    g[r * shard:(r + 1) * shard] = f[r * shard:(r + 1) * shard]
 
     def all_sum(self, values_per_rank):
         return [int(sum(v)) for v in zip(*values_per_rank)]
@@ -350,7 +363,13 @@ def run_hot_path(ctxs, comm, k, filter_size, num_hashes, table_slots, solid_slot
         sends.append(([buf[:sum(counts)]], counts))
     recvs = _exchange(comm, sends)
     del sends
-    filters = []
+    # the filter: sharded, binned adds (each rank owns a contiguous run of 16 MB segments and receives
+    # the bit indices that fall into them) or, as fallback, adds into replicated copies + OR-reduce
+    seg_bits = int(L.p3_bloom_seg_bits())
+    nseg = (filter_size + seg_bits - 1) // seg_bits
+    spr = (nseg + w - 1) // w                  # segments per rank
+    seg_words = seg_bits // 32
+    sharded = peer and nseg <= 1024 and 0 < num_hashes <= 32 and os.environ.get("P3_MG_FILTER", "sharded") != "replicated"
     for c, st, (tensors, rcounts) in zip(ctxs, stats, recvs):
         n = sum(rcounts)
         _check(L.p3_mg_owned_begin(c.h, owned_slots or max(2 * n, 1024)))
@@ -358,14 +377,63 @@ def run_hot_path(ctxs, comm, k, filter_size, num_hashes, table_slots, solid_slot
             t = tensors[0].contiguous()
             _check(L.p3_mg_owned_insert(c.h, t.data_ptr(), n))
         no = C.c_uint64()
-        _check(L.p3_mg_owned_end(c.h, k, filter_size, num_hashes, C.byref(no)))
+        if sharded:
+            _check(L.p3_mg_owned_list(c.h, k, filter_size, num_hashes, w * spr * seg_words, C.byref(no)))
+        else:
+            _check(L.p3_mg_owned_end(c.h, k, filter_size, num_hashes, C.byref(no)))
         st.update(owned_solid=no.value)
         c.k, c.filter_size, c.num_hashes = k, filter_size, num_hashes
-        ptr, nwords = C.c_void_p(), C.c_uint64()
-        _check(L.p3_mg_filter(c.h, C.byref(ptr), C.byref(nwords)))
-        filters.append(dev_tensor(ptr.value, nwords.value, torch.int32, device))
     del recvs
-    comm.or_reduce(filters)
+
+    def filter_tensors():
+        out = []
+        for c in ctxs:
+            ptr, nwords = C.c_void_p(), C.c_uint64()
+            _check(L.p3_mg_filter(c.h, C.byref(ptr), C.byref(nwords)))
+            out.append(dev_tensor(ptr.value, nwords.value, torch.int32, device))
+        return out
+
+    binned = False
+    if sharded:
+        n_all = [row[0] for row in comm.all_gather([[st["owned_solid"]] for st in stats])]
+        force = os.environ.get("P3_BLOOM_BINNED")
+        binned = (force != "0") if force is not None else (nseg >= 2 and sum(n_all) * num_hashes >= (1 << 22))
+    if binned:
+        cap_src = [int(n * num_hashes / nseg * 1.05) + 65536 for n in n_all]    # hashed indices are uniform
+        prefix = [sum(cap_src[:r]) for r in range(w)]
+        tot_cap = sum(cap_src)
+        ptr_rows = []
+        for c in ctxs:
+            pb = C.c_void_p()
+            _check(L.p3_mg_bloom_buffer(c.h, spr * tot_cap, C.byref(pb)))
+            ptr_rows.append([pb.value])
+        table = comm.share(ptr_rows, dev_index)
+        comm.barrier()
+        count_rows = []
+        for c, r in zip(ctxs, comm.local_ranks):
+            base = (C.c_uint64 * nseg)(*[table[s // spr][0] + 4 * ((s % spr) * tot_cap + prefix[r]) for s in range(nseg)])
+            counts = (C.c_uint64 * nseg)()
+            _check(L.p3_mg_bloom_bin(c.h, nseg, base, cap_src[r], counts))
+            count_rows.append([int(x) for x in counts])
+        cnt = np.array(comm.all_gather(count_rows), dtype=np.int64).reshape(w, nseg)
+        binned = bool((cnt <= np.array(cap_src)[:, None]).all())     # the same verdict on every rank
+        comm.barrier()
+    if binned:
+        for c, r, row in zip(ctxs, comm.local_ranks, ptr_rows):
+            first = r * spr
+            nloc = max(0, min(spr, nseg - first))
+            if nloc:
+                hp = (C.c_uint64 * (nloc * w))(*[row[0] + 4 * (sl * tot_cap + prefix[src]) for sl in range(nloc) for src in range(w)])
+                hn = (C.c_uint64 * (nloc * w))(*[int(cnt[src, first + sl]) for sl in range(nloc) for src in range(w)])
+                _check(L.p3_mg_bloom_apply(c.h, first, nloc, w, hp, hn))
+        comm.all_gather_shards(filter_tensors(), spr * seg_words)
+    else:
+        if sharded:
+            for c in ctxs:
+                _check(L.p3_mg_bloom_direct(c.h))
+        comm.or_reduce([f[: (filter_size + 31) // 32] for f in filter_tensors()])
+    for st in stats:
+        st["filter"] = "sharded" if binned else "replicated"
     torch.cuda.synchronize()
 
     mark("makebf")

@@ -95,12 +95,17 @@ def test_emulated_comm_matches_definition():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("exchange", ["peer", "nccl"])
+@pytest.mark.parametrize("exchange", ["peer", "peer-sharded-filter", "nccl"])
 @pytest.mark.parametrize("world,chunk", [(1, None), (2, None), (3, 512), (8, 4096)])
 def test_distributed_hot_path_emulated(oracle, world, chunk, exchange, monkeypatch):
     """R ranks as R contexts on one GPU: counts, filter, solid k-mers, adjacency and seeds equal the
     single-node oracle. exchange = "peer": the fused bin + exchange (sources store into the owners'
     receive buffers / coverage planes directly); "nccl": the all-to-all path"""
+    want_filter = "replicated"
+    if exchange == "peer-sharded-filter":   # small segments so that the sharded, binned adds really run at test size
+        exchange, want_filter = "peer", "sharded"
+        monkeypatch.setenv("P3_BLOOM_BINNED", "1")
+        monkeypatch.setenv("P3_BLOOM_SEG_BITS", "4096")
     monkeypatch.setenv("P3_MG_EXCHANGE", exchange)
     k = 32
     g = synth.random_genome(12000, 17)
@@ -122,7 +127,7 @@ def test_distributed_hot_path_emulated(oracle, world, chunk, exchange, monkeypat
     try:
         stats = pdist.run_hot_path(ctxs, pdist.EmulatedComm(world), k, fs, nh, table_slots=max(2 * len(okeys) // world, 4096),
                                    chunk_words=chunk)
-        assert all(s["exchange"] == exchange for s in stats)
+        assert all(s["exchange"] == exchange and s["filter"] == want_filter for s in stats)
         assert sum(s["owned_positions"] for s in stats) == int(ocounts.sum())
         assert sum(s["owned_distinct21"] for s in stats) == len(okeys)
         assert sum(s["n_adds"] for s in stats) == oadds
@@ -151,6 +156,9 @@ def test_distributed_hot_path_emulated(oracle, world, chunk, exchange, monkeypat
 def _nccl_worker(rank, world, port, tmp, exchange):
     """one real rank: its slice of the reads on its own GPU, results to an .npz for the parent"""
     import torch.distributed as dist
+    if exchange == "peer-sharded-filter":
+        exchange = "peer"
+        os.environ.update(P3_BLOOM_BINNED="1", P3_BLOOM_SEG_BITS="4096")
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), P3_MG_EXCHANGE=exchange)
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
@@ -165,7 +173,7 @@ def _nccl_worker(rank, world, port, tmp, exchange):
             keys, counts = c.short_kmer_export()
             kmers, adj = c.dbg_export(sort=False)
             np.savez(os.path.join(tmp, "out_%d.npz" % rank), keys=keys, counts=counts, bits=c.bf_export(), seeds=c.seed_export(),
-                     kmers=kmers, adj=adj, n_adds=st["n_adds"], exchange=st["exchange"])
+                     kmers=kmers, adj=adj, n_adds=st["n_adds"], exchange=st["exchange"], filter=st["filter"])
             comm.barrier()
             comm.close_shared()
             comm.barrier()
@@ -174,7 +182,7 @@ def _nccl_worker(rank, world, port, tmp, exchange):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("exchange", ["peer", "nccl"])
+@pytest.mark.parametrize("exchange", ["peer", "peer-sharded-filter", "nccl"])
 def test_distributed_hot_path_two_real_gpus(oracle, tmp_path, exchange):
     """two processes on two GPUs over NCCL + CUDA IPC peer buffers (skipped on a single-GPU box)"""
     if torch.cuda.device_count() < 2:
@@ -201,7 +209,8 @@ def test_distributed_hot_path_two_real_gpus(oracle, tmp_path, exchange):
         p.join(300)
         assert p.exitcode == 0
     outs = [np.load(tmp_path / ("out_%d.npz" % r)) for r in range(world)]
-    assert all(str(o["exchange"]) == exchange for o in outs)
+    assert all(str(o["exchange"]) == exchange.split("-")[0] for o in outs)
+    assert all(str(o["filter"]) == ("sharded" if exchange.endswith("filter") else "replicated") for o in outs)
     keys = np.concatenate([o["keys"] for o in outs]); counts = np.concatenate([o["counts"] for o in outs])
     order = np.argsort(keys)
     assert np.array_equal(keys[order], okeys) and np.array_equal(counts[order], ocounts)

@@ -77,6 +77,21 @@ def test_count_modes(ctx, oracle, env, monkeypatch):
     _full_check(ctx, oracle, [b"A" * 300, b"T" * 250, b"ACGT" * 50] * 20 + reads[:200], 25, m=30011)
 
 
+@pytest.mark.parametrize("seg_bits", [1024, 4096, 1 << 16])
+def test_binned_bloom_adds(ctx, oracle, seg_bits, monkeypatch):
+    """BF.add binned by filter segment (p3_bloom.inc.cu) sets exactly the reference's bits, for the
+    auto-sized filter (19 hashes), -m filters (10 hashes; sizes that are not a multiple of the segment,
+    and tiny ones where (h1 + n*h2) wraps past 2^64 relative to the modulus) and multi-word k"""
+    monkeypatch.setenv("P3_BLOOM_BINNED", "1")
+    monkeypatch.setenv("P3_BLOOM_SEG_BITS", str(seg_bits))
+    reads = _dataset(77, genome=6000, cov=16, rl=100, err=0.01)
+    _full_check(ctx, oracle, reads, 32)
+    _full_check(ctx, oracle, reads, 25, m=30011)
+    _full_check(ctx, oracle, reads, 27, m=3 * seg_bits)
+    _full_check(ctx, oracle, reads[:300], 31, m=1000003)
+    _long_check(ctx, oracle, _dataset(78, genome=3000, cov=30, rl=150, err=0.003), 63)
+
+
 def test_threshold_other_than_two(ctx, oracle):
     """cov_threshold != 2 takes the full-lookup path; 1 makes every k-mer solid, 3 fewer"""
     reads = _dataset(62, genome=3000, cov=12, rl=90, err=0.01)
