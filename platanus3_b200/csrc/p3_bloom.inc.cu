@@ -31,21 +31,6 @@ static int bloom_seg_shift() {
     return std::min(std::max(sh, 10), 31);
 }
 
-struct BloomStep {   // (h1 + q*h2) mod 2^64 mod d, advanced without a division
-    uint64_t x, h2, r, step, d, wrap;    // wrap = 2^64 mod d
-    __device__ __forceinline__ void init(uint64_t h1, uint64_t h2_, const FastMod &fm, uint64_t wrap_) {
-        x = h1; h2 = h2_; d = fm.d; wrap = wrap_;
-        r = fastmod(h1, fm); step = fastmod(h2_, fm);
-    }
-    __device__ __forceinline__ void next() {
-        uint64_t nx = x + h2;
-        r += step;
-        if (r >= d) r -= d;
-        if (nx < x) r = r >= wrap ? r - wrap : r + d - wrap;   // the 64-bit sum wrapped (the reference's uint64 arithmetic)
-        x = nx;
-    }
-};
-
 // hh = (h1, h2) pairs of GetDoubleHash_64bit(std::hash(kmer)); seg_base[s] = where THIS source's
 // records of segment s go (may be peer memory); cursor[s] = records written so far (starts at 0)
 __global__ void __launch_bounds__(kBinThreads)

@@ -326,6 +326,22 @@ __device__ __forceinline__ bool bloom_query(const Bloom &bf, uint64_t canon) {
     }
     return true;
 }
+// (h1 + q*h2) mod 2^64 mod d for q = 0, 1, 2, ... advanced without a division: the remainder moves by
+// h2 mod d per step and by -(2^64 mod d) whenever the reference's uint64 sum wraps
+struct BloomStep {
+    uint64_t x, h2, r, step, d, wrap;
+    __device__ __forceinline__ void init(uint64_t h1, uint64_t h2_, const FastMod &fm, uint64_t wrap_) {
+        x = h1; h2 = h2_; d = fm.d; wrap = wrap_;
+        r = fastmod(h1, fm); step = fastmod(h2_, fm);
+    }
+    __device__ __forceinline__ void next() {
+        uint64_t nx = x + h2;
+        r += step;
+        if (r >= d) r -= d;
+        if (nx < x) r = r >= wrap ? r - wrap : r + d - wrap;
+        x = nx;
+    }
+};
 // IsRecorded, reference src/DeBruijnGraph.cpp:318-323 (oriented k-mer in, canonicalised here)
 __device__ __forceinline__ bool is_recorded(const Bloom &bf, uint64_t kmer, int k) {
     uint64_t rc = revcomp(kmer, k);

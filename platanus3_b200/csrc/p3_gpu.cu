@@ -577,8 +577,10 @@ adjacency_kernel(const uint64_t *__restrict__ kmers, uint64_t n, int k, Bloom bf
             uint64_t nb = neighbour(__ldg(kmers + i), d, k);
             uint64_t rc = revcomp(nb, k);
             uint64_t c = nb <= rc ? nb : rc;   // IsRecorded canonicalises (DeBruijnGraph.cpp:320-321)
-            // set_b (multi-GPU): the rank's locally seen solid k-mers, which their owners added
-            rec = (set && set_contains(set, nbs, c)) || (set_b && set_contains(set_b, nbs_b, c)) || bloom_query(bf, c);
+            // set_b (multi-GPU): the rank's locally seen solid k-mers, which their owners added. It holds
+            // nearly every solid k-mer (each rank samples the whole genome), so it is asked INSTEAD of the
+            // owned set: the rare owned-but-not-seen member just walks its num_hashes probes.
+            rec = (set_b ? set_contains(set_b, nbs_b, c) : (set && set_contains(set, nbs, c))) || bloom_query(bf, c);
         }
         unsigned m = __ballot_sync(0xffffffffu, rec);
         if (d == 0 && i < n) {
@@ -757,6 +759,7 @@ struct p3_ctx {
         Bloom b; b.bits = d_bloom; b.fm = make_fastmod(filter_size); b.nh = (int)num_hashes; b.nbytes = (int)((2 * k + 7) / 8);
         return b;
     }
+    uint64_t wrap() const { return filter_size ? ((~0ULL % filter_size) + 1) % filter_size : 0; }
     int grid(int blocks_per_sm = 8) const { return n_sm * blocks_per_sm; }
 };
 
