@@ -310,10 +310,16 @@ def main():
     n_reads, total = wl["n_reads"], wl["total_bases"]
     n_pos = n_reads * (READ_LEN - 20)
     fs, nh = _lib.estimate_bloomfilter(total, K)
+    if os.environ.get("P3_BENCH_FS_SCALE"):      # experiment knob (invalidates the metric): a larger filter on the same reads
+        fs = int(fs * float(os.environ["P3_BENCH_FS_SCALE"]))
+        args.genome = -abs(genome)
     # capacity hints (a user gives these from the expected genome size / error rate)
     distinct21 = genome + int(total * ERR * 21 * 1.05)
     table_slots = int(distinct21 / 0.55)
     solid_slots = int(genome * 1.2 / 0.5)
+    if os.environ.get("P3_BENCH_SET_SCALE"):     # experiment knob (invalidates the metric): a sparser / larger solid set
+        solid_slots = int(solid_slots * float(os.environ["P3_BENCH_SET_SCALE"]))
+        args.genome = -abs(genome)
 
     stream = torch.cuda.current_stream()
     ctx = _lib.Context(local, ctypes.c_void_p(stream.cuda_stream))
@@ -420,7 +426,7 @@ def main():
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches, "clocks": clocks,
     }
-    if genome != GENOME:
+    if genome != GENOME or args.genome != genome:
         result["config"]["workload"] += " [DEBUG OVERRIDE genome=%d: not the headline config]" % genome
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         ctx2.close()

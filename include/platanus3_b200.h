@@ -164,12 +164,15 @@ int p3_mg_owner_scatter(p3_ctx *ctx, uint32_t n_ranks, uint32_t my_rank, uint64_
 /* fused bin + exchange: owner j's records are stored straight into keys_base[j] / words_base[j],
  * device addresses (as integers) inside rank j's receive buffer that are mapped into this process
  * over NVLink peer memory, already offset to the region reserved for this source rank (n_ranks <= 16).
- * The caller barriers all ranks before the owners consume their buffers. */
+ * The caller barriers all ranks before the owners consume their buffers.
+ * async != 0: the kernel is left running on the context's second stream (so that it overlaps the
+ * insert of the previous chunk); p3_mg_scatter_wait joins it. */
 int p3_mg_owner_scatter_peer(p3_ctx *ctx, uint32_t n_ranks, uint32_t my_rank, uint64_t w0, uint64_t w1,
-                             const uint64_t *keys_base, const uint64_t *words_base);
-/* the receive buffers peers store into (grow-only; exported with p3_ipc_export), and CUDA IPC
+                             const uint64_t *keys_base, const uint64_t *words_base, int async);
+int p3_mg_scatter_wait(p3_ctx *ctx);
+/* the receive buffers peers store into (two sets, which = 0/1; grow-only; exported with p3_ipc_export), and CUDA IPC
  * plumbing: a 64-byte handle of a buffer of this process / a mapping of another process's buffer */
-int p3_mg_recv_buffers(p3_ctx *ctx, uint64_t n_records, uint64_t **d_keys, uint32_t **d_words);
+int p3_mg_recv_buffers(p3_ctx *ctx, uint64_t n_records, uint32_t which, uint64_t **d_keys, uint32_t **d_words);
 int p3_ipc_export(const void *d_ptr, uint8_t handle[64]);
 int p3_ipc_open(int device, const uint8_t handle[64], void **d_ptr);
 int p3_ipc_close(int device, void *d_ptr);

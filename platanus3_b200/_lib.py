@@ -20,7 +20,7 @@ SYMBOLS = [
     "p3_short_kmer_export", "p3_short_kmer_lookup", "p3_make_bf", "p3_make_bf_stats", "p3_bf_export",
     "p3_bf_import", "p3_seed_export", "p3_solid_flags_export", "p3_bf_add", "p3_bf_possibly_contains",
     "p3_double_hash", "p3_dbg_adjacency", "p3_dbg_stats", "p3_dbg_close", "p3_dbg_export", "p3_check_directions",
-    "p3_owner_of_key", "p3_mg_owner_hist", "p3_mg_owner_scatter", "p3_mg_owner_scatter_peer", "p3_mg_recv_buffers", "p3_ipc_export", "p3_ipc_open", "p3_ipc_close", "p3_mg_cover_plane", "p3_mg_cover_peer", "p3_mg_count_begin", "p3_mg_count_records",
+    "p3_owner_of_key", "p3_mg_owner_hist", "p3_mg_owner_scatter", "p3_mg_owner_scatter_peer", "p3_mg_scatter_wait", "p3_mg_recv_buffers", "p3_ipc_export", "p3_ipc_open", "p3_ipc_close", "p3_mg_cover_plane", "p3_mg_cover_peer", "p3_mg_count_begin", "p3_mg_count_records",
     "p3_mg_count_end", "p3_mg_singletons", "p3_mg_cover_begin", "p3_mg_cover_clear", "p3_mg_solid_local",
     "p3_mg_kmer_owner_hist", "p3_mg_kmer_owner_scatter", "p3_mg_owned_begin", "p3_mg_owned_insert",
     "p3_mg_owned_end", "p3_mg_filter", "p3_bloom_seg_bits", "p3_mg_owned_list", "p3_mg_bloom_buffer", "p3_mg_bloom_bin",
@@ -86,8 +86,9 @@ def lib():
         L.p3_owner_of_key.argtypes = [u64, u32]
         L.p3_mg_owner_hist.argtypes = [vp, u32, u64, u64, vp]
         L.p3_mg_owner_scatter.argtypes = [vp, u32, u32, u64, u64, vp, vp]
-        L.p3_mg_owner_scatter_peer.argtypes = [vp, u32, u32, u64, u64, vp, vp]
-        L.p3_mg_recv_buffers.argtypes = [vp, u64, C.POINTER(vp), C.POINTER(vp)]
+        L.p3_mg_owner_scatter_peer.argtypes = [vp, u32, u32, u64, u64, vp, vp, i32]
+        L.p3_mg_scatter_wait.argtypes = [vp]
+        L.p3_mg_recv_buffers.argtypes = [vp, u64, u32, C.POINTER(vp), C.POINTER(vp)]
         L.p3_ipc_export.argtypes = [vp, vp]
         L.p3_ipc_open.argtypes = [C.c_int, vp, C.POINTER(vp)]
         L.p3_ipc_close.argtypes = [C.c_int, vp]

@@ -304,45 +304,47 @@ hist_rec_kernel(const uint64_t *__restrict__ in, uint64_t n, uint32_t P, unsigne
 }
 
 template <int PMODE, bool HAS_AUX>
-__global__ void __launch_bounds__(kTileWords)
+__global__ void __launch_bounds__(kScatterThreads)
 scatter_rec_kernel(const uint64_t *__restrict__ in, const uint32_t *__restrict__ aux_in, uint64_t n, uint32_t P,
                    unsigned long long *cursor, uint64_t *__restrict__ out, uint32_t *__restrict__ aux_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ScatterSmem &sm = *reinterpret_cast<ScatterSmem *>(smem_raw);
+    uint16_t *rank = &sm.rank[0][0];                 // flat [kTilePos]: arrival rank of record (j, tid)
+    constexpr int NT = kScatterThreads, PER = kTilePos / NT;   // 256 threads x 16 records
     const int tid = threadIdx.x;
     const uint64_t n_tiles = (n + kTilePos - 1) / kTilePos;
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        for (uint32_t i = tid; i < P; i += kTileWords) sm.hist[i] = 0;
+        for (uint32_t i = tid; i < P; i += NT) sm.hist[i] = 0;
         __syncthreads();
         const uint64_t t0 = tile * kTilePos;
-        uint64_t rec[32];
+        uint64_t rec[PER];
 #pragma unroll
-        for (int j = 0; j < 32; j++) {
-            uint64_t i = t0 + j * kTileWords + tid;
+        for (int j = 0; j < PER; j++) {
+            uint64_t i = t0 + j * NT + tid;
             rec[j] = i < n ? __ldcs(in + i) : 0;
         }
 #pragma unroll
-        for (int j = 0; j < 32; j++) {
-            uint64_t i = t0 + j * kTileWords + tid;
-            if (i < n) sm.rank[j][tid] = (uint16_t)atomicAdd(&sm.hist[pid_of<PMODE>(rec[j], P)], 1u);
+        for (int j = 0; j < PER; j++) {
+            uint64_t i = t0 + j * NT + tid;
+            if (i < n) rank[j * NT + tid] = (uint16_t)atomicAdd(&sm.hist[pid_of<PMODE>(rec[j], P)], 1u);
         }
         __syncthreads();
-        tile_scan_and_claim<kTileWords>(sm, P, cursor, tid);
+        tile_scan_and_claim<NT>(sm, P, cursor, tid);
         __syncthreads();
 #pragma unroll
-        for (int j = 0; j < 32; j++) {
-            uint64_t i = t0 + j * kTileWords + tid;
+        for (int j = 0; j < PER; j++) {
+            uint64_t i = t0 + j * NT + tid;
             if (i < n) {
                 uint32_t pt = pid_of<PMODE>(rec[j], P);
-                uint32_t idx = sm.offs[pt] + sm.rank[j][tid];
+                uint32_t idx = sm.offs[pt] + rank[j * NT + tid];
                 sm.key[idx] = rec[j];
                 sm.part[idx] = (uint16_t)pt;
-                sm.loc[idx] = (uint16_t)(j * kTileWords + tid);
+                sm.loc[idx] = (uint16_t)(j * NT + tid);
             }
         }
         __syncthreads();
         const uint32_t total = sm.total;
-        for (uint32_t i = tid; i < total; i += kTileWords) {
+        for (uint32_t i = tid; i < total; i += NT) {
             uint32_t pt = sm.part[i];
             unsigned long long dst = sm.gbase[pt] + (i - sm.offs[pt]);
             out[dst] = sm.key[i];
@@ -1386,7 +1388,12 @@ int p3_dbg_adjacency(p3_ctx *c) {
         int rcl = adjacency_long(c, long_words(c), n, c->d_adj, c->d_stats);
         if (rcl) return rcl;
     } else if (n) {
-        adjacency_kernel<<<c->grid(), 256, 0, c->stream>>>(c->d_list, n, (int)c->k, c->bloom(), c->set_valid ? c->d_set : nullptr, c->nbs, c->set_valid ? c->d_set_b : nullptr, c->nbs_b, c->d_adj, c->d_stats);
+        const uint64_t *sa = c->set_valid ? c->d_set : nullptr, *sb = c->set_valid ? c->d_set_b : nullptr;
+        if (const char *e = getenv("P3_ADJ_SET")) {   // experiment knob: which shortcut set the neighbour queries may use
+            if (!strcmp(e, "owned")) sb = nullptr;
+            else if (!strcmp(e, "none")) sa = sb = nullptr;
+        }
+        adjacency_kernel<<<c->grid(), 256, 0, c->stream>>>(c->d_list, n, (int)c->k, c->bloom(), sa, c->nbs, sb, c->nbs_b, c->d_adj, c->d_stats);
         c->launches++;
         CU(cudaGetLastError());
     }

@@ -100,7 +100,11 @@ struct MgState {   // extra per-context state of the multi-GPU path
     uint64_t n_local = 0;
     // receive buffers of the fused bin + exchange (peers store into them over NVLink); plain
     // cudaMalloc allocations so that cudaIpcGetMemHandle can export them to the other processes
-    uint64_t *d_rkeys = nullptr; uint32_t *d_rwords = nullptr; uint64_t cap_rkeys = 0, cap_rwords = 0;
+    // (two sets: chunk c+1 is received while chunk c is being inserted)
+    uint64_t *d_rkeys[2] = {nullptr, nullptr}; uint32_t *d_rwords[2] = {nullptr, nullptr};
+    uint64_t cap_rkeys[2] = {0, 0}, cap_rwords[2] = {0, 0};
+    // the fused bin + exchange kernel of the NEXT chunk runs on its own stream with its own cursors
+    cudaStream_t stream2 = nullptr; unsigned long long *d_cursor2 = nullptr;
     bool swapped = false;   // c->d_set/d_list currently hold the OWNED set (p3_mg_owned_end swapped them in)
 };
 static std::unordered_map<p3_ctx *, MgState> g_mg;   // keyed by context (p3_ctx layout stays private to p3_gpu.cu)
@@ -109,7 +113,10 @@ static void mg_release(p3_ctx *c) {
     auto it = g_mg.find(c);
     if (it == g_mg.end()) return;
     MgState &m = it->second;
-    dfree(m.d_sing); dfree(m.d_sing2); dfree(m.d_set2); dfree(m.d_list2); dfree(m.d_rkeys); dfree(m.d_rwords);
+    dfree(m.d_sing); dfree(m.d_sing2); dfree(m.d_set2); dfree(m.d_list2);
+    for (int i = 0; i < 2; i++) { dfree(m.d_rkeys[i]); dfree(m.d_rwords[i]); }
+    dfree(m.d_cursor2);
+    if (m.stream2) cudaStreamDestroy(m.stream2);
     g_mg.erase(it);
 }
 
@@ -173,39 +180,60 @@ int p3_mg_owner_scatter(p3_ctx *c, uint32_t n_ranks, uint32_t my_rank, uint64_t 
 // the region reserved for this source rank (sizes from the all-gathered p3_mg_owner_hist counts). The
 // caller synchronises all ranks before the owners read their buffers.
 int p3_mg_owner_scatter_peer(p3_ctx *c, uint32_t n_ranks, uint32_t my_rank, uint64_t w0, uint64_t w1,
-                             const uint64_t *keys_base, const uint64_t *words_base) {
+                             const uint64_t *keys_base, const uint64_t *words_base, int async) {
     if (!c || !c->have_reads || !keys_base || !words_base) return fail(P3_ERR_STATE, "p3_mg_owner_scatter_peer: no reads / null buffers");
     if (my_rank >= n_ranks || n_ranks > kMaxPeers) return fail(P3_ERR_ARG, "p3_mg_owner_scatter_peer: at most 16 ranks");
     CU(cudaSetDevice(c->device));
-    CU(ensure(c->d_valid, c->cap_valid, sizeof(uint32_t) * (c->n_words + 1)));
+    int rc = mg_hist_buffers(c);
+    if (rc) return rc;
+    MgState &m = g_mg[c];
+    if (!m.stream2) {
+        CU(cudaStreamCreateWithFlags(&m.stream2, cudaStreamNonBlocking));
+        CU(cudaMalloc(&m.d_cursor2, sizeof(unsigned long long) * (kMaxParts + 1)));
+    }
+    if (!c->d_valid || c->cap_valid < sizeof(uint32_t) * (c->n_words + 1)) {
+        CU(cudaStreamSynchronize(m.stream2));   // nothing in flight may still write the old plane
+        CU(ensure(c->d_valid, c->cap_valid, sizeof(uint32_t) * (c->n_words + 1)));
+    }
     PeerOut po;
     for (uint32_t j = 0; j < (uint32_t)kMaxPeers; j++) {
         po.keys[j] = j < n_ranks ? (uint64_t *)(uintptr_t)keys_base[j] : nullptr;
         po.words[j] = j < n_ranks ? (uint32_t *)(uintptr_t)words_base[j] : nullptr;
     }
-    // positions inside each destination region are relative: cursors start at zero
-    CU(cudaMemsetAsync(c->d_cursor, 0, sizeof(unsigned long long) * (kMaxParts + 1), c->stream));
+    // positions inside each destination region are relative: cursors start at zero. The kernel runs
+    // on the second stream so that it can overlap the owner-side insert of the previous chunk.
+    cudaStream_t st = m.stream2;
+    CU(cudaMemsetAsync(m.d_cursor2, 0, sizeof(unsigned long long) * (kMaxParts + 1), st));
     unsigned sblocks = (unsigned)std::min<uint64_t>(std::max<uint64_t>((w1 - w0 + kTileWords - 1) / kTileWords, 1), (uint64_t)c->n_sm * 3);
     const uint64_t tag = (uint64_t)my_rank << kRecRankShift;
-    if (c->d_nmask) scatter21_kernel<true, 1, true><<<sblocks, kScatterThreads, sizeof(ScatterSmem), c->stream>>>(c->d_packed, c->d_rend, c->d_nmask, w0, w1, n_ranks, c->d_cursor, nullptr, nullptr, c->d_valid, tag, po);
-    else scatter21_kernel<false, 1, true><<<sblocks, kScatterThreads, sizeof(ScatterSmem), c->stream>>>(c->d_packed, c->d_rend, nullptr, w0, w1, n_ranks, c->d_cursor, nullptr, nullptr, c->d_valid, tag, po);
+    if (c->d_nmask) scatter21_kernel<true, 1, true><<<sblocks, kScatterThreads, sizeof(ScatterSmem), st>>>(c->d_packed, c->d_rend, c->d_nmask, w0, w1, n_ranks, m.d_cursor2, nullptr, nullptr, c->d_valid, tag, po);
+    else scatter21_kernel<false, 1, true><<<sblocks, kScatterThreads, sizeof(ScatterSmem), st>>>(c->d_packed, c->d_rend, nullptr, w0, w1, n_ranks, m.d_cursor2, nullptr, nullptr, c->d_valid, tag, po);
     c->launches++;
     CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(c->stream));
+    if (!async) CU(cudaStreamSynchronize(st));
+    return P3_OK;
+}
+// waits for an async p3_mg_owner_scatter_peer of this context
+int p3_mg_scatter_wait(p3_ctx *c) {
+    if (!c) return fail(P3_ERR_ARG, "null ctx");
+    auto it = g_mg.find(c);
+    if (it == g_mg.end() || !it->second.stream2) return P3_OK;
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(it->second.stream2));
     return P3_OK;
 }
 
 // receive buffers for n_records count records (grow-only; a grown buffer is a NEW allocation, whose
 // handle has to be exported again)
-int p3_mg_recv_buffers(p3_ctx *c, uint64_t n_records, uint64_t **d_keys, uint32_t **d_words) {
-    if (!c) return fail(P3_ERR_ARG, "null ctx");
+int p3_mg_recv_buffers(p3_ctx *c, uint64_t n_records, uint32_t which, uint64_t **d_keys, uint32_t **d_words) {
+    if (!c || which > 1) return fail(P3_ERR_ARG, "p3_mg_recv_buffers: null ctx / buffer index > 1");
     CU(cudaSetDevice(c->device));
     MgState &m = g_mg[c];
     n_records = std::max<uint64_t>(n_records, 1);
-    CU(ensure(m.d_rkeys, m.cap_rkeys, sizeof(uint64_t) * n_records));
-    CU(ensure(m.d_rwords, m.cap_rwords, sizeof(uint32_t) * n_records));
-    if (d_keys) *d_keys = m.d_rkeys;
-    if (d_words) *d_words = m.d_rwords;
+    CU(ensure(m.d_rkeys[which], m.cap_rkeys[which], sizeof(uint64_t) * n_records));
+    CU(ensure(m.d_rwords[which], m.cap_rwords[which], sizeof(uint32_t) * n_records));
+    if (d_keys) *d_keys = m.d_rkeys[which];
+    if (d_words) *d_words = m.d_rwords[which];
     return P3_OK;
 }
 
@@ -268,7 +296,7 @@ int p3_mg_count_records(p3_ctx *c, const uint64_t *d_keys, const uint32_t *d_wor
     int rc = mg_scan(c, P, nullptr);
     if (rc) return rc;
     unsigned sblocks = (unsigned)std::min<uint64_t>((n + kTilePos - 1) / kTilePos, (uint64_t)c->n_sm * 3);
-    scatter_rec_kernel<0, true><<<sblocks, kTileWords, sizeof(ScatterSmem), c->stream>>>(d_keys, d_words, n, P, c->d_cursor, c->d_bkeys, c->d_bword);
+    scatter_rec_kernel<0, true><<<sblocks, kScatterThreads, sizeof(ScatterSmem), c->stream>>>(d_keys, d_words, n, P, c->d_cursor, c->d_bkeys, c->d_bword);
     CU(cudaMemsetAsync(&c->d_stats->work, 0, sizeof(unsigned long long), c->stream));
     insert_bins_kernel<<<c->grid(), 256, 0, c->stream>>>(c->d_bkeys, c->d_bword, n, c->table(), c->ovf(), c->d_stats, c->d_cand_slot, c->d_cand_pos, c->cand_cap);
     c->launches += 3;
@@ -314,7 +342,7 @@ int p3_mg_singletons(p3_ctx *c, uint32_t n_ranks, uint64_t *h_counts, const uint
     if (rc) return rc;
     if (ns) {
         unsigned sblocks = (unsigned)std::min<uint64_t>((ns + kTilePos - 1) / kTilePos, (uint64_t)c->n_sm * 3);
-        scatter_rec_kernel<2, false><<<sblocks, kTileWords, sizeof(ScatterSmem), c->stream>>>(m.d_sing, nullptr, ns, n_ranks, c->d_cursor, m.d_sing2, nullptr);
+        scatter_rec_kernel<2, false><<<sblocks, kScatterThreads, sizeof(ScatterSmem), c->stream>>>(m.d_sing, nullptr, ns, n_ranks, c->d_cursor, m.d_sing2, nullptr);
         c->launches += 2;
     }
     CU(cudaGetLastError());
@@ -427,7 +455,7 @@ int p3_mg_kmer_owner_scatter(p3_ctx *c, uint32_t n_ranks, uint64_t *d_out) {
     uint64_t n = g_mg[c].n_local;
     if (n) {
         unsigned sblocks = (unsigned)std::min<uint64_t>((n + kTilePos - 1) / kTilePos, (uint64_t)c->n_sm * 3);
-        scatter_rec_kernel<3, false><<<sblocks, kTileWords, sizeof(ScatterSmem), c->stream>>>(c->d_list, nullptr, n, n_ranks, c->d_cursor, d_out, nullptr);
+        scatter_rec_kernel<3, false><<<sblocks, kScatterThreads, sizeof(ScatterSmem), c->stream>>>(c->d_list, nullptr, n, n_ranks, c->d_cursor, d_out, nullptr);
         c->launches++;
     }
     CU(cudaGetLastError());

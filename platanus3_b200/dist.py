@@ -259,32 +259,48 @@ def run_hot_path(ctxs, comm, k, filter_size, num_hashes, table_slots, solid_slot
             rows.append(row)
         hist = np.array(comm.all_gather(rows), dtype=np.int64).reshape(w, n_chunks, w)   # [source][chunk][owner]
         cap = hist.sum(axis=0).max(axis=0) if n_chunks else np.zeros(w, np.int64)        # per owner
+        n_buf = 2 if n_chunks > 1 else 1
         ptr_rows = []
         for c, r in zip(ctxs, comm.local_ranks):
-            pk, pw = C.c_void_p(), C.c_void_p()
-            _check(L.p3_mg_recv_buffers(c.h, int(cap[r]), C.byref(pk), C.byref(pw)))
-            ptr_rows.append([pk.value, pw.value])
-        table = comm.share(ptr_rows, dev_index)     # [rank][0 = keys, 1 = words]
+            row = []
+            for b in range(n_buf):
+                pk, pw = C.c_void_p(), C.c_void_p()
+                _check(L.p3_mg_recv_buffers(c.h, int(cap[r]), b, C.byref(pk), C.byref(pw)))
+                row += [pk.value, pw.value]
+            ptr_rows.append(row)
+        table = comm.share(ptr_rows, dev_index)     # [rank][2*buffer + (0 = keys, 1 = words)]
         comm.barrier()
         sub["bin"] += 1e3 * (time.perf_counter() - t0)
-        for ch in range(n_chunks):
-            t0 = time.perf_counter()
+
+        def scatter(ch, asynchronous):
             before = np.cumsum(hist[:, ch, :], axis=0) - hist[:, ch, :]   # [source][owner]: records of lower sources
+            b = 2 * (ch % n_buf)
             for c, r, nw in zip(ctxs, comm.local_ranks, n_words):
                 w0, w1 = chunk_range(ch, nw)
-                kb = u64a(*[table[j][0] + 8 * int(before[r, j]) for j in range(w)])
-                wb = u64a(*[table[j][1] + 4 * int(before[r, j]) for j in range(w)])
-                _check(L.p3_mg_owner_scatter_peer(c.h, w, r, w0, w1, kb, wb))
-            t1 = time.perf_counter()
-            comm.barrier()      # every source's stores have landed
+                kb = u64a(*[table[j][b] + 8 * int(before[r, j]) for j in range(w)])
+                wb = u64a(*[table[j][b + 1] + 4 * int(before[r, j]) for j in range(w)])
+                _check(L.p3_mg_owner_scatter_peer(c.h, w, r, w0, w1, kb, wb, 1 if asynchronous else 0))
+
+        # software pipeline over the chunks: while the owners insert chunk ch (L2-latency bound), the
+        # binning kernel of chunk ch+1 (ALU / NVLink bound) already stores into the other buffer set
+        t0 = time.perf_counter()
+        if n_chunks:
+            scatter(0, False)
+        comm.barrier()              # every source's stores of chunk 0 have landed
+        sub["bin"] += 1e3 * (time.perf_counter() - t0)
+        for ch in range(n_chunks):
             t2 = time.perf_counter()
+            if ch + 1 < n_chunks:
+                scatter(ch + 1, True)
+            b = 2 * (ch % n_buf)
             for c, r, row in zip(ctxs, comm.local_ranks, ptr_rows):
                 n = int(hist[:, ch, r].sum())
                 if n:
-                    _check(L.p3_mg_count_records(c.h, row[0], row[1], n))
-            comm.barrier()      # the buffers may be overwritten by the next chunk
-            t3 = time.perf_counter()
-            sub["bin"] += 1e3 * (t1 - t0); sub["exchange"] += 1e3 * (t2 - t1); sub["insert"] += 1e3 * (t3 - t2)
+                    _check(L.p3_mg_count_records(c.h, row[b], row[b + 1], n))
+            for c in ctxs:
+                _check(L.p3_mg_scatter_wait(c.h))
+            comm.barrier()          # chunk ch+1 has landed everywhere; buffer set ch % 2 is free again
+            sub["insert"] += 1e3 * (time.perf_counter() - t2)
     for ch in range(n_chunks if not peer else 0):
         t0 = time.perf_counter()
         sends = []
