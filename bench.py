@@ -266,7 +266,7 @@ def main_multi(args, rank, world, local, dev):
             "dbg_edges_per_s": sums[3] / (ms_per_step * 1e-3),
             "counts": {"kmer_positions": n_pos, "distinct_21mers": sums[0], "bf_adds": sums[1], "solid_kmers": sums[2],
                        "dbg_edges": sums[3], "filter_size_bits": fs, "num_hashes": nh},
-            "stage_ms": st["stage_ms"], "count_substage": st["count_sub_ms"],
+            "stage_ms": st["stage_ms"], "count_substage": st["count_sub_ms"], "lap_ms": st.get("lap_ms"),
             "roofline": {"kernel": "count stage (owner binning fused with the exchange + L2-resident insert), rank 0", "bound": "hbm",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                          "peak_source": peak_src, "algorithmic_bytes_per_kmer": ALGO_BYTES_PER_KMER, "kernel_ms": count_ms},

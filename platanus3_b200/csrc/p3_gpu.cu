@@ -163,6 +163,11 @@ __global__ void scan_parts_kernel(const unsigned long long *__restrict__ ghist, 
     for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) cursor[i] = s[i];
 }
 
+// fixed-capacity bins: cursor[p] = p * cap (no histogram pass)
+__global__ void init_cursors_kernel(unsigned long long *cursor, uint32_t P, uint64_t cap) {
+    for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) cursor[i] = (unsigned long long)i * cap;
+}
+
 struct ScatterSmem {
     uint64_t key[kTilePos];               // 32 KB  records sorted by partition
     uint16_t part[kTilePos];              //  8 KB
@@ -218,7 +223,7 @@ __global__ void __launch_bounds__(kScatterThreads)
 scatter21_kernel(const uint64_t *__restrict__ packed, const uint32_t *__restrict__ rend,
                  const uint32_t *__restrict__ nmask, uint64_t w0, uint64_t w1, uint32_t P,
                  unsigned long long *cursor, uint64_t *__restrict__ bkeys, uint32_t *__restrict__ bword,
-                 uint32_t *__restrict__ valid_plane, uint64_t tag, PeerOut peer = PeerOut()) {
+                 uint32_t *__restrict__ valid_plane, uint64_t tag, PeerOut peer = PeerOut(), uint64_t cap = 0) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ScatterSmem &sm = *reinterpret_cast<ScatterSmem *>(smem_raw);
     const uint64_t W21 = ~0ULL << (64 - (kShortK - 1));
@@ -278,7 +283,7 @@ scatter21_kernel(const uint64_t *__restrict__ packed, const uint32_t *__restrict
             if (PEER) {   // remote (or local) stores over NVLink into owner pt's receive buffer
                 peer.keys[pt][dst] = sm.key[i];
                 peer.words[pt][dst] = (uint32_t)(tile_w0 + sm.loc[i]);
-            } else {
+            } else if (cap == 0 || dst < (uint64_t)(pt + 1) * cap) {   // fixed-capacity bins: an overflowing record is dropped, the cursor tells
                 bkeys[dst] = sm.key[i];
                 bword[dst] = (uint32_t)(tile_w0 + sm.loc[i]);
             }
@@ -306,7 +311,7 @@ hist_rec_kernel(const uint64_t *__restrict__ in, uint64_t n, uint32_t P, unsigne
 template <int PMODE, bool HAS_AUX>
 __global__ void __launch_bounds__(kScatterThreads)
 scatter_rec_kernel(const uint64_t *__restrict__ in, const uint32_t *__restrict__ aux_in, uint64_t n, uint32_t P,
-                   unsigned long long *cursor, uint64_t *__restrict__ out, uint32_t *__restrict__ aux_out) {
+                   unsigned long long *cursor, uint64_t *__restrict__ out, uint32_t *__restrict__ aux_out, uint64_t cap = 0) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ScatterSmem &sm = *reinterpret_cast<ScatterSmem *>(smem_raw);
     uint16_t *rank = &sm.rank[0][0];                 // flat [kTilePos]: arrival rank of record (j, tid)
@@ -347,6 +352,7 @@ scatter_rec_kernel(const uint64_t *__restrict__ in, const uint32_t *__restrict__
         for (uint32_t i = tid; i < total; i += NT) {
             uint32_t pt = sm.part[i];
             unsigned long long dst = sm.gbase[pt] + (i - sm.offs[pt]);
+            if (cap && dst >= (uint64_t)(pt + 1) * cap) continue;
             out[dst] = sm.key[i];
             if (HAS_AUX) aux_out[dst] = __ldg(aux_in + t0 + sm.loc[i]);
         }
@@ -364,7 +370,8 @@ constexpr int kSweepPer = kSweepChunk / 256;
 __global__ void __launch_bounds__(256, 4)
 insert_bins_kernel(const uint64_t *__restrict__ bkeys, const uint32_t *__restrict__ bword, uint64_t n,
                    Table table, Ovf ovf, Stats *st, uint64_t *__restrict__ cand_slot,
-                   uint64_t *__restrict__ cand_pos, uint64_t cand_cap) {
+                   uint64_t *__restrict__ cand_pos, uint64_t cand_cap,
+                   uint64_t cap = 0, const unsigned long long *__restrict__ bin_end = nullptr) {
     __shared__ unsigned long long s_base, s_cand;
     __shared__ unsigned s_wtot[8];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -374,13 +381,17 @@ insert_bins_kernel(const uint64_t *__restrict__ bkeys, const uint32_t *__restric
         __syncthreads();
         const uint64_t cbase = s_base;
         if (cbase >= n) break;
+        // fixed-capacity bins (cap > 0, a multiple of kSweepChunk): partition p's records are
+        // [p*cap, bin_end[p]); a chunk never straddles two partitions
+        const uint64_t lim = cap ? min((uint64_t)__ldg(bin_end + cbase / cap), n) : n;
+        if (cbase >= lim) continue;
         uint64_t rec[kSweepPer];
         uint32_t wd[kSweepPer];
 #pragma unroll
         for (int it = 0; it < kSweepPer; it++) {   // the whole chunk's records first: 8 independent coalesced loads
             uint64_t i = cbase + it * 256 + threadIdx.x;
-            rec[it] = i < n ? __ldcs(bkeys + i) : ~0ULL;
-            wd[it] = i < n ? __ldcs(bword + i) : 0u;
+            rec[it] = i < lim ? __ldcs(bkeys + i) : ~0ULL;
+            wd[it] = i < lim ? __ldcs(bword + i) : 0u;
         }
         uint64_t created[kSweepPer];
         unsigned mine = 0;
@@ -564,7 +575,7 @@ __global__ void seeds_kernel(const uint64_t *__restrict__ off, uint64_t n_reads,
 // `set` (may be null): the distinct solid k-mers. Every member was added to the filter, so
 // possiblyContains is certainly true for it and its num_hashes probes are skipped; only
 // non-members (which mostly fail after a few probes) walk the filter.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 8)   // 32 registers: the kernel lives on occupancy (34 registers cost 40 %: 97 -> 135 ms)
 adjacency_kernel(const uint64_t *__restrict__ kmers, uint64_t n, int k, Bloom bf, const uint64_t *__restrict__ set,
                  uint64_t nbs, const uint64_t *__restrict__ set_b, uint64_t nbs_b, uint8_t *__restrict__ adj, Stats *st) {
     const int lane = threadIdx.x & 31;
@@ -973,34 +984,66 @@ static int count_binned(p3_ctx *c, uint64_t upper) {
     uint64_t have = c->cap_bkeys + c->cap_bword;
     uint64_t budget = (uint64_t)(0.7 * (double)(fr + have));
     if (const char *e = getenv("P3_BIN_BUDGET_BYTES")) budget = strtoull(e, nullptr, 10);
-    uint64_t chunk_words = std::max<uint64_t>(budget / (12 * 32), kTileWords);
+    uint64_t chunk_words = std::max<uint64_t>(budget / (13 * 32), kTileWords);
     chunk_words = std::min<uint64_t>(chunk_words / kTileWords * kTileWords, (c->n_words + kTileWords - 1) / kTileWords * kTileWords);
     if (chunk_words == 0) chunk_words = kTileWords;
-    uint64_t rec_cap = chunk_words * 32;
+    // Fixed-capacity bins: the partition of a key is a hash, so a chunk's records spread evenly over
+    // the partitions; each gets room for its expected share + 3 % + 8192 and the histogram pass
+    // (hist21, 12 ms at configs[1]) is skipped. A partition that overflows anyway (heavy-hitter
+    // keys: satellites, homopolymers) is seen in its cursor and the chunk is redone with exact bins.
+    const bool want_fixed = !getenv("P3_EXACT_BINS");
+    const double pos_per_word = std::min(32.0, c->n_words ? (double)upper / (double)c->n_words : 32.0);
+    auto fixed_cap = [&](uint64_t words) -> uint64_t {
+        uint64_t share = (uint64_t)((double)words * pos_per_word / (double)P * 1.03) + 8192;
+        return (share + kSweepChunk - 1) / kSweepChunk * kSweepChunk;
+    };
+    uint64_t rec_cap = std::max<uint64_t>(chunk_words * 32, want_fixed ? fixed_cap(std::min(chunk_words, c->n_words)) * P : 0);
     CU(ensure(c->d_bkeys, c->cap_bkeys, sizeof(uint64_t) * rec_cap));
     CU(ensure(c->d_bword, c->cap_bword, sizeof(uint32_t) * rec_cap));
     c->n_chunks = 0; c->binned_pos = 0;
     for (int i = 0; i < 4; i++) c->ms_sub[i] = 0;
+    std::vector<unsigned long long> h_cur(P);
     CU(cudaEventRecord(c->ev[0], c->stream));
     for (uint64_t w0 = 0; w0 < c->n_words; w0 += chunk_words) {
         uint64_t w1 = std::min<uint64_t>(w0 + chunk_words, c->n_words);
-        CU(cudaMemsetAsync(c->d_ghist, 0, sizeof(unsigned long long) * (kMaxParts + 1), c->stream));
-        CU(cudaEventRecord(c->ev[10], c->stream));
-        if (c->d_nmask) hist21_kernel<true, 0><<<c->grid(), 256, 0, c->stream>>>(c->d_packed, c->d_rend, c->d_nmask, w0, w1, P, c->d_ghist);
-        else hist21_kernel<false, 0><<<c->grid(), 256, 0, c->stream>>>(c->d_packed, c->d_rend, nullptr, w0, w1, P, c->d_ghist);
-        scan_parts_kernel<<<1, 256, 0, c->stream>>>(c->d_ghist, P, c->d_cursor, c->d_ghist + kMaxParts);
-        CU(cudaEventRecord(c->ev[11], c->stream));
         unsigned sblocks = (unsigned)std::min<uint64_t>((w1 - w0 + kTileWords - 1) / kTileWords, (uint64_t)c->n_sm * 3);
-        if (c->d_nmask) scatter21_kernel<true, 0><<<sblocks, kScatterThreads, sizeof(ScatterSmem), c->stream>>>(c->d_packed, c->d_rend, c->d_nmask, w0, w1, P, c->d_cursor, c->d_bkeys, c->d_bword, c->d_valid, 0);
-        else scatter21_kernel<false, 0><<<sblocks, kScatterThreads, sizeof(ScatterSmem), c->stream>>>(c->d_packed, c->d_rend, nullptr, w0, w1, P, c->d_cursor, c->d_bkeys, c->d_bword, c->d_valid, 0);
-        CU(cudaGetLastError());
-        CU(cudaEventRecord(c->ev[12], c->stream));
         unsigned long long n_rec = 0;
-        CU(cudaMemcpyAsync(&n_rec, c->d_ghist + kMaxParts, sizeof(n_rec), cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaStreamSynchronize(c->stream));
+        uint64_t cap = want_fixed ? fixed_cap(w1 - w0) : 0;
+        CU(cudaEventRecord(c->ev[10], c->stream));
+        CU(cudaEventRecord(c->ev[11], c->stream));
+        if (cap) {
+            init_cursors_kernel<<<1, 256, 0, c->stream>>>(c->d_cursor, P, cap);
+            if (c->d_nmask) scatter21_kernel<true, 0><<<sblocks, kScatterThreads, sizeof(ScatterSmem), c->stream>>>(c->d_packed, c->d_rend, c->d_nmask, w0, w1, P, c->d_cursor, c->d_bkeys, c->d_bword, c->d_valid, 0, PeerOut(), cap);
+            else scatter21_kernel<false, 0><<<sblocks, kScatterThreads, sizeof(ScatterSmem), c->stream>>>(c->d_packed, c->d_rend, nullptr, w0, w1, P, c->d_cursor, c->d_bkeys, c->d_bword, c->d_valid, 0, PeerOut(), cap);
+            CU(cudaGetLastError());
+            c->launches += 2;
+            CU(cudaMemcpyAsync(h_cur.data(), c->d_cursor, sizeof(unsigned long long) * P, cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+            for (uint32_t q = 0; q < P; q++) {
+                unsigned long long cnt = h_cur[q] - (unsigned long long)q * cap;
+                if (cnt > cap) { cap = 0; break; }     // overflow: exact bins for this chunk
+                n_rec += cnt;
+            }
+        }
+        if (!cap) {
+            CU(cudaMemsetAsync(c->d_ghist, 0, sizeof(unsigned long long) * (kMaxParts + 1), c->stream));
+            CU(cudaEventRecord(c->ev[10], c->stream));
+            if (c->d_nmask) hist21_kernel<true, 0><<<c->grid(), 256, 0, c->stream>>>(c->d_packed, c->d_rend, c->d_nmask, w0, w1, P, c->d_ghist);
+            else hist21_kernel<false, 0><<<c->grid(), 256, 0, c->stream>>>(c->d_packed, c->d_rend, nullptr, w0, w1, P, c->d_ghist);
+            scan_parts_kernel<<<1, 256, 0, c->stream>>>(c->d_ghist, P, c->d_cursor, c->d_ghist + kMaxParts);
+            CU(cudaEventRecord(c->ev[11], c->stream));
+            if (c->d_nmask) scatter21_kernel<true, 0><<<sblocks, kScatterThreads, sizeof(ScatterSmem), c->stream>>>(c->d_packed, c->d_rend, c->d_nmask, w0, w1, P, c->d_cursor, c->d_bkeys, c->d_bword, c->d_valid, 0);
+            else scatter21_kernel<false, 0><<<sblocks, kScatterThreads, sizeof(ScatterSmem), c->stream>>>(c->d_packed, c->d_rend, nullptr, w0, w1, P, c->d_cursor, c->d_bkeys, c->d_bword, c->d_valid, 0);
+            CU(cudaGetLastError());
+            c->launches += 3;
+            CU(cudaMemcpyAsync(&n_rec, c->d_ghist + kMaxParts, sizeof(n_rec), cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+        }
+        CU(cudaEventRecord(c->ev[12], c->stream));
         if (n_rec) {
             CU(cudaMemsetAsync(&c->d_stats->work, 0, sizeof(unsigned long long), c->stream));
-            insert_bins_kernel<<<c->grid(), 256, 0, c->stream>>>(c->d_bkeys, c->d_bword, n_rec, c->table(), c->ovf(), c->d_stats, c->d_cand_slot, c->d_cand_pos, c->cand_cap);
+            if (cap) insert_bins_kernel<<<c->grid(), 256, 0, c->stream>>>(c->d_bkeys, c->d_bword, (uint64_t)P * cap, c->table(), c->ovf(), c->d_stats, c->d_cand_slot, c->d_cand_pos, c->cand_cap, cap, c->d_cursor);
+            else insert_bins_kernel<<<c->grid(), 256, 0, c->stream>>>(c->d_bkeys, c->d_bword, n_rec, c->table(), c->ovf(), c->d_stats, c->d_cand_slot, c->d_cand_pos, c->cand_cap);
             CU(cudaGetLastError());
             c->launches++;
         }
@@ -1013,7 +1056,6 @@ static int count_binned(p3_ctx *c, uint64_t upper) {
             cudaEventElapsedTime(&d, c->ev[12], c->ev[13]);
             c->ms_sub[0] += a; c->ms_sub[1] += b; c->ms_sub[2] += d;
         }
-        c->launches += 3;
         c->binned_pos += n_rec;        // accumulated on the host (records == valid positions)
         c->n_chunks++;
     }

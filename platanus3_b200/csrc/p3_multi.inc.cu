@@ -280,6 +280,7 @@ int p3_mg_count_begin(p3_ctx *c, uint64_t table_slots, uint64_t max_records_per_
     CU(ensure(c->d_cand_slot, c->cap_cand_slot, sizeof(uint64_t) * c->cand_cap));
     CU(ensure(c->d_cand_pos, c->cap_cand_pos, sizeof(uint64_t) * c->cand_cap));
     c->binned_pos = 0; c->n_chunks = 0;
+    for (int i = 0; i < 4; i++) c->ms_sub[i] = 0;
     c->have_counts = false;
     return P3_OK;
 }
@@ -288,20 +289,52 @@ int p3_mg_count_records(p3_ctx *c, const uint64_t *d_keys, const uint32_t *d_wor
     if (!c) return fail(P3_ERR_ARG, "null ctx");
     if (n == 0) return P3_OK;
     CU(cudaSetDevice(c->device));
-    CU(ensure(c->d_bkeys, c->cap_bkeys, sizeof(uint64_t) * n));   // local bins grow with the largest batch
-    CU(ensure(c->d_bword, c->cap_bword, sizeof(uint32_t) * n));
     const uint32_t P = c->parts;
-    CU(cudaMemsetAsync(c->d_ghist, 0, sizeof(unsigned long long) * (kMaxParts + 1), c->stream));
-    hist_rec_kernel<0><<<c->grid(), 256, 0, c->stream>>>(d_keys, n, P, c->d_ghist);
-    int rc = mg_scan(c, P, nullptr);
-    if (rc) return rc;
+    // fixed-capacity partition bins, as in the single-GPU count (p3_gpu.cu count_binned): no histogram
+    // pass over the received records unless a partition overflows its share + 3 % + 8192
+    uint64_t cap = getenv("P3_EXACT_BINS") ? 0 : (((uint64_t)((double)n / (double)P * 1.03) + 8192 + kSweepChunk - 1) / kSweepChunk * kSweepChunk);
+    const uint64_t rec_cap = std::max<uint64_t>(n, cap * P);
+    CU(ensure(c->d_bkeys, c->cap_bkeys, sizeof(uint64_t) * rec_cap));   // local bins grow with the largest batch
+    CU(ensure(c->d_bword, c->cap_bword, sizeof(uint32_t) * rec_cap));
     unsigned sblocks = (unsigned)std::min<uint64_t>((n + kTilePos - 1) / kTilePos, (uint64_t)c->n_sm * 3);
-    scatter_rec_kernel<0, true><<<sblocks, kScatterThreads, sizeof(ScatterSmem), c->stream>>>(d_keys, d_words, n, P, c->d_cursor, c->d_bkeys, c->d_bword);
+    CU(cudaEventRecord(c->ev[10], c->stream));
+    CU(cudaEventRecord(c->ev[11], c->stream));
+    if (cap) {
+        init_cursors_kernel<<<1, 256, 0, c->stream>>>(c->d_cursor, P, cap);
+        scatter_rec_kernel<0, true><<<sblocks, kScatterThreads, sizeof(ScatterSmem), c->stream>>>(d_keys, d_words, n, P, c->d_cursor, c->d_bkeys, c->d_bword, cap);
+        c->launches += 2;
+        CU(cudaGetLastError());
+        std::vector<unsigned long long> h_cur(P);
+        CU(cudaMemcpyAsync(h_cur.data(), c->d_cursor, sizeof(unsigned long long) * P, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        for (uint32_t q = 0; q < P; q++)
+            if (h_cur[q] - (unsigned long long)q * cap > cap) { cap = 0; break; }
+    }
+    if (!cap) {
+        CU(cudaMemsetAsync(c->d_ghist, 0, sizeof(unsigned long long) * (kMaxParts + 1), c->stream));
+        CU(cudaEventRecord(c->ev[10], c->stream));
+        hist_rec_kernel<0><<<c->grid(), 256, 0, c->stream>>>(d_keys, n, P, c->d_ghist);
+        int rc = mg_scan(c, P, nullptr);
+        if (rc) return rc;
+        CU(cudaEventRecord(c->ev[11], c->stream));
+        scatter_rec_kernel<0, true><<<sblocks, kScatterThreads, sizeof(ScatterSmem), c->stream>>>(d_keys, d_words, n, P, c->d_cursor, c->d_bkeys, c->d_bword);
+        c->launches += 3;
+    }
+    CU(cudaEventRecord(c->ev[12], c->stream));
     CU(cudaMemsetAsync(&c->d_stats->work, 0, sizeof(unsigned long long), c->stream));
-    insert_bins_kernel<<<c->grid(), 256, 0, c->stream>>>(c->d_bkeys, c->d_bword, n, c->table(), c->ovf(), c->d_stats, c->d_cand_slot, c->d_cand_pos, c->cand_cap);
-    c->launches += 3;
+    if (cap) insert_bins_kernel<<<c->grid(), 256, 0, c->stream>>>(c->d_bkeys, c->d_bword, (uint64_t)P * cap, c->table(), c->ovf(), c->d_stats, c->d_cand_slot, c->d_cand_pos, c->cand_cap, cap, c->d_cursor);
+    else insert_bins_kernel<<<c->grid(), 256, 0, c->stream>>>(c->d_bkeys, c->d_bword, n, c->table(), c->ovf(), c->d_stats, c->d_cand_slot, c->d_cand_pos, c->cand_cap);
+    CU(cudaEventRecord(c->ev[13], c->stream));
+    c->launches++;
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(c->stream));
+    {   // owner-side sub-stage times: partition histogram, tile sort by partition, L2-resident insert sweep
+        float a = 0, b = 0, d = 0;
+        cudaEventElapsedTime(&a, c->ev[10], c->ev[11]);
+        cudaEventElapsedTime(&b, c->ev[11], c->ev[12]);
+        cudaEventElapsedTime(&d, c->ev[12], c->ev[13]);
+        c->ms_sub[0] += a; c->ms_sub[1] += b; c->ms_sub[2] += d;
+    }
     c->binned_pos += n; c->n_chunks++;
     return P3_OK;
 }

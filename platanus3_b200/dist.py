@@ -330,11 +330,22 @@ def run_hot_path(ctxs, comm, k, filter_size, num_hashes, table_slots, solid_slot
         a, b = C.c_uint64(), C.c_uint64()
         _check(L.p3_short_kmer_stats(c.h, C.byref(a), C.byref(b)))
         st.update(owned_positions=a.value, owned_distinct21=b.value, exchange="peer" if peer else "nccl")
+        st["owner_count_ms"] = {kk: v for kk, v in c.count_substage_ms().items() if kk in ("hist", "scatter", "insert")}
 
     mark("count")
+    laps = {}
+    lap_t = [time.perf_counter()]
+
+    def lap(name):      # wall-clock laps between library calls (each of which returns synchronised)
+        torch.cuda.synchronize()
+        now = time.perf_counter()
+        laps[name] = laps.get(name, 0.0) + 1e3 * (now - lap_t[0])
+        lap_t[0] = now
     # ---- B1: singleton verdicts back to the reads ----------------------------------------------------
-    if peer and os.environ.get("P3_MG_COVER", "peer") != "nccl":
-        # owners clear the bits of their count-1 keys directly in the source ranks' planes (NVLink RED.AND)
+    if peer and os.environ.get("P3_MG_COVER", "nccl") == "peer":
+        # owners clear the bits of their count-1 keys directly in the source ranks' planes (NVLink RED.AND).
+        # NOT the default: remote atomics are slow — equal to the all-to-all route at 2 GPUs (57 vs 60 ms)
+        # but 2168 ms instead of 74 ms at 8 GPUs (profiles/r02_summary.md)
         ptr_rows = []
         for c in ctxs:
             _check(L.p3_mg_cover_begin(c.h))
@@ -364,6 +375,7 @@ def run_hot_path(ctxs, comm, k, filter_size, num_hashes, table_slots, solid_slot
                 _check(L.p3_mg_cover_clear(c.h, t.data_ptr(), n))
         del sends, recvs
 
+    lap("coverage")
     mark("coverage")
     # ---- B2: solid k-mers to their owners ---------------------------------------------------------------
     sends = []
@@ -371,14 +383,17 @@ def run_hot_path(ctxs, comm, k, filter_size, num_hashes, table_slots, solid_slot
         a, b = C.c_uint64(), C.c_uint64()
         _check(L.p3_mg_solid_local(c.h, k, solid_slots, C.byref(a), C.byref(b)))
         st.update(n_adds=a.value, local_distinct_solid=b.value)
+        lap("solid_local")
         counts = (C.c_uint64 * w)()
         _check(L.p3_mg_kmer_owner_hist(c.h, w, counts))
         counts = [int(x) for x in counts]
         buf = torch.empty(max(sum(counts), 1), dtype=torch.int64, device=device)
         _check(L.p3_mg_kmer_owner_scatter(c.h, w, buf.data_ptr()))
         sends.append(([buf[:sum(counts)]], counts))
+        lap("kmer_bin")
     recvs = _exchange(comm, sends)
     del sends
+    lap("kmer_exchange")
     # the filter: sharded, binned adds (each rank owns a contiguous run of 16 MB segments and receives
     # the bit indices that fall into them) or, as fallback, adds into replicated copies + OR-reduce
     seg_bits = int(L.p3_bloom_seg_bits())
@@ -400,6 +415,7 @@ def run_hot_path(ctxs, comm, k, filter_size, num_hashes, table_slots, solid_slot
         st.update(owned_solid=no.value)
         c.k, c.filter_size, c.num_hashes = k, filter_size, num_hashes
     del recvs
+    lap("owned_dedupe")
 
     def filter_tensors():
         out = []
@@ -434,6 +450,7 @@ def run_hot_path(ctxs, comm, k, filter_size, num_hashes, table_slots, solid_slot
         cnt = np.array(comm.all_gather(count_rows), dtype=np.int64).reshape(w, nseg)
         binned = bool((cnt <= np.array(cap_src)[:, None]).all())     # the same verdict on every rank
         comm.barrier()
+        lap("bloom_bin")
     if binned:
         for c, r, row in zip(ctxs, comm.local_ranks, ptr_rows):
             first = r * spr
@@ -442,7 +459,9 @@ def run_hot_path(ctxs, comm, k, filter_size, num_hashes, table_slots, solid_slot
                 hp = (C.c_uint64 * (nloc * w))(*[row[0] + 4 * (sl * tot_cap + prefix[src]) for sl in range(nloc) for src in range(w)])
                 hn = (C.c_uint64 * (nloc * w))(*[int(cnt[src, first + sl]) for sl in range(nloc) for src in range(w)])
                 _check(L.p3_mg_bloom_apply(c.h, first, nloc, w, hp, hn))
+        lap("bloom_apply")
         comm.all_gather_shards(filter_tensors(), spr * seg_words)
+        lap("filter_gather")
     else:
         if sharded:
             for c in ctxs:
@@ -463,4 +482,5 @@ def run_hot_path(ctxs, comm, k, filter_size, num_hashes, table_slots, solid_slot
     for st in stats:
         st["stage_ms"] = ms
         st["count_sub_ms"] = sub
+        st["lap_ms"] = dict(laps, **{"owner_" + kk: v for kk, v in st.get("owner_count_ms", {}).items()})
     return stats

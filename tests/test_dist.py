@@ -106,6 +106,7 @@ def test_distributed_hot_path_emulated(oracle, world, chunk, exchange, monkeypat
         exchange, want_filter = "peer", "sharded"
         monkeypatch.setenv("P3_BLOOM_BINNED", "1")
         monkeypatch.setenv("P3_BLOOM_SEG_BITS", "4096")
+        monkeypatch.setenv("P3_MG_COVER", "peer")      # and the remote RED.AND coverage route (not the default)
     monkeypatch.setenv("P3_MG_EXCHANGE", exchange)
     k = 32
     g = synth.random_genome(12000, 17)
@@ -158,7 +159,7 @@ def _nccl_worker(rank, world, port, tmp, exchange):
     import torch.distributed as dist
     if exchange == "peer-sharded-filter":
         exchange = "peer"
-        os.environ.update(P3_BLOOM_BINNED="1", P3_BLOOM_SEG_BITS="4096")
+        os.environ.update(P3_BLOOM_BINNED="1", P3_BLOOM_SEG_BITS="4096", P3_MG_COVER="peer")
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), P3_MG_EXCHANGE=exchange)
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))

@@ -67,6 +67,8 @@ def test_pipeline_small(ctx, oracle, k):
     {"P3_PARTS": "7"},
     {"P3_PARTS": "1024", "P3_BIN_BUDGET_BYTES": "200000"},   # many partitions, many chunks
     {"P3_PARTS": "3", "P3_BIN_BUDGET_BYTES": "1"},            # one tile per chunk
+    {"P3_EXACT_BINS": "1"},                                    # histogram-sized bins instead of fixed-capacity ones
+    {"P3_EXACT_BINS": "1", "P3_PARTS": "9", "P3_BIN_BUDGET_BYTES": "300000"},
 ])
 def test_count_modes(ctx, oracle, env, monkeypatch):
     """direct table vs binned/partitioned count (any partition count, any chunking) are all exact"""
@@ -90,6 +92,15 @@ def test_binned_bloom_adds(ctx, oracle, seg_bits, monkeypatch):
     _full_check(ctx, oracle, reads, 27, m=3 * seg_bits)
     _full_check(ctx, oracle, reads[:300], 31, m=1000003)
     _long_check(ctx, oracle, _dataset(78, genome=3000, cov=30, rl=150, err=0.003), 63)
+
+
+def test_fixed_capacity_bins_overflow_falls_back(ctx, oracle, monkeypatch):
+    """The binned count gives every table partition room for its expected share of a chunk; a heavy-hitter
+    key (here a homopolymer: 1.1 M occurrences of ONE 21-mer) overflows its partition, which must be
+    detected and redone with exact bins — counts stay bit-exact."""
+    monkeypatch.setenv("P3_PARTS", "64")
+    reads = [b"A" * 400] * 3000 + _dataset(91, genome=5000, cov=12, rl=100, err=0.01)
+    _full_check(ctx, oracle, reads, 32, n_adj=300)
 
 
 def test_threshold_other_than_two(ctx, oracle):

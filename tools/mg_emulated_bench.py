@@ -29,6 +29,7 @@ def main():
     ctxs, keep, total_all = [], [], 0
     for r in range(w):
         wl = workload.make_reads(genome, COV / w, RL, ERR, 1234, dev, read_seed=5678 + r)
+        torch.cuda.synchronize()    # the reads must be complete before the library's own stream looks at them
         c = _lib.Context(0, ctypes.c_void_p(stream.cuda_stream))
         c.attach(wl["packed"].data_ptr(), wl["total_bases"], wl["off"].data_ptr(), wl["n_reads"], None, keep=wl)
         ctxs.append(c); keep.append(wl); total_all += wl["total_bases"]
@@ -42,7 +43,7 @@ def main():
     out = None
     for _ in range(args.steps):
         out = pdist.run_hot_path(ctxs, comm, K, fs, nh, table_slots, solid_slots, owned_slots, 1 << 25, dev)
-    print(json.dumps({"world": w, "genome_bp": genome, "stage_ms": out[0]["stage_ms"], "count_sub_ms": out[0]["count_sub_ms"],
+    print(json.dumps({"world": w, "genome_bp": genome, "stage_ms": out[0]["stage_ms"], "count_sub_ms": out[0]["count_sub_ms"], "lap_ms": out[0]["lap_ms"],
                       "owned_solid": [s["owned_solid"] for s in out], "filter": out[0]["filter"], "exchange": out[0]["exchange"]}))
     for c in ctxs:
         c.close()
