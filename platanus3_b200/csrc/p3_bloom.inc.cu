@@ -247,3 +247,159 @@ static int bloom_add_binned(p3_ctx *c, uint64_t n, bool *done) {
     *done = true;
     return P3_OK;
 }
+
+// ---- binned coverage-bit clears --------------------------------------------------------------------
+// MakeBF's coverage test (reference src/MakeBloomFilter.cpp:52-58) clears one bit per count-1 key:
+// ~1.05 G single-bit RED.ANDs at random positions of a 0.54 GB plane at configs[1], 21.8 G/s from DRAM.
+// Same cure as for BF.add: the positions are tile-sorted by plane segment (2^27 positions = 16 MB) and
+// applied segment by segment with the window L2 resident. A segment can never receive more records
+// than it has positions, so the bins have a hard upper bound and need neither a histogram nor an
+// overflow path.
+constexpr int kPosKpt = 8;   // inputs per thread per tile
+// MODE 0: candidates (slot, position) of the binned count — emitted when the key's final count < thr
+// MODE 1: a plain list of position records
+template <int MODE>
+__global__ void __launch_bounds__(kBinThreads)
+pos_bin_kernel(const uint64_t *__restrict__ slots, const uint64_t *__restrict__ cand_slot, const uint64_t *__restrict__ pos_in,
+               uint64_t n, uint64_t thr, Ovf ovf, const Stats *st, int shift, uint32_t P, uint32_t *__restrict__ bins,
+               uint64_t cap, unsigned long long *cursor) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr uint32_t T = kBinThreads * kPosKpt;
+    uint32_t *s_rec = reinterpret_cast<uint32_t *>(smem_raw);
+    unsigned long long *s_gbase = reinterpret_cast<unsigned long long *>(s_rec + T);
+    uint32_t *s_hist = reinterpret_cast<uint32_t *>(s_gbase + P);
+    uint32_t *s_offs = s_hist + P;
+    uint32_t *s_cur = s_offs + P;
+    uint16_t *s_seg = reinterpret_cast<uint16_t *>(s_cur + P);
+    __shared__ uint32_t s_wtot[kBinThreads / 32];
+    __shared__ uint32_t s_total;
+    const int tid = threadIdx.x;
+    const unsigned n_overflow = MODE == 0 ? st->n_overflow : 0u;
+    const uint64_t pmask = (1ULL << kPosRankShift) - 1, smask = (1ULL << shift) - 1;
+    const uint64_t n_tiles = (n + T - 1) / T;
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (uint32_t i = tid; i < P; i += kBinThreads) s_hist[i] = 0;
+        __syncthreads();
+        uint64_t pos[kPosKpt];
+#pragma unroll
+        for (int q = 0; q < kPosKpt; q++) {
+            const uint64_t i = tile * T + (uint64_t)q * kBinThreads + tid;
+            pos[q] = ~0ULL;
+            if (i < n) {
+                if (MODE == 0) {
+                    uint64_t v = __ldcg(slots + __ldcs(cand_slot + i));
+                    uint64_t c = v >> 42;
+                    if (c < thr && n_overflow) c += ovf_get(ovf, v & kKey42) << 22;
+                    if (c < thr) pos[q] = __ldcs(pos_in + i) & pmask;
+                } else {
+                    pos[q] = __ldcs(pos_in + i) & pmask;
+                }
+            }
+            if (pos[q] != ~0ULL) atomicAdd(&s_hist[(uint32_t)(pos[q] >> shift)], 1u);
+        }
+        __syncthreads();
+        {
+            const uint32_t per = (P + kBinThreads - 1) / kBinThreads;
+            const uint32_t b0 = tid * per;
+            uint32_t local = 0;
+            for (uint32_t j = 0; j < per; j++) if (b0 + j < P) local += s_hist[b0 + j];
+            uint32_t incl = local;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, d); if ((tid & 31) >= d) incl += v; }
+            if ((tid & 31) == 31) s_wtot[tid >> 5] = incl;
+            __syncthreads();
+            uint32_t wbase = 0;
+            for (int q = 0; q < (tid >> 5); q++) wbase += s_wtot[q];
+            uint32_t run = wbase + incl - local;
+            for (uint32_t j = 0; j < per; j++) {
+                uint32_t i = b0 + j;
+                if (i < P) {
+                    uint32_t h = s_hist[i];
+                    s_offs[i] = run; s_cur[i] = run;
+                    if (h) s_gbase[i] = atomicAdd(&cursor[i], (unsigned long long)h);
+                    run += h;
+                }
+            }
+            if (tid == kBinThreads - 1) s_total = wbase + incl;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < kPosKpt; q++) {
+            if (pos[q] != ~0ULL) {
+                uint32_t sg = (uint32_t)(pos[q] >> shift);
+                uint32_t idx = atomicAdd(&s_cur[sg], 1u);
+                s_rec[idx] = (uint32_t)(pos[q] & smask);
+                s_seg[idx] = (uint16_t)sg;
+            }
+        }
+        __syncthreads();
+        const uint32_t total = s_total;
+        for (uint32_t i = tid; i < total; i += kBinThreads) {
+            uint32_t sg = s_seg[i];
+            unsigned long long dst = s_gbase[sg] + (i - s_offs[sg]);
+            if (dst < cap) bins[(uint64_t)sg * cap + dst] = s_rec[i];
+        }
+        __syncthreads();
+    }
+}
+// RED.AND of one segment's records into its window of a plane whose bit for position p is
+// 0x80000000 >> (p & 31) of word p >> 5 (the layout of the valid / coverage / solid planes)
+__global__ void __launch_bounds__(256)
+plane_clear_kernel(const uint32_t *__restrict__ rec, uint64_t n, uint32_t *__restrict__ seg_words) {
+    const uint64_t stride = gridDim.x * (uint64_t)blockDim.x;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint32_t off = __ldcs(rec + i);
+        atomicAnd(seg_words + (off >> 5), ~(0x80000000u >> (off & 31)));
+    }
+}
+
+// clears, in `plane` (n_pos positions), the bit of every emitted position; *done = false when the job is
+// too small to be worth it or the scratch does not fit (the caller then clears directly)
+template <int MODE>
+static int binned_plane_clear(p3_ctx *c, const uint64_t *cand_slot, const uint64_t *pos_in, uint64_t n, uint64_t thr,
+                              uint32_t *plane, uint64_t n_pos, bool *done) {
+    *done = false;
+    const int shift = bloom_seg_shift();
+    const uint64_t n_seg = (n_pos + (1ull << shift) - 1) >> shift;
+    if (n < (1u << 22) || n_seg < 2 || n_seg > (uint64_t)kMaxParts || getenv("P3_DIRECT_CLEARS")) {
+        if (!(getenv("P3_BINNED_CLEARS") && n && n_seg <= (uint64_t)kMaxParts)) return P3_OK;
+    }
+    const uint64_t cap = std::min<uint64_t>(1ull << shift, n);      // a segment has 2^shift positions: a hard bound
+    const uint64_t need = sizeof(uint32_t) * cap * n_seg;
+    BloomBinState &b = g_bbin[c];
+    uint32_t *bins = nullptr;
+    if (c->d_bkeys && c->cap_bkeys >= need) bins = reinterpret_cast<uint32_t *>(c->d_bkeys);   // count-stage bins are idle now
+    else {
+        size_t fr = 0, tot = 0;
+        CU(cudaMemGetInfo(&fr, &tot));
+        if (b.cap_bins < need && need > (uint64_t)(0.5 * (double)fr)) return P3_OK;
+        CU(ensure(b.d_bins, b.cap_bins, need));
+        bins = b.d_bins;
+    }
+    if (!c->d_ghist) {
+        CU(cudaMalloc(&c->d_ghist, sizeof(unsigned long long) * (kMaxParts + 1)));
+        CU(cudaMalloc(&c->d_cursor, sizeof(unsigned long long) * (kMaxParts + 1)));
+    }
+    CU(cudaMemsetAsync(c->d_cursor, 0, sizeof(unsigned long long) * (kMaxParts + 1), c->stream));
+    const size_t smem = (size_t)kBinThreads * kPosKpt * 6 + (size_t)n_seg * 20;
+    CU(cudaFuncSetAttribute(pos_bin_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint64_t T = (uint64_t)kBinThreads * kPosKpt;
+    unsigned blocks = (unsigned)std::min<uint64_t>((n + T - 1) / T, (uint64_t)c->n_sm * 8);
+    pos_bin_kernel<MODE><<<blocks, kBinThreads, smem, c->stream>>>(c->d_table, cand_slot, pos_in, n, thr, c->ovf(), c->d_stats, shift,
+                                                                   (uint32_t)n_seg, bins, cap, c->d_cursor);
+    c->launches++;
+    CU(cudaGetLastError());
+    std::vector<unsigned long long> h(n_seg);
+    CU(cudaMemcpyAsync(h.data(), c->d_cursor, sizeof(unsigned long long) * n_seg, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    for (uint64_t s = 0; s < n_seg; s++) {
+        if (h[s] > cap) return fail(P3_ERR_STATE, "binned_plane_clear: more records than positions in a segment (duplicate positions?)");
+        if (!h[s]) continue;
+        unsigned ab = (unsigned)std::min<uint64_t>((h[s] + 255) / 256, (uint64_t)c->grid());
+        plane_clear_kernel<<<ab, 256, 0, c->stream>>>(bins + s * cap, h[s], plane + (s << (shift - 5)));
+        c->launches++;
+    }
+    CU(cudaGetLastError());
+    *done = true;
+    return P3_OK;
+}

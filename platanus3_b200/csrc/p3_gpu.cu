@@ -780,6 +780,8 @@ static void mg_release(struct p3_ctx *c);   // p3_multi.inc.cu
 static void long_release(struct p3_ctx *c); // p3_long.inc.cu
 static void bloom_release(struct p3_ctx *c);                                  // p3_bloom.inc.cu
 static int bloom_add_binned(struct p3_ctx *c, uint64_t n, bool *done);
+template <int MODE> static int binned_plane_clear(struct p3_ctx *c, const uint64_t *cand_slot, const uint64_t *pos_in, uint64_t n,
+                                                  uint64_t thr, uint32_t *plane, uint64_t n_pos, bool *done);
 static int make_bf_long(struct p3_ctx *c, uint32_t k, uint64_t solid_slots);
 static int adjacency_long(struct p3_ctx *c, const uint64_t *d_words, uint64_t n, uint8_t *d_adj, struct p3::Stats *st);
 static const uint64_t *long_words(struct p3_ctx *c);
@@ -1252,7 +1254,12 @@ int p3_make_bf(p3_ctx *c, uint32_t k, uint64_t filter_size, uint32_t num_hashes,
         // every valid position is good unless it is the single occurrence of a count-1 key
         CU(cudaMemcpyAsync(c->d_good21, c->d_valid, sizeof(uint32_t) * c->n_words, cudaMemcpyDeviceToDevice, c->stream));
         uint64_t nc = c->h_stats.n_cand;
-        if (nc) {
+        bool cleared = false;
+        if (nc) {   // binned, L2-resident clears (p3_bloom.inc.cu); small jobs clear directly
+            int rcc = binned_plane_clear<0>(c, c->d_cand_slot, c->d_cand_pos, nc, cov_threshold, c->d_good21, c->n_words * 32, &cleared);
+            if (rcc) return rcc;
+        }
+        if (nc && !cleared) {
             cand_check_kernel<<<c->grid(), 256, 0, c->stream>>>(c->d_table, c->d_cand_slot, c->d_cand_pos, nc, cov_threshold, c->ovf(), c->d_stats, c->d_good21);
             c->launches++;
         }

@@ -410,6 +410,10 @@ int p3_mg_cover_clear(p3_ctx *c, const uint64_t *d_pos, uint64_t n) {
     if (!c || !c->d_good21) return fail(P3_ERR_STATE, "p3_mg_cover_clear: run p3_mg_cover_begin first");
     if (n == 0) return P3_OK;
     CU(cudaSetDevice(c->device));
+    bool cleared = false;
+    int rcc = binned_plane_clear<1>(c, nullptr, d_pos, n, 0, c->d_good21, c->n_words * 32, &cleared);
+    if (rcc) return rcc;
+    if (cleared) { CU(cudaStreamSynchronize(c->stream)); return P3_OK; }
     clear_positions_kernel<<<c->grid(), 256, 0, c->stream>>>(d_pos, n, c->d_good21);
     c->launches++;
     CU(cudaGetLastError());

@@ -283,6 +283,7 @@ def run_hot_path(ctxs, comm, k, filter_size, num_hashes, table_slots, solid_slot
 
         # software pipeline over the chunks: while the owners insert chunk ch (L2-latency bound), the
         # binning kernel of chunk ch+1 (ALU / NVLink bound) already stores into the other buffer set
+        overlap = os.environ.get("P3_MG_OVERLAP", "0") != "0"
         t0 = time.perf_counter()
         if n_chunks:
             scatter(0, False)
@@ -290,13 +291,15 @@ def run_hot_path(ctxs, comm, k, filter_size, num_hashes, table_slots, solid_slot
         sub["bin"] += 1e3 * (time.perf_counter() - t0)
         for ch in range(n_chunks):
             t2 = time.perf_counter()
-            if ch + 1 < n_chunks:
+            if ch + 1 < n_chunks and overlap:
                 scatter(ch + 1, True)
             b = 2 * (ch % n_buf)
             for c, r, row in zip(ctxs, comm.local_ranks, ptr_rows):
                 n = int(hist[:, ch, r].sum())
                 if n:
                     _check(L.p3_mg_count_records(c.h, row[b], row[b + 1], n))
+            if ch + 1 < n_chunks and not overlap:
+                scatter(ch + 1, False)
             for c in ctxs:
                 _check(L.p3_mg_scatter_wait(c.h))
             comm.barrier()          # chunk ch+1 has landed everywhere; buffer set ch % 2 is free again

@@ -106,7 +106,10 @@ def test_distributed_hot_path_emulated(oracle, world, chunk, exchange, monkeypat
         exchange, want_filter = "peer", "sharded"
         monkeypatch.setenv("P3_BLOOM_BINNED", "1")
         monkeypatch.setenv("P3_BLOOM_SEG_BITS", "4096")
-        monkeypatch.setenv("P3_MG_COVER", "peer")      # and the remote RED.AND coverage route (not the default)
+        if world == 3:
+            monkeypatch.setenv("P3_MG_COVER", "peer")  # the remote RED.AND coverage route (not the default)
+        else:
+            monkeypatch.setenv("P3_BINNED_CLEARS", "1")  # received singleton positions cleared segment by segment
     monkeypatch.setenv("P3_MG_EXCHANGE", exchange)
     k = 32
     g = synth.random_genome(12000, 17)

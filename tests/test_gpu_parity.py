@@ -67,6 +67,8 @@ def test_pipeline_small(ctx, oracle, k):
     {"P3_PARTS": "7"},
     {"P3_PARTS": "1024", "P3_BIN_BUDGET_BYTES": "200000"},   # many partitions, many chunks
     {"P3_PARTS": "3", "P3_BIN_BUDGET_BYTES": "1"},            # one tile per chunk
+    {"P3_BINNED_CLEARS": "1", "P3_BLOOM_SEG_BITS": "4096"},   # coverage-bit clears binned by plane segment
+    {"P3_BINNED_CLEARS": "1", "P3_BLOOM_SEG_BITS": "1024", "P3_PARTS": "5"},
     {"P3_EXACT_BINS": "1"},                                    # histogram-sized bins instead of fixed-capacity ones
     {"P3_EXACT_BINS": "1", "P3_PARTS": "9", "P3_BIN_BUDGET_BYTES": "300000"},
 ])
