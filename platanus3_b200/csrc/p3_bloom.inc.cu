@@ -227,8 +227,11 @@ static int bloom_add_binned(p3_ctx *c, uint64_t n, bool *done) {
     uint64_t *d_hh = nullptr;
     int rc = bloom_hash_list(c, n, &d_hh);
     if (rc) return rc;
-    // hashed indices are uniform over the filter: 5 % + 64 K slack per segment
-    const uint64_t cap = (uint64_t)((double)n * c->num_hashes / (double)n_seg * 1.05) + 65536;
+    // hashed indices are uniform over the filter: a FULL segment receives n * num_hashes * seg_bits /
+    // filter_size of them (the last segment is usually partial, so this is more than 1 / n_seg);
+    // 5 % + 64 K slack
+    const double share = std::min(1.0, (double)(1ull << shift) / (double)c->filter_size);
+    const uint64_t cap = (uint64_t)((double)n * c->num_hashes * share * 1.05) + 65536;
     const uint64_t need = sizeof(uint32_t) * cap * n_seg;
     BloomBinState &b = g_bbin[c];
     uint32_t *bins = nullptr;

@@ -258,11 +258,23 @@ __device__ __forceinline__ uint64_t count_lookup(const Table &t, uint64_t key, c
 }
 
 // ---- solid k-mer set: 64-bit keys, 4 per bucket --------------------------------------------------
+// Addressed like the count table: P partitions of nbp buckets, a key's partition from the top bits of
+// fmix64(key), its bucket inside the partition from the low 32 bits, probing stays inside the
+// partition. P = 1 is a plain table; with P > 1 the de-duplication sweep over k-mers binned by
+// partition works in one ~24 MB, L2-resident window at a time.
+struct KSet {
+    uint64_t *slots;
+    uint64_t nbp;   // buckets per partition (< 2^32)
+    uint32_t P;     // partitions
+};
+__device__ __forceinline__ uint32_t kset_part(uint64_t key, uint32_t P) { return part_of(fmix64(key), P); }
 // returns 1 = inserted now, 0 = already present, -1 = table full
-__device__ __forceinline__ int set_insert(uint64_t *table, uint64_t nb, uint64_t key) {
-    uint64_t b = __umul64hi(fmix64(key), nb);
-    for (uint64_t probe = 0; probe < nb; probe++) {
-        uint64_t *bp = table + 4 * b;
+__device__ __forceinline__ int set_insert(const KSet &t, uint64_t key) {
+    const uint64_t h = fmix64(key);
+    const uint64_t base = (uint64_t)part_of(h, t.P) * t.nbp;
+    uint64_t b = sub_of(h, t.nbp);
+    for (uint64_t probe = 0; probe < t.nbp; probe++) {
+        uint64_t *bp = t.slots + 4 * (base + b);
         uint64_t s[4];
         ld_bucket64(bp, s);
 #pragma unroll
@@ -275,23 +287,25 @@ __device__ __forceinline__ int set_insert(uint64_t *table, uint64_t nb, uint64_t
                 if (old == key) return 0;
             }
         }
-        b = (b + 1 == nb) ? 0 : b + 1;
+        b = (b + 1 == t.nbp) ? 0 : b + 1;
     }
     return -1;
 }
 
 // membership only (read-only table)
-__device__ __forceinline__ bool set_contains(const uint64_t *table, uint64_t nb, uint64_t key) {
-    uint64_t b = __umul64hi(fmix64(key), nb);
-    for (uint64_t probe = 0; probe < nb; probe++) {
+__device__ __forceinline__ bool set_contains(const KSet &t, uint64_t key) {
+    const uint64_t h = fmix64(key);
+    const uint64_t base = (uint64_t)part_of(h, t.P) * t.nbp;
+    uint64_t b = sub_of(h, t.nbp);
+    for (uint64_t probe = 0; probe < t.nbp; probe++) {
         uint64_t s[4];
-        ld_bucket64(table + 4 * b, s);
+        ld_bucket64(t.slots + 4 * (base + b), s);
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             if (s[i] == key) return true;
             if (s[i] == kEmpty) return false;
         }
-        b = (b + 1 == nb) ? 0 : b + 1;
+        b = (b + 1 == t.nbp) ? 0 : b + 1;
     }
     return false;
 }

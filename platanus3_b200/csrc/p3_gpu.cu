@@ -476,8 +476,7 @@ solid_kernel(const uint32_t *__restrict__ good21, uint64_t n_words, int k, uint3
 template <bool HAS_MASK>
 __global__ void __launch_bounds__(256)
 makebf_kernel(const uint64_t *__restrict__ packed, const uint32_t *__restrict__ nmask,
-              const uint32_t *__restrict__ solid, uint64_t n_words, int k, uint64_t *set, uint64_t nbs,
-              Stats *st) {
+              const uint32_t *__restrict__ solid, uint64_t n_words, int k, KSet set, Stats *st) {
     uint64_t stride = gridDim.x * (uint64_t)blockDim.x;
     bool full = false;
     for (uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < n_words; w += stride) {
@@ -491,8 +490,97 @@ makebf_kernel(const uint64_t *__restrict__ packed, const uint32_t *__restrict__ 
             s &= ~(0x80000000u >> o);
             uint64_t x = window(hi, lo, o);
             uint64_t m2 = HAS_MASK ? window(mhi, mlo, o) : 0;
-            if (set_insert(set, nbs, canonical_from_window(x, m2, k)) < 0) full = true;
+            if (set_insert(set, canonical_from_window(x, m2, k)) < 0) full = true;
         }
+    }
+    if (full) atomicExch(&st->err_table_full, 1u);
+}
+
+// ---- binned de-duplication (default for large inputs) ---------------------------------------------------
+// The direct kernel above pays one DRAM-random set access per solid position (2.97 G at configs[1],
+// 33 G/s). Binned: K1 tile-sorts the canonical k-mers of the solid positions by SET partition (the
+// scatter21 machinery, 8-byte records, fixed-capacity bins: partitions are hash-uniform), K2 sweeps
+// the bins with the work-counter hand-out of insert_bins so that the whole grid probes one ~24 MB
+// partition at a time out of L2. 95 % of the probes are plain hits (load + compare, no atomic).
+template <bool HAS_MASK>
+__global__ void __launch_bounds__(kScatterThreads)
+scatter_kmer_kernel(const uint64_t *__restrict__ packed, const uint32_t *__restrict__ nmask,
+                    const uint32_t *__restrict__ solid, uint64_t n_words, int k, uint32_t P,
+                    unsigned long long *cursor, uint64_t *__restrict__ bins, uint64_t cap) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ScatterSmem &sm = *reinterpret_cast<ScatterSmem *>(smem_raw);
+    const int tid = threadIdx.x;
+    const int wt = tid >> 1;            // word of the tile
+    const int o0 = (tid & 1) * 16;      // first offset this thread handles
+    const uint64_t n_tiles = (n_words + kTileWords - 1) / kTileWords;
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (uint32_t i = tid; i < P; i += kScatterThreads) sm.hist[i] = 0;
+        __syncthreads();
+        const uint64_t w = tile * kTileWords + wt;
+        uint64_t hi = 0, lo = 0, mhi = 0, mlo = 0;
+        uint32_t s = 0;
+        if (w < n_words) {
+            s = __ldg(solid + w);
+            if (s) {
+                hi = __ldg(packed + w); lo = __ldg(packed + w + 1);
+                if (HAS_MASK) { mhi = spread32(__ldg(nmask + w)); mlo = spread32(__ldg(nmask + w + 1)); }
+            }
+        }
+        uint64_t key[16];
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+            const int o = o0 + q;
+            key[q] = kEmpty;
+            if (s & (0x80000000u >> o)) {
+                key[q] = canonical_from_window(window(hi, lo, o), HAS_MASK ? window(mhi, mlo, o) : 0, k);
+                sm.rank[o][wt] = (uint16_t)atomicAdd(&sm.hist[kset_part(key[q], P)], 1u);
+            }
+        }
+        __syncthreads();
+        tile_scan_and_claim<kScatterThreads>(sm, P, cursor, tid);
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+            const int o = o0 + q;
+            if (s & (0x80000000u >> o)) {
+                uint32_t pt = kset_part(key[q], P);
+                uint32_t idx = sm.offs[pt] + sm.rank[o][wt];
+                sm.key[idx] = key[q];
+                sm.part[idx] = (uint16_t)pt;
+            }
+        }
+        __syncthreads();
+        const uint32_t total = sm.total;
+        for (uint32_t i = tid; i < total; i += kScatterThreads) {
+            uint32_t pt = sm.part[i];
+            unsigned long long dst = sm.gbase[pt] + (i - sm.offs[pt]);
+            if (dst < (uint64_t)(pt + 1) * cap) bins[dst] = sm.key[i];
+        }
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(256)
+set_sweep_kernel(const uint64_t *__restrict__ bins, uint64_t n, uint64_t cap, const unsigned long long *__restrict__ bin_end,
+                 KSet set, Stats *st) {
+    __shared__ unsigned long long s_base;
+    bool full = false;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_base = atomicAdd(&st->work, (unsigned long long)kSweepChunk);
+        __syncthreads();
+        const uint64_t cbase = s_base;
+        if (cbase >= n) break;
+        const uint64_t lim = min((uint64_t)__ldg(bin_end + cbase / cap), n);
+        if (cbase >= lim) continue;
+        uint64_t rec[kSweepPer];
+#pragma unroll
+        for (int it = 0; it < kSweepPer; it++) {
+            uint64_t i = cbase + it * 256 + threadIdx.x;
+            rec[it] = i < lim ? __ldcs(bins + i) : kEmpty;
+        }
+#pragma unroll
+        for (int it = 0; it < kSweepPer; it++)
+            if (rec[it] != kEmpty && set_insert(set, rec[it]) < 0) full = true;
     }
     if (full) atomicExch(&st->err_table_full, 1u);
 }
@@ -576,8 +664,8 @@ __global__ void seeds_kernel(const uint64_t *__restrict__ off, uint64_t n_reads,
 // possiblyContains is certainly true for it and its num_hashes probes are skipped; only
 // non-members (which mostly fail after a few probes) walk the filter.
 __global__ void __launch_bounds__(256, 8)   // 32 registers: the kernel lives on occupancy (34 registers cost 40 %: 97 -> 135 ms)
-adjacency_kernel(const uint64_t *__restrict__ kmers, uint64_t n, int k, Bloom bf, const uint64_t *__restrict__ set,
-                 uint64_t nbs, const uint64_t *__restrict__ set_b, uint64_t nbs_b, uint8_t *__restrict__ adj, Stats *st) {
+adjacency_kernel(const uint64_t *__restrict__ kmers, uint64_t n, int k, Bloom bf, KSet set, KSet set_b,
+                 uint8_t *__restrict__ adj, Stats *st) {
     const int lane = threadIdx.x & 31;
     const int d = lane & 7, g = lane >> 3;
     uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
@@ -593,7 +681,7 @@ adjacency_kernel(const uint64_t *__restrict__ kmers, uint64_t n, int k, Bloom bf
             // set_b (multi-GPU): the rank's locally seen solid k-mers, which their owners added. It holds
             // nearly every solid k-mer (each rank samples the whole genome), so it is asked INSTEAD of the
             // owned set: the rare owned-but-not-seen member just walks its num_hashes probes.
-            rec = (set_b ? set_contains(set_b, nbs_b, c) : (set && set_contains(set, nbs, c))) || bloom_query(bf, c);
+            rec = (set_b.slots ? set_contains(set_b, c) : (set.slots && set_contains(set, c))) || bloom_query(bf, c);
         }
         unsigned m = __ballot_sync(0xffffffffu, rec);
         if (d == 0 && i < n) {
@@ -614,7 +702,7 @@ adjacency_kernel(const uint64_t *__restrict__ kmers, uint64_t n, int k, Bloom bf
 // every CheckDirections it can possibly ask, with the reference's false positives included.
 __global__ void __launch_bounds__(256)
 closure_kernel(uint64_t *list, const uint8_t *__restrict__ adj, uint64_t lo, uint64_t hi, int k,
-               uint64_t *set, uint64_t nbs, uint64_t list_cap, Stats *st) {
+               KSet set, uint64_t list_cap, Stats *st) {
     __shared__ unsigned s_wtot[8];
     __shared__ unsigned long long s_base;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -633,7 +721,7 @@ closure_kernel(uint64_t *list, const uint8_t *__restrict__ adj, uint64_t lo, uin
                 uint64_t nb = neighbour(km, d, k);
                 uint64_t rc = revcomp(nb, k);
                 uint64_t c = nb <= rc ? nb : rc;
-                int ins = set_insert(set, nbs, c);
+                int ins = set_insert(set, c);
                 if (ins > 0) fresh[mine++] = c;
                 else if (ins < 0) atomicExch(&st->err_table_full, 1u);
             }
@@ -656,13 +744,13 @@ closure_kernel(uint64_t *list, const uint8_t *__restrict__ adj, uint64_t lo, uin
 }
 
 // walk roots (seed k-mers, oriented): make sure their canonical form has a table entry
-__global__ void roots_kernel(const uint64_t *__restrict__ roots, uint64_t n, int k, uint64_t *set, uint64_t nbs,
+__global__ void roots_kernel(const uint64_t *__restrict__ roots, uint64_t n, int k, KSet set,
                              uint64_t *list, uint64_t list_cap, Stats *st) {
     uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint64_t km = roots[i], rc = revcomp(km, k);
     uint64_t c = km <= rc ? km : rc;
-    int ins = set_insert(set, nbs, c);
+    int ins = set_insert(set, c);
     if (ins > 0) {
         unsigned long long j = atomicAdd(&st->n_distinct_solid, 1ULL);
         if (j < list_cap) list[j] = c;
@@ -753,9 +841,12 @@ struct p3_ctx {
     // make_bf
     uint32_t *d_good21 = nullptr, *d_solid = nullptr;
     uint32_t *d_proven2 = nullptr; uint64_t cap_proven = 0;
-    uint64_t *d_set = nullptr; uint64_t nbs = 0;
+    uint64_t *d_set = nullptr; uint64_t nbs = 0; uint32_t set_parts = 1;   // nbs = total buckets = set_parts * buckets per partition
     bool set_valid = false;   // d_set holds a subset of what the current filter contains
-    const uint64_t *d_set_b = nullptr; uint64_t nbs_b = 0;   // multi-GPU: second (locally seen) solid set, not owned here
+    const uint64_t *d_set_b = nullptr; uint64_t nbs_b = 0; uint32_t parts_b = 1;   // multi-GPU: second (locally seen) solid set, not owned here
+    KSet kset() const { KSet t; t.slots = d_set; t.P = set_parts ? set_parts : 1; t.nbp = nbs / t.P; return t; }
+    KSet kset_b() const { KSet t; t.slots = const_cast<uint64_t *>(d_set_b); t.P = parts_b ? parts_b : 1; t.nbp = nbs_b / t.P; return t; }
+    static KSet no_set() { KSet t; t.slots = nullptr; t.P = 1; t.nbp = 0; return t; }
     uint64_t *d_list = nullptr; uint64_t list_cap = 0;
     uint32_t *d_bloom = nullptr; uint64_t bloom_words = 0;
     int64_t *d_seed = nullptr;
@@ -960,6 +1051,8 @@ static int scatter_attrs() {
     CU(cudaFuncSetAttribute(scatter21_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz));
     CU(cudaFuncSetAttribute(scatter21_kernel<true, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz));
     CU(cudaFuncSetAttribute(scatter21_kernel<false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz));
+    CU(cudaFuncSetAttribute(scatter_kmer_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz));
+    CU(cudaFuncSetAttribute(scatter_kmer_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz));
     CU(cudaFuncSetAttribute(scatter_rec_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz));
     CU(cudaFuncSetAttribute(scatter_rec_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz));
     CU(cudaFuncSetAttribute(scatter_rec_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz));
@@ -1182,8 +1275,17 @@ static int alloc_bloom(p3_ctx *c, uint32_t k, uint64_t filter_size, uint32_t num
 // distinct canonical k-mers of the solid positions -> c->d_set / c->d_list (grows on overflow);
 // leaves n_distinct_solid in h_stats
 static int dedupe_solid_positions(p3_ctx *c, uint32_t k, uint64_t solid_slots) {
+    int rc0 = scatter_attrs();
+    if (rc0) return rc0;
     for (int attempt = 0;; attempt++) {
-        uint64_t nbs = (solid_slots + 3) / 4;
+        // partitions of ~24 MB (one stays L2 resident under the binned sweep)
+        uint64_t buckets = (solid_slots + 3) / 4;
+        uint64_t want = (buckets * 32 + (24ull << 20) - 1) / (24ull << 20);
+        if (const char *e = getenv("P3_SET_PARTS")) want = strtoull(e, nullptr, 10);
+        uint32_t P = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(want, 1), kMaxParts);
+        uint64_t nbp = std::max<uint64_t>((buckets + P - 1) / P, 1);
+        if (nbp >= (1ull << 32)) return fail(P3_ERR_ARG, "solid k-mer set partition too large");
+        uint64_t nbs = nbp * P;
         if (!c->d_set || c->nbs != nbs) {
             dfree(c->d_set); dfree(c->d_list);
             if (cudaMalloc(&c->d_set, nbs * 32) != cudaSuccess || cudaMalloc(&c->d_list, nbs * 32) != cudaSuccess) {
@@ -1192,15 +1294,54 @@ static int dedupe_solid_positions(p3_ctx *c, uint32_t k, uint64_t solid_slots) {
             }
             c->nbs = nbs; c->list_cap = nbs * 4;
         }
+        c->set_parts = P;
         CU(cudaMemsetAsync(c->d_set, 0xFF, nbs * 32, c->stream));
         CU(cudaMemsetAsync(&c->d_stats->n_distinct_solid, 0, sizeof(unsigned long long), c->stream));
         CU(cudaMemsetAsync(&c->d_stats->err_table_full, 0, sizeof(unsigned), c->stream));
-        if (c->d_nmask)
-            makebf_kernel<true><<<c->grid(), 256, 0, c->stream>>>(c->d_packed, c->d_nmask, c->d_solid, c->n_words, (int)k, c->d_set, nbs, c->d_stats);
-        else
-            makebf_kernel<false><<<c->grid(), 256, 0, c->stream>>>(c->d_packed, nullptr, c->d_solid, c->n_words, (int)k, c->d_set, nbs, c->d_stats);
+        // binned path: needs room for n_adds 8-byte records (+5 %) in the idle count-stage bins
+        const uint64_t n_occ = c->h_stats.n_adds;
+        bool binned = false;
+        const char *force = getenv("P3_DEDUPE_BINNED");
+        if (force ? atoi(force) != 0 : (P >= 2 && n_occ >= (1u << 22))) {
+            uint64_t cap = (uint64_t)((double)n_occ / (double)P * 1.05) + 8192;
+            cap = (cap + kSweepChunk - 1) / kSweepChunk * kSweepChunk;
+            const uint64_t need = sizeof(uint64_t) * cap * P;
+            if (!c->d_ghist) {
+                CU(cudaMalloc(&c->d_ghist, sizeof(unsigned long long) * (kMaxParts + 1)));
+                CU(cudaMalloc(&c->d_cursor, sizeof(unsigned long long) * (kMaxParts + 1)));
+            }
+            size_t fr = 0, tot = 0;
+            CU(cudaMemGetInfo(&fr, &tot));
+            if (c->cap_bkeys >= need || need < (uint64_t)(0.5 * (double)fr)) {
+                CU(ensure(c->d_bkeys, c->cap_bkeys, need));
+                init_cursors_kernel<<<1, 256, 0, c->stream>>>(c->d_cursor, P, cap);
+                unsigned sblocks = (unsigned)std::min<uint64_t>(std::max<uint64_t>((c->n_words + kTileWords - 1) / kTileWords, 1), (uint64_t)c->n_sm * 3);
+                if (c->d_nmask) scatter_kmer_kernel<true><<<sblocks, kScatterThreads, sizeof(ScatterSmem), c->stream>>>(c->d_packed, c->d_nmask, c->d_solid, c->n_words, (int)k, P, c->d_cursor, c->d_bkeys, cap);
+                else scatter_kmer_kernel<false><<<sblocks, kScatterThreads, sizeof(ScatterSmem), c->stream>>>(c->d_packed, nullptr, c->d_solid, c->n_words, (int)k, P, c->d_cursor, c->d_bkeys, cap);
+                c->launches += 2;
+                CU(cudaGetLastError());
+                std::vector<unsigned long long> h_cur(P);
+                CU(cudaMemcpyAsync(h_cur.data(), c->d_cursor, sizeof(unsigned long long) * P, cudaMemcpyDeviceToHost, c->stream));
+                CU(cudaStreamSynchronize(c->stream));
+                binned = true;
+                for (uint32_t q = 0; q < P; q++)
+                    if (h_cur[q] - (unsigned long long)q * cap > cap) { binned = false; break; }   // a heavy-hitter partition: direct path
+                if (binned) {
+                    CU(cudaMemsetAsync(&c->d_stats->work, 0, sizeof(unsigned long long), c->stream));
+                    set_sweep_kernel<<<c->grid(), 256, 0, c->stream>>>(c->d_bkeys, (uint64_t)P * cap, cap, c->d_cursor, c->kset(), c->d_stats);
+                    c->launches++;
+                }
+            }
+        }
+        if (!binned) {
+            if (c->d_nmask)
+                makebf_kernel<true><<<c->grid(), 256, 0, c->stream>>>(c->d_packed, c->d_nmask, c->d_solid, c->n_words, (int)k, c->kset(), c->d_stats);
+            else
+                makebf_kernel<false><<<c->grid(), 256, 0, c->stream>>>(c->d_packed, nullptr, c->d_solid, c->n_words, (int)k, c->kset(), c->d_stats);
+            c->launches++;
+        }
         compact_set_kernel<<<c->grid(), 256, 0, c->stream>>>(c->d_set, nbs * 4, c->d_list, c->list_cap, c->d_stats);
-        c->launches += 2;
+        c->launches++;
         CU(cudaGetLastError());
         int rc = pull_stats(c);
         if (rc) return rc;
@@ -1282,7 +1423,7 @@ int p3_make_bf(p3_ctx *c, uint32_t k, uint64_t filter_size, uint32_t num_hashes,
         CU(cudaEventElapsedTime(&c->ms[2], c->ev[4], c->ev[5]));
         CU(cudaEventElapsedTime(&c->ms[3], c->ev[5], c->ev[6]));
         c->have_bf = true; c->have_solid = true; c->have_adj = false; c->set_valid = false;
-        c->d_set_b = nullptr; c->nbs_b = 0;
+        c->d_set_b = nullptr; c->nbs_b = 0; c->parts_b = 1;
         return P3_OK;
     }
     // B2a: solid plane + n_adds; number of distinct good 21-mers sizes the solid set
@@ -1317,7 +1458,7 @@ int p3_make_bf(p3_ctx *c, uint32_t k, uint64_t filter_size, uint32_t num_hashes,
     CU(cudaEventElapsedTime(&c->ms[2], c->ev[4], c->ev[5]));
     CU(cudaEventElapsedTime(&c->ms[3], c->ev[5], c->ev[6]));
     c->have_bf = true; c->have_solid = true; c->have_adj = false; c->set_valid = true;
-    c->d_set_b = nullptr; c->nbs_b = 0;
+    c->d_set_b = nullptr; c->nbs_b = 0; c->parts_b = 1;
     return P3_OK;
 }
 
@@ -1437,12 +1578,12 @@ int p3_dbg_adjacency(p3_ctx *c) {
         int rcl = adjacency_long(c, long_words(c), n, c->d_adj, c->d_stats);
         if (rcl) return rcl;
     } else if (n) {
-        const uint64_t *sa = c->set_valid ? c->d_set : nullptr, *sb = c->set_valid ? c->d_set_b : nullptr;
+        KSet sa = c->set_valid ? c->kset() : p3_ctx::no_set(), sb = (c->set_valid && c->d_set_b) ? c->kset_b() : p3_ctx::no_set();
         if (const char *e = getenv("P3_ADJ_SET")) {   // experiment knob: which shortcut set the neighbour queries may use
-            if (!strcmp(e, "owned")) sb = nullptr;
-            else if (!strcmp(e, "none")) sa = sb = nullptr;
+            if (!strcmp(e, "owned")) sb = p3_ctx::no_set();
+            else if (!strcmp(e, "none")) sa = sb = p3_ctx::no_set();
         }
-        adjacency_kernel<<<c->grid(), 256, 0, c->stream>>>(c->d_list, n, (int)c->k, c->bloom(), sa, c->nbs, sb, c->nbs_b, c->d_adj, c->d_stats);
+        adjacency_kernel<<<c->grid(), 256, 0, c->stream>>>(c->d_list, n, (int)c->k, c->bloom(), sa, sb, c->d_adj, c->d_stats);
         c->launches++;
         CU(cudaGetLastError());
     }
@@ -1468,7 +1609,7 @@ int p3_dbg_close(p3_ctx *c, const uint64_t *h_roots, uint64_t n_roots, uint64_t 
         if (to <= from) return P3_OK;
         uint64_t nn = to - from, warps = (nn + 3) / 4;
         unsigned blocks = (unsigned)std::min<uint64_t>((warps + 7) / 8, (uint64_t)c->grid());
-        adjacency_kernel<<<blocks, 256, 0, c->stream>>>(c->d_list + from, nn, (int)c->k, c->bloom(), nullptr, 0, nullptr, 0, c->d_adj + from, nullptr);
+        adjacency_kernel<<<blocks, 256, 0, c->stream>>>(c->d_list + from, nn, (int)c->k, c->bloom(), p3_ctx::no_set(), p3_ctx::no_set(), c->d_adj + from, nullptr);
         c->launches++;
         CU(cudaGetLastError());
         return P3_OK;
@@ -1483,7 +1624,7 @@ int p3_dbg_close(p3_ctx *c, const uint64_t *h_roots, uint64_t n_roots, uint64_t 
         uint64_t *dr = nullptr;
         CU(cudaMalloc(&dr, sizeof(uint64_t) * n_roots));
         CU(cudaMemcpyAsync(dr, h_roots, sizeof(uint64_t) * n_roots, cudaMemcpyHostToDevice, c->stream));
-        roots_kernel<<<(unsigned)((n_roots + 255) / 256), 256, 0, c->stream>>>(dr, n_roots, (int)c->k, c->d_set, c->nbs, c->d_list, c->list_cap, c->d_stats);
+        roots_kernel<<<(unsigned)((n_roots + 255) / 256), 256, 0, c->stream>>>(dr, n_roots, (int)c->k, c->kset(), c->d_list, c->list_cap, c->d_stats);
         c->launches++;
         int rc = pull_stats(c);
         cudaFree(dr);
@@ -1496,7 +1637,7 @@ int p3_dbg_close(p3_ctx *c, const uint64_t *h_roots, uint64_t n_roots, uint64_t 
     uint64_t lo = c->closed ? c->n_closed : 0;
     for (int round = 0; lo < hi; round++) {
         if (round > 200) return fail(P3_ERR_TABLE_FULL, "p3_dbg_close: no fixed point (filter saturated: the reference walk would not terminate either)");
-        closure_kernel<<<c->grid(), 256, 0, c->stream>>>(c->d_list, c->d_adj, lo, hi, (int)c->k, c->d_set, c->nbs, c->list_cap, c->d_stats);
+        closure_kernel<<<c->grid(), 256, 0, c->stream>>>(c->d_list, c->d_adj, lo, hi, (int)c->k, c->kset(), c->list_cap, c->d_stats);
         c->launches++;
         CU(cudaGetLastError());
         int rc = pull_stats(c);
@@ -1547,7 +1688,7 @@ int p3_check_directions(p3_ctx *c, const uint64_t *h_kmers, uint64_t n, uint8_t 
     CU(cudaMalloc(&dout, n));
     uint64_t warps = (n + 3) / 4;
     unsigned blocks = (unsigned)std::min<uint64_t>((warps + 7) / 8, (uint64_t)c->grid());
-    adjacency_kernel<<<blocks, 256, 0, c->stream>>>(dk, n, (int)c->k, c->bloom(), c->set_valid ? c->d_set : nullptr, c->nbs, c->set_valid ? c->d_set_b : nullptr, c->nbs_b, dout, nullptr);
+    adjacency_kernel<<<blocks, 256, 0, c->stream>>>(dk, n, (int)c->k, c->bloom(), c->set_valid ? c->kset() : p3_ctx::no_set(), (c->set_valid && c->d_set_b) ? c->kset_b() : p3_ctx::no_set(), dout, nullptr);
     c->launches++;
     CU(cudaMemcpyAsync(h_mask, dout, n, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));

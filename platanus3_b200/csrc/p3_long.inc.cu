@@ -332,6 +332,7 @@ static int make_bf_long(p3_ctx *c, uint32_t k, uint64_t solid_slots) {
             }
             c->nbs = nbs; c->list_cap = nbs * 4;
         }
+        c->set_parts = 1;
         CU(cudaMemsetAsync(c->d_set, 0xFF, nbs * 32, c->stream));
         CU(cudaMemsetAsync(&c->d_stats->n_distinct_solid, 0, sizeof(unsigned long long), c->stream));
         CU(cudaMemsetAsync(&c->d_stats->err_table_full, 0, sizeof(unsigned), c->stream));

@@ -80,11 +80,11 @@ cand_check_peer_kernel(const uint64_t *__restrict__ slots, const uint64_t *__res
     }
 }
 
-__global__ void set_insert_list_kernel(const uint64_t *__restrict__ kmers, uint64_t n, uint64_t *set, uint64_t nbs, Stats *st) {
+__global__ void set_insert_list_kernel(const uint64_t *__restrict__ kmers, uint64_t n, KSet set, Stats *st) {
     uint64_t stride = gridDim.x * (uint64_t)blockDim.x;
     bool full = false;
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += stride)
-        if (set_insert(set, nbs, __ldcs(kmers + i)) < 0) full = true;
+        if (set_insert(set, __ldcs(kmers + i)) < 0) full = true;
     if (full) atomicExch(&st->err_table_full, 1u);
 }
 
@@ -95,7 +95,7 @@ static inline uint32_t owner_of_host(uint64_t key, uint32_t n) {
 
 struct MgState {   // extra per-context state of the multi-GPU path
     uint64_t *d_sing = nullptr, *d_sing2 = nullptr; uint64_t cap_sing = 0, cap_sing2 = 0;
-    uint64_t *d_set2 = nullptr, *d_list2 = nullptr; uint64_t nbs2 = 0;
+    uint64_t *d_set2 = nullptr, *d_list2 = nullptr; uint64_t nbs2 = 0; uint32_t parts2 = 1;
     uint64_t rec_cap = 0;
     uint64_t n_local = 0;
     // receive buffers of the fused bin + exchange (peers store into them over NVLink); plain
@@ -450,11 +450,11 @@ int p3_mg_solid_local(p3_ctx *c, uint32_t k, uint64_t solid_slots, uint64_t *n_a
     if (!c || !c->d_good21) return fail(P3_ERR_STATE, "p3_mg_solid_local: run p3_mg_cover_begin first");
     if (k < P3_MIN_K || k > 32) return fail(P3_ERR_ARG, "multi-GPU path: k outside [21,32] is not supported yet");
     CU(cudaSetDevice(c->device));
-    c->k = k; c->set_valid = false; c->d_set_b = nullptr; c->nbs_b = 0;
+    c->k = k; c->set_valid = false; c->d_set_b = nullptr; c->nbs_b = 0; c->parts_b = 1;
     {   // give the local-set buffers of the previous run back to their role so that they are reused
         MgState &m = g_mg[c];
         if (m.swapped) {
-            std::swap(c->d_set, m.d_set2); std::swap(c->d_list, m.d_list2); std::swap(c->nbs, m.nbs2);
+            std::swap(c->d_set, m.d_set2); std::swap(c->d_list, m.d_list2); std::swap(c->nbs, m.nbs2); std::swap(c->set_parts, m.parts2);
             c->list_cap = c->nbs * 4;
             m.swapped = false;
         }
@@ -514,6 +514,7 @@ int p3_mg_owned_begin(p3_ctx *c, uint64_t owned_slots) {
         }
         m.nbs2 = nbs;
     }
+    m.parts2 = 1;
     CU(cudaMemsetAsync(m.d_set2, 0xFF, nbs * 32, c->stream));
     CU(cudaMemsetAsync(&c->d_stats->err_table_full, 0, sizeof(unsigned), c->stream));
     return P3_OK;
@@ -523,7 +524,8 @@ int p3_mg_owned_insert(p3_ctx *c, const uint64_t *d_kmers, uint64_t n) {
     if (n == 0) return P3_OK;
     CU(cudaSetDevice(c->device));
     MgState &m = g_mg[c];
-    set_insert_list_kernel<<<c->grid(), 256, 0, c->stream>>>(d_kmers, n, m.d_set2, m.nbs2, c->d_stats);
+    KSet owned; owned.slots = m.d_set2; owned.P = 1; owned.nbp = m.nbs2;
+    set_insert_list_kernel<<<c->grid(), 256, 0, c->stream>>>(d_kmers, n, owned, c->d_stats);
     c->launches++;
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(c->stream));
@@ -540,7 +542,7 @@ static int owned_finish(p3_ctx *c, uint32_t k, uint64_t filter_size, uint32_t nu
     if (!m.d_set2) return fail(P3_ERR_STATE, "p3_mg_owned_end: run p3_mg_owned_begin first");
     int rc = alloc_bloom(c, k, filter_size, num_hashes, min_words);
     if (rc) return rc;
-    std::swap(c->d_set, m.d_set2); std::swap(c->d_list, m.d_list2); std::swap(c->nbs, m.nbs2);
+    std::swap(c->d_set, m.d_set2); std::swap(c->d_list, m.d_list2); std::swap(c->nbs, m.nbs2); std::swap(c->set_parts, m.parts2);
     c->list_cap = c->nbs * 4;
     m.swapped = true;
     CU(cudaMemsetAsync(&c->d_stats->n_distinct_solid, 0, sizeof(unsigned long long), c->stream));
@@ -556,7 +558,7 @@ static int owned_finish(p3_ctx *c, uint32_t k, uint64_t filter_size, uint32_t nu
     }
     CU(cudaStreamSynchronize(c->stream));
     c->have_bf = true; c->have_solid = true; c->have_adj = false; c->set_valid = true;
-    c->d_set_b = m.d_set2; c->nbs_b = m.nbs2;   // after the swap: the locally seen solid k-mers
+    c->d_set_b = m.d_set2; c->nbs_b = m.nbs2; c->parts_b = m.parts2;   // after the swap: the locally seen solid k-mers
     if (n_owned) *n_owned = c->h_stats.n_distinct_solid;
     return P3_OK;
 }

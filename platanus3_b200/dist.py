@@ -434,7 +434,9 @@ def run_hot_path(ctxs, comm, k, filter_size, num_hashes, table_slots, solid_slot
         force = os.environ.get("P3_BLOOM_BINNED")
         binned = (force != "0") if force is not None else (nseg >= 2 and sum(n_all) * num_hashes >= (1 << 22))
     if binned:
-        cap_src = [int(n * num_hashes / nseg * 1.05) + 65536 for n in n_all]    # hashed indices are uniform
+        # hashed indices are uniform: a full segment gets seg_bits / filter_size of a source's indices
+        share = min(1.0, seg_bits / filter_size)
+        cap_src = [int(n * num_hashes * share * 1.05) + 65536 for n in n_all]
         prefix = [sum(cap_src[:r]) for r in range(w)]
         tot_cap = sum(cap_src)
         ptr_rows = []

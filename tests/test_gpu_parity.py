@@ -69,6 +69,9 @@ def test_pipeline_small(ctx, oracle, k):
     {"P3_PARTS": "3", "P3_BIN_BUDGET_BYTES": "1"},            # one tile per chunk
     {"P3_BINNED_CLEARS": "1", "P3_BLOOM_SEG_BITS": "4096"},   # coverage-bit clears binned by plane segment
     {"P3_BINNED_CLEARS": "1", "P3_BLOOM_SEG_BITS": "1024", "P3_PARTS": "5"},
+    {"P3_DEDUPE_BINNED": "1", "P3_SET_PARTS": "7"},           # k-mer de-duplication binned by set partition
+    {"P3_DEDUPE_BINNED": "1", "P3_SET_PARTS": "1"},
+    {"P3_DEDUPE_BINNED": "0", "P3_SET_PARTS": "13"},          # direct de-duplication into a partitioned set
     {"P3_EXACT_BINS": "1"},                                    # histogram-sized bins instead of fixed-capacity ones
     {"P3_EXACT_BINS": "1", "P3_PARTS": "9", "P3_BIN_BUDGET_BYTES": "300000"},
 ])
@@ -94,6 +97,15 @@ def test_binned_bloom_adds(ctx, oracle, seg_bits, monkeypatch):
     _full_check(ctx, oracle, reads, 27, m=3 * seg_bits)
     _full_check(ctx, oracle, reads[:300], 31, m=1000003)
     _long_check(ctx, oracle, _dataset(78, genome=3000, cov=30, rl=150, err=0.003), 63)
+
+
+def test_binned_dedupe_overflow_falls_back(ctx, oracle, monkeypatch):
+    """a solid k-mer with very many occurrences overflows its set partition's bin: the direct path takes over"""
+    monkeypatch.setenv("P3_DEDUPE_BINNED", "1")
+    monkeypatch.setenv("P3_SET_PARTS", "64")
+    reads = [b"ACGTTGCA" * 40] * 4000 + _dataset(93, genome=5000, cov=12, rl=100, err=0.01)
+    _full_check(ctx, oracle, reads, 32, n_adj=300)
+    _full_check(ctx, oracle, reads, 25, m=30011, n_adj=300)
 
 
 def test_fixed_capacity_bins_overflow_falls_back(ctx, oracle, monkeypatch):
