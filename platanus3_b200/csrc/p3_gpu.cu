@@ -474,7 +474,7 @@ solid_kernel(const uint32_t *__restrict__ good21, uint64_t n_words, int k, uint3
 // the same canonical k-mer set identical bits, so each distinct k-mer is added once: the solid
 // set de-duplicates and its insertion winner does the num_hashes atomicOr's.
 template <bool HAS_MASK>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 8)   // 32 registers: DRAM-latency bound, lives on occupancy
 makebf_kernel(const uint64_t *__restrict__ packed, const uint32_t *__restrict__ nmask,
               const uint32_t *__restrict__ solid, uint64_t n_words, int k, KSet set, Stats *st) {
     uint64_t stride = gridDim.x * (uint64_t)blockDim.x;
@@ -559,7 +559,7 @@ scatter_kmer_kernel(const uint64_t *__restrict__ packed, const uint32_t *__restr
         __syncthreads();
     }
 }
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256)   // 41 registers; capping at 32 spills 250 bytes and costs 19 ms
 set_sweep_kernel(const uint64_t *__restrict__ bins, uint64_t n, uint64_t cap, const unsigned long long *__restrict__ bin_end,
                  KSet set, Stats *st) {
     __shared__ unsigned long long s_base;
@@ -1282,7 +1282,12 @@ static int dedupe_solid_positions(p3_ctx *c, uint32_t k, uint64_t solid_slots) {
         uint64_t buckets = (solid_slots + 3) / 4;
         uint64_t want = (buckets * 32 + (24ull << 20) - 1) / (24ull << 20);
         if (const char *e = getenv("P3_SET_PARTS")) want = strtoull(e, nullptr, 10);
+        // At most 96 partitions: the tile sort of 4096 positions needs runs of a few dozen records per
+        // partition to write coalesced (measured at configs[1]: 77 partitions 95 ms, 128 partitions 127 ms).
+        // A set too large for that (multi-GPU: every rank sees nearly all solid k-mers of the N-times larger
+        // genome) is left unpartitioned and filled directly: 135 ms binned vs 100 ms direct at 2 ranks.
         uint32_t P = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(want, 1), kMaxParts);
+        if (!getenv("P3_SET_PARTS") && P > 96) P = 1;
         uint64_t nbp = std::max<uint64_t>((buckets + P - 1) / P, 1);
         if (nbp >= (1ull << 32)) return fail(P3_ERR_ARG, "solid k-mer set partition too large");
         uint64_t nbs = nbp * P;
