@@ -8,7 +8,8 @@ set. At N=1 the workload is BASELINE.json configs[1]: 100 Mbp random genome, 50x
   value     k-mers/s with the 2-bit read staging already resident in HBM (p3_reads_attach)
   e2e       the same pass through p3_assemble_hot_path on pinned HOST staging buffers, with
             the H2D of the reads and the D2H of filter/seeds/k-mers/adjacency inside the timing
-  roofline  dominant kernel (count21): algorithmic bytes / CUDA-event time vs measured HBM peak
+  roofline  the count stage (scatter21 + insert_bins, the kernels that count the metric's k-mers):
+            algorithmic bytes / CUDA-event time vs the measured HBM copy peak
   cpu_baseline / --impl reference
             the unmodified reference (oracle/_ref/libp3ref.so; oracle port when absent) on a
             bounded, scaled-down sample of the same workload on the host cores
@@ -38,9 +39,9 @@ ERR = 0.01
 # staging in, one 8-byte table slot read and written back
 ALGO_BYTES_PER_KMER = 0.25 + 8 + 8
 # DRAM bytes of the count stage's kernels for ONE step of configs[1] on one B200, from
-# `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` (profiles/r01e_traffic_full_workload.csv):
-# hist21 1.88 + scatter21 60.66 + insert_bins 102.11 GB
-COUNT_STAGE_TRAFFIC_BYTES = 164.65e9
+# `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` (profiles/r01p3_traffic_full_workload.csv):
+# scatter21 4.90 + 55.02 GB, insert_bins 69.50 + 32.51 GB (the histogram pass is gone: fixed-capacity bins)
+COUNT_STAGE_TRAFFIC_BYTES = 161.93e9
 SAMPLE_GENOME = 200_000  # cpu_baseline / reference arm: same generator, 500x smaller genome
 
 
@@ -136,7 +137,9 @@ def run_reference(args):
         "vs_baseline": None, "dtype": "u64", "data": "synthetic",
         "config": workload_config(args.gpus),
         "dbg_edges_per_s": edges * args.steps / tot,
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample,
+                         "threads_note": "the reference's CountShortKmer (src/Load.cpp:105) and MakeBF (src/MakeBloomFilter.cpp:8) "
+                                         "are single-threaded whatever -t says; -t only feeds MakeDBG's walk, which is outside this path"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -289,6 +292,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--genome", type=int, default=GENOME, help="override genome size (debug only; invalidates the metric)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling only: skip the host-buffer leg (e2e is then null)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -386,15 +390,17 @@ def main():
     # e2e leg (its own context; the resident one is released first so both fit in HBM)
     ctx.close()
     ctx2 = _lib.Context(local, ctypes.c_void_p(stream.cuda_stream))
-    step_e2e()
     n_solid = 0
-    torch.cuda.synchronize()
-    e0.record(stream)
-    for _ in range(args.steps):
-        n_solid = step_e2e()
-    e1.record(stream)
-    torch.cuda.synchronize()
-    e2e_ms = e0.elapsed_time(e1)
+    e2e_ms = float("nan")
+    if not args.no_e2e:
+        step_e2e()
+        torch.cuda.synchronize()
+        e0.record(stream)
+        for _ in range(args.steps):
+            n_solid = step_e2e()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        e2e_ms = e0.elapsed_time(e1)
     h2d = h_packed.numel() * 8 + h_off.numel() * 8
     d2h = out_bits.numel() + out_seeds.numel() * 8 + n_solid * 9
 
@@ -413,12 +419,12 @@ def main():
                    "filter_size_bits": fs, "num_hashes": nh},
         "stage_ms": {kk: v / args.steps for kk, v in stage_acc.items()},
         "count_substage": {kk: v / args.steps for kk, v in sub_acc.items()},
-        "roofline": {"kernel": "count stage = hist21 + scatter21 + insert_bins (dominant: insert_bins_kernel)"
+        "roofline": {"kernel": "count stage = scatter21_kernel + insert_bins_kernel (dominant: insert_bins_kernel)"
                                if os.environ.get("P3_COUNT_MODE", "binned") != "direct" else "count21_kernel",
                      "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak,
                      "traffic": COUNT_STAGE_TRAFFIC_BYTES if (genome == GENOME and os.environ.get("P3_COUNT_MODE", "binned") != "direct") else None,
-                     "traffic_source": "profiles/r01e_traffic_full_workload.csv (ncu dram__bytes_read+write of the three kernels, one step)",
+                     "traffic_source": "profiles/r01p3_traffic_full_workload.csv (ncu dram__bytes_read+write of the two kernels, one step)",
                      "peak_source": peak_src,
                      "algorithmic_bytes_per_kmer": ALGO_BYTES_PER_KMER, "kernel_ms": k_ms},
         "count_mode": os.environ.get("P3_COUNT_MODE", "binned"),

@@ -348,7 +348,7 @@ def run_hot_path(ctxs, comm, k, filter_size, num_hashes, table_slots, solid_slot
     if peer and os.environ.get("P3_MG_COVER", "nccl") == "peer":
         # owners clear the bits of their count-1 keys directly in the source ranks' planes (NVLink RED.AND).
         # NOT the default: remote atomics are slow — equal to the all-to-all route at 2 GPUs (57 vs 60 ms)
-        # but 2168 ms instead of 74 ms at 8 GPUs (profiles/r02_summary.md)
+        # but 2168 ms instead of 74 ms at 8 GPUs (profiles/r01_summary.md)
         ptr_rows = []
         for c in ctxs:
             _check(L.p3_mg_cover_begin(c.h))
