@@ -9,8 +9,10 @@
  *
  * k-mer words: W = ceil(2k/64) little-endian uint64 words holding the same 2k-bit integer as
  * the reference's std::bitset<2k> (first base in the most significant 2 bits, A=0 C=1 G=2 T=3;
- * reference src/BitCalc.cpp:8-19). The device path supports 21 <= k <= 3001; the host walk
- * (p3_dbg_close, p3_assemble_file) is limited to k <= 32 (W = 1) in this build.
+ * reference src/BitCalc.cpp:8-19). The device path and the drop-in run (p3_assemble_file, the CLI)
+ * support 21 <= k <= 3001; the device-side closure p3_dbg_close, p3_node_coverage and the multi-GPU
+ * entry points are limited to k <= 32 (W = 1) in this build (for k > 32 the drop-in run closes the
+ * table from the host with p3_check_directions batches and counts node coverage on the host).
  *
  * 2-bit staging layout ("packed reads"): all reads back to back, 32 bases per uint64 word,
  * base j of the stream in word j/32 at bits [63-2(j%32)-1, 63-2(j%32)] (MSB first), zero
@@ -40,7 +42,7 @@ extern "C" {
 #define P3_COV_THRESHOLD 2  /* reference src/MakeBloomFilter.cpp:28 cov_threshold */
 #define P3_MIN_K 21
 #define P3_MAX_K 3001      /* device path: any k in [21,3001] (the reference's largest bitset) */
-#define P3_MAX_K_WALK 32   /* host unitig walk / p3_dbg_close / p3_assemble_file: single-word k-mers */
+#define P3_MAX_K_WALK 32   /* single-word k-mers: p3_dbg_close, p3_node_coverage, the uint64 fast path of the host walk */
 
 typedef struct p3_ctx p3_ctx;
 
@@ -249,6 +251,15 @@ int p3_node_coverage(p3_ctx *ctx, uint32_t k, const uint64_t *h_junctions, uint6
  * straights. */
 int p3_assemble_file(const char *read_path, uint32_t k, uint64_t m, int threads, int device,
                      const char *gfa_path, const char *log_path, uint64_t *stats);
+
+/* The host half of that run on its own: Load + MakeDBG (the reference's -t 1 order, src/DeBruijnGraph.cpp:94-297)
+ * + CountNodeCoverage (:394-449, counted on the host here) + PrintGraph (:452-544) over a CLOSED
+ * CheckDirections table from any source: n canonical k-mers (W words each) with one adjacency byte
+ * each, closed = every neighbour a byte reports is itself in the table; h_seeds = the ORIENTED seed
+ * k-mers (MakeBloomFilter.cpp:79-83). Needs no GPU. stats (optional, 3 values): junctions, joints,
+ * straights. */
+int p3_walk_table(const char *read_path, uint32_t k, const uint64_t *h_kmers, const uint8_t *h_adj, uint64_t n,
+                  const uint64_t *h_seeds, uint64_t n_seeds, const char *gfa_path, uint64_t *stats);
 
 /* device milliseconds of the last run of each stage (CUDA events on the context stream):
  * ms[0]=count21 ms[1]=coverage flags ms[2]=solid+bloom ms[3]=seeds ms[4]=adjacency */

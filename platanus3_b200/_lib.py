@@ -26,7 +26,7 @@ SYMBOLS = [
     "p3_mg_owned_end", "p3_mg_filter", "p3_bloom_seg_bits", "p3_mg_owned_list", "p3_mg_bloom_buffer", "p3_mg_bloom_bin",
     "p3_mg_bloom_apply", "p3_mg_bloom_direct",
     "p3_load_file", "p3_reads_free", "p3_reads_count", "p3_reads_all_bases", "p3_reads_total_bases",
-    "p3_reads_offsets", "p3_reads_packed", "p3_reads_nmask", "p3_reads_ascii", "p3_assemble_file", "p3_node_coverage",
+    "p3_reads_offsets", "p3_reads_packed", "p3_reads_nmask", "p3_reads_ascii", "p3_assemble_file", "p3_walk_table", "p3_node_coverage",
     "p3_assemble_hot_path", "p3_stage_ms", "p3_count_substage_ms", "p3_launch_count", "p3_bf_params",
 ]
 
@@ -124,6 +124,7 @@ def lib():
             getattr(L, nm).argtypes = [vp]
         L.p3_node_coverage.argtypes = [vp, u32, vp, u64, vp, u64, vp, vp]
         L.p3_assemble_file.argtypes = [C.c_char_p, u32, u64, i32, i32, C.c_char_p, C.c_char_p, C.POINTER(u64)]
+        L.p3_walk_table.argtypes = [C.c_char_p, u32, vp, vp, u64, vp, u64, C.c_char_p, C.POINTER(u64)]
         L.p3_stage_ms.argtypes = [vp, C.POINTER(C.c_float)]
         L.p3_count_substage_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(u32), C.POINTER(u64)]
         L.p3_launch_count.restype = u64
@@ -184,6 +185,18 @@ def load_file(path, k):
         return dict(seq=seq, off=off, all_bases=L.p3_reads_all_bases(h), packed=packed, nmask=nmask)
     finally:
         L.p3_reads_free(h)
+
+
+def walk_table(path, k, kmers, adj, seeds, gfa_path=None):
+    """host half of the drop-in over a closed CheckDirections table (no GPU needed)"""
+    kmers = np.ascontiguousarray(kmers, np.uint64)
+    adj = np.ascontiguousarray(adj, np.uint8)
+    seeds = np.ascontiguousarray(seeds, np.uint64)
+    W = (2 * k + 63) // 64
+    st = (C.c_uint64 * 3)()
+    check(lib().p3_walk_table(path.encode(), k, _ptr(kmers), _ptr(adj), len(adj), _ptr(seeds), seeds.size // W,
+                              gfa_path.encode() if gfa_path else None, st))
+    return dict(junctions=int(st[0]), joints=int(st[1]), straights=int(st[2]))
 
 
 def assemble_file(path, k, m=0, threads=1, device=0, gfa_path=None, log_path=None):

@@ -135,7 +135,10 @@ const char *p3_reads_ascii(const p3_reads *r) { return r->seq.data(); }
 }  // extern "C"
 
 // ---------------------------------------------------------------------------------------------
-// unitig walk over the exported adjacency table (k <= 32: one word per k-mer)
+// unitig walk over the exported adjacency table. One template, two k-mer representations:
+//   U64Ops  k <= 32: one 64-bit word per k-mer (first base in the top bits of the 2k-bit value)
+//   StrOps  k >  32: the k-mer as its ACGT string (what GetStringKmer prints); the reference's
+//           std::bitset<2k> order == the string order, so "canonical" and the seed order carry over
 // ---------------------------------------------------------------------------------------------
 namespace {
 
@@ -149,6 +152,93 @@ inline uint8_t rev8(uint8_t b) {
     b = (uint8_t)((b & 0xAA) >> 1 | (b & 0x55) << 1);
     return b;
 }
+inline int fcode(unsigned char c) { return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : 0; }
+// base_to_bit[trans_base[c]] of the reference: complement code, 0 for anything that is not ACGT
+inline int rcode(unsigned char c) { return c == 'A' ? 3 : c == 'C' ? 2 : c == 'G' ? 1 : 0; }
+
+struct U64Ops {
+    using K = uint64_t;
+    struct Hash { size_t operator()(uint64_t v) const { return (size_t)fmix64(v); } };
+    int k; uint64_t kmask;
+    explicit U64Ops(int k_) : k(k_), kmask(k_ >= 32 ? ~0ULL : ((1ULL << (2 * k_)) - 1)) {}
+    K revcomp(K v) const {   // GetComplementKmer, reference src/BitCalc.cpp:36-45
+        uint64_t x = ~v;
+        x = ((x >> 2) & 0x3333333333333333ULL) | ((x & 0x3333333333333333ULL) << 2);
+        x = ((x >> 4) & 0x0F0F0F0F0F0F0F0FULL) | ((x & 0x0F0F0F0F0F0F0F0FULL) << 4);
+        x = __builtin_bswap64(x);
+        return x >> (64 - 2 * k);
+    }
+    std::string str(K v) const {   // GetStringKmer, reference src/BitCalc.cpp:57-65
+        std::string s(k, 'A');
+        for (int i = 0; i < k; i++) s[i] = "ACGT"[(v >> (2 * (k - 1 - i))) & 3];
+        return s;
+    }
+    K neighbour(K km, int d) const {   // reference src/DeBruijnGraph.cpp:327-339
+        return d < 4 ? ((km >> 2) | ((uint64_t)d << (2 * k - 2))) : (((km << 2) | (uint64_t)(d - 4)) & kmask);
+    }
+    int first(K v) const { return (int)((v >> (2 * k - 2)) & 3); }
+    int last(K v) const { return (int)(v & 3); }
+    K from_read(const unsigned char *s) const {   // GetFirstKmerForward of s[0..k)
+        uint64_t v = 0;
+        for (int i = 0; i < k; i++) v = ((v << 2) | (uint64_t)fcode(s[i])) & kmask;
+        return v;
+    }
+    K from_read_backward(const unsigned char *s) const {   // GetFirstKmerBackward
+        uint64_t v = 0;
+        for (int i = k - 1; i >= 0; i--) v = ((v << 2) | (uint64_t)rcode(s[i])) & kmask;
+        return v;
+    }
+    K roll_fw(K v, unsigned char c) const { return ((v << 2) | (uint64_t)fcode(c)) & kmask; }
+    K roll_bw(K v, unsigned char c) const { return (v >> 2) | ((uint64_t)rcode(c) << (2 * k - 2)); }
+};
+
+struct StrOps {
+    using K = std::string;
+    using Hash = std::hash<std::string>;
+    int k;
+    explicit StrOps(int k_) : k(k_) {}
+    static char comp(char c) { return c == 'A' ? 'T' : c == 'C' ? 'G' : c == 'G' ? 'C' : 'A'; }
+    K revcomp(const K &v) const {
+        K r(v.size(), 'A');
+        for (size_t i = 0; i < v.size(); i++) r[i] = comp(v[v.size() - 1 - i]);
+        return r;
+    }
+    std::string str(const K &v) const { return v; }
+    K neighbour(const K &km, int d) const {
+        if (d < 4) return std::string(1, "ACGT"[d]) + km.substr(0, k - 1);
+        return km.substr(1) + "ACGT"[d - 4];
+    }
+    int first(const K &v) const { return fcode((unsigned char)v[0]); }
+    int last(const K &v) const { return fcode((unsigned char)v[k - 1]); }
+    K from_read(const unsigned char *s) const {
+        K v(k, 'A');
+        for (int i = 0; i < k; i++) v[i] = "ACGT"[fcode(s[i])];
+        return v;
+    }
+    K from_read_backward(const unsigned char *s) const {
+        K v(k, 'A');
+        for (int i = 0; i < k; i++) v[i] = "ACGT"[rcode(s[k - 1 - i])];
+        return v;
+    }
+    K roll_fw(const K &v, unsigned char c) const { return v.substr(1) + "ACGT"[fcode(c)]; }
+    K roll_bw(const K &v, unsigned char c) const { return std::string(1, "ACGT"[rcode(c)]) + v.substr(0, k - 1); }
+    // little-endian words of the bitset<2k> value (what the device and p3_check_directions use)
+    void to_words(const K &v, uint64_t *w, int W) const {
+        for (int j = 0; j < W; j++) w[j] = 0;
+        for (int i = 0; i < k; i++) {
+            int bit = 2 * (k - 1 - i);
+            w[bit >> 6] |= (uint64_t)fcode((unsigned char)v[i]) << (bit & 63);
+        }
+    }
+    K from_words(const uint64_t *w) const {
+        K v(k, 'A');
+        for (int i = 0; i < k; i++) {
+            int bit = 2 * (k - 1 - i);
+            v[i] = "ACGT"[(w[bit >> 6] >> (bit & 63)) & 3];
+        }
+        return v;
+    }
+};
 
 // canonical k-mer -> adjacency byte, open addressing (built once from p3_dbg_export)
 struct AdjTable {
@@ -174,50 +264,49 @@ struct AdjTable {
         return false;
     }
 };
+struct StrAdjTable {
+    std::unordered_map<std::string, uint8_t> m;
+    bool find(const std::string &key, uint8_t *v) const {
+        auto it = m.find(key);
+        if (it == m.end()) return false;
+        *v = it->second;
+        return true;
+    }
+};
 
 struct Junction { int id = 0; int coverage = 0; int left_cov[4] = {0, 0, 0, 0}; int right_cov[4] = {0, 0, 0, 0}; };
 struct Joint { int id = 0; int coverage = 0; int straight = 0; };
 struct Straight { int id = 0; std::string sequence; };
 
+template <class O, class A>
 struct Walker {
+    using K = typename O::K;
+    O ops;
     int k;
-    uint64_t kmask;
-    const AdjTable &adj;
-    std::unordered_map<uint64_t, Junction> junctions;
-    std::unordered_map<uint64_t, Joint> joints;
+    const A &adj;
+    std::unordered_map<K, Junction, typename O::Hash> junctions;
+    std::unordered_map<K, Joint, typename O::Hash> joints;
     std::vector<Straight> straights;   // id = index + 1
-    std::deque<uint64_t> visiting;
+    std::deque<K> visiting;
     int junction_id = 0, joint_id = 0;
     uint64_t missing = 0;              // CheckDirections on a k-mer the table lacks (must stay 0)
 
-    Walker(int k_, const AdjTable &a) : k(k_), kmask(k_ >= 32 ? ~0ULL : ((1ULL << (2 * k_)) - 1)), adj(a) {}
+    Walker(int k_, const A &a) : ops(k_), k(k_), adj(a) {}
 
-    uint64_t revcomp(uint64_t v) const {   // GetComplementKmer, reference src/BitCalc.cpp:36-45
-        uint64_t x = ~v;
-        x = ((x >> 2) & 0x3333333333333333ULL) | ((x & 0x3333333333333333ULL) << 2);
-        x = ((x >> 4) & 0x0F0F0F0F0F0F0F0FULL) | ((x & 0x0F0F0F0F0F0F0F0FULL) << 4);
-        x = __builtin_bswap64(x);
-        return x >> (64 - 2 * k);
-    }
-    std::string str(uint64_t v) const {   // GetStringKmer, reference src/BitCalc.cpp:57-65
-        std::string s(k, 'A');
-        for (int i = 0; i < k; i++) s[i] = "ACGT"[(v >> (2 * (k - 1 - i))) & 3];
-        return s;
-    }
+    K revcomp(const K &v) const { return ops.revcomp(v); }
+    std::string str(const K &v) const { return ops.str(v); }
+    K neighbour(const K &km, int d) const { return ops.neighbour(km, d); }
     // 8 CheckDirections bits of an ORIENTED k-mer: the table stores the canonical orientation;
     // for the other strand direction i of K is direction 7-i of revcomp(K)
-    uint8_t directions(uint64_t km) {
-        uint64_t rc = revcomp(km);
+    uint8_t directions(const K &km) {
+        K rc = revcomp(km);
         uint8_t a = 0;
         if (km <= rc) { if (!adj.find(km, &a)) missing++; return a; }
         if (!adj.find(rc, &a)) missing++;
         return rev8(a);
     }
-    uint64_t neighbour(uint64_t km, int d) const {   // reference src/DeBruijnGraph.cpp:327-339
-        return d < 4 ? ((km >> 2) | ((uint64_t)d << (2 * k - 2))) : (((km << 2) | (uint64_t)(d - 4)) & kmask);
-    }
     // CheckDirections, reference src/DeBruijnGraph.cpp:326-345
-    void check_directions(std::vector<uint64_t> &left, std::vector<uint64_t> &right, uint64_t km, int ignored) {
+    void check_directions(std::vector<K> &left, std::vector<K> &right, const K &km, int ignored) {
         left.clear(); right.clear();
         uint8_t a = directions(km);
         for (int i = 0; i < 8; i++) {
@@ -225,19 +314,19 @@ struct Walker {
             (i < 4 ? left : right).push_back(neighbour(km, i));
         }
     }
-    bool is_visited(uint64_t km) {   // reference src/DeBruijnGraph.cpp:300-315
-        uint64_t rc = revcomp(km);
+    bool is_visited(const K &km) {   // reference src/DeBruijnGraph.cpp:300-315
+        K rc = revcomp(km);
         return junctions.count(km) || junctions.count(rc) || joints.count(km) || joints.count(rc);
     }
-    void add_junction(uint64_t km) {   // :348-357
+    void add_junction(const K &km) {   // :348-357
         if (is_visited(km)) return;
         junctions[km].id = ++junction_id;
     }
-    void add_joint(uint64_t km) {      // :360-369
+    void add_joint(const K &km) {      // :360-369
         if (is_visited(km)) return;
         joints[km].id = ++joint_id;
     }
-    void add_straight(const std::string &seq, uint64_t lj, uint64_t rj) {   // :374-391
+    void add_straight(const std::string &seq, const K &lj, const K &rj) {   // :374-391
         if (is_visited(lj)) return;
         add_joint(lj);
         add_joint(rj);
@@ -246,17 +335,17 @@ struct Walker {
         joints[lj].straight = s.id;   // operator[] semantics: the entry exists afterwards even if
         joints[rj].straight = s.id;   // add_joint refused it (reference :385-389)
     }
-    void push_all(const std::vector<uint64_t> &l, const std::vector<uint64_t> &r) {
-        for (uint64_t v : l) visiting.push_back(v);
-        for (uint64_t v : r) visiting.push_back(v);
+    void push_all(const std::vector<K> &l, const std::vector<K> &r) {
+        for (const K &v : l) visiting.push_back(v);
+        for (const K &v : r) visiting.push_back(v);
     }
-    uint64_t extend_left(uint64_t target, uint64_t previous, std::vector<char> &ext, int previous_base) {   // :229-260
-        std::vector<uint64_t> l, r;
+    K extend_left(K target, K previous, std::vector<char> &ext, int previous_base) {   // :229-260
+        std::vector<K> l, r;
         check_directions(l, r, target, 4 + previous_base);
         while (l.size() == 1 && r.empty()) {
             if (is_visited(target)) { ext.clear(); return target; }
-            ext.push_back("ACGT"[(target >> (2 * k - 2)) & 3]);
-            previous_base = (int)(target & 3);
+            ext.push_back("ACGT"[ops.first(target)]);
+            previous_base = ops.last(target);
             previous = target;
             target = l[0];
             check_directions(l, r, target, 4 + previous_base);
@@ -264,13 +353,13 @@ struct Walker {
         if (!is_visited(target)) { push_all(l, r); add_junction(target); }
         return previous;
     }
-    uint64_t extend_right(uint64_t target, uint64_t previous, std::vector<char> &ext, int previous_base) {  // :264-297
-        std::vector<uint64_t> l, r;
+    K extend_right(K target, K previous, std::vector<char> &ext, int previous_base) {  // :264-297
+        std::vector<K> l, r;
         check_directions(l, r, target, previous_base);
         while (l.empty() && r.size() == 1) {
             if (is_visited(target)) { ext.clear(); return target; }
-            ext.push_back("ACGT"[target & 3]);
-            previous_base = (int)((target >> (2 * k - 2)) & 3);
+            ext.push_back("ACGT"[ops.last(target)]);
+            previous_base = ops.first(target);
             previous = target;
             target = r[0];
             check_directions(l, r, target, previous_base);
@@ -278,16 +367,16 @@ struct Walker {
         if (!is_visited(target)) { push_all(l, r); add_junction(target); }
         return previous;
     }
-    void search_node(uint64_t target) {   // :158-225
+    void search_node(const K &target) {   // :158-225
         if (is_visited(target)) return;
-        std::vector<uint64_t> l, r;
+        std::vector<K> l, r;
         check_directions(l, r, target, -1);
         if (l.size() != 1 || r.size() != 1) { push_all(l, r); add_junction(target); return; }
         std::vector<char> ext_l, ext_r;
-        uint64_t left_end = extend_left(l[0], target, ext_l, (int)(target & 3));
+        K left_end = extend_left(l[0], target, ext_l, ops.last(target));
         std::string left_part(ext_l.rbegin(), ext_l.rend());
         if (is_visited(left_end)) return;
-        uint64_t right_end = extend_right(r[0], target, ext_r, (int)((target >> (2 * k - 2)) & 3));
+        K right_end = extend_right(r[0], target, ext_r, ops.first(target));
         std::string right_part(ext_r.begin(), ext_r.end());
         if (is_visited(right_end)) return;
         if (left_end == right_end) { add_junction(left_end); return; }
@@ -295,33 +384,33 @@ struct Walker {
     }
     // MakeDBG with threads_num = 1, reference src/DeBruijnGraph.cpp:94-155. seeds sorted ascending
     // (== std::set<std::string> order for ACGT strings of equal length).
-    int make_dbg(const std::vector<uint64_t> &seeds, uint64_t node_limit) {
+    int make_dbg(const std::vector<K> &seeds, uint64_t node_limit) {
         uint64_t cnt = 0;
-        for (uint64_t s : seeds) {
+        for (const K &s : seeds) {
             cnt++;
             if (is_visited(s)) continue;
             visiting.push_back(s);
             if (cnt % 20 != 0) continue;
             while (!visiting.empty()) {
-                uint64_t v = visiting.front(); visiting.pop_front();
+                K v = visiting.front(); visiting.pop_front();
                 search_node(v);
                 if (junctions.size() > node_limit) return -1;
             }
         }
         while (!visiting.empty()) {
-            uint64_t v = visiting.front(); visiting.pop_front();
+            K v = visiting.front(); visiting.pop_front();
             search_node(v);
             if (junctions.size() > node_limit) return -1;
         }
         return 0;
     }
 };
+using Walker64 = Walker<U64Ops, AdjTable>;
+using WalkerStr = Walker<StrOps, StrAdjTable>;
 
-inline int fcode(unsigned char c) { return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : 0; }
-
-// CountNodeCoverage (reference src/DeBruijnGraph.cpp:394-439) runs on the GPU (p3_node_coverage):
-// the node k-mers go down in id order, the counters come back into the maps.
-int count_node_coverage(Walker &w, p3_ctx *ctx) {
+// CountNodeCoverage (reference src/DeBruijnGraph.cpp:394-439) for k <= 32 runs on the GPU
+// (p3_node_coverage): the node k-mers go down in id order, the counters come back into the maps.
+int count_node_coverage(Walker64 &w, p3_ctx *ctx) {
     std::vector<uint64_t> jk(w.junctions.size()), tk;
     std::vector<uint64_t> tkeys;
     for (auto &kv : w.junctions) jk[kv.second.id - 1] = kv.first;   // ids are 1..n without gaps
@@ -339,25 +428,71 @@ int count_node_coverage(Walker &w, p3_ctx *ctx) {
     return P3_OK;
 }
 
+// The same on the host, a transcription of the reference loop (one rolling forward and one rolling
+// backward k-mer per read). Used where the node k-mers are multi-word (k > 32; the reference does
+// this stage on the CPU too) and by the CPU tests of the walk.
+template <class W>
+void count_node_coverage_host(W &w, const std::string &seq, const std::vector<uint64_t> &off) {
+    const int k = w.k;
+    auto add_node = [&](const typename W::K &km) {   // AddNodeCoverage, :442-449
+        auto j = w.junctions.find(km);
+        if (j != w.junctions.end()) j->second.coverage++;
+        auto t = w.joints.find(km);
+        if (t != w.joints.end()) t->second.coverage++;
+    };
+    for (size_t r = 0; r + 1 < off.size(); r++) {
+        const unsigned char *rd = (const unsigned char *)seq.data() + off[r];
+        const size_t len = (size_t)(off[r + 1] - off[r]);
+        if (len < (size_t)k) continue;
+        auto rdat = [&](size_t i) -> unsigned char { return i < len ? rd[i] : (unsigned char)0; };   // std::string[size()] == '\0'
+        typename W::K fw = w.ops.from_read(rd), bw = w.ops.from_read_backward(rd);
+        add_node(fw); add_node(bw);
+        auto jf = w.junctions.find(fw);
+        if (jf != w.junctions.end()) jf->second.right_cov[fcode(rdat(k))]++;
+        else {
+            auto jb = w.junctions.find(bw);
+            if (jb != w.junctions.end()) jb->second.left_cov[rcode(rdat(k))]++;
+        }
+        for (size_t i = k; i < len; i++) {
+            fw = w.ops.roll_fw(fw, rd[i]);
+            bw = w.ops.roll_bw(bw, rd[i]);
+            add_node(fw); add_node(bw);
+            auto j1 = w.junctions.find(fw);
+            if (j1 != w.junctions.end()) {
+                j1->second.left_cov[fcode(rd[i - k])]++;
+                if (i < len - 1) j1->second.right_cov[fcode(rd[i + 1])]++;
+            } else {
+                auto j2 = w.junctions.find(bw);
+                if (j2 != w.junctions.end()) {
+                    j2->second.right_cov[rcode(rd[i - k])]++;
+                    if (i < len - 1) j2->second.left_cov[rcode(rd[i + 1])]++;
+                }
+            }
+        }
+    }
+}
+
 // PrintGraph, reference src/DeBruijnGraph.cpp:452-544. The reference iterates unordered_maps, so its
 // line order is unspecified; this writes straights and junctions by id.
-int print_graph(Walker &w, const char *path) {
+template <class W>
+int print_graph(W &w, const char *path) {
+    using K = typename W::K;
     FILE *f = fopen(path, "w");
     if (!f) return P3_ERR_IO;
     const int k = w.k;
     fprintf(f, "H\tVN:Z:1.0\n");
     for (auto &s : w.straights) fprintf(f, "S\tStraight_%d\t%s\tKC:i:%zu\n", s.id, s.sequence.c_str(), s.sequence.size());
-    std::vector<std::pair<int, uint64_t>> js;
+    std::vector<std::pair<int, K>> js;
     for (auto &kv : w.junctions) js.push_back({kv.second.id, kv.first});
-    std::sort(js.begin(), js.end());
+    std::sort(js.begin(), js.end(), [](const std::pair<int, K> &a, const std::pair<int, K> &b) { return a.first < b.first; });
     for (auto &p : js) fprintf(f, "S\tJunction_%d\t%s\tKC:i:%d\n", p.first, w.str(p.second).c_str(), w.junctions[p.second].coverage * k);
     for (auto &p : js) {
-        const uint64_t km = p.second;
+        const K km = p.second;
         const Junction &J = w.junctions[km];
         const uint8_t a = w.directions(km);
         for (int i = 0; i < 4; i++) {
             if (J.left_cov[i] == 0 || !((a >> i) & 1)) continue;   // IsRecorded(output_left_kmer)
-            uint64_t n = w.neighbour(km, i), nb = w.revcomp(n);
+            K n = w.neighbour(km, i), nb = w.revcomp(n);
             auto j1 = w.junctions.find(n);
             if (j1 != w.junctions.end()) { fprintf(f, "L\tJunction_%d\t+\tJunction_%d\t+\t%dM\n", j1->second.id, J.id, k - 1); continue; }
             auto t1 = w.joints.find(n);
@@ -369,7 +504,7 @@ int print_graph(Walker &w, const char *path) {
         }
         for (int i = 0; i < 4; i++) {
             if (J.right_cov[i] == 0 || !((a >> (4 + i)) & 1)) continue;
-            uint64_t n = w.neighbour(km, 4 + i), nb = w.revcomp(n);
+            K n = w.neighbour(km, 4 + i), nb = w.revcomp(n);
             auto j1 = w.junctions.find(n);
             if (j1 != w.junctions.end()) { fprintf(f, "L\tJunction_%d\t+\tJunction_%d\t+\t%dM\n", J.id, j1->second.id, k - 1); continue; }
             auto t1 = w.joints.find(n);
@@ -395,6 +530,166 @@ struct Log {   // reference src/Logging.cpp: append one line per call
 
 }  // namespace
 
+namespace {
+
+// k > 32: the device exports the distinct solid k-mers as n x W words with their adjacency bytes;
+// the walk works on strings. The table is closed under reported neighbours from the host: every
+// neighbour that CheckDirections reports but the table lacks (a Bloom false positive, or a seed) is
+// sent back to the GPU in batches (p3_check_directions answers the 8 queries of each), wave after
+// wave until nothing new appears — the k <= 32 path does the same on the device (p3_dbg_close).
+// Returns 0, a negative P3_ERR_* from the library (p3_last_error is set by it) or a POSITIVE
+// -P3_ERR_* for host-side failures (message set here).
+int close_table_long(p3_ctx *ctx, const StrOps &ops, int W, StrAdjTable &table, std::vector<std::string> frontier) {
+    for (int round = 0; !frontier.empty(); round++) {
+        if (round > 200) { g_host_err = "closure found no fixed point (filter saturated: the reference walk would not terminate either)"; return -P3_ERR_TABLE_FULL; }
+        std::vector<std::string> want;
+        std::unordered_map<std::string, char> seen;
+        for (const std::string &km : frontier) {
+            uint8_t a = 0;
+            if (!table.find(km, &a)) continue;
+            for (int d = 0; d < 8; d++) {
+                if (!((a >> d) & 1)) continue;
+                std::string n = ops.neighbour(km, d), rc = ops.revcomp(n);
+                const std::string &c = n <= rc ? n : rc;
+                uint8_t dummy;
+                if (table.find(c, &dummy) || seen.count(c)) continue;
+                seen.emplace(c, 1);
+                want.push_back(c);
+            }
+        }
+        if (want.empty()) break;
+        std::vector<uint64_t> words(want.size() * (size_t)W);
+        for (size_t i = 0; i < want.size(); i++) ops.to_words(want[i], words.data() + i * W, W);
+        std::vector<uint8_t> masks(want.size());
+        int rc = p3_check_directions(ctx, words.data(), want.size(), masks.data());
+        if (rc) return rc;
+        for (size_t i = 0; i < want.size(); i++) table.m.emplace(want[i], masks[i]);
+        frontier.swap(want);
+    }
+    return 0;
+}
+
+int assemble_long(p3_ctx *ctx, p3_reads *rd, uint32_t k, const std::vector<int64_t> &seed_pos, Log &log,
+                  const char *gfa_path, uint64_t *stats) {
+    const StrOps ops((int)k);
+    const int W = (int)((2 * k + 63) / 64);
+    const uint64_t n_reads = p3_reads_count(rd);
+    std::vector<std::string> seeds;
+    for (uint64_t r = 0; r < n_reads; r++)
+        if (seed_pos[r] >= 0) seeds.push_back(ops.from_read((const unsigned char *)rd->seq.data() + rd->off[r] + seed_pos[r]));
+    std::sort(seeds.begin(), seeds.end());
+    seeds.erase(std::unique(seeds.begin(), seeds.end()), seeds.end());
+    log.line("seed kmer num= " + std::to_string(seeds.size()));
+
+    int rc = p3_dbg_adjacency(ctx);
+    if (rc) return rc;
+    uint64_t n_solid = 0, n_edges = 0, n_pos = 0, n_d21 = 0, got = 0;
+    p3_dbg_stats(ctx, &n_solid, &n_edges);
+    p3_short_kmer_stats(ctx, &n_pos, &n_d21);
+    std::vector<uint64_t> words((size_t)std::max<uint64_t>(n_solid, 1) * W);
+    std::vector<uint8_t> adjb(std::max<uint64_t>(n_solid, 1));
+    rc = p3_dbg_export(ctx, words.data(), adjb.data(), std::max<uint64_t>(n_solid, 1), &got);
+    if (rc) return rc;
+    StrAdjTable table;
+    table.m.reserve((size_t)(got * 1.3) + 16);
+    std::vector<std::string> frontier;
+    frontier.reserve(got);
+    for (uint64_t i = 0; i < got; i++) {
+        frontier.push_back(ops.from_words(words.data() + i * W));
+        table.m.emplace(frontier.back(), adjb[i]);
+    }
+    std::vector<uint64_t>().swap(words);
+    // walk roots that are not solid (a seed with a non-ACGT base) get an entry of their own
+    {
+        std::vector<std::string> roots;
+        for (const std::string &s : seeds) {
+            std::string rcs = ops.revcomp(s);
+            const std::string &c = s <= rcs ? s : rcs;
+            uint8_t dummy;
+            if (!table.find(c, &dummy)) roots.push_back(c);
+        }
+        std::sort(roots.begin(), roots.end());
+        roots.erase(std::unique(roots.begin(), roots.end()), roots.end());
+        if (!roots.empty()) {
+            std::vector<uint64_t> rw(roots.size() * (size_t)W);
+            for (size_t i = 0; i < roots.size(); i++) ops.to_words(roots[i], rw.data() + i * W, W);
+            std::vector<uint8_t> masks(roots.size());
+            rc = p3_check_directions(ctx, rw.data(), roots.size(), masks.data());
+            if (rc) return rc;
+            for (size_t i = 0; i < roots.size(); i++) { table.m.emplace(roots[i], masks[i]); frontier.push_back(roots[i]); }
+        }
+    }
+    rc = close_table_long(ctx, ops, W, table, std::move(frontier));
+    if (rc) return rc;
+
+    log.line("start graph extention");
+    WalkerStr w((int)k, table);
+    if (w.make_dbg(seeds, /*node_limit*/ 4 * (table.m.size() + 16)) != 0 || w.missing) {
+        g_host_err = w.missing ? "internal: walk left the closed adjacency table" : "walk did not terminate";
+        return -P3_ERR_STATE;
+    }
+    log.line("de bruijn graph loaded");
+    count_node_coverage_host(w, rd->seq, rd->off);
+    log.line("count node coverage");
+    if (gfa_path && print_graph(w, gfa_path) != P3_OK) { g_host_err = "cannot write GFA"; return -P3_ERR_IO; }
+    if (stats) {
+        stats[0] = n_reads; stats[1] = rd->all_bases; stats[2] = n_d21; stats[3] = n_solid; stats[4] = table.m.size();
+        stats[5] = w.junctions.size(); stats[6] = w.joints.size(); stats[7] = w.straights.size();
+    }
+    return 0;
+}
+
+template <class W, class T, class KV>
+int walk_and_print(int k, const T &table, const KV &seeds, uint64_t n_table, const p3_reads *rd, const char *gfa_path, uint64_t *stats) {
+    W w(k, table);
+    if (w.make_dbg(seeds, 4 * (n_table + 16)) != 0) { g_host_err = "walk did not terminate"; return P3_ERR_STATE; }
+    if (w.missing) { g_host_err = "the adjacency table is not closed: the walk asked for a k-mer it lacks"; return P3_ERR_STATE; }
+    count_node_coverage_host(w, rd->seq, rd->off);
+    if (gfa_path && print_graph(w, gfa_path) != P3_OK) { g_host_err = "cannot write GFA"; return P3_ERR_IO; }
+    if (stats) { stats[0] = w.junctions.size(); stats[1] = w.joints.size(); stats[2] = w.straights.size(); }
+    return P3_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+// Host half of the drop-in on its own: Load + MakeDBG (-t 1 order) + CountNodeCoverage + PrintGraph
+// over a CLOSED CheckDirections table from any source (n canonical k-mers of W = ceil(2k/64)
+// little-endian words each, one adjacency byte each; closed = every reported neighbour is present)
+// and the ORIENTED seed k-mers. Needs no GPU: node coverage is counted on the host here.
+// stats (optional, 3 values): junctions, joints, straights.
+int p3_walk_table(const char *read_path, uint32_t k, const uint64_t *h_kmers, const uint8_t *h_adj, uint64_t n,
+                  const uint64_t *h_seeds, uint64_t n_seeds, const char *gfa_path, uint64_t *stats) {
+    if (!read_path || (!h_kmers && n) || (!h_adj && n) || (!h_seeds && n_seeds)) { g_host_err = "p3_walk_table: null argument"; return P3_ERR_ARG; }
+    if (k < P3_MIN_K || k > P3_MAX_K) { g_host_err = "k outside [21,3001] is not supported"; return P3_ERR_ARG; }
+    p3_reads *rd = nullptr;
+    int rc = p3_load_file(read_path, k, &rd);
+    if (rc) return rc;
+    if (k <= P3_MAX_K_WALK) {
+        std::vector<uint64_t> kk(h_kmers, h_kmers + n), seeds(h_seeds, h_seeds + n_seeds);
+        std::vector<uint8_t> aa(h_adj, h_adj + n);
+        AdjTable table; table.build(kk, aa);
+        std::sort(seeds.begin(), seeds.end());
+        seeds.erase(std::unique(seeds.begin(), seeds.end()), seeds.end());
+        rc = walk_and_print<Walker64>((int)k, table, seeds, n, rd, gfa_path, stats);
+    } else {
+        const StrOps ops((int)k);
+        const int W = (int)((2 * k + 63) / 64);
+        StrAdjTable table;
+        for (uint64_t i = 0; i < n; i++) table.m.emplace(ops.from_words(h_kmers + i * W), h_adj[i]);
+        std::vector<std::string> seeds;
+        for (uint64_t i = 0; i < n_seeds; i++) seeds.push_back(ops.from_words(h_seeds + i * W));
+        std::sort(seeds.begin(), seeds.end());
+        seeds.erase(std::unique(seeds.begin(), seeds.end()), seeds.end());
+        rc = walk_and_print<WalkerStr>((int)k, table, seeds, n, rd, gfa_path, stats);
+    }
+    p3_reads_free(rd);
+    return rc;
+}
+
+}  // extern "C"
+
 extern "C" {
 
 // main.cpp:11-31 + Assemble<>, reference src/Assemble.cpp:7-28, for one read file.
@@ -405,7 +700,7 @@ int p3_assemble_file(const char *read_path, uint32_t k, uint64_t m, int threads,
                      const char *gfa_path, const char *log_path, uint64_t *stats) {
     (void)threads;
     Log log; log.path = log_path ? log_path : "";
-    if (k < P3_MIN_K || k > P3_MAX_K_WALK) { g_host_err = "k outside [21,32] is not supported by the host walk of this build"; return P3_ERR_ARG; }
+    if (k < P3_MIN_K || k > P3_MAX_K) { g_host_err = "k outside [21,3001] is not supported"; return P3_ERR_ARG; }
     p3_reads *rd = nullptr;
     int rc = p3_load_file(read_path, k, &rd);
     if (rc) return rc;
@@ -443,6 +738,15 @@ int p3_assemble_file(const char *read_path, uint32_t k, uint64_t m, int threads,
     std::vector<int64_t> seed_pos(n_reads);
     rc = p3_seed_export(ctx, seed_pos.data());
     if (rc) return bail(rc);
+    if (k > P3_MAX_K_WALK) {   // multi-word k-mers: string walk, closure driven from the host (assemble_long)
+        rc = assemble_long(ctx, rd, k, seed_pos, log, gfa_path, stats);
+        if (rc > 0) { p3_destroy(ctx); p3_reads_free(rd); return -rc; }   // host-side failure, message already set
+        if (rc) return bail(rc);
+        p3_destroy(ctx);
+        p3_reads_free(rd);
+        log.line("finish");
+        return P3_OK;
+    }
     // seed_kmer: std::set of the forward strings (MakeBloomFilter.cpp:80-81) -> sorted unique values
     std::vector<uint64_t> seeds;
     const uint64_t kmask = k >= 32 ? ~0ULL : ((1ULL << (2 * k)) - 1);
@@ -474,7 +778,7 @@ int p3_assemble_file(const char *read_path, uint32_t k, uint64_t m, int threads,
     log.line("start graph extention");
     AdjTable table; table.build(kmers, adjb);
     std::vector<uint64_t>().swap(kmers);
-    Walker w((int)k, table);
+    Walker64 w((int)k, table);
     if (w.make_dbg(seeds, /*node_limit*/ 4 * (got + 16)) != 0 || w.missing) {
         g_host_err = w.missing ? "internal: walk left the closed adjacency table" : "walk did not terminate";
         p3_destroy(ctx);

@@ -55,16 +55,90 @@ def test_load_file_edge_cases(tmp_path):
         _lib.load_file(str(tmp_path / "missing.fasta"), 21)
 
 
+def _closed_table_from_oracle(oracle, g, path):
+    """solid k-mers + adjacency + Bloom-false-positive closure + seeds, all from the oracle (CPU)"""
+    from _checkers import kmer_str_to_words, nwords
+    k, fs, nh = int(g["k"]), int(g["filter_size"]), int(g["num_hashes"])
+    W = nwords(k)
+    seq, off, _ = oracle.load_reads(path, k)
+    keys, counts = np.ascontiguousarray(g["keys"], np.uint64), np.ascontiguousarray(g["counts"], np.uint64)
+    bloom = np.ascontiguousarray(g["bloom"], np.uint8)
+    solid = oracle.solid_kmers(seq, off, k, keys, counts)
+    mask = (1 << (2 * k)) - 1
+
+    def to_int(w):
+        return sum(int(x) << (64 * i) for i, x in enumerate(w))
+
+    def to_words(v):
+        return np.array([(v >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(W)], np.uint64)
+
+    def canon(v):
+        r, x = 0, v
+        for _ in range(k):
+            r = (r << 2) | (3 - (x & 3))
+            x >>= 2
+        return min(v, r)
+
+    table = {}
+    frontier = []
+    for w in solid:
+        v = to_int(w)
+        table[v] = oracle.check_directions(bloom, fs, nh, w, k)
+        frontier.append(v)
+    seeds = [to_int(kmer_str_to_words(str(sd), k)) for sd in g["seeds"]]
+    for sd in seeds:                       # walk roots that are not solid get an entry too
+        c = canon(sd)
+        if c not in table:
+            table[c] = oracle.check_directions(bloom, fs, nh, to_words(c), k)
+            frontier.append(c)
+    while frontier:                        # closure under reported neighbours (Bloom false positives)
+        nxt = []
+        for v in frontier:
+            a = table[v]
+            for d in range(8):
+                if (a >> d) & 1:
+                    nb = (v >> 2) | (d << (2 * k - 2)) if d < 4 else ((v << 2) | (d - 4)) & mask
+                    c = canon(nb)
+                    if c not in table:
+                        table[c] = oracle.check_directions(bloom, fs, nh, to_words(c), k)
+                        nxt.append(c)
+        frontier = nxt
+    kk = np.array([to_words(v) for v in table], np.uint64).reshape(-1, W)
+    aa = np.array(list(table.values()), np.uint8)
+    ss = np.array([to_words(v) for v in seeds], np.uint64).reshape(-1, W)
+    return kk, aa, ss, len(solid)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_host_walk_over_oracle_table_matches_reference_gfa(oracle, name, tmp_path):
+    """The host half of the drop-in (Load, MakeDBG in -t 1 order, CountNodeCoverage on the host, PrintGraph)
+    needs no GPU when it is handed a closed CheckDirections table: here the table comes from the oracle, the
+    GFA must equal the reference's — for single-word k (uint64 walk) and for k = 63 / 101 (string walk)."""
+    g, path = _load(name)
+    k = int(g["k"])
+    kk, aa, ss, n_solid = _closed_table_from_oracle(oracle, g, path)
+    assert len(aa) >= n_solid
+    gfa = str(tmp_path / "walk.gfa")
+    st = _lib.walk_table(path, k, kk, aa, ss, gfa_path=gfa)
+    assert (st["junctions"], st["joints"], st["straights"]) == (int(g["n_junctions"]), int(g["n_joints"]), int(g["n_straights"]))
+    assert sorted(open(gfa).read().splitlines()) == [str(x) for x in g["gfa"]]
+
+
+def test_host_walk_refuses_an_open_table(oracle, tmp_path):
+    g, path = _load("k25_err")
+    kk, aa, ss, n_solid = _closed_table_from_oracle(oracle, g, path)
+    if len(aa) == n_solid:
+        pytest.skip("no false-positive k-mers in this fixture")
+    with pytest.raises(_lib.P3Error):      # drop the closure's additions: the walk must notice, not mis-assemble
+        _lib.walk_table(path, 25, kk[:n_solid], aa[:n_solid], ss, gfa_path=str(tmp_path / "x.gfa"))
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", CASES)
 def test_assemble_file_matches_reference_gfa(name, tmp_path):
     """GFA (as a set of lines), node counts and seed count equal the reference's -t 1 run"""
     g, path = _load(name)
     gfa, log = str(tmp_path / "out.gfa"), str(tmp_path / "out.log")
-    if int(g["k"]) > 32:   # the host walk is single-word in this build: must refuse, not mis-assemble
-        with pytest.raises(_lib.P3Error):
-            _lib.assemble_file(path, int(g["k"]), m=int(g["m"]), threads=1, gfa_path=gfa, log_path=log)
-        return
     st = _lib.assemble_file(path, int(g["k"]), m=int(g["m"]), threads=1, gfa_path=gfa, log_path=log)
     assert (st["junctions"], st["joints"], st["straights"]) == (int(g["n_junctions"]), int(g["n_joints"]), int(g["n_straights"]))
     assert st["reads"] == int(g["n_reads"]) and st["all_bases"] == int(g["all_bases"])
@@ -87,7 +161,7 @@ def test_cli_drop_in(tmp_path):
     assert (tmp_path / "platanus3.log").read_text().splitlines()[-1] == "finish"
     r = subprocess.run([exe], cwd=tmp_path, capture_output=True, text=True, timeout=60)
     assert r.returncode == 0 and r.stdout.startswith("Usage: platanus3 -i")      # main.cpp:16-19
-    r = subprocess.run([exe, "-i", path, "-k", "63"], cwd=tmp_path, capture_output=True, text=True, timeout=60)
+    r = subprocess.run([exe, "-i", path, "-k", "3002"], cwd=tmp_path, capture_output=True, text=True, timeout=60)
     assert r.returncode == 1 and "not supported" in r.stderr
 
 
