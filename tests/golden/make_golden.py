@@ -35,6 +35,8 @@ CASES = [
     # multi-word k-mers, two of the values the reference's own Assemble_k offers (Assemble.cpp:38-41)
     ("k63_err", 63, 0, 1500, 50, 150, 0.005, "fasta"),
     ("k101_m", 101, 300007, 1500, 30, 250, 0.003, "fastq"),
+    # 16 words per k-mer; long reads (Assemble.cpp:42)
+    ("k501_m", 501, 400009, 3000, 30, 800, 0.002, "fasta"),
 ]
 
 
@@ -58,7 +60,10 @@ def build_reads(name, genome, cov, rl, err, seed):
 
 def main():
     import multiprocessing as mp
+    only = set(sys.argv[1:])       # optional: names of the cases to (re)generate
     for ci, case in enumerate(CASES):
+        if only and case[0] not in only:
+            continue
         p = mp.Process(target=one_case, args=(ci,) + case)
         p.start()
         p.join(600)
