@@ -38,6 +38,104 @@ def test_load_file_matches_oracle(oracle, name):
         assert np.array_equal(nmask, mine["nmask"])
 
 
+def _numpy_pack(seq):
+    """straightforward restatement of the staging layout: 32 bases per uint64, first base on top; a
+    byte outside ACGT packs as 0 and sets its bit (MSB first) in the non-ACGT plane"""
+    n = len(seq)
+    words = (n + 31) // 32 + 1
+    code = np.full(256, 4, np.uint8)
+    for i, ch in enumerate(b"ACGT"):
+        code[ch] = i
+    c = code[seq]
+    bad = (c >> 2).astype(np.uint64)
+    c = (c & 3).astype(np.uint64)
+    pad = (-n) % 32
+    c = np.concatenate([c, np.zeros(pad, np.uint64)]).reshape(-1, 32)
+    bad = np.concatenate([bad, np.zeros(pad, np.uint64)]).reshape(-1, 32)
+    pk = np.zeros(words, np.uint64)
+    nm = np.zeros(words, np.uint32)
+    pk[:len(c)] = (c << np.arange(62, -2, -2, dtype=np.uint64)).sum(axis=1, dtype=np.uint64)
+    nm[:len(c)] = (bad << np.arange(31, -1, -1, dtype=np.uint64)).sum(axis=1, dtype=np.uint64).astype(np.uint32)
+    return pk, nm
+
+
+@pytest.mark.parametrize("n", [0, 1, 31, 32, 33, 257, 100_003, (1 << 25) + 77])
+def test_pack_reads_matches_the_layout_definition(n):
+    """p3_pack_reads (8 bases per step with BMI2 bit gathers, threads above 2^20 words) against the plain
+    definition, with every byte value present and ~2 % arbitrary bytes"""
+    rng = np.random.default_rng(n)
+    seq = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, n)].copy()
+    if n > 40:
+        idx = rng.integers(0, n, max(1, n // 50))
+        seq[idx] = rng.integers(0, 256, len(idx)).astype(np.uint8)
+    if n >= 257:
+        seq[:256] = np.arange(256, dtype=np.uint8)
+    pk, nm = _lib.pack_reads(seq, np.array([0, n], np.uint64))
+    rpk, rnm = _numpy_pack(seq)
+    assert np.array_equal(pk, rpk)
+    assert (nm is None and not rnm.any()) or (nm is not None and np.array_equal(nm, rnm))
+
+
+def _messy_file(rng, kind, k):
+    """a read file full of the things real files do: multi-line FASTA with ragged widths, blank lines,
+    repeated and empty name lines, reads shorter than / exactly k, non-ACGT and lower-case bytes,
+    CRLF line ends, a missing final newline, '@' and '>' inside FASTQ quality lines"""
+    out = []
+    n = int(rng.integers(1, 40))
+    names = ["%s r%d x" % (">" if kind == "fasta" else "@", i) for i in range(n)]
+    for i in range(n):
+        r = int(rng.integers(0, 12))
+        if r == 0:
+            names[i] = names[int(rng.integers(0, n))]              # repeated name line
+        elif r == 1:
+            names[i] = ">" if kind == "fasta" else "@"              # nothing but the marker
+        L = int(rng.choice([k - 1, k, k + 1, int(rng.integers(1, 4 * k))]))
+        seq = bytearray(b"ACGT"[j] for j in rng.integers(0, 4, L))
+        for _ in range(int(rng.integers(0, 3))):
+            if L:
+                seq[int(rng.integers(0, L))] = int(rng.choice(list(b"NnacgtRY-")))
+        eol = b"\r\n" if rng.integers(0, 10) == 0 else b"\n"
+        if kind == "fasta":
+            out.append(names[i].encode() + eol)
+            w = int(rng.integers(1, 2 * k))
+            for j in range(0, max(L, 1), w):
+                out.append(bytes(seq[j:j + w]) + eol)
+                if rng.integers(0, 25) == 0:
+                    out.append(eol)                                   # blank line inside a record
+        else:
+            qual = bytes(rng.choice(list(b"@>+I!#5"), L).tolist())
+            out.append(names[i].encode() + eol + bytes(seq) + eol + b"+" + eol + qual + eol)
+            if rng.integers(0, 30) == 0:
+                out.append(eol)             # a stray blank line: shifts the 4-line rhythm, empty "name" lines follow
+    data = b"".join(out)
+    if rng.integers(0, 3) == 0 and data.endswith(b"\n"):
+        data = data[:-1]                                              # no newline at the end of the file
+    return data
+
+
+@pytest.mark.parametrize("kind", ["fasta", "fastq"])
+def test_load_file_differential(oracle, tmp_path, kind):
+    """p3_load_file (one mmap pass, no per-line strings) against the reference's own LoadFile (when the
+    reference is compiled here) and the oracle's restatement, on 60 messy files per format"""
+    from _checkers import Ref, have_ref
+    k = 21
+    for trial in range(60):
+        rng = np.random.default_rng(1000 * (kind == "fastq") + trial)
+        path = str(tmp_path / ("t%d_x.%s" % (trial, kind)))
+        with open(path, "wb") as f:
+            f.write(_messy_file(rng, kind, k))
+        mine = _lib.load_file(path, k)
+        a = sorted(mine["seq"][int(mine["off"][i]):int(mine["off"][i + 1])].tobytes() for i in range(len(mine["off"]) - 1))
+        seq, off, all_bases = oracle.load_reads(path, k)
+        b = sorted(seq[int(off[i]):int(off[i + 1])].tobytes() for i in range(len(off) - 1))
+        assert a == b and mine["all_bases"] == all_bases, trial
+        if have_ref():
+            ref = Ref(k, readfile=path)
+            ref.load_file()
+            assert a == sorted(ref.reads()) and mine["all_bases"] == ref.all_bases, trial
+            ref.close()
+
+
 def test_load_file_edge_cases(tmp_path):
     p = tmp_path / "empty.fasta"
     p.write_bytes(b"")
