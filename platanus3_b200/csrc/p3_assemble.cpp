@@ -10,6 +10,7 @@
 #include "../../include/platanus3_b200.h"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -18,6 +19,7 @@
 #include <fstream>
 #include <string>
 #include <string_view>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -87,15 +89,19 @@ struct FileView {
 
 extern "C" {
 
-// One pass over the mapped file with memchr; sequence bytes are appended to ONE buffer as they are
-// met and a record is committed or rolled back when its end is known, so there is no per-line or
-// per-read std::string (the first version, std::getline + a vector of strings, loaded 60 Mbases/s:
-// 80 s for configs[1]'s 5 Gbp against 0.4 s for the GPU hot path). The state machine is the
-// reference's line loop verbatim (src/Load.cpp:51-103): lines as std::getline cuts them ('\r'
-// stays), FASTA or single-line FASTQ chosen by the first byte of the first line, a record is added
-// when the NEXT header arrives (only if the current name line is non-empty) and once more at the
-// end of the file, reads shorter than k are dropped, a repeated name line replaces the earlier
-// record while all_bases counts both.
+// Load in three phases over the mapped file, two of them parallel (the first version — std::getline
+// plus a vector of strings — loaded 60 Mbases/s: 80 s for configs[1]'s 5 Gbp against 0.4 s for the
+// GPU hot path; a single memchr pass with an open-addressing name index reached 250):
+//   A  (threads) newlines per chunk -> the line number every chunk starts at; then each thread turns
+//      the lines that START in its chunk into events: header line / run of sequence lines, with the
+//      name hash computed on the spot
+//   B  (serial, a few ns per event) the reference's line loop verbatim over the events
+//      (src/Load.cpp:51-103): FASTA or single-line FASTQ chosen by the first byte of the first line,
+//      a record is added when the NEXT header arrives (only if the current name line is non-empty;
+//      otherwise the sequence keeps growing) and once more at the end of the file, reads shorter
+//      than k are dropped, a repeated name line replaces the earlier record while all_bases counts both
+//   C  (threads) the sequence bytes of the surviving records are copied to their final offsets
+//      (lines as std::getline cuts them: the '\n' goes, a '\r' stays), then p3_pack_reads
 int p3_load_file(const char *path, uint32_t k, p3_reads **out) {
     if (!path || !out) return P3_ERR_ARG;
     // reference src/Load.cpp:26: file_name.substr(size-5, 5) throws for names shorter than 5
@@ -106,94 +112,200 @@ int p3_load_file(const char *path, uint32_t k, p3_reads **out) {
     FileView fv;
     if (!fv.open(path)) { g_host_err = std::string("cannot open ") + path; return P3_ERR_IO; }
     p3_reads *r = new p3_reads();
-    struct Rec { uint64_t start, len; const char *name; uint32_t name_len; bool alive; };
-    std::vector<Rec> recs;
-    // name line -> latest record with that name: open addressing over (hash, record index); the names
-    // themselves stay in the mapped file (std::unordered_map<string_view> cost 0.7 us per read here)
-    struct NameIndex {
-        std::vector<uint64_t> h; std::vector<uint32_t> rec; uint64_t mask = 0, used = 0;
-        static uint64_t hash(const char *p, size_t n) {
-            uint64_t x = 0x9E3779B97F4A7C15ULL ^ (n * 0xff51afd7ed558ccdULL);
-            while (n >= 8) { uint64_t v; memcpy(&v, p, 8); x = (x ^ v) * 0xc4ceb9fe1a85ec53ULL; x ^= x >> 29; p += 8; n -= 8; }
-            uint64_t v = 0; memcpy(&v, p, n);
-            x = (x ^ v) * 0xff51afd7ed558ccdULL; x ^= x >> 32; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 29;
-            return x | 1;     // 0 marks an empty cell
+    const char *const data = fv.data, *const fend = fv.data + fv.size;
+
+    int mode = 0;   // 1 FASTA, 2 FASTQ, decided by the first byte of the first line (Load.cpp:40-48)
+    if (fv.size) {
+        const char *nl = (const char *)memchr(data, '\n', fv.size);
+        const size_t len0 = nl ? (size_t)(nl - data) : fv.size;
+        if (len0 && data[0] == '>') mode = 1;
+        else if (len0 && data[0] == '@') mode = 2;
+    }
+
+    struct Event { const char *p; uint64_t a, b; };   // header: p = line, a = length, b = name hash | 1
+                                                      // sequence run: p = first line, a = bytes up to the run's end, b = 0
+    auto name_hash = [](const char *q, size_t n) -> uint64_t {
+        uint64_t x = 0x9E3779B97F4A7C15ULL ^ (n * 0xff51afd7ed558ccdULL);
+        while (n >= 8) { uint64_t v; memcpy(&v, q, 8); x = (x ^ v) * 0xc4ceb9fe1a85ec53ULL; x ^= x >> 29; q += 8; n -= 8; }
+        uint64_t v = 0; memcpy(&v, q, n);
+        x = (x ^ v) * 0xff51afd7ed558ccdULL; x ^= x >> 32; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 29;
+        return x | 1;
+    };
+
+    // ---- phase A -------------------------------------------------------------------------------------
+    unsigned n_thr = std::thread::hardware_concurrency();
+    n_thr = std::max(1u, std::min(n_thr ? n_thr : 1u, 32u));
+    size_t chunk = std::max<size_t>((fv.size + n_thr - 1) / n_thr, 1 << 20);
+    if (const char *e = getenv("P3_LOAD_CHUNK_BYTES")) chunk = std::max<size_t>(strtoull(e, nullptr, 10), 1);   // tests: tiny chunks
+    const size_t n_chunks = mode ? (fv.size + chunk - 1) / chunk : 0;
+    if (n_chunks > (1u << 20)) { delete r; g_host_err = "P3_LOAD_CHUNK_BYTES too small for this file"; return P3_ERR_ARG; }
+    std::vector<uint64_t> nl_before(n_chunks + 1, 0);
+    std::vector<std::vector<Event>> events(n_chunks);
+    auto run_chunks = [&](auto fn) {      // chunks are dealt out dynamically to n_thr threads
+        std::atomic<size_t> next{0};
+        auto body = [&] { for (size_t c; (c = next.fetch_add(1)) < n_chunks;) fn(c); };
+        if (n_thr == 1 || n_chunks <= 1) { body(); return; }
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < std::min<size_t>(n_thr, n_chunks); t++) th.emplace_back(body);
+        for (auto &x : th) x.join();
+    };
+    run_chunks([&](size_t c) {
+        const char *q = data + c * chunk, *e = std::min(fend, q + chunk);
+        uint64_t n = 0;
+        while (q < e) { const char *nl = (const char *)memchr(q, '\n', (size_t)(e - q)); if (!nl) break; n++; q = nl + 1; }
+        nl_before[c + 1] = n;
+    });
+    for (size_t c = 0; c < n_chunks; c++) nl_before[c + 1] += nl_before[c];
+    run_chunks([&](size_t c) {
+        const char *cb = data + c * chunk, *ce = std::min(fend, cb + chunk);
+        // first line that STARTS in this chunk, and its line number
+        const char *q = cb;
+        uint64_t line = nl_before[c];
+        if (c && cb[-1] != '\n') {
+            const char *nl = (const char *)memchr(cb, '\n', (size_t)(fend - cb));
+            if (!nl) return;                    // the rest of the file is one line that started earlier
+            if (nl >= ce) return;               // ... or that line ends beyond this chunk: no line starts here
+            q = nl + 1; line = nl_before[c] + 1;
         }
+        std::vector<Event> &ev = events[c];
+        const char *run = nullptr;              // open run of sequence lines
+        while (q < ce) {
+            const char *nl = (const char *)memchr(q, '\n', (size_t)(fend - q));
+            const char *le = nl ? nl : fend;
+            bool header, is_seq;
+            if (mode == 1) { header = le > q && q[0] == '>'; is_seq = !header; }
+            else { header = line % 4 == 0; is_seq = line % 4 == 1; }
+            if (header) {
+                if (run) { ev.push_back({run, (uint64_t)(q - run), 0}); run = nullptr; }
+                ev.push_back({q, (uint64_t)(le - q), name_hash(q, (size_t)(le - q))});
+            } else if (is_seq) {
+                if (!run) run = q;
+                if (mode == 2) { ev.push_back({run, (uint64_t)((nl ? nl + 1 : fend) - run), 0}); run = nullptr; }
+            }
+            q = nl ? nl + 1 : fend;
+            line++;
+        }
+        if (run) ev.push_back({run, (uint64_t)(q - run), 0});
+    });
+    auto t_events = now();
+
+    // ---- phase B -------------------------------------------------------------------------------------
+    struct Rec { uint64_t len; const char *name; uint32_t name_len; uint32_t n_runs; uint64_t run0; bool alive; };
+    std::vector<Rec> recs;
+    std::vector<std::pair<const char *, uint64_t>> runs;   // (first byte, bytes) of every sequence run of every record
+    struct NameIndex {      // name line -> latest record with that name: open addressing over (hash, record)
+        std::vector<uint64_t> h; std::vector<uint32_t> rec; uint64_t mask = 0, used = 0;
         void grow() {
             uint64_t cap = mask ? (mask + 1) * 4 : (1u << 16);
             std::vector<uint64_t> nh(cap, 0); std::vector<uint32_t> nr(cap, 0);
-            for (uint64_t i = 0; i <= mask && mask; i++)
+            for (uint64_t i = 0; mask && i <= mask; i++)
                 if (h[i]) { uint64_t s = h[i] & (cap - 1); while (nh[s]) s = (s + 1) & (cap - 1); nh[s] = h[i]; nr[s] = rec[i]; }
             h.swap(nh); rec.swap(nr); mask = cap - 1;
         }
     } index;
-    std::string &seq = r->seq;
-    seq.reserve(fv.size / 2 + 64);
-    uint64_t all_bases = 0, cur_start = 0, dead = 0;
-    std::string_view name;            // current header line
-    bool have_name_line = false;      // a header line has been seen (its text may be empty)
-    auto add_record = [&](std::string_view nm) {          // the current sequence is seq[cur_start, end)
-        const uint64_t len = seq.size() - cur_start;
-        if (len >= k) {
-            if (recs.size() >= 0xFFFFFFFFull) return;            // record index is 32 bits in the name table
-            if (2 * (index.used + 1) > index.mask + 1 || !index.mask) index.grow();
-            const uint64_t hv = NameIndex::hash(nm.data(), nm.size());
+    // bases of a run = its bytes minus its '\n's (a '\r' counts: std::getline keeps it)
+    auto run_bases = [&](const char *q, uint64_t bytes) -> uint64_t {
+        uint64_t n = bytes;
+        const char *e = q + bytes;
+        while (q < e) { const char *nl = (const char *)memchr(q, '\n', (size_t)(e - q)); if (!nl) break; n--; q = nl + 1; }
+        return n;
+    };
+    uint64_t all_bases = 0, dead = 0, total = 0;
+    bool too_many = false;
+    const char *name = nullptr; uint64_t name_len = 0, name_h = 0;   // current header line (empty before the first)
+    uint64_t cur_run0 = 0, cur_len = 0;                               // current sequence = runs[cur_run0 ..), cur_len bases
+    auto add_record = [&] {
+        if (cur_len >= k) {
+            if (recs.size() >= 0xFFFFFFFFull) { too_many = true; return; }
+            if (!index.mask || 2 * (index.used + 1) > index.mask + 1) index.grow();
+            const uint64_t hv = name ? name_h : 1;
             uint64_t s = hv & index.mask;
             for (;; s = (s + 1) & index.mask) {
                 if (!index.h[s]) { index.h[s] = hv; index.rec[s] = (uint32_t)recs.size(); index.used++; break; }
                 if (index.h[s] != hv) continue;
                 Rec &o = recs[index.rec[s]];
-                if (o.name_len == nm.size() && memcmp(o.name, nm.data(), nm.size()) == 0) {
-                    o.alive = false; dead++;                     // the later record replaces the earlier
+                if (o.name_len == name_len && (name_len == 0 || memcmp(o.name, name, name_len) == 0)) {
+                    o.alive = false; dead++; total -= o.len;     // the later record replaces the earlier
                     index.rec[s] = (uint32_t)recs.size();
                     break;
                 }
             }
-            recs.push_back({cur_start, len, nm.data(), (uint32_t)nm.size(), true});
-            all_bases += len;
-            cur_start = seq.size();
+            recs.push_back({cur_len, name, (uint32_t)name_len, (uint32_t)(runs.size() - cur_run0), cur_run0, true});
+            all_bases += cur_len; total += cur_len;
         } else {
-            seq.resize(cur_start);                          // dropped: shorter than k
+            runs.resize(cur_run0);                               // dropped: shorter than k
         }
+        cur_run0 = runs.size(); cur_len = 0;
     };
-    int mode = 0;   // 1 FASTA, 2 FASTQ, decided by the first byte of the first line (Load.cpp:40-48)
-    uint64_t line_cnt = 0;
-    const char *p = fv.data, *end = fv.data + fv.size;
-    while (p < end) {
-        const char *nl = (const char *)memchr(p, '\n', (size_t)(end - p));
-        const char *le = nl ? nl : end;
-        std::string_view line(p, (size_t)(le - p));
-        p = nl ? nl + 1 : end;
-        if (line_cnt == 0) {
-            if (!line.empty() && line[0] == '>') mode = 1;
-            else if (!line.empty() && line[0] == '@') mode = 2;
-            else break;   // neither: nothing is loaded
-        }
-        const bool header = mode == 1 ? (!line.empty() && line[0] == '>') : (line_cnt % 4 == 0);
-        if (header) {
-            if (have_name_line && !name.empty()) add_record(name);   // (seq is NOT cleared when the name is empty)
-            name = line; have_name_line = true;
-        } else if (mode == 1 || line_cnt % 4 == 1) {
-            seq.append(line.data(), line.size());
-        }
-        line_cnt++;
+    {   // one allocation each for the record and run lists, and a name table that will not have to grow
+        size_t n_ev = 0;
+        for (size_t c = 0; c < n_chunks; c++) n_ev += events[c].size();
+        recs.reserve(n_ev / 2 + 16); runs.reserve(n_ev / 2 + 16);
+        while (index.mask + 1 < n_ev + 16 && index.mask + 1 < (1ull << 33)) index.grow();
     }
-    if (mode && seq.size() - cur_start >= k) add_record(name);   // Load.cpp:71-74
-    else seq.resize(cur_start);
-    if (dead) {   // compact the replaced records away
-        uint64_t w = 0;
-        for (Rec &rc : recs) {
-            if (!rc.alive) continue;
-            if (rc.start != w) memmove(&seq[w], &seq[rc.start], rc.len);
-            rc.start = w; w += rc.len;
+    for (size_t c = 0; c < n_chunks; c++) {
+        const std::vector<Event> &evs = events[c];
+        for (size_t ei = 0; ei < evs.size(); ei++) {
+            const Event &e = evs[ei];
+            if (ei + 16 < evs.size() && evs[ei + 16].b) {        // the name table is far larger than the caches
+                __builtin_prefetch(&index.h[evs[ei + 16].b & index.mask]);
+                __builtin_prefetch(&index.rec[evs[ei + 16].b & index.mask]);
+            }
+            if (e.b) {                                           // header line
+                if (name_len) add_record();                      // (the sequence is NOT cleared when the name is empty)
+                name = e.p; name_len = e.a; name_h = e.b;
+            } else {
+                runs.emplace_back(e.p, e.a);
+                cur_len += mode == 2 ? e.a - (e.a && e.p[e.a - 1] == '\n' ? 1 : 0) : run_bases(e.p, e.a);
+            }
         }
-        seq.resize(w);
+        std::vector<Event>().swap(events[c]);
     }
+    if (mode && cur_len >= k) add_record();                      // Load.cpp:71-74
+    if (too_many) { delete r; g_host_err = "more than 2^32 reads in one file"; return P3_ERR_ARG; }
     auto t_parsed = now();
+
+    // ---- phase C -------------------------------------------------------------------------------------
     r->all_bases = all_bases;
     r->off.reserve(recs.size() - dead + 1);
     r->off.push_back(0);
-    for (const Rec &rc : recs) if (rc.alive) r->off.push_back(rc.start + rc.len);
+    std::vector<uint32_t> alive;
+    alive.reserve(recs.size() - dead);
+    for (size_t i = 0; i < recs.size(); i++)
+        if (recs[i].alive) { alive.push_back((uint32_t)i); r->off.push_back(r->off.back() + recs[i].len); }
+    r->seq.resize(total);
+    {
+        char *dst0 = &r->seq[0];
+        const size_t n_alive = alive.size();
+        const size_t per = std::max<size_t>((n_alive + 8 * n_thr - 1) / (8 * n_thr), 1);
+        const size_t n_jobs = (n_alive + per - 1) / per;
+        std::atomic<size_t> next{0};
+        auto body = [&] {
+            for (size_t j; (j = next.fetch_add(1)) < n_jobs;) {
+                for (size_t i = j * per; i < std::min(n_alive, (j + 1) * per); i++) {
+                    const Rec &rc = recs[alive[i]];
+                    char *d = dst0 + r->off[i];
+                    for (uint32_t u = 0; u < rc.n_runs; u++) {
+                        const char *q = runs[rc.run0 + u].first, *e = q + runs[rc.run0 + u].second;
+                        while (q < e) {
+                            const char *nl = (const char *)memchr(q, '\n', (size_t)(e - q));
+                            const char *le = nl ? nl : e;
+                            memcpy(d, q, (size_t)(le - q));
+                            d += le - q;
+                            q = nl ? nl + 1 : e;
+                        }
+                    }
+                }
+            }
+        };
+        if (n_thr == 1 || n_jobs <= 1) body();
+        else {
+            std::vector<std::thread> th;
+            for (unsigned t = 0; t < std::min<size_t>(n_thr, n_jobs); t++) th.emplace_back(body);
+            for (auto &x : th) x.join();
+        }
+    }
+    auto t_copied = now();
     uint64_t words = p3_packed_words(r->seq.size());
     r->packed = (uint64_t *)p3_host_alloc(words * sizeof(uint64_t));
     r->nmask = (uint32_t *)p3_host_alloc(words * sizeof(uint32_t));
@@ -209,8 +321,10 @@ int p3_load_file(const char *path, uint32_t k, p3_reads **out) {
     if (timing) {
         auto t_end = now();
         auto sec = [](auto a, auto b) { return std::chrono::duration<double>(b - a).count(); };
-        fprintf(stderr, "p3_load_file: parse %.3f s, staging alloc %.3f s, pack %.3f s (%zu bytes, %zu reads)\n",
-                sec(t_start, t_parsed), sec(t_parsed, t_alloc), sec(t_alloc, t_end), fv.size, r->off.size() - 1);
+        fprintf(stderr, "p3_load_file: events %.3f s, line loop %.3f s, copy %.3f s, staging alloc %.3f s, pack %.3f s "
+                        "(%zu bytes, %zu reads, %u threads)\n",
+                sec(t_start, t_events), sec(t_events, t_parsed), sec(t_parsed, t_copied), sec(t_copied, t_alloc),
+                sec(t_alloc, t_end), fv.size, r->off.size() - 1, n_thr);
     }
     *out = r;
     return P3_OK;

@@ -113,11 +113,15 @@ def _messy_file(rng, kind, k):
     return data
 
 
+@pytest.mark.parametrize("chunk", [None, 1, 7, 64, 1000])
 @pytest.mark.parametrize("kind", ["fasta", "fastq"])
-def test_load_file_differential(oracle, tmp_path, kind):
-    """p3_load_file (one mmap pass, no per-line strings) against the reference's own LoadFile (when the
-    reference is compiled here) and the oracle's restatement, on 60 messy files per format"""
+def test_load_file_differential(oracle, tmp_path, kind, chunk, monkeypatch):
+    """p3_load_file (parallel over byte chunks of the mapped file) against the reference's own LoadFile
+    (when the reference is compiled here) and the oracle's restatement, on 60 messy files per format;
+    chunk sizes down to ONE byte put a chunk boundary at every possible place of a record"""
     from _checkers import Ref, have_ref
+    if chunk is not None:
+        monkeypatch.setenv("P3_LOAD_CHUNK_BYTES", str(chunk))
     k = 21
     for trial in range(60):
         rng = np.random.default_rng(1000 * (kind == "fastq") + trial)
