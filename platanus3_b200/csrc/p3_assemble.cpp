@@ -683,6 +683,63 @@ void count_node_coverage_host(W &w, const std::string &seq, const std::vector<ui
     }
 }
 
+// The same for string k-mers without O(k) work per base: a 64-bit rolling hash of the forward and of
+// the backward k-mer (polynomial in the 2-bit codes, arithmetic mod 2^64; the backward one slides by
+// multiplying with the inverse of the base) is looked up in the set of node hashes first; only a hit
+// builds the two strings and runs the reference's bookkeeping (nodes are few, so hits are
+// ~nodes x coverage). Equal k-mers have equal hashes, so nothing is missed; a colliding non-node just
+// fails the exact lookups.
+void count_node_coverage_host(WalkerStr &w, const std::string &seq, const std::vector<uint64_t> &off) {
+    const int k = w.k;
+    const uint64_t B = 0x9E3779B97F4A7C15ULL;      // odd: invertible mod 2^64
+    uint64_t Binv = B;                              // Newton iteration for the inverse
+    for (int i = 0; i < 6; i++) Binv *= 2 - B * Binv;
+    uint64_t Bk1 = 1;                               // B^(k-1)
+    for (int i = 0; i < k - 1; i++) Bk1 *= B;
+    auto hash_str = [&](const std::string &s) { uint64_t h = 0; for (char c : s) h = h * B + (uint64_t)fcode((unsigned char)c) + 1; return h; };
+    std::unordered_map<uint64_t, char> node_hash;
+    node_hash.reserve(2 * (w.junctions.size() + w.joints.size()) + 16);
+    for (auto &kv : w.junctions) node_hash.emplace(hash_str(kv.first), 1);
+    for (auto &kv : w.joints) node_hash.emplace(hash_str(kv.first), 1);
+    auto add_node = [&](const std::string &km) {   // AddNodeCoverage, :442-449
+        auto j = w.junctions.find(km);
+        if (j != w.junctions.end()) j->second.coverage++;
+        auto t = w.joints.find(km);
+        if (t != w.joints.end()) t->second.coverage++;
+    };
+    for (size_t r = 0; r + 1 < off.size(); r++) {
+        const unsigned char *rd = (const unsigned char *)seq.data() + off[r];
+        const size_t len = (size_t)(off[r + 1] - off[r]);
+        if (len < (size_t)k) continue;
+        auto rdat = [&](size_t i) -> unsigned char { return i < len ? rd[i] : (unsigned char)0; };
+        // digit = code + 1 so that leading 'A's count; fw digits: fcode(read[j]); bw digits: rcode(read[i]) first
+        uint64_t hf = 0, hb = 0;
+        for (int j = 0; j < k; j++) hf = hf * B + (uint64_t)fcode(rd[j]) + 1;
+        for (int j = k - 1; j >= 0; j--) hb = hb * B + (uint64_t)rcode(rd[j]) + 1;
+        for (size_t i = (size_t)k - 1; i < len; i++) {   // k-mer ending at base i
+            if (i >= (size_t)k) {
+                hf = (hf - ((uint64_t)fcode(rd[i - k]) + 1) * Bk1) * B + (uint64_t)fcode(rd[i]) + 1;
+                hb = (hb - ((uint64_t)rcode(rd[i - k]) + 1)) * Binv + ((uint64_t)rcode(rd[i]) + 1) * Bk1;
+            }
+            if (!node_hash.count(hf) && !node_hash.count(hb)) continue;
+            const std::string fw = w.ops.from_read(rd + i + 1 - k), bw = w.ops.from_read_backward(rd + i + 1 - k);
+            add_node(fw); add_node(bw);
+            auto jf = w.junctions.find(fw);
+            auto jb = jf == w.junctions.end() ? w.junctions.find(bw) : w.junctions.end();
+            if (i == (size_t)k - 1) {   // first k-mer of the read (:407-413)
+                if (jf != w.junctions.end()) jf->second.right_cov[fcode(rdat(k))]++;
+                else if (jb != w.junctions.end()) jb->second.left_cov[rcode(rdat(k))]++;
+            } else if (jf != w.junctions.end()) {   // (:424-435)
+                jf->second.left_cov[fcode(rd[i - k])]++;
+                if (i < len - 1) jf->second.right_cov[fcode(rd[i + 1])]++;
+            } else if (jb != w.junctions.end()) {
+                jb->second.right_cov[rcode(rd[i - k])]++;
+                if (i < len - 1) jb->second.left_cov[rcode(rd[i + 1])]++;
+            }
+        }
+    }
+}
+
 // PrintGraph, reference src/DeBruijnGraph.cpp:452-544. The reference iterates unordered_maps, so its
 // line order is unspecified; this writes straights and junctions by id.
 template <class W>
