@@ -367,8 +367,38 @@ inline int fcode(unsigned char c) { return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G
 // base_to_bit[trans_base[c]] of the reference: complement code, 0 for anything that is not ACGT
 inline int rcode(unsigned char c) { return c == 'A' ? 3 : c == 'C' ? 2 : c == 'G' ? 1 : 0; }
 
+// canonical k-mers of every node recorded so far: is_visited (4 map lookups in the reference, :300-315)
+// is one probe here. Flat open addressing for uint64 k-mers, a hash set of strings for long ones.
+struct VisitedU64 {
+    std::vector<uint64_t> keys; uint64_t mask = 0, used = 0;   // ~0 = empty (all-T is never canonical: all-A is smaller)
+    void grow() {
+        uint64_t cap = mask ? (mask + 1) * 2 : (1u << 12);
+        std::vector<uint64_t> nk(cap, ~0ULL);
+        for (uint64_t v : keys) if (v != ~0ULL) { uint64_t s = fmix64(v) & (cap - 1); while (nk[s] != ~0ULL) s = (s + 1) & (cap - 1); nk[s] = v; }
+        keys.swap(nk); mask = cap - 1;
+    }
+    void insert(uint64_t v) {
+        if (!mask || 2 * (used + 1) > mask + 1) grow();
+        uint64_t s = fmix64(v) & mask;
+        while (keys[s] != ~0ULL) { if (keys[s] == v) return; s = (s + 1) & mask; }
+        keys[s] = v; used++;
+    }
+    bool contains(uint64_t v) const {
+        if (!mask) return false;
+        uint64_t s = fmix64(v) & mask;
+        while (keys[s] != ~0ULL) { if (keys[s] == v) return true; s = (s + 1) & mask; }
+        return false;
+    }
+};
+struct VisitedStr {
+    std::unordered_map<std::string, char> m;
+    void insert(const std::string &v) { m.emplace(v, 1); }
+    bool contains(const std::string &v) const { return m.count(v) != 0; }
+};
+
 struct U64Ops {
     using K = uint64_t;
+    using Visited = VisitedU64;
     struct Hash { size_t operator()(uint64_t v) const { return (size_t)fmix64(v); } };
     int k; uint64_t kmask;
     explicit U64Ops(int k_) : k(k_), kmask(k_ >= 32 ? ~0ULL : ((1ULL << (2 * k_)) - 1)) {}
@@ -405,6 +435,7 @@ struct U64Ops {
 
 struct StrOps {
     using K = std::string;
+    using Visited = VisitedStr;
     using Hash = std::hash<std::string>;
     int k;
     explicit StrOps(int k_) : k(k_) {}
@@ -516,8 +547,16 @@ struct Walker {
         if (!adj.find(rc, &a)) missing++;
         return rev8(a);
     }
+    struct Nb {   // at most 4 neighbours on a side: no heap
+        K v[4]; int n = 0;
+        void clear() { n = 0; }
+        void push_back(const K &x) { v[n++] = x; }
+        int size() const { return n; }
+        bool empty() const { return n == 0; }
+        const K &operator[](int i) const { return v[i]; }
+    };
     // CheckDirections, reference src/DeBruijnGraph.cpp:326-345
-    void check_directions(std::vector<K> &left, std::vector<K> &right, const K &km, int ignored) {
+    void check_directions(Nb &left, Nb &right, const K &km, int ignored) {
         left.clear(); right.clear();
         uint8_t a = directions(km);
         for (int i = 0; i < 8; i++) {
@@ -525,17 +564,23 @@ struct Walker {
             (i < 4 ? left : right).push_back(neighbour(km, i));
         }
     }
-    bool is_visited(const K &km) {   // reference src/DeBruijnGraph.cpp:300-315
-        K rc = revcomp(km);
-        return junctions.count(km) || junctions.count(rc) || joints.count(km) || joints.count(rc);
+    // reference src/DeBruijnGraph.cpp:300-315: km or its reverse complement is a junction or a joint.
+    // Every key the two maps ever receive is mirrored (in canonical form) in `visited`.
+    typename O::Visited visited;
+    void mark(const K &km) { K rc = revcomp(km); visited.insert(km <= rc ? km : rc); }
+    bool is_visited(const K &km) const {
+        K rc = ops.revcomp(km);
+        return visited.contains(km <= rc ? km : rc);
     }
     void add_junction(const K &km) {   // :348-357
         if (is_visited(km)) return;
         junctions[km].id = ++junction_id;
+        mark(km);
     }
     void add_joint(const K &km) {      // :360-369
         if (is_visited(km)) return;
         joints[km].id = ++joint_id;
+        mark(km);
     }
     void add_straight(const std::string &seq, const K &lj, const K &rj) {   // :374-391
         if (is_visited(lj)) return;
@@ -545,13 +590,14 @@ struct Walker {
         straights.push_back(s);
         joints[lj].straight = s.id;   // operator[] semantics: the entry exists afterwards even if
         joints[rj].straight = s.id;   // add_joint refused it (reference :385-389)
+        mark(lj); mark(rj);
     }
-    void push_all(const std::vector<K> &l, const std::vector<K> &r) {
-        for (const K &v : l) visiting.push_back(v);
-        for (const K &v : r) visiting.push_back(v);
+    void push_all(const Nb &l, const Nb &r) {
+        for (int i = 0; i < l.size(); i++) visiting.push_back(l[i]);
+        for (int i = 0; i < r.size(); i++) visiting.push_back(r[i]);
     }
     K extend_left(K target, K previous, std::vector<char> &ext, int previous_base) {   // :229-260
-        std::vector<K> l, r;
+        Nb l, r;
         check_directions(l, r, target, 4 + previous_base);
         while (l.size() == 1 && r.empty()) {
             if (is_visited(target)) { ext.clear(); return target; }
@@ -565,7 +611,7 @@ struct Walker {
         return previous;
     }
     K extend_right(K target, K previous, std::vector<char> &ext, int previous_base) {  // :264-297
-        std::vector<K> l, r;
+        Nb l, r;
         check_directions(l, r, target, previous_base);
         while (l.empty() && r.size() == 1) {
             if (is_visited(target)) { ext.clear(); return target; }
@@ -580,7 +626,7 @@ struct Walker {
     }
     void search_node(const K &target) {   // :158-225
         if (is_visited(target)) return;
-        std::vector<K> l, r;
+        Nb l, r;
         check_directions(l, r, target, -1);
         if (l.size() != 1 || r.size() != 1) { push_all(l, r); add_junction(target); return; }
         std::vector<char> ext_l, ext_r;
@@ -909,11 +955,20 @@ int assemble_long(p3_ctx *ctx, p3_reads *rd, uint32_t k, const std::vector<int64
 
 template <class W, class T, class KV>
 int walk_and_print(int k, const T &table, const KV &seeds, uint64_t n_table, const p3_reads *rd, const char *gfa_path, uint64_t *stats) {
+    const bool timing = getenv("P3_LOAD_TIMING") != nullptr;
+    auto t0 = std::chrono::steady_clock::now();
     W w(k, table);
     if (w.make_dbg(seeds, 4 * (n_table + 16)) != 0) { g_host_err = "walk did not terminate"; return P3_ERR_STATE; }
     if (w.missing) { g_host_err = "the adjacency table is not closed: the walk asked for a k-mer it lacks"; return P3_ERR_STATE; }
+    auto t1 = std::chrono::steady_clock::now();
     count_node_coverage_host(w, rd->seq, rd->off);
+    auto t2 = std::chrono::steady_clock::now();
     if (gfa_path && print_graph(w, gfa_path) != P3_OK) { g_host_err = "cannot write GFA"; return P3_ERR_IO; }
+    if (timing) {
+        auto t3 = std::chrono::steady_clock::now();
+        auto sec = [](auto a, auto b) { return std::chrono::duration<double>(b - a).count(); };
+        fprintf(stderr, "p3_walk_table: walk %.3f s, node coverage (host) %.3f s, GFA %.3f s\n", sec(t0, t1), sec(t1, t2), sec(t2, t3));
+    }
     if (stats) { stats[0] = w.junctions.size(); stats[1] = w.joints.size(); stats[2] = w.straights.size(); }
     return P3_OK;
 }
