@@ -37,6 +37,8 @@ CASES = [
     ("k101_m", 101, 300007, 1500, 30, 250, 0.003, "fastq"),
     # 16 words per k-mer; long reads (Assemble.cpp:42)
     ("k501_m", 501, 400009, 3000, 30, 800, 0.002, "fasta"),
+    # the largest k the reference offers: 94 words per k-mer (Assemble.cpp:45)
+    ("k3001_m", 3001, 900001, 9000, 25, 4500, 0.001, "fastq"),
 ]
 
 
@@ -89,9 +91,9 @@ def one_case(ci, name, k, m, genome, cov, rl, err, kind):
         rng = np.random.default_rng(ci)
         probes = []
         for r in loaded[:: max(1, len(loaded) // 40)]:
-            for p in range(0, len(r) - k + 1, 11):
+            for p in range(0, len(r) - k + 1, 11 if k <= 1000 else 401):    # long k-mers: fewer, the fixture stays small
                 probes.append(r[p:p + k].decode())
-        probes += ["".join("ACGT"[i] for i in rng.integers(0, 4, k)) for _ in range(40)]
+        probes += ["".join("ACGT"[i] for i in rng.integers(0, 4, k)) for _ in range(40 if k <= 1000 else 8)]
         probes = [p for p in probes if set(p) <= set("ACGT")]
         masks = np.array([ref.check_directions(p) for p in probes], np.uint8)
         ref.make_dbg()
