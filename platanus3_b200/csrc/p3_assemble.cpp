@@ -568,6 +568,18 @@ struct Walker {
     // Every key the two maps ever receive is mirrored (in canonical form) in `visited`.
     typename O::Visited visited;
     void mark(const K &km) { K rc = revcomp(km); visited.insert(km <= rc ? km : rc); }
+    // k-mers strictly inside a recorded straight. The reference re-walks such a unitig from every
+    // later seed that lies on it (every read has a seed) up to its joint, finds the joint visited and
+    // returns without having changed anything: all k-mers on the way have exactly one neighbour on
+    // each side (which neighbours a k-mer reports depends only on the neighbours' own filter
+    // membership, so this holds in either walking direction) and none of them is a node. Remembering
+    // them turns that walk into one lookup: ~10x fewer steps at 30x coverage, same graph.
+    typename O::Visited covered;
+    std::vector<K> path;            // k-mers passed by the current search_node (both extensions)
+    bool is_covered(const K &km) const {
+        K rc = ops.revcomp(km);
+        return covered.contains(km <= rc ? km : rc);
+    }
     bool is_visited(const K &km) const {
         K rc = ops.revcomp(km);
         return visited.contains(km <= rc ? km : rc);
@@ -601,6 +613,7 @@ struct Walker {
         check_directions(l, r, target, 4 + previous_base);
         while (l.size() == 1 && r.empty()) {
             if (is_visited(target)) { ext.clear(); return target; }
+            path.push_back(target);
             ext.push_back("ACGT"[ops.first(target)]);
             previous_base = ops.last(target);
             previous = target;
@@ -615,6 +628,7 @@ struct Walker {
         check_directions(l, r, target, previous_base);
         while (l.empty() && r.size() == 1) {
             if (is_visited(target)) { ext.clear(); return target; }
+            path.push_back(target);
             ext.push_back("ACGT"[ops.last(target)]);
             previous_base = ops.first(target);
             previous = target;
@@ -626,6 +640,9 @@ struct Walker {
     }
     void search_node(const K &target) {   // :158-225
         if (is_visited(target)) return;
+        if (is_covered(target)) return;   // inside a recorded straight: the reference's walk from here changes nothing
+        path.clear();
+        path.push_back(target);
         Nb l, r;
         check_directions(l, r, target, -1);
         if (l.size() != 1 || r.size() != 1) { push_all(l, r); add_junction(target); return; }
@@ -637,7 +654,14 @@ struct Walker {
         std::string right_part(ext_r.begin(), ext_r.end());
         if (is_visited(right_end)) return;
         if (left_end == right_end) { add_junction(left_end); return; }
-        if (left_part.size() + right_part.size() >= 1) add_straight(left_part + str(target) + right_part, left_end, right_end);
+        if (left_part.size() + right_part.size() >= 1) {
+            add_straight(left_part + str(target) + right_part, left_end, right_end);
+            for (const K &x : path) {          // the straight's k-mers; its two joints are nodes, not interior
+                if (x == left_end || x == right_end) continue;
+                K rc = revcomp(x);
+                covered.insert(x <= rc ? x : rc);
+            }
+        }
     }
     // MakeDBG with threads_num = 1, reference src/DeBruijnGraph.cpp:94-155. seeds sorted ascending
     // (== std::set<std::string> order for ACGT strings of equal length).
