@@ -737,6 +737,9 @@ void count_node_coverage_host(W &w, const std::string &seq, const std::vector<ui
         for (size_t i = k; i < len; i++) {
             fw = w.ops.roll_fw(fw, rd[i]);
             bw = w.ops.roll_bw(bw, rd[i]);
+            // neither k-mer is a node (the common case): one or two probes of the flat visited set
+            // instead of four map lookups. (bw is not always revcomp(fw): a non-ACGT base reads as A on both.)
+            if (!w.is_visited(fw) && !w.is_visited(bw)) continue;
             add_node(fw); add_node(bw);
             auto j1 = w.junctions.find(fw);
             if (j1 != w.junctions.end()) {
