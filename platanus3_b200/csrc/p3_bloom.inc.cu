@@ -134,7 +134,8 @@ bloom_apply_kernel(ApplyRegions rg, uint32_t *__restrict__ seg_words) {
 
 struct BloomBinState {
     uint64_t *d_hh = nullptr; uint64_t cap_hh = 0;
-    uint32_t *d_bins = nullptr; uint64_t cap_bins = 0;
+    uint32_t *d_bins = nullptr; uint64_t cap_bins = 0;     // PEER-SHARED (p3_mg_bloom_buffer): never reallocated here
+    uint32_t *d_local = nullptr; uint64_t cap_local = 0;   // local scratch of the single-context binned paths
     uint32_t **d_segbase = nullptr; uint64_t cap_segbase = 0;
     std::vector<void *> graveyard;   // outgrown peer-shared buffers: freed with the context, never while peers may map them
 };
@@ -142,7 +143,7 @@ static std::unordered_map<p3_ctx *, BloomBinState> g_bbin;
 static void bloom_release(p3_ctx *c) {
     auto it = g_bbin.find(c);
     if (it == g_bbin.end()) return;
-    dfree(it->second.d_hh); dfree(it->second.d_bins); dfree(it->second.d_segbase);
+    dfree(it->second.d_hh); dfree(it->second.d_bins); dfree(it->second.d_local); dfree(it->second.d_segbase);
     for (void *p : it->second.graveyard) cudaFree(p);
     g_bbin.erase(it);
 }
@@ -236,7 +237,7 @@ static int bloom_add_binned(p3_ctx *c, uint64_t n, bool *done) {
     BloomBinState &b = g_bbin[c];
     uint32_t *bins = nullptr;
     if (c->d_bkeys && c->cap_bkeys >= need) bins = reinterpret_cast<uint32_t *>(c->d_bkeys);   // count-stage bins are idle now
-    else { CU(ensure(b.d_bins, b.cap_bins, need)); bins = b.d_bins; }
+    else { CU(ensure(b.d_local, b.cap_local, need)); bins = b.d_local; }
     std::vector<uint64_t> base(n_seg), counts(n_seg);
     for (uint64_t s = 0; s < n_seg; s++) base[s] = (uint64_t)(uintptr_t)(bins + s * cap);
     rc = bloom_bin_launch(c, d_hh, n, (uint32_t)n_seg, shift, base.data(), cap, counts.data());
@@ -375,9 +376,9 @@ static int binned_plane_clear(p3_ctx *c, const uint64_t *cand_slot, const uint64
     else {
         size_t fr = 0, tot = 0;
         CU(cudaMemGetInfo(&fr, &tot));
-        if (b.cap_bins < need && need > (uint64_t)(0.5 * (double)fr)) return P3_OK;
-        CU(ensure(b.d_bins, b.cap_bins, need));
-        bins = b.d_bins;
+        if (b.cap_local < need && need > (uint64_t)(0.5 * (double)fr)) return P3_OK;
+        CU(ensure(b.d_local, b.cap_local, need));
+        bins = b.d_local;
     }
     if (!c->d_ghist) {
         CU(cudaMalloc(&c->d_ghist, sizeof(unsigned long long) * (kMaxParts + 1)));
