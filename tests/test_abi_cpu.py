@@ -73,3 +73,22 @@ def test_no_gpu_fails_loudly():
         pytest.skip("GPU present")
     with pytest.raises(_lib.P3Error):
         _lib.Context(0)
+
+
+def test_binding_example_compiles_against_the_header(tmp_path):
+    """examples/reference_binding.cpp is the stub of INTEGRATION.md as a real program: it must build
+    with nothing but include/platanus3_b200.h and the shared library, and on a box without a GPU it must
+    stop at p3_create with the 'no CPU fallback' message (not crash, not produce a graph)"""
+    import subprocess
+    exe = str(tmp_path / "reference_binding")
+    pkg = os.path.join(ROOT, "platanus3_b200")
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "examples", "reference_binding.cpp"), "-o", exe,
+                        "-L" + pkg, "-lplatanus3_b200", "-Wl,-rpath," + pkg], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    if _lib.lib().p3_device_count() > 0:
+        return
+    gold = os.path.join(ROOT, "tests", "golden", "k25_err.fasta")
+    r = subprocess.run([exe, gold, "25", str(tmp_path / "x.gfa")], capture_output=True, text=True)
+    assert r.returncode == 1 and "no CPU fallback" in r.stderr
+    assert not os.path.exists(tmp_path / "x.gfa")
