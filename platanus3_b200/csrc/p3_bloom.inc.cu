@@ -139,13 +139,13 @@ struct BloomBinState {
     uint32_t **d_segbase = nullptr; uint64_t cap_segbase = 0;
     std::vector<void *> graveyard;   // outgrown peer-shared buffers: freed with the context, never while peers may map them
 };
-static std::unordered_map<p3_ctx *, BloomBinState> g_bbin;
+static CtxStates<BloomBinState> g_bbin;
 static void bloom_release(p3_ctx *c) {
-    auto it = g_bbin.find(c);
-    if (it == g_bbin.end()) return;
-    dfree(it->second.d_hh); dfree(it->second.d_bins); dfree(it->second.d_local); dfree(it->second.d_segbase);
-    for (void *p : it->second.graveyard) cudaFree(p);
-    g_bbin.erase(it);
+    BloomBinState *b = g_bbin.find(c);
+    if (!b) return;
+    dfree(b->d_hh); dfree(b->d_bins); dfree(b->d_local); dfree(b->d_segbase);
+    for (void *p : b->graveyard) cudaFree(p);
+    g_bbin.erase(c);
 }
 
 static size_t bloom_bin_smem(uint32_t nh, uint32_t P) {
@@ -155,7 +155,7 @@ static size_t bloom_bin_smem(uint32_t nh, uint32_t P) {
 
 // (h1, h2) of the context's current distinct k-mer list (single word or W-word arrays)
 static int bloom_hash_list(p3_ctx *c, uint64_t n, uint64_t **d_hh) {
-    BloomBinState &b = g_bbin[c];
+    BloomBinState &b = g_bbin.get(c);
     CU(ensure(b.d_hh, b.cap_hh, sizeof(uint64_t) * 2 * std::max<uint64_t>(n, 1)));
     if (n) {
         unsigned blocks = (unsigned)((n + 255) / 256);
@@ -173,7 +173,7 @@ static int bloom_hash_list(p3_ctx *c, uint64_t n, uint64_t **d_hh) {
 // the caller falls back to the direct path)
 static int bloom_bin_launch(p3_ctx *c, const uint64_t *d_hh, uint64_t n, uint32_t n_seg, int shift,
                             const uint64_t *h_segbase, uint64_t cap, uint64_t *h_counts) {
-    BloomBinState &b = g_bbin[c];
+    BloomBinState &b = g_bbin.get(c);
     if (!c->d_ghist) {
         CU(cudaMalloc(&c->d_ghist, sizeof(unsigned long long) * (kMaxParts + 1)));
         CU(cudaMalloc(&c->d_cursor, sizeof(unsigned long long) * (kMaxParts + 1)));
@@ -234,7 +234,7 @@ static int bloom_add_binned(p3_ctx *c, uint64_t n, bool *done) {
     const double share = std::min(1.0, (double)(1ull << shift) / (double)c->filter_size);
     const uint64_t cap = (uint64_t)((double)n * c->num_hashes * share * 1.05) + 65536;
     const uint64_t need = sizeof(uint32_t) * cap * n_seg;
-    BloomBinState &b = g_bbin[c];
+    BloomBinState &b = g_bbin.get(c);
     uint32_t *bins = nullptr;
     if (c->d_bkeys && c->cap_bkeys >= need) bins = reinterpret_cast<uint32_t *>(c->d_bkeys);   // count-stage bins are idle now
     else { CU(ensure(b.d_local, b.cap_local, need)); bins = b.d_local; }
@@ -370,7 +370,7 @@ static int binned_plane_clear(p3_ctx *c, const uint64_t *cand_slot, const uint64
     }
     const uint64_t cap = std::min<uint64_t>(1ull << shift, n);      // a segment has 2^shift positions: a hard bound
     const uint64_t need = sizeof(uint32_t) * cap * n_seg;
-    BloomBinState &b = g_bbin[c];
+    BloomBinState &b = g_bbin.get(c);
     uint32_t *bins = nullptr;
     if (c->d_bkeys && c->cap_bkeys >= need) bins = reinterpret_cast<uint32_t *>(c->d_bkeys);   // count-stage bins are idle now
     else {

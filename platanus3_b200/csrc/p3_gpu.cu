@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -867,6 +868,17 @@ struct p3_ctx {
     int grid(int blocks_per_sm = 8) const { return n_sm * blocks_per_sm; }
 };
 
+// Per-context state of the optional paths (multi-GPU, multi-word k, binned Bloom adds) lives beside
+// the context in small registries. A context is used by one host thread at a time, but different
+// threads may create / use / destroy DIFFERENT contexts concurrently, so the registries lock around
+// lookup, insertion and erasure (references to unordered_map elements stay valid across rehashes).
+template <class S> struct CtxStates {
+    std::mutex mu;
+    std::unordered_map<struct p3_ctx *, S> m;
+    S &get(struct p3_ctx *c) { std::lock_guard<std::mutex> g(mu); return m[c]; }
+    S *find(struct p3_ctx *c) { std::lock_guard<std::mutex> g(mu); auto it = m.find(c); return it == m.end() ? nullptr : &it->second; }
+    void erase(struct p3_ctx *c) { std::lock_guard<std::mutex> g(mu); m.erase(c); }
+};
 static void mg_release(struct p3_ctx *c);   // p3_multi.inc.cu
 static void long_release(struct p3_ctx *c); // p3_long.inc.cu
 static void bloom_release(struct p3_ctx *c);                                  // p3_bloom.inc.cu

@@ -284,16 +284,16 @@ adjacency_words_kernel(const uint64_t *__restrict__ words, uint64_t n, LongK L, 
 
 // ---- host side of the long-k path --------------------------------------------------------------------------
 struct LongState { uint64_t *d_words = nullptr; uint64_t cap_words = 0; };
-static std::unordered_map<p3_ctx *, LongState> g_long;
+static CtxStates<LongState> g_long;
 static void long_release(p3_ctx *c) {
-    auto it = g_long.find(c);
-    if (it == g_long.end()) return;
-    dfree(it->second.d_words);
-    g_long.erase(it);
+    LongState *ls = g_long.find(c);
+    if (!ls) return;
+    dfree(ls->d_words);
+    g_long.erase(c);
 }
 
 static int bloom_add_words(p3_ctx *c, const uint64_t *d_words, uint64_t n) {
-    if (d_words == g_long[c].d_words) {   // the context's own k-mer list: binned adds (p3_bloom.inc.cu)
+    if (d_words == g_long.get(c).d_words) {   // the context's own k-mer list: binned adds (p3_bloom.inc.cu)
         bool done = false;
         int rcb = bloom_add_binned(c, n, &done);
         if (rcb || done) return rcb;
@@ -347,7 +347,7 @@ static int make_bf_long(p3_ctx *c, uint32_t k, uint64_t solid_slots) {
         solid_slots = std::max<uint64_t>(solid_slots * 4, 1024);
     }
     uint64_t nd = c->h_stats.n_distinct_solid;
-    LongState &ls = g_long[c];
+    LongState &ls = g_long.get(c);
     CU(ensure(ls.d_words, ls.cap_words, sizeof(uint64_t) * std::max<uint64_t>(nd * L.W, 1)));
     if (nd) {
         materialise_kernel<<<c->grid(), 256, 0, c->stream>>>(st, L, c->d_list, nd, ls.d_words);
@@ -377,7 +377,7 @@ static int adjacency_long(p3_ctx *c, const uint64_t *d_words, uint64_t n, uint8_
     return P3_OK;
 }
 
-static const uint64_t *long_words(p3_ctx *c) { return g_long[c].d_words; }
+static const uint64_t *long_words(p3_ctx *c) { return g_long.get(c).d_words; }
 
 // host-array batch entry points for W-word k-mers: 0 = BF.add, 1 = possiblyContains,
 // 2 = GetDoubleHash_64bit, 3 = CheckDirections

@@ -107,17 +107,17 @@ struct MgState {   // extra per-context state of the multi-GPU path
     cudaStream_t stream2 = nullptr; unsigned long long *d_cursor2 = nullptr;
     bool swapped = false;   // c->d_set/d_list currently hold the OWNED set (p3_mg_owned_end swapped them in)
 };
-static std::unordered_map<p3_ctx *, MgState> g_mg;   // keyed by context (p3_ctx layout stays private to p3_gpu.cu)
+static CtxStates<MgState> g_mg;
 
 static void mg_release(p3_ctx *c) {
-    auto it = g_mg.find(c);
-    if (it == g_mg.end()) return;
-    MgState &m = it->second;
+    MgState *mp = g_mg.find(c);
+    if (!mp) return;
+    MgState &m = *mp;
     dfree(m.d_sing); dfree(m.d_sing2); dfree(m.d_set2); dfree(m.d_list2);
     for (int i = 0; i < 2; i++) { dfree(m.d_rkeys[i]); dfree(m.d_rwords[i]); }
     dfree(m.d_cursor2);
     if (m.stream2) cudaStreamDestroy(m.stream2);
-    g_mg.erase(it);
+    g_mg.erase(c);
 }
 
 static int mg_scan(p3_ctx *c, uint32_t P, uint64_t *h_counts) {
@@ -186,7 +186,7 @@ int p3_mg_owner_scatter_peer(p3_ctx *c, uint32_t n_ranks, uint32_t my_rank, uint
     CU(cudaSetDevice(c->device));
     int rc = mg_hist_buffers(c);
     if (rc) return rc;
-    MgState &m = g_mg[c];
+    MgState &m = g_mg.get(c);
     if (!m.stream2) {
         CU(cudaStreamCreateWithFlags(&m.stream2, cudaStreamNonBlocking));
         CU(cudaMalloc(&m.d_cursor2, sizeof(unsigned long long) * (kMaxParts + 1)));
@@ -216,10 +216,10 @@ int p3_mg_owner_scatter_peer(p3_ctx *c, uint32_t n_ranks, uint32_t my_rank, uint
 // waits for an async p3_mg_owner_scatter_peer of this context
 int p3_mg_scatter_wait(p3_ctx *c) {
     if (!c) return fail(P3_ERR_ARG, "null ctx");
-    auto it = g_mg.find(c);
-    if (it == g_mg.end() || !it->second.stream2) return P3_OK;
+    MgState *mp = g_mg.find(c);
+    if (!mp || !mp->stream2) return P3_OK;
     CU(cudaSetDevice(c->device));
-    CU(cudaStreamSynchronize(it->second.stream2));
+    CU(cudaStreamSynchronize(mp->stream2));
     return P3_OK;
 }
 
@@ -228,7 +228,7 @@ int p3_mg_scatter_wait(p3_ctx *c) {
 int p3_mg_recv_buffers(p3_ctx *c, uint64_t n_records, uint32_t which, uint64_t **d_keys, uint32_t **d_words) {
     if (!c || which > 1) return fail(P3_ERR_ARG, "p3_mg_recv_buffers: null ctx / buffer index > 1");
     CU(cudaSetDevice(c->device));
-    MgState &m = g_mg[c];
+    MgState &m = g_mg.get(c);
     n_records = std::max<uint64_t>(n_records, 1);
     CU(ensure(m.d_rkeys[which], m.cap_rkeys[which], sizeof(uint64_t) * n_records));
     CU(ensure(m.d_rwords[which], m.cap_rwords[which], sizeof(uint32_t) * n_records));
@@ -272,7 +272,7 @@ int p3_mg_count_begin(p3_ctx *c, uint64_t table_slots, uint64_t max_records_per_
     c->binned = true;
     rc = setup_table(c, table_slots);
     if (rc) return rc;
-    MgState &m = g_mg[c];
+    MgState &m = g_mg.get(c);
     m.rec_cap = std::max<uint64_t>(max_records_per_call, 1);
     CU(ensure(c->d_bkeys, c->cap_bkeys, sizeof(uint64_t) * m.rec_cap));
     CU(ensure(c->d_bword, c->cap_bword, sizeof(uint32_t) * m.rec_cap));
@@ -357,7 +357,7 @@ int p3_mg_count_end(p3_ctx *c) {
 int p3_mg_singletons(p3_ctx *c, uint32_t n_ranks, uint64_t *h_counts, const uint64_t **d_pos) {
     if (!c || !c->have_counts) return fail(P3_ERR_STATE, "p3_mg_singletons: no counts");
     CU(cudaSetDevice(c->device));
-    MgState &m = g_mg[c];
+    MgState &m = g_mg.get(c);
     uint64_t nc = c->h_stats.n_cand;
     CU(ensure(m.d_sing, m.cap_sing, sizeof(uint64_t) * std::max<uint64_t>(nc, 1)));
     CU(ensure(m.d_sing2, m.cap_sing2, sizeof(uint64_t) * std::max<uint64_t>(nc, 1)));
@@ -452,7 +452,7 @@ int p3_mg_solid_local(p3_ctx *c, uint32_t k, uint64_t solid_slots, uint64_t *n_a
     CU(cudaSetDevice(c->device));
     c->k = k; c->set_valid = false; c->d_set_b = nullptr; c->nbs_b = 0; c->parts_b = 1;
     {   // give the local-set buffers of the previous run back to their role so that they are reused
-        MgState &m = g_mg[c];
+        MgState &m = g_mg.get(c);
         if (m.swapped) {
             std::swap(c->d_set, m.d_set2); std::swap(c->d_list, m.d_list2); std::swap(c->nbs, m.nbs2); std::swap(c->set_parts, m.parts2);
             c->list_cap = c->nbs * 4;
@@ -470,7 +470,7 @@ int p3_mg_solid_local(p3_ctx *c, uint32_t k, uint64_t solid_slots, uint64_t *n_a
     seeds_kernel<<<c->grid(4), 256, 0, c->stream>>>(c->d_off, c->n_reads, c->d_solid, (int)k, c->d_seed);
     c->launches++;
     CU(cudaStreamSynchronize(c->stream));
-    g_mg[c].n_local = c->h_stats.n_distinct_solid;
+    g_mg.get(c).n_local = c->h_stats.n_distinct_solid;
     c->have_solid = true;
     if (n_adds) *n_adds = c->h_stats.n_adds;
     if (n_local) *n_local = c->h_stats.n_distinct_solid;
@@ -480,7 +480,7 @@ int p3_mg_solid_local(p3_ctx *c, uint32_t k, uint64_t solid_slots, uint64_t *n_a
 int p3_mg_kmer_owner_hist(p3_ctx *c, uint32_t n_ranks, uint64_t *h_counts) {
     if (!c || !c->have_solid) return fail(P3_ERR_STATE, "p3_mg_kmer_owner_hist: run p3_mg_solid_local first");
     CU(cudaSetDevice(c->device));
-    uint64_t n = g_mg[c].n_local;
+    uint64_t n = g_mg.get(c).n_local;
     CU(cudaMemsetAsync(c->d_ghist, 0, sizeof(unsigned long long) * (kMaxParts + 1), c->stream));
     if (n) { hist_rec_kernel<3><<<c->grid(), 256, 0, c->stream>>>(c->d_list, n, n_ranks, c->d_ghist); c->launches++; }
     CU(cudaGetLastError());
@@ -489,7 +489,7 @@ int p3_mg_kmer_owner_hist(p3_ctx *c, uint32_t n_ranks, uint64_t *h_counts) {
 int p3_mg_kmer_owner_scatter(p3_ctx *c, uint32_t n_ranks, uint64_t *d_out) {
     if (!c || !c->have_solid || !d_out) return fail(P3_ERR_STATE, "p3_mg_kmer_owner_scatter: bad state");
     CU(cudaSetDevice(c->device));
-    uint64_t n = g_mg[c].n_local;
+    uint64_t n = g_mg.get(c).n_local;
     if (n) {
         unsigned sblocks = (unsigned)std::min<uint64_t>((n + kTilePos - 1) / kTilePos, (uint64_t)c->n_sm * 3);
         scatter_rec_kernel<3, false><<<sblocks, kScatterThreads, sizeof(ScatterSmem), c->stream>>>(c->d_list, nullptr, n, n_ranks, c->d_cursor, d_out, nullptr);
@@ -503,7 +503,7 @@ int p3_mg_kmer_owner_scatter(p3_ctx *c, uint32_t n_ranks, uint64_t *d_out) {
 int p3_mg_owned_begin(p3_ctx *c, uint64_t owned_slots) {
     if (!c) return fail(P3_ERR_ARG, "null ctx");
     CU(cudaSetDevice(c->device));
-    MgState &m = g_mg[c];
+    MgState &m = g_mg.get(c);
     if (m.swapped) return fail(P3_ERR_STATE, "p3_mg_owned_begin: run p3_mg_solid_local first");
     uint64_t nbs = (std::max<uint64_t>(owned_slots, 1024) + 3) / 4;
     if (!m.d_set2 || m.nbs2 != nbs) {
@@ -523,7 +523,7 @@ int p3_mg_owned_insert(p3_ctx *c, const uint64_t *d_kmers, uint64_t n) {
     if (!c) return fail(P3_ERR_ARG, "null ctx");
     if (n == 0) return P3_OK;
     CU(cudaSetDevice(c->device));
-    MgState &m = g_mg[c];
+    MgState &m = g_mg.get(c);
     KSet owned; owned.slots = m.d_set2; owned.P = 1; owned.nbp = m.nbs2;
     set_insert_list_kernel<<<c->grid(), 256, 0, c->stream>>>(d_kmers, n, owned, c->d_stats);
     c->launches++;
@@ -538,7 +538,7 @@ static int owned_finish(p3_ctx *c, uint32_t k, uint64_t filter_size, uint32_t nu
                         bool do_adds, uint64_t *n_owned) {
     if (!c) return fail(P3_ERR_ARG, "null ctx");
     CU(cudaSetDevice(c->device));
-    MgState &m = g_mg[c];
+    MgState &m = g_mg.get(c);
     if (!m.d_set2) return fail(P3_ERR_STATE, "p3_mg_owned_end: run p3_mg_owned_begin first");
     int rc = alloc_bloom(c, k, filter_size, num_hashes, min_words);
     if (rc) return rc;
@@ -579,7 +579,7 @@ uint64_t p3_bloom_seg_bits(void) { return 1ull << bloom_seg_shift(); }
 int p3_mg_bloom_buffer(p3_ctx *c, uint64_t n_u32, uint32_t **d_buf) {
     if (!c) return fail(P3_ERR_ARG, "null ctx");
     CU(cudaSetDevice(c->device));
-    BloomBinState &b = g_bbin[c];
+    BloomBinState &b = g_bbin.get(c);
     uint64_t need = sizeof(uint32_t) * std::max<uint64_t>(n_u32, 1);
     if (!b.d_bins || b.cap_bins < need) {
         if (b.d_bins) b.graveyard.push_back(b.d_bins);
