@@ -33,7 +33,7 @@ extern "C" {
 #define P3_OK 0
 #define P3_ERR_CUDA (-1)       /* no device / CUDA runtime error */
 #define P3_ERR_ARG (-2)        /* bad argument (unsupported k, null pointer, ...) */
-#define P3_ERR_TABLE_FULL (-3) /* a hash table overflowed its capacity (after auto-grow) */
+#define P3_ERR_TABLE_FULL (-3) /* a hash table / bin overflowed its capacity (the solid set grows by itself, the count table does not) */
 #define P3_ERR_STATE (-4)      /* stage called out of order */
 #define P3_ERR_NOMEM (-5)
 #define P3_ERR_IO (-6)
@@ -150,74 +150,80 @@ int p3_assemble_hot_path(p3_ctx *ctx, const uint64_t *h_packed, uint64_t total_b
                          uint64_t all_bases, uint32_t k, uint64_t filter_size, uint32_t num_hashes,
                          uint64_t table_slots, uint64_t solid_slots);
 
-/* ---- multi-GPU building blocks (one process per GPU; the caller moves the buffers with NCCL) -------
+/* The same, with the results of MakeBF and CheckDirections written to host buffers (pinned for overlap; any may be
+ * NULL): BF::m_bits as p3_bf_export, seed positions as p3_seed_export, the distinct solid k-mers and their adjacency
+ * bytes as p3_dbg_export (cap = capacity in k-mers, *n = their number). The staging is uploaded in pieces while the
+ * binning kernel already works, and filter / seeds / k-mers leave the device while CheckDirections runs. */
+int p3_assemble_hot_path_to_host(p3_ctx *ctx, const uint64_t *h_packed, uint64_t total_bases,
+                                 const uint64_t *h_off, uint64_t n_reads, const uint32_t *h_nmask,
+                                 uint64_t all_bases, uint32_t k, uint64_t filter_size, uint32_t num_hashes,
+                                 uint64_t table_slots, uint64_t solid_slots, uint8_t *h_bits, int64_t *h_seed_pos,
+                                 uint64_t *h_kmers, uint8_t *h_adj, uint64_t cap, uint64_t *n);
+
+/* ---- multi-GPU hot path (one process per GPU; csrc/p3_multi.inc.cu, driver: platanus3_b200/dist.py) ------------
  *
- * Canonical k-mers are hash-partitioned over the ranks: the OWNER of a key counts it / de-duplicates
- * it. Every entry point works on device pointers so that torch.distributed (or NCCL directly) can
- * all-to-all them in place. Order of use: see platanus3_b200/dist.py or csrc/p3_multi.inc.cu.
- * Count record = uint64 [rank:8 @47 | offset-in-word:5 @42 | canonical 21-mer:42] + uint32 word
- * index; position record = uint64 [rank:8 @56 | stream position:56]. */
+ * Canonical k-mers are hash-partitioned over the ranks: the OWNER of a key counts it / de-duplicates it
+ * (BASELINE.json north_star; the reference itself is single-process). Every rank owns one peer-visible arena
+ * (control block + two receive sets of n_ranks regions each). The binning kernels store a destination rank's
+ * records straight into that rank's region over NVLink peer memory (transport 0); transport 1 stages the same
+ * regions locally and leaves the movement to the caller's all-to-all (NCCL). All *_send / *_recv / *_finish
+ * calls only enqueue work on the context's stream; *_end waits and checks. Order of use:
+ *   p3_mg_arena, p3_ipc_export/open, p3_mg_connect                       once (again when set_bytes changes)
+ *   A   p3_mg_count_begin, p3_mg_sync, per chunk: _send, sync, _recv;    p3_mg_count_finish, p3_mg_count_end
+ *   B1  p3_mg_cover_begin, p3_mg_sync, per slice: _send, sync, _recv
+ *   B2  p3_mg_solid_begin, p3_mg_sync, per chunk: _send, sync, _recv;    p3_mg_solid_finish, p3_mg_solid_end
+ *   B3  p3_mg_bloom_bin / _apply (sharded filter, then all-gather the shards) or p3_mg_bloom_direct (then OR-reduce)
+ *   C   p3_dbg_adjacency                                                  (the filter is complete and local)
+ * "sync" = p3_mg_sync for transport 0, the all-to-all of p3_mg_staged_buffers for transport 1.
+ * Count record = uint64 [rank:8 @47 | offset-in-word:5 @42 | canonical 21-mer:42] + uint32 word index; position record
+ * = uint64 [rank:8 @56 | stream position:56]; k-mer record = uint64 canonical k-mer + uint8 adjacency hint (k <= 32). */
 uint32_t p3_owner_of_key(uint64_t key, uint32_t n_ranks);
-/* 21-mer positions of words [w0,w1) per owner rank (h_counts[n_ranks]); then the records themselves,
- * grouped by owner in rank order, into caller buffers of sum(h_counts) entries */
-int p3_mg_owner_hist(p3_ctx *ctx, uint32_t n_ranks, uint64_t w0, uint64_t w1, uint64_t *h_counts);
-int p3_mg_owner_scatter(p3_ctx *ctx, uint32_t n_ranks, uint32_t my_rank, uint64_t w0, uint64_t w1,
-                        uint64_t *d_keys, uint32_t *d_words);
-/* fused bin + exchange: owner j's records are stored straight into keys_base[j] / words_base[j],
- * device addresses (as integers) inside rank j's receive buffer that are mapped into this process
- * over NVLink peer memory, already offset to the region reserved for this source rank (n_ranks <= 16).
- * The caller barriers all ranks before the owners consume their buffers.
- * async != 0: the kernel is left running on the context's second stream (so that it overlaps the
- * insert of the previous chunk); p3_mg_scatter_wait joins it. */
-int p3_mg_owner_scatter_peer(p3_ctx *ctx, uint32_t n_ranks, uint32_t my_rank, uint64_t w0, uint64_t w1,
-                             const uint64_t *keys_base, const uint64_t *words_base, int async);
-int p3_mg_scatter_wait(p3_ctx *ctx);
-/* the receive buffers peers store into (two sets, which = 0/1; grow-only; exported with p3_ipc_export), and CUDA IPC
- * plumbing: a 64-byte handle of a buffer of this process / a mapping of another process's buffer */
-int p3_mg_recv_buffers(p3_ctx *ctx, uint64_t n_records, uint32_t which, uint64_t **d_keys, uint32_t **d_words);
+/* CUDA IPC plumbing: a 64-byte handle of a buffer of this process / a mapping of another process's buffer */
 int p3_ipc_export(const void *d_ptr, uint8_t handle[64]);
 int p3_ipc_open(int device, const uint8_t handle[64], void **d_ptr);
 int p3_ipc_close(int device, void *d_ptr);
-/* owner side of CountShortKmer: table of table_slots 8-byte slots, then any number of record
- * batches (each <= max_records_per_call), then _end */
-int p3_mg_count_begin(p3_ctx *ctx, uint64_t table_slots, uint64_t max_records_per_call);
-int p3_mg_count_records(p3_ctx *ctx, const uint64_t *d_keys, const uint32_t *d_words, uint64_t n);
-int p3_mg_count_end(p3_ctx *ctx);
-/* owned keys with final count < 2: their (rank, position) records grouped by source rank */
-int p3_mg_singletons(p3_ctx *ctx, uint32_t n_ranks, uint64_t *h_counts, const uint64_t **d_pos);
-/* source side of MakeBF's coverage test: plane := valid positions, minus the received positions */
-int p3_mg_cover_begin(p3_ctx *ctx);
-int p3_mg_cover_clear(p3_ctx *ctx, const uint64_t *d_pos, uint64_t n);
-/* fused alternative to p3_mg_singletons + all-to-all + p3_mg_cover_clear: the owner clears the bits
- * of its count-1 keys directly in the source ranks' planes (planes[j] = rank j's p3_mg_cover_plane as
- * mapped into this process; RED.AND over NVLink). Ranks synchronise before and after. */
-int p3_mg_cover_plane(p3_ctx *ctx, uint32_t **d_plane);
-int p3_mg_cover_peer(p3_ctx *ctx, uint32_t n_ranks, const uint64_t *planes);
-/* solid plane, seeds and the locally distinct solid k-mers (solid_slots 0 = auto) */
-int p3_mg_solid_local(p3_ctx *ctx, uint32_t k, uint64_t solid_slots, uint64_t *n_adds, uint64_t *n_local);
-int p3_mg_kmer_owner_hist(p3_ctx *ctx, uint32_t n_ranks, uint64_t *h_counts);
-int p3_mg_kmer_owner_scatter(p3_ctx *ctx, uint32_t n_ranks, uint64_t *d_out);
-/* owner side of MakeBF: de-duplicate received k-mers; _end makes them this context's k-mer list,
- * clears its filter copy and BF.adds them (then OR-reduce the copies, then p3_dbg_adjacency) */
-int p3_mg_owned_begin(p3_ctx *ctx, uint64_t owned_slots);
-int p3_mg_owned_insert(p3_ctx *ctx, const uint64_t *d_kmers, uint64_t n);
-int p3_mg_owned_end(p3_ctx *ctx, uint32_t k, uint64_t filter_size, uint32_t num_hashes, uint64_t *n_owned);
-int p3_mg_filter(p3_ctx *ctx, uint32_t **d_bits, uint64_t *n_words);
-/* Sharded BF.add (reference src/bloomfilter.cpp:69-74) instead of replicated adds + OR-reduce: the
- * filter is cut into segments of p3_bloom_seg_bits() bits, dealt out to the ranks in contiguous
- * shards. p3_mg_owned_list = p3_mg_owned_end without the adds (filter allocation of at least
- * filter_words_cap words, cleared). p3_mg_bloom_bin computes every owned k-mer's num_hashes bit
- * indices once, sorts them by segment and stores segment s's 4-byte in-segment offsets to
- * h_segbase[s] (device addresses, normally inside the shard owner's p3_mg_bloom_buffer mapped over
- * NVLink peer memory; cap records each); h_counts[s] = records written. The owner ORs them in with
- * p3_mg_bloom_apply (h_ptr/h_n: [n_local][n_src] regions), then the shards are all-gathered.
- * p3_mg_bloom_direct is the fallback (adds into the local full copy; OR-reduce afterwards). */
+/* this rank's arena (set_bytes per receive set, the same on every rank; n_ranks <= 16); arena_ptrs[r] = rank r's arena as
+ * mapped into this process. same_stream != 0: all ranks are contexts of one process launching on one stream (tests). */
+int p3_mg_arena(p3_ctx *ctx, uint32_t n_ranks, uint32_t my_rank, uint64_t set_bytes, int transport, void **d_arena);
+int p3_mg_connect(p3_ctx *ctx, const uint64_t *arena_ptrs, int same_stream);
+/* device-side barrier over the peers' control blocks (a one-block kernel on the context's stream; no host wait) */
+int p3_mg_sync(p3_ctx *ctx);
+/* transport 1: the blocks and counts the caller's all-to-all moves for a stage (0 = A, 1 = B1, 2 = B2), see p3_multi.inc.cu */
+int p3_mg_staged_buffers(p3_ctx *ctx, int stage, int set, uint64_t out[8]);
+/* A: ReadFile::CountShortKmer, reference src/Load.cpp:105-127, over all ranks' reads. table_slots: this rank's table;
+ * owner_positions: upper estimate of the 21-mer positions this rank will own; chunk_words / n_chunks: the same on every rank */
+int p3_mg_count_begin(p3_ctx *ctx, uint64_t table_slots, uint64_t owner_positions, uint64_t chunk_words, uint64_t n_chunks);
+int p3_mg_count_send(p3_ctx *ctx, uint64_t chunk);
+int p3_mg_count_recv(p3_ctx *ctx, uint64_t chunk);
+int p3_mg_count_finish(p3_ctx *ctx);
+int p3_mg_count_end(p3_ctx *ctx);   /* then p3_short_kmer_stats / _export / _lookup answer for the OWNED keys */
+/* B1: MakeBF's coverage test, reference src/MakeBloomFilter.cpp:52-58: owners return the positions of keys whose count
+ * stayed below cov_threshold, in *n_slices rounds (owner_distinct: the largest n_distinct of any rank) */
+int p3_mg_cover_begin(p3_ctx *ctx, uint32_t cov_threshold, uint64_t owner_distinct, uint32_t *n_slices);
+int p3_mg_cover_send(p3_ctx *ctx, uint32_t cov_threshold, uint32_t slice);
+int p3_mg_cover_recv(p3_ctx *ctx, uint32_t slice);
+/* B2: MakeBF's RMQ test, seeds and solid k-mers (reference src/MakeBloomFilter.cpp:60-83); owned_slots: capacity of this
+ * rank's set of owned distinct solid k-mers. p3_mg_solid_end leaves an empty filter of >= filter_words_cap words. */
+int p3_mg_solid_begin(p3_ctx *ctx, uint32_t k, uint64_t owned_slots);
+int p3_mg_solid_send(p3_ctx *ctx, uint64_t chunk);
+int p3_mg_solid_recv(p3_ctx *ctx, uint64_t chunk);
+int p3_mg_solid_finish(p3_ctx *ctx);
+int p3_mg_solid_end(p3_ctx *ctx, uint64_t filter_size, uint32_t num_hashes, uint64_t filter_words_cap, uint64_t *n_adds, uint64_t *n_owned);
+/* B3: sharded BF.add (reference src/bloomfilter.cpp:69-74): the filter is cut into segments of p3_bloom_seg_bits() bits,
+ * dealt out to the ranks in contiguous shards. p3_mg_bloom_bin computes every owned k-mer's num_hashes bit indices once,
+ * sorts them by segment and stores segment s's 4-byte in-segment offsets to h_segbase[s] (device addresses, normally
+ * inside the shard owner's p3_mg_bloom_buffer mapped over NVLink peer memory; cap records each); h_counts[s] = records
+ * written. The owner ORs them in with p3_mg_bloom_apply (h_ptr/h_n: [n_local][n_src] regions), then the shards are
+ * all-gathered. p3_mg_bloom_direct is the fallback (adds into the local full copy; OR-reduce afterwards). */
 uint64_t p3_bloom_seg_bits(void);
-int p3_mg_owned_list(p3_ctx *ctx, uint32_t k, uint64_t filter_size, uint32_t num_hashes, uint64_t filter_words_cap, uint64_t *n_owned);
 int p3_mg_bloom_buffer(p3_ctx *ctx, uint64_t n_u32, uint32_t **d_buf);
 int p3_mg_bloom_bin(p3_ctx *ctx, uint32_t n_seg, const uint64_t *h_segbase, uint64_t cap, uint64_t *h_counts);
 int p3_mg_bloom_apply(p3_ctx *ctx, uint64_t seg_first, uint32_t n_local, uint32_t n_src, const uint64_t *h_ptr, const uint64_t *h_n);
 int p3_mg_bloom_direct(p3_ctx *ctx);
+int p3_mg_filter(p3_ctx *ctx, uint32_t **d_bits, uint64_t *n_words);
+int p3_mg_makebf_done(p3_ctx *ctx);
+/* device memory in use on the context's GPU (total - free), for the benchmark's hbm_peak_bytes */
+uint64_t p3_device_mem_used(p3_ctx *ctx);
 
 /* ---- host side of the drop-in (row f: callers / formats either side of the path) ------------- */
 

@@ -20,14 +20,15 @@ SYMBOLS = [
     "p3_short_kmer_export", "p3_short_kmer_lookup", "p3_make_bf", "p3_make_bf_stats", "p3_bf_export",
     "p3_bf_import", "p3_seed_export", "p3_solid_flags_export", "p3_bf_add", "p3_bf_possibly_contains",
     "p3_double_hash", "p3_dbg_adjacency", "p3_dbg_stats", "p3_dbg_close", "p3_dbg_export", "p3_check_directions",
-    "p3_owner_of_key", "p3_mg_owner_hist", "p3_mg_owner_scatter", "p3_mg_owner_scatter_peer", "p3_mg_scatter_wait", "p3_mg_recv_buffers", "p3_ipc_export", "p3_ipc_open", "p3_ipc_close", "p3_mg_cover_plane", "p3_mg_cover_peer", "p3_mg_count_begin", "p3_mg_count_records",
-    "p3_mg_count_end", "p3_mg_singletons", "p3_mg_cover_begin", "p3_mg_cover_clear", "p3_mg_solid_local",
-    "p3_mg_kmer_owner_hist", "p3_mg_kmer_owner_scatter", "p3_mg_owned_begin", "p3_mg_owned_insert",
-    "p3_mg_owned_end", "p3_mg_filter", "p3_bloom_seg_bits", "p3_mg_owned_list", "p3_mg_bloom_buffer", "p3_mg_bloom_bin",
-    "p3_mg_bloom_apply", "p3_mg_bloom_direct",
+    "p3_owner_of_key", "p3_ipc_export", "p3_ipc_open", "p3_ipc_close", "p3_mg_arena", "p3_mg_connect", "p3_mg_sync",
+    "p3_mg_staged_buffers", "p3_mg_count_begin", "p3_mg_count_send", "p3_mg_count_recv", "p3_mg_count_finish",
+    "p3_mg_count_end", "p3_mg_cover_begin", "p3_mg_cover_send", "p3_mg_cover_recv", "p3_mg_solid_begin",
+    "p3_mg_solid_send", "p3_mg_solid_recv", "p3_mg_solid_finish", "p3_mg_solid_end", "p3_bloom_seg_bits",
+    "p3_mg_bloom_buffer", "p3_mg_bloom_bin", "p3_mg_bloom_apply", "p3_mg_bloom_direct", "p3_mg_filter",
+    "p3_mg_makebf_done", "p3_device_mem_used",
     "p3_load_file", "p3_reads_free", "p3_reads_count", "p3_reads_all_bases", "p3_reads_total_bases",
     "p3_reads_offsets", "p3_reads_packed", "p3_reads_nmask", "p3_reads_ascii", "p3_assemble_file", "p3_walk_table", "p3_node_coverage",
-    "p3_assemble_hot_path", "p3_stage_ms", "p3_count_substage_ms", "p3_launch_count", "p3_bf_params",
+    "p3_assemble_hot_path", "p3_assemble_hot_path_to_host", "p3_stage_ms", "p3_count_substage_ms", "p3_launch_count", "p3_bf_params",
 ]
 
 
@@ -82,38 +83,39 @@ def lib():
         L.p3_dbg_export.argtypes = [vp, vp, vp, u64, C.POINTER(u64)]
         L.p3_check_directions.argtypes = [vp, vp, u64, vp]
         L.p3_assemble_hot_path.argtypes = [vp, vp, u64, vp, u64, vp, u64, u32, u64, u32, u64, u64]
+        L.p3_assemble_hot_path_to_host.argtypes = [vp, vp, u64, vp, u64, vp, u64, u32, u64, u32, u64, u64, vp, vp, vp, vp, u64, C.POINTER(u64)]
         L.p3_owner_of_key.restype = u32
         L.p3_owner_of_key.argtypes = [u64, u32]
-        L.p3_mg_owner_hist.argtypes = [vp, u32, u64, u64, vp]
-        L.p3_mg_owner_scatter.argtypes = [vp, u32, u32, u64, u64, vp, vp]
-        L.p3_mg_owner_scatter_peer.argtypes = [vp, u32, u32, u64, u64, vp, vp, i32]
-        L.p3_mg_scatter_wait.argtypes = [vp]
-        L.p3_mg_recv_buffers.argtypes = [vp, u64, u32, C.POINTER(vp), C.POINTER(vp)]
         L.p3_ipc_export.argtypes = [vp, vp]
         L.p3_ipc_open.argtypes = [C.c_int, vp, C.POINTER(vp)]
         L.p3_ipc_close.argtypes = [C.c_int, vp]
-        L.p3_mg_cover_plane.argtypes = [vp, C.POINTER(vp)]
-        L.p3_mg_cover_peer.argtypes = [vp, u32, vp]
-        L.p3_mg_count_begin.argtypes = [vp, u64, u64]
-        L.p3_mg_count_records.argtypes = [vp, vp, vp, u64]
+        L.p3_mg_arena.argtypes = [vp, u32, u32, u64, i32, C.POINTER(vp)]
+        L.p3_mg_connect.argtypes = [vp, vp, i32]
+        L.p3_mg_sync.argtypes = [vp]
+        L.p3_mg_staged_buffers.argtypes = [vp, i32, i32, vp]
+        L.p3_mg_count_begin.argtypes = [vp, u64, u64, u64, u64]
+        L.p3_mg_count_send.argtypes = [vp, u64]
+        L.p3_mg_count_recv.argtypes = [vp, u64]
+        L.p3_mg_count_finish.argtypes = [vp]
         L.p3_mg_count_end.argtypes = [vp]
-        L.p3_mg_singletons.argtypes = [vp, u32, vp, C.POINTER(vp)]
-        L.p3_mg_cover_begin.argtypes = [vp]
-        L.p3_mg_cover_clear.argtypes = [vp, vp, u64]
-        L.p3_mg_solid_local.argtypes = [vp, u32, u64, C.POINTER(u64), C.POINTER(u64)]
-        L.p3_mg_kmer_owner_hist.argtypes = [vp, u32, vp]
-        L.p3_mg_kmer_owner_scatter.argtypes = [vp, u32, vp]
-        L.p3_mg_owned_begin.argtypes = [vp, u64]
-        L.p3_mg_owned_insert.argtypes = [vp, vp, u64]
-        L.p3_mg_owned_end.argtypes = [vp, u32, u64, u32, C.POINTER(u64)]
+        L.p3_mg_cover_begin.argtypes = [vp, u32, u64, C.POINTER(u32)]
+        L.p3_mg_cover_send.argtypes = [vp, u32, u32]
+        L.p3_mg_cover_recv.argtypes = [vp, u32]
+        L.p3_mg_solid_begin.argtypes = [vp, u32, u64]
+        L.p3_mg_solid_send.argtypes = [vp, u64]
+        L.p3_mg_solid_recv.argtypes = [vp, u64]
+        L.p3_mg_solid_finish.argtypes = [vp]
+        L.p3_mg_solid_end.argtypes = [vp, u64, u32, u64, C.POINTER(u64), C.POINTER(u64)]
         L.p3_mg_filter.argtypes = [vp, C.POINTER(vp), C.POINTER(u64)]
         L.p3_bloom_seg_bits.restype = u64
         L.p3_bloom_seg_bits.argtypes = []
-        L.p3_mg_owned_list.argtypes = [vp, u32, u64, u32, u64, C.POINTER(u64)]
         L.p3_mg_bloom_buffer.argtypes = [vp, u64, C.POINTER(vp)]
         L.p3_mg_bloom_bin.argtypes = [vp, u32, vp, u64, vp]
         L.p3_mg_bloom_apply.argtypes = [vp, u64, u32, u32, vp, vp]
         L.p3_mg_bloom_direct.argtypes = [vp]
+        L.p3_mg_makebf_done.argtypes = [vp]
+        L.p3_device_mem_used.restype = u64
+        L.p3_device_mem_used.argtypes = [vp]
         L.p3_load_file.argtypes = [C.c_char_p, u32, C.POINTER(vp)]
         L.p3_reads_free.argtypes = [vp]
         for nm in ("p3_reads_count", "p3_reads_all_bases", "p3_reads_total_bases"):

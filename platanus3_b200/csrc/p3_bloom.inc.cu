@@ -35,7 +35,7 @@ static int bloom_seg_shift() {
 // records of segment s go (may be peer memory); cursor[s] = records written so far (starts at 0)
 __global__ void __launch_bounds__(kBinThreads)
 bloom_bin_kernel(const uint64_t *__restrict__ hh, uint64_t n, FastMod fm, uint64_t wrap, int nh, int shift, uint32_t P,
-                 uint32_t *const *__restrict__ seg_base, unsigned long long *cursor, uint64_t cap) {
+                 uint32_t *const *__restrict__ seg_base, unsigned long long *cursor, uint64_t cap, Stats *st) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t T = kBinThreads * kBinKpt * (uint32_t)nh;
     uint32_t *s_rec = reinterpret_cast<uint32_t *>(smem_raw);
@@ -109,7 +109,8 @@ bloom_bin_kernel(const uint64_t *__restrict__ hh, uint64_t n, FastMod fm, uint64
         for (uint32_t i = tid; i < total; i += kBinThreads) {
             uint32_t sg = s_seg[i];
             unsigned long long dst = s_gbase[sg] + (i - s_offs[sg]);
-            if (dst < cap) seg_base[sg][dst] = s_rec[i];   // overflow is detected on the host from the cursors
+            if (dst < cap) seg_base[sg][dst] = s_rec[i];   // overflow: flagged here, and visible in the cursors
+            else atomicExch(&st->err_bin_overflow, 1u);
         }
         __syncthreads();
     }
@@ -132,11 +133,45 @@ bloom_apply_kernel(ApplyRegions rg, uint32_t *__restrict__ seg_words) {
     }
 }
 
+// All segments in ONE launch: the [n_seg x cap] bin space is handed out in chunks from a global
+// counter (like insert_bins), so the chunks in flight lie in one or two neighbouring segments and
+// their 16 MB windows stay in L2; the per-segment record counts are read from the device cursors
+// (no host round trip between binning and applying). CLEAR = false: RED.OR of filter bits
+// (bit i = word i>>5 bit i&31); CLEAR = true: RED.AND of plane bits (0x80000000 >> (p & 31)).
+template <bool CLEAR>
+__global__ void __launch_bounds__(256)
+apply_bins_kernel(const uint32_t *__restrict__ bins, uint64_t cap, const unsigned long long *__restrict__ count, uint32_t n_seg,
+                  int shift, uint32_t *__restrict__ target, Stats *st) {
+    __shared__ unsigned long long s_base;
+    const uint64_t n = (uint64_t)n_seg * cap;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_base = atomicAdd(&st->work, (unsigned long long)kSweepChunk);
+        __syncthreads();
+        const uint64_t cbase = s_base;
+        if (cbase >= n) break;
+        const uint64_t sg = cbase / cap;
+        const uint64_t lim = sg * cap + min((uint64_t)__ldg(count + sg), cap);
+        if (cbase >= lim) continue;
+        uint32_t *seg_words = target + (sg << (shift - 5));
+#pragma unroll
+        for (int it = 0; it < kSweepPer; it++) {
+            const uint64_t i = cbase + it * 256 + threadIdx.x;
+            if (i < lim) {
+                const uint32_t off = __ldcs(bins + i);
+                if (CLEAR) atomicAnd(seg_words + (off >> 5), ~(0x80000000u >> (off & 31)));
+                else atomicOr(seg_words + (off >> 5), 1u << (off & 31));
+            }
+        }
+    }
+}
+
 struct BloomBinState {
     uint64_t *d_hh = nullptr; uint64_t cap_hh = 0;
     uint32_t *d_bins = nullptr; uint64_t cap_bins = 0;     // PEER-SHARED (p3_mg_bloom_buffer): never reallocated here
     uint32_t *d_local = nullptr; uint64_t cap_local = 0;   // local scratch of the single-context binned paths
     uint32_t **d_segbase = nullptr; uint64_t cap_segbase = 0;
+    size_t smem_set = 0, smem_pos[2] = {0, 0};   // dynamic shared memory opted into so far (per context = per device)
     std::vector<void *> graveyard;   // outgrown peer-shared buffers: freed with the context, never while peers may map them
 };
 static CtxStates<BloomBinState> g_bbin;
@@ -174,29 +209,32 @@ static int bloom_hash_list(p3_ctx *c, uint64_t n, uint64_t **d_hh) {
 static int bloom_bin_launch(p3_ctx *c, const uint64_t *d_hh, uint64_t n, uint32_t n_seg, int shift,
                             const uint64_t *h_segbase, uint64_t cap, uint64_t *h_counts) {
     BloomBinState &b = g_bbin.get(c);
-    if (!c->d_ghist) {
-        CU(cudaMalloc(&c->d_ghist, sizeof(unsigned long long) * (kMaxParts + 1)));
-        CU(cudaMalloc(&c->d_cursor, sizeof(unsigned long long) * (kMaxParts + 1)));
-    }
+    int rc0 = hist_buffers(c);
+    if (rc0) return rc0;
     CU(ensure(b.d_segbase, b.cap_segbase, sizeof(uint32_t *) * kMaxParts));
     CU(cudaMemcpyAsync(b.d_segbase, h_segbase, sizeof(uint64_t) * n_seg, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemsetAsync(c->d_cursor, 0, sizeof(unsigned long long) * (kMaxParts + 1), c->stream));
     const size_t smem = bloom_bin_smem(c->num_hashes, n_seg);
-    CU(cudaFuncSetAttribute(bloom_bin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > b.smem_set) {
+        CU(cudaFuncSetAttribute(bloom_bin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        b.smem_set = smem;
+    }
     if (n) {
         const uint64_t tile_k = (uint64_t)kBinThreads * kBinKpt;
         unsigned blocks = (unsigned)std::min<uint64_t>((n + tile_k - 1) / tile_k, (uint64_t)c->n_sm * 2);
         FastMod fm = make_fastmod(c->filter_size);
         uint64_t wrap = ((~0ULL % c->filter_size) + 1) % c->filter_size;
         bloom_bin_kernel<<<blocks, kBinThreads, smem, c->stream>>>(d_hh, n, fm, wrap, (int)c->num_hashes, shift, n_seg,
-                                                                   b.d_segbase, c->d_cursor, cap);
+                                                                   b.d_segbase, c->d_cursor, cap, c->d_stats);
         c->launches++;
         CU(cudaGetLastError());
     }
-    std::vector<unsigned long long> h(n_seg);
-    CU(cudaMemcpyAsync(h.data(), c->d_cursor, sizeof(unsigned long long) * n_seg, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-    for (uint32_t i = 0; i < n_seg; i++) h_counts[i] = h[i];
+    if (h_counts) {   // multi-GPU: the caller routes the per-segment counts to the shard owners
+        std::vector<unsigned long long> h(n_seg);
+        CU(cudaMemcpyAsync(h.data(), c->d_cursor, sizeof(unsigned long long) * n_seg, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        for (uint32_t i = 0; i < n_seg; i++) h_counts[i] = h[i];
+    }
     return P3_OK;
 }
 
@@ -230,43 +268,73 @@ static int bloom_add_binned(p3_ctx *c, uint64_t n, bool *done) {
     if (rc) return rc;
     // hashed indices are uniform over the filter: a FULL segment receives n * num_hashes * seg_bits /
     // filter_size of them (the last segment is usually partial, so this is more than 1 / n_seg);
-    // 5 % + 64 K slack
+    // 5 % + 64 K slack, rounded to the sweep chunk
     const double share = std::min(1.0, (double)(1ull << shift) / (double)c->filter_size);
-    const uint64_t cap = (uint64_t)((double)n * c->num_hashes * share * 1.05) + 65536;
+    uint64_t cap = (uint64_t)((double)n * c->num_hashes * share * 1.05) + 65536;
+    cap = (cap + kSweepChunk - 1) / kSweepChunk * kSweepChunk;
     const uint64_t need = sizeof(uint32_t) * cap * n_seg;
     BloomBinState &b = g_bbin.get(c);
     uint32_t *bins = nullptr;
-    if (c->d_bkeys && c->cap_bkeys >= need) bins = reinterpret_cast<uint32_t *>(c->d_bkeys);   // count-stage bins are idle now
+    if (b.d_local && b.cap_local >= need) bins = b.d_local;
+    else if (c->d_bkeys && c->cap_bkeys >= need) { bins = reinterpret_cast<uint32_t *>(c->d_bkeys); c->bins_valid = false; }   // count-stage bins are idle now
     else { CU(ensure(b.d_local, b.cap_local, need)); bins = b.d_local; }
-    std::vector<uint64_t> base(n_seg), counts(n_seg);
+    std::vector<uint64_t> base(n_seg);
     for (uint64_t s = 0; s < n_seg; s++) base[s] = (uint64_t)(uintptr_t)(bins + s * cap);
-    rc = bloom_bin_launch(c, d_hh, n, (uint32_t)n_seg, shift, base.data(), cap, counts.data());
+    rc = bloom_bin_launch(c, d_hh, n, (uint32_t)n_seg, shift, base.data(), cap, nullptr);
     if (rc) return rc;
-    for (uint64_t s = 0; s < n_seg; s++) if (counts[s] > cap) return P3_OK;   // direct path instead
-    for (uint64_t s = 0; s < n_seg; s++) {
-        ApplyRegions rg; rg.count = 1; rg.ptr[0] = bins + s * cap; rg.n[0] = counts[s];
-        rc = bloom_apply_launch(c, s, shift, rg);
-        if (rc) return rc;
-    }
+    // an overflowing segment (impossible for uniform hashes within the slack) raises err_bin_overflow; the
+    // records that fit are applied anyway (OR is idempotent) and p3_make_bf re-adds directly when it sees the flag
+    CU(cudaMemsetAsync(&c->d_stats->work, 0, sizeof(unsigned long long), c->stream));
+    apply_bins_kernel<false><<<c->grid(), 256, 0, c->stream>>>(bins, cap, c->d_cursor, (uint32_t)n_seg, shift, c->d_bloom, c->d_stats);
+    c->launches++;
+    CU(cudaGetLastError());
     *done = true;
     return P3_OK;
 }
 
 // ---- binned coverage-bit clears --------------------------------------------------------------------
-// MakeBF's coverage test (reference src/MakeBloomFilter.cpp:52-58) clears one bit per count-1 key:
-// ~1.05 G single-bit RED.ANDs at random positions of a 0.54 GB plane at configs[1], 21.8 G/s from DRAM.
-// Same cure as for BF.add: the positions are tile-sorted by plane segment (2^27 positions = 16 MB) and
-// applied segment by segment with the window L2 resident. A segment can never receive more records
-// than it has positions, so the bins have a hard upper bound and need neither a histogram nor an
-// overflow path.
+// MakeBF's coverage test (reference src/MakeBloomFilter.cpp:52-58) clears one bit per occurrence of a key
+// whose count stayed below the threshold: ~0.75 G single-bit RED.ANDs at random positions of a 0.54 GB
+// plane at configs[1], 21.8 G/s from DRAM. Same cure as for BF.add: the positions are tile-sorted by plane
+// segment (2^27 positions = 16 MB) and applied segment by segment with the window L2 resident. The bins
+// have a fixed capacity (the expected share of a segment + 10 % + slack: error k-mers are spread evenly
+// over the reads); a segment that overflows raises err_bin_overflow and the caller clears directly.
 constexpr int kPosKpt = 8;   // inputs per thread per tile
-// MODE 0: candidates (slot, position) of the binned count — emitted when the key's final count < thr
-// MODE 1: a plain list of position records
+
+// KC[key] < thr, the first bucket of the probe sequence already loaded (see count_insert_pre)
+__device__ __forceinline__ bool count_below_pre(const Table &t, uint64_t key, uint64_t base, uint64_t b, uint64_t s[4],
+                                                uint64_t thr, const Ovf &ovf, unsigned n_overflow) {
+    for (uint64_t probe = 0; probe < t.nbp; probe++) {
+        if (probe) ld_bucket(t.slots + 4 * (base + b), s);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            uint64_t v = s[i];
+            if ((v & kKey42) == key) {
+                uint64_t c = v >> 42;
+                if (c < thr && n_overflow) c += ovf_get(ovf, key) << 22;
+                return c < thr;
+            }
+            if (v == kEmpty) return true;   // absent: count 0
+        }
+        b = (b + 1 == t.nbp) ? 0 : b + 1;
+    }
+    return true;
+}
+
+// MODE 0: the verdict sweep — the input is the partition bins of the count (records + word indices, laid
+//         out as in_cap-sized bins ending at in_end[p], or contiguous when in_cap == 0); every record whose
+//         key's final count < thr emits its position. Tiles are handed out from a global counter so that
+//         the grid stays inside one or two table partitions (L2 resident), like insert_bins.
+//         out_list != nullptr: no tile sort; the position records (with their rank byte) are appended to
+//         out_list instead (multi-GPU owner: they go back to their source ranks).
+// MODE 1: a plain list of position records, or (in_cap > 0) a row of regions of in_cap records holding
+//         in_end[r] records each (received from the owner ranks)
 template <int MODE>
 __global__ void __launch_bounds__(kBinThreads)
-pos_bin_kernel(const uint64_t *__restrict__ slots, const uint64_t *__restrict__ cand_slot, const uint64_t *__restrict__ pos_in,
-               uint64_t n, uint64_t thr, Ovf ovf, const Stats *st, int shift, uint32_t P, uint32_t *__restrict__ bins,
-               uint64_t cap, unsigned long long *cursor) {
+pos_bin_kernel(Table table, const uint64_t *__restrict__ in, const uint32_t *__restrict__ in_word,
+               uint64_t n, uint64_t in_cap, const unsigned long long *__restrict__ in_end, const unsigned long long *__restrict__ n_dev,
+               uint64_t thr, Ovf ovf, Stats *st, int shift, uint32_t P, uint32_t *__restrict__ bins,
+               uint64_t cap, unsigned long long *cursor, uint64_t *__restrict__ out_list) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr uint32_t T = kBinThreads * kPosKpt;
     uint32_t *s_rec = reinterpret_cast<uint32_t *>(smem_raw);
@@ -277,133 +345,250 @@ pos_bin_kernel(const uint64_t *__restrict__ slots, const uint64_t *__restrict__ 
     uint16_t *s_seg = reinterpret_cast<uint16_t *>(s_cur + P);
     __shared__ uint32_t s_wtot[kBinThreads / 32];
     __shared__ uint32_t s_total;
+    __shared__ unsigned long long s_tile, s_lbase;
     const int tid = threadIdx.x;
     const unsigned n_overflow = MODE == 0 ? st->n_overflow : 0u;
     const uint64_t pmask = (1ULL << kPosRankShift) - 1, smask = (1ULL << shift) - 1;
-    const uint64_t n_tiles = (n + T - 1) / T;
-    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        for (uint32_t i = tid; i < P; i += kBinThreads) s_hist[i] = 0;
-        __syncthreads();
-        uint64_t pos[kPosKpt];
-#pragma unroll
-        for (int q = 0; q < kPosKpt; q++) {
-            const uint64_t i = tile * T + (uint64_t)q * kBinThreads + tid;
-            pos[q] = ~0ULL;
-            if (i < n) {
-                if (MODE == 0) {
-                    uint64_t v = __ldcg(slots + __ldcs(cand_slot + i));
-                    uint64_t c = v >> 42;
-                    if (c < thr && n_overflow) c += ovf_get(ovf, v & kKey42) << 22;
-                    if (c < thr) pos[q] = __ldcs(pos_in + i) & pmask;
-                } else {
-                    pos[q] = __ldcs(pos_in + i) & pmask;
-                }
-            }
-            if (pos[q] != ~0ULL) atomicAdd(&s_hist[(uint32_t)(pos[q] >> shift)], 1u);
-        }
-        __syncthreads();
-        {
-            const uint32_t per = (P + kBinThreads - 1) / kBinThreads;
-            const uint32_t b0 = tid * per;
-            uint32_t local = 0;
-            for (uint32_t j = 0; j < per; j++) if (b0 + j < P) local += s_hist[b0 + j];
-            uint32_t incl = local;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, d); if ((tid & 31) >= d) incl += v; }
-            if ((tid & 31) == 31) s_wtot[tid >> 5] = incl;
+    if (n_dev) n = min(n, (uint64_t)*n_dev);
+    bool over = false;
+    uint64_t t0 = (uint64_t)blockIdx.x * T;
+    for (;;) {
+        if (MODE == 0) {   // dynamic hand-out (L2 residency of the table partition)
             __syncthreads();
-            uint32_t wbase = 0;
-            for (int q = 0; q < (tid >> 5); q++) wbase += s_wtot[q];
-            uint32_t run = wbase + incl - local;
-            for (uint32_t j = 0; j < per; j++) {
-                uint32_t i = b0 + j;
-                if (i < P) {
-                    uint32_t h = s_hist[i];
-                    s_offs[i] = run; s_cur[i] = run;
-                    if (h) s_gbase[i] = atomicAdd(&cursor[i], (unsigned long long)h);
-                    run += h;
+            if (tid == 0) s_tile = atomicAdd(&st->work, (unsigned long long)T);
+            __syncthreads();
+            t0 = s_tile;
+        }
+        if (t0 >= n) break;
+        uint64_t lim = n;
+        if (in_cap) { const uint64_t r = t0 / in_cap; lim = min(n, r * in_cap + min((uint64_t)__ldcg(in_end + r) - (MODE == 0 ? r * in_cap : 0), in_cap)); }
+        if (t0 < lim) {
+            for (uint32_t i = tid; i < P; i += kBinThreads) s_hist[i] = 0;
+            __syncthreads();
+            uint64_t pos[kPosKpt];
+            if (MODE == 0) {
+                uint64_t rec[kPosKpt / 2], s[kPosKpt / 2][4];
+#pragma unroll
+                for (int half = 0; half < 2; half++) {
+#pragma unroll
+                    for (int q = 0; q < kPosKpt / 2; q++) {
+                        const uint64_t i = t0 + (uint64_t)(half * (kPosKpt / 2) + q) * kBinThreads + tid;
+                        rec[q] = i < lim ? __ldcs(in + i) : ~0ULL;
+                        if (rec[q] != ~0ULL) {
+                            const uint64_t h = fmix64(rec[q] & kKey42);
+                            ld_bucket(table.slots + 4 * ((uint64_t)part_of(h, table.P) * table.nbp + sub_of(h, table.nbp)), s[q]);
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < kPosKpt / 2; q++) {
+                        const int qq = half * (kPosKpt / 2) + q;
+                        const uint64_t i = t0 + (uint64_t)qq * kBinThreads + tid;
+                        pos[qq] = ~0ULL;
+                        if (rec[q] != ~0ULL) {
+                            const uint64_t h = fmix64(rec[q] & kKey42);
+                            if (count_below_pre(table, rec[q] & kKey42, (uint64_t)part_of(h, table.P) * table.nbp, sub_of(h, table.nbp), s[q], thr, ovf, n_overflow))
+                                pos[qq] = posrec_of(rec[q], __ldcs(in_word + i));
+                        }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < kPosKpt; q++) {
+                    const uint64_t i = t0 + (uint64_t)q * kBinThreads + tid;
+                    pos[q] = i < lim ? (__ldcs(in + i) & pmask) : ~0ULL;
                 }
             }
-            if (tid == kBinThreads - 1) s_total = wbase + incl;
-        }
-        __syncthreads();
+            if (MODE == 0 && out_list) {   // block-level compaction into the list (one global atomic per tile)
+                unsigned mine = 0;
 #pragma unroll
-        for (int q = 0; q < kPosKpt; q++) {
-            if (pos[q] != ~0ULL) {
-                uint32_t sg = (uint32_t)(pos[q] >> shift);
-                uint32_t idx = atomicAdd(&s_cur[sg], 1u);
-                s_rec[idx] = (uint32_t)(pos[q] & smask);
-                s_seg[idx] = (uint16_t)sg;
+                for (int q = 0; q < kPosKpt; q++) mine += pos[q] != ~0ULL;
+                unsigned incl = mine;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { unsigned v = __shfl_up_sync(0xffffffffu, incl, d); if ((tid & 31) >= d) incl += v; }
+                if ((tid & 31) == 31) s_wtot[tid >> 5] = incl;
+                __syncthreads();
+                unsigned wbase = 0, total = 0;
+#pragma unroll
+                for (int q = 0; q < kBinThreads / 32; q++) { unsigned t = s_wtot[q]; if (q < (tid >> 5)) wbase += t; total += t; }
+                if (tid == 0 && total) s_lbase = atomicAdd(&st->n_export, (unsigned long long)total);
+                __syncthreads();
+                unsigned long long j = s_lbase + wbase + incl - mine;
+#pragma unroll
+                for (int q = 0; q < kPosKpt; q++) if (pos[q] != ~0ULL) { if (j < cap) out_list[j] = pos[q]; else over = true; j++; }
+            } else {
+#pragma unroll
+                for (int q = 0; q < kPosKpt; q++) {
+                    if (pos[q] != ~0ULL) { pos[q] &= pmask; atomicAdd(&s_hist[(uint32_t)(pos[q] >> shift)], 1u); }
+                }
+                __syncthreads();
+                {
+                    const uint32_t per = (P + kBinThreads - 1) / kBinThreads;
+                    const uint32_t b0 = tid * per;
+                    uint32_t local = 0;
+                    for (uint32_t j = 0; j < per; j++) if (b0 + j < P) local += s_hist[b0 + j];
+                    uint32_t incl = local;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, d); if ((tid & 31) >= d) incl += v; }
+                    if ((tid & 31) == 31) s_wtot[tid >> 5] = incl;
+                    __syncthreads();
+                    uint32_t wbase = 0;
+                    for (int q = 0; q < (tid >> 5); q++) wbase += s_wtot[q];
+                    uint32_t run = wbase + incl - local;
+                    for (uint32_t j = 0; j < per; j++) {
+                        uint32_t i = b0 + j;
+                        if (i < P) {
+                            uint32_t h = s_hist[i];
+                            s_offs[i] = run; s_cur[i] = run;
+                            if (h) s_gbase[i] = atomicAdd(&cursor[i], (unsigned long long)h);
+                            run += h;
+                        }
+                    }
+                    if (tid == kBinThreads - 1) s_total = wbase + incl;
+                }
+                __syncthreads();
+#pragma unroll
+                for (int q = 0; q < kPosKpt; q++) {
+                    if (pos[q] != ~0ULL) {
+                        uint32_t sg = (uint32_t)(pos[q] >> shift);
+                        uint32_t idx = atomicAdd(&s_cur[sg], 1u);
+                        s_rec[idx] = (uint32_t)(pos[q] & smask);
+                        s_seg[idx] = (uint16_t)sg;
+                    }
+                }
+                __syncthreads();
+                const uint32_t total = s_total;
+                for (uint32_t i = tid; i < total; i += kBinThreads) {
+                    uint32_t sg = s_seg[i];
+                    unsigned long long dst = s_gbase[sg] + (i - s_offs[sg]);
+                    if (dst < cap) bins[(uint64_t)sg * cap + dst] = s_rec[i];
+                    else over = true;
+                }
+                __syncthreads();
             }
         }
-        __syncthreads();
-        const uint32_t total = s_total;
-        for (uint32_t i = tid; i < total; i += kBinThreads) {
-            uint32_t sg = s_seg[i];
-            unsigned long long dst = s_gbase[sg] + (i - s_offs[sg]);
-            if (dst < cap) bins[(uint64_t)sg * cap + dst] = s_rec[i];
-        }
-        __syncthreads();
+        if (MODE != 0) { t0 += (uint64_t)gridDim.x * T; }
     }
+    if (over) atomicExch(&st->err_bin_overflow, 1u);
 }
-// RED.AND of one segment's records into its window of a plane whose bit for position p is
-// 0x80000000 >> (p & 31) of word p >> 5 (the layout of the valid / coverage / solid planes)
+
+// direct (un-binned) form of the same two jobs, for small inputs and as the fallback when a segment bin overflows
+template <int MODE>
 __global__ void __launch_bounds__(256)
-plane_clear_kernel(const uint32_t *__restrict__ rec, uint64_t n, uint32_t *__restrict__ seg_words) {
+pos_clear_direct_kernel(Table table, const uint64_t *__restrict__ in, const uint32_t *__restrict__ in_word, uint64_t n,
+                        uint64_t in_cap, const unsigned long long *__restrict__ in_end, const unsigned long long *__restrict__ n_dev,
+                        uint64_t thr, Ovf ovf, const Stats *st, uint32_t *plane) {
+    const unsigned n_overflow = MODE == 0 ? st->n_overflow : 0u;
+    if (n_dev) n = min(n, (uint64_t)*n_dev);
     const uint64_t stride = gridDim.x * (uint64_t)blockDim.x;
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
-        uint32_t off = __ldcs(rec + i);
-        atomicAnd(seg_words + (off >> 5), ~(0x80000000u >> (off & 31)));
+        if (in_cap) {
+            const uint64_t r = i / in_cap;
+            if (i - r * in_cap >= min((uint64_t)__ldcg(in_end + r) - (MODE == 0 ? r * in_cap : 0), in_cap)) continue;
+        }
+        uint64_t pos;
+        if (MODE == 0) {
+            const uint64_t rec = __ldcs(in + i);
+            if (count_lookup(table, rec & kKey42, ovf, n_overflow) >= thr) continue;
+            pos = posrec_of(rec, __ldcs(in_word + i));
+        } else pos = __ldcs(in + i);
+        pos &= (1ULL << kPosRankShift) - 1;
+        atomicAnd(plane + (pos >> 5), ~(0x80000000u >> (pos & 31)));
     }
 }
 
-// clears, in `plane` (n_pos positions), the bit of every emitted position; *done = false when the job is
-// too small to be worth it or the scratch does not fit (the caller then clears directly)
+// the input of a clear job (see pos_bin_kernel)
+struct ClearInput {
+    const uint64_t *rec = nullptr; const uint32_t *word = nullptr;    // MODE 0: count records + word indices; MODE 1: position records
+    uint64_t n = 0;                                                   // inputs (capacity space when in_cap > 0)
+    uint64_t in_cap = 0; const unsigned long long *in_end = nullptr;  // binned / regioned layout
+    const unsigned long long *n_dev = nullptr;                        // contiguous layout with the count on the device
+};
+
+// clears, in `plane` (n_pos positions), the bit of every emitted position; n_expect = how many positions the
+// input is expected to emit at most (sizes the bins). Small jobs, unfitting scratch and P3_DIRECT_CLEARS clear
+// directly. A segment that outgrows its bin raises Stats::err_bin_overflow: the caller checks it at its next
+// stats read and calls again with force_direct (clearing twice is harmless).
 template <int MODE>
-static int binned_plane_clear(p3_ctx *c, const uint64_t *cand_slot, const uint64_t *pos_in, uint64_t n, uint64_t thr,
-                              uint32_t *plane, uint64_t n_pos, bool *done) {
-    *done = false;
+static int plane_clear_job(p3_ctx *c, const ClearInput &in, uint64_t n_expect, uint64_t thr, uint32_t *plane, uint64_t n_pos,
+                           bool force_direct, bool *binned) {
+    if (binned) *binned = false;
+    if (in.n == 0) return P3_OK;
     const int shift = bloom_seg_shift();
     const uint64_t n_seg = (n_pos + (1ull << shift) - 1) >> shift;
-    if (n < (1u << 22) || n_seg < 2 || n_seg > (uint64_t)kMaxParts || getenv("P3_DIRECT_CLEARS")) {
-        if (!(getenv("P3_BINNED_CLEARS") && n && n_seg <= (uint64_t)kMaxParts)) return P3_OK;
-    }
-    const uint64_t cap = std::min<uint64_t>(1ull << shift, n);      // a segment has 2^shift positions: a hard bound
-    const uint64_t need = sizeof(uint32_t) * cap * n_seg;
+    bool want = !force_direct && !getenv("P3_DIRECT_CLEARS") && n_seg <= (uint64_t)kMaxParts &&
+                ((n_expect >= (1u << 22) && n_seg >= 2) || getenv("P3_BINNED_CLEARS"));
     BloomBinState &b = g_bbin.get(c);
-    uint32_t *bins = nullptr;
-    if (c->d_bkeys && c->cap_bkeys >= need) bins = reinterpret_cast<uint32_t *>(c->d_bkeys);   // count-stage bins are idle now
-    else {
-        size_t fr = 0, tot = 0;
-        CU(cudaMemGetInfo(&fr, &tot));
-        if (b.cap_local < need && need > (uint64_t)(0.5 * (double)fr)) return P3_OK;
-        CU(ensure(b.d_local, b.cap_local, need));
-        bins = b.d_local;
+    uint64_t cap = 0;
+    if (want) {
+        // a full segment's expected share of the emitted positions + 10 % + 64 K, never more than it has positions
+        const double share = std::min(1.0, (double)(1ull << shift) / (double)std::max<uint64_t>(n_pos, 1));
+        cap = std::min<uint64_t>(1ull << shift, (uint64_t)((double)n_expect * share * 1.10) + 65536);
+        cap = (cap + kSweepChunk - 1) / kSweepChunk * kSweepChunk;
+        const uint64_t need = sizeof(uint32_t) * cap * n_seg;
+        if (b.cap_local < need) {
+            size_t fr = 0, tot = 0;
+            CU(cudaMemGetInfo(&fr, &tot));
+            if (need > (uint64_t)(0.5 * (double)(fr + b.cap_local))) want = false;
+            else CU(ensure(b.d_local, b.cap_local, need));
+        }
     }
-    if (!c->d_ghist) {
-        CU(cudaMalloc(&c->d_ghist, sizeof(unsigned long long) * (kMaxParts + 1)));
-        CU(cudaMalloc(&c->d_cursor, sizeof(unsigned long long) * (kMaxParts + 1)));
+    int rc0 = hist_buffers(c);
+    if (rc0) return rc0;
+    if (MODE == 0) CU(cudaMemsetAsync(&c->d_stats->work, 0, sizeof(unsigned long long), c->stream));
+    if (!want) {
+        pos_clear_direct_kernel<MODE><<<c->grid(), 256, 0, c->stream>>>(c->table(), in.rec, in.word, in.n, in.in_cap, in.in_end, in.n_dev,
+                                                                       thr, c->ovf(), c->d_stats, plane);
+        c->launches++;
+        CU(cudaGetLastError());
+        return P3_OK;
     }
     CU(cudaMemsetAsync(c->d_cursor, 0, sizeof(unsigned long long) * (kMaxParts + 1), c->stream));
     const size_t smem = (size_t)kBinThreads * kPosKpt * 6 + (size_t)n_seg * 20;
-    CU(cudaFuncSetAttribute(pos_bin_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const uint64_t T = (uint64_t)kBinThreads * kPosKpt;
-    unsigned blocks = (unsigned)std::min<uint64_t>((n + T - 1) / T, (uint64_t)c->n_sm * 8);
-    pos_bin_kernel<MODE><<<blocks, kBinThreads, smem, c->stream>>>(c->d_table, cand_slot, pos_in, n, thr, c->ovf(), c->d_stats, shift,
-                                                                   (uint32_t)n_seg, bins, cap, c->d_cursor);
-    c->launches++;
-    CU(cudaGetLastError());
-    std::vector<unsigned long long> h(n_seg);
-    CU(cudaMemcpyAsync(h.data(), c->d_cursor, sizeof(unsigned long long) * n_seg, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-    for (uint64_t s = 0; s < n_seg; s++) {
-        if (h[s] > cap) return fail(P3_ERR_STATE, "binned_plane_clear: more records than positions in a segment (duplicate positions?)");
-        if (!h[s]) continue;
-        unsigned ab = (unsigned)std::min<uint64_t>((h[s] + 255) / 256, (uint64_t)c->grid());
-        plane_clear_kernel<<<ab, 256, 0, c->stream>>>(bins + s * cap, h[s], plane + (s << (shift - 5)));
-        c->launches++;
+    if (smem > b.smem_pos[MODE]) {
+        CU(cudaFuncSetAttribute(pos_bin_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        b.smem_pos[MODE] = smem;
     }
+    const uint64_t T = (uint64_t)kBinThreads * kPosKpt;
+    unsigned blocks = (unsigned)std::min<uint64_t>((in.n + T - 1) / T, (uint64_t)c->n_sm * (MODE == 0 ? 4 : 8));
+    pos_bin_kernel<MODE><<<blocks, kBinThreads, smem, c->stream>>>(c->table(), in.rec, in.word, in.n, in.in_cap, in.in_end, in.n_dev, thr, c->ovf(),
+                                                                   c->d_stats, shift, (uint32_t)n_seg, b.d_local, cap, c->d_cursor, nullptr);
+    CU(cudaMemsetAsync(&c->d_stats->work, 0, sizeof(unsigned long long), c->stream));
+    apply_bins_kernel<true><<<c->grid(), 256, 0, c->stream>>>(b.d_local, cap, c->d_cursor, (uint32_t)n_seg, shift, plane, c->d_stats);
+    c->launches += 2;
     CU(cudaGetLastError());
-    *done = true;
+    if (binned) *binned = true;
+    return P3_OK;
+}
+
+// MakeBF's coverage flags from the binned count (reference src/MakeBloomFilter.cpp:52-58, any threshold):
+// good21 := valid, then every occurrence of a key whose final count < thr clears its bit. The bins of a
+// one-chunk count are still there; otherwise the reads are binned again chunk by chunk.
+static int verdict_sweep(p3_ctx *c, uint64_t thr, bool force_direct, bool *binned_any) {
+    *binned_any = false;
+    CU(cudaMemcpyAsync(c->d_good21, c->d_valid, sizeof(uint32_t) * c->n_words, cudaMemcpyDeviceToDevice, c->stream));
+    if (!c->h_stats.n_cand) return P3_OK;
+    // occurrences below the threshold: at most (thr - 1) per distinct key, and never more than the positions
+    const uint64_t n_expect = std::min<uint64_t>(c->h_stats.n_pos21, c->h_stats.n_cand * std::max<uint64_t>(thr - 1, 1));
+    auto one = [&](uint64_t share_num, uint64_t share_den) -> int {
+        ClearInput in;
+        in.rec = c->d_bkeys; in.word = c->d_bword; in.n = c->bin_n; in.in_cap = c->bin_cap; in.in_end = c->d_binmeta;
+        in.n_dev = c->bin_cap ? nullptr : c->d_binmeta + kMaxParts;
+        bool b = false;
+        int rc = plane_clear_job<0>(c, in, n_expect / share_den * share_num + (1u << 16), thr, c->d_good21, c->n_words * 32, force_direct, &b);
+        *binned_any = *binned_any || b;
+        return rc;
+    };
+    if (c->bins_valid) return one(1, 1);
+    BinPlan pl;
+    int rc = plan_bins(c, c->bin_upper, c->bin_exact, &pl);
+    if (rc) return rc;
+    const uint64_t n_ch = (c->n_words + pl.chunk_words - 1) / pl.chunk_words;
+    for (uint64_t w0 = 0; w0 < c->n_words; w0 += pl.chunk_words) {
+        const uint64_t w1 = std::min<uint64_t>(w0 + pl.chunk_words, c->n_words);
+        rc = bin_chunk(c, pl, w0, w1, nullptr);
+        if (!rc) rc = one(2, std::max<uint64_t>(n_ch, 1));   // a chunk's share of the clears, with a factor 2 of slack
+        if (rc) return rc;
+    }
+    c->bins_valid = false;
     return P3_OK;
 }

@@ -6,12 +6,16 @@
 //   junction counters: [coverage, left_kmers_cov[4], right_kmers_cov[4]]  (9 per node)
 //   joint counters   : [coverage]
 
-struct NodeTable { const uint64_t *keys; const uint32_t *idx; uint64_t mask; };
+// At k = 32 the all-T k-mer equals the table's empty marker (kEmpty = ~0), and the keys here are
+// ORIENTED k-mers, so it is a legal key (a read with 32 T's forward, 32 A's backward). It never enters
+// the table: its node index travels beside it in `ones_idx` (-1 = no such node).
+struct NodeTable { const uint64_t *keys; const uint32_t *idx; uint64_t mask; int ones_idx; };
 
 __global__ void node_table_build_kernel(const uint64_t *__restrict__ kmers, uint64_t n, uint64_t *keys, uint32_t *idx, uint64_t mask) {
     uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint64_t key = kmers[i];
+    if (key == kEmpty) return;   // kept outside the table (NodeTable::ones_idx)
     uint64_t s = fmix64(key) & mask;
     for (;;) {
         uint64_t old = atomicCAS(ull(keys + s), kEmpty, key);
@@ -20,6 +24,7 @@ __global__ void node_table_build_kernel(const uint64_t *__restrict__ kmers, uint
     }
 }
 __device__ __forceinline__ int node_find(const NodeTable &t, uint64_t key) {
+    if (key == kEmpty) return t.ones_idx;
     if (!t.keys) return -1;
     uint64_t s = fmix64(key) & t.mask;
     for (;;) {
@@ -93,9 +98,10 @@ node_coverage_kernel(const uint64_t *__restrict__ packed, const uint32_t *__rest
     }
 }
 
-static int build_node_table(p3_ctx *c, const uint64_t *h_kmers, uint64_t n, uint64_t **d_keys, uint32_t **d_idx, uint64_t *mask) {
-    *d_keys = nullptr; *d_idx = nullptr; *mask = 0;
+static int build_node_table(p3_ctx *c, const uint64_t *h_kmers, uint64_t n, uint64_t **d_keys, uint32_t **d_idx, uint64_t *mask, int *ones_idx) {
+    *d_keys = nullptr; *d_idx = nullptr; *mask = 0; *ones_idx = -1;
     if (n == 0) return P3_OK;
+    for (uint64_t i = 0; i < n; i++) if (h_kmers[i] == kEmpty) *ones_idx = (int)i;   // last one wins, like the table
     uint64_t cap = 16;
     while (cap < 2 * n + 16) cap <<= 1;
     uint64_t *dk = nullptr;
@@ -118,16 +124,16 @@ extern "C" int p3_node_coverage(p3_ctx *c, uint32_t k, const uint64_t *h_junctio
     if (!c || !c->have_reads) return fail(P3_ERR_STATE, "p3_node_coverage: no reads attached");
     if (k < P3_MIN_K || k > P3_MAX_K_WALK) return fail(P3_ERR_ARG, "p3_node_coverage: k outside [21,32]");
     CU(cudaSetDevice(c->device));
-    uint64_t *jk = nullptr, *tk = nullptr; uint32_t *ji = nullptr, *ti = nullptr; uint64_t jm = 0, tm = 0;
-    int rc = build_node_table(c, h_junctions, nj, &jk, &ji, &jm);
-    if (!rc) rc = build_node_table(c, h_joints, nt, &tk, &ti, &tm);
+    uint64_t *jk = nullptr, *tk = nullptr; uint32_t *ji = nullptr, *ti = nullptr; uint64_t jm = 0, tm = 0; int jo = -1, to = -1;
+    int rc = build_node_table(c, h_junctions, nj, &jk, &ji, &jm, &jo);
+    if (!rc) rc = build_node_table(c, h_joints, nt, &tk, &ti, &tm, &to);
     int *djc = nullptr, *dtc = nullptr;
     if (!rc) {
         CU(cudaMalloc(&djc, sizeof(int) * std::max<uint64_t>(9 * nj, 1)));
         CU(cudaMalloc(&dtc, sizeof(int) * std::max<uint64_t>(nt, 1)));
         CU(cudaMemsetAsync(djc, 0, sizeof(int) * std::max<uint64_t>(9 * nj, 1), c->stream));
         CU(cudaMemsetAsync(dtc, 0, sizeof(int) * std::max<uint64_t>(nt, 1), c->stream));
-        NodeTable J{jk, ji, jm}, T{tk, ti, tm};
+        NodeTable J{jk, ji, jm, jo}, T{tk, ti, tm, to};
         if (nj + nt) {
             if (c->d_nmask) node_coverage_kernel<true><<<c->grid(), 256, 0, c->stream>>>(c->d_packed, c->d_rend, c->d_nmask, c->n_words, (int)k, J, T, djc, dtc);
             else node_coverage_kernel<false><<<c->grid(), 256, 0, c->stream>>>(c->d_packed, c->d_rend, nullptr, c->n_words, (int)k, J, T, djc, dtc);

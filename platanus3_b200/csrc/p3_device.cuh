@@ -25,11 +25,16 @@ struct Stats {
     unsigned long long n_edges;           // adjacency bits set
     unsigned long long n_good21;          // distinct 21-mers with count >= threshold
     unsigned long long n_export;          // scratch counter for export kernels
-    unsigned long long n_cand;            // first-occurrence candidates logged by the binned count
+    unsigned long long n_cand;            // keys created by the binned count (== distinct 21-mers)
     unsigned long long work;              // dynamic work counter of the sweep kernels
     unsigned int err_table_full;
     unsigned int err_ovf_full;
     unsigned int n_overflow;              // entries in the overflow table
+    unsigned int err_bin_overflow;        // a fixed-capacity bin overflowed (deferred check: the host redoes the stage with exact bins)
+    unsigned long long probes;            // bucket probes of the instrumented (PROBE_STATS) insert kernels
+    unsigned int max_probe;               // longest probe chain seen by them
+    unsigned int err_kbin_overflow;       // same deferred check for the k-mer bins of the binned de-duplication
+    unsigned int err_peer_timeout;        // a multi-GPU device-side barrier gave up waiting for a peer
     unsigned int pad;
 };
 
@@ -198,10 +203,12 @@ constexpr int kRecOffShift = 42, kRecRankShift = 47, kPosRankShift = 56;
 // partition function of the tile-sort scatter kernels
 //   0 = table partition of a count record   1 = owner of a count record
 //   2 = rank field of a position record     3 = owner of a full 64-bit k-mer
+//   4 = solid-set partition of a full 64-bit k-mer
 template <int PMODE> __device__ __forceinline__ uint32_t pid_of(uint64_t rec, uint32_t P) {
     if (PMODE == 0) return part_of(fmix64(rec & kKey42), P);
     if (PMODE == 1) return owner_of(rec & kKey42, P);
     if (PMODE == 2) return (uint32_t)(rec >> kPosRankShift);
+    if (PMODE == 4) return part_of(fmix64(rec), P);   // set partition of a full 64-bit k-mer (kset_part)
     return owner_of(rec, P);
 }
 __device__ __forceinline__ uint64_t sub_of(uint64_t h, uint64_t nbp) { return ((h & 0xFFFFFFFFULL) * nbp) >> 32; }
@@ -285,6 +292,30 @@ __device__ __forceinline__ int set_insert(const KSet &t, uint64_t key) {
                 uint64_t old = atomicCAS(ull(bp + i), kEmpty, key);
                 if (old == kEmpty) return 1;
                 if (old == key) return 0;
+            }
+        }
+        b = (b + 1 == t.nbp) ? 0 : b + 1;
+    }
+    return -1;
+}
+
+// like set_insert, and *slot = global slot index of the key (inserted now or found)
+__device__ __forceinline__ int set_insert_slot(const KSet &t, uint64_t key, uint64_t *slot) {
+    const uint64_t h = fmix64(key);
+    const uint64_t base = (uint64_t)part_of(h, t.P) * t.nbp;
+    uint64_t b = sub_of(h, t.nbp);
+    for (uint64_t probe = 0; probe < t.nbp; probe++) {
+        uint64_t *bp = t.slots + 4 * (base + b);
+        uint64_t s[4];
+        ld_bucket64(bp, s);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            uint64_t v = s[i];
+            if (v == key) { *slot = 4 * (base + b) + i; return 0; }
+            if (v == kEmpty) {
+                uint64_t old = atomicCAS(ull(bp + i), kEmpty, key);
+                if (old == kEmpty) { *slot = 4 * (base + b) + i; return 1; }
+                if (old == key) { *slot = 4 * (base + b) + i; return 0; }
             }
         }
         b = (b + 1 == t.nbp) ? 0 : b + 1;

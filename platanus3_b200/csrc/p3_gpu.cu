@@ -108,18 +108,20 @@ flags21_kernel(const uint64_t *__restrict__ packed, const uint32_t *__restrict__
     }
 }
 
-// ---- binned count (default): bin -> L2-resident insert sweep -> first-occurrence candidates ----------
+// ---- binned count (default): bin -> L2-resident insert sweep -> creator positions ------------------
 //
-// K1 hist21:    per-partition record counts of a chunk of words (smem histogram per block)
+// K1 hist21:    per-partition record counts of a chunk of words (smem histogram per block; only for
+//               exact bins — the default is fixed-capacity bins, no histogram)
 // K2 scan:      exclusive scan -> bin bases / cursors
 // K3 scatter21: block-local counting sort of a 4096-position tile by partition, then coalesced
 //               runs into the bins. Record = [o:5 | key:42] (uint64) + word index (uint32).
-// K4 insert_bins: grid-stride sweep over the binned records. Records are ordered by partition, so
-//               the whole grid works inside one ~25 MB table partition at a time (L2 resident).
-//               The inserting thread that CREATES a key logs (slot, position): a key with final
-//               count 1 has exactly one occurrence, the one that created it.
-// K5 cand_check: for every candidate whose final count < 2, clear its bit in the coverage plane.
-constexpr int kTileWords = 128;                 // words per scatter tile = threads per block
+// K4 insert_bins: sweep over the binned records. Records are ordered by partition, so the whole grid
+//               works inside one ~24 MB table partition at a time (L2 resident).
+// K5 verdict sweep (p3_bloom.inc.cu pos_bin<0>): once every count is final, the SAME bins are swept a
+//               second time (again partition by partition out of L2, loads only): a record whose key's
+//               count stayed below the threshold clears its position's bit in the coverage plane
+//               (reference src/MakeBloomFilter.cpp:52-58). Works for any threshold, needs no side table.
+constexpr int kTileWords = 128;                 // words per scatter tile
 constexpr int kTilePos = kTileWords * 32;       // 4096 positions
 
 template <bool HAS_MASK, int PMODE>
@@ -168,23 +170,35 @@ __global__ void scan_parts_kernel(const unsigned long long *__restrict__ ghist, 
 __global__ void init_cursors_kernel(unsigned long long *cursor, uint32_t P, uint64_t cap) {
     for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) cursor[i] = (unsigned long long)i * cap;
 }
+// deferred overflow check of fixed-capacity bins (no host round trip per chunk): a partition whose
+// cursor ran past its capacity dropped records; the flag makes the host redo the stage with exact bins
+__global__ void check_cursors_kernel(const unsigned long long *__restrict__ cursor, uint32_t P, uint64_t cap, Stats *st) {
+    for (uint32_t i = threadIdx.x; i < P; i += blockDim.x)
+        if (cursor[i] - (unsigned long long)i * cap > cap) atomicExch(&st->err_bin_overflow, 1u);
+}
 
-struct ScatterSmem {
+// Shared memory of the tile sorts. The sorted records of the 21-mer sort carry their partition and
+// their word-in-tile in the bits the key leaves free ([pt:10 @54 | loc:7 @47 | o:5 @42 | key:42]), so
+// that no side arrays are needed: 44 KB per block = 5 blocks per SM (72 KB = 3 blocks before). The
+// generic record sort (arbitrary 64-bit records) keeps a 16-bit partition array, and a 16-bit source
+// index when an auxiliary word travels with the record.
+template <bool PART, bool LOC>
+struct ScatterSmemT {
     uint64_t key[kTilePos];               // 32 KB  records sorted by partition
-    uint16_t part[kTilePos];              //  8 KB
-    uint16_t loc[kTilePos];               //  8 KB  word-in-tile of each sorted record
-    uint16_t rank[32][kTileWords];        //  8 KB  arrival rank of (offset, thread) inside its partition
-    uint32_t hist[kMaxParts];             //  4 KB
-    uint32_t offs[kMaxParts];             //  4 KB
+    uint32_t hist[kMaxParts];             //  4 KB  per-partition counts, then (in place) exclusive offsets
     unsigned long long gbase[kMaxParts];  //  8 KB
-    uint32_t warp_tot[8];
+    uint16_t part[PART ? kTilePos : 1];   //  8 KB
+    uint16_t loc[LOC ? kTilePos : 1];     //  8 KB
+    uint32_t warp_tot[16];
     uint32_t total;
 };
+using ScatterSmem21 = ScatterSmemT<false, false>;
+constexpr int kSmPtShift = 54, kSmLocShift = 47;
 
-// exclusive scan of sm.hist[0..P) into sm.offs, one global claim per non-empty partition into
-// sm.gbase, total into sm.total. Called by all NT threads of the block between two __syncthreads().
-template <int NT>
-__device__ __forceinline__ void tile_scan_and_claim(ScatterSmem &sm, uint32_t P, unsigned long long *cursor, int tid) {
+// exclusive scan of sm.hist[0..P) in place, one global claim per non-empty partition into sm.gbase,
+// total into sm.total. Called by all NT threads of the block between two __syncthreads().
+template <int NT, class SM>
+__device__ __forceinline__ void tile_scan_and_claim(SM &sm, uint32_t P, unsigned long long *cursor, int tid) {
     const uint32_t per_thread = (P + NT - 1) / NT;
     uint32_t local = 0;
     const uint32_t b0 = tid * per_thread;
@@ -201,7 +215,7 @@ __device__ __forceinline__ void tile_scan_and_claim(ScatterSmem &sm, uint32_t P,
         uint32_t i = b0 + j;
         if (i < P) {
             uint32_t h = sm.hist[i];
-            sm.offs[i] = run;
+            sm.hist[i] = run;
             if (h) sm.gbase[i] = atomicAdd(&cursor[i], (unsigned long long)h);
             run += h;
         }
@@ -216,48 +230,60 @@ __device__ __forceinline__ void tile_scan_and_claim(ScatterSmem &sm, uint32_t P,
 constexpr int kMaxPeers = 16;
 struct PeerOut { uint64_t *keys[kMaxPeers]; uint32_t *words[kMaxPeers]; };
 
-// 256 threads per 128-word tile: thread t handles 16 of the 32 offsets of word t>>1, so the tile's
-// shared memory is covered by 8 warps instead of 4 (occupancy was 18 % with 4)
-constexpr int kScatterThreads = 2 * kTileWords;
+// 512 threads per 128-word tile: thread t handles 8 of the 32 offsets of word t>>2 (16 per thread
+// needed ~70 registers = 3 blocks of 256 per SM; 8 per thread fit 40 = 3 blocks of 512).
+// The reverse strand is taken from the bit-reversed, complemented word pair (computed once per
+// thread): the reverse complement of the k-mer at offset o is a funnel shift of that pair, like the
+// forward k-mer is a funnel shift of (hi, lo) — no per-position bit reversal.
+constexpr int kScatterThreads = 4 * kTileWords;
+constexpr int kScatterPer = kTilePos / kScatterThreads;   // 8
 template <bool HAS_MASK, int PMODE, bool PEER = false>
-__global__ void __launch_bounds__(kScatterThreads)
+__global__ void __launch_bounds__(kScatterThreads, 3)
 scatter21_kernel(const uint64_t *__restrict__ packed, const uint32_t *__restrict__ rend,
                  const uint32_t *__restrict__ nmask, uint64_t w0, uint64_t w1, uint32_t P,
                  unsigned long long *cursor, uint64_t *__restrict__ bkeys, uint32_t *__restrict__ bword,
-                 uint32_t *__restrict__ valid_plane, uint64_t tag, PeerOut peer = PeerOut(), uint64_t cap = 0) {
+                 uint32_t *__restrict__ valid_plane, uint64_t tag, Stats *st, PeerOut peer = PeerOut(), uint64_t cap = 0) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    ScatterSmem &sm = *reinterpret_cast<ScatterSmem *>(smem_raw);
+    ScatterSmem21 &sm = *reinterpret_cast<ScatterSmem21 *>(smem_raw);
     const uint64_t W21 = ~0ULL << (64 - (kShortK - 1));
     const int tid = threadIdx.x;
-    const int wt = tid >> 1;            // word of the tile
-    const int o0 = (tid & 1) * 16;      // first offset this thread handles
+    const int wt = tid >> 2;                    // word of the tile
+    const int o0 = (tid & 3) * kScatterPer;     // first offset this thread handles
     const uint64_t n_tiles = (w1 - w0 + kTileWords - 1) / kTileWords;
+    unsigned long long n_pos = 0;               // last thread only: positions binned by this block
+    bool over = false;
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         for (uint32_t i = tid; i < P; i += kScatterThreads) sm.hist[i] = 0;
         __syncthreads();
         const uint64_t w = w0 + tile * kTileWords + wt;
-        uint64_t hi = 0, lo = 0, mhi = 0, mlo = 0;
-        uint32_t valid = 0;
+        uint64_t hi = 0, lo = 0, rlo = 0, rhi = 0;
+        uint32_t valid = 0;                     // bit (7 - q): offset o0 + q starts a 21-mer inside one read
         if (w < w1) {
             hi = __ldg(packed + w); lo = __ldg(packed + w + 1);
-            uint64_t E = ((uint64_t)__ldg(rend + w) << 32) | __ldg(rend + w + 1);
-            if (HAS_MASK) { mhi = spread32(__ldg(nmask + w)); mlo = spread32(__ldg(nmask + w + 1)); }
+            const uint64_t E = (((uint64_t)__ldg(rend + w) << 32) | __ldg(rend + w + 1)) << o0;
+            uint64_t chi = ~hi, clo = ~lo;
+            if (HAS_MASK) { chi &= ~spread32(__ldg(nmask + w)); clo &= ~spread32(__ldg(nmask + w + 1)); }
+            rlo = rev2(chi); rhi = rev2(clo);      // complemented bases in reverse order: base j at bits [2j+1, 2j]
 #pragma unroll
-            for (int o = 0; o < 32; o++) valid |= (((E << o) & W21) == 0) ? (0x80000000u >> o) : 0u;
-            if ((tid & 1) == 0) valid_plane[w] = valid;
+            for (int q = 0; q < kScatterPer; q++) valid |= (((E << q) & W21) == 0) ? (0x80u >> q) : 0u;
+            reinterpret_cast<uint8_t *>(valid_plane)[4 * w + (3 - (tid & 3))] = (uint8_t)valid;   // plane bit of offset o = 0x80000000 >> o
         }
         // pass 1: canonical key + partition id once per position, kept in registers as
-        // [pid:12 @52 | key:42]; arrival rank inside (tile, partition) from the shared histogram
-        uint64_t kp[16];
+        // [pid:10 @54 | key:42]; arrival rank inside (tile, partition) from the shared histogram
+        uint64_t kp[kScatterPer];
+        uint32_t rk[kScatterPer / 2];           // two 16-bit arrival ranks per register
 #pragma unroll
-        for (int q = 0; q < 16; q++) {
+        for (int q = 0; q < kScatterPer; q++) {
             const int o = o0 + q;
             kp[q] = ~0ULL;
-            if (valid & (0x80000000u >> o)) {
-                uint64_t key = canonical_from_window(window(hi, lo, o), HAS_MASK ? window(mhi, mlo, o) : 0, kShortK);
-                uint32_t pt = pid_of<PMODE>(key, P);
-                kp[q] = key | ((uint64_t)pt << 52);
-                sm.rank[o][wt] = (uint16_t)atomicAdd(&sm.hist[pt], 1u);
+            if ((q & 1) == 0) rk[q >> 1] = 0;
+            if (valid & (0x80u >> q)) {
+                const uint64_t f = window(hi, lo, o) >> (64 - 2 * kShortK);
+                const uint64_t r = (o ? ((rlo >> (2 * o)) | (rhi << (64 - 2 * o))) : rlo) & kKey42;
+                const uint64_t key = f <= r ? f : r;
+                const uint32_t pt = pid_of<PMODE>(key, P);
+                kp[q] = key | ((uint64_t)pt << kSmPtShift);
+                rk[q >> 1] |= atomicAdd(&sm.hist[pt], 1u) << (16 * (q & 1));
             }
         }
         __syncthreads();
@@ -265,36 +291,39 @@ scatter21_kernel(const uint64_t *__restrict__ packed, const uint32_t *__restrict
         __syncthreads();
         // pass 2: place records sorted by partition
 #pragma unroll
-        for (int q = 0; q < 16; q++) {
+        for (int q = 0; q < kScatterPer; q++) {
             const int o = o0 + q;
             if (kp[q] != ~0ULL) {
-                uint32_t pt = (uint32_t)(kp[q] >> 52);
-                uint32_t idx = sm.offs[pt] + sm.rank[o][wt];
-                sm.key[idx] = (kp[q] & kKey42) | ((uint64_t)o << kRecOffShift) | tag;
-                sm.part[idx] = (uint16_t)pt;
-                sm.loc[idx] = (uint16_t)wt;
+                const uint32_t pt = (uint32_t)(kp[q] >> kSmPtShift);
+                sm.key[sm.hist[pt] + ((rk[q >> 1] >> (16 * (q & 1))) & 0xFFFFu)] = kp[q] | ((uint64_t)o << kRecOffShift) | ((uint64_t)wt << kSmLocShift);
             }
         }
         __syncthreads();
         const uint32_t total = sm.total;
         const uint64_t tile_w0 = w0 + tile * kTileWords;
+        if (tid == kScatterThreads - 1) n_pos += total;
         for (uint32_t i = tid; i < total; i += kScatterThreads) {
-            uint32_t pt = sm.part[i];
-            unsigned long long dst = sm.gbase[pt] + (i - sm.offs[pt]);
-            if (PEER) {   // remote (or local) stores over NVLink into owner pt's receive buffer
-                peer.keys[pt][dst] = sm.key[i];
-                peer.words[pt][dst] = (uint32_t)(tile_w0 + sm.loc[i]);
+            const uint64_t v = sm.key[i];
+            const uint32_t pt = (uint32_t)(v >> kSmPtShift);
+            const unsigned long long dst = sm.gbase[pt] + (i - sm.hist[pt]);
+            const uint64_t rec = (v & ((1ULL << kSmLocShift) - 1)) | tag;
+            const uint32_t wd = (uint32_t)(tile_w0 + ((v >> kSmLocShift) & (kTileWords - 1)));
+            if (PEER) {   // remote (or local) stores over NVLink into owner pt's receive region (cap records, 0 = unbounded)
+                if (cap == 0 || dst < cap) { peer.keys[pt][dst] = rec; peer.words[pt][dst] = wd; }
+                else over = true;
             } else if (cap == 0 || dst < (uint64_t)(pt + 1) * cap) {   // fixed-capacity bins: an overflowing record is dropped, the cursor tells
-                bkeys[dst] = sm.key[i];
-                bword[dst] = (uint32_t)(tile_w0 + sm.loc[i]);
+                bkeys[dst] = rec;
+                bword[dst] = wd;
             }
         }
         __syncthreads();
     }
+    if (tid == kScatterThreads - 1 && n_pos && st) atomicAdd(&st->n_pos21, n_pos);
+    if (over && st) atomicExch(&st->err_bin_overflow, 1u);
 }
 
 // the same tile sort for records that already sit in an array (received from other ranks, k-mer
-// lists, position lists): 4096 records per tile, thread t takes records j*128+t (coalesced)
+// lists, position lists): 4096 records per tile, thread t takes records j*512+t (coalesced)
 template <int PMODE>
 __global__ void __launch_bounds__(256)
 hist_rec_kernel(const uint64_t *__restrict__ in, uint64_t n, uint32_t P, unsigned long long *__restrict__ ghist) {
@@ -309,30 +338,44 @@ hist_rec_kernel(const uint64_t *__restrict__ in, uint64_t n, uint32_t P, unsigne
         if (sh[i]) atomicAdd(&ghist[i], (unsigned long long)sh[i]);
 }
 
-template <int PMODE, bool HAS_AUX>
-__global__ void __launch_bounds__(kScatterThreads)
-scatter_rec_kernel(const uint64_t *__restrict__ in, const uint32_t *__restrict__ aux_in, uint64_t n, uint32_t P,
-                   unsigned long long *cursor, uint64_t *__restrict__ out, uint32_t *__restrict__ aux_out, uint64_t cap = 0) {
+// AUXB: bytes of the auxiliary value that travels with each record (0 none, 4 = uint32 word index, 1 = uint8 hint).
+// n_dev (optional): the record count lives on the device (written by an earlier kernel of the stream).
+// Segmented input (in_cap > 0, a multiple of kTilePos): the input is a row of regions of in_cap records
+// each, region r holding in_counts[r] records (what source rank r stored into this rank's receive buffer;
+// the counts arrive through the peer mailbox, so they are read on the device) and n = regions * in_cap.
+template <int PMODE, int AUXB>
+__global__ void __launch_bounds__(kScatterThreads, 3)
+scatter_rec_kernel(const uint64_t *__restrict__ in, const void *__restrict__ aux_in_, uint64_t n, uint32_t P,
+                   unsigned long long *cursor, uint64_t *__restrict__ out, void *__restrict__ aux_out_, uint64_t cap = 0,
+                   const unsigned long long *__restrict__ n_dev = nullptr,
+                   uint64_t in_cap = 0, const unsigned long long *__restrict__ in_counts = nullptr, Stats *st = nullptr) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    ScatterSmem &sm = *reinterpret_cast<ScatterSmem *>(smem_raw);
-    uint16_t *rank = &sm.rank[0][0];                 // flat [kTilePos]: arrival rank of record (j, tid)
-    constexpr int NT = kScatterThreads, PER = kTilePos / NT;   // 256 threads x 16 records
+    using SM = ScatterSmemT<true, AUXB != 0>;
+    SM &sm = *reinterpret_cast<SM *>(smem_raw);
+    constexpr int NT = kScatterThreads, PER = kTilePos / NT;   // 512 threads x 8 records
     const int tid = threadIdx.x;
+    if (n_dev) n = min(n, (uint64_t)*n_dev);
     const uint64_t n_tiles = (n + kTilePos - 1) / kTilePos;
+    bool over = false;
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint64_t t0 = tile * kTilePos;
+        uint64_t lim = n;
+        if (in_cap) { const uint64_t r = t0 / in_cap; lim = r * in_cap + min((uint64_t)__ldcg(in_counts + r), in_cap); }
+        if (t0 >= lim) continue;    // block-uniform
         for (uint32_t i = tid; i < P; i += NT) sm.hist[i] = 0;
         __syncthreads();
-        const uint64_t t0 = tile * kTilePos;
         uint64_t rec[PER];
+        uint32_t rk[PER / 2];   // two 16-bit arrival ranks per register
 #pragma unroll
         for (int j = 0; j < PER; j++) {
             uint64_t i = t0 + j * NT + tid;
-            rec[j] = i < n ? __ldcs(in + i) : 0;
+            rec[j] = i < lim ? __ldcs(in + i) : 0;
         }
 #pragma unroll
         for (int j = 0; j < PER; j++) {
             uint64_t i = t0 + j * NT + tid;
-            if (i < n) rank[j * NT + tid] = (uint16_t)atomicAdd(&sm.hist[pid_of<PMODE>(rec[j], P)], 1u);
+            if ((j & 1) == 0) rk[j >> 1] = 0;
+            if (i < lim) rk[j >> 1] |= atomicAdd(&sm.hist[pid_of<PMODE>(rec[j], P)], 1u) << (16 * (j & 1));
         }
         __syncthreads();
         tile_scan_and_claim<NT>(sm, P, cursor, tid);
@@ -340,25 +383,55 @@ scatter_rec_kernel(const uint64_t *__restrict__ in, const uint32_t *__restrict__
 #pragma unroll
         for (int j = 0; j < PER; j++) {
             uint64_t i = t0 + j * NT + tid;
-            if (i < n) {
+            if (i < lim) {
                 uint32_t pt = pid_of<PMODE>(rec[j], P);
-                uint32_t idx = sm.offs[pt] + rank[j * NT + tid];
+                uint32_t idx = sm.hist[pt] + ((rk[j >> 1] >> (16 * (j & 1))) & 0xFFFFu);
                 sm.key[idx] = rec[j];
                 sm.part[idx] = (uint16_t)pt;
-                sm.loc[idx] = (uint16_t)(j * NT + tid);
+                if (AUXB) sm.loc[idx] = (uint16_t)(j * NT + tid);
             }
         }
         __syncthreads();
         const uint32_t total = sm.total;
         for (uint32_t i = tid; i < total; i += NT) {
             uint32_t pt = sm.part[i];
-            unsigned long long dst = sm.gbase[pt] + (i - sm.offs[pt]);
-            if (cap && dst >= (uint64_t)(pt + 1) * cap) continue;
+            unsigned long long dst = sm.gbase[pt] + (i - sm.hist[pt]);
+            if (cap && dst >= (uint64_t)(pt + 1) * cap) { over = true; continue; }
             out[dst] = sm.key[i];
-            if (HAS_AUX) aux_out[dst] = __ldg(aux_in + t0 + sm.loc[i]);
+            if (AUXB == 4) static_cast<uint32_t *>(aux_out_)[dst] = __ldg(static_cast<const uint32_t *>(aux_in_) + t0 + sm.loc[i]);
+            if (AUXB == 1) static_cast<uint8_t *>(aux_out_)[dst] = __ldg(static_cast<const uint8_t *>(aux_in_) + t0 + sm.loc[i]);
         }
         __syncthreads();
     }
+    if (over && st) atomicExch(&st->err_bin_overflow, 1u);
+}
+
+// Insert of one occurrence whose first bucket (bucket b of partition `base`, already in s[]) was
+// loaded ahead of time; the rest of the probe sequence is count_insert's. Returns true when this
+// call created the key (*slot = its global slot index). The pre-loaded bucket may be stale by the
+// time it is used: slots only ever go empty -> key, an occupied slot never changes its key, and an
+// empty-looking slot is claimed with a CAS, so a stale view is still a correct starting point.
+template <bool PROBE_STATS>
+__device__ __forceinline__ bool count_insert_pre(const Table &t, uint64_t key, uint64_t base, uint64_t b, uint64_t s[4],
+                                                 const Ovf &ovf, Stats *st, uint64_t *slot, unsigned *n_probes) {
+    for (uint64_t probe = 0; probe < t.nbp; probe++) {
+        uint64_t *bp = t.slots + 4 * (base + b);
+        if (probe) ld_bucket(bp, s);
+        if (PROBE_STATS) (*n_probes)++;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            uint64_t v = s[i];
+            if ((v & kKey42) == key) { count_bump(bp + i, v, key, ovf, st); return false; }
+            if (v == kEmpty) {
+                uint64_t old = atomicCAS(ull(bp + i), kEmpty, key | kCntOne);
+                if (old == kEmpty) { *slot = 4 * (base + b) + i; return true; }
+                if ((old & kKey42) == key) { count_bump(bp + i, old, key, ovf, st); return false; }
+            }
+        }
+        b = (b + 1 == t.nbp) ? 0 : b + 1;
+    }
+    atomicExch(&st->err_table_full, 1u);
+    return false;
 }
 
 // Work is handed out in chunks from ONE global counter instead of a static grid-stride loop:
@@ -366,16 +439,21 @@ scatter_rec_kernel(const uint64_t *__restrict__ in, const uint32_t *__restrict__
 // partitions ahead, so that several hundred MB of table are live at once and L2 thrashes
 // (measured: 22 G rec/s). With the shared counter all in-flight chunks lie within
 // gridDim * kSweepChunk records of each other, i.e. inside one or two partitions.
+// Inside a chunk a thread works on kSweepBatch records at a time: their bucket loads are all issued
+// before the first one is consumed, so a thread has kSweepBatch L2 round trips in flight instead of
+// one (the round-1 kernel was bound by exactly that dependent load -> RED chain).
 constexpr int kSweepChunk = 2048;   // records per block per grab (8 per thread)
 constexpr int kSweepPer = kSweepChunk / 256;
-__global__ void __launch_bounds__(256, 4)
-insert_bins_kernel(const uint64_t *__restrict__ bkeys, const uint32_t *__restrict__ bword, uint64_t n,
-                   Table table, Ovf ovf, Stats *st, uint64_t *__restrict__ cand_slot,
-                   uint64_t *__restrict__ cand_pos, uint64_t cand_cap,
-                   uint64_t cap = 0, const unsigned long long *__restrict__ bin_end = nullptr) {
-    __shared__ unsigned long long s_base, s_cand;
-    __shared__ unsigned s_wtot[8];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+constexpr int kSweepBatch = 4;
+template <bool PROBE_STATS>
+__global__ void __launch_bounds__(256, 3)   // 4 blocks per SM would cap it at 64 registers: 76 bytes of spills in the batch loop
+insert_bins_kernel(const uint64_t *__restrict__ bkeys, uint64_t n,
+                   Table table, Ovf ovf, Stats *st,
+                   uint64_t cap = 0, const unsigned long long *__restrict__ bin_end = nullptr,
+                   const unsigned long long *__restrict__ n_dev = nullptr) {
+    __shared__ unsigned long long s_base;
+    if (n_dev) n = min(n, (uint64_t)*n_dev);
+    unsigned created = 0, probes = 0, longest = 0;
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) s_base = atomicAdd(&st->work, (unsigned long long)kSweepChunk);
@@ -383,68 +461,50 @@ insert_bins_kernel(const uint64_t *__restrict__ bkeys, const uint32_t *__restric
         const uint64_t cbase = s_base;
         if (cbase >= n) break;
         // fixed-capacity bins (cap > 0, a multiple of kSweepChunk): partition p's records are
-        // [p*cap, bin_end[p]); a chunk never straddles two partitions
-        const uint64_t lim = cap ? min((uint64_t)__ldg(bin_end + cbase / cap), n) : n;
+        // [p*cap, min(bin_end[p], (p+1)*cap)); a chunk never straddles two partitions
+        uint64_t lim = n;
+        if (cap) { const uint64_t p = cbase / cap; lim = min((uint64_t)__ldg(bin_end + p), (p + 1) * cap); }
         if (cbase >= lim) continue;
-        uint64_t rec[kSweepPer];
-        uint32_t wd[kSweepPer];
 #pragma unroll
-        for (int it = 0; it < kSweepPer; it++) {   // the whole chunk's records first: 8 independent coalesced loads
-            uint64_t i = cbase + it * 256 + threadIdx.x;
-            rec[it] = i < lim ? __ldcs(bkeys + i) : ~0ULL;
-            wd[it] = i < lim ? __ldcs(bword + i) : 0u;
-        }
-        uint64_t created[kSweepPer];
-        unsigned mine = 0;
+        for (int half = 0; half < kSweepPer / kSweepBatch; half++) {
+            uint64_t rec[kSweepBatch], s[kSweepBatch][4];
 #pragma unroll
-        for (int it = 0; it < kSweepPer; it++) {
-            created[it] = ~0ULL;
-            if (rec[it] != ~0ULL) count_insert(table, rec[it] & kKey42, ovf, st, &created[it]);
-            mine += created[it] != ~0ULL;
-        }
-        // one global atomic per block per chunk for the candidate list (a per-warp atomic on the
-        // single list cursor serialises in L2 and was the whole kernel time)
-        unsigned incl = mine;
+            for (int it = 0; it < kSweepBatch; it++) {
+                const uint64_t i = cbase + (uint64_t)(half * kSweepBatch + it) * 256 + threadIdx.x;
+                rec[it] = i < lim ? __ldcs(bkeys + i) : ~0ULL;
+            }
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { unsigned v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
-        if (lane == 31) s_wtot[wid] = incl;
-        __syncthreads();
-        unsigned wbase = 0, total = 0;
+            for (int it = 0; it < kSweepBatch; it++) {
+                if (rec[it] != ~0ULL) {
+                    const uint64_t h = fmix64(rec[it] & kKey42);
+                    ld_bucket(table.slots + 4 * ((uint64_t)part_of(h, table.P) * table.nbp + sub_of(h, table.nbp)), s[it]);
+                }
+            }
 #pragma unroll
-        for (int q = 0; q < 8; q++) { unsigned t = s_wtot[q]; if (q < wid) wbase += t; total += t; }
-        if (threadIdx.x == 0 && total) s_cand = atomicAdd(&st->n_cand, (unsigned long long)total);
-        __syncthreads();
-        if (mine) {
-            unsigned long long j = s_cand + wbase + incl - mine;
-#pragma unroll
-            for (int it = 0; it < kSweepPer; it++) {
-                if (created[it] != ~0ULL) {
-                    if (j < cand_cap) {
-                        cand_slot[j] = created[it];
-                        cand_pos[j] = ((uint64_t)wd[it] * 32 + ((rec[it] >> kRecOffShift) & 31)) | (((rec[it] >> kRecRankShift) & 0xFF) << kPosRankShift);
-                    }
-                    j++;
+            for (int it = 0; it < kSweepBatch; it++) {
+                if (rec[it] != ~0ULL) {
+                    uint64_t slot;
+                    unsigned np = 0;
+                    const uint64_t h = fmix64(rec[it] & kKey42);   // recomputed: cheaper than carrying it across the loads
+                    if (count_insert_pre<PROBE_STATS>(table, rec[it] & kKey42, (uint64_t)part_of(h, table.P) * table.nbp, sub_of(h, table.nbp), s[it], ovf, st, &slot, &np))
+                        created++;
+                    if (PROBE_STATS) { probes += np; longest = max(longest, np); }
                 }
             }
         }
     }
+    unsigned long long tot = warp_sum(created);
+    if ((threadIdx.x & 31) == 0 && tot) atomicAdd(&st->n_cand, tot);
+    if (PROBE_STATS) {
+        unsigned long long tp = warp_sum(probes);
+        unsigned mx = __reduce_max_sync(0xffffffffu, longest);
+        if ((threadIdx.x & 31) == 0) { if (tp) atomicAdd(&st->probes, tp); atomicMax(&st->max_probe, mx); }
+    }
 }
 
-__global__ void __launch_bounds__(256)
-cand_check_kernel(const uint64_t *__restrict__ slots, const uint64_t *__restrict__ cand_slot,
-                  const uint64_t *__restrict__ cand_pos, uint64_t n_cand, uint64_t thr, Ovf ovf,
-                  const Stats *st, uint32_t *good21) {
-    const unsigned n_overflow = st->n_overflow;
-    uint64_t stride = gridDim.x * (uint64_t)blockDim.x;
-    for (uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; j < n_cand; j += stride) {
-        uint64_t v = __ldcg(slots + __ldcs(cand_slot + j));
-        uint64_t c = v >> 42;
-        if (c < thr && n_overflow) c += ovf_get(ovf, v & kKey42) << 22;
-        if (c < thr) {
-            uint64_t pos = __ldcs(cand_pos + j) & ((1ULL << kPosRankShift) - 1);
-            atomicAnd(good21 + (pos >> 5), ~(0x80000000u >> (pos & 31)));
-        }
-    }
+// position record [rank:8 @56 | stream position:56] of a count record and its word index
+__device__ __forceinline__ uint64_t posrec_of(uint64_t rec, uint32_t wd) {
+    return ((uint64_t)wd * 32 + ((rec >> kRecOffShift) & 31)) | (((rec >> kRecRankShift) & 0xFF) << kPosRankShift);
 }
 
 // RMQ window minimum >= threshold  <=>  every 21-mer flag in the window is set
@@ -503,66 +563,116 @@ makebf_kernel(const uint64_t *__restrict__ packed, const uint32_t *__restrict__ 
 // scatter21 machinery, 8-byte records, fixed-capacity bins: partitions are hash-uniform), K2 sweeps
 // the bins with the work-counter hand-out of insert_bins so that the whole grid probes one ~24 MB
 // partition at a time out of L2. 95 % of the probes are plain hits (load + compare, no atomic).
-template <bool HAS_MASK>
-__global__ void __launch_bounds__(kScatterThreads)
+// Every solid occurrence also carries an adjacency HINT: when the position before / after it in the
+// read is solid too, that neighbouring k-mer was added to the filter, so the corresponding direction of
+// CheckDirections (reference src/DeBruijnGraph.cpp:326-345) is certainly "recorded" and needs no query
+// later. Bit d of the hint = direction d of the CANONICAL k-mer (0-3 left extension by A,C,G,T; 4-7
+// right extension); for an occurrence whose canonical form is the reverse strand, left and right swap
+// and the base is complemented. Occurrences near a non-ACGT character carry no hint (the reference adds
+// such k-mers with its both-strands-read-as-A quirk, so the neighbour relation need not hold).
+struct PeerOutK { uint64_t *keys[kMaxPeers]; uint8_t *hints[kMaxPeers]; };
+template <bool HAS_MASK, bool PEER>
+__global__ void __launch_bounds__(kScatterThreads, 3)
 scatter_kmer_kernel(const uint64_t *__restrict__ packed, const uint32_t *__restrict__ nmask,
-                    const uint32_t *__restrict__ solid, uint64_t n_words, int k, uint32_t P,
-                    unsigned long long *cursor, uint64_t *__restrict__ bins, uint64_t cap) {
+                    const uint32_t *__restrict__ solid, uint64_t w0, uint64_t w1, int k, uint32_t P,
+                    unsigned long long *cursor, uint64_t *__restrict__ bins, uint8_t *__restrict__ hbins, uint64_t cap,
+                    Stats *st, PeerOutK peer = PeerOutK()) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    ScatterSmem &sm = *reinterpret_cast<ScatterSmem *>(smem_raw);
+    using SM = ScatterSmemT<true, true>;    // loc[] carries the hint of the sorted record
+    SM &sm = *reinterpret_cast<SM *>(smem_raw);
     const int tid = threadIdx.x;
-    const int wt = tid >> 1;            // word of the tile
-    const int o0 = (tid & 1) * 16;      // first offset this thread handles
-    const uint64_t n_tiles = (n_words + kTileWords - 1) / kTileWords;
+    const int wt = tid >> 2;                    // word of the tile
+    const int o0 = (tid & 3) * kScatterPer;     // first offset this thread handles
+    const uint64_t n_tiles = (w1 - w0 + kTileWords - 1) / kTileWords;
+    const uint64_t km = kmask(k);
+    bool over = false;
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         for (uint32_t i = tid; i < P; i += kScatterThreads) sm.hist[i] = 0;
         __syncthreads();
-        const uint64_t w = tile * kTileWords + wt;
-        uint64_t hi = 0, lo = 0, mhi = 0, mlo = 0;
-        uint32_t s = 0;
-        if (w < n_words) {
-            s = __ldg(solid + w);
+        const uint64_t w = w0 + tile * kTileWords + wt;
+        uint64_t hi = 0, lo = 0, rlo = 0, rhi = 0, S = 0, mbits = 0;
+        uint32_t s = 0, prev_base = 0;          // s bit (7 - q): offset o0 + q is a solid position
+        bool pm = false;
+        if (w < w1) {
+            const uint32_t sc = __ldg(solid + w);
+            s = (sc >> (24 - o0)) & 0xFFu;
             if (s) {
                 hi = __ldg(packed + w); lo = __ldg(packed + w + 1);
-                if (HAS_MASK) { mhi = spread32(__ldg(nmask + w)); mlo = spread32(__ldg(nmask + w + 1)); }
+                uint64_t chi = ~hi, clo = ~lo;
+                if (HAS_MASK) {
+                    const uint32_t ma = __ldg(nmask + w), mb = __ldg(nmask + w + 1);
+                    chi &= ~spread32(ma); clo &= ~spread32(mb);
+                    mbits = ((uint64_t)ma << 32) | mb;
+                    pm = w ? (__ldg(nmask + w - 1) & 1u) : false;
+                }
+                rlo = rev2(chi); rhi = rev2(clo);
+                // S bit (33 - j): position 32w + j is solid, j = -1 .. 32
+                S = ((uint64_t)(w ? (__ldg(solid + w - 1) & 1u) : 0u) << 33) | ((uint64_t)sc << 1) | (__ldg(solid + w + 1) >> 31);
+                prev_base = w ? (uint32_t)(__ldg(packed + w - 1) & 3) : 0u;
             }
         }
-        uint64_t key[16];
+        uint64_t key[kScatterPer];
+        uint32_t rk[kScatterPer / 2], hint[kScatterPer / 4];   // 16-bit arrival ranks, 8-bit hints
 #pragma unroll
-        for (int q = 0; q < 16; q++) {
+        for (int q = 0; q < kScatterPer; q++) {
             const int o = o0 + q;
             key[q] = kEmpty;
-            if (s & (0x80000000u >> o)) {
-                key[q] = canonical_from_window(window(hi, lo, o), HAS_MASK ? window(mhi, mlo, o) : 0, k);
-                sm.rank[o][wt] = (uint16_t)atomicAdd(&sm.hist[kset_part(key[q], P)], 1u);
+            if ((q & 1) == 0) rk[q >> 1] = 0;
+            if ((q & 3) == 0) hint[q >> 2] = 0;
+            if (s & (0x80u >> q)) {
+                const uint64_t f = window(hi, lo, o) >> (64 - 2 * k);
+                const uint64_t r = (o ? ((rlo >> (2 * o)) | (rhi << (64 - 2 * o))) : rlo) & km;
+                const bool fwd = f <= r;
+                key[q] = fwd ? f : r;
+                rk[q >> 1] |= atomicAdd(&sm.hist[PEER ? owner_of(key[q], P) : kset_part(key[q], P)], 1u) << (16 * (q & 1));
+                bool lh = (S >> (34 - o)) & 1, rh = (S >> (32 - o)) & 1;
+                if (HAS_MASK) {
+                    if (lh) lh = o ? (((mbits << (o - 1)) >> (63 - k)) == 0) : (!pm && (mbits >> (64 - k)) == 0);
+                    if (rh) rh = ((mbits << o) >> (63 - k)) == 0;
+                }
+                uint32_t h = 0;
+                if (lh) { const uint32_t lb = o ? (uint32_t)((hi >> (64 - 2 * o)) & 3) : prev_base; h |= fwd ? (1u << lb) : (16u << (3 - lb)); }
+                if (rh) {
+                    const int j = o + k;
+                    const uint32_t rb = (uint32_t)((j < 32 ? (hi >> (62 - 2 * j)) : (lo >> (126 - 2 * j))) & 3);
+                    h |= fwd ? (16u << rb) : (1u << (3 - rb));
+                }
+                hint[q >> 2] |= h << (8 * (q & 3));
             }
         }
         __syncthreads();
         tile_scan_and_claim<kScatterThreads>(sm, P, cursor, tid);
         __syncthreads();
 #pragma unroll
-        for (int q = 0; q < 16; q++) {
-            const int o = o0 + q;
-            if (s & (0x80000000u >> o)) {
-                uint32_t pt = kset_part(key[q], P);
-                uint32_t idx = sm.offs[pt] + sm.rank[o][wt];
+        for (int q = 0; q < kScatterPer; q++) {
+            if (s & (0x80u >> q)) {
+                uint32_t pt = PEER ? owner_of(key[q], P) : kset_part(key[q], P);
+                uint32_t idx = sm.hist[pt] + ((rk[q >> 1] >> (16 * (q & 1))) & 0xFFFFu);
                 sm.key[idx] = key[q];
                 sm.part[idx] = (uint16_t)pt;
+                sm.loc[idx] = (uint16_t)((hint[q >> 2] >> (8 * (q & 3))) & 0xFFu);
             }
         }
         __syncthreads();
         const uint32_t total = sm.total;
         for (uint32_t i = tid; i < total; i += kScatterThreads) {
             uint32_t pt = sm.part[i];
-            unsigned long long dst = sm.gbase[pt] + (i - sm.offs[pt]);
-            if (dst < (uint64_t)(pt + 1) * cap) bins[dst] = sm.key[i];
+            unsigned long long dst = sm.gbase[pt] + (i - sm.hist[pt]);
+            if (PEER) {   // owner pt's receive region for this source (cap records)
+                if (dst < cap) { peer.keys[pt][dst] = sm.key[i]; peer.hints[pt][dst] = (uint8_t)sm.loc[i]; }
+                else over = true;
+            } else if (dst < (uint64_t)(pt + 1) * cap) { bins[dst] = sm.key[i]; hbins[dst] = (uint8_t)sm.loc[i]; }
+            else over = true;
         }
         __syncthreads();
     }
+    if (over) atomicExch(PEER ? &st->err_bin_overflow : &st->err_kbin_overflow, 1u);   // deferred check on the host
 }
-__global__ void __launch_bounds__(256)   // 41 registers; capping at 32 spills 250 bytes and costs 19 ms
-set_sweep_kernel(const uint64_t *__restrict__ bins, uint64_t n, uint64_t cap, const unsigned long long *__restrict__ bin_end,
-                 KSet set, Stats *st) {
+// hints (optional): one byte per record, OR-ed into the byte of the set slot that holds the k-mer
+// (a plain load first: 95 % of the records repeat a hint that is already there)
+__global__ void __launch_bounds__(256)   // capping at 32 registers spills 250 bytes and costs 19 ms
+set_sweep_kernel(const uint64_t *__restrict__ bins, const uint8_t *__restrict__ hbins, uint64_t n, uint64_t cap,
+                 const unsigned long long *__restrict__ bin_end, KSet set, uint32_t *__restrict__ slot_hint, Stats *st) {
     __shared__ unsigned long long s_base;
     bool full = false;
     for (;;) {
@@ -571,17 +681,26 @@ set_sweep_kernel(const uint64_t *__restrict__ bins, uint64_t n, uint64_t cap, co
         __syncthreads();
         const uint64_t cbase = s_base;
         if (cbase >= n) break;
-        const uint64_t lim = min((uint64_t)__ldg(bin_end + cbase / cap), n);
+        const uint64_t pq = cbase / cap;
+        const uint64_t lim = min(min((uint64_t)__ldg(bin_end + pq), (pq + 1) * cap), n);
         if (cbase >= lim) continue;
         uint64_t rec[kSweepPer];
+        uint32_t hb[kSweepPer / 4];
 #pragma unroll
         for (int it = 0; it < kSweepPer; it++) {
             uint64_t i = cbase + it * 256 + threadIdx.x;
             rec[it] = i < lim ? __ldcs(bins + i) : kEmpty;
+            if ((it & 3) == 0) hb[it >> 2] = 0;
+            if (hbins && i < lim) hb[it >> 2] |= (uint32_t)__ldcs(hbins + i) << (8 * (it & 3));
         }
 #pragma unroll
-        for (int it = 0; it < kSweepPer; it++)
-            if (rec[it] != kEmpty && set_insert(set, rec[it]) < 0) full = true;
+        for (int it = 0; it < kSweepPer; it++) {
+            if (rec[it] == kEmpty) continue;
+            uint64_t slot;
+            if (set_insert_slot(set, rec[it], &slot) < 0) { full = true; continue; }
+            const uint32_t h = ((hb[it >> 2] >> (8 * (it & 3))) & 0xFFu) << (8 * (slot & 3));
+            if (h && (__ldcg(slot_hint + (slot >> 2)) & h) != h) atomicOr(slot_hint + (slot >> 2), h);
+        }
     }
     if (full) atomicExch(&st->err_table_full, 1u);
 }
@@ -590,7 +709,7 @@ set_sweep_kernel(const uint64_t *__restrict__ bins, uint64_t n, uint64_t cap, co
 // atomic per block-iteration (a per-winner atomic on one list cursor serialises in L2).
 __global__ void __launch_bounds__(256)
 compact_set_kernel(const uint64_t *__restrict__ set, uint64_t n_slots, uint64_t *__restrict__ list,
-                   uint64_t list_cap, Stats *st) {
+                   uint64_t list_cap, Stats *st, const uint8_t *__restrict__ slot_hint = nullptr, uint8_t *__restrict__ adj = nullptr) {
     __shared__ unsigned s_wtot[8];
     __shared__ unsigned long long s_base;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -609,7 +728,7 @@ compact_set_kernel(const uint64_t *__restrict__ set, uint64_t n_slots, uint64_t 
         __syncthreads();
         if (v != kEmpty) {
             unsigned long long j = s_base + wbase + __popc(m & ((1u << lane) - 1));
-            if (j < list_cap) list[j] = v;
+            if (j < list_cap) { list[j] = v; if (slot_hint) adj[j] = slot_hint[i]; }   // adjacency bytes start as the hints
         }
         __syncthreads();
     }
@@ -664,6 +783,9 @@ __global__ void seeds_kernel(const uint64_t *__restrict__ off, uint64_t n_reads,
 // `set` (may be null): the distinct solid k-mers. Every member was added to the filter, so
 // possiblyContains is certainly true for it and its num_hashes probes are skipped; only
 // non-members (which mostly fail after a few probes) walk the filter.
+// HINT: adj[] comes in holding the hint byte of every k-mer (directions known to be recorded because the
+// neighbouring k-mer was seen solid right beside this one in a read): those lanes skip their query.
+template <bool HINT>
 __global__ void __launch_bounds__(256, 8)   // 32 registers: the kernel lives on occupancy (34 registers cost 40 %: 97 -> 135 ms)
 adjacency_kernel(const uint64_t *__restrict__ kmers, uint64_t n, int k, Bloom bf, KSet set, KSet set_b,
                  uint8_t *__restrict__ adj, Stats *st) {
@@ -675,7 +797,8 @@ adjacency_kernel(const uint64_t *__restrict__ kmers, uint64_t n, int k, Bloom bf
     for (uint64_t base = warp * 4; base < n; base += n_warps * 4) {
         uint64_t i = base + g;
         bool rec = false;
-        if (i < n) {
+        if (HINT && i < n) rec = (adj[i] >> d) & 1;   // read by all 8 lanes before the ballot below, rewritten after it
+        if (i < n && !rec) {
             uint64_t nb = neighbour(__ldg(kmers + i), d, k);
             uint64_t rc = revcomp(nb, k);
             uint64_t c = nb <= rc ? nb : rc;   // IsRecorded canonicalises (DeBruijnGraph.cpp:320-321)
@@ -831,11 +954,21 @@ struct p3_ctx {
     bool binned = true;                                // P3_COUNT_MODE=direct switches it off
     uint64_t *d_bkeys = nullptr; uint32_t *d_bword = nullptr; uint64_t cap_bkeys = 0, cap_bword = 0;
     uint32_t *d_valid = nullptr; uint64_t cap_valid = 0;
-    uint64_t *d_cand_slot = nullptr, *d_cand_pos = nullptr; uint64_t cap_cand_slot = 0, cap_cand_pos = 0, cand_cap = 0;
+    uint64_t bin_cap = 0, bin_n = 0; bool bins_valid = false;   // the partition bins of the last count (one chunk) are still there for the verdict sweep
+    uint64_t bin_upper = 0; bool bin_exact = false;
+    unsigned long long *d_binmeta = nullptr;   // [kMaxParts] bin ends + [kMaxParts] record total of the current bins
     unsigned long long *d_ghist = nullptr, *d_cursor = nullptr;
+    std::vector<cudaEvent_t> evpool;       // per-chunk timing events of the binned count (no sync inside the chunk loop)
+    // host-buffer path (p3_assemble_hot_path*): the 2-bit staging arrives in pieces on a copy stream while the binning
+    // kernel already works on the pieces that are there; results leave on the copy stream while CheckDirections runs
+    cudaStream_t copy_stream = nullptr;
+    std::vector<cudaEvent_t> up_ev; uint64_t up_pieces = 0, up_piece_words = 0;   // pending upload (consumed by the next count)
+    cudaEvent_t ev_main = nullptr, ev_copy = nullptr;
+    bool probe_stats = false;              // P3_PROBE_STATS: instrumented insert kernels (bench.py --config 4)
+    bool attrs_set = false;
     float ms_sub[4] = {0, 0, 0, 0};
     float ms_bloom = 0;                    // hist, scatter, insert, cand_check
-    uint64_t n_chunks = 0, binned_pos = 0;
+    uint64_t n_chunks = 0, binned_pos = 0; bool pos_on_host = false;
     Table table() const { Table t; t.slots = d_table; t.nbp = nbp; t.P = parts; return t; }
     uint64_t *d_ovf_keys = nullptr; unsigned long long *d_ovf_wraps = nullptr;
     bool have_counts = false;
@@ -844,6 +977,8 @@ struct p3_ctx {
     uint32_t *d_proven2 = nullptr; uint64_t cap_proven = 0;
     uint64_t *d_set = nullptr; uint64_t nbs = 0; uint32_t set_parts = 1;   // nbs = total buckets = set_parts * buckets per partition
     bool set_valid = false;   // d_set holds a subset of what the current filter contains
+    uint32_t *d_hint = nullptr; uint64_t cap_hint = 0;   // one hint byte per set slot (binned de-duplication)
+    bool hints_valid = false; // d_adj[0..n_distinct) holds the hint bytes of the current list
     const uint64_t *d_set_b = nullptr; uint64_t nbs_b = 0; uint32_t parts_b = 1;   // multi-GPU: second (locally seen) solid set, not owned here
     KSet kset() const { KSet t; t.slots = d_set; t.P = set_parts ? set_parts : 1; t.nbp = nbs / t.P; return t; }
     KSet kset_b() const { KSet t; t.slots = const_cast<uint64_t *>(d_set_b); t.P = parts_b ? parts_b : 1; t.nbp = nbs_b / t.P; return t; }
@@ -883,9 +1018,9 @@ static void mg_release(struct p3_ctx *c);   // p3_multi.inc.cu
 static void long_release(struct p3_ctx *c); // p3_long.inc.cu
 static void bloom_release(struct p3_ctx *c);                                  // p3_bloom.inc.cu
 static int bloom_add_binned(struct p3_ctx *c, uint64_t n, bool *done);
-template <int MODE> static int binned_plane_clear(struct p3_ctx *c, const uint64_t *cand_slot, const uint64_t *pos_in, uint64_t n,
-                                                  uint64_t thr, uint32_t *plane, uint64_t n_pos, bool *done);
 static int make_bf_long(struct p3_ctx *c, uint32_t k, uint64_t solid_slots);
+static int verdict_sweep(struct p3_ctx *c, uint64_t thr, bool force_direct, bool *binned_any);   // p3_bloom.inc.cu
+static int bloom_add_direct_long(struct p3_ctx *c, uint64_t nd);
 static int adjacency_long(struct p3_ctx *c, const uint64_t *d_words, uint64_t n, uint8_t *d_adj, struct p3::Stats *st);
 static const uint64_t *long_words(struct p3_ctx *c);
 static int long_batch(struct p3_ctx *c, int op, uint32_t k, const uint64_t *h_kmers, uint64_t n, void *h_out);
@@ -903,8 +1038,8 @@ template <typename T> static cudaError_t ensure(T *&p, uint64_t &cap_bytes, uint
 static int pull_stats(p3_ctx *c) {
     CU(cudaMemcpyAsync(&c->h_stats, c->d_stats, sizeof(Stats), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    if (c->binned) {  // the binned count keeps its position total on the host; distinct keys == candidates
-        c->h_stats.n_pos21 = c->binned_pos;
+    if (c->binned) {  // distinct keys == keys created; the multi-GPU owner keeps its position total on the host
+        if (c->pos_on_host) c->h_stats.n_pos21 = c->binned_pos;
         c->h_stats.n_distinct21 = c->h_stats.n_cand;
     }
     return P3_OK;
@@ -970,7 +1105,7 @@ static void free_reads(p3_ctx *c) {
 }
 static void free_bf(p3_ctx *c) {
     dfree(c->d_good21); dfree(c->d_solid); dfree(c->d_set); dfree(c->d_list); dfree(c->d_bloom);
-    dfree(c->d_seed); dfree(c->d_adj); c->adj_cap = 0; c->cap_planes = c->cap_seed = 0;
+    dfree(c->d_seed); dfree(c->d_adj); dfree(c->d_hint); c->cap_hint = 0; c->adj_cap = 0; c->cap_planes = c->cap_seed = 0;
     c->nbs = 0; c->bloom_words = 0;
     c->have_bf = c->have_solid = c->have_adj = false;
 }
@@ -984,8 +1119,13 @@ void p3_destroy(p3_ctx *c) {
     bloom_release(c);
     free_reads(c); free_bf(c);
     dfree(c->d_table); dfree(c->d_proven2); dfree(c->d_bkeys); dfree(c->d_bword); dfree(c->d_valid);
-    dfree(c->d_cand_slot); dfree(c->d_cand_pos); dfree(c->d_ghist); dfree(c->d_cursor); dfree(c->d_ovf_keys); dfree(c->d_ovf_wraps); dfree(c->d_stats);
+    dfree(c->d_ghist); dfree(c->d_binmeta); dfree(c->d_cursor); dfree(c->d_ovf_keys); dfree(c->d_ovf_wraps); dfree(c->d_stats);
     for (auto &e : c->ev) cudaEventDestroy(e);
+    for (auto &e : c->evpool) cudaEventDestroy(e);
+    for (auto &e : c->up_ev) cudaEventDestroy(e);
+    if (c->ev_main) cudaEventDestroy(c->ev_main);
+    if (c->ev_copy) cudaEventDestroy(c->ev_copy);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -1052,122 +1192,182 @@ static int count_direct(p3_ctx *c) {
     return P3_OK;
 }
 
-// the tile-sort kernels need > 48 KB of dynamic shared memory
-static int scatter_attrs() {
-    static bool done = false;
-    if (done) return P3_OK;
-    const int sz = (int)sizeof(ScatterSmem);
-    CU(cudaFuncSetAttribute(scatter21_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz));
-    CU(cudaFuncSetAttribute(scatter21_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz));
-    CU(cudaFuncSetAttribute(scatter21_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz));
-    CU(cudaFuncSetAttribute(scatter21_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz));
-    CU(cudaFuncSetAttribute(scatter21_kernel<true, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz));
-    CU(cudaFuncSetAttribute(scatter21_kernel<false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz));
-    CU(cudaFuncSetAttribute(scatter_kmer_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz));
-    CU(cudaFuncSetAttribute(scatter_kmer_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz));
-    CU(cudaFuncSetAttribute(scatter_rec_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz));
-    CU(cudaFuncSetAttribute(scatter_rec_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz));
-    CU(cudaFuncSetAttribute(scatter_rec_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz));
-    done = true;
+// the tile-sort kernels need > 48 KB of dynamic shared memory when they carry side arrays. The
+// attribute is per DEVICE (per context), so it is set once per context, not once per process.
+static int scatter_attrs(p3_ctx *c) {
+    if (c->attrs_set) return P3_OK;
+    const int s21 = (int)sizeof(ScatterSmem21), sP = (int)sizeof(ScatterSmemT<true, false>), sPL = (int)sizeof(ScatterSmemT<true, true>);
+    CU(cudaFuncSetAttribute(scatter21_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, s21));
+    CU(cudaFuncSetAttribute(scatter21_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, s21));
+    CU(cudaFuncSetAttribute(scatter21_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, s21));
+    CU(cudaFuncSetAttribute(scatter21_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, s21));
+    CU(cudaFuncSetAttribute(scatter21_kernel<true, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s21));
+    CU(cudaFuncSetAttribute(scatter21_kernel<false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s21));
+    CU(cudaFuncSetAttribute(scatter_kmer_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sPL));
+    CU(cudaFuncSetAttribute(scatter_kmer_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sPL));
+    CU(cudaFuncSetAttribute(scatter_kmer_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sPL));
+    CU(cudaFuncSetAttribute(scatter_kmer_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sPL));
+    CU(cudaFuncSetAttribute(scatter_rec_kernel<0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sPL));
+    CU(cudaFuncSetAttribute(scatter_rec_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sP));
+    CU(cudaFuncSetAttribute(scatter_rec_kernel<3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sP));
+    CU(cudaFuncSetAttribute(scatter_rec_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sPL));
+    c->attrs_set = true;
     return P3_OK;
 }
-
-static int count_binned(p3_ctx *c, uint64_t upper) {
-    int rc0 = scatter_attrs();
-    if (rc0) return rc0;
-    const uint32_t P = c->parts;
+static int hist_buffers(p3_ctx *c) {
     if (!c->d_ghist) {
         CU(cudaMalloc(&c->d_ghist, sizeof(unsigned long long) * (kMaxParts + 1)));
         CU(cudaMalloc(&c->d_cursor, sizeof(unsigned long long) * (kMaxParts + 1)));
     }
-    CU(ensure(c->d_valid, c->cap_valid, sizeof(uint32_t) * (c->n_words + 1)));
-    // candidates: one per distinct key, never more than slots or positions
-    c->cand_cap = std::min<uint64_t>(c->nb * 4, std::max<uint64_t>(upper, 1));
-    CU(ensure(c->d_cand_slot, c->cap_cand_slot, sizeof(uint64_t) * c->cand_cap));
-    CU(ensure(c->d_cand_pos, c->cap_cand_pos, sizeof(uint64_t) * c->cand_cap));
-    // chunk the words so that the bins (12 B per position) fit the memory budget
-    size_t fr = 0, tot = 0;
-    CU(cudaMemGetInfo(&fr, &tot));
-    uint64_t have = c->cap_bkeys + c->cap_bword;
-    uint64_t budget = (uint64_t)(0.7 * (double)(fr + have));
-    if (const char *e = getenv("P3_BIN_BUDGET_BYTES")) budget = strtoull(e, nullptr, 10);
-    uint64_t chunk_words = std::max<uint64_t>(budget / (13 * 32), kTileWords);
-    chunk_words = std::min<uint64_t>(chunk_words / kTileWords * kTileWords, (c->n_words + kTileWords - 1) / kTileWords * kTileWords);
-    if (chunk_words == 0) chunk_words = kTileWords;
-    // Fixed-capacity bins: the partition of a key is a hash, so a chunk's records spread evenly over
-    // the partitions; each gets room for its expected share + 3 % + 8192 and the histogram pass
-    // (hist21, 12 ms at configs[1]) is skipped. A partition that overflows anyway (heavy-hitter
-    // keys: satellites, homopolymers) is seen in its cursor and the chunk is redone with exact bins.
-    const bool want_fixed = !getenv("P3_EXACT_BINS");
-    const double pos_per_word = std::min(32.0, c->n_words ? (double)upper / (double)c->n_words : 32.0);
-    auto fixed_cap = [&](uint64_t words) -> uint64_t {
-        uint64_t share = (uint64_t)((double)words * pos_per_word / (double)P * 1.03) + 8192;
-        return (share + kSweepChunk - 1) / kSweepChunk * kSweepChunk;
+    return scatter_attrs(c);
+}
+static cudaEvent_t pool_event(p3_ctx *c, size_t i) {
+    while (c->evpool.size() <= i) { cudaEvent_t e; cudaEventCreate(&e); c->evpool.push_back(e); }
+    return c->evpool[i];
+}
+constexpr size_t kSmem21 = sizeof(ScatterSmem21), kSmemP = sizeof(ScatterSmemT<true, false>), kSmemPL = sizeof(ScatterSmemT<true, true>);
+
+extern "C++" {
+template <bool HAS_MASK>
+static void launch_scatter21_local(p3_ctx *c, unsigned sblocks, uint64_t w0, uint64_t w1, uint32_t P, uint64_t cap) {
+    scatter21_kernel<HAS_MASK, 0><<<sblocks, kScatterThreads, kSmem21, c->stream>>>(
+        c->d_packed, c->d_rend, HAS_MASK ? c->d_nmask : nullptr, w0, w1, P, c->d_cursor, c->d_bkeys, c->d_bword, c->d_valid, 0, c->d_stats, PeerOut(), cap);
+}
+}  // extern "C++"
+static void launch_insert_bins(p3_ctx *c, const uint64_t *keys, const uint32_t *words, uint64_t n, uint64_t cap,
+                               const unsigned long long *bin_end, const unsigned long long *n_dev) {
+    (void)words;
+    if (c->probe_stats) insert_bins_kernel<true><<<c->grid(3), 256, 0, c->stream>>>(keys, n, c->table(), c->ovf(), c->d_stats, cap, bin_end, n_dev);
+    else insert_bins_kernel<false><<<c->grid(3), 256, 0, c->stream>>>(keys, n, c->table(), c->ovf(), c->d_stats, cap, bin_end, n_dev);
+}
+
+// Plan of the binned count: how many words per chunk so that the bins (12 B per record) fit, and the
+// fixed bin capacity. exact = false: fixed-capacity bins — the partition of a key is a hash, so a chunk's
+// records spread evenly over the partitions; each gets room for its expected share + 3 % + 8192 and no
+// histogram pass is needed. A partition that overflows anyway (heavy-hitter keys: satellites,
+// homopolymers) raises Stats::err_bin_overflow on the device; the caller then redoes the stage with exact
+// (histogram-sized) bins. Nothing inside the chunk loop waits for the device.
+struct BinPlan { uint64_t chunk_words = 0; double pos_per_word = 32; uint32_t P = 1; bool exact = false; };
+static uint64_t plan_fixed_cap(const BinPlan &pl, uint64_t words) {
+    uint64_t share = (uint64_t)((double)words * pl.pos_per_word / (double)pl.P * 1.03) + 8192;
+    return (share + kSweepChunk - 1) / kSweepChunk * kSweepChunk;
+}
+static int plan_bins(p3_ctx *c, uint64_t upper, bool exact, BinPlan *pl) {
+    int rc0 = hist_buffers(c);
+    if (rc0) return rc0;
+    if (!c->d_binmeta) CU(cudaMalloc(&c->d_binmeta, sizeof(unsigned long long) * (kMaxParts + 2)));
+    pl->P = c->parts; pl->exact = exact;
+    pl->pos_per_word = std::min(32.0, c->n_words ? (double)upper / (double)c->n_words : 32.0);
+    auto records_for = [&](uint64_t words) -> uint64_t {
+        return std::max<uint64_t>(words * 32, exact ? 0 : plan_fixed_cap(*pl, words) * pl->P);
     };
-    uint64_t rec_cap = std::max<uint64_t>(chunk_words * 32, want_fixed ? fixed_cap(std::min(chunk_words, c->n_words)) * P : 0);
+    // the device is only asked for its free memory when the bins have to grow
+    const uint64_t all_words = std::max<uint64_t>((c->n_words + kTileWords - 1) / kTileWords * kTileWords, kTileWords);
+    uint64_t chunk_words = all_words;
+    const char *benv = getenv("P3_BIN_BUDGET_BYTES");
+    if (benv || records_for(std::min(all_words, c->n_words)) * 12 > c->cap_bkeys + c->cap_bword) {
+        uint64_t budget;
+        if (benv) budget = strtoull(benv, nullptr, 10);
+        else {
+            size_t fr = 0, tot = 0;
+            CU(cudaMemGetInfo(&fr, &tot));
+            budget = (uint64_t)(0.7 * (double)(fr + c->cap_bkeys + c->cap_bword));
+        }
+        chunk_words = std::max<uint64_t>(budget / (13 * 32), kTileWords) / kTileWords * kTileWords;
+        chunk_words = std::min<uint64_t>(std::max<uint64_t>(chunk_words, kTileWords), all_words);
+    }
+    pl->chunk_words = chunk_words;
+    const uint64_t rec_cap = records_for(std::min(chunk_words, c->n_words));
     CU(ensure(c->d_bkeys, c->cap_bkeys, sizeof(uint64_t) * rec_cap));
     CU(ensure(c->d_bword, c->cap_bword, sizeof(uint32_t) * rec_cap));
-    c->n_chunks = 0; c->binned_pos = 0;
-    for (int i = 0; i < 4; i++) c->ms_sub[i] = 0;
-    std::vector<unsigned long long> h_cur(P);
-    CU(cudaEventRecord(c->ev[0], c->stream));
-    for (uint64_t w0 = 0; w0 < c->n_words; w0 += chunk_words) {
-        uint64_t w1 = std::min<uint64_t>(w0 + chunk_words, c->n_words);
-        unsigned sblocks = (unsigned)std::min<uint64_t>((w1 - w0 + kTileWords - 1) / kTileWords, (uint64_t)c->n_sm * 3);
-        unsigned long long n_rec = 0;
-        uint64_t cap = want_fixed ? fixed_cap(w1 - w0) : 0;
-        CU(cudaEventRecord(c->ev[10], c->stream));
-        CU(cudaEventRecord(c->ev[11], c->stream));
-        if (cap) {
-            init_cursors_kernel<<<1, 256, 0, c->stream>>>(c->d_cursor, P, cap);
-            if (c->d_nmask) scatter21_kernel<true, 0><<<sblocks, kScatterThreads, sizeof(ScatterSmem), c->stream>>>(c->d_packed, c->d_rend, c->d_nmask, w0, w1, P, c->d_cursor, c->d_bkeys, c->d_bword, c->d_valid, 0, PeerOut(), cap);
-            else scatter21_kernel<false, 0><<<sblocks, kScatterThreads, sizeof(ScatterSmem), c->stream>>>(c->d_packed, c->d_rend, nullptr, w0, w1, P, c->d_cursor, c->d_bkeys, c->d_bword, c->d_valid, 0, PeerOut(), cap);
-            CU(cudaGetLastError());
-            c->launches += 2;
-            CU(cudaMemcpyAsync(h_cur.data(), c->d_cursor, sizeof(unsigned long long) * P, cudaMemcpyDeviceToHost, c->stream));
-            CU(cudaStreamSynchronize(c->stream));
-            for (uint32_t q = 0; q < P; q++) {
-                unsigned long long cnt = h_cur[q] - (unsigned long long)q * cap;
-                if (cnt > cap) { cap = 0; break; }     // overflow: exact bins for this chunk
-                n_rec += cnt;
-            }
-        }
-        if (!cap) {
-            CU(cudaMemsetAsync(c->d_ghist, 0, sizeof(unsigned long long) * (kMaxParts + 1), c->stream));
-            CU(cudaEventRecord(c->ev[10], c->stream));
-            if (c->d_nmask) hist21_kernel<true, 0><<<c->grid(), 256, 0, c->stream>>>(c->d_packed, c->d_rend, c->d_nmask, w0, w1, P, c->d_ghist);
-            else hist21_kernel<false, 0><<<c->grid(), 256, 0, c->stream>>>(c->d_packed, c->d_rend, nullptr, w0, w1, P, c->d_ghist);
-            scan_parts_kernel<<<1, 256, 0, c->stream>>>(c->d_ghist, P, c->d_cursor, c->d_ghist + kMaxParts);
-            CU(cudaEventRecord(c->ev[11], c->stream));
-            if (c->d_nmask) scatter21_kernel<true, 0><<<sblocks, kScatterThreads, sizeof(ScatterSmem), c->stream>>>(c->d_packed, c->d_rend, c->d_nmask, w0, w1, P, c->d_cursor, c->d_bkeys, c->d_bword, c->d_valid, 0);
-            else scatter21_kernel<false, 0><<<sblocks, kScatterThreads, sizeof(ScatterSmem), c->stream>>>(c->d_packed, c->d_rend, nullptr, w0, w1, P, c->d_cursor, c->d_bkeys, c->d_bword, c->d_valid, 0);
-            CU(cudaGetLastError());
-            c->launches += 3;
-            CU(cudaMemcpyAsync(&n_rec, c->d_ghist + kMaxParts, sizeof(n_rec), cudaMemcpyDeviceToHost, c->stream));
-            CU(cudaStreamSynchronize(c->stream));
-        }
-        CU(cudaEventRecord(c->ev[12], c->stream));
-        if (n_rec) {
-            CU(cudaMemsetAsync(&c->d_stats->work, 0, sizeof(unsigned long long), c->stream));
-            if (cap) insert_bins_kernel<<<c->grid(), 256, 0, c->stream>>>(c->d_bkeys, c->d_bword, (uint64_t)P * cap, c->table(), c->ovf(), c->d_stats, c->d_cand_slot, c->d_cand_pos, c->cand_cap, cap, c->d_cursor);
-            else insert_bins_kernel<<<c->grid(), 256, 0, c->stream>>>(c->d_bkeys, c->d_bword, n_rec, c->table(), c->ovf(), c->d_stats, c->d_cand_slot, c->d_cand_pos, c->cand_cap);
-            CU(cudaGetLastError());
+    CU(ensure(c->d_valid, c->cap_valid, sizeof(uint32_t) * (c->n_words + 1)));
+    return P3_OK;
+}
+// bins the 21-mers of words [w0, w1) by table partition into d_bkeys / d_bword; the bin ends (and, for
+// exact bins, the record total) are copied to d_binmeta, which no later kernel touches
+static int bin_chunk(p3_ctx *c, const BinPlan &pl, uint64_t w0, uint64_t w1, cudaEvent_t ev_hist_done) {
+    const uint32_t P = pl.P;
+    const unsigned sblocks = (unsigned)std::min<uint64_t>((w1 - w0 + kTileWords - 1) / kTileWords, (uint64_t)c->n_sm * 3);
+    const uint64_t cap = pl.exact ? 0 : plan_fixed_cap(pl, w1 - w0);
+    if (cap && c->up_pieces) {
+        // the reads are still arriving (p3_assemble_hot_path): bin piece by piece as the uploads complete, into the same bins
+        init_cursors_kernel<<<1, 256, 0, c->stream>>>(c->d_cursor, P, cap);
+        if (ev_hist_done) CU(cudaEventRecord(ev_hist_done, c->stream));
+        for (uint64_t i = 0; i < c->up_pieces; i++) {
+            CU(cudaStreamWaitEvent(c->stream, c->up_ev[i], 0));
+            const uint64_t a = std::max<uint64_t>(w0, i * c->up_piece_words), b = std::min<uint64_t>(w1, (i + 1) * c->up_piece_words);
+            if (b <= a) continue;
+            const unsigned sb = (unsigned)std::min<uint64_t>((b - a + kTileWords - 1) / kTileWords, (uint64_t)c->n_sm * 3);
+            if (c->d_nmask) launch_scatter21_local<true>(c, sb, a, b, P, cap);
+            else launch_scatter21_local<false>(c, sb, a, b, P, cap);
             c->launches++;
         }
-        CU(cudaEventRecord(c->ev[13], c->stream));
-        CU(cudaEventSynchronize(c->ev[13]));
-        {
-            float a = 0, b = 0, d = 0;
-            cudaEventElapsedTime(&a, c->ev[10], c->ev[11]);
-            cudaEventElapsedTime(&b, c->ev[11], c->ev[12]);
-            cudaEventElapsedTime(&d, c->ev[12], c->ev[13]);
-            c->ms_sub[0] += a; c->ms_sub[1] += b; c->ms_sub[2] += d;
-        }
-        c->binned_pos += n_rec;        // accumulated on the host (records == valid positions)
+        c->up_pieces = 0;
+        check_cursors_kernel<<<1, 256, 0, c->stream>>>(c->d_cursor, P, cap, c->d_stats);
+    } else if (cap) {
+        init_cursors_kernel<<<1, 256, 0, c->stream>>>(c->d_cursor, P, cap);
+        if (ev_hist_done) CU(cudaEventRecord(ev_hist_done, c->stream));
+        if (c->d_nmask) launch_scatter21_local<true>(c, sblocks, w0, w1, P, cap);
+        else launch_scatter21_local<false>(c, sblocks, w0, w1, P, cap);
+        check_cursors_kernel<<<1, 256, 0, c->stream>>>(c->d_cursor, P, cap, c->d_stats);
+    } else {
+        CU(cudaMemsetAsync(c->d_ghist, 0, sizeof(unsigned long long) * (kMaxParts + 1), c->stream));
+        if (c->d_nmask) hist21_kernel<true, 0><<<c->grid(), 256, 0, c->stream>>>(c->d_packed, c->d_rend, c->d_nmask, w0, w1, P, c->d_ghist);
+        else hist21_kernel<false, 0><<<c->grid(), 256, 0, c->stream>>>(c->d_packed, c->d_rend, nullptr, w0, w1, P, c->d_ghist);
+        scan_parts_kernel<<<1, 256, 0, c->stream>>>(c->d_ghist, P, c->d_cursor, c->d_ghist + kMaxParts);
+        if (ev_hist_done) CU(cudaEventRecord(ev_hist_done, c->stream));
+        if (c->d_nmask) launch_scatter21_local<true>(c, sblocks, w0, w1, P, 0);
+        else launch_scatter21_local<false>(c, sblocks, w0, w1, P, 0);
+        CU(cudaMemcpyAsync(c->d_binmeta + kMaxParts, c->d_ghist + kMaxParts, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, c->stream));
+    }
+    CU(cudaMemcpyAsync(c->d_binmeta, c->d_cursor, sizeof(unsigned long long) * P, cudaMemcpyDeviceToDevice, c->stream));
+    c->launches += 3;
+    CU(cudaGetLastError());
+    c->bin_cap = cap;
+    c->bin_n = cap ? (uint64_t)P * cap : (w1 - w0) * 32;
+    return P3_OK;
+}
+// the main stream waits for every piece of a pending upload (paths that cannot consume it piece by piece)
+static void upload_wait_all(p3_ctx *c) {
+    for (uint64_t i = 0; i < c->up_pieces; i++) cudaStreamWaitEvent(c->stream, c->up_ev[i], 0);
+    c->up_pieces = 0;
+}
+static int count_binned(p3_ctx *c, uint64_t upper, bool exact) {
+    BinPlan pl;
+    int rc = plan_bins(c, upper, exact, &pl);
+    if (rc) return rc;
+    if (c->up_pieces && pl.chunk_words < c->n_words) upload_wait_all(c);   // several chunks: no piecewise binning
+    c->n_chunks = 0; c->bins_valid = false;
+    for (int i = 0; i < 4; i++) c->ms_sub[i] = 0;
+    CU(cudaEventRecord(c->ev[0], c->stream));
+    for (uint64_t w0 = 0; w0 < c->n_words; w0 += pl.chunk_words) {
+        const uint64_t w1 = std::min<uint64_t>(w0 + pl.chunk_words, c->n_words);
+        const size_t e = 4 * (size_t)c->n_chunks;
+        CU(cudaEventRecord(pool_event(c, e), c->stream));
+        rc = bin_chunk(c, pl, w0, w1, pool_event(c, e + 1));
+        if (rc) return rc;
+        CU(cudaEventRecord(pool_event(c, e + 2), c->stream));
+        CU(cudaMemsetAsync(&c->d_stats->work, 0, sizeof(unsigned long long), c->stream));
+        launch_insert_bins(c, c->d_bkeys, c->d_bword, c->bin_n, c->bin_cap, c->d_binmeta, c->bin_cap ? nullptr : c->d_binmeta + kMaxParts);
+        CU(cudaGetLastError());
+        c->launches++;
+        CU(cudaEventRecord(pool_event(c, e + 3), c->stream));
         c->n_chunks++;
     }
+    c->bins_valid = c->n_chunks == 1;   // the verdict sweep of MakeBF can reuse them
+    c->bin_upper = upper; c->bin_exact = exact;
     CU(cudaEventRecord(c->ev[1], c->stream));
     return P3_OK;
+}
+// sub-stage times of the chunks of the last count_binned (after the stream has been synchronised)
+static void count_binned_times(p3_ctx *c) {
+    for (uint64_t ci = 0; ci < c->n_chunks && 4 * ci + 3 < c->evpool.size(); ci++) {
+        float a = 0, b = 0, d = 0;
+        cudaEventElapsedTime(&a, c->evpool[4 * ci], c->evpool[4 * ci + 1]);
+        cudaEventElapsedTime(&b, c->evpool[4 * ci + 1], c->evpool[4 * ci + 2]);
+        cudaEventElapsedTime(&d, c->evpool[4 * ci + 2], c->evpool[4 * ci + 3]);
+        c->ms_sub[0] += a; c->ms_sub[1] += b; c->ms_sub[2] += d;
+    }
 }
 
 // allocate (or reuse) and clear the count table: partitions of ~24 MB each in binned mode so that
@@ -1189,6 +1389,7 @@ static int setup_table(p3_ctx *c, uint64_t table_slots) {
         c->nb = nb;
     }
     c->parts = P; c->nbp = nbp;
+    c->probe_stats = getenv("P3_PROBE_STATS") != nullptr;
     CU(cudaMemsetAsync(c->d_table, 0xFF, nb * 32, c->stream));
     CU(cudaMemsetAsync(c->d_ovf_keys, 0xFF, sizeof(uint64_t) * kOvfCap, c->stream));
     CU(cudaMemsetAsync(c->d_ovf_wraps, 0, sizeof(unsigned long long) * kOvfCap, c->stream));
@@ -1213,14 +1414,23 @@ int p3_count_short_kmers(p3_ctx *c, uint64_t table_slots) {
     }
     int rc = setup_table(c, table_slots);
     if (rc) return rc;
-    rc = c->binned ? count_binned(c, upper) : count_direct(c);
+    c->pos_on_host = false;
+    bool exact = getenv("P3_EXACT_BINS") != nullptr;
+    if (c->up_pieces && (!c->binned || exact)) upload_wait_all(c);
+    rc = c->binned ? count_binned(c, upper, exact) : count_direct(c);
     if (rc) return rc;
     rc = pull_stats(c);
     if (rc) return rc;
+    if (c->binned && c->h_stats.err_bin_overflow && !exact) {   // a heavy-hitter partition overflowed its fixed share: exact bins
+        rc = setup_table(c, table_slots);
+        if (!rc) rc = count_binned(c, upper, true);
+        if (!rc) rc = pull_stats(c);
+        if (rc) return rc;
+    }
+    if (c->binned) count_binned_times(c);
     CU(cudaEventElapsedTime(&c->ms[0], c->ev[0], c->ev[1]));
     if (c->h_stats.err_table_full) return fail(P3_ERR_TABLE_FULL, "21-mer count table full: raise table_slots");
     if (c->h_stats.err_ovf_full) return fail(P3_ERR_TABLE_FULL, "count overflow side table full");
-    if (c->binned && c->h_stats.n_cand > c->cand_cap) return fail(P3_ERR_TABLE_FULL, "candidate list overflow");
     c->have_counts = true;
     c->have_bf = c->have_solid = c->have_adj = false;  // buffers are kept for reuse
     return P3_OK;
@@ -1287,8 +1497,9 @@ static int alloc_bloom(p3_ctx *c, uint32_t k, uint64_t filter_size, uint32_t num
 // distinct canonical k-mers of the solid positions -> c->d_set / c->d_list (grows on overflow);
 // leaves n_distinct_solid in h_stats
 static int dedupe_solid_positions(p3_ctx *c, uint32_t k, uint64_t solid_slots) {
-    int rc0 = scatter_attrs();
+    int rc0 = hist_buffers(c);
     if (rc0) return rc0;
+    bool allow_binned = true;
     for (int attempt = 0;; attempt++) {
         // partitions of ~24 MB (one stays L2 resident under the binned sweep)
         uint64_t buckets = (solid_slots + 3) / 4;
@@ -1296,8 +1507,7 @@ static int dedupe_solid_positions(p3_ctx *c, uint32_t k, uint64_t solid_slots) {
         if (const char *e = getenv("P3_SET_PARTS")) want = strtoull(e, nullptr, 10);
         // At most 96 partitions: the tile sort of 4096 positions needs runs of a few dozen records per
         // partition to write coalesced (measured at configs[1]: 77 partitions 95 ms, 128 partitions 127 ms).
-        // A set too large for that (multi-GPU: every rank sees nearly all solid k-mers of the N-times larger
-        // genome) is left unpartitioned and filled directly: 135 ms binned vs 100 ms direct at 2 ranks.
+        // A larger set is left unpartitioned and filled directly.
         uint32_t P = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(want, 1), kMaxParts);
         if (!getenv("P3_SET_PARTS") && P > 96) P = 1;
         uint64_t nbp = std::max<uint64_t>((buckets + P - 1) / P, 1);
@@ -1315,39 +1525,39 @@ static int dedupe_solid_positions(p3_ctx *c, uint32_t k, uint64_t solid_slots) {
         CU(cudaMemsetAsync(c->d_set, 0xFF, nbs * 32, c->stream));
         CU(cudaMemsetAsync(&c->d_stats->n_distinct_solid, 0, sizeof(unsigned long long), c->stream));
         CU(cudaMemsetAsync(&c->d_stats->err_table_full, 0, sizeof(unsigned), c->stream));
+        CU(cudaMemsetAsync(&c->d_stats->err_kbin_overflow, 0, sizeof(unsigned), c->stream));
         // binned path: needs room for n_adds 8-byte records (+5 %) in the idle count-stage bins
         const uint64_t n_occ = c->h_stats.n_adds;
         bool binned = false;
         const char *force = getenv("P3_DEDUPE_BINNED");
-        if (force ? atoi(force) != 0 : (P >= 2 && n_occ >= (1u << 22))) {
+        if (allow_binned && (force ? atoi(force) != 0 : (P >= 2 && n_occ >= (1u << 22)))) {
             uint64_t cap = (uint64_t)((double)n_occ / (double)P * 1.05) + 8192;
             cap = (cap + kSweepChunk - 1) / kSweepChunk * kSweepChunk;
             const uint64_t need = sizeof(uint64_t) * cap * P;
-            if (!c->d_ghist) {
-                CU(cudaMalloc(&c->d_ghist, sizeof(unsigned long long) * (kMaxParts + 1)));
-                CU(cudaMalloc(&c->d_cursor, sizeof(unsigned long long) * (kMaxParts + 1)));
+            bool fits = c->cap_bkeys >= need;
+            if (!fits) {
+                size_t fr = 0, tot = 0;
+                CU(cudaMemGetInfo(&fr, &tot));
+                fits = need < (uint64_t)(0.5 * (double)(fr + c->cap_bkeys));
             }
-            size_t fr = 0, tot = 0;
-            CU(cudaMemGetInfo(&fr, &tot));
-            if (c->cap_bkeys >= need || need < (uint64_t)(0.5 * (double)fr)) {
+            if (fits) {
+                c->bins_valid = false;                                          // the count bins become the k-mer bins
                 CU(ensure(c->d_bkeys, c->cap_bkeys, need));
+                CU(ensure(c->d_bword, c->cap_bword, cap * P));                 // one hint byte per binned k-mer
+                CU(ensure(c->d_hint, c->cap_hint, nbs * 4));                   // one hint byte per set slot
+                CU(cudaMemsetAsync(c->d_hint, 0, nbs * 4, c->stream));
+                CU(cudaMemsetAsync(c->d_solid + c->n_words, 0, sizeof(uint32_t), c->stream));   // the hint of the last word looks one word ahead
                 init_cursors_kernel<<<1, 256, 0, c->stream>>>(c->d_cursor, P, cap);
                 unsigned sblocks = (unsigned)std::min<uint64_t>(std::max<uint64_t>((c->n_words + kTileWords - 1) / kTileWords, 1), (uint64_t)c->n_sm * 3);
-                if (c->d_nmask) scatter_kmer_kernel<true><<<sblocks, kScatterThreads, sizeof(ScatterSmem), c->stream>>>(c->d_packed, c->d_nmask, c->d_solid, c->n_words, (int)k, P, c->d_cursor, c->d_bkeys, cap);
-                else scatter_kmer_kernel<false><<<sblocks, kScatterThreads, sizeof(ScatterSmem), c->stream>>>(c->d_packed, nullptr, c->d_solid, c->n_words, (int)k, P, c->d_cursor, c->d_bkeys, cap);
-                c->launches += 2;
+                uint8_t *hb = reinterpret_cast<uint8_t *>(c->d_bword);
+                if (c->d_nmask) scatter_kmer_kernel<true, false><<<sblocks, kScatterThreads, kSmemPL, c->stream>>>(c->d_packed, c->d_nmask, c->d_solid, 0, c->n_words, (int)k, P, c->d_cursor, c->d_bkeys, hb, cap, c->d_stats);
+                else scatter_kmer_kernel<false, false><<<sblocks, kScatterThreads, kSmemPL, c->stream>>>(c->d_packed, nullptr, c->d_solid, 0, c->n_words, (int)k, P, c->d_cursor, c->d_bkeys, hb, cap, c->d_stats);
+                // a heavy-hitter partition that outgrew its bin dropped records: err_kbin_overflow, seen below
+                CU(cudaMemsetAsync(&c->d_stats->work, 0, sizeof(unsigned long long), c->stream));
+                set_sweep_kernel<<<c->grid(), 256, 0, c->stream>>>(c->d_bkeys, hb, (uint64_t)P * cap, cap, c->d_cursor, c->kset(), c->d_hint, c->d_stats);
+                c->launches += 3;
                 CU(cudaGetLastError());
-                std::vector<unsigned long long> h_cur(P);
-                CU(cudaMemcpyAsync(h_cur.data(), c->d_cursor, sizeof(unsigned long long) * P, cudaMemcpyDeviceToHost, c->stream));
-                CU(cudaStreamSynchronize(c->stream));
                 binned = true;
-                for (uint32_t q = 0; q < P; q++)
-                    if (h_cur[q] - (unsigned long long)q * cap > cap) { binned = false; break; }   // a heavy-hitter partition: direct path
-                if (binned) {
-                    CU(cudaMemsetAsync(&c->d_stats->work, 0, sizeof(unsigned long long), c->stream));
-                    set_sweep_kernel<<<c->grid(), 256, 0, c->stream>>>(c->d_bkeys, (uint64_t)P * cap, cap, c->d_cursor, c->kset(), c->d_stats);
-                    c->launches++;
-                }
             }
         }
         if (!binned) {
@@ -1357,11 +1567,19 @@ static int dedupe_solid_positions(p3_ctx *c, uint32_t k, uint64_t solid_slots) {
                 makebf_kernel<false><<<c->grid(), 256, 0, c->stream>>>(c->d_packed, nullptr, c->d_solid, c->n_words, (int)k, c->kset(), c->d_stats);
             c->launches++;
         }
-        compact_set_kernel<<<c->grid(), 256, 0, c->stream>>>(c->d_set, nbs * 4, c->d_list, c->list_cap, c->d_stats);
+        if (binned && (!c->d_adj || c->adj_cap < c->list_cap)) {   // the adjacency bytes start as the hints
+            dfree(c->d_adj);
+            c->adj_cap = c->list_cap;
+            CU(cudaMalloc(&c->d_adj, c->adj_cap));
+        }
+        compact_set_kernel<<<c->grid(), 256, 0, c->stream>>>(c->d_set, nbs * 4, c->d_list, c->list_cap, c->d_stats,
+                                                             binned ? reinterpret_cast<const uint8_t *>(c->d_hint) : nullptr, c->d_adj);
         c->launches++;
         CU(cudaGetLastError());
         int rc = pull_stats(c);
         if (rc) return rc;
+        if (binned && c->h_stats.err_kbin_overflow) { allow_binned = false; continue; }   // direct path, same capacity
+        c->hints_valid = binned;
         if (!c->h_stats.err_table_full) return P3_OK;
         if (attempt >= 16) return fail(P3_ERR_TABLE_FULL, "solid k-mer set full after growing");
         solid_slots = std::max<uint64_t>(solid_slots * 4, 1024);
@@ -1370,10 +1588,8 @@ static int dedupe_solid_positions(p3_ctx *c, uint32_t k, uint64_t solid_slots) {
 
 // dense BF.add over the first nd k-mers of c->d_list: binned by filter segment (p3_bloom.inc.cu);
 // tiny jobs and single-segment filters take the direct kernel, one pass per L2-sized segment
-static int bloom_add_list(p3_ctx *c, uint64_t nd) {
-    bool done = false;
-    int rcb = bloom_add_binned(c, nd, &done);
-    if (rcb || done) return rcb;
+static int bloom_add_direct(p3_ctx *c, uint64_t nd) {
+    if (c->k > 32) return bloom_add_direct_long(c, nd);
     uint64_t seg_bits = 40ull << 23;                       // 40 MB of filter per pass
     uint64_t n_seg = (c->filter_size + seg_bits - 1) / seg_bits;
     if (n_seg > 16 || nd * c->num_hashes < (1u << 22)) { n_seg = 1; seg_bits = c->filter_size; }   // huge filter / tiny job: one pass
@@ -1385,13 +1601,19 @@ static int bloom_add_list(p3_ctx *c, uint64_t nd) {
     CU(cudaGetLastError());
     return P3_OK;
 }
+static int bloom_add_list(p3_ctx *c, uint64_t nd) {
+    bool done = false;
+    int rcb = bloom_add_binned(c, nd, &done);
+    if (rcb || done) return rcb;
+    return bloom_add_direct(c, nd);
+}
 
 int p3_make_bf(p3_ctx *c, uint32_t k, uint64_t filter_size, uint32_t num_hashes, uint32_t cov_threshold,
                uint64_t solid_slots) {
     if (!c) return fail(P3_ERR_ARG, "null ctx");
     if (!c->have_counts) return fail(P3_ERR_STATE, "p3_make_bf: run p3_count_short_kmers first");
     CU(cudaSetDevice(c->device));
-    c->set_valid = false;
+    c->set_valid = false; c->hints_valid = false;
     int rc = alloc_bloom(c, k, filter_size, num_hashes);
     if (rc) return rc;
     uint64_t pw = c->n_words + 1;
@@ -1407,22 +1629,14 @@ int p3_make_bf(p3_ctx *c, uint32_t k, uint64_t filter_size, uint32_t num_hashes,
     CU(cudaMemsetAsync(c->d_good21 + c->n_words, 0, sizeof(uint32_t), c->stream));
 
     // B1: coverage flags
+    CU(cudaMemsetAsync(&c->d_stats->err_bin_overflow, 0, sizeof(unsigned), c->stream));
     CU(cudaEventRecord(c->ev[2], c->stream));
-    if (c->binned && cov_threshold == 2) {
-        // every valid position is good unless it is the single occurrence of a count-1 key
-        CU(cudaMemcpyAsync(c->d_good21, c->d_valid, sizeof(uint32_t) * c->n_words, cudaMemcpyDeviceToDevice, c->stream));
-        uint64_t nc = c->h_stats.n_cand;
-        bool cleared = false;
-        if (nc) {   // binned, L2-resident clears (p3_bloom.inc.cu); small jobs clear directly
-            int rcc = binned_plane_clear<0>(c, c->d_cand_slot, c->d_cand_pos, nc, cov_threshold, c->d_good21, c->n_words * 32, &cleared);
-            if (rcc) return rcc;
-        }
-        if (nc && !cleared) {
-            cand_check_kernel<<<c->grid(), 256, 0, c->stream>>>(c->d_table, c->d_cand_slot, c->d_cand_pos, nc, cov_threshold, c->ovf(), c->d_stats, c->d_good21);
-            c->launches++;
-        }
+    bool clears_binned = false;
+    if (c->binned) {
+        rc = verdict_sweep(c, cov_threshold, false, &clears_binned);
+        if (rc) return rc;
     } else {
-        const uint32_t *proven = (!c->binned && cov_threshold == 2) ? c->d_proven2 : nullptr;
+        const uint32_t *proven = cov_threshold == 2 ? c->d_proven2 : nullptr;
         if (c->d_nmask)
             flags21_kernel<true><<<c->grid(), 256, 0, c->stream>>>(c->d_packed, c->d_rend, c->d_nmask, c->n_words, c->table(), c->ovf(), c->d_stats, cov_threshold, proven, c->d_good21);
         else
@@ -1431,6 +1645,33 @@ int p3_make_bf(p3_ctx *c, uint32_t k, uint64_t filter_size, uint32_t num_hashes,
     }
     CU(cudaGetLastError());
     CU(cudaEventRecord(c->ev[3], c->stream));
+
+    // B2a: solid plane + n_adds; number of distinct good 21-mers sizes the solid set
+    auto solid_pass = [&]() -> int {
+        CU(cudaMemsetAsync(&c->d_stats->n_adds, 0, sizeof(unsigned long long), c->stream));
+        if (k > 32) return P3_OK;   // the multi-word path builds its own solid plane (p3_long.inc.cu)
+        solid_kernel<<<c->grid(), 256, 0, c->stream>>>(c->d_good21, c->n_words, (int)k, c->d_solid, c->d_stats);
+        c->launches++;
+        return P3_OK;
+    };
+    rc = solid_pass();
+    if (rc) return rc;
+    if (k <= 32 && solid_slots == 0) {
+        export_counts_kernel<<<c->grid(), 256, 0, c->stream>>>(c->d_table, c->nb * 4, c->ovf(), c->d_stats, cov_threshold, nullptr, nullptr, 0);
+        c->launches++;
+    }
+    rc = pull_stats(c);
+    if (rc) return rc;
+    if (clears_binned && c->h_stats.err_bin_overflow) {
+        // a plane segment outgrew its bin (positions of count-1 keys bunched up): clear directly — clearing a
+        // bit twice is harmless — and redo the solid plane
+        CU(cudaMemsetAsync(&c->d_stats->err_bin_overflow, 0, sizeof(unsigned), c->stream));
+        rc = verdict_sweep(c, cov_threshold, true, &clears_binned);
+        if (rc) return rc;
+        rc = solid_pass();
+        if (!rc) rc = pull_stats(c);
+        if (rc) return rc;
+    }
 
     if (k > 32) {   // multi-word k-mers: p3_long.inc.cu
         rc = make_bf_long(c, k, solid_slots);
@@ -1443,15 +1684,6 @@ int p3_make_bf(p3_ctx *c, uint32_t k, uint64_t filter_size, uint32_t num_hashes,
         c->d_set_b = nullptr; c->nbs_b = 0; c->parts_b = 1;
         return P3_OK;
     }
-    // B2a: solid plane + n_adds; number of distinct good 21-mers sizes the solid set
-    solid_kernel<<<c->grid(), 256, 0, c->stream>>>(c->d_good21, c->n_words, (int)k, c->d_solid, c->d_stats);
-    c->launches++;
-    if (solid_slots == 0) {
-        export_counts_kernel<<<c->grid(), 256, 0, c->stream>>>(c->d_table, c->nb * 4, c->ovf(), c->d_stats, cov_threshold, nullptr, nullptr, 0);
-        c->launches++;
-    }
-    rc = pull_stats(c);
-    if (rc) return rc;
     if (solid_slots == 0) {
         uint64_t est = std::min<uint64_t>(c->h_stats.n_adds, (uint64_t)(1.25 * (double)c->h_stats.n_good21) + 1024);
         solid_slots = std::max<uint64_t>(2 * est, 1024);
@@ -1469,7 +1701,14 @@ int p3_make_bf(p3_ctx *c, uint32_t k, uint64_t filter_size, uint32_t num_hashes,
     seeds_kernel<<<c->grid(4), 256, 0, c->stream>>>(c->d_off, c->n_reads, c->d_solid, (int)k, c->d_seed);
     c->launches++;
     CU(cudaEventRecord(c->ev[6], c->stream));
-    CU(cudaStreamSynchronize(c->stream));
+    rc = pull_stats(c);
+    if (rc) return rc;
+    if (c->h_stats.err_bin_overflow) {   // a filter segment outgrew its bin: add directly (OR is idempotent)
+        CU(cudaMemsetAsync(&c->d_stats->err_bin_overflow, 0, sizeof(unsigned), c->stream));
+        rc = bloom_add_direct(c, c->h_stats.n_distinct_solid);
+        if (!rc) rc = pull_stats(c);
+        if (rc) return rc;
+    }
     CU(cudaEventElapsedTime(&c->ms_bloom, c->ev[14], c->ev[15]));
     CU(cudaEventElapsedTime(&c->ms[1], c->ev[2], c->ev[3]));
     CU(cudaEventElapsedTime(&c->ms[2], c->ev[4], c->ev[5]));
@@ -1499,7 +1738,7 @@ int p3_bf_import(p3_ctx *c, uint32_t k, uint64_t filter_size, uint32_t num_hashe
     CU(cudaSetDevice(c->device));
     int rc = alloc_bloom(c, k, filter_size, num_hashes);
     if (rc) return rc;
-    c->set_valid = false; c->have_solid = false; c->have_adj = false;
+    c->set_valid = false; c->hints_valid = false; c->have_solid = false; c->have_adj = false;
     CU(cudaMemsetAsync(c->d_bloom, 0, sizeof(uint32_t) * c->bloom_words, c->stream));
     if (h_bits) CU(cudaMemcpyAsync(c->d_bloom, h_bits, (filter_size + 7) / 8, cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));
@@ -1600,7 +1839,10 @@ int p3_dbg_adjacency(p3_ctx *c) {
             if (!strcmp(e, "owned")) sb = p3_ctx::no_set();
             else if (!strcmp(e, "none")) sa = sb = p3_ctx::no_set();
         }
-        adjacency_kernel<<<c->grid(), 256, 0, c->stream>>>(c->d_list, n, (int)c->k, c->bloom(), sa, sb, c->d_adj, c->d_stats);
+        if (c->hints_valid) {   // hinted directions need no query; the rest go straight to the filter (a set lookup would only add an access)
+            if (getenv("P3_ADJ_SET") && !strcmp(getenv("P3_ADJ_SET"), "hint+set")) adjacency_kernel<true><<<c->grid(), 256, 0, c->stream>>>(c->d_list, n, (int)c->k, c->bloom(), sa, sb, c->d_adj, c->d_stats);
+            else adjacency_kernel<true><<<c->grid(), 256, 0, c->stream>>>(c->d_list, n, (int)c->k, c->bloom(), p3_ctx::no_set(), p3_ctx::no_set(), c->d_adj, c->d_stats);
+        } else adjacency_kernel<false><<<c->grid(), 256, 0, c->stream>>>(c->d_list, n, (int)c->k, c->bloom(), sa, sb, c->d_adj, c->d_stats);
         c->launches++;
         CU(cudaGetLastError());
     }
@@ -1626,7 +1868,7 @@ int p3_dbg_close(p3_ctx *c, const uint64_t *h_roots, uint64_t n_roots, uint64_t 
         if (to <= from) return P3_OK;
         uint64_t nn = to - from, warps = (nn + 3) / 4;
         unsigned blocks = (unsigned)std::min<uint64_t>((warps + 7) / 8, (uint64_t)c->grid());
-        adjacency_kernel<<<blocks, 256, 0, c->stream>>>(c->d_list + from, nn, (int)c->k, c->bloom(), p3_ctx::no_set(), p3_ctx::no_set(), c->d_adj + from, nullptr);
+        adjacency_kernel<false><<<blocks, 256, 0, c->stream>>>(c->d_list + from, nn, (int)c->k, c->bloom(), p3_ctx::no_set(), p3_ctx::no_set(), c->d_adj + from, nullptr);
         c->launches++;
         CU(cudaGetLastError());
         return P3_OK;
@@ -1705,7 +1947,7 @@ int p3_check_directions(p3_ctx *c, const uint64_t *h_kmers, uint64_t n, uint8_t 
     CU(cudaMalloc(&dout, n));
     uint64_t warps = (n + 3) / 4;
     unsigned blocks = (unsigned)std::min<uint64_t>((warps + 7) / 8, (uint64_t)c->grid());
-    adjacency_kernel<<<blocks, 256, 0, c->stream>>>(dk, n, (int)c->k, c->bloom(), c->set_valid ? c->kset() : p3_ctx::no_set(), (c->set_valid && c->d_set_b) ? c->kset_b() : p3_ctx::no_set(), dout, nullptr);
+    adjacency_kernel<false><<<blocks, 256, 0, c->stream>>>(dk, n, (int)c->k, c->bloom(), c->set_valid ? c->kset() : p3_ctx::no_set(), (c->set_valid && c->d_set_b) ? c->kset_b() : p3_ctx::no_set(), dout, nullptr);
     c->launches++;
     CU(cudaMemcpyAsync(h_mask, dout, n, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
@@ -1714,21 +1956,89 @@ int p3_check_directions(p3_ctx *c, const uint64_t *h_kmers, uint64_t n, uint8_t 
 }
 
 // ---- whole path ----------------------------------------------------------------------------------
-int p3_assemble_hot_path(p3_ctx *c, const uint64_t *h_packed, uint64_t total_bases, const uint64_t *h_off,
+// upload for the whole-path entry points: offsets (and the non-ACGT plane) on the main stream, the 2-bit staging in
+// pieces on the copy stream, one event per piece; the count bins a piece as soon as it is there
+static int upload_pieces(p3_ctx *c, const uint64_t *h_packed, uint64_t total_bases, const uint64_t *h_off, uint64_t n_reads, const uint32_t *h_nmask) {
+    if (!h_packed || !h_off) return fail(P3_ERR_ARG, "p3_assemble_hot_path: null argument");
+    CU(cudaSetDevice(c->device));
+    if (!c->copy_stream) {
+        CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming));
+    }
+    c->have_reads = false;
+    c->total_bases = total_bases; c->n_reads = n_reads; c->n_words = (total_bases + 31) / 32;
+    const uint64_t pw = c->n_words + 1;
+    CU(ensure(c->own_packed, c->cap_packed, sizeof(uint64_t) * pw));
+    CU(ensure(c->own_off, c->cap_off, sizeof(uint64_t) * (n_reads + 1)));
+    CU(cudaMemcpyAsync(c->own_off, h_off, sizeof(uint64_t) * (n_reads + 1), cudaMemcpyHostToDevice, c->stream));
+    if (h_nmask) {
+        CU(ensure(c->own_nmask, c->cap_nmask, sizeof(uint32_t) * pw));
+        CU(cudaMemcpyAsync(c->own_nmask, h_nmask, sizeof(uint32_t) * pw, cudaMemcpyHostToDevice, c->stream));
+    }
+    // the copy stream may only overwrite the staging once the main stream's earlier kernels are done with it
+    CU(cudaEventRecord(c->ev_main, c->stream));
+    CU(cudaStreamWaitEvent(c->copy_stream, c->ev_main, 0));
+    const uint64_t pieces = std::min<uint64_t>(std::max<uint64_t>(c->n_words >> 22, 1), 16);
+    const uint64_t piece_words = ((c->n_words + pieces - 1) / pieces + kTileWords - 1) / kTileWords * kTileWords;
+    while (c->up_ev.size() < pieces) { cudaEvent_t e; CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c->up_ev.push_back(e); }
+    for (uint64_t i = 0; i < pieces; i++) {
+        const uint64_t a = std::min<uint64_t>(i * piece_words, pw), b = std::min<uint64_t>((i + 1) * piece_words + 1, pw);   // + the hand-off word
+        if (b > a) CU(cudaMemcpyAsync(c->own_packed + a, h_packed + a, sizeof(uint64_t) * (b - a), cudaMemcpyHostToDevice, c->copy_stream));
+        CU(cudaEventRecord(c->up_ev[i], c->copy_stream));
+    }
+    c->up_pieces = pieces; c->up_piece_words = std::max<uint64_t>(piece_words, 1);
+    c->d_packed = c->own_packed; c->d_off = c->own_off; c->d_nmask = h_nmask ? c->own_nmask : nullptr;
+    return finish_reads(c);   // the read-end plane only needs the offsets
+}
+static int hot_path_impl(p3_ctx *c, const uint64_t *h_packed, uint64_t total_bases, const uint64_t *h_off,
                          uint64_t n_reads, const uint32_t *h_nmask, uint64_t all_bases, uint32_t k,
-                         uint64_t filter_size, uint32_t num_hashes, uint64_t table_slots, uint64_t solid_slots) {
+                         uint64_t filter_size, uint32_t num_hashes, uint64_t table_slots, uint64_t solid_slots,
+                         uint8_t *h_bits, int64_t *h_seed_pos, uint64_t *h_kmers, uint8_t *h_adj, uint64_t cap, uint64_t *n_out) {
     if (!c) return fail(P3_ERR_ARG, "null ctx");
     if (filter_size == 0) {
         int rc = p3_estimate_bloomfilter(all_bases, k, &filter_size, &num_hashes);
         if (rc) return rc;
     }
-    int rc = p3_reads_upload(c, h_packed, total_bases, h_off, n_reads, h_nmask);
-    if (rc) return rc;
-    rc = p3_count_short_kmers(c, table_slots);
+    int rc = upload_pieces(c, h_packed, total_bases, h_off, n_reads, h_nmask);
+    if (!rc) rc = p3_count_short_kmers(c, table_slots);
+    if (c->up_pieces) upload_wait_all(c);
     if (rc) return rc;
     rc = p3_make_bf(c, k, filter_size, num_hashes, P3_COV_THRESHOLD, solid_slots);
     if (rc) return rc;
-    return p3_dbg_adjacency(c);
+    const bool want_out = h_bits || h_seed_pos || h_kmers || h_adj;
+    const uint64_t nd = c->h_stats.n_distinct_solid, W = (2 * (uint64_t)k + 63) / 64;
+    if (n_out) *n_out = nd;
+    if (want_out && (h_kmers || h_adj) && cap < nd) return fail(P3_ERR_ARG, "p3_assemble_hot_path_to_host: capacity too small");
+    if (want_out) {   // filter, seeds and k-mers are final now: they leave on the copy stream while CheckDirections runs
+        CU(cudaEventRecord(c->ev_main, c->stream));
+        CU(cudaStreamWaitEvent(c->copy_stream, c->ev_main, 0));
+        if (h_bits) CU(cudaMemcpyAsync(h_bits, c->d_bloom, (c->filter_size + 7) / 8, cudaMemcpyDeviceToHost, c->copy_stream));
+        if (h_seed_pos) CU(cudaMemcpyAsync(h_seed_pos, c->d_seed, sizeof(int64_t) * c->n_reads, cudaMemcpyDeviceToHost, c->copy_stream));
+        if (h_kmers && nd) CU(cudaMemcpyAsync(h_kmers, k > 32 ? long_words(c) : c->d_list, sizeof(uint64_t) * nd * W, cudaMemcpyDeviceToHost, c->copy_stream));
+        CU(cudaEventRecord(c->ev_copy, c->copy_stream));
+    }
+    rc = p3_dbg_adjacency(c);
+    if (rc) return rc;
+    if (want_out) {
+        if (h_adj && nd) CU(cudaMemcpyAsync(h_adj, c->d_adj, nd, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamWaitEvent(c->stream, c->ev_copy, 0));
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    return P3_OK;
+}
+int p3_assemble_hot_path(p3_ctx *c, const uint64_t *h_packed, uint64_t total_bases, const uint64_t *h_off,
+                         uint64_t n_reads, const uint32_t *h_nmask, uint64_t all_bases, uint32_t k,
+                         uint64_t filter_size, uint32_t num_hashes, uint64_t table_slots, uint64_t solid_slots) {
+    return hot_path_impl(c, h_packed, total_bases, h_off, n_reads, h_nmask, all_bases, k, filter_size, num_hashes, table_slots, solid_slots,
+                         nullptr, nullptr, nullptr, nullptr, 0, nullptr);
+}
+int p3_assemble_hot_path_to_host(p3_ctx *c, const uint64_t *h_packed, uint64_t total_bases, const uint64_t *h_off,
+                                 uint64_t n_reads, const uint32_t *h_nmask, uint64_t all_bases, uint32_t k,
+                                 uint64_t filter_size, uint32_t num_hashes, uint64_t table_slots, uint64_t solid_slots,
+                                 uint8_t *h_bits, int64_t *h_seed_pos, uint64_t *h_kmers, uint8_t *h_adj, uint64_t cap, uint64_t *n) {
+    return hot_path_impl(c, h_packed, total_bases, h_off, n_reads, h_nmask, all_bases, k, filter_size, num_hashes, table_slots, solid_slots,
+                         h_bits, h_seed_pos, h_kmers, h_adj, cap, n);
 }
 
 int p3_count_substage_ms(p3_ctx *c, float ms[4], uint32_t *parts, uint64_t *chunks) {

@@ -292,12 +292,7 @@ static void long_release(p3_ctx *c) {
     g_long.erase(c);
 }
 
-static int bloom_add_words(p3_ctx *c, const uint64_t *d_words, uint64_t n) {
-    if (d_words == g_long.get(c).d_words) {   // the context's own k-mer list: binned adds (p3_bloom.inc.cu)
-        bool done = false;
-        int rcb = bloom_add_binned(c, n, &done);
-        if (rcb || done) return rcb;
-    }
+static int bloom_add_words_direct(p3_ctx *c, const uint64_t *d_words, uint64_t n) {
     LongK L = make_longk(c->k);
     uint64_t seg_bits = 40ull << 23;
     uint64_t n_seg = (c->filter_size + seg_bits - 1) / seg_bits;
@@ -309,6 +304,15 @@ static int bloom_add_words(p3_ctx *c, const uint64_t *d_words, uint64_t n) {
     }
     CU(cudaGetLastError());
     return P3_OK;
+}
+static int bloom_add_direct_long(p3_ctx *c, uint64_t nd) { return bloom_add_words_direct(c, g_long.get(c).d_words, nd); }
+static int bloom_add_words(p3_ctx *c, const uint64_t *d_words, uint64_t n) {
+    if (d_words == g_long.get(c).d_words) {   // the context's own k-mer list: binned adds (p3_bloom.inc.cu)
+        bool done = false;
+        int rcb = bloom_add_binned(c, n, &done);
+        if (rcb || done) return rcb;
+    }
+    return bloom_add_words_direct(c, d_words, n);
 }
 
 // stage B for k > 32; the coverage plane (good21) is ready, planes are allocated, filter allocated
@@ -362,7 +366,14 @@ static int make_bf_long(p3_ctx *c, uint32_t k, uint64_t solid_slots) {
     seeds_kernel<<<c->grid(4), 256, 0, c->stream>>>(c->d_off, c->n_reads, c->d_solid, (int)k, c->d_seed);
     c->launches++;
     CU(cudaEventRecord(c->ev[6], c->stream));
-    CU(cudaStreamSynchronize(c->stream));
+    rc = pull_stats(c);
+    if (rc) return rc;
+    if (c->h_stats.err_bin_overflow) {   // a filter segment outgrew its bin: add directly (OR is idempotent)
+        CU(cudaMemsetAsync(&c->d_stats->err_bin_overflow, 0, sizeof(unsigned), c->stream));
+        rc = bloom_add_words_direct(c, ls.d_words, nd);
+        if (!rc) rc = pull_stats(c);
+        if (rc) return rc;
+    }
     return P3_OK;
 }
 

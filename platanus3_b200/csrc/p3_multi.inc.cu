@@ -1,91 +1,109 @@
-// p3_multi.inc.cu — multi-GPU building blocks (DESIGN.md row e), part of the p3_gpu.cu translation
-// unit. One process per GPU; the exchanges themselves (all-to-all, filter OR-reduce) are done by
-// the caller with torch.distributed/NCCL on the device buffers these entry points fill or read:
+// p3_multi.inc.cu — multi-GPU hot path (DESIGN.md row e), part of the p3_gpu.cu translation unit.
+// One process per GPU. Canonical k-mers are hash-partitioned: the OWNER of a key counts it / de-duplicates
+// it. Per-rank work does not grow with the number of ranks:
 //
-//   every rank : bin its 21-mers by OWNER rank          p3_mg_owner_hist / p3_mg_owner_scatter
-//   all-to-all of the count records (12 B each)
-//   owner      : binned, L2-resident insert             p3_mg_count_begin / _records / _end
-//   owner      : singleton verdicts by source rank      p3_mg_singletons
-//   all-to-all of the positions (8 B each)
-//   every rank : coverage plane, solid plane, seeds,    p3_mg_cover_begin / _clear, p3_mg_solid_local
-//                locally distinct solid k-mers
-//   every rank : bin those k-mers by owner              p3_mg_kmer_owner_hist / _scatter
-//   all-to-all of the k-mers (8 B each)
-//   owner      : de-duplicate, BF.add into its copy     p3_mg_owned_begin / _insert / _end
-//   OR-reduce of the filter copies                      p3_mg_filter gives the buffer
-//   owner      : CheckDirections of its k-mers          p3_dbg_adjacency (filter is complete & local)
+//   A   every rank bins its 21-mers by owner; the binning kernel stores owner j's records STRAIGHT INTO
+//       rank j's receive region over NVLink peer memory (bin + exchange are one kernel). The owner sorts
+//       what it received into its table-partition bins (which persist over the chunks) and, after the
+//       last chunk, counts everything in ONE L2-resident insert sweep.
+//   B1  the owner sweeps its bins a second time: records of keys whose count stayed below the threshold
+//       go back to their source rank (sorted by rank, peer stores), which clears those coverage bits.
+//   B2  solid plane and seeds are local. Every solid OCCURRENCE (canonical k-mer + adjacency hint, 9 B)
+//       goes to the owner of the k-mer the same way; the owner sorts them by set partition and
+//       de-duplicates them in one L2-resident sweep that also ORs the hints together.
+//   B3  Bloom adds: sharded filter (p3_bloom.inc.cu), all-gather of the shards.
+//   C   CheckDirections of the owned k-mers: hinted directions are known, the others probe the filter.
+//
+// Every rank owns ONE peer-visible arena: [PeerCtl | receive set 0 | receive set 1]. A set is a row of
+// n_ranks regions (region r = what source rank r sent). Stages alternate between the two sets, so one
+// cross-rank barrier per step is enough (see p3_mg_sync). The barrier is a one-block kernel that writes
+// an epoch into every peer's PeerCtl and spins on its own — no host round trip, no NCCL call.
+// Transport 1 ("staged") writes the same regions into a local staging buffer instead and leaves the
+// movement to the caller's all-to-all (NCCL): the baseline the fused path is measured against.
 
-__global__ void __launch_bounds__(256)
-singleton_list_kernel(const uint64_t *__restrict__ slots, const uint64_t *__restrict__ cand_slot,
-                      const uint64_t *__restrict__ cand_pos, uint64_t n_cand, uint64_t thr, Ovf ovf,
-                      Stats *st, uint64_t *__restrict__ out) {
-    __shared__ unsigned s_wtot[8];
-    __shared__ unsigned long long s_base;
-    const unsigned n_overflow = st->n_overflow;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    uint64_t stride = gridDim.x * (uint64_t)blockDim.x;
-    uint64_t n_round = (n_cand + stride - 1) / stride;
-    for (uint64_t r = 0; r < n_round; r++) {
-        uint64_t j = r * stride + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-        bool single = false;
-        uint64_t pos = 0;
-        if (j < n_cand) {
-            uint64_t v = __ldcg(slots + __ldcs(cand_slot + j));
-            uint64_t c = v >> 42;
-            if (c < thr && n_overflow) c += ovf_get(ovf, v & kKey42) << 22;
-            single = c < thr;
-            if (single) pos = __ldcs(cand_pos + j);
-        }
-        unsigned m = __ballot_sync(0xffffffffu, single);
-        if (lane == 0) s_wtot[wid] = __popc(m);
+constexpr int kCtlBytes = 4096;
+struct PeerCtl {
+    unsigned long long flag[kMaxPeers];         // flag[r]: last barrier epoch rank r announced to this rank
+    unsigned long long count[2][kMaxPeers];     // count[set][r]: records source r stored into region r of receive set `set`
+};
+struct PeerLinks { unsigned char *arena[kMaxPeers]; };
+struct PeerOut64 { uint64_t *p[kMaxPeers]; };
+
+__global__ void peer_sync_kernel(PeerLinks L, int me, int n, unsigned long long epoch, Stats *st) {
+    const int j = threadIdx.x;
+    if (j >= n) return;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&reinterpret_cast<PeerCtl *>(L.arena[j])->flag[me]), "l"(epoch) : "memory");
+    const unsigned long long *mine = &reinterpret_cast<PeerCtl *>(L.arena[me])->flag[j];
+    unsigned long long v = 0;
+    const long long t0 = clock64();
+    for (;;) {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
+        if (v >= epoch) break;
+        if (clock64() - t0 > 60000000000LL) { atomicExch(&st->err_peer_timeout, 1u); break; }   // ~30 s: a peer died
+        __nanosleep(500);
+    }
+}
+// count[set][me] of every destination rank := what this rank sent there (peer stores; the barrier that follows publishes them)
+__global__ void publish_counts_kernel(PeerLinks L, int me, int n, int set, const unsigned long long *__restrict__ sent) {
+    const int j = threadIdx.x;
+    if (j < n) reinterpret_cast<PeerCtl *>(L.arena[j])->count[set][me] = sent[j];
+}
+// staged transport: the counts travel with the caller's all-to-all; this only lines them up
+__global__ void stage_counts_kernel(unsigned long long *dst, const unsigned long long *__restrict__ sent, int n) {
+    const int j = threadIdx.x;
+    if (j < n) dst[j] = sent[j];
+}
+
+// tile sort of a position list by source rank (the top byte) into the ranks' regions
+__global__ void __launch_bounds__(kScatterThreads, 3)
+scatter_pos_peer_kernel(const uint64_t *__restrict__ in, uint64_t n, const unsigned long long *__restrict__ n_dev, uint32_t P,
+                        unsigned long long *cursor, PeerOut64 out, uint64_t cap, Stats *st) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    using SM = ScatterSmemT<true, false>;
+    SM &sm = *reinterpret_cast<SM *>(smem_raw);
+    constexpr int NT = kScatterThreads, PER = kTilePos / NT;
+    const int tid = threadIdx.x;
+    if (n_dev) n = min(n, (uint64_t)*n_dev);
+    const uint64_t n_tiles = (n + kTilePos - 1) / kTilePos;
+    bool over = false;
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (uint32_t i = tid; i < P; i += NT) sm.hist[i] = 0;
         __syncthreads();
-        unsigned wbase = 0, total = 0;
+        const uint64_t t0 = tile * kTilePos;
+        uint64_t rec[PER];
+        uint32_t rk[PER / 2];
 #pragma unroll
-        for (int q = 0; q < 8; q++) { unsigned t = s_wtot[q]; if (q < wid) wbase += t; total += t; }
-        if (threadIdx.x == 0 && total) s_base = atomicAdd(&st->n_export, (unsigned long long)total);
-        __syncthreads();
-        if (single) out[s_base + wbase + __popc(m & ((1u << lane) - 1))] = pos;
-        __syncthreads();
-    }
-}
-
-__global__ void clear_positions_kernel(const uint64_t *__restrict__ pos, uint64_t n, uint32_t *good21) {
-    uint64_t stride = gridDim.x * (uint64_t)blockDim.x;
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
-        uint64_t p = __ldcs(pos + i) & ((1ULL << kPosRankShift) - 1);
-        atomicAnd(good21 + (p >> 5), ~(0x80000000u >> (p & 31)));
-    }
-}
-
-// Coverage verdicts without a list, a sort and an all-to-all: the owner looks at each of its
-// first-occurrence candidates and, when the key's final count stayed below the threshold, clears the
-// position's bit straight in the SOURCE rank's coverage plane (RED.AND over NVLink peer memory; the
-// rank is the top byte of the position record).
-struct PeerPlanes { uint32_t *p[kMaxPeers]; };
-__global__ void __launch_bounds__(256)
-cand_check_peer_kernel(const uint64_t *__restrict__ slots, const uint64_t *__restrict__ cand_slot,
-                       const uint64_t *__restrict__ cand_pos, uint64_t n_cand, uint64_t thr, Ovf ovf,
-                       const Stats *st, PeerPlanes planes) {
-    const unsigned n_overflow = st->n_overflow;
-    uint64_t stride = gridDim.x * (uint64_t)blockDim.x;
-    for (uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; j < n_cand; j += stride) {
-        uint64_t v = __ldcg(slots + __ldcs(cand_slot + j));
-        uint64_t c = v >> 42;
-        if (c < thr && n_overflow) c += ovf_get(ovf, v & kKey42) << 22;
-        if (c < thr) {
-            uint64_t rec = __ldcs(cand_pos + j);
-            uint64_t pos = rec & ((1ULL << kPosRankShift) - 1);
-            atomicAnd(planes.p[(rec >> kPosRankShift) & (kMaxPeers - 1)] + (pos >> 5), ~(0x80000000u >> (pos & 31)));
+        for (int j = 0; j < PER; j++) {
+            uint64_t i = t0 + j * NT + tid;
+            rec[j] = i < n ? __ldcs(in + i) : 0;
+            if ((j & 1) == 0) rk[j >> 1] = 0;
+            if (i < n) rk[j >> 1] |= atomicAdd(&sm.hist[pid_of<2>(rec[j], P)], 1u) << (16 * (j & 1));
         }
+        __syncthreads();
+        tile_scan_and_claim<NT>(sm, P, cursor, tid);
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < PER; j++) {
+            uint64_t i = t0 + j * NT + tid;
+            if (i < n) {
+                uint32_t pt = pid_of<2>(rec[j], P);
+                uint32_t idx = sm.hist[pt] + ((rk[j >> 1] >> (16 * (j & 1))) & 0xFFFFu);
+                sm.key[idx] = rec[j];
+                sm.part[idx] = (uint16_t)pt;
+            }
+        }
+        __syncthreads();
+        const uint32_t total = sm.total;
+        for (uint32_t i = tid; i < total; i += NT) {
+            uint32_t pt = sm.part[i];
+            unsigned long long dst = sm.gbase[pt] + (i - sm.hist[pt]);
+            if (dst < cap) out.p[pt][dst] = sm.key[i];
+            else over = true;
+        }
+        __syncthreads();
     }
-}
-
-__global__ void set_insert_list_kernel(const uint64_t *__restrict__ kmers, uint64_t n, KSet set, Stats *st) {
-    uint64_t stride = gridDim.x * (uint64_t)blockDim.x;
-    bool full = false;
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += stride)
-        if (set_insert(set, __ldcs(kmers + i)) < 0) full = true;
-    if (full) atomicExch(&st->err_table_full, 1u);
+    if (over) atomicExch(&st->err_bin_overflow, 1u);
 }
 
 // host-side copy of owner_of (for tests and for callers that route on the host)
@@ -93,19 +111,23 @@ static inline uint32_t owner_of_host(uint64_t key, uint32_t n) {
     return (uint32_t)(((unsigned __int128)owner_mix(key) * n) >> 64);
 }
 
-struct MgState {   // extra per-context state of the multi-GPU path
-    uint64_t *d_sing = nullptr, *d_sing2 = nullptr; uint64_t cap_sing = 0, cap_sing2 = 0;
-    uint64_t *d_set2 = nullptr, *d_list2 = nullptr; uint64_t nbs2 = 0; uint32_t parts2 = 1;
-    uint64_t rec_cap = 0;
-    uint64_t n_local = 0;
-    // receive buffers of the fused bin + exchange (peers store into them over NVLink); plain
-    // cudaMalloc allocations so that cudaIpcGetMemHandle can export them to the other processes
-    // (two sets: chunk c+1 is received while chunk c is being inserted)
-    uint64_t *d_rkeys[2] = {nullptr, nullptr}; uint32_t *d_rwords[2] = {nullptr, nullptr};
-    uint64_t cap_rkeys[2] = {0, 0}, cap_rwords[2] = {0, 0};
-    // the fused bin + exchange kernel of the NEXT chunk runs on its own stream with its own cursors
-    cudaStream_t stream2 = nullptr; unsigned long long *d_cursor2 = nullptr;
-    bool swapped = false;   // c->d_set/d_list currently hold the OWNED set (p3_mg_owned_end swapped them in)
+struct MgState {   // per-context state of the multi-GPU path
+    uint32_t n_ranks = 0, my_rank = 0; int transport = 0; bool emulated = false, connected = false;
+    unsigned char *arena = nullptr; uint64_t arena_bytes = 0, set_bytes = 0;
+    unsigned char *staging = nullptr; uint64_t cap_staging = 0;         // transport 1: one set worth of send regions
+    unsigned long long *d_stage_cnt = nullptr;                          // transport 1: counts lined up for the all-to-all
+    PeerLinks links;
+    unsigned long long epoch = 0;
+    unsigned long long *d_sent = nullptr;                               // [kMaxParts + 1] per-destination cursors of the current send
+    // A
+    uint64_t chunk_words = 0, n_chunks = 0, capA = 0, part_cap = 0;
+    // B1
+    uint64_t *d_sing = nullptr; uint64_t cap_sing = 0; uint64_t capB = 0; uint32_t n_slices = 0;
+    // B2
+    uint64_t capK = 0, kpart_cap = 0; uint32_t k = 0;
+    std::vector<void *> graveyard;   // outgrown peer-visible buffers: freed with the context, never while peers may map them
+    unsigned char *set_ptr(uint32_t rank, int set) const { return links.arena[rank] + kCtlBytes + (uint64_t)set * set_bytes; }
+    PeerCtl *ctl() const { return reinterpret_cast<PeerCtl *>(arena); }
 };
 static CtxStates<MgState> g_mg;
 
@@ -113,133 +135,30 @@ static void mg_release(p3_ctx *c) {
     MgState *mp = g_mg.find(c);
     if (!mp) return;
     MgState &m = *mp;
-    dfree(m.d_sing); dfree(m.d_sing2); dfree(m.d_set2); dfree(m.d_list2);
-    for (int i = 0; i < 2; i++) { dfree(m.d_rkeys[i]); dfree(m.d_rwords[i]); }
-    dfree(m.d_cursor2);
-    if (m.stream2) cudaStreamDestroy(m.stream2);
+    dfree(m.arena); dfree(m.staging); dfree(m.d_stage_cnt); dfree(m.d_sent); dfree(m.d_sing);
+    for (void *p : m.graveyard) cudaFree(p);
     g_mg.erase(c);
 }
-
-static int mg_scan(p3_ctx *c, uint32_t P, uint64_t *h_counts) {
-    scan_parts_kernel<<<1, 256, 0, c->stream>>>(c->d_ghist, P, c->d_cursor, c->d_ghist + kMaxParts);
-    c->launches++;
-    if (h_counts) {
-        std::vector<unsigned long long> h(P);
-        CU(cudaMemcpyAsync(h.data(), c->d_ghist, sizeof(unsigned long long) * P, cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaStreamSynchronize(c->stream));
-        for (uint32_t i = 0; i < P; i++) h_counts[i] = h[i];
-    }
+static int mg_ready(p3_ctx *c, MgState **out, const char *who) {
+    if (!c) return fail(P3_ERR_ARG, "null ctx");
+    MgState *m = g_mg.find(c);
+    if (!m || !m->connected) return fail(P3_ERR_STATE, std::string(who) + ": run p3_mg_arena and p3_mg_connect first");
+    CU(cudaSetDevice(c->device));
+    *out = m;
     return P3_OK;
 }
-static int mg_hist_buffers(p3_ctx *c) {
-    if (!c->d_ghist) {
-        CU(cudaMalloc(&c->d_ghist, sizeof(unsigned long long) * (kMaxParts + 1)));
-        CU(cudaMalloc(&c->d_cursor, sizeof(unsigned long long) * (kMaxParts + 1)));
-    }
-    return scatter_attrs();
-}
+// records per region of a receive set for records of `bytes` bytes each (keys block + aux block), a multiple of the sort tile
+static uint64_t region_cap(const MgState &m, uint64_t bytes) { return m.set_bytes / m.n_ranks / bytes / kTilePos * kTilePos; }
+// where this rank's records for destination j go: peer transport = region my_rank of rank j's set, staged = region j of the local staging
+static unsigned char *dest_block(const MgState &m, uint32_t j, int set) { return m.transport == 0 ? m.set_ptr(j, set) : m.staging; }
+static uint32_t dest_region(const MgState &m, uint32_t j) { return m.transport == 0 ? m.my_rank : j; }
 
 extern "C" {
 
 uint32_t p3_owner_of_key(uint64_t key, uint32_t n_ranks) { return n_ranks ? owner_of_host(key, n_ranks) : 0; }
 
-int p3_mg_owner_hist(p3_ctx *c, uint32_t n_ranks, uint64_t w0, uint64_t w1, uint64_t *h_counts) {
-    if (!c || !c->have_reads) return fail(P3_ERR_STATE, "p3_mg_owner_hist: no reads attached");
-    if (n_ranks == 0 || n_ranks > 256 || w1 > c->n_words || w0 > w1) return fail(P3_ERR_ARG, "p3_mg_owner_hist: bad arguments");
-    CU(cudaSetDevice(c->device));
-    int rc = mg_hist_buffers(c);
-    if (rc) return rc;
-    CU(cudaMemsetAsync(c->d_ghist, 0, sizeof(unsigned long long) * (kMaxParts + 1), c->stream));
-    if (c->d_nmask) hist21_kernel<true, 1><<<c->grid(), 256, 0, c->stream>>>(c->d_packed, c->d_rend, c->d_nmask, w0, w1, n_ranks, c->d_ghist);
-    else hist21_kernel<false, 1><<<c->grid(), 256, 0, c->stream>>>(c->d_packed, c->d_rend, nullptr, w0, w1, n_ranks, c->d_ghist);
-    c->launches++;
-    CU(cudaGetLastError());
-    return mg_scan(c, n_ranks, h_counts);
-}
-
-// must follow p3_mg_owner_hist with the same arguments (it consumes the cursors that call set up)
-int p3_mg_owner_scatter(p3_ctx *c, uint32_t n_ranks, uint32_t my_rank, uint64_t w0, uint64_t w1,
-                        uint64_t *d_keys, uint32_t *d_words) {
-    if (!c || !c->have_reads || !d_keys || !d_words) return fail(P3_ERR_STATE, "p3_mg_owner_scatter: no reads / null buffers");
-    if (my_rank >= n_ranks || n_ranks > 256) return fail(P3_ERR_ARG, "p3_mg_owner_scatter: bad rank");
-    CU(cudaSetDevice(c->device));
-    CU(ensure(c->d_valid, c->cap_valid, sizeof(uint32_t) * (c->n_words + 1)));
-    unsigned sblocks = (unsigned)std::min<uint64_t>(std::max<uint64_t>((w1 - w0 + kTileWords - 1) / kTileWords, 1), (uint64_t)c->n_sm * 3);
-    const uint64_t tag = (uint64_t)my_rank << kRecRankShift;
-    if (c->d_nmask) scatter21_kernel<true, 1><<<sblocks, kScatterThreads, sizeof(ScatterSmem), c->stream>>>(c->d_packed, c->d_rend, c->d_nmask, w0, w1, n_ranks, c->d_cursor, d_keys, d_words, c->d_valid, tag);
-    else scatter21_kernel<false, 1><<<sblocks, kScatterThreads, sizeof(ScatterSmem), c->stream>>>(c->d_packed, c->d_rend, nullptr, w0, w1, n_ranks, c->d_cursor, d_keys, d_words, c->d_valid, tag);
-    c->launches++;
-    CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(c->stream));
-    return P3_OK;
-}
-
-// Fused bin + exchange: like p3_mg_owner_scatter, but owner j's records are stored straight to
-// keys_base[j] / words_base[j] — device pointers into rank j's receive buffer that are mapped into
-// this process (NVLink peer memory: p3_ipc_open of the owner's p3_mg_recv_buffers), already offset to
-// the region reserved for this source rank (sizes from the all-gathered p3_mg_owner_hist counts). The
-// caller synchronises all ranks before the owners read their buffers.
-int p3_mg_owner_scatter_peer(p3_ctx *c, uint32_t n_ranks, uint32_t my_rank, uint64_t w0, uint64_t w1,
-                             const uint64_t *keys_base, const uint64_t *words_base, int async) {
-    if (!c || !c->have_reads || !keys_base || !words_base) return fail(P3_ERR_STATE, "p3_mg_owner_scatter_peer: no reads / null buffers");
-    if (my_rank >= n_ranks || n_ranks > kMaxPeers) return fail(P3_ERR_ARG, "p3_mg_owner_scatter_peer: at most 16 ranks");
-    CU(cudaSetDevice(c->device));
-    int rc = mg_hist_buffers(c);
-    if (rc) return rc;
-    MgState &m = g_mg.get(c);
-    if (!m.stream2) {
-        CU(cudaStreamCreateWithFlags(&m.stream2, cudaStreamNonBlocking));
-        CU(cudaMalloc(&m.d_cursor2, sizeof(unsigned long long) * (kMaxParts + 1)));
-    }
-    if (!c->d_valid || c->cap_valid < sizeof(uint32_t) * (c->n_words + 1)) {
-        CU(cudaStreamSynchronize(m.stream2));   // nothing in flight may still write the old plane
-        CU(ensure(c->d_valid, c->cap_valid, sizeof(uint32_t) * (c->n_words + 1)));
-    }
-    PeerOut po;
-    for (uint32_t j = 0; j < (uint32_t)kMaxPeers; j++) {
-        po.keys[j] = j < n_ranks ? (uint64_t *)(uintptr_t)keys_base[j] : nullptr;
-        po.words[j] = j < n_ranks ? (uint32_t *)(uintptr_t)words_base[j] : nullptr;
-    }
-    // positions inside each destination region are relative: cursors start at zero. The kernel runs
-    // on the second stream so that it can overlap the owner-side insert of the previous chunk.
-    cudaStream_t st = m.stream2;
-    CU(cudaMemsetAsync(m.d_cursor2, 0, sizeof(unsigned long long) * (kMaxParts + 1), st));
-    unsigned sblocks = (unsigned)std::min<uint64_t>(std::max<uint64_t>((w1 - w0 + kTileWords - 1) / kTileWords, 1), (uint64_t)c->n_sm * 3);
-    const uint64_t tag = (uint64_t)my_rank << kRecRankShift;
-    if (c->d_nmask) scatter21_kernel<true, 1, true><<<sblocks, kScatterThreads, sizeof(ScatterSmem), st>>>(c->d_packed, c->d_rend, c->d_nmask, w0, w1, n_ranks, m.d_cursor2, nullptr, nullptr, c->d_valid, tag, po);
-    else scatter21_kernel<false, 1, true><<<sblocks, kScatterThreads, sizeof(ScatterSmem), st>>>(c->d_packed, c->d_rend, nullptr, w0, w1, n_ranks, m.d_cursor2, nullptr, nullptr, c->d_valid, tag, po);
-    c->launches++;
-    CU(cudaGetLastError());
-    if (!async) CU(cudaStreamSynchronize(st));
-    return P3_OK;
-}
-// waits for an async p3_mg_owner_scatter_peer of this context
-int p3_mg_scatter_wait(p3_ctx *c) {
-    if (!c) return fail(P3_ERR_ARG, "null ctx");
-    MgState *mp = g_mg.find(c);
-    if (!mp || !mp->stream2) return P3_OK;
-    CU(cudaSetDevice(c->device));
-    CU(cudaStreamSynchronize(mp->stream2));
-    return P3_OK;
-}
-
-// receive buffers for n_records count records (grow-only; a grown buffer is a NEW allocation, whose
-// handle has to be exported again)
-int p3_mg_recv_buffers(p3_ctx *c, uint64_t n_records, uint32_t which, uint64_t **d_keys, uint32_t **d_words) {
-    if (!c || which > 1) return fail(P3_ERR_ARG, "p3_mg_recv_buffers: null ctx / buffer index > 1");
-    CU(cudaSetDevice(c->device));
-    MgState &m = g_mg.get(c);
-    n_records = std::max<uint64_t>(n_records, 1);
-    CU(ensure(m.d_rkeys[which], m.cap_rkeys[which], sizeof(uint64_t) * n_records));
-    CU(ensure(m.d_rwords[which], m.cap_rwords[which], sizeof(uint32_t) * n_records));
-    if (d_keys) *d_keys = m.d_rkeys[which];
-    if (d_words) *d_words = m.d_rwords[which];
-    return P3_OK;
-}
-
-// CUDA IPC plumbing for the peer buffers (one process per GPU): export a cudaMalloc'ed buffer of this
-// process as a 64-byte handle / map another process's buffer into this one (NVLink peer access is
-// enabled on first use)
+// CUDA IPC plumbing for the arenas (one process per GPU): export a cudaMalloc'ed buffer of this process as a
+// 64-byte handle / map another process's buffer into this one (NVLink peer access is enabled on first use)
 int p3_ipc_export(const void *d_ptr, uint8_t handle[64]) {
     if (!d_ptr || !handle) return fail(P3_ERR_ARG, "p3_ipc_export: null argument");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
@@ -263,127 +182,213 @@ int p3_ipc_close(int device, void *d_ptr) {
     return P3_OK;
 }
 
-int p3_mg_count_begin(p3_ctx *c, uint64_t table_slots, uint64_t max_records_per_call) {
+// The peer-visible arena of this rank: control block + two receive sets of set_bytes each (the same value on every
+// rank). transport 0 = peers store into it over NVLink (export it with p3_ipc_export), 1 = staged: a local send
+// buffer of one set is added and the caller moves the regions with an all-to-all. A grown arena is a NEW
+// allocation (export it again); the old one is kept until the context is destroyed because peers may still map it.
+int p3_mg_arena(p3_ctx *c, uint32_t n_ranks, uint32_t my_rank, uint64_t set_bytes, int transport, void **d_arena) {
     if (!c) return fail(P3_ERR_ARG, "null ctx");
-    if (table_slots == 0) return fail(P3_ERR_ARG, "p3_mg_count_begin: table_slots required");
+    if (n_ranks == 0 || n_ranks > (uint32_t)kMaxPeers || my_rank >= n_ranks) return fail(P3_ERR_ARG, "p3_mg_arena: 1..16 ranks");
+    if (transport != 0 && transport != 1) return fail(P3_ERR_ARG, "p3_mg_arena: transport 0 (peer) or 1 (staged)");
     CU(cudaSetDevice(c->device));
-    int rc = mg_hist_buffers(c);
-    if (rc) return rc;
-    c->binned = true;
-    rc = setup_table(c, table_slots);
-    if (rc) return rc;
     MgState &m = g_mg.get(c);
-    m.rec_cap = std::max<uint64_t>(max_records_per_call, 1);
-    CU(ensure(c->d_bkeys, c->cap_bkeys, sizeof(uint64_t) * m.rec_cap));
-    CU(ensure(c->d_bword, c->cap_bword, sizeof(uint32_t) * m.rec_cap));
-    c->cand_cap = c->nb * 4;
-    CU(ensure(c->d_cand_slot, c->cap_cand_slot, sizeof(uint64_t) * c->cand_cap));
-    CU(ensure(c->d_cand_pos, c->cap_cand_pos, sizeof(uint64_t) * c->cand_cap));
-    c->binned_pos = 0; c->n_chunks = 0;
-    for (int i = 0; i < 4; i++) c->ms_sub[i] = 0;
-    c->have_counts = false;
+    set_bytes = std::max<uint64_t>((set_bytes + 4095) / 4096 * 4096, (uint64_t)n_ranks * kTilePos * 12);
+    const uint64_t need = kCtlBytes + 2 * set_bytes;
+    if (!m.arena || m.arena_bytes != need) {
+        if (m.arena) m.graveyard.push_back(m.arena);
+        m.arena = nullptr;
+        if (cudaMalloc((void **)&m.arena, need) != cudaSuccess) { cudaGetLastError(); return fail(P3_ERR_NOMEM, "p3_mg_arena: allocation failed"); }
+        m.arena_bytes = need;
+        CU(cudaMemsetAsync(m.arena, 0, kCtlBytes, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        m.epoch = 0;
+    }
+    m.set_bytes = set_bytes; m.n_ranks = n_ranks; m.my_rank = my_rank; m.transport = transport; m.connected = false;
+    if (transport == 1) {
+        CU(ensure(m.staging, m.cap_staging, set_bytes));
+        if (!m.d_stage_cnt) CU(cudaMalloc(&m.d_stage_cnt, sizeof(unsigned long long) * kMaxPeers));
+    }
+    if (!m.d_sent) CU(cudaMalloc(&m.d_sent, sizeof(unsigned long long) * (kMaxParts + 1)));
+    if (d_arena) *d_arena = m.arena;
     return P3_OK;
 }
-
-int p3_mg_count_records(p3_ctx *c, const uint64_t *d_keys, const uint32_t *d_words, uint64_t n) {
-    if (!c) return fail(P3_ERR_ARG, "null ctx");
-    if (n == 0) return P3_OK;
-    CU(cudaSetDevice(c->device));
-    const uint32_t P = c->parts;
-    // fixed-capacity partition bins, as in the single-GPU count (p3_gpu.cu count_binned): no histogram
-    // pass over the received records unless a partition overflows its share + 3 % + 8192
-    uint64_t cap = getenv("P3_EXACT_BINS") ? 0 : (((uint64_t)((double)n / (double)P * 1.03) + 8192 + kSweepChunk - 1) / kSweepChunk * kSweepChunk);
-    const uint64_t rec_cap = std::max<uint64_t>(n, cap * P);
-    CU(ensure(c->d_bkeys, c->cap_bkeys, sizeof(uint64_t) * rec_cap));   // local bins grow with the largest batch
-    CU(ensure(c->d_bword, c->cap_bword, sizeof(uint32_t) * rec_cap));
-    unsigned sblocks = (unsigned)std::min<uint64_t>((n + kTilePos - 1) / kTilePos, (uint64_t)c->n_sm * 3);
-    CU(cudaEventRecord(c->ev[10], c->stream));
-    CU(cudaEventRecord(c->ev[11], c->stream));
-    if (cap) {
-        init_cursors_kernel<<<1, 256, 0, c->stream>>>(c->d_cursor, P, cap);
-        scatter_rec_kernel<0, true><<<sblocks, kScatterThreads, sizeof(ScatterSmem), c->stream>>>(d_keys, d_words, n, P, c->d_cursor, c->d_bkeys, c->d_bword, cap);
-        c->launches += 2;
-        CU(cudaGetLastError());
-        std::vector<unsigned long long> h_cur(P);
-        CU(cudaMemcpyAsync(h_cur.data(), c->d_cursor, sizeof(unsigned long long) * P, cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaStreamSynchronize(c->stream));
-        for (uint32_t q = 0; q < P; q++)
-            if (h_cur[q] - (unsigned long long)q * cap > cap) { cap = 0; break; }
-    }
-    if (!cap) {
-        CU(cudaMemsetAsync(c->d_ghist, 0, sizeof(unsigned long long) * (kMaxParts + 1), c->stream));
-        CU(cudaEventRecord(c->ev[10], c->stream));
-        hist_rec_kernel<0><<<c->grid(), 256, 0, c->stream>>>(d_keys, n, P, c->d_ghist);
-        int rc = mg_scan(c, P, nullptr);
-        if (rc) return rc;
-        CU(cudaEventRecord(c->ev[11], c->stream));
-        scatter_rec_kernel<0, true><<<sblocks, kScatterThreads, sizeof(ScatterSmem), c->stream>>>(d_keys, d_words, n, P, c->d_cursor, c->d_bkeys, c->d_bword);
-        c->launches += 3;
-    }
-    CU(cudaEventRecord(c->ev[12], c->stream));
-    CU(cudaMemsetAsync(&c->d_stats->work, 0, sizeof(unsigned long long), c->stream));
-    if (cap) insert_bins_kernel<<<c->grid(), 256, 0, c->stream>>>(c->d_bkeys, c->d_bword, (uint64_t)P * cap, c->table(), c->ovf(), c->d_stats, c->d_cand_slot, c->d_cand_pos, c->cand_cap, cap, c->d_cursor);
-    else insert_bins_kernel<<<c->grid(), 256, 0, c->stream>>>(c->d_bkeys, c->d_bword, n, c->table(), c->ovf(), c->d_stats, c->d_cand_slot, c->d_cand_pos, c->cand_cap);
-    CU(cudaEventRecord(c->ev[13], c->stream));
+// arena_ptrs[r] = rank r's arena as mapped into this process (p3_ipc_open; this rank's own pointer at my_rank).
+// same_stream != 0: all ranks are contexts of ONE process that launch on ONE stream (the emulated communicator of the
+// tests); stream order then replaces the barrier.
+int p3_mg_connect(p3_ctx *c, const uint64_t *arena_ptrs, int same_stream) {
+    if (!c || !arena_ptrs) return fail(P3_ERR_ARG, "p3_mg_connect: null argument");
+    MgState *mp = g_mg.find(c);
+    if (!mp || !mp->arena) return fail(P3_ERR_STATE, "p3_mg_connect: run p3_mg_arena first");
+    MgState &m = *mp;
+    for (uint32_t j = 0; j < (uint32_t)kMaxPeers; j++) m.links.arena[j] = j < m.n_ranks ? (unsigned char *)(uintptr_t)arena_ptrs[j] : nullptr;
+    if (m.links.arena[m.my_rank] != m.arena) return fail(P3_ERR_ARG, "p3_mg_connect: arena_ptrs[my_rank] is not this rank's arena");
+    m.emulated = same_stream != 0;
+    m.connected = true;
+    return P3_OK;
+}
+// Cross-rank barrier on the context's stream: everything this rank stored into its peers before is visible to
+// them after, and the other way round. One per step is enough because the stages alternate between the two
+// receive sets: a rank can only enter step s+1's barrier after it has consumed step s, so nobody overwrites a
+// set that is still being read. Also needed once at the start of every stage. Staged transport / one rank /
+// same-stream emulation: nothing to do (the all-to-all resp. the stream orders the steps).
+int p3_mg_sync(p3_ctx *c) {
+    MgState *m;
+    int rc = mg_ready(c, &m, "p3_mg_sync");
+    if (rc) return rc;
+    if (m->n_ranks == 1 || m->emulated || m->transport == 1) return P3_OK;
+    m->epoch++;
+    peer_sync_kernel<<<1, 32, 0, c->stream>>>(m->links, (int)m->my_rank, (int)m->n_ranks, m->epoch, c->d_stats);
     c->launches++;
     CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(c->stream));
-    {   // owner-side sub-stage times: partition histogram, tile sort by partition, L2-resident insert sweep
-        float a = 0, b = 0, d = 0;
-        cudaEventElapsedTime(&a, c->ev[10], c->ev[11]);
-        cudaEventElapsedTime(&b, c->ev[11], c->ev[12]);
-        cudaEventElapsedTime(&d, c->ev[12], c->ev[13]);
-        c->ms_sub[0] += a; c->ms_sub[1] += b; c->ms_sub[2] += d;
-    }
-    c->binned_pos += n; c->n_chunks++;
+    return P3_OK;
+}
+// staged transport: what the caller's all-to-all has to move for receive set `set` of a stage (0 = A count records,
+// 1 = B1 positions, 2 = B2 k-mers). out[0..2] = send block, receive block, bytes per rank of the 8-byte records;
+// out[3..5] the same for the auxiliary block (bytes per rank 0 = none); out[6..7] = send / receive counts (n_ranks uint64 each).
+int p3_mg_staged_buffers(p3_ctx *c, int stage, int set, uint64_t out[8]) {
+    MgState *m;
+    int rc = mg_ready(c, &m, "p3_mg_staged_buffers");
+    if (rc) return rc;
+    if (m->transport != 1 || set < 0 || set > 1 || !out) return fail(P3_ERR_ARG, "p3_mg_staged_buffers: staged transport only");
+    const uint64_t auxb = stage == 0 ? 4 : stage == 2 ? 1 : 0;
+    const uint64_t cap = stage == 0 ? m->capA : stage == 1 ? m->capB : m->capK;
+    unsigned char *recv = m->set_ptr(m->my_rank, set);
+    out[0] = (uint64_t)(uintptr_t)m->staging; out[1] = (uint64_t)(uintptr_t)recv; out[2] = cap * 8;
+    out[3] = (uint64_t)(uintptr_t)(m->staging + (uint64_t)m->n_ranks * cap * 8); out[4] = (uint64_t)(uintptr_t)(recv + (uint64_t)m->n_ranks * cap * 8); out[5] = cap * auxb;
+    out[6] = (uint64_t)(uintptr_t)m->d_stage_cnt; out[7] = (uint64_t)(uintptr_t)&m->ctl()->count[set][0];
+    return P3_OK;
+}
+static int mg_publish(p3_ctx *c, MgState &m, int set) {
+    if (m.transport == 0) publish_counts_kernel<<<1, 32, 0, c->stream>>>(m.links, (int)m.my_rank, (int)m.n_ranks, set, m.d_sent);
+    else stage_counts_kernel<<<1, 32, 0, c->stream>>>(m.d_stage_cnt, m.d_sent, (int)m.n_ranks);
+    c->launches++;
+    CU(cudaGetLastError());
     return P3_OK;
 }
 
-int p3_mg_count_end(p3_ctx *c) {
-    if (!c) return fail(P3_ERR_ARG, "null ctx");
-    CU(cudaSetDevice(c->device));
-    int rc = pull_stats(c);
+// ---- A: CountShortKmer, reference src/Load.cpp:105-127 ----------------------------------------------------------
+// table_slots: capacity of this rank's count table. owner_positions: upper estimate of the 21-mer positions this rank
+// will own (all ranks' positions / n_ranks for a hash partition) — sizes the partition bins, which hold every
+// received record until the one insert sweep. n_chunks / chunk_words: the same on every rank (ranks with fewer words
+// send empty chunks).
+int p3_mg_count_begin(p3_ctx *c, uint64_t table_slots, uint64_t owner_positions, uint64_t chunk_words, uint64_t n_chunks) {
+    MgState *mp;
+    int rc = mg_ready(c, &mp, "p3_mg_count_begin");
     if (rc) return rc;
+    MgState &m = *mp;
+    if (!c->have_reads) return fail(P3_ERR_STATE, "p3_mg_count_begin: no reads attached");
+    if (table_slots == 0 || chunk_words == 0) return fail(P3_ERR_ARG, "p3_mg_count_begin: table_slots and chunk_words required");
+    c->binned = true;
+    rc = setup_table(c, table_slots);
+    if (!rc) rc = hist_buffers(c);
+    if (rc) return rc;
+    if (!c->d_binmeta) CU(cudaMalloc(&c->d_binmeta, sizeof(unsigned long long) * (kMaxParts + 2)));
+    m.chunk_words = (chunk_words + kTileWords - 1) / kTileWords * kTileWords; m.n_chunks = n_chunks;
+    m.capA = region_cap(m, 12);
+    const uint64_t per_region = (uint64_t)((double)std::min<uint64_t>(m.chunk_words, c->n_words + kTileWords) * 32 / m.n_ranks * 1.03) + 8192;
+    if (m.capA < per_region) return fail(P3_ERR_ARG, "p3_mg_count_begin: receive set too small for this chunk size (raise set_bytes or lower chunk_words)");
+    const uint32_t P = c->parts;
+    m.part_cap = ((uint64_t)((double)owner_positions / P * 1.03) + 8192 + kSweepChunk - 1) / kSweepChunk * kSweepChunk;
+    CU(ensure(c->d_bkeys, c->cap_bkeys, sizeof(uint64_t) * m.part_cap * P));
+    CU(ensure(c->d_bword, c->cap_bword, sizeof(uint32_t) * m.part_cap * P));
+    CU(ensure(c->d_valid, c->cap_valid, sizeof(uint32_t) * (c->n_words + 1)));
+    init_cursors_kernel<<<1, 256, 0, c->stream>>>(c->d_cursor, P, m.part_cap);   // the bins persist over the chunks
+    c->launches++;
+    CU(cudaEventRecord(c->ev[0], c->stream));
+    c->bins_valid = false; c->have_counts = false; c->pos_on_host = true; c->binned_pos = 0; c->n_chunks = 0;
+    return P3_OK;
+}
+// bin chunk `ch` of this rank's reads by owner, straight into the owners' receive set ch % 2 (peer stores)
+int p3_mg_count_send(p3_ctx *c, uint64_t ch) {
+    MgState *mp;
+    int rc = mg_ready(c, &mp, "p3_mg_count_send");
+    if (rc) return rc;
+    MgState &m = *mp;
+    const int set = (int)(ch & 1);
+    const uint64_t w0 = std::min<uint64_t>(ch * m.chunk_words, c->n_words), w1 = std::min<uint64_t>((ch + 1) * m.chunk_words, c->n_words);
+    CU(cudaMemsetAsync(m.d_sent, 0, sizeof(unsigned long long) * (kMaxParts + 1), c->stream));
+    if (w1 > w0) {
+        PeerOut po;
+        for (uint32_t j = 0; j < (uint32_t)kMaxPeers; j++) {
+            po.keys[j] = nullptr; po.words[j] = nullptr;
+            if (j < m.n_ranks) {
+                unsigned char *blk = dest_block(m, j, set);
+                const uint64_t reg = dest_region(m, j);
+                po.keys[j] = reinterpret_cast<uint64_t *>(blk) + reg * m.capA;
+                po.words[j] = reinterpret_cast<uint32_t *>(blk + (uint64_t)m.n_ranks * m.capA * 8) + reg * m.capA;
+            }
+        }
+        const unsigned sblocks = (unsigned)std::min<uint64_t>((w1 - w0 + kTileWords - 1) / kTileWords, (uint64_t)c->n_sm * 3);
+        const uint64_t tag = (uint64_t)m.my_rank << kRecRankShift;
+        if (c->d_nmask) scatter21_kernel<true, 1, true><<<sblocks, kScatterThreads, kSmem21, c->stream>>>(c->d_packed, c->d_rend, c->d_nmask, w0, w1, m.n_ranks, m.d_sent, nullptr, nullptr, c->d_valid, tag, c->d_stats, po, m.capA);
+        else scatter21_kernel<false, 1, true><<<sblocks, kScatterThreads, kSmem21, c->stream>>>(c->d_packed, c->d_rend, nullptr, w0, w1, m.n_ranks, m.d_sent, nullptr, nullptr, c->d_valid, tag, c->d_stats, po, m.capA);
+        c->launches++;
+        CU(cudaGetLastError());
+    }
+    return mg_publish(c, m, set);
+}
+// owner side: sort what arrived in receive set ch % 2 into the table-partition bins
+int p3_mg_count_recv(p3_ctx *c, uint64_t ch) {
+    MgState *mp;
+    int rc = mg_ready(c, &mp, "p3_mg_count_recv");
+    if (rc) return rc;
+    MgState &m = *mp;
+    const int set = (int)(ch & 1);
+    unsigned char *blk = m.set_ptr(m.my_rank, set);
+    const uint64_t n = (uint64_t)m.n_ranks * m.capA;
+    const unsigned sblocks = (unsigned)std::min<uint64_t>((n + kTilePos - 1) / kTilePos, (uint64_t)c->n_sm * 3);
+    scatter_rec_kernel<0, 4><<<sblocks, kScatterThreads, kSmemPL, c->stream>>>(
+        reinterpret_cast<const uint64_t *>(blk), blk + n * 8, n, c->parts, c->d_cursor, c->d_bkeys, c->d_bword, m.part_cap, nullptr,
+        m.capA, &m.ctl()->count[set][0], c->d_stats);
+    c->launches++;
+    CU(cudaGetLastError());
+    c->n_chunks++;
+    return P3_OK;
+}
+// after the last chunk: one L2-resident insert sweep over everything this rank owns (enqueue only)
+int p3_mg_count_finish(p3_ctx *c) {
+    MgState *mp;
+    int rc = mg_ready(c, &mp, "p3_mg_count_finish");
+    if (rc) return rc;
+    MgState &m = *mp;
+    const uint32_t P = c->parts;
+    check_cursors_kernel<<<1, 256, 0, c->stream>>>(c->d_cursor, P, m.part_cap, c->d_stats);
+    CU(cudaMemcpyAsync(c->d_binmeta, c->d_cursor, sizeof(unsigned long long) * P, cudaMemcpyDeviceToDevice, c->stream));
+    CU(cudaEventRecord(c->ev[10], c->stream));
+    CU(cudaMemsetAsync(&c->d_stats->work, 0, sizeof(unsigned long long), c->stream));
+    c->bin_cap = m.part_cap; c->bin_n = (uint64_t)P * m.part_cap;
+    launch_insert_bins(c, c->d_bkeys, c->d_bword, c->bin_n, c->bin_cap, c->d_binmeta, nullptr);
+    c->launches += 2;
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(c->ev[1], c->stream));
+    return P3_OK;
+}
+// waits for the stage and checks it; the counts of the owned keys are final afterwards
+int p3_mg_count_end(p3_ctx *c) {
+    MgState *mp;
+    int rc = mg_ready(c, &mp, "p3_mg_count_end");
+    if (rc) return rc;
+    std::vector<unsigned long long> ends(c->parts);
+    CU(cudaMemcpyAsync(ends.data(), c->d_binmeta, sizeof(unsigned long long) * c->parts, cudaMemcpyDeviceToHost, c->stream));
+    rc = pull_stats(c);
+    if (rc) return rc;
+    if (c->h_stats.err_peer_timeout) return fail(P3_ERR_CUDA, "multi-GPU barrier timed out waiting for a peer rank");
+    if (c->h_stats.err_bin_overflow) return fail(P3_ERR_TABLE_FULL, "multi-GPU count: a receive region or partition bin overflowed (skewed keys: raise set_bytes / owner_positions)");
     if (c->h_stats.err_table_full) return fail(P3_ERR_TABLE_FULL, "21-mer count table full: raise table_slots");
     if (c->h_stats.err_ovf_full) return fail(P3_ERR_TABLE_FULL, "count overflow side table full");
-    if (c->h_stats.n_cand > c->cand_cap) return fail(P3_ERR_TABLE_FULL, "candidate list overflow");
+    c->binned_pos = 0;
+    for (uint32_t p = 0; p < c->parts; p++) c->binned_pos += ends[p] - (unsigned long long)p * mp->part_cap;
+    c->h_stats.n_pos21 = c->binned_pos;
+    CU(cudaEventElapsedTime(&c->ms[0], c->ev[0], c->ev[1]));
+    CU(cudaEventElapsedTime(&c->ms_sub[2], c->ev[10], c->ev[1]));
+    c->ms_sub[0] = 0; c->ms_sub[1] = c->ms[0] - c->ms_sub[2];
+    c->bins_valid = true;
     c->have_counts = true;
     c->have_bf = c->have_solid = c->have_adj = false;
     return P3_OK;
 }
 
-// positions (with their source rank in the top byte) of every key this rank owns whose final
-// count is below the reference's cov_threshold of 2, grouped by source rank
-int p3_mg_singletons(p3_ctx *c, uint32_t n_ranks, uint64_t *h_counts, const uint64_t **d_pos) {
-    if (!c || !c->have_counts) return fail(P3_ERR_STATE, "p3_mg_singletons: no counts");
-    CU(cudaSetDevice(c->device));
-    MgState &m = g_mg.get(c);
-    uint64_t nc = c->h_stats.n_cand;
-    CU(ensure(m.d_sing, m.cap_sing, sizeof(uint64_t) * std::max<uint64_t>(nc, 1)));
-    CU(ensure(m.d_sing2, m.cap_sing2, sizeof(uint64_t) * std::max<uint64_t>(nc, 1)));
-    CU(cudaMemsetAsync(&c->d_stats->n_export, 0, sizeof(unsigned long long), c->stream));
-    if (nc) {
-        singleton_list_kernel<<<c->grid(), 256, 0, c->stream>>>(c->d_table, c->d_cand_slot, c->d_cand_pos, nc, P3_COV_THRESHOLD, c->ovf(), c->d_stats, m.d_sing);
-        c->launches++;
-    }
-    int rc = pull_stats(c);
-    if (rc) return rc;
-    uint64_t ns = c->h_stats.n_export;
-    CU(cudaMemsetAsync(c->d_ghist, 0, sizeof(unsigned long long) * (kMaxParts + 1), c->stream));
-    if (ns) hist_rec_kernel<2><<<c->grid(), 256, 0, c->stream>>>(m.d_sing, ns, n_ranks, c->d_ghist);
-    rc = mg_scan(c, n_ranks, h_counts);
-    if (rc) return rc;
-    if (ns) {
-        unsigned sblocks = (unsigned)std::min<uint64_t>((ns + kTilePos - 1) / kTilePos, (uint64_t)c->n_sm * 3);
-        scatter_rec_kernel<2, false><<<sblocks, kScatterThreads, sizeof(ScatterSmem), c->stream>>>(m.d_sing, nullptr, ns, n_ranks, c->d_cursor, m.d_sing2, nullptr);
-        c->launches += 2;
-    }
-    CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(c->stream));
-    if (d_pos) *d_pos = m.d_sing2;
-    return P3_OK;
-}
-
+// ---- B1: MakeBF's coverage test, reference src/MakeBloomFilter.cpp:52-58 -----------------------------------------
 static int ensure_planes(p3_ctx *c) {
     uint64_t pw = c->n_words + 1;
     if (!c->d_good21 || !c->d_solid || c->cap_planes < sizeof(uint32_t) * pw) {
@@ -395,182 +400,219 @@ static int ensure_planes(p3_ctx *c) {
     CU(ensure(c->d_seed, c->cap_seed, sizeof(int64_t) * std::max<uint64_t>(c->n_reads, 1)));
     return P3_OK;
 }
-
-// coverage plane := every valid 21-mer position (p3_mg_owner_scatter filled the valid plane)
-int p3_mg_cover_begin(p3_ctx *c) {
-    if (!c || !c->have_reads || !c->d_valid) return fail(P3_ERR_STATE, "p3_mg_cover_begin: run p3_mg_owner_scatter first");
-    CU(cudaSetDevice(c->device));
-    int rc = ensure_planes(c);
+// coverage plane := every valid 21-mer position. The owners send their verdicts in *n_slices rounds so that a round
+// fits the receive regions; owner_distinct = the largest number of distinct owned 21-mers of any rank (so that every
+// rank computes the same number of rounds).
+int p3_mg_cover_begin(p3_ctx *c, uint32_t cov_threshold, uint64_t owner_distinct, uint32_t *n_slices) {
+    MgState *mp;
+    int rc = mg_ready(c, &mp, "p3_mg_cover_begin");
+    if (rc) return rc;
+    MgState &m = *mp;
+    if (!c->have_counts || !c->bins_valid) return fail(P3_ERR_STATE, "p3_mg_cover_begin: run the count stage first");
+    rc = ensure_planes(c);
     if (rc) return rc;
     CU(cudaMemcpyAsync(c->d_good21, c->d_valid, sizeof(uint32_t) * c->n_words, cudaMemcpyDeviceToDevice, c->stream));
     CU(cudaMemsetAsync(c->d_good21 + c->n_words, 0, sizeof(uint32_t), c->stream));
+    m.capB = region_cap(m, 8);
+    // occurrences below the threshold per owner: at most (thr - 1) per distinct key; a source's share of a slice must fit a region
+    const uint64_t worst = std::max<uint64_t>(owner_distinct * std::max<uint32_t>(cov_threshold > 1 ? cov_threshold - 1 : 1, 1), 1);
+    const uint64_t per_slice = std::max<uint64_t>(m.capB * m.n_ranks / 5 * 4, 1);   // 25 % slack for the spread over the sources
+    uint64_t want_slices = std::max<uint64_t>((worst + per_slice - 1) / per_slice, 1);
+    if (const char *e = getenv("P3_MG_COVER_SLICES")) want_slices = std::max<uint64_t>(want_slices, strtoull(e, nullptr, 10));   // test knob
+    m.n_slices = (uint32_t)std::min<uint64_t>(want_slices, c->parts);
+    CU(ensure(m.d_sing, m.cap_sing, sizeof(uint64_t) * std::min<uint64_t>(worst + 1024, m.capB * m.n_ranks)));
+    if (n_slices) *n_slices = m.n_slices;
+    CU(cudaMemsetAsync(&c->d_stats->err_bin_overflow, 0, sizeof(unsigned), c->stream));
+    CU(cudaEventRecord(c->ev[2], c->stream));
     return P3_OK;
 }
-int p3_mg_cover_clear(p3_ctx *c, const uint64_t *d_pos, uint64_t n) {
-    if (!c || !c->d_good21) return fail(P3_ERR_STATE, "p3_mg_cover_clear: run p3_mg_cover_begin first");
-    if (n == 0) return P3_OK;
-    CU(cudaSetDevice(c->device));
-    bool cleared = false;
-    int rcc = binned_plane_clear<1>(c, nullptr, d_pos, n, 0, c->d_good21, c->n_words * 32, &cleared);
-    if (rcc) return rcc;
-    if (cleared) { CU(cudaStreamSynchronize(c->stream)); return P3_OK; }
-    clear_positions_kernel<<<c->grid(), 256, 0, c->stream>>>(d_pos, n, c->d_good21);
-    c->launches++;
-    CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(c->stream));
-    return P3_OK;
-}
-
-int p3_mg_cover_plane(p3_ctx *c, uint32_t **d_plane) {
-    if (!c || !c->d_good21) return fail(P3_ERR_STATE, "p3_mg_cover_plane: run p3_mg_cover_begin first");
-    if (d_plane) *d_plane = c->d_good21;
-    return P3_OK;
-}
-// owner side, fused with the exchange: clear the bits of this rank's count-1 keys directly in the
-// source ranks' planes (planes[j] = rank j's p3_mg_cover_plane, mapped into this process). All ranks
-// must have run p3_mg_cover_begin before any rank calls this, and must synchronise afterwards.
-int p3_mg_cover_peer(p3_ctx *c, uint32_t n_ranks, const uint64_t *planes) {
-    if (!c || !c->have_counts || !planes) return fail(P3_ERR_STATE, "p3_mg_cover_peer: no counts / null planes");
-    if (n_ranks == 0 || n_ranks > kMaxPeers) return fail(P3_ERR_ARG, "p3_mg_cover_peer: at most 16 ranks");
-    CU(cudaSetDevice(c->device));
-    PeerPlanes pp;
-    for (uint32_t j = 0; j < (uint32_t)kMaxPeers; j++) pp.p[j] = (uint32_t *)(uintptr_t)planes[j < n_ranks ? j : 0];
-    uint64_t nc = c->h_stats.n_cand;
-    if (nc) {
-        cand_check_peer_kernel<<<c->grid(), 256, 0, c->stream>>>(c->d_table, c->d_cand_slot, c->d_cand_pos, nc, P3_COV_THRESHOLD, c->ovf(), c->d_stats, pp);
-        c->launches++;
+// owner side, round `slice`: sweep the bins of its share of the table partitions; the positions of keys whose
+// final count < cov_threshold go to the regions of their source ranks (receive set slice % 2)
+int p3_mg_cover_send(p3_ctx *c, uint32_t cov_threshold, uint32_t slice) {
+    MgState *mp;
+    int rc = mg_ready(c, &mp, "p3_mg_cover_send");
+    if (rc) return rc;
+    MgState &m = *mp;
+    if (slice >= m.n_slices) return fail(P3_ERR_ARG, "p3_mg_cover_send: slice out of range");
+    const int set = (int)(slice & 1);
+    const uint32_t P = c->parts;
+    const uint32_t p0 = (uint32_t)((uint64_t)P * slice / m.n_slices), p1 = (uint32_t)((uint64_t)P * (slice + 1) / m.n_slices);
+    CU(cudaMemsetAsync(m.d_sent, 0, sizeof(unsigned long long) * (kMaxParts + 1), c->stream));
+    CU(cudaMemsetAsync(&c->d_stats->n_export, 0, sizeof(unsigned long long), c->stream));
+    if (p1 > p0) {
+        // verdict sweep over partitions [p0, p1): tiles are handed out from st->work, which starts at the slice's first record
+        const unsigned long long first = (unsigned long long)p0 * m.part_cap;
+        CU(cudaMemcpyAsync(&c->d_stats->work, &first, sizeof(first), cudaMemcpyHostToDevice, c->stream));
+        const uint64_t n_end = (uint64_t)p1 * m.part_cap;
+        const size_t smem = (size_t)kBinThreads * kPosKpt * 6 + 20;
+        const uint64_t T = (uint64_t)kBinThreads * kPosKpt;
+        unsigned blocks = (unsigned)std::min<uint64_t>((n_end - first + T - 1) / T, (uint64_t)c->n_sm * 4);
+        pos_bin_kernel<0><<<blocks, kBinThreads, smem, c->stream>>>(c->table(), c->d_bkeys, c->d_bword, n_end, m.part_cap, c->d_binmeta, nullptr,
+                                                                   cov_threshold, c->ovf(), c->d_stats, 27, 1, nullptr, m.cap_sing / sizeof(uint64_t), nullptr, m.d_sing);
+        PeerOut64 po;
+        for (uint32_t j = 0; j < (uint32_t)kMaxPeers; j++)
+            po.p[j] = j < m.n_ranks ? reinterpret_cast<uint64_t *>(dest_block(m, j, set)) + dest_region(m, j) * m.capB : nullptr;
+        const uint64_t nmax = m.cap_sing / sizeof(uint64_t);
+        unsigned sblocks = (unsigned)std::min<uint64_t>((nmax + kTilePos - 1) / kTilePos, (uint64_t)c->n_sm * 3);
+        scatter_pos_peer_kernel<<<sblocks, kScatterThreads, kSmemP, c->stream>>>(m.d_sing, nmax, &c->d_stats->n_export, m.n_ranks, m.d_sent, po, m.capB, c->d_stats);
+        c->launches += 2;
         CU(cudaGetLastError());
     }
-    CU(cudaStreamSynchronize(c->stream));
+    return mg_publish(c, m, set);
+}
+// source side: clear the bits of the positions that arrived in receive set slice % 2
+int p3_mg_cover_recv(p3_ctx *c, uint32_t slice) {
+    MgState *mp;
+    int rc = mg_ready(c, &mp, "p3_mg_cover_recv");
+    if (rc) return rc;
+    MgState &m = *mp;
+    const int set = (int)(slice & 1);
+    ClearInput in;
+    in.rec = reinterpret_cast<const uint64_t *>(m.set_ptr(m.my_rank, set));
+    in.n = (uint64_t)m.n_ranks * m.capB; in.in_cap = m.capB; in.in_end = &m.ctl()->count[set][0];
+    // what a round may deliver: the regions' capacity at most, normally this rank's share of the owners' verdicts
+    const uint64_t n_expect = std::min<uint64_t>(in.n, (c->h_stats.n_cand / std::max<uint32_t>(m.n_slices, 1)) * 3 / 2 + (1u << 20));
+    rc = plane_clear_job<1>(c, in, n_expect, 0, c->d_good21, c->n_words * 32, false, nullptr);
+    if (rc) return rc;
+    CU(cudaEventRecord(c->ev[3], c->stream));
     return P3_OK;
 }
 
-// solid plane (window AND of the coverage plane), seeds, and the locally distinct solid k-mers
-int p3_mg_solid_local(p3_ctx *c, uint32_t k, uint64_t solid_slots, uint64_t *n_adds, uint64_t *n_local) {
-    if (!c || !c->d_good21) return fail(P3_ERR_STATE, "p3_mg_solid_local: run p3_mg_cover_begin first");
-    if (k < P3_MIN_K || k > 32) return fail(P3_ERR_ARG, "multi-GPU path: k outside [21,32] is not supported yet");
-    CU(cudaSetDevice(c->device));
-    c->k = k; c->set_valid = false; c->d_set_b = nullptr; c->nbs_b = 0; c->parts_b = 1;
-    {   // give the local-set buffers of the previous run back to their role so that they are reused
-        MgState &m = g_mg.get(c);
-        if (m.swapped) {
-            std::swap(c->d_set, m.d_set2); std::swap(c->d_list, m.d_list2); std::swap(c->nbs, m.nbs2); std::swap(c->set_parts, m.parts2);
-            c->list_cap = c->nbs * 4;
-            m.swapped = false;
-        }
-    }
+// ---- B2: solid k-mers to their owners, reference src/MakeBloomFilter.cpp:60-83 ------------------------------------
+// solid plane (RMQ test as a window AND of the coverage plane) and seeds are local; sizes the owned set (owned_slots)
+// and turns the count bins into k-mer bins. k <= 32 (multi-word k-mers are single-GPU in this build).
+int p3_mg_solid_begin(p3_ctx *c, uint32_t k, uint64_t owned_slots) {
+    MgState *mp;
+    int rc = mg_ready(c, &mp, "p3_mg_solid_begin");
+    if (rc) return rc;
+    MgState &m = *mp;
+    if (!c->d_good21) return fail(P3_ERR_STATE, "p3_mg_solid_begin: run the coverage stage first");
+    if (k < P3_MIN_K || k > 32) return fail(P3_ERR_ARG, "multi-GPU path: k outside [21,32] is not supported");
+    c->k = k; m.k = k; c->set_valid = false; c->hints_valid = false; c->d_set_b = nullptr; c->nbs_b = 0; c->parts_b = 1;
+    CU(cudaEventRecord(c->ev[4], c->stream));
     CU(cudaMemsetAsync(&c->d_stats->n_adds, 0, sizeof(unsigned long long) * 5, c->stream));
+    CU(cudaMemsetAsync(&c->d_stats->err_table_full, 0, sizeof(unsigned), c->stream));
+    CU(cudaMemsetAsync(c->d_solid + c->n_words, 0, sizeof(uint32_t), c->stream));
     solid_kernel<<<c->grid(), 256, 0, c->stream>>>(c->d_good21, c->n_words, (int)k, c->d_solid, c->d_stats);
-    c->launches++;
-    int rc = pull_stats(c);
-    if (rc) return rc;
-    if (solid_slots == 0) solid_slots = std::max<uint64_t>(2 * std::min<uint64_t>(c->h_stats.n_adds, 1ull << 26), 1024);
-    rc = dedupe_solid_positions(c, k, solid_slots);
-    if (rc) return rc;
     seeds_kernel<<<c->grid(4), 256, 0, c->stream>>>(c->d_off, c->n_reads, c->d_solid, (int)k, c->d_seed);
-    c->launches++;
-    CU(cudaStreamSynchronize(c->stream));
-    g_mg.get(c).n_local = c->h_stats.n_distinct_solid;
-    c->have_solid = true;
-    if (n_adds) *n_adds = c->h_stats.n_adds;
-    if (n_local) *n_local = c->h_stats.n_distinct_solid;
-    return P3_OK;
-}
-
-int p3_mg_kmer_owner_hist(p3_ctx *c, uint32_t n_ranks, uint64_t *h_counts) {
-    if (!c || !c->have_solid) return fail(P3_ERR_STATE, "p3_mg_kmer_owner_hist: run p3_mg_solid_local first");
-    CU(cudaSetDevice(c->device));
-    uint64_t n = g_mg.get(c).n_local;
-    CU(cudaMemsetAsync(c->d_ghist, 0, sizeof(unsigned long long) * (kMaxParts + 1), c->stream));
-    if (n) { hist_rec_kernel<3><<<c->grid(), 256, 0, c->stream>>>(c->d_list, n, n_ranks, c->d_ghist); c->launches++; }
-    CU(cudaGetLastError());
-    return mg_scan(c, n_ranks, h_counts);
-}
-int p3_mg_kmer_owner_scatter(p3_ctx *c, uint32_t n_ranks, uint64_t *d_out) {
-    if (!c || !c->have_solid || !d_out) return fail(P3_ERR_STATE, "p3_mg_kmer_owner_scatter: bad state");
-    CU(cudaSetDevice(c->device));
-    uint64_t n = g_mg.get(c).n_local;
-    if (n) {
-        unsigned sblocks = (unsigned)std::min<uint64_t>((n + kTilePos - 1) / kTilePos, (uint64_t)c->n_sm * 3);
-        scatter_rec_kernel<3, false><<<sblocks, kScatterThreads, sizeof(ScatterSmem), c->stream>>>(c->d_list, nullptr, n, n_ranks, c->d_cursor, d_out, nullptr);
-        c->launches++;
-    }
-    CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(c->stream));
-    return P3_OK;
-}
-
-int p3_mg_owned_begin(p3_ctx *c, uint64_t owned_slots) {
-    if (!c) return fail(P3_ERR_ARG, "null ctx");
-    CU(cudaSetDevice(c->device));
-    MgState &m = g_mg.get(c);
-    if (m.swapped) return fail(P3_ERR_STATE, "p3_mg_owned_begin: run p3_mg_solid_local first");
-    uint64_t nbs = (std::max<uint64_t>(owned_slots, 1024) + 3) / 4;
-    if (!m.d_set2 || m.nbs2 != nbs) {
-        dfree(m.d_set2); dfree(m.d_list2);
-        if (cudaMalloc(&m.d_set2, nbs * 32) != cudaSuccess || cudaMalloc(&m.d_list2, nbs * 32) != cudaSuccess) {
+    c->launches += 2;
+    // the owned set: partitions of ~24 MB (at most 96, see dedupe_solid_positions), list, hints, adjacency
+    uint64_t buckets = (std::max<uint64_t>(owned_slots, 1024) + 3) / 4;
+    uint64_t want = (buckets * 32 + (24ull << 20) - 1) / (24ull << 20);
+    if (const char *e = getenv("P3_SET_PARTS")) want = strtoull(e, nullptr, 10);
+    uint32_t P = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(want, 1), 96);
+    uint64_t nbp = std::max<uint64_t>((buckets + P - 1) / P, 1);
+    uint64_t nbs = nbp * P;
+    if (!c->d_set || c->nbs != nbs) {
+        dfree(c->d_set); dfree(c->d_list);
+        if (cudaMalloc(&c->d_set, nbs * 32) != cudaSuccess || cudaMalloc(&c->d_list, nbs * 32) != cudaSuccess) {
             cudaGetLastError();
             return fail(P3_ERR_NOMEM, "owned k-mer set allocation failed");
         }
-        m.nbs2 = nbs;
+        c->nbs = nbs; c->list_cap = nbs * 4;
     }
-    m.parts2 = 1;
-    CU(cudaMemsetAsync(m.d_set2, 0xFF, nbs * 32, c->stream));
-    CU(cudaMemsetAsync(&c->d_stats->err_table_full, 0, sizeof(unsigned), c->stream));
-    return P3_OK;
-}
-int p3_mg_owned_insert(p3_ctx *c, const uint64_t *d_kmers, uint64_t n) {
-    if (!c) return fail(P3_ERR_ARG, "null ctx");
-    if (n == 0) return P3_OK;
-    CU(cudaSetDevice(c->device));
-    MgState &m = g_mg.get(c);
-    KSet owned; owned.slots = m.d_set2; owned.P = 1; owned.nbp = m.nbs2;
-    set_insert_list_kernel<<<c->grid(), 256, 0, c->stream>>>(d_kmers, n, owned, c->d_stats);
+    c->set_parts = P;
+    CU(ensure(c->d_hint, c->cap_hint, nbs * 4));
+    if (!c->d_adj || c->adj_cap < c->list_cap) { dfree(c->d_adj); c->adj_cap = c->list_cap; CU(cudaMalloc(&c->d_adj, c->adj_cap)); }
+    CU(cudaMemsetAsync(c->d_set, 0xFF, nbs * 32, c->stream));
+    CU(cudaMemsetAsync(c->d_hint, 0, nbs * 4, c->stream));
+    // k-mer bins in the (now idle) count bins: 8-byte k-mers in d_bkeys, one hint byte each in d_bword
+    c->bins_valid = false;
+    const uint64_t room = std::min<uint64_t>(c->cap_bkeys / 8, c->cap_bword);
+    m.kpart_cap = room / P / kSweepChunk * kSweepChunk;
+    if (m.kpart_cap == 0) return fail(P3_ERR_STATE, "p3_mg_solid_begin: no bins (run the count stage first)");
+    m.capK = region_cap(m, 9);
+    init_cursors_kernel<<<1, 256, 0, c->stream>>>(c->d_cursor, P, m.kpart_cap);
     c->launches++;
     CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(c->stream));
     return P3_OK;
 }
-
-// the owned set becomes THE set/list of this context; the filter copy (at least min_words words) is
-// cleared and, with do_adds, receives BF.add of every owned k-mer
-static int owned_finish(p3_ctx *c, uint32_t k, uint64_t filter_size, uint32_t num_hashes, uint64_t min_words,
-                        bool do_adds, uint64_t *n_owned) {
-    if (!c) return fail(P3_ERR_ARG, "null ctx");
-    CU(cudaSetDevice(c->device));
-    MgState &m = g_mg.get(c);
-    if (!m.d_set2) return fail(P3_ERR_STATE, "p3_mg_owned_end: run p3_mg_owned_begin first");
-    int rc = alloc_bloom(c, k, filter_size, num_hashes, min_words);
+// the solid occurrences of chunk `ch` (canonical k-mer + adjacency hint) to the owners' receive set ch % 2
+int p3_mg_solid_send(p3_ctx *c, uint64_t ch) {
+    MgState *mp;
+    int rc = mg_ready(c, &mp, "p3_mg_solid_send");
     if (rc) return rc;
-    std::swap(c->d_set, m.d_set2); std::swap(c->d_list, m.d_list2); std::swap(c->nbs, m.nbs2); std::swap(c->set_parts, m.parts2);
-    c->list_cap = c->nbs * 4;
-    m.swapped = true;
-    CU(cudaMemsetAsync(&c->d_stats->n_distinct_solid, 0, sizeof(unsigned long long), c->stream));
-    compact_set_kernel<<<c->grid(), 256, 0, c->stream>>>(c->d_set, c->nbs * 4, c->d_list, c->list_cap, c->d_stats);
+    MgState &m = *mp;
+    const int set = (int)(ch & 1);
+    const uint64_t w0 = std::min<uint64_t>(ch * m.chunk_words, c->n_words), w1 = std::min<uint64_t>((ch + 1) * m.chunk_words, c->n_words);
+    CU(cudaMemsetAsync(m.d_sent, 0, sizeof(unsigned long long) * (kMaxParts + 1), c->stream));
+    if (w1 > w0) {
+        PeerOutK po;
+        for (uint32_t j = 0; j < (uint32_t)kMaxPeers; j++) {
+            po.keys[j] = nullptr; po.hints[j] = nullptr;
+            if (j < m.n_ranks) {
+                unsigned char *blk = dest_block(m, j, set);
+                const uint64_t reg = dest_region(m, j);
+                po.keys[j] = reinterpret_cast<uint64_t *>(blk) + reg * m.capK;
+                po.hints[j] = blk + (uint64_t)m.n_ranks * m.capK * 8 + reg * m.capK;
+            }
+        }
+        const unsigned sblocks = (unsigned)std::min<uint64_t>((w1 - w0 + kTileWords - 1) / kTileWords, (uint64_t)c->n_sm * 3);
+        if (c->d_nmask) scatter_kmer_kernel<true, true><<<sblocks, kScatterThreads, kSmemPL, c->stream>>>(c->d_packed, c->d_nmask, c->d_solid, w0, w1, (int)m.k, m.n_ranks, m.d_sent, nullptr, nullptr, m.capK, c->d_stats, po);
+        else scatter_kmer_kernel<false, true><<<sblocks, kScatterThreads, kSmemPL, c->stream>>>(c->d_packed, nullptr, c->d_solid, w0, w1, (int)m.k, m.n_ranks, m.d_sent, nullptr, nullptr, m.capK, c->d_stats, po);
+        c->launches++;
+        CU(cudaGetLastError());
+    }
+    return mg_publish(c, m, set);
+}
+// owner side: sort the occurrences that arrived in receive set ch % 2 into the set-partition bins
+int p3_mg_solid_recv(p3_ctx *c, uint64_t ch) {
+    MgState *mp;
+    int rc = mg_ready(c, &mp, "p3_mg_solid_recv");
+    if (rc) return rc;
+    MgState &m = *mp;
+    const int set = (int)(ch & 1);
+    unsigned char *blk = m.set_ptr(m.my_rank, set);
+    const uint64_t n = (uint64_t)m.n_ranks * m.capK;
+    const unsigned sblocks = (unsigned)std::min<uint64_t>((n + kTilePos - 1) / kTilePos, (uint64_t)c->n_sm * 3);
+    scatter_rec_kernel<4, 1><<<sblocks, kScatterThreads, kSmemPL, c->stream>>>(
+        reinterpret_cast<const uint64_t *>(blk), blk + n * 8, n, c->set_parts, c->d_cursor, c->d_bkeys, c->d_bword, m.kpart_cap, nullptr,
+        m.capK, &m.ctl()->count[set][0], c->d_stats);
     c->launches++;
+    CU(cudaGetLastError());
+    return P3_OK;
+}
+// after the last chunk: one L2-resident de-duplication sweep (hints OR-ed per k-mer), then set -> list + hint bytes
+int p3_mg_solid_finish(p3_ctx *c) {
+    MgState *mp;
+    int rc = mg_ready(c, &mp, "p3_mg_solid_finish");
+    if (rc) return rc;
+    MgState &m = *mp;
+    const uint32_t P = c->set_parts;
+    check_cursors_kernel<<<1, 256, 0, c->stream>>>(c->d_cursor, P, m.kpart_cap, c->d_stats);
+    CU(cudaMemsetAsync(&c->d_stats->work, 0, sizeof(unsigned long long), c->stream));
+    set_sweep_kernel<<<c->grid(), 256, 0, c->stream>>>(c->d_bkeys, reinterpret_cast<const uint8_t *>(c->d_bword), (uint64_t)P * m.kpart_cap, m.kpart_cap,
+                                                      c->d_cursor, c->kset(), c->d_hint, c->d_stats);
+    CU(cudaMemsetAsync(&c->d_stats->n_distinct_solid, 0, sizeof(unsigned long long), c->stream));
+    compact_set_kernel<<<c->grid(), 256, 0, c->stream>>>(c->d_set, c->nbs * 4, c->d_list, c->list_cap, c->d_stats,
+                                                         reinterpret_cast<const uint8_t *>(c->d_hint), c->d_adj);
+    c->launches += 3;
+    CU(cudaGetLastError());
+    return P3_OK;
+}
+// waits for the stage; this context then holds its OWNED distinct solid k-mers (list + hints) and an empty filter of at
+// least filter_words_cap words (room for whole shards), ready for p3_mg_bloom_bin / p3_mg_bloom_direct
+int p3_mg_solid_end(p3_ctx *c, uint64_t filter_size, uint32_t num_hashes, uint64_t filter_words_cap, uint64_t *n_adds, uint64_t *n_owned) {
+    MgState *mp;
+    int rc = mg_ready(c, &mp, "p3_mg_solid_end");
+    if (rc) return rc;
     rc = pull_stats(c);
     if (rc) return rc;
+    if (c->h_stats.err_peer_timeout) return fail(P3_ERR_CUDA, "multi-GPU barrier timed out waiting for a peer rank");
+    if (c->h_stats.err_bin_overflow) return fail(P3_ERR_TABLE_FULL, "multi-GPU MakeBF: a receive region or bin overflowed (raise set_bytes)");
     if (c->h_stats.err_table_full) return fail(P3_ERR_TABLE_FULL, "owned k-mer set full: raise owned_slots");
+    rc = alloc_bloom(c, mp->k, filter_size, num_hashes, filter_words_cap);
+    if (rc) return rc;
     CU(cudaMemsetAsync(c->d_bloom, 0, sizeof(uint32_t) * c->bloom_words, c->stream));
-    if (do_adds) {
-        rc = bloom_add_list(c, c->h_stats.n_distinct_solid);
-        if (rc) return rc;
-    }
-    CU(cudaStreamSynchronize(c->stream));
-    c->have_bf = true; c->have_solid = true; c->have_adj = false; c->set_valid = true;
-    c->d_set_b = m.d_set2; c->nbs_b = m.nbs2; c->parts_b = m.parts2;   // after the swap: the locally seen solid k-mers
+    CU(cudaEventRecord(c->ev[5], c->stream));
+    CU(cudaEventRecord(c->ev[14], c->stream));
+    c->have_bf = true; c->have_solid = true; c->have_adj = false; c->set_valid = true; c->hints_valid = true;
+    if (n_adds) *n_adds = c->h_stats.n_adds;
     if (n_owned) *n_owned = c->h_stats.n_distinct_solid;
     return P3_OK;
 }
-// replicated-filter variant: adds into this rank's full copy (the caller then OR-reduces the copies)
-int p3_mg_owned_end(p3_ctx *c, uint32_t k, uint64_t filter_size, uint32_t num_hashes, uint64_t *n_owned) {
-    return owned_finish(c, k, filter_size, num_hashes, 0, true, n_owned);
-}
-// sharded-filter variant: list only; the adds follow as p3_mg_bloom_bin / _apply (or _direct)
-int p3_mg_owned_list(p3_ctx *c, uint32_t k, uint64_t filter_size, uint32_t num_hashes, uint64_t filter_words_cap, uint64_t *n_owned) {
-    return owned_finish(c, k, filter_size, num_hashes, filter_words_cap, false, n_owned);
-}
 
+// ---- B3: sharded BF.add, reference src/bloomfilter.cpp:69-74 ---------------------------------------------------------
 uint64_t p3_bloom_seg_bits(void) { return 1ull << bloom_seg_shift(); }
 
 // buffer that receives the binned bit indices of the segments this rank owns (peers store into it;
@@ -594,7 +636,7 @@ int p3_mg_bloom_buffer(p3_ctx *c, uint64_t n_u32, uint32_t **d_buf) {
 // h_segbase[s] (device addresses, possibly peer memory; cap records each). h_counts[s] = records
 // written (a count above cap means that segment overflowed: use p3_mg_bloom_direct on all ranks).
 int p3_mg_bloom_bin(p3_ctx *c, uint32_t n_seg, const uint64_t *h_segbase, uint64_t cap, uint64_t *h_counts) {
-    if (!c || !c->have_bf || !h_segbase || !h_counts) return fail(P3_ERR_STATE, "p3_mg_bloom_bin: run p3_mg_owned_list first");
+    if (!c || !c->have_bf || !h_segbase || !h_counts) return fail(P3_ERR_STATE, "p3_mg_bloom_bin: run p3_mg_solid_end first");
     if (n_seg == 0 || n_seg > (uint32_t)kMaxParts || c->num_hashes > (uint32_t)kBinMaxHashes)
         return fail(P3_ERR_ARG, "p3_mg_bloom_bin: too many segments / hash functions for the binned path");
     CU(cudaSetDevice(c->device));
@@ -602,7 +644,9 @@ int p3_mg_bloom_bin(p3_ctx *c, uint32_t n_seg, const uint64_t *h_segbase, uint64
     uint64_t *d_hh = nullptr;
     int rc = bloom_hash_list(c, n, &d_hh);
     if (rc) return rc;
-    return bloom_bin_launch(c, d_hh, n, n_seg, bloom_seg_shift(), h_segbase, cap, h_counts);
+    rc = bloom_bin_launch(c, d_hh, n, n_seg, bloom_seg_shift(), h_segbase, cap, h_counts);
+    CU(cudaMemsetAsync(&c->d_stats->err_bin_overflow, 0, sizeof(unsigned), c->stream));   // the caller judges overflow from the counts
+    return rc;
 }
 // owner side: OR the received records of local segments [seg_first, seg_first + n_local) into this
 // context's filter; h_ptr / h_n [n_local][n_src] = where source r's records of the segment are and how many
@@ -618,7 +662,6 @@ int p3_mg_bloom_apply(p3_ctx *c, uint64_t seg_first, uint32_t n_local, uint32_t 
         int rc = bloom_apply_launch(c, seg_first + s, shift, rg);
         if (rc) return rc;
     }
-    CU(cudaStreamSynchronize(c->stream));
     return P3_OK;
 }
 // fallback of the sharded adds: every owned k-mer straight into this rank's full copy (then OR-reduce)
@@ -626,17 +669,28 @@ int p3_mg_bloom_direct(p3_ctx *c) {
     if (!c || !c->have_bf) return fail(P3_ERR_STATE, "p3_mg_bloom_direct: no filter");
     CU(cudaSetDevice(c->device));
     CU(cudaMemsetAsync(c->d_bloom, 0, sizeof(uint32_t) * c->bloom_words, c->stream));
-    int rc = bloom_add_list(c, c->h_stats.n_distinct_solid);
-    if (rc) return rc;
-    CU(cudaStreamSynchronize(c->stream));
-    return P3_OK;
+    return bloom_add_direct(c, c->h_stats.n_distinct_solid);
 }
-
 int p3_mg_filter(p3_ctx *c, uint32_t **d_bits, uint64_t *n_words) {
     if (!c || !c->d_bloom) return fail(P3_ERR_STATE, "p3_mg_filter: no filter");
     if (d_bits) *d_bits = c->d_bloom;
     if (n_words) *n_words = c->bloom_words;
     return P3_OK;
+}
+// marks the end of the MakeBF stage for p3_stage_ms (call once the filter is complete, before p3_dbg_adjacency)
+int p3_mg_makebf_done(p3_ctx *c) {
+    if (!c) return fail(P3_ERR_ARG, "null ctx");
+    CU(cudaSetDevice(c->device));
+    CU(cudaEventRecord(c->ev[15], c->stream));
+    CU(cudaEventRecord(c->ev[6], c->stream));
+    return P3_OK;
+}
+// bytes of device memory in use on this context's GPU (total - free), for the benchmark's hbm_peak_bytes
+uint64_t p3_device_mem_used(p3_ctx *c) {
+    if (!c) return 0;
+    size_t fr = 0, tot = 0;
+    if (cudaSetDevice(c->device) != cudaSuccess || cudaMemGetInfo(&fr, &tot) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return (uint64_t)(tot - fr);
 }
 
 }  // extern "C"

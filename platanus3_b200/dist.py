@@ -1,18 +1,24 @@
-"""Multi-GPU hot path: canonical k-mers hash-partitioned by owner rank, exchanged with all-to-all.
+"""Multi-GPU hot path: canonical k-mers hash-partitioned by owner rank (csrc/p3_multi.inc.cu).
 
-One process per GPU (torch.distributed / NCCL). All heavy work is in the CUDA library
-(csrc/p3_multi.inc.cu); this module only sequences the stages and moves the device buffers:
+One process per GPU (torch.distributed for the plumbing). All heavy work is in the CUDA library; this
+module only sequences the stages. With the default transport the binning kernels store every
+destination rank's records straight into that rank's receive region over NVLink peer memory and the
+ranks meet at device-side barriers (p3_mg_sync), so a step is one long stream of kernel launches with
+three host waits (after the count, after the k-mer de-duplication, after the adjacency):
 
-  A   every rank bins its 21-mers by owner -> all-to-all (12 B records) -> owner counts them
-  B1  owner lists its count-1 keys' (rank, position) -> all-to-all -> ranks clear coverage bits
-  B2  ranks build solid planes/seeds and their locally distinct solid k-mers -> all-to-all by
-      owner -> owner de-duplicates and BF.adds into its filter copy -> OR-reduce of the copies
+  A   every rank bins its 21-mers by owner -> owner sorts them into its partition bins -> one insert sweep
+  B1  owner sweeps its bins again: positions of count-1 keys -> back to their source rank -> bits cleared
+  B2  solid plane and seeds are local; every solid occurrence (k-mer + adjacency hint) -> owner ->
+      sorted by set partition -> one de-duplication sweep; sharded Bloom adds; all-gather of the shards
   C   owner runs CheckDirections for its k-mers against the (now complete, local) filter
 
-The same driver runs over an emulated communicator (several contexts of one process on one GPU),
-which is how the parity tests exercise the distributed algorithm on a single-GPU box.
+P3_MG_EXCHANGE=nccl selects the staged transport: the same regions are filled in a local buffer and moved
+with all_to_all_single (the baseline the fused path is measured against). The same driver runs over an
+emulated communicator (several contexts of one process on one GPU and one stream), which is how the
+parity tests exercise the distributed algorithm on a single-GPU box.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -34,62 +40,40 @@ def dev_tensor(ptr, n, dtype, device):
     return torch.as_tensor(_DevView(ptr, n, typestr), device=device)
 
 
+def _check(rc):
+    _lib.check(rc)
+
+
+def _staged_info(ctx, stage, rset):
+    out = (C.c_uint64 * 8)()
+    _check(_lib.lib().p3_mg_staged_buffers(ctx.h, stage, rset, out))
+    return [int(x) for x in out]
+
+
 # ---------------------------------------------------------------------------- communicators
 class TorchDistComm:
-    """all-to-all with variable splits and bitwise-OR reduction over torch.distributed"""
+    """one rank per process over torch.distributed (NCCL on the box, gloo in the CPU tests)"""
+    same_stream = 0
 
     def __init__(self, group=None):
         import torch.distributed as dist
         self.dist, self.group = dist, group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         self.local_ranks = [self.rank]
-
-    def exchange(self, sends):
-        """sends: [(tensors, counts)] for the one local rank -> [(recv_tensors, recv_counts)]"""
-        (tensors, counts), = sends
-        dev = tensors[0].device
-        sc = torch.tensor(counts, dtype=torch.int64, device=dev)
-        rc = torch.empty_like(sc)
-        self.dist.all_to_all_single(rc, sc, group=self.group)
-        rcounts = [int(x) for x in rc.tolist()]
-        outs = []
-        for t in tensors:
-            out = torch.empty(sum(rcounts), dtype=t.dtype, device=dev)
-            self.dist.all_to_all_single(out, t, output_split_sizes=rcounts, input_split_sizes=[int(c) for c in counts], group=self.group)
-            outs.append(out)
-        return [(outs, rcounts)]
-
-    def or_reduce(self, filters):
-        """bitwise OR of the int32 filter copies of all ranks, in place: all-to-all of shards, local OR,
-        all-gather (NCCL has no bitwise-or reduction op)"""
-        f, = filters
-        n, w = f.numel(), self.world
-        if w == 1:
-            return
-        shard = (n + w - 1) // w
-        buf = torch.zeros(shard * w, dtype=f.dtype, device=f.device)
-        buf[:n] = f
-        recv = torch.empty_like(buf)
-        self.dist.all_to_all_single(recv, buf, group=self.group)
-        acc = recv[:shard].clone()
-        for i in range(1, w):
-            torch.bitwise_or(acc, recv[i * shard:(i + 1) * shard], out=acc)
-        self.dist.all_gather_into_tensor(buf, acc, group=self.group)
-        f.copy_(buf[:n])
+        self._mapped = {}
 
     def _dev(self):
         return "cuda" if torch.cuda.is_available() and self.dist.get_backend(self.group) == "nccl" else "cpu"
 
-    def all_gather_shards(self, filters, shard):
-        """filters: the one local filter tensor of world*shard words whose shard `rank` is final ->
-        every shard final on every rank (in-place all-gather)"""
-        f, = filters
-        if self.world > 1:
-            self.dist.all_gather_into_tensor(f[: self.world * shard], f[self.rank * shard:(self.rank + 1) * shard], group=self.group)
-
     def all_sum(self, values):
         t = torch.tensor(values, dtype=torch.int64, device=self._dev())
         self.dist.all_reduce(t, group=self.group)
+        return [int(x) for x in t.tolist()]
+
+    def all_max(self, values):
+        (row,) = values
+        t = torch.tensor(row, dtype=torch.int64, device=self._dev())
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
         return [int(x) for x in t.tolist()]
 
     def all_gather(self, rows):
@@ -118,8 +102,6 @@ class TorchDistComm:
             handles.append(bytes(h))
         gathered = [None] * self.world
         self.dist.all_gather_object(gathered, handles, group=self.group)
-        if not hasattr(self, "_mapped"):
-            self._mapped = {}
         table = []
         for r in range(self.world):
             if r == self.rank:
@@ -138,30 +120,92 @@ class TorchDistComm:
     def close_shared(self):
         """unmap every peer buffer (call on all ranks BEFORE the owners free their buffers)"""
         L = _lib.lib()
-        for ptr, dev in getattr(self, "_mapped", {}).values():
+        for ptr, dev in self._mapped.values():
             L.p3_ipc_close(dev, C.c_void_p(ptr))
         self._mapped = {}
+        self.__dict__.pop("_p3_setup", None)
+        self.__dict__.pop("_p3_bloom", None)
+
+    def staged_exchange(self, ctxs, stage, rset, device):
+        """staged transport: all-to-all of the fixed-size regions (8-byte records, auxiliary block, counts)"""
+        (c,) = ctxs
+        w = self.world
+        info = _staged_info(c, stage, rset)
+        for s, r, per in ((info[0], info[1], info[2]), (info[3], info[4], info[5])):
+            if per:
+                self.dist.all_to_all_single(dev_tensor(r, w * per, torch.uint8, device), dev_tensor(s, w * per, torch.uint8, device), group=self.group)
+        self.dist.all_to_all_single(dev_tensor(info[7], w, torch.int64, device), dev_tensor(info[6], w, torch.int64, device), group=self.group)
+
+    def or_reduce(self, filters):
+        """bitwise OR of the int32 filter copies of all ranks, in place: all-to-all of shards, local OR,
+        all-gather (NCCL has no bitwise-or reduction op)"""
+        f, = filters
+        n, w = f.numel(), self.world
+        if w == 1:
+            return
+        shard = (n + w - 1) // w
+        buf = torch.zeros(shard * w, dtype=f.dtype, device=f.device)
+        buf[:n] = f
+        recv = torch.empty_like(buf)
+        self.dist.all_to_all_single(recv, buf, group=self.group)
+        acc = recv[:shard].clone()
+        for i in range(1, w):
+            torch.bitwise_or(acc, recv[i * shard:(i + 1) * shard], out=acc)
+        self.dist.all_gather_into_tensor(buf, acc, group=self.group)
+        f.copy_(buf[:n])
+
+    def all_gather_shards(self, filters, shard):
+        """filters: the one local filter tensor of world*shard words whose shard `rank` is final ->
+        every shard final on every rank (in-place all-gather)"""
+        f, = filters
+        if self.world > 1:
+            self.dist.all_gather_into_tensor(f[: self.world * shard], f[self.rank * shard:(self.rank + 1) * shard], group=self.group)
 
 
 class EmulatedComm:
-    """all ranks live in this process (one context each); exchanges are slicing and concatenation"""
+    """all ranks live in this process (one context each, all on ONE stream); exchanges are copies"""
+    same_stream = 1
 
     def __init__(self, world):
         self.world = world
         self.local_ranks = list(range(world))
 
-    def exchange(self, sends):
+    def all_sum(self, values_per_rank):
+        return [int(sum(v)) for v in zip(*values_per_rank)]
+
+    def all_max(self, values_per_rank):
+        return [int(max(v)) for v in zip(*values_per_rank)]
+
+    def all_gather(self, rows):
+        return [list(r) for r in rows]
+
+    def barrier(self):
+        torch.cuda.synchronize()
+
+    def share(self, ptr_rows, device_index):
+        return [list(r) for r in ptr_rows]   # one process: every rank's pointers are valid as they are
+
+    def close_shared(self):
+        self.__dict__.pop("_p3_setup", None)
+        self.__dict__.pop("_p3_bloom", None)
+
+    def staged_exchange(self, ctxs, stage, rset, device):
         w = self.world
-        offs = [np.concatenate([[0], np.cumsum(counts)]).astype(np.int64) for _, counts in sends]
-        out = []
-        for j in range(w):
-            rcounts = [int(sends[i][1][j]) for i in range(w)]
-            outs = []
-            for ti in range(len(sends[0][0])):
-                parts = [sends[i][0][ti][int(offs[i][j]):int(offs[i][j + 1])] for i in range(w)]
-                outs.append(torch.cat(parts) if parts else sends[0][0][ti][:0])
-            out.append((outs, rcounts))
-        return out
+        infos = [_staged_info(c, stage, rset) for c in ctxs]
+        for a, b, p in ((0, 1, 2), (3, 4, 5)):
+            per = infos[0][p]
+            if not per:
+                continue
+            send = [dev_tensor(i[a], w * per, torch.uint8, device) for i in infos]
+            recv = [dev_tensor(i[b], w * per, torch.uint8, device) for i in infos]
+            for i in range(w):
+                for j in range(w):
+                    recv[j][i * per:(i + 1) * per] = send[i][j * per:(j + 1) * per]
+        sc = [dev_tensor(i[6], w, torch.int64, device) for i in infos]
+        rc = [dev_tensor(i[7], w, torch.int64, device) for i in infos]
+        for i in range(w):
+            for j in range(w):
+                rc[j][i] = sc[i][j]
 
     def or_reduce(self, filters):
         acc = filters[0].clone()
@@ -176,227 +220,125 @@ class EmulatedComm:
                 if o != r:
                     g[r * shard:(r + 1) * shard] = f[r * shard:(r + 1) * shard]
 
-    def all_sum(self, values_per_rank):
-        return [int(sum(v)) for v in zip(*values_per_rank)]
-
-    def all_gather(self, rows):
-        return [list(r) for r in rows]
-
-    def barrier(self):
-        torch.cuda.synchronize()
-
-    def share(self, ptr_rows, device_index):
-        return [list(r) for r in ptr_rows]   # one process: every rank's pointers are valid as they are
-
-    def close_shared(self):
-        pass
-
 
 # ---------------------------------------------------------------------------- driver
-def _check(rc):
-    _lib.check(rc)
+def default_set_bytes(chunk_words, world):
+    """receive set for one chunk of 21-mer records (12 B each): expected share + 3 % + slack per region"""
+    per_region = int(chunk_words * 32 / world * 1.03) + 8192 + 4096
+    return per_region * 12 * world
 
 
-def _exchange(comm, sends):
-    """all-to-all, then wait for it: the library launches on its context's stream, which need not be
-    the torch stream NCCL synchronises with (every p3_mg_* call itself returns synchronised)"""
-    out = comm.exchange(sends)
-    torch.cuda.synchronize()
-    return out
+def _setup(ctxs, comm, set_bytes, transport, dev_index):
+    """arena of every local rank; handles exchanged and peers mapped ONCE per (contexts, size, transport)"""
+    L = _lib.lib()
+    key = (tuple(c.h for c in ctxs), set_bytes, transport)
+    if getattr(comm, "_p3_setup", None) == key:
+        return
+    ptr_rows = []
+    for c, r in zip(ctxs, comm.local_ranks):
+        p = C.c_void_p()
+        _check(L.p3_mg_arena(c.h, comm.world, r, set_bytes, transport, C.byref(p)))
+        ptr_rows.append([p.value])
+    table = comm.share(ptr_rows, dev_index)     # [rank][0]
+    arr = (C.c_uint64 * comm.world)(*[table[j][0] for j in range(comm.world)])
+    for c in ctxs:
+        _check(L.p3_mg_connect(c.h, arr, comm.same_stream))
+    comm.barrier()      # every arena is zeroed and mapped before anybody stores into it
+    comm._p3_setup = key
 
 
 def run_hot_path(ctxs, comm, k, filter_size, num_hashes, table_slots, solid_slots=0, owned_slots=0,
-                 chunk_words=None, device=None):
-    """ctxs: the Context of every LOCAL rank (reads already attached/uploaded), in comm.local_ranks
-    order. table_slots: per-rank count-table capacity. Returns one stats dict per local rank; the
-    results stay in the contexts (owned 21-mer counts, owned k-mers + adjacency, local seeds, the
-    complete filter)."""
+                 chunk_words=None, device=None, set_bytes=None, cov_threshold=2):
+    """ctxs: the Context of every LOCAL rank (reads already attached/uploaded, all contexts of one process on
+    the current torch stream), in comm.local_ranks order. table_slots / owned_slots: per-rank capacities of
+    the count table and of the owned solid k-mer set. Returns one stats dict per local rank; the results
+    stay in the contexts (owned 21-mer counts, owned k-mers + adjacency, local seeds, the complete filter).
+    solid_slots is accepted for compatibility and unused (there is no local k-mer set any more)."""
     L = _lib.lib()
     w = comm.world
     device = device or torch.device("cuda", torch.cuda.current_device())
+    dev_index = device.index if device.index is not None else torch.cuda.current_device()
     stats = [dict(rank=r) for r in comm.local_ranks]
     marks = []
+    mem_peak = [0]
 
     def mark(name):
         e = torch.cuda.Event(enable_timing=True)
         e.record()
         marks.append((name, e))
-    mark("start")
-    n_words = [(c.total_bases + 31) // 32 for c in ctxs]
-    cw = chunk_words or max(max(n_words), 1)
-    n_chunks = max((nw + cw - 1) // cw for nw in n_words) if n_words else 0
-    if hasattr(comm, "dist"):   # ranks may hold different amounts of reads: agree on the chunk count
-        t = torch.tensor([n_chunks], dtype=torch.int64, device=device)
-        comm.dist.all_reduce(t, op=comm.dist.ReduceOp.MAX, group=comm.group)
-        n_chunks = int(t.item())
+        mem_peak[0] = max([mem_peak[0]] + [int(L.p3_device_mem_used(c.h)) for c in ctxs])
 
-    import os
-    import time
-    peer = os.environ.get("P3_MG_EXCHANGE", "peer") != "nccl" and w <= 16
-    dev_index = device.index if device.index is not None else torch.cuda.current_device()
-    u64a = C.c_uint64 * w
-    sub = dict(bin=0.0, exchange=0.0, insert=0.0)
+    peer = os.environ.get("P3_MG_EXCHANGE", "peer") != "nccl"
+    transport = 0 if peer else 1
+    n_words = [(c.total_bases + 31) // 32 for c in ctxs]
+    cw = chunk_words or max(max(n_words), 128)
+    cw = (cw + 127) // 128 * 128
+    pos_upper = [max(c.total_bases - 20 * c.n_reads, 0) for c in ctxs]
+    n_chunks, = comm.all_max([[max((nw + cw - 1) // cw, 1)] for nw in n_words])
+    total_pos, = comm.all_sum([[p] for p in pos_upper])
+    owner_positions = int(total_pos / w * 1.02) + 65536
+    set_bytes = set_bytes or default_set_bytes(min(cw, max(comm.all_max([[nw] for nw in n_words])[0], 128)), w)
+    _setup(ctxs, comm, set_bytes, transport, dev_index)
+
+    def sync(stage, rset):
+        if peer:
+            for c in ctxs:
+                _check(L.p3_mg_sync(c.h))
+        else:
+            comm.staged_exchange(ctxs, stage, rset, device)
+
+    def stage_start():
+        for c in ctxs:
+            _check(L.p3_mg_sync(c.h))
+
+    mark("start")
     # ---- A: count ------------------------------------------------------------------------------
     for c in ctxs:
-        _check(L.p3_mg_count_begin(c.h, table_slots, 1))
-
-    def chunk_range(ch, nw):
-        return min(ch * cw, nw), min((ch + 1) * cw, nw)
-
-    if peer:
-        # Fused bin + exchange (csrc: scatter21_kernel<.., PEER>): every rank stores owner j's records
-        # straight into rank j's receive buffer over NVLink, tile by tile, while it bins. Needs the
-        # per-chunk owner histograms of all ranks first (where each source's region starts).
-        t0 = time.perf_counter()
-        rows = []
-        for c, nw in zip(ctxs, n_words):
-            row = []
-            for ch in range(n_chunks):
-                w0, w1 = chunk_range(ch, nw)
-                counts = u64a()
-                _check(L.p3_mg_owner_hist(c.h, w, w0, w1, counts))
-                row += [int(x) for x in counts]
-            rows.append(row)
-        hist = np.array(comm.all_gather(rows), dtype=np.int64).reshape(w, n_chunks, w)   # [source][chunk][owner]
-        cap = hist.sum(axis=0).max(axis=0) if n_chunks else np.zeros(w, np.int64)        # per owner
-        n_buf = 2 if n_chunks > 1 else 1
-        ptr_rows = []
-        for c, r in zip(ctxs, comm.local_ranks):
-            row = []
-            for b in range(n_buf):
-                pk, pw = C.c_void_p(), C.c_void_p()
-                _check(L.p3_mg_recv_buffers(c.h, int(cap[r]), b, C.byref(pk), C.byref(pw)))
-                row += [pk.value, pw.value]
-            ptr_rows.append(row)
-        table = comm.share(ptr_rows, dev_index)     # [rank][2*buffer + (0 = keys, 1 = words)]
-        comm.barrier()
-        sub["bin"] += 1e3 * (time.perf_counter() - t0)
-
-        def scatter(ch, asynchronous):
-            before = np.cumsum(hist[:, ch, :], axis=0) - hist[:, ch, :]   # [source][owner]: records of lower sources
-            b = 2 * (ch % n_buf)
-            for c, r, nw in zip(ctxs, comm.local_ranks, n_words):
-                w0, w1 = chunk_range(ch, nw)
-                kb = u64a(*[table[j][b] + 8 * int(before[r, j]) for j in range(w)])
-                wb = u64a(*[table[j][b + 1] + 4 * int(before[r, j]) for j in range(w)])
-                _check(L.p3_mg_owner_scatter_peer(c.h, w, r, w0, w1, kb, wb, 1 if asynchronous else 0))
-
-        # software pipeline over the chunks: while the owners insert chunk ch (L2-latency bound), the
-        # binning kernel of chunk ch+1 (ALU / NVLink bound) already stores into the other buffer set
-        overlap = os.environ.get("P3_MG_OVERLAP", "0") != "0"
-        t0 = time.perf_counter()
-        if n_chunks:
-            scatter(0, False)
-        comm.barrier()              # every source's stores of chunk 0 have landed
-        sub["bin"] += 1e3 * (time.perf_counter() - t0)
-        for ch in range(n_chunks):
-            t2 = time.perf_counter()
-            if ch + 1 < n_chunks and overlap:
-                scatter(ch + 1, True)
-            b = 2 * (ch % n_buf)
-            for c, r, row in zip(ctxs, comm.local_ranks, ptr_rows):
-                n = int(hist[:, ch, r].sum())
-                if n:
-                    _check(L.p3_mg_count_records(c.h, row[b], row[b + 1], n))
-            if ch + 1 < n_chunks and not overlap:
-                scatter(ch + 1, False)
-            for c in ctxs:
-                _check(L.p3_mg_scatter_wait(c.h))
-            comm.barrier()          # chunk ch+1 has landed everywhere; buffer set ch % 2 is free again
-            sub["insert"] += 1e3 * (time.perf_counter() - t2)
-    for ch in range(n_chunks if not peer else 0):
-        t0 = time.perf_counter()
-        sends = []
-        for c, r, nw in zip(ctxs, comm.local_ranks, n_words):
-            w0, w1 = chunk_range(ch, nw)
-            counts = (C.c_uint64 * w)()
-            _check(L.p3_mg_owner_hist(c.h, w, w0, w1, counts))
-            counts = [int(x) for x in counts]
-            tot = sum(counts)
-            keys = torch.empty(max(tot, 1), dtype=torch.int64, device=device)
-            words = torch.empty(max(tot, 1), dtype=torch.int32, device=device)
-            _check(L.p3_mg_owner_scatter(c.h, w, r, w0, w1, keys.data_ptr(), words.data_ptr()))
-            sends.append(([keys[:tot], words[:tot]], counts))
-        t1 = time.perf_counter()
-        recvs = _exchange(comm, sends)
-        del sends
-        t2 = time.perf_counter()
-        for c, (tensors, rcounts) in zip(ctxs, recvs):
-            n = sum(rcounts)
-            if n:
-                _check(L.p3_mg_count_records(c.h, tensors[0].data_ptr(), tensors[1].data_ptr(), n))
-        del recvs
-        t3 = time.perf_counter()
-        sub["bin"] += 1e3 * (t1 - t0); sub["exchange"] += 1e3 * (t2 - t1); sub["insert"] += 1e3 * (t3 - t2)
+        _check(L.p3_mg_count_begin(c.h, table_slots, owner_positions, cw, n_chunks))
+    stage_start()
+    for ch in range(n_chunks):
+        for c in ctxs:
+            _check(L.p3_mg_count_send(c.h, ch))
+        sync(0, ch & 1)
+        for c in ctxs:
+            _check(L.p3_mg_count_recv(c.h, ch))
+    for c in ctxs:
+        _check(L.p3_mg_count_finish(c.h))
+    mark("count")
     for c, st in zip(ctxs, stats):
         _check(L.p3_mg_count_end(c.h))
         a, b = C.c_uint64(), C.c_uint64()
         _check(L.p3_short_kmer_stats(c.h, C.byref(a), C.byref(b)))
         st.update(owned_positions=a.value, owned_distinct21=b.value, exchange="peer" if peer else "nccl")
-        st["owner_count_ms"] = {kk: v for kk, v in c.count_substage_ms().items() if kk in ("hist", "scatter", "insert")}
-
-    mark("count")
-    laps = {}
-    lap_t = [time.perf_counter()]
-
-    def lap(name):      # wall-clock laps between library calls (each of which returns synchronised)
-        torch.cuda.synchronize()
-        now = time.perf_counter()
-        laps[name] = laps.get(name, 0.0) + 1e3 * (now - lap_t[0])
-        lap_t[0] = now
-    # ---- B1: singleton verdicts back to the reads ----------------------------------------------------
-    if peer and os.environ.get("P3_MG_COVER", "nccl") == "peer":
-        # owners clear the bits of their count-1 keys directly in the source ranks' planes (NVLink RED.AND).
-        # NOT the default: remote atomics are slow — equal to the all-to-all route at 2 GPUs (57 vs 60 ms)
-        # but 2168 ms instead of 74 ms at 8 GPUs (profiles/r01_summary.md)
-        ptr_rows = []
+        st["owner_count_ms"] = {kk: v for kk, v in c.count_substage_ms().items() if kk in ("scatter", "insert")}
+    # ---- B1: verdicts back to the reads ---------------------------------------------------------------
+    owner_distinct, = comm.all_max([[st["owned_distinct21"]] for st in stats])
+    n_slices = 1
+    for c in ctxs:
+        ns = C.c_uint32()
+        _check(L.p3_mg_cover_begin(c.h, cov_threshold, owner_distinct, C.byref(ns)))
+        n_slices = ns.value
+    stage_start()
+    for sl in range(n_slices):
         for c in ctxs:
-            _check(L.p3_mg_cover_begin(c.h))
-            pp = C.c_void_p()
-            _check(L.p3_mg_cover_plane(c.h, C.byref(pp)))
-            ptr_rows.append([pp.value])
-        planes = comm.share(ptr_rows, dev_index)
-        comm.barrier()
-        pl = u64a(*[planes[j][0] for j in range(w)])
+            _check(L.p3_mg_cover_send(c.h, cov_threshold, sl))
+        sync(1, sl & 1)
         for c in ctxs:
-            _check(L.p3_mg_cover_peer(c.h, w, pl))
-        comm.barrier()
-    else:
-        sends = []
-        for c in ctxs:
-            counts = (C.c_uint64 * w)()
-            ptr = C.c_void_p()
-            _check(L.p3_mg_singletons(c.h, w, counts, C.byref(ptr)))
-            counts = [int(x) for x in counts]
-            sends.append(([dev_tensor(ptr.value, sum(counts), torch.int64, device)], counts))
-        recvs = _exchange(comm, sends)
-        for c, (tensors, rcounts) in zip(ctxs, recvs):
-            _check(L.p3_mg_cover_begin(c.h))
-            n = sum(rcounts)
-            if n:
-                t = tensors[0].contiguous()
-                _check(L.p3_mg_cover_clear(c.h, t.data_ptr(), n))
-        del sends, recvs
-
-    lap("coverage")
+            _check(L.p3_mg_cover_recv(c.h, sl))
     mark("coverage")
-    # ---- B2: solid k-mers to their owners ---------------------------------------------------------------
-    sends = []
-    for c, st in zip(ctxs, stats):
-        a, b = C.c_uint64(), C.c_uint64()
-        _check(L.p3_mg_solid_local(c.h, k, solid_slots, C.byref(a), C.byref(b)))
-        st.update(n_adds=a.value, local_distinct_solid=b.value)
-        lap("solid_local")
-        counts = (C.c_uint64 * w)()
-        _check(L.p3_mg_kmer_owner_hist(c.h, w, counts))
-        counts = [int(x) for x in counts]
-        buf = torch.empty(max(sum(counts), 1), dtype=torch.int64, device=device)
-        _check(L.p3_mg_kmer_owner_scatter(c.h, w, buf.data_ptr()))
-        sends.append(([buf[:sum(counts)]], counts))
-        lap("kmer_bin")
-    recvs = _exchange(comm, sends)
-    del sends
-    lap("kmer_exchange")
+    # ---- B2: solid occurrences to their owners ---------------------------------------------------------
+    for c, nw in zip(ctxs, n_words):
+        _check(L.p3_mg_solid_begin(c.h, k, owned_slots or max(2 * nw * 32 // max(w, 1), 1024)))
+    stage_start()
+    for ch in range(n_chunks):
+        for c in ctxs:
+            _check(L.p3_mg_solid_send(c.h, ch))
+        sync(2, ch & 1)
+        for c in ctxs:
+            _check(L.p3_mg_solid_recv(c.h, ch))
+    for c in ctxs:
+        _check(L.p3_mg_solid_finish(c.h))
+    mark("dedupe")
     # the filter: sharded, binned adds (each rank owns a contiguous run of 16 MB segments and receives
     # the bit indices that fall into them) or, as fallback, adds into replicated copies + OR-reduce
     seg_bits = int(L.p3_bloom_seg_bits())
@@ -404,21 +346,11 @@ def run_hot_path(ctxs, comm, k, filter_size, num_hashes, table_slots, solid_slot
     spr = (nseg + w - 1) // w                  # segments per rank
     seg_words = seg_bits // 32
     sharded = peer and nseg <= 1024 and 0 < num_hashes <= 32 and os.environ.get("P3_MG_FILTER", "sharded") != "replicated"
-    for c, st, (tensors, rcounts) in zip(ctxs, stats, recvs):
-        n = sum(rcounts)
-        _check(L.p3_mg_owned_begin(c.h, owned_slots or max(2 * n, 1024)))
-        if n:
-            t = tensors[0].contiguous()
-            _check(L.p3_mg_owned_insert(c.h, t.data_ptr(), n))
-        no = C.c_uint64()
-        if sharded:
-            _check(L.p3_mg_owned_list(c.h, k, filter_size, num_hashes, w * spr * seg_words, C.byref(no)))
-        else:
-            _check(L.p3_mg_owned_end(c.h, k, filter_size, num_hashes, C.byref(no)))
-        st.update(owned_solid=no.value)
+    for c, st in zip(ctxs, stats):
+        na, no = C.c_uint64(), C.c_uint64()
+        _check(L.p3_mg_solid_end(c.h, filter_size, num_hashes, w * spr * seg_words if sharded else 0, C.byref(na), C.byref(no)))
+        st.update(n_adds=na.value, owned_solid=no.value)
         c.k, c.filter_size, c.num_hashes = k, filter_size, num_hashes
-    del recvs
-    lap("owned_dedupe")
 
     def filter_tensors():
         out = []
@@ -439,13 +371,20 @@ def run_hot_path(ctxs, comm, k, filter_size, num_hashes, table_slots, solid_slot
         cap_src = [int(n * num_hashes * share * 1.05) + 65536 for n in n_all]
         prefix = [sum(cap_src[:r]) for r in range(w)]
         tot_cap = sum(cap_src)
-        ptr_rows = []
-        for c in ctxs:
-            pb = C.c_void_p()
-            _check(L.p3_mg_bloom_buffer(c.h, spr * tot_cap, C.byref(pb)))
-            ptr_rows.append([pb.value])
-        table = comm.share(ptr_rows, dev_index)
-        comm.barrier()
+        # the buffers only ever grow, and their size is the same function of the same numbers on every rank:
+        # when it does not exceed what was shared before, every rank still has the same buffer and mapping
+        cached = getattr(comm, "_p3_bloom", None)
+        if cached and cached[0] == tuple(c.h for c in ctxs) and spr * tot_cap <= cached[1]:
+            ptr_rows, table = cached[2], cached[3]
+        else:
+            ptr_rows = []
+            for c in ctxs:
+                pb = C.c_void_p()
+                _check(L.p3_mg_bloom_buffer(c.h, spr * tot_cap, C.byref(pb)))
+                ptr_rows.append([pb.value])
+            table = comm.share(ptr_rows, dev_index)
+            comm.barrier()
+            comm._p3_bloom = (tuple(c.h for c in ctxs), spr * tot_cap, ptr_rows, table)
         count_rows = []
         for c, r in zip(ctxs, comm.local_ranks):
             base = (C.c_uint64 * nseg)(*[table[s // spr][0] + 4 * ((s % spr) * tot_cap + prefix[r]) for s in range(nseg)])
@@ -454,8 +393,7 @@ def run_hot_path(ctxs, comm, k, filter_size, num_hashes, table_slots, solid_slot
             count_rows.append([int(x) for x in counts])
         cnt = np.array(comm.all_gather(count_rows), dtype=np.int64).reshape(w, nseg)
         binned = bool((cnt <= np.array(cap_src)[:, None]).all())     # the same verdict on every rank
-        comm.barrier()
-        lap("bloom_bin")
+        stage_start()       # every source's stores have landed
     if binned:
         for c, r, row in zip(ctxs, comm.local_ranks, ptr_rows):
             first = r * spr
@@ -464,19 +402,17 @@ def run_hot_path(ctxs, comm, k, filter_size, num_hashes, table_slots, solid_slot
                 hp = (C.c_uint64 * (nloc * w))(*[row[0] + 4 * (sl * tot_cap + prefix[src]) for sl in range(nloc) for src in range(w)])
                 hn = (C.c_uint64 * (nloc * w))(*[int(cnt[src, first + sl]) for sl in range(nloc) for src in range(w)])
                 _check(L.p3_mg_bloom_apply(c.h, first, nloc, w, hp, hn))
-        lap("bloom_apply")
         comm.all_gather_shards(filter_tensors(), spr * seg_words)
-        lap("filter_gather")
+        stage_start()       # nobody overwrites a bloom buffer of the next step before it has been applied
     else:
-        if sharded:
-            for c in ctxs:
-                _check(L.p3_mg_bloom_direct(c.h))
+        for c in ctxs:
+            _check(L.p3_mg_bloom_direct(c.h))
         comm.or_reduce([f[: (filter_size + 31) // 32] for f in filter_tensors()])
-    for st in stats:
+    for c, st in zip(ctxs, stats):
         st["filter"] = "sharded" if binned else "replicated"
-    torch.cuda.synchronize()
+        _check(L.p3_mg_makebf_done(c.h))
 
-    mark("makebf")
+    mark("bloom")
     # ---- C: adjacency of the owned k-mers ---------------------------------------------------------------------
     for c, st in zip(ctxs, stats):
         nk, ne = c.dbg_adjacency()
@@ -484,8 +420,10 @@ def run_hot_path(ctxs, comm, k, filter_size, num_hashes, table_slots, solid_slot
     mark("adjacency")
     torch.cuda.synchronize()
     ms = {marks[i][0]: marks[i - 1][1].elapsed_time(marks[i][1]) for i in range(1, len(marks))}
+    ms["makebf"] = ms["dedupe"] + ms["bloom"]
     for st in stats:
         st["stage_ms"] = ms
-        st["count_sub_ms"] = sub
-        st["lap_ms"] = dict(laps, **{"owner_" + kk: v for kk, v in st.get("owner_count_ms", {}).items()})
+        st["lap_ms"] = {"owner_" + kk: v for kk, v in st.get("owner_count_ms", {}).items()}
+        st["hbm_used_peak_bytes"] = mem_peak[0]
+        st["n_chunks"], st["cover_slices"], st["set_bytes"] = n_chunks, n_slices, set_bytes
     return stats

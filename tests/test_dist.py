@@ -1,6 +1,7 @@
 """Multi-GPU path. CPU: the communicator (variable all-to-all, OR-reduce) over gloo with
 world_size 2, and the owner function. GPU: the whole distributed algorithm with R ranks emulated
 as R contexts on one device, bit-exact against the oracle."""
+import ctypes as C
 import os
 import socket
 
@@ -39,14 +40,6 @@ def _gloo_worker(rank, world, port, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         comm = pdist.TorchDistComm()
-        # variable all-to-all: rank r sends (r+1)*(j+2) records to rank j, values encode (src, dst, i)
-        counts = [(rank + 1) * (j + 2) for j in range(world)]
-        a = torch.cat([torch.arange(c, dtype=torch.int64) + 1000 * rank + 100000 * j for j, c in enumerate(counts)])
-        b = (a % 97).to(torch.int32)
-        (outs, rcounts), = comm.exchange([([a, b], counts)])
-        want_counts = [(i + 1) * (rank + 2) for i in range(world)]
-        want = torch.cat([torch.arange(c, dtype=torch.int64) + 1000 * i + 100000 * rank for i, c in enumerate(want_counts)])
-        ok = rcounts == want_counts and torch.equal(outs[0], want) and torch.equal(outs[1], (want % 97).to(torch.int32))
         # OR-reduce of filter copies whose length is not a multiple of the world size
         g = torch.Generator().manual_seed(5)
         full = [torch.randint(-2 ** 31, 2 ** 31 - 1, (1001,), generator=g, dtype=torch.int64).to(torch.int32) for _ in range(world)]
@@ -55,8 +48,16 @@ def _gloo_worker(rank, world, port, q):
         acc = full[0].clone()
         for f in full[1:]:
             acc |= f
-        ok = ok and torch.equal(mine, acc)
+        ok = torch.equal(mine, acc)
+        # in-place all-gather of filter shards: shard r is final on rank r only
+        shard = 37
+        f = torch.zeros(world * shard + 5, dtype=torch.int32)
+        f[rank * shard:(rank + 1) * shard] = torch.arange(shard, dtype=torch.int32) + 1000 * (rank + 1)
+        comm.all_gather_shards([f], shard)
+        want = torch.cat([torch.arange(shard, dtype=torch.int32) + 1000 * (r + 1) for r in range(world)] + [torch.zeros(5, dtype=torch.int32)])
+        ok = ok and torch.equal(f, want)
         ok = ok and comm.all_sum([rank + 1, 10]) == [sum(range(1, world + 1)), 10 * world]
+        ok = ok and comm.all_max([[rank + 1, 10 - rank]]) == [world, 10]
         ok = ok and comm.all_gather([[rank, 7 * rank + 1, 3]]) == [[r, 7 * r + 1, 3] for r in range(world)]
         ok = ok and comm.all_gather([[]]) == [[] for _ in range(world)]
         q.put((rank, bool(ok)))
@@ -80,36 +81,64 @@ def test_comm_over_gloo_world2():
 
 def test_emulated_comm_matches_definition():
     comm = pdist.EmulatedComm(3)
-    sends = []
-    for r in range(3):
-        counts = [r + j + 1 for j in range(3)]
-        t = torch.cat([torch.full((c,), 10 * r + j, dtype=torch.int64) for j, c in enumerate(counts)])
-        sends.append(([t], counts))
-    recvs = comm.exchange(sends)
-    for j, (outs, rcounts) in enumerate(recvs):
-        assert rcounts == [i + j + 1 for i in range(3)]
-        assert outs[0].tolist() == sum(([10 * i + j] * (i + j + 1) for i in range(3)), [])
+    assert comm.all_sum([[1, 2], [10, 20], [100, 200]]) == [111, 222]
+    assert comm.all_max([[1, 9], [5, 2], [3, 3]]) == [5, 9]
+    assert comm.all_gather([[1], [2], [3]]) == [[1], [2], [3]]
     fs = [torch.tensor([1, 0, 4], dtype=torch.int32), torch.tensor([2, 0, 4], dtype=torch.int32)]
     pdist.EmulatedComm(2).or_reduce(fs)
     assert fs[0].tolist() == fs[1].tolist() == [3, 0, 4]
+    sh = [torch.tensor([1, 2, 0, 0, 7], dtype=torch.int32), torch.tensor([0, 0, 3, 4, 7], dtype=torch.int32)]
+    pdist.EmulatedComm(2).all_gather_shards(sh, 2)
+    assert sh[0].tolist() == sh[1].tolist() == [1, 2, 3, 4, 7]
+    assert pdist.default_set_bytes(1 << 20, 4) >= (1 << 20) * 32 * 12
+
+
+def _check_distributed(oracle, ctxs, stats, reads, bounds, world, k, fs, nh, thr=2):
+    """counts, owner placement, filter bits, seeds, solid set and adjacency of R ranks against the oracle"""
+    seq, off = reads_to_arrays(reads)
+    okeys, ocounts = oracle.count_short_kmers(seq, off)
+    obits, oseeds, _, oadds = oracle.make_bf(seq, off, k, okeys, ocounts, fs, nh)
+    osolid = oracle.solid_kmers(seq, off, k, okeys, ocounts)[:, 0]
+    assert sum(s["owned_positions"] for s in stats) == int(ocounts.sum())
+    assert sum(s["owned_distinct21"] for s in stats) == len(okeys)
+    assert sum(s["n_adds"] for s in stats) == oadds
+    exp = [c.short_kmer_export() for c in ctxs]
+    keys = np.concatenate([e[0] for e in exp])
+    counts = np.concatenate([e[1] for e in exp])
+    o = np.argsort(keys)
+    assert np.array_equal(keys[o], okeys) and np.array_equal(counts[o], ocounts)
+    L = _lib.lib()
+    for r, c in enumerate(ctxs):   # every key sits on its owner
+        kk = exp[r][0]
+        assert all(L.p3_owner_of_key(int(x), world) == r for x in kk[:: max(1, len(kk) // 200)])
+        assert np.array_equal(c.bf_export(), obits)
+        assert np.array_equal(c.seed_export(), oseeds[bounds[r]:bounds[r + 1]])
+    dbg = [c.dbg_export(sort=False) for c in ctxs]
+    kmers = np.concatenate([d[0] for d in dbg])
+    adj = np.concatenate([d[1] for d in dbg])
+    for r, d in enumerate(dbg):    # every solid k-mer sits on its owner
+        assert all(L.p3_owner_of_key(int(x), world) == r for x in d[0][:: max(1, len(d[0]) // 200)])
+    o = np.argsort(kmers)
+    kmers, adj = kmers[o], adj[o]
+    assert np.array_equal(kmers, osolid)
+    for i in range(0, len(osolid), max(1, len(osolid) // 1500)):
+        assert adj[i] == oracle.check_directions(obits, fs, nh, osolid[i:i + 1], k)
 
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("exchange", ["peer", "peer-sharded-filter", "nccl"])
-@pytest.mark.parametrize("world,chunk", [(1, None), (2, None), (3, 512), (8, 4096)])
-def test_distributed_hot_path_emulated(oracle, world, chunk, exchange, monkeypatch):
-    """R ranks as R contexts on one GPU: counts, filter, solid k-mers, adjacency and seeds equal the
-    single-node oracle. exchange = "peer": the fused bin + exchange (sources store into the owners'
-    receive buffers / coverage planes directly); "nccl": the all-to-all path"""
+@pytest.mark.parametrize("world,chunk,set_kb", [(1, None, None), (2, None, None), (3, 512, 900), (8, 4096, 3072)])
+def test_distributed_hot_path_emulated(oracle, world, chunk, set_kb, exchange, monkeypatch):
+    """R ranks as R contexts on one GPU and one stream: counts, filter, solid k-mers, adjacency and seeds equal the
+    single-node oracle. exchange = "peer": the fused bin + exchange (sources store into the owners' receive regions
+    directly); "nccl": the staged transport (regions filled locally, moved by the all-to-all). Small receive sets
+    force several chunks and several verdict rounds."""
     want_filter = "replicated"
     if exchange == "peer-sharded-filter":   # small segments so that the sharded, binned adds really run at test size
         exchange, want_filter = "peer", "sharded"
         monkeypatch.setenv("P3_BLOOM_BINNED", "1")
         monkeypatch.setenv("P3_BLOOM_SEG_BITS", "4096")
-        if world == 3:
-            monkeypatch.setenv("P3_MG_COVER", "peer")  # the remote RED.AND coverage route (not the default)
-        else:
-            monkeypatch.setenv("P3_BINNED_CLEARS", "1")  # received singleton positions cleared segment by segment
+        monkeypatch.setenv("P3_BINNED_CLEARS", "1")  # received verdict positions cleared segment by segment
     monkeypatch.setenv("P3_MG_EXCHANGE", exchange)
     k = 32
     g = synth.random_genome(12000, 17)
@@ -117,44 +146,60 @@ def test_distributed_hot_path_emulated(oracle, world, chunk, exchange, monkeypat
     reads[3] = reads[3][:40] + b"N" + reads[3][41:]
     seq, off = reads_to_arrays(reads)
     fs, nh = _lib.estimate_bloomfilter(int(off[-1]), k)
-    okeys, ocounts = oracle.count_short_kmers(seq, off)
-    obits, oseeds, _, oadds = oracle.make_bf(seq, off, k, okeys, ocounts, fs, nh)
-    osolid = oracle.solid_kmers(seq, off, k, okeys, ocounts)[:, 0]
-
+    n_keys = len(oracle.count_short_kmers(seq, off)[0])
     bounds = np.linspace(0, len(reads), world + 1).astype(int)
+    stream = torch.cuda.Stream()
     ctxs = []
-    for r in range(world):
-        s, o = reads_to_arrays(reads[bounds[r]:bounds[r + 1]])
-        c = _lib.Context(0)
-        c.load_ascii(s, o)
-        ctxs.append(c)
-    try:
-        stats = pdist.run_hot_path(ctxs, pdist.EmulatedComm(world), k, fs, nh, table_slots=max(2 * len(okeys) // world, 4096),
-                                   chunk_words=chunk)
-        assert all(s["exchange"] == exchange and s["filter"] == want_filter for s in stats)
-        assert sum(s["owned_positions"] for s in stats) == int(ocounts.sum())
-        assert sum(s["owned_distinct21"] for s in stats) == len(okeys)
-        assert sum(s["n_adds"] for s in stats) == oadds
-        keys = np.concatenate([c.short_kmer_export()[0] for c in ctxs])
-        counts = np.concatenate([c.short_kmer_export()[1] for c in ctxs])
-        o = np.argsort(keys)
-        assert np.array_equal(keys[o], okeys) and np.array_equal(counts[o], ocounts)
-        L = _lib.lib()
-        for r, c in enumerate(ctxs):   # every key sits on its owner
-            kk = c.short_kmer_export()[0]
-            assert all(L.p3_owner_of_key(int(x), world) == r for x in kk[:: max(1, len(kk) // 200)])
-            assert np.array_equal(c.bf_export(), obits)
-            assert np.array_equal(c.seed_export(), oseeds[bounds[r]:bounds[r + 1]])
-        kmers = np.concatenate([c.dbg_export(sort=False)[0] for c in ctxs])
-        adj = np.concatenate([c.dbg_export(sort=False)[1] for c in ctxs])
-        o = np.argsort(kmers)
-        kmers, adj = kmers[o], adj[o]
-        assert np.array_equal(kmers, osolid)
-        for i in range(0, len(osolid), max(1, len(osolid) // 1500)):
-            assert adj[i] == oracle.check_directions(obits, fs, nh, osolid[i:i + 1], k)
-    finally:
-        for c in ctxs:
-            c.close()
+    with torch.cuda.stream(stream):
+        for r in range(world):
+            s, o = reads_to_arrays(reads[bounds[r]:bounds[r + 1]])
+            c = _lib.Context(0, C.c_void_p(stream.cuda_stream))
+            c.load_ascii(s, o)
+            ctxs.append(c)
+        try:
+            comm = pdist.EmulatedComm(world)
+            for _ in range(2):     # twice: arenas, mappings and bins are reused
+                stats = pdist.run_hot_path(ctxs, comm, k, fs, nh, table_slots=max(2 * n_keys // world, 4096), chunk_words=chunk,
+                                           set_bytes=set_kb * 1024 if set_kb else None)
+            assert all(s["exchange"] == exchange and s["filter"] == want_filter for s in stats)
+            if set_kb:
+                assert stats[0]["n_chunks"] > 1
+            _check_distributed(oracle, ctxs, stats, reads, bounds, world, k, fs, nh)
+        finally:
+            for c in ctxs:
+                c.close()
+
+
+@pytest.mark.gpu
+def test_distributed_many_verdict_rounds_and_skew(oracle, monkeypatch):
+    """a receive set so small that the verdicts need several rounds, ragged per-rank read counts (one rank
+    without reads), a homopolymer run (one hot key), another k"""
+    world, k = 4, 27
+    monkeypatch.setenv("P3_PARTS", "7")
+    monkeypatch.setenv("P3_MG_COVER_SLICES", "3")
+    g = synth.random_genome(9000, 31)
+    reads = synth.reads_as_bytes(synth.simulate_reads(g, 25, 100, 0.02, 32))
+    reads += [b"A" * 300, b"ACGT" * 40]
+    seq, off = reads_to_arrays(reads)
+    fs, nh = _lib.estimate_bloomfilter(int(off[-1]), k)
+    n_keys = len(oracle.count_short_kmers(seq, off)[0])
+    bounds = np.array([0, len(reads) // 2, len(reads) // 2, len(reads) - 40, len(reads)])
+    stream = torch.cuda.Stream()
+    ctxs = []
+    with torch.cuda.stream(stream):
+        for r in range(world):
+            s, o = reads_to_arrays(reads[bounds[r]:bounds[r + 1]])
+            c = _lib.Context(0, C.c_void_p(stream.cuda_stream))
+            c.load_ascii(s, o)
+            ctxs.append(c)
+        try:
+            stats = pdist.run_hot_path(ctxs, pdist.EmulatedComm(world), k, fs, nh, table_slots=max(3 * n_keys // world, 4096),
+                                       chunk_words=1024, set_bytes=900 * 1024)
+            assert stats[0]["cover_slices"] > 1 and stats[0]["n_chunks"] > 1
+            _check_distributed(oracle, ctxs, stats, reads, bounds, world, k, fs, nh)
+        finally:
+            for c in ctxs:
+                c.close()
 
 
 def _nccl_worker(rank, world, port, tmp, exchange):
@@ -162,18 +207,19 @@ def _nccl_worker(rank, world, port, tmp, exchange):
     import torch.distributed as dist
     if exchange == "peer-sharded-filter":
         exchange = "peer"
-        os.environ.update(P3_BLOOM_BINNED="1", P3_BLOOM_SEG_BITS="4096", P3_MG_COVER="peer")
+        os.environ.update(P3_BLOOM_BINNED="1", P3_BLOOM_SEG_BITS="4096", P3_BINNED_CLEARS="1")
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), P3_MG_EXCHANGE=exchange)
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
         d = np.load(os.path.join(tmp, "in_%d.npz" % rank))
         comm = pdist.TorchDistComm()
-        with _lib.Context(rank) as c:
+        stream = torch.cuda.Stream()
+        with torch.cuda.stream(stream), _lib.Context(rank, C.c_void_p(stream.cuda_stream)) as c:
             c.load_ascii(d["seq"], d["off"])
-            for _ in range(2):   # twice: buffers and peer mappings are reused
+            for _ in range(2):   # twice: arenas and peer mappings are reused
                 st = pdist.run_hot_path([c], comm, int(d["k"]), int(d["fs"]), int(d["nh"]), table_slots=int(d["slots"]),
-                                        chunk_words=int(d["chunk"]), device=torch.device("cuda", rank))[0]
+                                        chunk_words=int(d["chunk"]), device=torch.device("cuda", rank), set_bytes=2 << 20)[0]
             keys, counts = c.short_kmer_export()
             kmers, adj = c.dbg_export(sort=False)
             np.savez(os.path.join(tmp, "out_%d.npz" % rank), keys=keys, counts=counts, bits=c.bf_export(), seeds=c.seed_export(),
