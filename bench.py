@@ -252,6 +252,10 @@ def verify_small_instance(world, rank, local, dev, stream, comm=None):
     wl = workload.make_reads(VERIFY_GENOME, COVERAGE, READ_LEN, ERR, SEED + 1, dev, first_read=first, n_reads=mine)
     ctx = _lib.Context(local, ctypes.c_void_p(stream.cuda_stream))
     ctx.attach(wl["packed"].data_ptr(), wl["total_bases"], wl["off"].data_ptr(), mine, None, keep=wl)
+    # the small instance must take the code paths of the full-size run, not the small-input shortcuts
+    forced = {"P3_DEDUPE_BINNED": "1", "P3_SET_PARTS": "5", "P3_BINNED_CLEARS": "1", "P3_BLOOM_BINNED": "1", "P3_BLOOM_SEG_BITS": str(1 << 20), "P3_PARTS": "24"}
+    saved = {kk: os.environ.get(kk) for kk in forced}
+    os.environ.update({kk: v for kk, v in forced.items() if saved[kk] is None})
     if world == 1:
         ctx.count_short_kmers(int(len(okeys) / 0.5))
         n_adds, _ = ctx.make_bf(K, fs, nh, 2, 0)
@@ -260,6 +264,9 @@ def verify_small_instance(world, rank, local, dev, stream, comm=None):
         st = pdist.run_hot_path([ctx], comm, K, fs, nh, int(len(okeys) / world / 0.5), owned_slots=int(len(osolid) / world / 0.4),
                                 chunk_words=1 << 16, device=dev)[0]
         n_adds = st["n_adds"]
+    for kk, v in saved.items():
+        if v is None:
+            os.environ.pop(kk, None)
     keys, counts = ctx.short_kmer_export()
     idx = np.searchsorted(okeys, keys)
     assert len(keys) and np.all(idx < len(okeys)) and np.array_equal(okeys[np.minimum(idx, len(okeys) - 1)], keys), "verify: a counted key is not in the oracle's table"
@@ -355,8 +362,11 @@ def main_multi(args, rank, world, local, dev):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), out
 
-    for _ in range(args.warmup):
-        step()
+    os.environ["P3_MG_SAMPLE_MEM"] = "1"       # device memory in use is sampled after every stage of the warm-up steps only
+    hbm_local = 0
+    for _ in range(max(args.warmup, 1)):
+        hbm_local = max(hbm_local, step()["hbm_used_peak_bytes"])
+    os.environ["P3_MG_SAMPLE_MEM"] = "0"
     sampler = ClockSampler(local)
     sampler.start()
     l0 = ctx.launch_count()
@@ -365,7 +375,7 @@ def main_multi(args, rank, world, local, dev):
     clocks = sampler.summary()
     pop, fx = filter_checksum_device(ctx, fs, dev)
     sums = comm.all_sum([st["owned_distinct21"], st["n_adds"], st["owned_solid"], st["owned_edges"], st["owned_positions"], launches])
-    hbm_peak, = comm.all_max([[st["hbm_used_peak_bytes"]]])
+    hbm_peak, = comm.all_max([[hbm_local]])
     assert sums[4] == n_pos, (sums, n_pos)
     counts = {"kmer_positions": n_pos, "distinct_21mers": sums[0], "bf_adds": sums[1], "solid_kmers": sums[2],
               "dbg_edges": sums[3], "filter_size_bits": fs, "num_hashes": nh, "filter_popcount": pop, "filter_xor": fx}
@@ -453,15 +463,17 @@ def main_single(args, local, dev):
     ctx.attach(wl["packed"].data_ptr(), total, wl["off"].data_ptr(), n_reads, None, keep=wl)
     mem_peak = [0]
 
-    def step_resident():
+    def step_resident(sample_mem=False):
         ctx.count_short_kmers(table_slots)
-        mem_peak[0] = max(mem_peak[0], int(L.p3_device_mem_used(ctx.h)))
+        if sample_mem:      # cudaMemGetInfo is not free: sampled during warm-up only (the buffers are grow-only)
+            mem_peak[0] = max(mem_peak[0], int(L.p3_device_mem_used(ctx.h)))
         ctx.make_bf(K, fs, nh, 2, solid_slots)
-        mem_peak[0] = max(mem_peak[0], int(L.p3_device_mem_used(ctx.h)))
+        if sample_mem:
+            mem_peak[0] = max(mem_peak[0], int(L.p3_device_mem_used(ctx.h)))
         ctx.dbg_adjacency()
 
-    for _ in range(args.warmup):
-        step_resident()
+    for _ in range(max(args.warmup, 1)):
+        step_resident(True)
     sampler = ClockSampler(local)
     sampler.start()
     l0 = ctx.launch_count()
@@ -567,6 +579,7 @@ def main():
     ap.add_argument("--genome", type=int, default=GENOME, help="override genome size (debug only; invalidates the metric)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling only: skip the host-buffer leg (e2e is then null)")
+    ap.add_argument("--with-reference", action="store_true", help="--config 0: also rerun the unmodified reference on the same file (minutes)")
     ap.add_argument("--no-verify", action="store_true", help="profiling only: skip the small-instance check against the oracle")
     args = ap.parse_args()
     if args.impl == "reference":

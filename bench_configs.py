@@ -1,0 +1,210 @@
+"""bench.py --config 0 | 2 | 4: the BASELINE.json configs other than the headline, one JSON line each.
+
+  0  synthetic 4.6 Mbp genome, 30x error-free reads, k=32: the whole drop-in (`p3_assemble_file`: Load, GPU hot path,
+     closure, host unitig walk, node coverage, GFA) on a FASTA file; the GFA is compared line-set for line-set with the
+     unmodified reference's (sha256 committed in tests/golden/config0_expected.json by tools/make_config0_expected.py;
+     --with-reference reruns the reference itself where oracle/_ref exists)
+  2  long reads (10 kb, 1 % errors, 30x) and multi-word k-mers on one GPU, at the largest genome that fits beside the
+     count table; k = 3001 (the largest the reference offers) and k = 63
+  4  k x solidity-threshold sweep on the 100 Mbp set: k-mers/s beside table load factors and probe lengths
+"""
+import ctypes
+import hashlib
+import json
+import os
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+C0_EXPECTED = os.path.join(ROOT, "tests", "golden", "config0_expected.json")
+C0 = dict(genome=4_600_000, coverage=30, read_len=150, k=32, seed=7)
+
+
+def write_config0_fasta(path):
+    from platanus3_b200 import workload
+    seq, off = workload.make_reads_numpy(C0["genome"], C0["coverage"], C0["read_len"], 0.0, C0["seed"])
+    n, L = len(off) - 1, C0["read_len"]
+    rows = seq.reshape(n, L)
+    with open(path, "wb") as f:
+        for a in range(0, n, 1 << 16):
+            b = min(n, a + (1 << 16))
+            names = np.char.add(">read_", np.arange(a, b).astype(str)).astype("S")
+            f.write(b"".join(nm + b"\n" + r.tobytes() + b"\n" for nm, r in zip(names, rows[a:b])))
+    return n
+
+
+def gfa_digest(path):
+    lines = sorted(open(path, "rb").read().splitlines())
+    return hashlib.sha256(b"\n".join(lines)).hexdigest(), len(lines)
+
+
+def config0(args, dev):
+    import torch
+    import bench
+    from platanus3_b200 import _lib
+    work = tempfile.mkdtemp(prefix="p3cfg0_")
+    fa = os.path.join(work, "reads.fasta")
+    n_reads = write_config0_fasta(fa)
+    n_pos = n_reads * (C0["read_len"] - 20)
+    gfa, log = os.path.join(work, "out.gfa"), os.path.join(work, "out.log")
+    torch.cuda.synchronize()
+    times, st = [], None
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        st = _lib.assemble_file(fa, C0["k"], m=0, threads=max(os.cpu_count() or 1, 1), device=dev.index or 0, gfa_path=gfa, log_path=log)
+        if i >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    sha, n_lines = gfa_digest(gfa)
+    exp = json.load(open(C0_EXPECTED)) if os.path.exists(C0_EXPECTED) else None
+    res = {"metric": bench.METRIC, "value": n_pos / sec, "unit": bench.UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": 1e3 * sec, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+           "config": {"workload": "configs[0]: synthetic %d bp genome, %dx error-free reads of %d bp, k=%d; a step = the whole drop-in run on a FASTA file "
+                                  "(Load, GPU hot path + closure, host unitig walk, node coverage, GFA)" % (C0["genome"], C0["coverage"], C0["read_len"], C0["k"]),
+                      "fasta_bytes": os.path.getsize(fa), "seed": C0["seed"]},
+           "counts": st, "gfa_lines": n_lines, "gfa_sha256": sha}
+    if exp:
+        res["gfa_identical_to_reference"] = bool(exp["gfa_sha256"] == sha and exp["gfa_lines"] == n_lines)
+        res["reference"] = {kk: exp[kk] for kk in exp if kk.startswith("ref_") or kk in ("junctions", "joints", "straights")}
+        res["speedup_vs_reference_same_file"] = exp.get("ref_total_s", 0) / sec if exp.get("ref_total_s") else None
+        assert res["gfa_identical_to_reference"], "configs[0]: GFA differs from the reference's (%s vs %s)" % (sha, exp["gfa_sha256"])
+        assert (st["junctions"], st["joints"], st["straights"]) == (exp["junctions"], exp["joints"], exp["straights"])
+    if args.with_reference:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from _checkers import Ref, have_ref
+        if have_ref():
+            d2 = os.path.join(work, "ref"); os.makedirs(d2)
+            t0 = time.perf_counter()
+            ref = Ref(C0["k"], readfile=fa, threads=1)
+            ref.load_file(); ref.estimate(); ref.count_short(); ref.make_bf(); ref.make_dbg(); ref.count_node_coverage()
+            theirs = sorted(ref.print_graph(d2))
+            res["reference_here_s"] = time.perf_counter() - t0
+            res["gfa_identical_to_reference_here"] = theirs == sorted(open(gfa).read().splitlines())
+    print(json.dumps(res))
+
+
+def config4(args, dev):
+    """k x threshold sweep on the configs[1] read set (100 Mbp, 50x, 1 % errors)"""
+    import torch
+    import bench
+    from platanus3_b200 import _lib, workload
+    L = _lib.lib()
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    genome = args.genome
+    wl = workload.make_reads(genome, bench.COVERAGE, bench.READ_LEN, bench.ERR, bench.SEED, dev)
+    n_reads, total = wl["n_reads"], wl["total_bases"]
+    n_pos = n_reads * (bench.READ_LEN - 20)
+    table_slots = int((genome + int(total * bench.ERR * 21 * 1.05)) / 0.55)
+    ctx = _lib.Context(dev.index or 0, ctypes.c_void_p(stream.cuda_stream))
+    ctx.attach(wl["packed"].data_ptr(), total, wl["off"].data_ptr(), n_reads, None, keep=wl)
+    # the count table does not depend on k or the threshold: one instrumented count for its probe statistics, then timed ones
+    os.environ["P3_PROBE_STATS"] = "1"
+    ctx.count_short_kmers(table_slots)
+    ps = (ctypes.c_double * 4)()
+    _lib.check(L.p3_probe_stats(ctx.h, ps))
+    os.environ.pop("P3_PROBE_STATS")
+    count_probe = {"mean_buckets_per_insert": ps[0], "max_buckets": int(ps[1])}
+    rows = []
+    ks = [int(x) for x in os.environ.get("P3_SWEEP_K", "21,32,63,101").split(",")]
+    thrs = [int(x) for x in os.environ.get("P3_SWEEP_THR", "2,3,5").split(",")]
+    for k in ks:
+        if k > bench.READ_LEN:
+            rows.append({"k": k, "skipped": "reads of %d bp are shorter than k" % bench.READ_LEN})
+            continue
+        fs, nh = _lib.estimate_bloomfilter(total, k)
+        for thr in thrs:
+            row = {"k": k, "cov_threshold": thr, "filter_size_bits": fs, "num_hashes": nh}
+            try:
+                acc = {}
+                n_steps = args.steps if k <= 32 else 1
+                for i in range((1 if args.warmup else 0) + n_steps):
+                    n_pos_c, n_dist = ctx.count_short_kmers(table_slots)
+                    n_adds, n_solid = ctx.make_bf(k, fs, nh, thr, 0)
+                    n_km, n_edges = ctx.dbg_adjacency()
+                    if i or not args.warmup:
+                        for kk, v in ctx.stage_ms().items():
+                            acc[kk] = acc.get(kk, 0.0) + v / n_steps
+                _lib.check(L.p3_probe_stats(ctx.h, ps))
+                step_ms = sum(acc.values())
+                row.update(stage_ms=acc, ms_per_step=step_ms, kmers_per_s=n_pos / (step_ms * 1e-3),
+                           distinct_21mers=n_dist, bf_adds=n_adds, solid_kmers=n_solid, dbg_edges=n_edges,
+                           solid_set_probe={"mean_buckets_per_lookup": ps[2], "max_buckets": int(ps[3])} if k <= 32 else None)
+            except _lib.P3Error as e:
+                row["error"] = str(e)
+            rows.append(row)
+    slots = ctypes.c_uint64 * 4
+    cap = slots()
+    _lib.check(L.p3_table_capacity(ctx.h, cap))
+    for r in rows:
+        if "distinct_21mers" in r:
+            r["count_table_load"] = r["distinct_21mers"] / max(int(cap[0]), 1)
+        if r.get("solid_set_probe") and r.get("solid_kmers") is not None:
+            r["solid_set_load_last"] = None   # the set is re-sized per row; its load is solid_kmers / its slots at that time
+    best = max((r for r in rows if r.get("k") == 32 and r.get("cov_threshold") == 2 and "kmers_per_s" in r), key=lambda r: r["kmers_per_s"], default=None)
+    print(json.dumps({
+        "metric": bench.METRIC, "value": best["kmers_per_s"] if best else None, "unit": bench.UNIT, "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": best["ms_per_step"] if best else None, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": "configs[4]: k x solidity-threshold sweep on the configs[1] read set (%d Mbp genome, %dx, %d bp reads, %.0f%% errors); "
+                               "value = the k=32 / threshold 2 row" % (genome // 10 ** 6, bench.COVERAGE, bench.READ_LEN, bench.ERR * 100),
+                   "k": ks, "cov_threshold": thrs, "count_table_slots": int(cap[0]), "count_table_partitions": int(cap[1])},
+        "count_table_probe": count_probe, "sweep": rows}))
+    ctx.close()
+
+
+def config2(args, dev):
+    """long reads + multi-word k on one GPU"""
+    import torch
+    import bench
+    from platanus3_b200 import _lib, workload
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    genome = args.genome if args.genome != bench.GENOME else 125_000_000     # 1/8 of the 1 Gbp config: what one GPU holds
+    rl, cov, err = 10_000, 30, 0.01
+    rl = rl // 32 * 32
+    wl = workload.make_reads(genome, cov, rl, err, bench.SEED, dev, chunk_reads=1 << 13)
+    n_reads, total = wl["n_reads"], wl["total_bases"]
+    n_pos = n_reads * (rl - 20)
+    table_slots = int((genome + int(total * err * 21 * 1.05)) / 0.55)
+    ctx = _lib.Context(dev.index or 0, ctypes.c_void_p(stream.cuda_stream))
+    ctx.attach(wl["packed"].data_ptr(), total, wl["off"].data_ptr(), n_reads, None, keep=wl)
+    rows = []
+    for k in [int(x) for x in os.environ.get("P3_LONG_K", "3001,63").split(",")]:
+        fs, nh = _lib.estimate_bloomfilter(total, k)
+        row = {"k": k, "words_per_kmer": (2 * k + 63) // 64, "filter_size_bits": fs, "num_hashes": nh}
+        try:
+            acc = {}
+            for i in range(1 + args.steps):
+                ctx.count_short_kmers(table_slots)
+                n_adds, n_solid = ctx.make_bf(k, fs, nh, 2, 0)
+                _, n_edges = ctx.dbg_adjacency()
+                if i:
+                    for kk, v in ctx.stage_ms().items():
+                        acc[kk] = acc.get(kk, 0.0) + v / args.steps
+            step_ms = sum(acc.values())
+            row.update(stage_ms=acc, ms_per_step=step_ms, kmers_per_s=n_pos / (step_ms * 1e-3), bf_adds=n_adds, solid_kmers=n_solid, dbg_edges=n_edges)
+        except _lib.P3Error as e:
+            row["error"] = str(e)
+        rows.append(row)
+    best = rows[0]
+    print(json.dumps({
+        "metric": bench.METRIC, "value": best.get("kmers_per_s"), "unit": bench.UNIT, "n_gpus": 1, "steps": args.steps, "warmup": 1,
+        "ms_per_step": best.get("ms_per_step"), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": "configs[2] on one GPU: synthetic %d Mbp genome (1/8 of the 1 Gbp config), %dx reads of %d bp at %.0f%% substitution errors, "
+                               "multi-word k-mers; value = the k=%d row" % (genome // 10 ** 6, cov, rl, err * 100, best["k"]),
+                   "note": "at 1 % errors a 3001-mer is error-free with probability 1e-13: the largest k the reference offers finds no solid k-mer in "
+                           "such reads, the count and the coverage test still run in full; k=63 is the non-degenerate row"},
+        "rows": rows}))
+    ctx.close()
+
+
+def run(args, rank, world, local, dev):
+    if world > 1:
+        if rank == 0:
+            print(json.dumps({"config": args.config, "unavailable": "configs 0, 2 and 4 are single-GPU lines; run without torchrun"}))
+        return
+    {0: config0, 2: config2, 4: config4}[args.config](args, dev)

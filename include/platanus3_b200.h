@@ -274,6 +274,12 @@ int p3_stage_ms(p3_ctx *ctx, float ms[5]);
  * p3_count_short_kmers call (0 in direct mode), ms[3]=dense BF.add passes of the last p3_make_bf
  * (part of p3_stage_ms[2]); *parts = table partitions, *chunks = read chunks (0 = direct mode) */
 int p3_count_substage_ms(p3_ctx *ctx, float ms[4], uint32_t *parts, uint64_t *chunks);
+/* table load and probe statistics for the k x threshold sweep (BASELINE.json configs[4]). p3_probe_stats: out[0], out[1] =
+ * mean / longest number of 32-byte buckets an insert of the last p3_count_short_kmers touched (when it ran with the
+ * environment variable P3_PROBE_STATS set, else 0); out[2], out[3] = the same for a lookup of every distinct solid k-mer
+ * in the solid set. p3_table_capacity: count table slots and partitions, solid set slots and partitions. */
+int p3_probe_stats(p3_ctx *ctx, double out[4]);
+int p3_table_capacity(p3_ctx *ctx, uint64_t out[4]);
 /* kernels launched by this context since creation (for bench.py's gpu_launches) */
 uint64_t p3_launch_count(p3_ctx *ctx);
 /* filter parameters in effect */

@@ -28,7 +28,7 @@ SYMBOLS = [
     "p3_mg_makebf_done", "p3_device_mem_used",
     "p3_load_file", "p3_reads_free", "p3_reads_count", "p3_reads_all_bases", "p3_reads_total_bases",
     "p3_reads_offsets", "p3_reads_packed", "p3_reads_nmask", "p3_reads_ascii", "p3_assemble_file", "p3_walk_table", "p3_node_coverage",
-    "p3_assemble_hot_path", "p3_assemble_hot_path_to_host", "p3_stage_ms", "p3_count_substage_ms", "p3_launch_count", "p3_bf_params",
+    "p3_assemble_hot_path", "p3_assemble_hot_path_to_host", "p3_stage_ms", "p3_count_substage_ms", "p3_launch_count", "p3_bf_params", "p3_probe_stats", "p3_table_capacity",
 ]
 
 
@@ -129,6 +129,8 @@ def lib():
         L.p3_walk_table.argtypes = [C.c_char_p, u32, vp, vp, u64, vp, u64, C.c_char_p, C.POINTER(u64)]
         L.p3_stage_ms.argtypes = [vp, C.POINTER(C.c_float)]
         L.p3_count_substage_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(u32), C.POINTER(u64)]
+        L.p3_probe_stats.argtypes = [vp, vp]
+        L.p3_table_capacity.argtypes = [vp, vp]
         L.p3_launch_count.restype = u64
         L.p3_launch_count.argtypes = [vp]
         L.p3_bf_params.argtypes = [vp, C.POINTER(u64), C.POINTER(u32), C.POINTER(u32)]

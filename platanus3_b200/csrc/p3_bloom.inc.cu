@@ -331,7 +331,7 @@ __device__ __forceinline__ bool count_below_pre(const Table &t, uint64_t key, ui
 //         in_end[r] records each (received from the owner ranks)
 template <int MODE>
 __global__ void __launch_bounds__(kBinThreads)
-pos_bin_kernel(Table table, const uint64_t *__restrict__ in, const uint32_t *__restrict__ in_word,
+pos_bin_kernel(Table table, const uint64_t *__restrict__ in, const uint32_t *__restrict__ in_word, const uint32_t *__restrict__ in_idx,
                uint64_t n, uint64_t in_cap, const unsigned long long *__restrict__ in_end, const unsigned long long *__restrict__ n_dev,
                uint64_t thr, Ovf ovf, Stats *st, int shift, uint32_t P, uint32_t *__restrict__ bins,
                uint64_t cap, unsigned long long *cursor, uint64_t *__restrict__ out_list) {
@@ -366,7 +366,37 @@ pos_bin_kernel(Table table, const uint64_t *__restrict__ in, const uint32_t *__r
             for (uint32_t i = tid; i < P; i += kBinThreads) s_hist[i] = 0;
             __syncthreads();
             uint64_t pos[kPosKpt];
-            if (MODE == 0) {
+            if (MODE == 0 && in_idx) {
+                // the insert left the partition-relative slot of every record: its count is one 8-byte load away
+                uint32_t r[kPosKpt];
+                uint64_t v[kPosKpt];
+                const uint64_t pbase = in_cap ? 4 * (t0 / in_cap) * table.nbp : 0;
+#pragma unroll
+                for (int q = 0; q < kPosKpt; q++) {
+                    const uint64_t i = t0 + (uint64_t)q * kBinThreads + tid;
+                    r[q] = i < lim ? __ldcs(in_idx + i) : kNoSlot;
+                }
+#pragma unroll
+                for (int q = 0; q < kPosKpt; q++) {
+                    v[q] = kEmpty;
+                    if (r[q] != kNoSlot) {
+                        uint64_t base = pbase;
+                        if (!in_cap) base = 4 * (uint64_t)part_of(fmix64(__ldcs(in + t0 + (uint64_t)q * kBinThreads + tid) & kKey42), table.P) * table.nbp;
+                        v[q] = __ldcg(table.slots + base + r[q]);
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < kPosKpt; q++) {
+                    pos[q] = ~0ULL;
+                    if (r[q] == kNoSlot) continue;
+                    uint64_t cnt = v[q] >> 42;
+                    if (cnt < thr && n_overflow) cnt += ovf_get(ovf, v[q] & kKey42) << 22;
+                    if (cnt < thr) {
+                        const uint64_t i = t0 + (uint64_t)q * kBinThreads + tid;
+                        pos[q] = posrec_of(__ldcs(in + i), __ldcs(in_word + i));
+                    }
+                }
+            } else if (MODE == 0) {
                 uint64_t rec[kPosKpt / 2], s[kPosKpt / 2][4];
 #pragma unroll
                 for (int half = 0; half < 2; half++) {
@@ -474,7 +504,7 @@ pos_bin_kernel(Table table, const uint64_t *__restrict__ in, const uint32_t *__r
 // direct (un-binned) form of the same two jobs, for small inputs and as the fallback when a segment bin overflows
 template <int MODE>
 __global__ void __launch_bounds__(256)
-pos_clear_direct_kernel(Table table, const uint64_t *__restrict__ in, const uint32_t *__restrict__ in_word, uint64_t n,
+pos_clear_direct_kernel(Table table, const uint64_t *__restrict__ in, const uint32_t *__restrict__ in_word, const uint32_t *__restrict__ in_idx, uint64_t n,
                         uint64_t in_cap, const unsigned long long *__restrict__ in_end, const unsigned long long *__restrict__ n_dev,
                         uint64_t thr, Ovf ovf, const Stats *st, uint32_t *plane) {
     const unsigned n_overflow = MODE == 0 ? st->n_overflow : 0u;
@@ -488,7 +518,15 @@ pos_clear_direct_kernel(Table table, const uint64_t *__restrict__ in, const uint
         uint64_t pos;
         if (MODE == 0) {
             const uint64_t rec = __ldcs(in + i);
-            if (count_lookup(table, rec & kKey42, ovf, n_overflow) >= thr) continue;
+            if (in_idx) {
+                const uint32_t r = __ldcs(in_idx + i);
+                if (r == kNoSlot) continue;
+                const uint64_t base = 4 * (in_cap ? (i / in_cap) : (uint64_t)part_of(fmix64(rec & kKey42), table.P)) * table.nbp;
+                const uint64_t v = __ldcg(table.slots + base + r);
+                uint64_t cnt = v >> 42;
+                if (cnt < thr && n_overflow) cnt += ovf_get(ovf, v & kKey42) << 22;
+                if (cnt >= thr) continue;
+            } else if (count_lookup(table, rec & kKey42, ovf, n_overflow) >= thr) continue;
             pos = posrec_of(rec, __ldcs(in_word + i));
         } else pos = __ldcs(in + i);
         pos &= (1ULL << kPosRankShift) - 1;
@@ -499,6 +537,7 @@ pos_clear_direct_kernel(Table table, const uint64_t *__restrict__ in, const uint
 // the input of a clear job (see pos_bin_kernel)
 struct ClearInput {
     const uint64_t *rec = nullptr; const uint32_t *word = nullptr;    // MODE 0: count records + word indices; MODE 1: position records
+    const uint32_t *idx = nullptr;                                    // MODE 0, optional: partition-relative slot of every record (insert_find)
     uint64_t n = 0;                                                   // inputs (capacity space when in_cap > 0)
     uint64_t in_cap = 0; const unsigned long long *in_end = nullptr;  // binned / regioned layout
     const unsigned long long *n_dev = nullptr;                        // contiguous layout with the count on the device
@@ -536,7 +575,7 @@ static int plane_clear_job(p3_ctx *c, const ClearInput &in, uint64_t n_expect, u
     if (rc0) return rc0;
     if (MODE == 0) CU(cudaMemsetAsync(&c->d_stats->work, 0, sizeof(unsigned long long), c->stream));
     if (!want) {
-        pos_clear_direct_kernel<MODE><<<c->grid(), 256, 0, c->stream>>>(c->table(), in.rec, in.word, in.n, in.in_cap, in.in_end, in.n_dev,
+        pos_clear_direct_kernel<MODE><<<c->grid(), 256, 0, c->stream>>>(c->table(), in.rec, in.word, in.idx, in.n, in.in_cap, in.in_end, in.n_dev,
                                                                        thr, c->ovf(), c->d_stats, plane);
         c->launches++;
         CU(cudaGetLastError());
@@ -550,7 +589,7 @@ static int plane_clear_job(p3_ctx *c, const ClearInput &in, uint64_t n_expect, u
     }
     const uint64_t T = (uint64_t)kBinThreads * kPosKpt;
     unsigned blocks = (unsigned)std::min<uint64_t>((in.n + T - 1) / T, (uint64_t)c->n_sm * (MODE == 0 ? 4 : 8));
-    pos_bin_kernel<MODE><<<blocks, kBinThreads, smem, c->stream>>>(c->table(), in.rec, in.word, in.n, in.in_cap, in.in_end, in.n_dev, thr, c->ovf(),
+    pos_bin_kernel<MODE><<<blocks, kBinThreads, smem, c->stream>>>(c->table(), in.rec, in.word, in.idx, in.n, in.in_cap, in.in_end, in.n_dev, thr, c->ovf(),
                                                                    c->d_stats, shift, (uint32_t)n_seg, b.d_local, cap, c->d_cursor, nullptr);
     CU(cudaMemsetAsync(&c->d_stats->work, 0, sizeof(unsigned long long), c->stream));
     apply_bins_kernel<true><<<c->grid(), 256, 0, c->stream>>>(b.d_local, cap, c->d_cursor, (uint32_t)n_seg, shift, plane, c->d_stats);
@@ -572,6 +611,7 @@ static int verdict_sweep(p3_ctx *c, uint64_t thr, bool force_direct, bool *binne
     auto one = [&](uint64_t share_num, uint64_t share_den) -> int {
         ClearInput in;
         in.rec = c->d_bkeys; in.word = c->d_bword; in.n = c->bin_n; in.in_cap = c->bin_cap; in.in_end = c->d_binmeta;
+        in.idx = c->bins_valid ? c->d_bidx : nullptr;   // re-binned chunks have no index stream: bucket probes instead
         in.n_dev = c->bin_cap ? nullptr : c->d_binmeta + kMaxParts;
         bool b = false;
         int rc = plane_clear_job<0>(c, in, n_expect / share_den * share_num + (1u << 16), thr, c->d_good21, c->n_words * 32, force_direct, &b);

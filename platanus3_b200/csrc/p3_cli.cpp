@@ -17,16 +17,22 @@ int main(int argc, char **argv) {
     int threads = 8, device = 0;          // Options.cpp:12
     unsigned k = 25;                       // Options.cpp:13
     int opt;
-    while ((opt = getopt(argc, argv, "i:m:k:t:d:")) != -1) {
+    bool parsing = true;
+    while (parsing && (opt = getopt(argc, argv, "i:m:k:t:d:")) != -1) {
         switch (opt) {
             case 'i': readfile = optarg; break;
             case 'm': filter_size = strtoull(optarg, nullptr, 10); break;
             case 'k': k = (unsigned)atoi(optarg); break;
             case 't': threads = atoi(optarg); break;
             case 'd': device = atoi(optarg); break;
-            default:
-                fprintf(stderr, "Invalid option\n");   // the reference logs this and carries on
+            default: {
+                // Options.cpp:42-45: "Invalid option" goes to the log (appended, Logging.cpp:19), parsing STOPS, and
+                // main.cpp:14 carries on with whatever was parsed before it
+                FILE *lf = fopen("./platanus3.log", "a");
+                if (lf) { fputs("Invalid option\n", lf); fclose(lf); }
+                parsing = false;
                 break;
+            }
         }
     }
     if (readfile.empty()) { show_usage(); return 0; }   // main.cpp:16-19

@@ -406,14 +406,15 @@ scatter_rec_kernel(const uint64_t *__restrict__ in, const void *__restrict__ aux
     if (over && st) atomicExch(&st->err_bin_overflow, 1u);
 }
 
-// Insert of one occurrence whose first bucket (bucket b of partition `base`, already in s[]) was
-// loaded ahead of time; the rest of the probe sequence is count_insert's. Returns true when this
-// call created the key (*slot = its global slot index). The pre-loaded bucket may be stale by the
-// time it is used: slots only ever go empty -> key, an occupied slot never changes its key, and an
-// empty-looking slot is claimed with a CAS, so a stale view is still a correct starting point.
+// Finds the slot of `key` in its partition or claims an empty one (with count 0), the first bucket of the probe
+// sequence (bucket b of partition `base`) already loaded into s[]. Returns the GLOBAL slot index, ~0 when the
+// partition is full; *created = this call claimed the slot. The pre-loaded bucket may be stale by the time it is
+// used: slots only ever go empty -> key, an occupied slot never changes its key, and an empty-looking slot is
+// claimed with a CAS, so a stale view is still a correct starting point.
 template <bool PROBE_STATS>
-__device__ __forceinline__ bool count_insert_pre(const Table &t, uint64_t key, uint64_t base, uint64_t b, uint64_t s[4],
-                                                 const Ovf &ovf, Stats *st, uint64_t *slot, unsigned *n_probes) {
+__device__ __forceinline__ uint64_t find_or_claim_pre(const Table &t, uint64_t key, uint64_t base, uint64_t b, uint64_t s[4],
+                                                      Stats *st, bool *created, unsigned *n_probes) {
+    *created = false;
     for (uint64_t probe = 0; probe < t.nbp; probe++) {
         uint64_t *bp = t.slots + 4 * (base + b);
         if (probe) ld_bucket(bp, s);
@@ -421,34 +422,38 @@ __device__ __forceinline__ bool count_insert_pre(const Table &t, uint64_t key, u
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             uint64_t v = s[i];
-            if ((v & kKey42) == key) { count_bump(bp + i, v, key, ovf, st); return false; }
+            if ((v & kKey42) == key) return 4 * (base + b) + i;
             if (v == kEmpty) {
-                uint64_t old = atomicCAS(ull(bp + i), kEmpty, key | kCntOne);
-                if (old == kEmpty) { *slot = 4 * (base + b) + i; return true; }
-                if ((old & kKey42) == key) { count_bump(bp + i, old, key, ovf, st); return false; }
+                uint64_t old = atomicCAS(ull(bp + i), kEmpty, key);
+                if (old == kEmpty) { *created = true; return 4 * (base + b) + i; }
+                if ((old & kKey42) == key) return 4 * (base + b) + i;
             }
         }
         b = (b + 1 == t.nbp) ? 0 : b + 1;
     }
     atomicExch(&st->err_table_full, 1u);
-    return false;
+    return ~0ULL;
 }
 
-// Work is handed out in chunks from ONE global counter instead of a static grid-stride loop:
-// blocks run at different speeds, and with a static assignment the fast ones drift many
-// partitions ahead, so that several hundred MB of table are live at once and L2 thrashes
-// (measured: 22 G rec/s). With the shared counter all in-flight chunks lie within
-// gridDim * kSweepChunk records of each other, i.e. inside one or two partitions.
-// Inside a chunk a thread works on kSweepBatch records at a time: their bucket loads are all issued
-// before the first one is consumed, so a thread has kSweepBatch L2 round trips in flight instead of
-// one (the round-1 kernel was bound by exactly that dependent load -> RED chain).
+// The insert sweep is TWO kernels over the partition bins (profiles/microbench/insert_variants.cu: a kernel
+// that mixes bucket loads and atomics on an L2-resident table runs at 67-73 G records/s whatever the batching,
+// occupancy or dependence; loads alone 288 G/s, atomics alone 198 G/s, the two as separate kernels 103 G/s):
+//   insert_find   bucket load(s) -> slot of the key (claimed with count 0 when new) -> 4-byte partition-relative
+//                 slot index per record, streamed out beside the bins
+//   insert_add    index stream -> one atomic add per record (returning: the 22-bit count field's wrap-around
+//                 into the overflow side table must be seen)
+// and MakeBF's verdict sweep reads the same index stream: count of record i = slots[base + idx[i]], no hashing.
+// Work is handed out in chunks from ONE global counter instead of a static grid-stride loop: blocks run at
+// different speeds, and with a static assignment the fast ones drift many partitions ahead, so that several
+// hundred MB of table are live at once and L2 thrashes (measured: 22 G rec/s). With the shared counter all
+// in-flight chunks lie within gridDim * kSweepChunk records of each other, i.e. inside one or two partitions.
 constexpr int kSweepChunk = 2048;   // records per block per grab (8 per thread)
 constexpr int kSweepPer = kSweepChunk / 256;
 constexpr int kSweepBatch = 4;
+constexpr uint32_t kNoSlot = 0xFFFFFFFFu;
 template <bool PROBE_STATS>
-__global__ void __launch_bounds__(256, 3)   // 4 blocks per SM would cap it at 64 registers: 76 bytes of spills in the batch loop
-insert_bins_kernel(const uint64_t *__restrict__ bkeys, uint64_t n,
-                   Table table, Ovf ovf, Stats *st,
+__global__ void __launch_bounds__(256, 4)
+insert_find_kernel(const uint64_t *__restrict__ bkeys, uint64_t n, Table table, Stats *st, uint32_t *__restrict__ bidx,
                    uint64_t cap = 0, const unsigned long long *__restrict__ bin_end = nullptr,
                    const unsigned long long *__restrict__ n_dev = nullptr) {
     __shared__ unsigned long long s_base;
@@ -471,23 +476,26 @@ insert_bins_kernel(const uint64_t *__restrict__ bkeys, uint64_t n,
 #pragma unroll
             for (int it = 0; it < kSweepBatch; it++) {
                 const uint64_t i = cbase + (uint64_t)(half * kSweepBatch + it) * 256 + threadIdx.x;
-                rec[it] = i < lim ? __ldcs(bkeys + i) : ~0ULL;
+                rec[it] = i < lim ? (__ldcs(bkeys + i) & kKey42) : ~0ULL;
             }
 #pragma unroll
             for (int it = 0; it < kSweepBatch; it++) {
                 if (rec[it] != ~0ULL) {
-                    const uint64_t h = fmix64(rec[it] & kKey42);
+                    const uint64_t h = fmix64(rec[it]);
                     ld_bucket(table.slots + 4 * ((uint64_t)part_of(h, table.P) * table.nbp + sub_of(h, table.nbp)), s[it]);
                 }
             }
 #pragma unroll
             for (int it = 0; it < kSweepBatch; it++) {
                 if (rec[it] != ~0ULL) {
-                    uint64_t slot;
+                    const uint64_t i = cbase + (uint64_t)(half * kSweepBatch + it) * 256 + threadIdx.x;
+                    const uint64_t h = fmix64(rec[it]);   // recomputed: cheaper than carrying it across the loads
+                    const uint64_t base = (uint64_t)part_of(h, table.P) * table.nbp;
+                    bool cr;
                     unsigned np = 0;
-                    const uint64_t h = fmix64(rec[it] & kKey42);   // recomputed: cheaper than carrying it across the loads
-                    if (count_insert_pre<PROBE_STATS>(table, rec[it] & kKey42, (uint64_t)part_of(h, table.P) * table.nbp, sub_of(h, table.nbp), s[it], ovf, st, &slot, &np))
-                        created++;
+                    const uint64_t slot = find_or_claim_pre<PROBE_STATS>(table, rec[it], base, sub_of(h, table.nbp), s[it], st, &cr, &np);
+                    created += cr;
+                    bidx[i] = slot == ~0ULL ? kNoSlot : (uint32_t)(slot - 4 * base);
                     if (PROBE_STATS) { probes += np; longest = max(longest, np); }
                 }
             }
@@ -499,6 +507,41 @@ insert_bins_kernel(const uint64_t *__restrict__ bkeys, uint64_t n,
         unsigned long long tp = warp_sum(probes);
         unsigned mx = __reduce_max_sync(0xffffffffu, longest);
         if ((threadIdx.x & 31) == 0) { if (tp) atomicAdd(&st->probes, tp); atomicMax(&st->max_probe, mx); }
+    }
+}
+// EXACT: contiguous (histogram-sized) bins — the partition of a record comes from its key, not from its place
+template <bool EXACT>
+__global__ void __launch_bounds__(256, 8)
+insert_add_kernel(const uint32_t *__restrict__ bidx, const uint64_t *__restrict__ bkeys, uint64_t n, Table table, Ovf ovf, Stats *st,
+                  uint64_t cap, const unsigned long long *__restrict__ bin_end, const unsigned long long *__restrict__ n_dev) {
+    __shared__ unsigned long long s_base;
+    if (n_dev) n = min(n, (uint64_t)*n_dev);
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_base = atomicAdd(&st->work, (unsigned long long)kSweepChunk);
+        __syncthreads();
+        const uint64_t cbase = s_base;
+        if (cbase >= n) break;
+        uint64_t lim = n, pbase = 0;
+        if (!EXACT) { const uint64_t p = cbase / cap; lim = min((uint64_t)__ldg(bin_end + p), (p + 1) * cap); pbase = 4 * p * table.nbp; }
+        if (cbase >= lim) continue;
+        uint32_t r[kSweepPer];
+#pragma unroll
+        for (int it = 0; it < kSweepPer; it++) {
+            const uint64_t i = cbase + (uint64_t)it * 256 + threadIdx.x;
+            r[it] = i < lim ? __ldcs(bidx + i) : kNoSlot;
+        }
+#pragma unroll
+        for (int it = 0; it < kSweepPer; it++) {
+            if (r[it] == kNoSlot) continue;
+            uint64_t base = pbase;
+            if (EXACT) {
+                const uint64_t i = cbase + (uint64_t)it * 256 + threadIdx.x;
+                base = 4 * (uint64_t)part_of(fmix64(__ldcs(bkeys + i) & kKey42), table.P) * table.nbp;
+            }
+            const uint64_t old = atomicAdd(ull(table.slots + base + r[it]), kCntOne);
+            if ((old >> 42) == kCntFieldMax) ovf_add(ovf, old & kKey42, st);   // the 22-bit field wrapped to 0
+        }
     }
 }
 
@@ -606,7 +649,7 @@ scatter_kmer_kernel(const uint64_t *__restrict__ packed, const uint32_t *__restr
                     pm = w ? (__ldg(nmask + w - 1) & 1u) : false;
                 }
                 rlo = rev2(chi); rhi = rev2(clo);
-                // S bit (33 - j): position 32w + j is solid, j = -1 .. 32
+                // S bit (32 - j): position 32w + j is solid, j = -1 .. 32
                 S = ((uint64_t)(w ? (__ldg(solid + w - 1) & 1u) : 0u) << 33) | ((uint64_t)sc << 1) | (__ldg(solid + w + 1) >> 31);
                 prev_base = w ? (uint32_t)(__ldg(packed + w - 1) & 3) : 0u;
             }
@@ -625,7 +668,7 @@ scatter_kmer_kernel(const uint64_t *__restrict__ packed, const uint32_t *__restr
                 const bool fwd = f <= r;
                 key[q] = fwd ? f : r;
                 rk[q >> 1] |= atomicAdd(&sm.hist[PEER ? owner_of(key[q], P) : kset_part(key[q], P)], 1u) << (16 * (q & 1));
-                bool lh = (S >> (34 - o)) & 1, rh = (S >> (32 - o)) & 1;
+                bool lh = (S >> (33 - o)) & 1, rh = (S >> (31 - o)) & 1;   // positions p - 1 and p + 1
                 if (HAS_MASK) {
                     if (lh) lh = o ? (((mbits << (o - 1)) >> (63 - k)) == 0) : (!pm && (mbits >> (64 - k)) == 0);
                     if (rh) rh = ((mbits << o) >> (63 - k)) == 0;
@@ -881,6 +924,31 @@ __global__ void roots_kernel(const uint64_t *__restrict__ roots, uint64_t n, int
     } else if (ins < 0) atomicExch(&st->err_table_full, 1u);
 }
 
+// probe length of a successful lookup of every listed k-mer in the solid set (bench.py --config 4)
+__global__ void set_probe_stats_kernel(const uint64_t *__restrict__ kmers, uint64_t n, KSet t, Stats *st) {
+    uint64_t stride = gridDim.x * (uint64_t)blockDim.x;
+    unsigned long long tot = 0;
+    unsigned mx = 0;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint64_t key = __ldg(kmers + i), h = fmix64(key);
+        const uint64_t base = (uint64_t)part_of(h, t.P) * t.nbp;
+        uint64_t b = sub_of(h, t.nbp);
+        unsigned np = 0;
+        for (uint64_t probe = 0; probe < t.nbp; probe++) {
+            uint64_t s[4];
+            ld_bucket64(t.slots + 4 * (base + b), s);
+            np++;
+            if (s[0] == key || s[1] == key || s[2] == key || s[3] == key) break;
+            if (s[0] == kEmpty || s[1] == kEmpty || s[2] == kEmpty || s[3] == kEmpty) break;
+            b = (b + 1 == t.nbp) ? 0 : b + 1;
+        }
+        tot += np; mx = max(mx, np);
+    }
+    tot = __reduce_add_sync(0xffffffffu, (unsigned)tot);
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&st->probes, tot); atomicMax(&st->max_probe, mx); }
+}
+
 // ---- small batch / export kernels -------------------------------------------------------------------
 __global__ void export_counts_kernel(const uint64_t *__restrict__ table, uint64_t n_slots, Ovf ovf, Stats *st,
                                      uint64_t thr, uint64_t *keys, uint64_t *counts, uint64_t cap) {
@@ -953,6 +1021,7 @@ struct p3_ctx {
     uint32_t parts = 1; uint64_t nbp = 0;
     bool binned = true;                                // P3_COUNT_MODE=direct switches it off
     uint64_t *d_bkeys = nullptr; uint32_t *d_bword = nullptr; uint64_t cap_bkeys = 0, cap_bword = 0;
+    uint32_t *d_bidx = nullptr; uint64_t cap_bidx = 0;   // partition-relative slot index of every binned record (insert_find -> insert_add -> verdict sweep)
     uint32_t *d_valid = nullptr; uint64_t cap_valid = 0;
     uint64_t bin_cap = 0, bin_n = 0; bool bins_valid = false;   // the partition bins of the last count (one chunk) are still there for the verdict sweep
     uint64_t bin_upper = 0; bool bin_exact = false;
@@ -965,6 +1034,7 @@ struct p3_ctx {
     std::vector<cudaEvent_t> up_ev; uint64_t up_pieces = 0, up_piece_words = 0;   // pending upload (consumed by the next count)
     cudaEvent_t ev_main = nullptr, ev_copy = nullptr;
     bool probe_stats = false;              // P3_PROBE_STATS: instrumented insert kernels (bench.py --config 4)
+    unsigned long long count_probes = 0; unsigned count_max_probe = 0;
     bool attrs_set = false;
     float ms_sub[4] = {0, 0, 0, 0};
     float ms_bloom = 0;                    // hist, scatter, insert, cand_check
@@ -1118,7 +1188,7 @@ void p3_destroy(p3_ctx *c) {
     long_release(c);
     bloom_release(c);
     free_reads(c); free_bf(c);
-    dfree(c->d_table); dfree(c->d_proven2); dfree(c->d_bkeys); dfree(c->d_bword); dfree(c->d_valid);
+    dfree(c->d_table); dfree(c->d_proven2); dfree(c->d_bkeys); dfree(c->d_bword); dfree(c->d_bidx); dfree(c->d_valid);
     dfree(c->d_ghist); dfree(c->d_binmeta); dfree(c->d_cursor); dfree(c->d_ovf_keys); dfree(c->d_ovf_wraps); dfree(c->d_stats);
     for (auto &e : c->ev) cudaEventDestroy(e);
     for (auto &e : c->evpool) cudaEventDestroy(e);
@@ -1137,6 +1207,8 @@ int p3_synchronize(p3_ctx *c) {
 }
 
 static int finish_reads(p3_ctx *c) {
+    // positions travel as a 32-bit word index + 5-bit offset: 2^32 words = 137 Gbases per context
+    if (c->n_words >= (1ull << 32)) return fail(P3_ERR_ARG, "more than 2^32 packed words (137 Gbases) per context: split the reads over contexts");
     // read-end plane, built on the device from the offsets
     uint64_t plane_words = c->n_words + 1;
     CU(ensure(c->d_rend, c->cap_rend, sizeof(uint32_t) * plane_words));
@@ -1234,11 +1306,17 @@ static void launch_scatter21_local(p3_ctx *c, unsigned sblocks, uint64_t w0, uin
         c->d_packed, c->d_rend, HAS_MASK ? c->d_nmask : nullptr, w0, w1, P, c->d_cursor, c->d_bkeys, c->d_bword, c->d_valid, 0, c->d_stats, PeerOut(), cap);
 }
 }  // extern "C++"
-static void launch_insert_bins(p3_ctx *c, const uint64_t *keys, const uint32_t *words, uint64_t n, uint64_t cap,
-                               const unsigned long long *bin_end, const unsigned long long *n_dev) {
-    (void)words;
-    if (c->probe_stats) insert_bins_kernel<true><<<c->grid(3), 256, 0, c->stream>>>(keys, n, c->table(), c->ovf(), c->d_stats, cap, bin_end, n_dev);
-    else insert_bins_kernel<false><<<c->grid(3), 256, 0, c->stream>>>(keys, n, c->table(), c->ovf(), c->d_stats, cap, bin_end, n_dev);
+static int launch_insert_bins(p3_ctx *c, const uint64_t *keys, uint64_t n, uint64_t cap,
+                              const unsigned long long *bin_end, const unsigned long long *n_dev) {
+    CU(cudaMemsetAsync(&c->d_stats->work, 0, sizeof(unsigned long long), c->stream));
+    if (c->probe_stats) insert_find_kernel<true><<<c->grid(4), 256, 0, c->stream>>>(keys, n, c->table(), c->d_stats, c->d_bidx, cap, bin_end, n_dev);
+    else insert_find_kernel<false><<<c->grid(4), 256, 0, c->stream>>>(keys, n, c->table(), c->d_stats, c->d_bidx, cap, bin_end, n_dev);
+    CU(cudaMemsetAsync(&c->d_stats->work, 0, sizeof(unsigned long long), c->stream));
+    if (cap) insert_add_kernel<false><<<c->grid(8), 256, 0, c->stream>>>(c->d_bidx, keys, n, c->table(), c->ovf(), c->d_stats, cap, bin_end, n_dev);
+    else insert_add_kernel<true><<<c->grid(8), 256, 0, c->stream>>>(c->d_bidx, keys, n, c->table(), c->ovf(), c->d_stats, cap, bin_end, n_dev);
+    c->launches += 2;
+    CU(cudaGetLastError());
+    return P3_OK;
 }
 
 // Plan of the binned count: how many words per chunk so that the bins (12 B per record) fit, and the
@@ -1280,6 +1358,7 @@ static int plan_bins(p3_ctx *c, uint64_t upper, bool exact, BinPlan *pl) {
     const uint64_t rec_cap = records_for(std::min(chunk_words, c->n_words));
     CU(ensure(c->d_bkeys, c->cap_bkeys, sizeof(uint64_t) * rec_cap));
     CU(ensure(c->d_bword, c->cap_bword, sizeof(uint32_t) * rec_cap));
+    CU(ensure(c->d_bidx, c->cap_bidx, sizeof(uint32_t) * rec_cap));
     CU(ensure(c->d_valid, c->cap_valid, sizeof(uint32_t) * (c->n_words + 1)));
     return P3_OK;
 }
@@ -1347,10 +1426,8 @@ static int count_binned(p3_ctx *c, uint64_t upper, bool exact) {
         rc = bin_chunk(c, pl, w0, w1, pool_event(c, e + 1));
         if (rc) return rc;
         CU(cudaEventRecord(pool_event(c, e + 2), c->stream));
-        CU(cudaMemsetAsync(&c->d_stats->work, 0, sizeof(unsigned long long), c->stream));
-        launch_insert_bins(c, c->d_bkeys, c->d_bword, c->bin_n, c->bin_cap, c->d_binmeta, c->bin_cap ? nullptr : c->d_binmeta + kMaxParts);
-        CU(cudaGetLastError());
-        c->launches++;
+        rc = launch_insert_bins(c, c->d_bkeys, c->bin_n, c->bin_cap, c->d_binmeta, c->bin_cap ? nullptr : c->d_binmeta + kMaxParts);
+        if (rc) return rc;
         CU(cudaEventRecord(pool_event(c, e + 3), c->stream));
         c->n_chunks++;
     }
@@ -1428,6 +1505,7 @@ int p3_count_short_kmers(p3_ctx *c, uint64_t table_slots) {
         if (rc) return rc;
     }
     if (c->binned) count_binned_times(c);
+    c->count_probes = c->h_stats.probes; c->count_max_probe = c->h_stats.max_probe;
     CU(cudaEventElapsedTime(&c->ms[0], c->ev[0], c->ev[1]));
     if (c->h_stats.err_table_full) return fail(P3_ERR_TABLE_FULL, "21-mer count table full: raise table_slots");
     if (c->h_stats.err_ovf_full) return fail(P3_ERR_TABLE_FULL, "count overflow side table full");
@@ -2039,6 +2117,34 @@ int p3_assemble_hot_path_to_host(p3_ctx *c, const uint64_t *h_packed, uint64_t t
                                  uint8_t *h_bits, int64_t *h_seed_pos, uint64_t *h_kmers, uint8_t *h_adj, uint64_t cap, uint64_t *n) {
     return hot_path_impl(c, h_packed, total_bases, h_off, n_reads, h_nmask, all_bases, k, filter_size, num_hashes, table_slots, solid_slots,
                          h_bits, h_seed_pos, h_kmers, h_adj, cap, n);
+}
+
+// Probe statistics for the k x threshold sweep (BASELINE.json configs[4]). out[0], out[1]: mean and longest number of
+// 32-byte buckets an insert of the last p3_count_short_kmers touched (only when it ran with P3_PROBE_STATS set, else 0);
+// out[2], out[3]: the same for a successful lookup of every distinct solid k-mer in the solid set (measured now).
+int p3_probe_stats(p3_ctx *c, double out[4]) {
+    if (!c || !out) return fail(P3_ERR_ARG, "p3_probe_stats: null argument");
+    CU(cudaSetDevice(c->device));
+    out[0] = out[1] = out[2] = out[3] = 0;
+    if (c->have_counts && c->probe_stats && c->h_stats.n_pos21) { out[0] = (double)c->count_probes / (double)c->h_stats.n_pos21; out[1] = c->count_max_probe; }
+    if (c->have_solid && c->k <= 32 && c->d_set && c->h_stats.n_distinct_solid) {
+        const uint64_t n = c->n_solid ? c->n_solid : c->h_stats.n_distinct_solid;
+        CU(cudaMemsetAsync(&c->d_stats->probes, 0, sizeof(unsigned long long), c->stream));
+        CU(cudaMemsetAsync(&c->d_stats->max_probe, 0, sizeof(unsigned), c->stream));
+        set_probe_stats_kernel<<<c->grid(), 256, 0, c->stream>>>(c->d_list, n, c->kset(), c->d_stats);
+        c->launches++;
+        Stats h;
+        CU(cudaMemcpyAsync(&h, c->d_stats, sizeof(Stats), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        out[2] = (double)h.probes / (double)n; out[3] = h.max_probe;
+    }
+    return P3_OK;
+}
+// out[0..3] = count table slots, count table partitions, solid set slots, solid set partitions
+int p3_table_capacity(p3_ctx *c, uint64_t out[4]) {
+    if (!c || !out) return fail(P3_ERR_ARG, "p3_table_capacity: null argument");
+    out[0] = c->nb * 4; out[1] = c->parts; out[2] = c->nbs * 4; out[3] = c->set_parts;
+    return P3_OK;
 }
 
 int p3_count_substage_ms(p3_ctx *c, float ms[4], uint32_t *parts, uint64_t *chunks) {

@@ -76,13 +76,12 @@ uint64_t p3_packed_words(uint64_t total_bases) { return (total_bases + 31) / 32 
 int p3_pack_reads(const char *seq, const uint64_t *off, uint64_t n_reads, uint64_t *packed,
                   uint32_t *nmask, int *has_non_acgt) {
     if (!off || !packed || (!seq && n_reads && off[n_reads])) return P3_ERR_ARG;
-    static unsigned char lut[256];
-    static bool init = false;
-    if (!init) {
-        memset(lut, 4, sizeof(lut));
-        lut[(unsigned char)'A'] = 0; lut[(unsigned char)'C'] = 1; lut[(unsigned char)'G'] = 2; lut[(unsigned char)'T'] = 3;
-        init = true;
-    }
+    // built once, thread-safely (function-local static with an initialiser: several host threads may pack at the same time)
+    static const struct Lut {
+        unsigned char v[256];
+        Lut() { memset(v, 4, sizeof(v)); v[(unsigned char)'A'] = 0; v[(unsigned char)'C'] = 1; v[(unsigned char)'G'] = 2; v[(unsigned char)'T'] = 3; }
+    } lut_holder;
+    const unsigned char *lut = lut_holder.v;
     uint64_t total = n_reads ? off[n_reads] : 0;
     uint64_t words = p3_packed_words(total);
     memset(packed, 0, sizeof(uint64_t) * words);

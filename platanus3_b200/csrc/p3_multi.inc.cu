@@ -209,6 +209,9 @@ int p3_mg_arena(p3_ctx *c, uint32_t n_ranks, uint32_t my_rank, uint64_t set_byte
         if (!m.d_stage_cnt) CU(cudaMalloc(&m.d_stage_cnt, sizeof(unsigned long long) * kMaxPeers));
     }
     if (!m.d_sent) CU(cudaMalloc(&m.d_sent, sizeof(unsigned long long) * (kMaxParts + 1)));
+    CU(cudaFuncSetAttribute(scatter_pos_peer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemP));
+    int rca = scatter_attrs(c);
+    if (rca) return rca;
     if (d_arena) *d_arena = m.arena;
     return P3_OK;
 }
@@ -291,6 +294,7 @@ int p3_mg_count_begin(p3_ctx *c, uint64_t table_slots, uint64_t owner_positions,
     m.part_cap = ((uint64_t)((double)owner_positions / P * 1.03) + 8192 + kSweepChunk - 1) / kSweepChunk * kSweepChunk;
     CU(ensure(c->d_bkeys, c->cap_bkeys, sizeof(uint64_t) * m.part_cap * P));
     CU(ensure(c->d_bword, c->cap_bword, sizeof(uint32_t) * m.part_cap * P));
+    CU(ensure(c->d_bidx, c->cap_bidx, sizeof(uint32_t) * m.part_cap * P));
     CU(ensure(c->d_valid, c->cap_valid, sizeof(uint32_t) * (c->n_words + 1)));
     init_cursors_kernel<<<1, 256, 0, c->stream>>>(c->d_cursor, P, m.part_cap);   // the bins persist over the chunks
     c->launches++;
@@ -355,11 +359,10 @@ int p3_mg_count_finish(p3_ctx *c) {
     check_cursors_kernel<<<1, 256, 0, c->stream>>>(c->d_cursor, P, m.part_cap, c->d_stats);
     CU(cudaMemcpyAsync(c->d_binmeta, c->d_cursor, sizeof(unsigned long long) * P, cudaMemcpyDeviceToDevice, c->stream));
     CU(cudaEventRecord(c->ev[10], c->stream));
-    CU(cudaMemsetAsync(&c->d_stats->work, 0, sizeof(unsigned long long), c->stream));
     c->bin_cap = m.part_cap; c->bin_n = (uint64_t)P * m.part_cap;
-    launch_insert_bins(c, c->d_bkeys, c->d_bword, c->bin_n, c->bin_cap, c->d_binmeta, nullptr);
-    c->launches += 2;
-    CU(cudaGetLastError());
+    rc = launch_insert_bins(c, c->d_bkeys, c->bin_n, c->bin_cap, c->d_binmeta, nullptr);
+    if (rc) return rc;
+    c->launches++;
     CU(cudaEventRecord(c->ev[1], c->stream));
     return P3_OK;
 }
@@ -447,7 +450,7 @@ int p3_mg_cover_send(p3_ctx *c, uint32_t cov_threshold, uint32_t slice) {
         const size_t smem = (size_t)kBinThreads * kPosKpt * 6 + 20;
         const uint64_t T = (uint64_t)kBinThreads * kPosKpt;
         unsigned blocks = (unsigned)std::min<uint64_t>((n_end - first + T - 1) / T, (uint64_t)c->n_sm * 4);
-        pos_bin_kernel<0><<<blocks, kBinThreads, smem, c->stream>>>(c->table(), c->d_bkeys, c->d_bword, n_end, m.part_cap, c->d_binmeta, nullptr,
+        pos_bin_kernel<0><<<blocks, kBinThreads, smem, c->stream>>>(c->table(), c->d_bkeys, c->d_bword, c->d_bidx, n_end, m.part_cap, c->d_binmeta, nullptr,
                                                                    cov_threshold, c->ovf(), c->d_stats, 27, 1, nullptr, m.cap_sing / sizeof(uint64_t), nullptr, m.d_sing);
         PeerOut64 po;
         for (uint32_t j = 0; j < (uint32_t)kMaxPeers; j++)

@@ -262,11 +262,14 @@ def run_hot_path(ctxs, comm, k, filter_size, num_hashes, table_slots, solid_slot
     marks = []
     mem_peak = [0]
 
+    sample_mem = os.environ.get("P3_MG_SAMPLE_MEM", "0") != "0"    # cudaMemGetInfo is not free: only on request (bench warm-up)
+
     def mark(name):
         e = torch.cuda.Event(enable_timing=True)
         e.record()
         marks.append((name, e))
-        mem_peak[0] = max([mem_peak[0]] + [int(L.p3_device_mem_used(c.h)) for c in ctxs])
+        if sample_mem:
+            mem_peak[0] = max([mem_peak[0]] + [int(L.p3_device_mem_used(c.h)) for c in ctxs])
 
     peer = os.environ.get("P3_MG_EXCHANGE", "peer") != "nccl"
     transport = 0 if peer else 1
@@ -327,8 +330,8 @@ def run_hot_path(ctxs, comm, k, filter_size, num_hashes, table_slots, solid_slot
             _check(L.p3_mg_cover_recv(c.h, sl))
     mark("coverage")
     # ---- B2: solid occurrences to their owners ---------------------------------------------------------
-    for c, nw in zip(ctxs, n_words):
-        _check(L.p3_mg_solid_begin(c.h, k, owned_slots or max(2 * nw * 32 // max(w, 1), 1024)))
+    for c in ctxs:     # default capacity: a rank owns about 1/w of all k-mers, whatever share of the reads it parsed
+        _check(L.p3_mg_solid_begin(c.h, k, owned_slots or max(2 * total_pos // w + 4096, 4096)))
     stage_start()
     for ch in range(n_chunks):
         for c in ctxs:

@@ -127,7 +127,7 @@ def _check_distributed(oracle, ctxs, stats, reads, bounds, world, k, fs, nh, thr
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("exchange", ["peer", "peer-sharded-filter", "nccl"])
-@pytest.mark.parametrize("world,chunk,set_kb", [(1, None, None), (2, None, None), (3, 512, 900), (8, 4096, 3072)])
+@pytest.mark.parametrize("world,chunk,set_kb", [(1, None, None), (2, None, None), (3, 512, 900), (8, 384, 1536)])
 def test_distributed_hot_path_emulated(oracle, world, chunk, set_kb, exchange, monkeypatch):
     """R ranks as R contexts on one GPU and one stream: counts, filter, solid k-mers, adjacency and seeds equal the
     single-node oracle. exchange = "peer": the fused bin + exchange (sources store into the owners' receive regions
@@ -194,7 +194,7 @@ def test_distributed_many_verdict_rounds_and_skew(oracle, monkeypatch):
             ctxs.append(c)
         try:
             stats = pdist.run_hot_path(ctxs, pdist.EmulatedComm(world), k, fs, nh, table_slots=max(3 * n_keys // world, 4096),
-                                       chunk_words=1024, set_bytes=900 * 1024)
+                                       chunk_words=1024, set_bytes=1200 * 1024)
             assert stats[0]["cover_slices"] > 1 and stats[0]["n_chunks"] > 1
             _check_distributed(oracle, ctxs, stats, reads, bounds, world, k, fs, nh)
         finally:
