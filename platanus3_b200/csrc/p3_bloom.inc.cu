@@ -171,7 +171,7 @@ struct BloomBinState {
     uint32_t *d_bins = nullptr; uint64_t cap_bins = 0;     // PEER-SHARED (p3_mg_bloom_buffer): never reallocated here
     uint32_t *d_local = nullptr; uint64_t cap_local = 0;   // local scratch of the single-context binned paths
     uint32_t **d_segbase = nullptr; uint64_t cap_segbase = 0;
-    size_t smem_set = 0, smem_pos[2] = {0, 0};   // dynamic shared memory opted into so far (per context = per device)
+    size_t smem_set = 0, smem_pos[4] = {0, 0, 0, 0};   // dynamic shared memory opted into so far (per context = per device)
     std::vector<void *> graveyard;   // outgrown peer-shared buffers: freed with the context, never while peers may map them
 };
 static CtxStates<BloomBinState> g_bbin;
@@ -329,8 +329,8 @@ __device__ __forceinline__ bool count_below_pre(const Table &t, uint64_t key, ui
 //         out_list instead (multi-GPU owner: they go back to their source ranks).
 // MODE 1: a plain list of position records, or (in_cap > 0) a row of regions of in_cap records holding
 //         in_end[r] records each (received from the owner ranks)
-template <int MODE>
-__global__ void __launch_bounds__(kBinThreads)
+template <int MODE, bool IDX>
+__global__ void __launch_bounds__(kBinThreads, IDX ? 4 : 2)
 pos_bin_kernel(Table table, const uint64_t *__restrict__ in, const uint32_t *__restrict__ in_word, const uint32_t *__restrict__ in_idx,
                uint64_t n, uint64_t in_cap, const unsigned long long *__restrict__ in_end, const unsigned long long *__restrict__ n_dev,
                uint64_t thr, Ovf ovf, Stats *st, int shift, uint32_t P, uint32_t *__restrict__ bins,
@@ -366,15 +366,18 @@ pos_bin_kernel(Table table, const uint64_t *__restrict__ in, const uint32_t *__r
             for (uint32_t i = tid; i < P; i += kBinThreads) s_hist[i] = 0;
             __syncthreads();
             uint64_t pos[kPosKpt];
-            if (MODE == 0 && in_idx) {
-                // the insert left the partition-relative slot of every record: its count is one 8-byte load away
-                uint32_t r[kPosKpt];
+            if (MODE == 0 && IDX) {
+                // the insert left the partition-relative slot of every record: its count is one 8-byte load away. When the
+                // index also carries the record's offset and rank (table.sb), the position needs the word index only.
+                uint32_t r[kPosKpt], wd[kPosKpt];
                 uint64_t v[kPosKpt];
                 const uint64_t pbase = in_cap ? 4 * (t0 / in_cap) * table.nbp : 0;
+                const uint32_t smask = table.sb ? (1u << table.sb) - 1 : 0xFFFFFFFFu;
 #pragma unroll
                 for (int q = 0; q < kPosKpt; q++) {
                     const uint64_t i = t0 + (uint64_t)q * kBinThreads + tid;
                     r[q] = i < lim ? __ldcs(in_idx + i) : kNoSlot;
+                    wd[q] = (table.sb && i < lim) ? __ldcs(in_word + i) : 0u;
                 }
 #pragma unroll
                 for (int q = 0; q < kPosKpt; q++) {
@@ -382,7 +385,7 @@ pos_bin_kernel(Table table, const uint64_t *__restrict__ in, const uint32_t *__r
                     if (r[q] != kNoSlot) {
                         uint64_t base = pbase;
                         if (!in_cap) base = 4 * (uint64_t)part_of(fmix64(__ldcs(in + t0 + (uint64_t)q * kBinThreads + tid) & kKey42), table.P) * table.nbp;
-                        v[q] = __ldcg(table.slots + base + r[q]);
+                        v[q] = __ldcg(table.slots + base + (r[q] & smask));
                     }
                 }
 #pragma unroll
@@ -392,11 +395,16 @@ pos_bin_kernel(Table table, const uint64_t *__restrict__ in, const uint32_t *__r
                     uint64_t cnt = v[q] >> 42;
                     if (cnt < thr && n_overflow) cnt += ovf_get(ovf, v[q] & kKey42) << 22;
                     if (cnt < thr) {
-                        const uint64_t i = t0 + (uint64_t)q * kBinThreads + tid;
-                        pos[q] = posrec_of(__ldcs(in + i), __ldcs(in_word + i));
+                        if (table.sb) {
+                            const uint32_t tag = r[q] >> table.sb;   // offset:5 | rank:4
+                            pos[q] = ((uint64_t)wd[q] * 32 + (tag & 31)) | ((uint64_t)(tag >> 5) << kPosRankShift);
+                        } else {
+                            const uint64_t i = t0 + (uint64_t)q * kBinThreads + tid;
+                            pos[q] = posrec_of(__ldcs(in + i), __ldcs(in_word + i));
+                        }
                     }
                 }
-            } else if (MODE == 0) {
+            } else if (MODE == 0 && !IDX) {
                 uint64_t rec[kPosKpt / 2], s[kPosKpt / 2][4];
 #pragma unroll
                 for (int half = 0; half < 2; half++) {
@@ -522,7 +530,7 @@ pos_clear_direct_kernel(Table table, const uint64_t *__restrict__ in, const uint
                 const uint32_t r = __ldcs(in_idx + i);
                 if (r == kNoSlot) continue;
                 const uint64_t base = 4 * (in_cap ? (i / in_cap) : (uint64_t)part_of(fmix64(rec & kKey42), table.P)) * table.nbp;
-                const uint64_t v = __ldcg(table.slots + base + r);
+                const uint64_t v = __ldcg(table.slots + base + (table.sb ? (r & ((1u << table.sb) - 1)) : r));
                 uint64_t cnt = v >> 42;
                 if (cnt < thr && n_overflow) cnt += ovf_get(ovf, v & kKey42) << 22;
                 if (cnt >= thr) continue;
@@ -583,14 +591,18 @@ static int plane_clear_job(p3_ctx *c, const ClearInput &in, uint64_t n_expect, u
     }
     CU(cudaMemsetAsync(c->d_cursor, 0, sizeof(unsigned long long) * (kMaxParts + 1), c->stream));
     const size_t smem = (size_t)kBinThreads * kPosKpt * 6 + (size_t)n_seg * 20;
-    if (smem > b.smem_pos[MODE]) {
-        CU(cudaFuncSetAttribute(pos_bin_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        b.smem_pos[MODE] = smem;
+    const bool idx = MODE == 0 && in.idx != nullptr;
+    if (smem > b.smem_pos[MODE + (idx ? 2 : 0)]) {
+        if (idx) CU(cudaFuncSetAttribute(pos_bin_kernel<MODE, MODE == 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else CU(cudaFuncSetAttribute(pos_bin_kernel<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        b.smem_pos[MODE + (idx ? 2 : 0)] = smem;
     }
     const uint64_t T = (uint64_t)kBinThreads * kPosKpt;
     unsigned blocks = (unsigned)std::min<uint64_t>((in.n + T - 1) / T, (uint64_t)c->n_sm * (MODE == 0 ? 4 : 8));
-    pos_bin_kernel<MODE><<<blocks, kBinThreads, smem, c->stream>>>(c->table(), in.rec, in.word, in.idx, in.n, in.in_cap, in.in_end, in.n_dev, thr, c->ovf(),
-                                                                   c->d_stats, shift, (uint32_t)n_seg, b.d_local, cap, c->d_cursor, nullptr);
+    if (idx) pos_bin_kernel<MODE, MODE == 0><<<blocks, kBinThreads, smem, c->stream>>>(c->table(), in.rec, in.word, in.idx, in.n, in.in_cap, in.in_end, in.n_dev, thr, c->ovf(),
+                                                                                       c->d_stats, shift, (uint32_t)n_seg, b.d_local, cap, c->d_cursor, nullptr);
+    else pos_bin_kernel<MODE, false><<<blocks, kBinThreads, smem, c->stream>>>(c->table(), in.rec, in.word, in.idx, in.n, in.in_cap, in.in_end, in.n_dev, thr, c->ovf(),
+                                                                               c->d_stats, shift, (uint32_t)n_seg, b.d_local, cap, c->d_cursor, nullptr);
     CU(cudaMemsetAsync(&c->d_stats->work, 0, sizeof(unsigned long long), c->stream));
     apply_bins_kernel<true><<<c->grid(), 256, 0, c->stream>>>(b.d_local, cap, c->d_cursor, (uint32_t)n_seg, shift, plane, c->d_stats);
     c->launches += 2;

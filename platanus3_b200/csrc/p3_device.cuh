@@ -186,6 +186,8 @@ struct Table {
     uint64_t *slots;
     uint64_t nbp;   // buckets per partition (< 2^32)
     uint32_t P;     // partitions
+    uint32_t sb;    // bits of a partition-relative slot index when the insert's index stream can also carry the record's
+                    // offset-in-word (5 bits) and rank (4 bits) above it (sb + 9 <= 31), else 0 (index only)
 };
 __device__ __forceinline__ uint32_t part_of(uint64_t h, uint32_t P) { return (uint32_t)__umul64hi(h, (uint64_t)P); }
 // owner GPU of a key (21-mer or k-mer) among n ranks: a hash independent of the table hash, so

@@ -451,7 +451,7 @@ constexpr int kSweepChunk = 2048;   // records per block per grab (8 per thread)
 constexpr int kSweepPer = kSweepChunk / 256;
 constexpr int kSweepBatch = 4;
 constexpr uint32_t kNoSlot = 0xFFFFFFFFu;
-template <bool PROBE_STATS>
+template <bool PROBE_STATS, bool EXACT>
 __global__ void __launch_bounds__(256, 4)
 insert_find_kernel(const uint64_t *__restrict__ bkeys, uint64_t n, Table table, Stats *st, uint32_t *__restrict__ bidx,
                    uint64_t cap = 0, const unsigned long long *__restrict__ bin_end = nullptr,
@@ -467,35 +467,40 @@ insert_find_kernel(const uint64_t *__restrict__ bkeys, uint64_t n, Table table, 
         if (cbase >= n) break;
         // fixed-capacity bins (cap > 0, a multiple of kSweepChunk): partition p's records are
         // [p*cap, min(bin_end[p], (p+1)*cap)); a chunk never straddles two partitions
-        uint64_t lim = n;
-        if (cap) { const uint64_t p = cbase / cap; lim = min((uint64_t)__ldg(bin_end + p), (p + 1) * cap); }
+        uint64_t lim = n, pbase = 0;
+        if (!EXACT) { const uint64_t p = cbase / cap; lim = min((uint64_t)__ldg(bin_end + p), (p + 1) * cap); pbase = p * table.nbp; }
         if (cbase >= lim) continue;
 #pragma unroll
         for (int half = 0; half < kSweepPer / kSweepBatch; half++) {
             uint64_t rec[kSweepBatch], s[kSweepBatch][4];
+            uint32_t b32[kSweepBatch];
 #pragma unroll
             for (int it = 0; it < kSweepBatch; it++) {
                 const uint64_t i = cbase + (uint64_t)(half * kSweepBatch + it) * 256 + threadIdx.x;
-                rec[it] = i < lim ? (__ldcs(bkeys + i) & kKey42) : ~0ULL;
+                rec[it] = i < lim ? __ldcs(bkeys + i) : ~0ULL;
             }
 #pragma unroll
             for (int it = 0; it < kSweepBatch; it++) {
                 if (rec[it] != ~0ULL) {
-                    const uint64_t h = fmix64(rec[it]);
-                    ld_bucket(table.slots + 4 * ((uint64_t)part_of(h, table.P) * table.nbp + sub_of(h, table.nbp)), s[it]);
+                    const uint64_t h = fmix64(rec[it] & kKey42);
+                    b32[it] = (uint32_t)sub_of(h, table.nbp);
+                    const uint64_t base = EXACT ? (uint64_t)part_of(h, table.P) * table.nbp : pbase;
+                    ld_bucket(table.slots + 4 * (base + b32[it]), s[it]);
                 }
             }
 #pragma unroll
             for (int it = 0; it < kSweepBatch; it++) {
                 if (rec[it] != ~0ULL) {
                     const uint64_t i = cbase + (uint64_t)(half * kSweepBatch + it) * 256 + threadIdx.x;
-                    const uint64_t h = fmix64(rec[it]);   // recomputed: cheaper than carrying it across the loads
-                    const uint64_t base = (uint64_t)part_of(h, table.P) * table.nbp;
+                    const uint64_t key = rec[it] & kKey42;
+                    const uint64_t base = EXACT ? (uint64_t)part_of(fmix64(key), table.P) * table.nbp : pbase;
                     bool cr;
                     unsigned np = 0;
-                    const uint64_t slot = find_or_claim_pre<PROBE_STATS>(table, rec[it], base, sub_of(h, table.nbp), s[it], st, &cr, &np);
+                    const uint64_t slot = find_or_claim_pre<PROBE_STATS>(table, key, base, b32[it], s[it], st, &cr, &np);
                     created += cr;
-                    bidx[i] = slot == ~0ULL ? kNoSlot : (uint32_t)(slot - 4 * base);
+                    // the index stream also carries the record's offset-in-word and rank when they fit above the slot bits
+                    bidx[i] = slot == ~0ULL ? kNoSlot
+                                            : (uint32_t)(slot - 4 * base) | (table.sb ? (uint32_t)((rec[it] >> kRecOffShift) & 0x1FF) << table.sb : 0u);
                     if (PROBE_STATS) { probes += np; longest = max(longest, np); }
                 }
             }
@@ -539,7 +544,8 @@ insert_add_kernel(const uint32_t *__restrict__ bidx, const uint64_t *__restrict_
                 const uint64_t i = cbase + (uint64_t)it * 256 + threadIdx.x;
                 base = 4 * (uint64_t)part_of(fmix64(__ldcs(bkeys + i) & kKey42), table.P) * table.nbp;
             }
-            const uint64_t old = atomicAdd(ull(table.slots + base + r[it]), kCntOne);
+            const uint32_t rel = table.sb ? (r[it] & ((1u << table.sb) - 1)) : r[it];
+            const uint64_t old = atomicAdd(ull(table.slots + base + rel), kCntOne);
             if ((old >> 42) == kCntFieldMax) ovf_add(ovf, old & kKey42, st);   // the 22-bit field wrapped to 0
         }
     }
@@ -740,9 +746,14 @@ set_sweep_kernel(const uint64_t *__restrict__ bins, const uint8_t *__restrict__ 
         for (int it = 0; it < kSweepPer; it++) {
             if (rec[it] == kEmpty) continue;
             uint64_t slot;
-            if (set_insert_slot(set, rec[it], &slot) < 0) { full = true; continue; }
+            const int ins = set_insert_slot(set, rec[it], &slot);
+            if (ins < 0) { full = true; continue; }
+            // Hints are optional knowledge (a direction without one is simply queried later). The occurrence that creates the
+            // k-mer always leaves its hint; of the repeats only every 4th record looks at the slot's hint byte (an extra L2
+            // load per record otherwise): a third of the solid set occurs just twice, so plain sampling would lose too many.
+            if (ins == 0 && (it & 3)) continue;
             const uint32_t h = ((hb[it >> 2] >> (8 * (it & 3))) & 0xFFu) << (8 * (slot & 3));
-            if (h && (__ldcg(slot_hint + (slot >> 2)) & h) != h) atomicOr(slot_hint + (slot >> 2), h);
+            if (h && (ins || (__ldcg(slot_hint + (slot >> 2)) & h) != h)) atomicOr(slot_hint + (slot >> 2), h);
         }
     }
     if (full) atomicExch(&st->err_table_full, 1u);
@@ -1039,7 +1050,13 @@ struct p3_ctx {
     float ms_sub[4] = {0, 0, 0, 0};
     float ms_bloom = 0;                    // hist, scatter, insert, cand_check
     uint64_t n_chunks = 0, binned_pos = 0; bool pos_on_host = false;
-    Table table() const { Table t; t.slots = d_table; t.nbp = nbp; t.P = parts; return t; }
+    Table table() const {
+        Table t; t.slots = d_table; t.nbp = nbp; t.P = parts;
+        uint32_t sb = 1;
+        while ((1ull << sb) < nbp * 4) sb++;
+        t.sb = sb + 9 <= 31 ? sb : 0;
+        return t;
+    }
     uint64_t *d_ovf_keys = nullptr; unsigned long long *d_ovf_wraps = nullptr;
     bool have_counts = false;
     // make_bf
@@ -1309,8 +1326,13 @@ static void launch_scatter21_local(p3_ctx *c, unsigned sblocks, uint64_t w0, uin
 static int launch_insert_bins(p3_ctx *c, const uint64_t *keys, uint64_t n, uint64_t cap,
                               const unsigned long long *bin_end, const unsigned long long *n_dev) {
     CU(cudaMemsetAsync(&c->d_stats->work, 0, sizeof(unsigned long long), c->stream));
-    if (c->probe_stats) insert_find_kernel<true><<<c->grid(4), 256, 0, c->stream>>>(keys, n, c->table(), c->d_stats, c->d_bidx, cap, bin_end, n_dev);
-    else insert_find_kernel<false><<<c->grid(4), 256, 0, c->stream>>>(keys, n, c->table(), c->d_stats, c->d_bidx, cap, bin_end, n_dev);
+    if (c->probe_stats) {
+        if (cap) insert_find_kernel<true, false><<<c->grid(4), 256, 0, c->stream>>>(keys, n, c->table(), c->d_stats, c->d_bidx, cap, bin_end, n_dev);
+        else insert_find_kernel<true, true><<<c->grid(4), 256, 0, c->stream>>>(keys, n, c->table(), c->d_stats, c->d_bidx, cap, bin_end, n_dev);
+    } else {
+        if (cap) insert_find_kernel<false, false><<<c->grid(4), 256, 0, c->stream>>>(keys, n, c->table(), c->d_stats, c->d_bidx, cap, bin_end, n_dev);
+        else insert_find_kernel<false, true><<<c->grid(4), 256, 0, c->stream>>>(keys, n, c->table(), c->d_stats, c->d_bidx, cap, bin_end, n_dev);
+    }
     CU(cudaMemsetAsync(&c->d_stats->work, 0, sizeof(unsigned long long), c->stream));
     if (cap) insert_add_kernel<false><<<c->grid(8), 256, 0, c->stream>>>(c->d_bidx, keys, n, c->table(), c->ovf(), c->d_stats, cap, bin_end, n_dev);
     else insert_add_kernel<true><<<c->grid(8), 256, 0, c->stream>>>(c->d_bidx, keys, n, c->table(), c->ovf(), c->d_stats, cap, bin_end, n_dev);

@@ -421,9 +421,10 @@ int p3_mg_cover_begin(p3_ctx *c, uint32_t cov_threshold, uint64_t owner_distinct
     const uint64_t worst = std::max<uint64_t>(owner_distinct * std::max<uint32_t>(cov_threshold > 1 ? cov_threshold - 1 : 1, 1), 1);
     const uint64_t per_slice = std::max<uint64_t>(m.capB * m.n_ranks / 5 * 4, 1);   // 25 % slack for the spread over the sources
     uint64_t want_slices = std::max<uint64_t>((worst + per_slice - 1) / per_slice, 1);
+    want_slices = std::max<uint64_t>(want_slices, (worst + (1ull << 28) - 1) >> 28);   // the owner's verdict list stays below 2^28 records (2 GB)
     if (const char *e = getenv("P3_MG_COVER_SLICES")) want_slices = std::max<uint64_t>(want_slices, strtoull(e, nullptr, 10));   // test knob
     m.n_slices = (uint32_t)std::min<uint64_t>(want_slices, c->parts);
-    CU(ensure(m.d_sing, m.cap_sing, sizeof(uint64_t) * std::min<uint64_t>(worst + 1024, m.capB * m.n_ranks)));
+    CU(ensure(m.d_sing, m.cap_sing, sizeof(uint64_t) * std::min<uint64_t>(worst / m.n_slices * 5 / 4 + (1u << 20), m.capB * m.n_ranks)));
     if (n_slices) *n_slices = m.n_slices;
     CU(cudaMemsetAsync(&c->d_stats->err_bin_overflow, 0, sizeof(unsigned), c->stream));
     CU(cudaEventRecord(c->ev[2], c->stream));
@@ -450,7 +451,7 @@ int p3_mg_cover_send(p3_ctx *c, uint32_t cov_threshold, uint32_t slice) {
         const size_t smem = (size_t)kBinThreads * kPosKpt * 6 + 20;
         const uint64_t T = (uint64_t)kBinThreads * kPosKpt;
         unsigned blocks = (unsigned)std::min<uint64_t>((n_end - first + T - 1) / T, (uint64_t)c->n_sm * 4);
-        pos_bin_kernel<0><<<blocks, kBinThreads, smem, c->stream>>>(c->table(), c->d_bkeys, c->d_bword, c->d_bidx, n_end, m.part_cap, c->d_binmeta, nullptr,
+        pos_bin_kernel<0, true><<<blocks, kBinThreads, smem, c->stream>>>(c->table(), c->d_bkeys, c->d_bword, c->d_bidx, n_end, m.part_cap, c->d_binmeta, nullptr,
                                                                    cov_threshold, c->ovf(), c->d_stats, 27, 1, nullptr, m.cap_sing / sizeof(uint64_t), nullptr, m.d_sing);
         PeerOut64 po;
         for (uint32_t j = 0; j < (uint32_t)kMaxPeers; j++)

@@ -66,6 +66,9 @@ class TorchDistComm:
         return "cuda" if torch.cuda.is_available() and self.dist.get_backend(self.group) == "nccl" else "cpu"
 
     def all_sum(self, values):
+        """values: [ints] or, like the emulated communicator, [[ints]] of the one local rank"""
+        if values and isinstance(values[0], (list, tuple)):
+            (values,) = values
         t = torch.tensor(values, dtype=torch.int64, device=self._dev())
         self.dist.all_reduce(t, group=self.group)
         return [int(x) for x in t.tolist()]

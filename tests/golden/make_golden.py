@@ -32,6 +32,9 @@ CASES = [
     ("k32_err", 32, 0, 1500, 50, 100, 0.01, "fastq"),
     ("k32_m", 32, 200003, 2000, 10, 90, 0.02, "fasta"),
     ("k25_quirks", 25, 60013, 1500, 10, 70, 0.005, "fasta"),
+    # k = 32 with runs of 64 T's and 64 A's inside the genome: the all-T 32-mer is 2^64 - 1 as an integer, the value
+    # hash tables like to use as "empty"; it becomes a junction node here, counted by CountNodeCoverage in both orientations
+    ("k32_homopoly", 32, 400009, 1800, 40, 120, 0.004, "fasta"),
     # multi-word k-mers, two of the values the reference's own Assemble_k offers (Assemble.cpp:38-41)
     ("k63_err", 63, 0, 1500, 50, 150, 0.005, "fasta"),
     ("k101_m", 101, 300007, 1500, 30, 250, 0.003, "fastq"),
@@ -44,6 +47,11 @@ CASES = [
 
 def build_reads(name, genome, cov, rl, err, seed):
     g = synth.random_genome(genome, seed)
+    if name.endswith("homopoly"):
+        g = g.copy()
+        g[300:364] = 3          # 64 T's
+        g[900:964] = 0          # 64 A's
+        g[1400:1440] = 3        # a shorter T run: all-T 32-mers from a second context
     reads = synth.reads_as_bytes(synth.simulate_reads(g, cov, rl, err, seed + 1))
     names = [">read_%d" % i for i in range(len(reads))]
     if name.endswith("quirks"):

@@ -57,6 +57,7 @@ def _gloo_worker(rank, world, port, q):
         want = torch.cat([torch.arange(shard, dtype=torch.int32) + 1000 * (r + 1) for r in range(world)] + [torch.zeros(5, dtype=torch.int32)])
         ok = ok and torch.equal(f, want)
         ok = ok and comm.all_sum([rank + 1, 10]) == [sum(range(1, world + 1)), 10 * world]
+        ok = ok and comm.all_sum([[rank + 1, 10]]) == [sum(range(1, world + 1)), 10 * world]
         ok = ok and comm.all_max([[rank + 1, 10 - rank]]) == [world, 10]
         ok = ok and comm.all_gather([[rank, 7 * rank + 1, 3]]) == [[r, 7 * r + 1, 3] for r in range(world)]
         ok = ok and comm.all_gather([[]]) == [[] for _ in range(world)]
