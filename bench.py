@@ -385,7 +385,12 @@ def main_multi(args, rank, world, local, dev):
     e2e = None
     if not args.no_e2e:
         h_packed, h_off = wl["packed"].cpu().pin_memory(), wl["off"].cpu().pin_memory()
-        out_bits = torch.empty((fs + 7) // 8, dtype=torch.uint8).pin_memory()
+        # every rank holds the complete filter after the step; together the ranks return it ONCE (rank r its r-th part),
+        # plus each rank's own seeds, owned k-mers and adjacency bytes
+        nw32 = (fs + 31) // 32
+        part = (nw32 + world - 1) // world
+        fa, fb = min(rank * part, nw32), min((rank + 1) * part, nw32)
+        out_bits = torch.empty(max(fb - fa, 1), dtype=torch.int32).pin_memory()
         out_seeds = torch.empty(n_reads, dtype=torch.int64).pin_memory()
         out_kmers = torch.empty(owned_slots, dtype=torch.int64).pin_memory()
         out_adj = torch.empty(owned_slots, dtype=torch.uint8).pin_memory()
@@ -395,7 +400,10 @@ def main_multi(args, rank, world, local, dev):
         def step_e2e():
             _lib.check(L.p3_reads_upload(ctx.h, h_packed.data_ptr(), total, h_off.data_ptr(), n_reads, None))
             pdist.run_hot_path([ctx], comm, K, fs, nh, table_slots, 0, owned_slots, chunk_words, dev)
-            _lib.check(L.p3_bf_export(ctx.h, out_bits.data_ptr()))
+            ptr, nwords = ctypes.c_void_p(), ctypes.c_uint64()
+            _lib.check(L.p3_mg_filter(ctx.h, ctypes.byref(ptr), ctypes.byref(nwords)))
+            if fb > fa:
+                out_bits[: fb - fa].copy_(pdist.dev_tensor(ptr.value, nw32, torch.int32, dev)[fa:fb], non_blocking=True)
             _lib.check(L.p3_seed_export(ctx.h, out_seeds.data_ptr()))
             n = ctypes.c_uint64()
             _lib.check(L.p3_dbg_export(ctx.h, out_kmers.data_ptr(), out_adj.data_ptr(), owned_slots, ctypes.byref(n)))
@@ -403,7 +411,7 @@ def main_multi(args, rank, world, local, dev):
 
         step_e2e()
         e2e_ms, _ = timed(step_e2e, args.steps)
-        io = comm.all_sum([h_packed.numel() * 8 + h_off.numel() * 8, out_bits.numel() + out_seeds.numel() * 8 + got[0] * 9])
+        io = comm.all_sum([h_packed.numel() * 8 + h_off.numel() * 8, (fb - fa) * 4 + out_seeds.numel() * 8 + got[0] * 9])
         e2e = {"value": n_pos / (e2e_ms / args.steps * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
                "h2d_bytes_per_step": io[0], "d2h_bytes_per_step": io[1]}
 

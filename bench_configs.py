@@ -109,8 +109,15 @@ def config4(args, dev):
     os.environ.pop("P3_PROBE_STATS")
     count_probe = {"mean_buckets_per_insert": ps[0], "max_buckets": int(ps[1])}
     rows = []
-    ks = [int(x) for x in os.environ.get("P3_SWEEP_K", "21,32,63,101").split(",")]
+    # multi-word k (63, 101 ...) can be added with P3_SWEEP_K: its de-duplication is DRAM-random with word compares and
+    # is not in the default sweep at this size (see DESIGN.md "Multi-word k-mers")
+    ks = [int(x) for x in os.environ.get("P3_SWEEP_K", "21,25,32").split(",")]
     thrs = [int(x) for x in os.environ.get("P3_SWEEP_THR", "2,3,5").split(",")]
+    def note(msg):
+        sys.stderr.write("[config4 %.0fs] %s\n" % (time.perf_counter() - t_start, msg))
+        sys.stderr.flush()
+    t_start = time.perf_counter()
+    note("count table probe statistics done: %r" % (count_probe,))
     for k in ks:
         if k > bench.READ_LEN:
             rows.append({"k": k, "skipped": "reads of %d bp are shorter than k" % bench.READ_LEN})
@@ -135,6 +142,7 @@ def config4(args, dev):
                            solid_set_probe={"mean_buckets_per_lookup": ps[2], "max_buckets": int(ps[3])} if k <= 32 else None)
             except _lib.P3Error as e:
                 row["error"] = str(e)
+            note("k=%d thr=%d: %s" % (k, thr, {kk: row.get(kk) for kk in ("ms_per_step", "solid_kmers", "error")}))
             rows.append(row)
     slots = ctypes.c_uint64 * 4
     cap = slots()
@@ -173,6 +181,8 @@ def config2(args, dev):
     ctx = _lib.Context(dev.index or 0, ctypes.c_void_p(stream.cuda_stream))
     ctx.attach(wl["packed"].data_ptr(), total, wl["off"].data_ptr(), n_reads, None, keep=wl)
     rows = []
+    t_start = time.perf_counter()
+    sys.stderr.write("[config2] %d reads of %d bp generated\n" % (n_reads, rl)); sys.stderr.flush()
     for k in [int(x) for x in os.environ.get("P3_LONG_K", "3001,63").split(",")]:
         fs, nh = _lib.estimate_bloomfilter(total, k)
         row = {"k": k, "words_per_kmer": (2 * k + 63) // 64, "filter_size_bits": fs, "num_hashes": nh}
@@ -189,6 +199,7 @@ def config2(args, dev):
             row.update(stage_ms=acc, ms_per_step=step_ms, kmers_per_s=n_pos / (step_ms * 1e-3), bf_adds=n_adds, solid_kmers=n_solid, dbg_edges=n_edges)
         except _lib.P3Error as e:
             row["error"] = str(e)
+        sys.stderr.write("[config2 %.0fs] k=%d: %r\n" % (time.perf_counter() - t_start, k, {kk: row.get(kk) for kk in ("stage_ms", "solid_kmers", "error")})); sys.stderr.flush()
         rows.append(row)
     best = rows[0]
     print(json.dumps({

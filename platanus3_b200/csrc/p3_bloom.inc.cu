@@ -321,6 +321,37 @@ __device__ __forceinline__ bool count_below_pre(const Table &t, uint64_t key, ui
     return true;
 }
 
+// "count < thr" of every table slot as ONE BIT (streaming pass over the table, 32 slots per thread): the verdict sweep then
+// asks a 0.75 MB window per 48 MB partition instead of the slots themselves — always an L2 (mostly L1) hit
+__global__ void __launch_bounds__(256)
+below_bits_kernel(const uint64_t *__restrict__ slots, uint64_t n_slots, uint64_t thr, Ovf ovf, const Stats *st, uint32_t *__restrict__ bits) {
+    const unsigned n_overflow = st->n_overflow;
+    const int lane = threadIdx.x & 31;
+    const uint64_t n_words = (n_slots + 31) / 32;
+    const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * (uint64_t)blockDim.x) >> 5;
+    // a warp turns 32 x 32 consecutive slots into 32 words: lane l reads slot 32 j + l of word j (coalesced), the ballot is
+    // word j, lane j keeps it
+    for (uint64_t w0 = warp * 32; w0 < n_words; w0 += n_warps * 32) {
+        uint32_t mine = 0;
+#pragma unroll 4
+        for (int j = 0; j < 32; j++) {
+            const uint64_t i = (w0 + j) * 32 + lane;
+            bool below = false;
+            if (i < n_slots) {
+                const uint64_t v = __ldcs(slots + i);
+                if (v != kEmpty) {
+                    uint64_t cnt = v >> 42;
+                    if (cnt < thr && n_overflow) cnt += ovf_get(ovf, v & kKey42) << 22;
+                    below = cnt < thr;
+                }
+            }
+            const uint32_t m = __ballot_sync(0xffffffffu, below);
+            if (lane == j) mine = m;
+        }
+        if (w0 + lane < n_words) bits[w0 + lane] = mine;
+    }
+}
+
 // MODE 0: the verdict sweep — the input is the partition bins of the count (records + word indices, laid
 //         out as in_cap-sized bins ending at in_end[p], or contiguous when in_cap == 0); every record whose
 //         key's final count < thr emits its position. Tiles are handed out from a global counter so that
@@ -330,8 +361,9 @@ __device__ __forceinline__ bool count_below_pre(const Table &t, uint64_t key, ui
 // MODE 1: a plain list of position records, or (in_cap > 0) a row of regions of in_cap records holding
 //         in_end[r] records each (received from the owner ranks)
 template <int MODE, bool IDX>
-__global__ void __launch_bounds__(kBinThreads, IDX ? 4 : 2)
+__global__ void __launch_bounds__(kBinThreads, IDX ? 6 : 2)
 pos_bin_kernel(Table table, const uint64_t *__restrict__ in, const uint32_t *__restrict__ in_word, const uint32_t *__restrict__ in_idx,
+               const uint32_t *__restrict__ below,
                uint64_t n, uint64_t in_cap, const unsigned long long *__restrict__ in_end, const unsigned long long *__restrict__ n_dev,
                uint64_t thr, Ovf ovf, Stats *st, int shift, uint32_t P, uint32_t *__restrict__ bins,
                uint64_t cap, unsigned long long *cursor, uint64_t *__restrict__ out_list) {
@@ -369,38 +401,40 @@ pos_bin_kernel(Table table, const uint64_t *__restrict__ in, const uint32_t *__r
             if (MODE == 0 && IDX) {
                 // the insert left the partition-relative slot of every record: its count is one 8-byte load away. When the
                 // index also carries the record's offset and rank (table.sb), the position needs the word index only.
-                uint32_t r[kPosKpt], wd[kPosKpt];
-                uint64_t v[kPosKpt];
                 const uint64_t pbase = in_cap ? 4 * (t0 / in_cap) * table.nbp : 0;
                 const uint32_t smask = table.sb ? (1u << table.sb) - 1 : 0xFFFFFFFFu;
 #pragma unroll
-                for (int q = 0; q < kPosKpt; q++) {
-                    const uint64_t i = t0 + (uint64_t)q * kBinThreads + tid;
-                    r[q] = i < lim ? __ldcs(in_idx + i) : kNoSlot;
-                    wd[q] = (table.sb && i < lim) ? __ldcs(in_word + i) : 0u;
-                }
+                for (int half = 0; half < 2; half++) {     // four records at a time keeps the kernel at 6 blocks per SM
+                    constexpr int H = kPosKpt / 2;
+                    uint32_t r[H], wd[H], v[H];
 #pragma unroll
-                for (int q = 0; q < kPosKpt; q++) {
-                    v[q] = kEmpty;
-                    if (r[q] != kNoSlot) {
-                        uint64_t base = pbase;
-                        if (!in_cap) base = 4 * (uint64_t)part_of(fmix64(__ldcs(in + t0 + (uint64_t)q * kBinThreads + tid) & kKey42), table.P) * table.nbp;
-                        v[q] = __ldcg(table.slots + base + (r[q] & smask));
+                    for (int q = 0; q < H; q++) {
+                        const uint64_t i = t0 + (uint64_t)(half * H + q) * kBinThreads + tid;
+                        r[q] = i < lim ? __ldcs(in_idx + i) : kNoSlot;
+                        wd[q] = (table.sb && i < lim) ? __ldcs(in_word + i) : 0u;
                     }
-                }
 #pragma unroll
-                for (int q = 0; q < kPosKpt; q++) {
-                    pos[q] = ~0ULL;
-                    if (r[q] == kNoSlot) continue;
-                    uint64_t cnt = v[q] >> 42;
-                    if (cnt < thr && n_overflow) cnt += ovf_get(ovf, v[q] & kKey42) << 22;
-                    if (cnt < thr) {
-                        if (table.sb) {
-                            const uint32_t tag = r[q] >> table.sb;   // offset:5 | rank:4
-                            pos[q] = ((uint64_t)wd[q] * 32 + (tag & 31)) | ((uint64_t)(tag >> 5) << kPosRankShift);
-                        } else {
-                            const uint64_t i = t0 + (uint64_t)q * kBinThreads + tid;
-                            pos[q] = posrec_of(__ldcs(in + i), __ldcs(in_word + i));
+                    for (int q = 0; q < H; q++) {
+                        v[q] = 0;
+                        if (r[q] != kNoSlot) {
+                            uint64_t base = pbase;
+                            if (!in_cap) base = 4 * (uint64_t)part_of(fmix64(__ldcs(in + t0 + (uint64_t)(half * H + q) * kBinThreads + tid) & kKey42), table.P) * table.nbp;
+                            const uint64_t slot = base + (r[q] & smask);
+                            v[q] = (__ldg(below + (slot >> 5)) >> (slot & 31)) & 1u;     // final count of the record's key < thr
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < H; q++) {
+                        const int qq = half * H + q;
+                        pos[qq] = ~0ULL;
+                        if (v[q]) {
+                            if (table.sb) {
+                                const uint32_t tag = r[q] >> table.sb;   // offset:5 | rank:4
+                                pos[qq] = ((uint64_t)wd[q] * 32 + (tag & 31)) | ((uint64_t)(tag >> 5) << kPosRankShift);
+                            } else {
+                                const uint64_t i = t0 + (uint64_t)qq * kBinThreads + tid;
+                                pos[qq] = posrec_of(__ldcs(in + i), __ldcs(in_word + i));
+                            }
                         }
                     }
                 }
@@ -546,6 +580,7 @@ pos_clear_direct_kernel(Table table, const uint64_t *__restrict__ in, const uint
 struct ClearInput {
     const uint64_t *rec = nullptr; const uint32_t *word = nullptr;    // MODE 0: count records + word indices; MODE 1: position records
     const uint32_t *idx = nullptr;                                    // MODE 0, optional: partition-relative slot of every record (insert_find)
+    const uint32_t *below = nullptr;                                  // with idx: one bit per table slot, final count < thr (below_bits_kernel)
     uint64_t n = 0;                                                   // inputs (capacity space when in_cap > 0)
     uint64_t in_cap = 0; const unsigned long long *in_end = nullptr;  // binned / regioned layout
     const unsigned long long *n_dev = nullptr;                        // contiguous layout with the count on the device
@@ -591,7 +626,7 @@ static int plane_clear_job(p3_ctx *c, const ClearInput &in, uint64_t n_expect, u
     }
     CU(cudaMemsetAsync(c->d_cursor, 0, sizeof(unsigned long long) * (kMaxParts + 1), c->stream));
     const size_t smem = (size_t)kBinThreads * kPosKpt * 6 + (size_t)n_seg * 20;
-    const bool idx = MODE == 0 && in.idx != nullptr;
+    const bool idx = MODE == 0 && in.idx != nullptr && in.below != nullptr;
     if (smem > b.smem_pos[MODE + (idx ? 2 : 0)]) {
         if (idx) CU(cudaFuncSetAttribute(pos_bin_kernel<MODE, MODE == 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         else CU(cudaFuncSetAttribute(pos_bin_kernel<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -599,9 +634,9 @@ static int plane_clear_job(p3_ctx *c, const ClearInput &in, uint64_t n_expect, u
     }
     const uint64_t T = (uint64_t)kBinThreads * kPosKpt;
     unsigned blocks = (unsigned)std::min<uint64_t>((in.n + T - 1) / T, (uint64_t)c->n_sm * (MODE == 0 ? 4 : 8));
-    if (idx) pos_bin_kernel<MODE, MODE == 0><<<blocks, kBinThreads, smem, c->stream>>>(c->table(), in.rec, in.word, in.idx, in.n, in.in_cap, in.in_end, in.n_dev, thr, c->ovf(),
+    if (idx) pos_bin_kernel<MODE, MODE == 0><<<blocks, kBinThreads, smem, c->stream>>>(c->table(), in.rec, in.word, in.idx, in.below, in.n, in.in_cap, in.in_end, in.n_dev, thr, c->ovf(),
                                                                                        c->d_stats, shift, (uint32_t)n_seg, b.d_local, cap, c->d_cursor, nullptr);
-    else pos_bin_kernel<MODE, false><<<blocks, kBinThreads, smem, c->stream>>>(c->table(), in.rec, in.word, in.idx, in.n, in.in_cap, in.in_end, in.n_dev, thr, c->ovf(),
+    else pos_bin_kernel<MODE, false><<<blocks, kBinThreads, smem, c->stream>>>(c->table(), in.rec, in.word, in.idx, nullptr, in.n, in.in_cap, in.in_end, in.n_dev, thr, c->ovf(),
                                                                                c->d_stats, shift, (uint32_t)n_seg, b.d_local, cap, c->d_cursor, nullptr);
     CU(cudaMemsetAsync(&c->d_stats->work, 0, sizeof(unsigned long long), c->stream));
     apply_bins_kernel<true><<<c->grid(), 256, 0, c->stream>>>(b.d_local, cap, c->d_cursor, (uint32_t)n_seg, shift, plane, c->d_stats);
@@ -614,6 +649,15 @@ static int plane_clear_job(p3_ctx *c, const ClearInput &in, uint64_t n_expect, u
 // MakeBF's coverage flags from the binned count (reference src/MakeBloomFilter.cpp:52-58, any threshold):
 // good21 := valid, then every occurrence of a key whose final count < thr clears its bit. The bins of a
 // one-chunk count are still there; otherwise the reads are binned again chunk by chunk.
+// one bit per table slot: final count < thr (input of the verdict sweep over the insert's index stream)
+static int below_bits(p3_ctx *c, uint64_t thr) {
+    const uint64_t n_slots = c->nb * 4;
+    CU(ensure(c->d_below, c->cap_below, sizeof(uint32_t) * ((n_slots + 31) / 32 + 1)));
+    below_bits_kernel<<<c->grid(), 256, 0, c->stream>>>(c->d_table, n_slots, thr, c->ovf(), c->d_stats, c->d_below);
+    c->launches++;
+    CU(cudaGetLastError());
+    return P3_OK;
+}
 static int verdict_sweep(p3_ctx *c, uint64_t thr, bool force_direct, bool *binned_any) {
     *binned_any = false;
     CU(cudaMemcpyAsync(c->d_good21, c->d_valid, sizeof(uint32_t) * c->n_words, cudaMemcpyDeviceToDevice, c->stream));
@@ -624,13 +668,18 @@ static int verdict_sweep(p3_ctx *c, uint64_t thr, bool force_direct, bool *binne
         ClearInput in;
         in.rec = c->d_bkeys; in.word = c->d_bword; in.n = c->bin_n; in.in_cap = c->bin_cap; in.in_end = c->d_binmeta;
         in.idx = c->bins_valid ? c->d_bidx : nullptr;   // re-binned chunks have no index stream: bucket probes instead
+        in.below = c->bins_valid ? c->d_below : nullptr;
         in.n_dev = c->bin_cap ? nullptr : c->d_binmeta + kMaxParts;
         bool b = false;
         int rc = plane_clear_job<0>(c, in, n_expect / share_den * share_num + (1u << 16), thr, c->d_good21, c->n_words * 32, force_direct, &b);
         *binned_any = *binned_any || b;
         return rc;
     };
-    if (c->bins_valid) return one(1, 1);
+    if (c->bins_valid) {
+        int rcb = below_bits(c, thr);
+        if (rcb) return rcb;
+        return one(1, 1);
+    }
     BinPlan pl;
     int rc = plan_bins(c, c->bin_upper, c->bin_exact, &pl);
     if (rc) return rc;

@@ -182,6 +182,10 @@ __device__ __forceinline__ void count_bump(uint64_t *slot, uint64_t seen, uint64
 // a sweep over records binned by partition touches one partition at a time, which then stays
 // L2 resident (profiles/r01_randacc.md: 62-77 G inserts/s instead of 17.4 G/s from DRAM).
 constexpr int kMaxParts = 1024;
+// Longest probe sequence an insert walks before it reports "full": a (nearly) full partition must fail fast instead of
+// crawling through every bucket for every remaining record. At the load factors in use (<= 0.6) the longest chains
+// measured are ~12 buckets.
+constexpr uint64_t kMaxProbe = 4096;
 struct Table {
     uint64_t *slots;
     uint64_t nbp;   // buckets per partition (< 2^32)
@@ -224,7 +228,7 @@ __device__ __forceinline__ uint64_t count_insert(const Table &t, uint64_t key, c
     const uint64_t base = (uint64_t)part_of(h, t.P) * t.nbp;
     uint64_t b = sub_of(h, t.nbp);
     *created_slot = ~0ULL;
-    for (uint64_t probe = 0; probe < t.nbp; probe++) {
+    for (uint64_t probe = 0; probe < t.nbp && probe < kMaxProbe; probe++) {
         uint64_t *bp = t.slots + 4 * (base + b);
         uint64_t s[4];
         ld_bucket(bp, s);
@@ -282,7 +286,7 @@ __device__ __forceinline__ int set_insert(const KSet &t, uint64_t key) {
     const uint64_t h = fmix64(key);
     const uint64_t base = (uint64_t)part_of(h, t.P) * t.nbp;
     uint64_t b = sub_of(h, t.nbp);
-    for (uint64_t probe = 0; probe < t.nbp; probe++) {
+    for (uint64_t probe = 0; probe < t.nbp && probe < kMaxProbe; probe++) {
         uint64_t *bp = t.slots + 4 * (base + b);
         uint64_t s[4];
         ld_bucket64(bp, s);
@@ -306,7 +310,7 @@ __device__ __forceinline__ int set_insert_slot(const KSet &t, uint64_t key, uint
     const uint64_t h = fmix64(key);
     const uint64_t base = (uint64_t)part_of(h, t.P) * t.nbp;
     uint64_t b = sub_of(h, t.nbp);
-    for (uint64_t probe = 0; probe < t.nbp; probe++) {
+    for (uint64_t probe = 0; probe < t.nbp && probe < kMaxProbe; probe++) {
         uint64_t *bp = t.slots + 4 * (base + b);
         uint64_t s[4];
         ld_bucket64(bp, s);

@@ -182,13 +182,15 @@ __global__ void check_cursors_kernel(const unsigned long long *__restrict__ curs
 // that no side arrays are needed: 44 KB per block = 5 blocks per SM (72 KB = 3 blocks before). The
 // generic record sort (arbitrary 64-bit records) keeps a 16-bit partition array, and a 16-bit source
 // index when an auxiliary word travels with the record.
-template <bool PART, bool LOC>
+template <bool PART, bool LOC, int AUXB = 0>
 struct ScatterSmemT {
     uint64_t key[kTilePos];               // 32 KB  records sorted by partition
     uint32_t hist[kMaxParts];             //  4 KB  per-partition counts, then (in place) exclusive offsets
     unsigned long long gbase[kMaxParts];  //  8 KB
     uint16_t part[PART ? kTilePos : 1];   //  8 KB
     uint16_t loc[LOC ? kTilePos : 1];     //  8 KB
+    uint32_t aux4[AUXB == 4 ? kTilePos : 1];   // 16 KB  the auxiliary word of every sorted record (generic record sort)
+    uint8_t aux1[AUXB == 1 ? kTilePos : 1];    //  4 KB
     uint32_t warp_tot[16];
     uint32_t total;
 };
@@ -350,7 +352,7 @@ scatter_rec_kernel(const uint64_t *__restrict__ in, const void *__restrict__ aux
                    const unsigned long long *__restrict__ n_dev = nullptr,
                    uint64_t in_cap = 0, const unsigned long long *__restrict__ in_counts = nullptr, Stats *st = nullptr) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    using SM = ScatterSmemT<true, AUXB != 0>;
+    using SM = ScatterSmemT<true, false, AUXB>;
     SM &sm = *reinterpret_cast<SM *>(smem_raw);
     constexpr int NT = kScatterThreads, PER = kTilePos / NT;   // 512 threads x 8 records
     const int tid = threadIdx.x;
@@ -364,18 +366,28 @@ scatter_rec_kernel(const uint64_t *__restrict__ in, const void *__restrict__ aux
         if (t0 >= lim) continue;    // block-uniform
         for (uint32_t i = tid; i < P; i += NT) sm.hist[i] = 0;
         __syncthreads();
+        // records, their auxiliary values and their partition ids are read / computed ONCE, coalesced, and kept in registers
         uint64_t rec[PER];
-        uint32_t rk[PER / 2];   // two 16-bit arrival ranks per register
+        uint32_t rk[PER / 2], pt2[PER / 2], aux[AUXB == 4 ? PER : (AUXB == 1 ? PER / 4 : 1)];
 #pragma unroll
         for (int j = 0; j < PER; j++) {
             uint64_t i = t0 + j * NT + tid;
             rec[j] = i < lim ? __ldcs(in + i) : 0;
+            if (AUXB == 4) aux[j] = i < lim ? __ldcs(static_cast<const uint32_t *>(aux_in_) + i) : 0u;
+            if (AUXB == 1) {
+                if ((j & 3) == 0) aux[j >> 2] = 0;
+                if (i < lim) aux[j >> 2] |= (uint32_t)__ldcs(static_cast<const uint8_t *>(aux_in_) + i) << (8 * (j & 3));
+            }
         }
 #pragma unroll
         for (int j = 0; j < PER; j++) {
             uint64_t i = t0 + j * NT + tid;
-            if ((j & 1) == 0) rk[j >> 1] = 0;
-            if (i < lim) rk[j >> 1] |= atomicAdd(&sm.hist[pid_of<PMODE>(rec[j], P)], 1u) << (16 * (j & 1));
+            if ((j & 1) == 0) { rk[j >> 1] = 0; pt2[j >> 1] = 0; }
+            if (i < lim) {
+                const uint32_t pt = pid_of<PMODE>(rec[j], P);
+                pt2[j >> 1] |= pt << (16 * (j & 1));
+                rk[j >> 1] |= atomicAdd(&sm.hist[pt], 1u) << (16 * (j & 1));
+            }
         }
         __syncthreads();
         tile_scan_and_claim<NT>(sm, P, cursor, tid);
@@ -384,11 +396,12 @@ scatter_rec_kernel(const uint64_t *__restrict__ in, const void *__restrict__ aux
         for (int j = 0; j < PER; j++) {
             uint64_t i = t0 + j * NT + tid;
             if (i < lim) {
-                uint32_t pt = pid_of<PMODE>(rec[j], P);
-                uint32_t idx = sm.hist[pt] + ((rk[j >> 1] >> (16 * (j & 1))) & 0xFFFFu);
+                const uint32_t pt = (pt2[j >> 1] >> (16 * (j & 1))) & 0xFFFFu;
+                const uint32_t idx = sm.hist[pt] + ((rk[j >> 1] >> (16 * (j & 1))) & 0xFFFFu);
                 sm.key[idx] = rec[j];
                 sm.part[idx] = (uint16_t)pt;
-                if (AUXB) sm.loc[idx] = (uint16_t)(j * NT + tid);
+                if (AUXB == 4) sm.aux4[idx] = aux[j];
+                if (AUXB == 1) sm.aux1[idx] = (uint8_t)(aux[j >> 2] >> (8 * (j & 3)));
             }
         }
         __syncthreads();
@@ -398,8 +411,8 @@ scatter_rec_kernel(const uint64_t *__restrict__ in, const void *__restrict__ aux
             unsigned long long dst = sm.gbase[pt] + (i - sm.hist[pt]);
             if (cap && dst >= (uint64_t)(pt + 1) * cap) { over = true; continue; }
             out[dst] = sm.key[i];
-            if (AUXB == 4) static_cast<uint32_t *>(aux_out_)[dst] = __ldg(static_cast<const uint32_t *>(aux_in_) + t0 + sm.loc[i]);
-            if (AUXB == 1) static_cast<uint8_t *>(aux_out_)[dst] = __ldg(static_cast<const uint8_t *>(aux_in_) + t0 + sm.loc[i]);
+            if (AUXB == 4) static_cast<uint32_t *>(aux_out_)[dst] = sm.aux4[i];
+            if (AUXB == 1) static_cast<uint8_t *>(aux_out_)[dst] = sm.aux1[i];
         }
         __syncthreads();
     }
@@ -415,7 +428,7 @@ template <bool PROBE_STATS>
 __device__ __forceinline__ uint64_t find_or_claim_pre(const Table &t, uint64_t key, uint64_t base, uint64_t b, uint64_t s[4],
                                                       Stats *st, bool *created, unsigned *n_probes) {
     *created = false;
-    for (uint64_t probe = 0; probe < t.nbp; probe++) {
+    for (uint64_t probe = 0; probe < t.nbp && probe < kMaxProbe; probe++) {
         uint64_t *bp = t.slots + 4 * (base + b);
         if (probe) ld_bucket(bp, s);
         if (PROBE_STATS) (*n_probes)++;
@@ -449,10 +462,10 @@ __device__ __forceinline__ uint64_t find_or_claim_pre(const Table &t, uint64_t k
 // in-flight chunks lie within gridDim * kSweepChunk records of each other, i.e. inside one or two partitions.
 constexpr int kSweepChunk = 2048;   // records per block per grab (8 per thread)
 constexpr int kSweepPer = kSweepChunk / 256;
-constexpr int kSweepBatch = 4;
+constexpr int kSweepBatch = 1;   // records in flight per thread: 1 at full occupancy beat 2 / 4 / 8 with fewer warps (84 / 94 / 113 / 166 ms)
 constexpr uint32_t kNoSlot = 0xFFFFFFFFu;
-template <bool PROBE_STATS, bool EXACT>
-__global__ void __launch_bounds__(256, 4)
+template <bool PROBE_STATS, bool EXACT, int BATCH = kSweepBatch>
+__global__ void __launch_bounds__(256, BATCH == 8 ? 2 : (BATCH == 4 ? 4 : (BATCH == 2 ? 6 : 8)))
 insert_find_kernel(const uint64_t *__restrict__ bkeys, uint64_t n, Table table, Stats *st, uint32_t *__restrict__ bidx,
                    uint64_t cap = 0, const unsigned long long *__restrict__ bin_end = nullptr,
                    const unsigned long long *__restrict__ n_dev = nullptr) {
@@ -471,16 +484,16 @@ insert_find_kernel(const uint64_t *__restrict__ bkeys, uint64_t n, Table table, 
         if (!EXACT) { const uint64_t p = cbase / cap; lim = min((uint64_t)__ldg(bin_end + p), (p + 1) * cap); pbase = p * table.nbp; }
         if (cbase >= lim) continue;
 #pragma unroll
-        for (int half = 0; half < kSweepPer / kSweepBatch; half++) {
-            uint64_t rec[kSweepBatch], s[kSweepBatch][4];
-            uint32_t b32[kSweepBatch];
+        for (int half = 0; half < kSweepPer / BATCH; half++) {
+            uint64_t rec[BATCH], s[BATCH][4];
+            uint32_t b32[BATCH];
 #pragma unroll
-            for (int it = 0; it < kSweepBatch; it++) {
-                const uint64_t i = cbase + (uint64_t)(half * kSweepBatch + it) * 256 + threadIdx.x;
+            for (int it = 0; it < BATCH; it++) {
+                const uint64_t i = cbase + (uint64_t)(half * BATCH + it) * 256 + threadIdx.x;
                 rec[it] = i < lim ? __ldcs(bkeys + i) : ~0ULL;
             }
 #pragma unroll
-            for (int it = 0; it < kSweepBatch; it++) {
+            for (int it = 0; it < BATCH; it++) {
                 if (rec[it] != ~0ULL) {
                     const uint64_t h = fmix64(rec[it] & kKey42);
                     b32[it] = (uint32_t)sub_of(h, table.nbp);
@@ -489,9 +502,9 @@ insert_find_kernel(const uint64_t *__restrict__ bkeys, uint64_t n, Table table, 
                 }
             }
 #pragma unroll
-            for (int it = 0; it < kSweepBatch; it++) {
+            for (int it = 0; it < BATCH; it++) {
                 if (rec[it] != ~0ULL) {
-                    const uint64_t i = cbase + (uint64_t)(half * kSweepBatch + it) * 256 + threadIdx.x;
+                    const uint64_t i = cbase + (uint64_t)(half * BATCH + it) * 256 + threadIdx.x;
                     const uint64_t key = rec[it] & kKey42;
                     const uint64_t base = EXACT ? (uint64_t)part_of(fmix64(key), table.P) * table.nbp : pbase;
                     bool cr;
@@ -499,8 +512,9 @@ insert_find_kernel(const uint64_t *__restrict__ bkeys, uint64_t n, Table table, 
                     const uint64_t slot = find_or_claim_pre<PROBE_STATS>(table, key, base, b32[it], s[it], st, &cr, &np);
                     created += cr;
                     // the index stream also carries the record's offset-in-word and rank when they fit above the slot bits
-                    bidx[i] = slot == ~0ULL ? kNoSlot
-                                            : (uint32_t)(slot - 4 * base) | (table.sb ? (uint32_t)((rec[it] >> kRecOffShift) & 0x1FF) << table.sb : 0u);
+                    // streaming store: the index stream must not push the table partition out of L2
+                    __stcs(bidx + i, slot == ~0ULL ? kNoSlot
+                                                   : (uint32_t)(slot - 4 * base) | (table.sb ? (uint32_t)((rec[it] >> kRecOffShift) & 0x1FF) << table.sb : 0u));
                     if (PROBE_STATS) { probes += np; longest = max(longest, np); }
                 }
             }
@@ -719,7 +733,7 @@ scatter_kmer_kernel(const uint64_t *__restrict__ packed, const uint32_t *__restr
 }
 // hints (optional): one byte per record, OR-ed into the byte of the set slot that holds the k-mer
 // (a plain load first: 95 % of the records repeat a hint that is already there)
-__global__ void __launch_bounds__(256)   // capping at 32 registers spills 250 bytes and costs 19 ms
+__global__ void __launch_bounds__(256, 6)   // 42 registers; capping at 32 spills 250 bytes and costs 19 ms
 set_sweep_kernel(const uint64_t *__restrict__ bins, const uint8_t *__restrict__ hbins, uint64_t n, uint64_t cap,
                  const unsigned long long *__restrict__ bin_end, KSet set, uint32_t *__restrict__ slot_hint, Stats *st) {
     __shared__ unsigned long long s_base;
@@ -1032,6 +1046,7 @@ struct p3_ctx {
     uint32_t parts = 1; uint64_t nbp = 0;
     bool binned = true;                                // P3_COUNT_MODE=direct switches it off
     uint64_t *d_bkeys = nullptr; uint32_t *d_bword = nullptr; uint64_t cap_bkeys = 0, cap_bword = 0;
+    uint32_t *d_below = nullptr; uint64_t cap_below = 0;   // one bit per table slot: final count < threshold (verdict sweep)
     uint32_t *d_bidx = nullptr; uint64_t cap_bidx = 0;   // partition-relative slot index of every binned record (insert_find -> insert_add -> verdict sweep)
     uint32_t *d_valid = nullptr; uint64_t cap_valid = 0;
     uint64_t bin_cap = 0, bin_n = 0; bool bins_valid = false;   // the partition bins of the last count (one chunk) are still there for the verdict sweep
@@ -1105,7 +1120,7 @@ static void mg_release(struct p3_ctx *c);   // p3_multi.inc.cu
 static void long_release(struct p3_ctx *c); // p3_long.inc.cu
 static void bloom_release(struct p3_ctx *c);                                  // p3_bloom.inc.cu
 static int bloom_add_binned(struct p3_ctx *c, uint64_t n, bool *done);
-static int make_bf_long(struct p3_ctx *c, uint32_t k, uint64_t solid_slots);
+static int make_bf_long(struct p3_ctx *c, uint32_t k, uint64_t solid_slots, uint64_t est_distinct);
 static int verdict_sweep(struct p3_ctx *c, uint64_t thr, bool force_direct, bool *binned_any);   // p3_bloom.inc.cu
 static int bloom_add_direct_long(struct p3_ctx *c, uint64_t nd);
 static int adjacency_long(struct p3_ctx *c, const uint64_t *d_words, uint64_t n, uint8_t *d_adj, struct p3::Stats *st);
@@ -1205,7 +1220,7 @@ void p3_destroy(p3_ctx *c) {
     long_release(c);
     bloom_release(c);
     free_reads(c); free_bf(c);
-    dfree(c->d_table); dfree(c->d_proven2); dfree(c->d_bkeys); dfree(c->d_bword); dfree(c->d_bidx); dfree(c->d_valid);
+    dfree(c->d_table); dfree(c->d_proven2); dfree(c->d_bkeys); dfree(c->d_bword); dfree(c->d_bidx); dfree(c->d_below); dfree(c->d_valid);
     dfree(c->d_ghist); dfree(c->d_binmeta); dfree(c->d_cursor); dfree(c->d_ovf_keys); dfree(c->d_ovf_wraps); dfree(c->d_stats);
     for (auto &e : c->ev) cudaEventDestroy(e);
     for (auto &e : c->evpool) cudaEventDestroy(e);
@@ -1286,6 +1301,7 @@ static int count_direct(p3_ctx *c) {
 static int scatter_attrs(p3_ctx *c) {
     if (c->attrs_set) return P3_OK;
     const int s21 = (int)sizeof(ScatterSmem21), sP = (int)sizeof(ScatterSmemT<true, false>), sPL = (int)sizeof(ScatterSmemT<true, true>);
+    const int sA4 = (int)sizeof(ScatterSmemT<true, false, 4>), sA1 = (int)sizeof(ScatterSmemT<true, false, 1>);
     CU(cudaFuncSetAttribute(scatter21_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, s21));
     CU(cudaFuncSetAttribute(scatter21_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, s21));
     CU(cudaFuncSetAttribute(scatter21_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, s21));
@@ -1296,10 +1312,10 @@ static int scatter_attrs(p3_ctx *c) {
     CU(cudaFuncSetAttribute(scatter_kmer_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sPL));
     CU(cudaFuncSetAttribute(scatter_kmer_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sPL));
     CU(cudaFuncSetAttribute(scatter_kmer_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sPL));
-    CU(cudaFuncSetAttribute(scatter_rec_kernel<0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sPL));
+    CU(cudaFuncSetAttribute(scatter_rec_kernel<0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sA4));
     CU(cudaFuncSetAttribute(scatter_rec_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sP));
     CU(cudaFuncSetAttribute(scatter_rec_kernel<3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sP));
-    CU(cudaFuncSetAttribute(scatter_rec_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sPL));
+    CU(cudaFuncSetAttribute(scatter_rec_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sA1));
     c->attrs_set = true;
     return P3_OK;
 }
@@ -1315,6 +1331,7 @@ static cudaEvent_t pool_event(p3_ctx *c, size_t i) {
     return c->evpool[i];
 }
 constexpr size_t kSmem21 = sizeof(ScatterSmem21), kSmemP = sizeof(ScatterSmemT<true, false>), kSmemPL = sizeof(ScatterSmemT<true, true>);
+constexpr size_t kSmemA4 = sizeof(ScatterSmemT<true, false, 4>), kSmemA1 = sizeof(ScatterSmemT<true, false, 1>);
 
 extern "C++" {
 template <bool HAS_MASK>
@@ -1327,11 +1344,16 @@ static int launch_insert_bins(p3_ctx *c, const uint64_t *keys, uint64_t n, uint6
                               const unsigned long long *bin_end, const unsigned long long *n_dev) {
     CU(cudaMemsetAsync(&c->d_stats->work, 0, sizeof(unsigned long long), c->stream));
     if (c->probe_stats) {
-        if (cap) insert_find_kernel<true, false><<<c->grid(4), 256, 0, c->stream>>>(keys, n, c->table(), c->d_stats, c->d_bidx, cap, bin_end, n_dev);
-        else insert_find_kernel<true, true><<<c->grid(4), 256, 0, c->stream>>>(keys, n, c->table(), c->d_stats, c->d_bidx, cap, bin_end, n_dev);
+        if (cap) insert_find_kernel<true, false><<<c->grid(8), 256, 0, c->stream>>>(keys, n, c->table(), c->d_stats, c->d_bidx, cap, bin_end, n_dev);
+        else insert_find_kernel<true, true><<<c->grid(8), 256, 0, c->stream>>>(keys, n, c->table(), c->d_stats, c->d_bidx, cap, bin_end, n_dev);
+    } else if (cap) {
+        static const int variant = getenv("P3_FIND_BATCH") ? atoi(getenv("P3_FIND_BATCH")) : kSweepBatch;   // experiment knob
+        if (variant == 8) insert_find_kernel<false, false, 8><<<c->grid(2), 256, 0, c->stream>>>(keys, n, c->table(), c->d_stats, c->d_bidx, cap, bin_end, n_dev);
+        else if (variant == 2) insert_find_kernel<false, false, 2><<<c->grid(6), 256, 0, c->stream>>>(keys, n, c->table(), c->d_stats, c->d_bidx, cap, bin_end, n_dev);
+        else if (variant == 4) insert_find_kernel<false, false, 4><<<c->grid(4), 256, 0, c->stream>>>(keys, n, c->table(), c->d_stats, c->d_bidx, cap, bin_end, n_dev);
+        else insert_find_kernel<false, false><<<c->grid(8), 256, 0, c->stream>>>(keys, n, c->table(), c->d_stats, c->d_bidx, cap, bin_end, n_dev);
     } else {
-        if (cap) insert_find_kernel<false, false><<<c->grid(4), 256, 0, c->stream>>>(keys, n, c->table(), c->d_stats, c->d_bidx, cap, bin_end, n_dev);
-        else insert_find_kernel<false, true><<<c->grid(4), 256, 0, c->stream>>>(keys, n, c->table(), c->d_stats, c->d_bidx, cap, bin_end, n_dev);
+        insert_find_kernel<false, true><<<c->grid(8), 256, 0, c->stream>>>(keys, n, c->table(), c->d_stats, c->d_bidx, cap, bin_end, n_dev);
     }
     CU(cudaMemsetAsync(&c->d_stats->work, 0, sizeof(unsigned long long), c->stream));
     if (cap) insert_add_kernel<false><<<c->grid(8), 256, 0, c->stream>>>(c->d_bidx, keys, n, c->table(), c->ovf(), c->d_stats, cap, bin_end, n_dev);
@@ -1474,7 +1496,12 @@ static void count_binned_times(p3_ctx *c) {
 static int setup_table(p3_ctx *c, uint64_t table_slots) {
     uint32_t P = 1;
     if (c->binned) {
-        uint64_t want = (table_slots * 8 + (24ull << 20) - 1) / (24ull << 20);
+        // ~48 MB per partition: the insert sweep is insensitive to the partition size between 17 and 50 MB (measured), while
+        // every tile sort pays a scan + one global claim per partition and tile (scatter21: 33 / 42 / 53 / 72 ms at 350 / 520 /
+        // 696 / 1000 partitions)
+        uint64_t part_bytes = 48ull << 20;
+        if (const char *e = getenv("P3_PART_MB")) part_bytes = std::max<uint64_t>(strtoull(e, nullptr, 10), 1) << 20;
+        uint64_t want = (table_slots * 8 + part_bytes - 1) / part_bytes;
         if (const char *e = getenv("P3_PARTS")) want = strtoull(e, nullptr, 10);
         P = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(want, 1), kMaxParts);
     }
@@ -1756,7 +1783,7 @@ int p3_make_bf(p3_ctx *c, uint32_t k, uint64_t filter_size, uint32_t num_hashes,
     };
     rc = solid_pass();
     if (rc) return rc;
-    if (k <= 32 && solid_slots == 0) {
+    if (solid_slots == 0) {
         export_counts_kernel<<<c->grid(), 256, 0, c->stream>>>(c->d_table, c->nb * 4, c->ovf(), c->d_stats, cov_threshold, nullptr, nullptr, 0);
         c->launches++;
     }
@@ -1774,7 +1801,7 @@ int p3_make_bf(p3_ctx *c, uint32_t k, uint64_t filter_size, uint32_t num_hashes,
     }
 
     if (k > 32) {   // multi-word k-mers: p3_long.inc.cu
-        rc = make_bf_long(c, k, solid_slots);
+        rc = make_bf_long(c, k, solid_slots, (uint64_t)(1.25 * (double)c->h_stats.n_good21) + 1024);
         if (rc) return rc;
         CU(cudaEventElapsedTime(&c->ms_bloom, c->ev[14], c->ev[15]));
         CU(cudaEventElapsedTime(&c->ms[1], c->ev[2], c->ev[3]));

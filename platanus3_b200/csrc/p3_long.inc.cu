@@ -137,7 +137,7 @@ dedupe_long_kernel(Stream2 st, const uint32_t *__restrict__ solid, uint64_t n_wo
             const uint64_t val = (tag << 40) | p;
             uint64_t b = __umul64hi(fmix64(h0), nbs);
             bool done = false;
-            for (uint64_t probe = 0; probe < nbs && !done; probe++) {
+            for (uint64_t probe = 0; probe < nbs && probe < kMaxProbe && !done; probe++) {   // a full table fails fast
                 uint64_t *bp = set + 4 * b;
                 uint64_t sl[4];
                 ld_bucket(bp, sl);
@@ -316,7 +316,7 @@ static int bloom_add_words(p3_ctx *c, const uint64_t *d_words, uint64_t n) {
 }
 
 // stage B for k > 32; the coverage plane (good21) is ready, planes are allocated, filter allocated
-static int make_bf_long(p3_ctx *c, uint32_t k, uint64_t solid_slots) {
+static int make_bf_long(p3_ctx *c, uint32_t k, uint64_t solid_slots, uint64_t est_distinct) {
     if (c->total_bases >= kPos40) return fail(P3_ERR_ARG, "k > 32 supports up to 2^40 bases per context");
     LongK L = make_longk(k);
     Stream2 st; st.packed = c->d_packed; st.nmask = c->d_nmask;
@@ -324,7 +324,9 @@ static int make_bf_long(p3_ctx *c, uint32_t k, uint64_t solid_slots) {
     c->launches++;
     int rc = pull_stats(c);
     if (rc) return rc;
-    if (solid_slots == 0) solid_slots = std::max<uint64_t>(2 * std::min<uint64_t>(c->h_stats.n_adds, 1ull << 24), 1024);
+    // distinct solid k-mers: never more than the solid positions, normally about the distinct 21-mers that passed the
+    // coverage test (est_distinct); an underestimate fails fast (bounded probes) and the set grows
+    if (solid_slots == 0) solid_slots = std::max<uint64_t>(2 * std::min<uint64_t>(c->h_stats.n_adds, est_distinct), 1024);
     CU(cudaEventRecord(c->ev[4], c->stream));
     for (int attempt = 0;; attempt++) {
         uint64_t nbs = (solid_slots + 3) / 4;

@@ -341,7 +341,7 @@ int p3_mg_count_recv(p3_ctx *c, uint64_t ch) {
     unsigned char *blk = m.set_ptr(m.my_rank, set);
     const uint64_t n = (uint64_t)m.n_ranks * m.capA;
     const unsigned sblocks = (unsigned)std::min<uint64_t>((n + kTilePos - 1) / kTilePos, (uint64_t)c->n_sm * 3);
-    scatter_rec_kernel<0, 4><<<sblocks, kScatterThreads, kSmemPL, c->stream>>>(
+    scatter_rec_kernel<0, 4><<<sblocks, kScatterThreads, kSmemA4, c->stream>>>(
         reinterpret_cast<const uint64_t *>(blk), blk + n * 8, n, c->parts, c->d_cursor, c->d_bkeys, c->d_bword, m.part_cap, nullptr,
         m.capA, &m.ctl()->count[set][0], c->d_stats);
     c->launches++;
@@ -426,6 +426,8 @@ int p3_mg_cover_begin(p3_ctx *c, uint32_t cov_threshold, uint64_t owner_distinct
     m.n_slices = (uint32_t)std::min<uint64_t>(want_slices, c->parts);
     CU(ensure(m.d_sing, m.cap_sing, sizeof(uint64_t) * std::min<uint64_t>(worst / m.n_slices * 5 / 4 + (1u << 20), m.capB * m.n_ranks)));
     if (n_slices) *n_slices = m.n_slices;
+    rc = below_bits(c, cov_threshold);      // "count < threshold" of every owned slot as one bit: what the verdict sweep asks
+    if (rc) return rc;
     CU(cudaMemsetAsync(&c->d_stats->err_bin_overflow, 0, sizeof(unsigned), c->stream));
     CU(cudaEventRecord(c->ev[2], c->stream));
     return P3_OK;
@@ -451,7 +453,7 @@ int p3_mg_cover_send(p3_ctx *c, uint32_t cov_threshold, uint32_t slice) {
         const size_t smem = (size_t)kBinThreads * kPosKpt * 6 + 20;
         const uint64_t T = (uint64_t)kBinThreads * kPosKpt;
         unsigned blocks = (unsigned)std::min<uint64_t>((n_end - first + T - 1) / T, (uint64_t)c->n_sm * 4);
-        pos_bin_kernel<0, true><<<blocks, kBinThreads, smem, c->stream>>>(c->table(), c->d_bkeys, c->d_bword, c->d_bidx, n_end, m.part_cap, c->d_binmeta, nullptr,
+        pos_bin_kernel<0, true><<<blocks, kBinThreads, smem, c->stream>>>(c->table(), c->d_bkeys, c->d_bword, c->d_bidx, c->d_below, n_end, m.part_cap, c->d_binmeta, nullptr,
                                                                    cov_threshold, c->ovf(), c->d_stats, 27, 1, nullptr, m.cap_sing / sizeof(uint64_t), nullptr, m.d_sing);
         PeerOut64 po;
         for (uint32_t j = 0; j < (uint32_t)kMaxPeers; j++)
@@ -569,7 +571,7 @@ int p3_mg_solid_recv(p3_ctx *c, uint64_t ch) {
     unsigned char *blk = m.set_ptr(m.my_rank, set);
     const uint64_t n = (uint64_t)m.n_ranks * m.capK;
     const unsigned sblocks = (unsigned)std::min<uint64_t>((n + kTilePos - 1) / kTilePos, (uint64_t)c->n_sm * 3);
-    scatter_rec_kernel<4, 1><<<sblocks, kScatterThreads, kSmemPL, c->stream>>>(
+    scatter_rec_kernel<4, 1><<<sblocks, kScatterThreads, kSmemA1, c->stream>>>(
         reinterpret_cast<const uint64_t *>(blk), blk + n * 8, n, c->set_parts, c->d_cursor, c->d_bkeys, c->d_bword, m.kpart_cap, nullptr,
         m.capK, &m.ctl()->count[set][0], c->d_stats);
     c->launches++;
