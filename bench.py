@@ -17,7 +17,9 @@ with N (weak scaling: N x 100 Mbp at 50x; every rank parses 1/N of the reads = 5
   cpu_baseline / --impl reference
             the unmodified reference (oracle/_ref/libp3ref.so; oracle port when absent) on a
             bounded, scaled-down sample of the same workload on the host cores
-  --config 0 | 2 | 4   the other BASELINE.json configs as their own JSON lines (see the functions below)
+  --config 0 | 2 | 4   the other BASELINE.json configs as their own JSON lines (bench_configs.py)
+  --config 3           human scale (3.1 Gbp, 30x) on 8 GPUs, or its per-rank share (387.5 Mbp, 11.6 Gbp of reads per rank)
+                       on fewer: the multi-GPU path with the owner's insert in rounds (platanus3_b200/dist.py)
 """
 import argparse
 import ctypes
@@ -48,6 +50,7 @@ SEED = 1234
 ALGO_BYTES_PER_KMER = 0.25 + 8 + 8
 SAMPLE_GENOME = 200_000   # cpu_baseline / reference arm: same generator, 500x smaller genome
 VERIFY_GENOME = 400_000   # the instance checked against the oracle before timing
+CONFIG = 1                # BASELINE.json configs index of the N-GPU line (1 = headline; 3 = human scale, see use_config3)
 EXPECTED = os.path.join(ROOT, "tests", "golden", "expected_counts.json")
 TRAFFIC = os.path.join(ROOT, "profiles", "count_stage_traffic.json")
 
@@ -96,8 +99,24 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons, "samples": len(sm)}
 
 
+def use_config3():
+    """BASELINE.json configs[3]: human-scale 3.1 Gbp genome at 30x on 8 GPUs = 387.5 Mbp of genome and 11.6 Gbp of reads per
+    rank. With fewer ranks the per-rank share stays the same (weak scaling towards the 8-GPU point): every rank runs the
+    multi-GPU path at human-scale load (count table ~41 GB, owner bins re-used over several insert rounds)."""
+    global CONFIG, GENOME, COVERAGE
+    CONFIG, GENOME, COVERAGE = 3, 387_500_000, 30
+
+
 def workload_config(n_gpus, genome=None):
     genome = genome or GENOME * n_gpus
+    if CONFIG == 3:
+        what = ("configs[3]: human-scale synthetic %.2f Gbp genome, %dx reads of %d bp (%.1f Gbp of reads), %.0f%% substitution errors, k=%d, %d GPUs"
+                if n_gpus == 8 else
+                "configs[3] per-rank share on fewer GPUs: synthetic %.2f Gbp genome, %dx reads of %d bp (%.1f Gbp of reads), %.0f%% substitution errors, k=%d, "
+                "%d rank(s) x 11.6 Gbp of reads (the 8-GPU run is 3.1 Gbp)") % (genome / 1e9, COVERAGE, READ_LEN, genome * COVERAGE / 1e9, ERR * 100, K, n_gpus)
+        return {"workload": what, "k": K, "short_k": 21, "cov_threshold": 2, "read_len": READ_LEN, "genome_bp": genome, "coverage": COVERAGE,
+                "error_rate": ERR, "seed": SEED, "generator": "platanus3_b200/workload.py (hash-defined, identical on GPU / numpy / C)",
+                "l2": "inputs larger than L2 (2.9 GB read staging, ~41 GB count table per GPU)", "parallelism": "%d GPUs" % n_gpus}
     return {"workload": ("configs[1]: synthetic %d Mbp genome, %dx reads of %d bp, %.0f%% substitution errors, k=%d"
                          % (genome // 10 ** 6, COVERAGE, READ_LEN, ERR * 100, K)) if n_gpus == 1 else
                         ("configs[1] scaled weakly: synthetic %d Mbp genome, %dx reads of %d bp, %.0f%% substitution errors, k=%d, %d ranks x 5 Gbp of reads"
@@ -254,16 +273,20 @@ def verify_small_instance(world, rank, local, dev, stream, comm=None):
     ctx.attach(wl["packed"].data_ptr(), wl["total_bases"], wl["off"].data_ptr(), mine, None, keep=wl)
     # the small instance must take the code paths of the full-size run, not the small-input shortcuts
     forced = {"P3_DEDUPE_BINNED": "1", "P3_SET_PARTS": "5", "P3_BINNED_CLEARS": "1", "P3_BLOOM_BINNED": "1", "P3_BLOOM_SEG_BITS": str(1 << 20), "P3_PARTS": "24"}
+    if CONFIG == 3:     # human scale runs the insert in rounds and the Bloom adds in passes: so does its small instance
+        forced.update({"P3_MG_BIN_BUDGET": str(24_000_000 // world + 2_000_000), "P3_MG_BLOOM_BUDGET": "2000000"})
     saved = {kk: os.environ.get(kk) for kk in forced}
     os.environ.update({kk: v for kk, v in forced.items() if saved[kk] is None})
-    if world == 1:
+    if world == 1 and comm is None:
         ctx.count_short_kmers(int(len(okeys) / 0.5))
         n_adds, _ = ctx.make_bf(K, fs, nh, 2, 0)
         ctx.dbg_adjacency()
     else:
         st = pdist.run_hot_path([ctx], comm, K, fs, nh, int(len(okeys) / world / 0.5), owned_slots=int(len(osolid) / world / 0.4),
-                                chunk_words=1 << 16, device=dev)[0]
+                                chunk_words=(1 << 16) if CONFIG != 3 else max(1024, (1 << 16) // world), device=dev)[0]
         n_adds = st["n_adds"]
+        if CONFIG == 3:
+            assert st["insert_rounds"] > 1, "verify: the small instance did not run the insert in rounds"
     for kk, v in saved.items():
         if v is None:
             os.environ.pop(kk, None)
@@ -290,7 +313,7 @@ def verify_small_instance(world, rank, local, dev, stream, comm=None):
     if world > 1:
         totals = comm.all_sum(totals)
     assert totals == [len(okeys), int(ocounts.sum()), oadds, len(osolid)], ("verify: totals differ from the oracle", totals)
-    if world > 1:
+    if comm is not None:
         comm.barrier()
         comm.close_shared()
         comm.barrier()
@@ -321,6 +344,10 @@ def main_multi(args, rank, world, local, dev):
     from platanus3_b200 import _lib, workload, dist as pdist
     if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
         os.environ.pop("NCCL_DEBUG")   # NCCL prints its banner on stdout; stdout carries the one JSON line
+    if "MASTER_ADDR" not in os.environ:      # plain `python bench.py --config 3`: a world of one rank
+        import socket
+        s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK="0", WORLD_SIZE="1", LOCAL_RANK=str(local))
     dist.init_process_group("nccl", device_id=dev)
     comm = pdist.TorchDistComm()
     stream = torch.cuda.Stream()
@@ -335,6 +362,7 @@ def main_multi(args, rank, world, local, dev):
     n_reads = per if rank < world - 1 else n_total - first
     wl = workload.make_reads(genome, COVERAGE, READ_LEN, ERR, SEED, dev, first_read=first, n_reads=n_reads)
     torch.cuda.synchronize()
+    torch.cuda.empty_cache()        # the generator's temporaries (several GB) go back to the device
     total = wl["total_bases"]
     n_pos_local = n_reads * (READ_LEN - 20)
     all_bases, n_pos = comm.all_sum([total, n_pos_local])
@@ -346,8 +374,11 @@ def main_multi(args, rank, world, local, dev):
     ctx = _lib.Context(local, ctypes.c_void_p(stream.cuda_stream))
     ctx.attach(wl["packed"].data_ptr(), total, wl["off"].data_ptr(), n_reads, None, keep=wl)
 
+    # human scale: owner bins for a quarter of the records at a time, shard buffers for an eighth of the bit indices
+    budgets = dict(bin_budget_bytes=45e9, bloom_budget_bytes=8e9) if CONFIG == 3 else {}
+
     def step():
-        return pdist.run_hot_path([ctx], comm, K, fs, nh, table_slots, 0, owned_slots, chunk_words, dev)[0]
+        return pdist.run_hot_path([ctx], comm, K, fs, nh, table_slots, 0, owned_slots, chunk_words, dev, **budgets)[0]
 
     def timed(fn, steps):
         dist.barrier(); torch.cuda.synchronize()
@@ -399,7 +430,7 @@ def main_multi(args, rank, world, local, dev):
 
         def step_e2e():
             _lib.check(L.p3_reads_upload(ctx.h, h_packed.data_ptr(), total, h_off.data_ptr(), n_reads, None))
-            pdist.run_hot_path([ctx], comm, K, fs, nh, table_slots, 0, owned_slots, chunk_words, dev)
+            pdist.run_hot_path([ctx], comm, K, fs, nh, table_slots, 0, owned_slots, chunk_words, dev, **budgets)
             ptr, nwords = ctypes.c_void_p(), ctypes.c_uint64()
             _lib.check(L.p3_mg_filter(ctx.h, ctypes.byref(ptr), ctypes.byref(nwords)))
             if fb > fa:
@@ -427,6 +458,7 @@ def main_multi(args, rank, world, local, dev):
                               ) if st.get("exchange") == "peer" else (
                               "%d GPUs: k-mers hash-partitioned by owner; the same regions staged locally and moved by NCCL all_to_all_single" % world)
         cfg["chunk_words"], cfg["receive_set_bytes"] = chunk_words, st["set_bytes"]
+        cfg["insert_rounds"], cfg["bloom_passes"] = st.get("insert_rounds"), st.get("bloom_passes")
         print(json.dumps({
             "metric": METRIC, "value": n_pos / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -583,7 +615,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--config", type=int, default=1, help="BASELINE.json configs index: 1 (default, the headline), 0, 2 or 4")
+    ap.add_argument("--config", type=int, default=1, help="BASELINE.json configs index: 1 (default, the headline), 0, 2, 3 or 4")
     ap.add_argument("--genome", type=int, default=GENOME, help="override genome size (debug only; invalidates the metric)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling only: skip the host-buffer leg (e2e is then null)")
@@ -600,6 +632,12 @@ def main():
         import torch
         torch.cuda.set_device(local)
         dev = torch.device("cuda", local)
+        if args.config == 3:    # human scale: the multi-GPU path at 11.6 Gbp of reads per rank, whatever the number of ranks
+            use_config3()
+            if args.genome == 100_000_000:
+                args.genome = GENOME
+            args.no_e2e = args.no_e2e or os.environ.get("P3_BENCH_E2E") != "1"   # 8 GB of pinned result buffers per rank: on request only
+            return main_multi(args, rank, world, local, dev)
         if args.config != 1:
             import bench_configs
             return bench_configs.run(args, rank, world, local, dev)

@@ -188,7 +188,7 @@ int p3_mg_arena(p3_ctx *ctx, uint32_t n_ranks, uint32_t my_rank, uint64_t set_by
 int p3_mg_connect(p3_ctx *ctx, const uint64_t *arena_ptrs, int same_stream);
 /* device-side barrier over the peers' control blocks (a one-block kernel on the context's stream; no host wait) */
 int p3_mg_sync(p3_ctx *ctx);
-/* transport 1: the blocks and counts the caller's all-to-all moves for a stage (0 = A, 1 = B1, 2 = B2), see p3_multi.inc.cu */
+/* transport 1: the blocks and counts the caller's all-to-all moves for a stage (0 = A, 1 = B1, 2 = B2, 3 = B2 with multi-word k-mers), see p3_multi.inc.cu */
 int p3_mg_staged_buffers(p3_ctx *ctx, int stage, int set, uint64_t out[8]);
 /* A: ReadFile::CountShortKmer, reference src/Load.cpp:105-127, over all ranks' reads. table_slots: this rank's table;
  * owner_positions: upper estimate of the 21-mer positions this rank will own; chunk_words / n_chunks: the same on every rank */
@@ -197,6 +197,16 @@ int p3_mg_count_send(p3_ctx *ctx, uint64_t chunk);
 int p3_mg_count_recv(p3_ctx *ctx, uint64_t chunk);
 int p3_mg_count_finish(p3_ctx *ctx);
 int p3_mg_count_end(p3_ctx *ctx);   /* then p3_short_kmer_stats / _export / _lookup answer for the OWNED keys */
+/* Human-scale inputs (BASELINE.json configs[3]): an owner cannot keep every received record (16 B each) until one insert
+ * sweep. The count then runs in ROUNDS of chunks: p3_mg_count_finish after the last chunk of every round and
+ * p3_mg_count_next_round between two rounds (the bins start empty again; owner_positions of p3_mg_count_begin is then the
+ * estimate for ONE round). The verdict stage sends and sorts each round's chunks again between p3_mg_cover_rebin_begin /
+ * _end (p3_mg_count_send / _recv), followed by that round's slices; the solid stage de-duplicates per round
+ * (p3_mg_solid_next_round between two rounds). Results are identical to the one-round schedule. */
+int p3_mg_count_next_round(p3_ctx *ctx);
+int p3_mg_cover_rebin_begin(p3_ctx *ctx);
+int p3_mg_cover_rebin_end(p3_ctx *ctx);
+int p3_mg_solid_next_round(p3_ctx *ctx);
 /* B1: MakeBF's coverage test, reference src/MakeBloomFilter.cpp:52-58: owners return the positions of keys whose count
  * stayed below cov_threshold, in *n_slices rounds (owner_distinct: the largest n_distinct of any rank) */
 int p3_mg_cover_begin(p3_ctx *ctx, uint32_t cov_threshold, uint64_t owner_distinct, uint32_t *n_slices);
@@ -209,6 +219,19 @@ int p3_mg_solid_send(p3_ctx *ctx, uint64_t chunk);
 int p3_mg_solid_recv(p3_ctx *ctx, uint64_t chunk);
 int p3_mg_solid_finish(p3_ctx *ctx);
 int p3_mg_solid_end(p3_ctx *ctx, uint64_t filter_size, uint32_t num_hashes, uint64_t filter_words_cap, uint64_t *n_adds, uint64_t *n_owned);
+/* B2 for multi-word k-mers (33 <= k <= 3001; the reference's std::bitset<2k> k-mers, src/Assemble.cpp:30-53): instead of
+ * p3_mg_solid_begin .. _finish. p3_mg_long_solid builds the local solid plane and seeds and returns this rank's solid
+ * occurrences; p3_mg_long_begin sizes the owner's store of received W-word records (owner_occurrences), its set
+ * (owned_slots) and the chunking of the sends (occ_per_word: upper estimate of solid occurrences per packed word on any
+ * rank, max_words: the largest n_words of any rank; *chunk_words / *n_chunks are the same on every rank); per chunk
+ * p3_mg_long_send, sync (stage 3 for transport 1), p3_mg_long_recv; p3_mg_long_finish de-duplicates the store and leaves
+ * the owned distinct k-mers as the context's n x W word list; then p3_mg_solid_end and B3 / C as for k <= 32. */
+int p3_mg_long_solid(p3_ctx *ctx, uint32_t k, uint64_t *n_adds);
+int p3_mg_long_begin(p3_ctx *ctx, uint64_t owned_slots, uint64_t owner_occurrences, double occ_per_word, uint64_t max_words,
+                     uint64_t *chunk_words, uint64_t *n_chunks);
+int p3_mg_long_send(p3_ctx *ctx, uint64_t chunk);
+int p3_mg_long_recv(p3_ctx *ctx, uint64_t chunk);
+int p3_mg_long_finish(p3_ctx *ctx);
 /* B3: sharded BF.add (reference src/bloomfilter.cpp:69-74): the filter is cut into segments of p3_bloom_seg_bits() bits,
  * dealt out to the ranks in contiguous shards. p3_mg_bloom_bin computes every owned k-mer's num_hashes bit indices once,
  * sorts them by segment and stores segment s's 4-byte in-segment offsets to h_segbase[s] (device addresses, normally
@@ -218,6 +241,8 @@ int p3_mg_solid_end(p3_ctx *ctx, uint64_t filter_size, uint32_t num_hashes, uint
 uint64_t p3_bloom_seg_bits(void);
 int p3_mg_bloom_buffer(p3_ctx *ctx, uint64_t n_u32, uint32_t **d_buf);
 int p3_mg_bloom_bin(p3_ctx *ctx, uint32_t n_seg, const uint64_t *h_segbase, uint64_t cap, uint64_t *h_counts);
+/* the same for k-mers [first, first + count) of the owned list: one PASS at a time through smaller shard buffers */
+int p3_mg_bloom_bin_range(p3_ctx *ctx, uint32_t n_seg, const uint64_t *h_segbase, uint64_t cap, uint64_t *h_counts, uint64_t first, uint64_t count);
 int p3_mg_bloom_apply(p3_ctx *ctx, uint64_t seg_first, uint32_t n_local, uint32_t n_src, const uint64_t *h_ptr, const uint64_t *h_n);
 int p3_mg_bloom_direct(p3_ctx *ctx);
 int p3_mg_filter(p3_ctx *ctx, uint32_t **d_bits, uint64_t *n_words);

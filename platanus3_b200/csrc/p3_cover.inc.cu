@@ -105,6 +105,7 @@ static int build_node_table(p3_ctx *c, const uint64_t *h_kmers, uint64_t n, uint
     uint64_t cap = 16;
     while (cap < 2 * n + 16) cap <<= 1;
     uint64_t *dk = nullptr;
+    TmpFree tmp; tmp.own(&dk);
     CU(cudaMalloc(d_keys, sizeof(uint64_t) * cap));
     CU(cudaMalloc(d_idx, sizeof(uint32_t) * cap));
     CU(cudaMalloc(&dk, sizeof(uint64_t) * n));
@@ -114,7 +115,6 @@ static int build_node_table(p3_ctx *c, const uint64_t *h_kmers, uint64_t n, uint
     c->launches++;
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(c->stream));
-    cudaFree(dk);
     *mask = cap - 1;
     return P3_OK;
 }
@@ -125,9 +125,10 @@ extern "C" int p3_node_coverage(p3_ctx *c, uint32_t k, const uint64_t *h_junctio
     if (k < P3_MIN_K || k > P3_MAX_K_WALK) return fail(P3_ERR_ARG, "p3_node_coverage: k outside [21,32]");
     CU(cudaSetDevice(c->device));
     uint64_t *jk = nullptr, *tk = nullptr; uint32_t *ji = nullptr, *ti = nullptr; uint64_t jm = 0, tm = 0; int jo = -1, to = -1;
+    int *djc = nullptr, *dtc = nullptr;
+    TmpFree tmp; tmp.own(&jk); tmp.own(&ji); tmp.own(&tk); tmp.own(&ti); tmp.own(&djc); tmp.own(&dtc);
     int rc = build_node_table(c, h_junctions, nj, &jk, &ji, &jm, &jo);
     if (!rc) rc = build_node_table(c, h_joints, nt, &tk, &ti, &tm, &to);
-    int *djc = nullptr, *dtc = nullptr;
     if (!rc) {
         CU(cudaMalloc(&djc, sizeof(int) * std::max<uint64_t>(9 * nj, 1)));
         CU(cudaMalloc(&dtc, sizeof(int) * std::max<uint64_t>(nt, 1)));
@@ -144,6 +145,5 @@ extern "C" int p3_node_coverage(p3_ctx *c, uint32_t k, const uint64_t *h_junctio
         if (nt) CU(cudaMemcpyAsync(h_tcov, dtc, sizeof(int) * nt, cudaMemcpyDeviceToHost, c->stream));
         CU(cudaStreamSynchronize(c->stream));
     }
-    cudaFree(jk); cudaFree(ji); cudaFree(tk); cudaFree(ti); cudaFree(djc); cudaFree(dtc);
     return rc;
 }

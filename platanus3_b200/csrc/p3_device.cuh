@@ -36,6 +36,7 @@ struct Stats {
     unsigned int err_kbin_overflow;       // same deferred check for the k-mer bins of the binned de-duplication
     unsigned int err_peer_timeout;        // a multi-GPU device-side barrier gave up waiting for a peer
     unsigned int pad;
+    unsigned long long owned_pos;         // multi-GPU owner: records inserted in the rounds before the current one
 };
 
 struct FastMod {  // x % d for a run-time invariant d (filter_size), reference bloomfilter.cpp:65

@@ -1067,9 +1067,11 @@ struct p3_ctx {
     uint64_t n_chunks = 0, binned_pos = 0; bool pos_on_host = false;
     Table table() const {
         Table t; t.slots = d_table; t.nbp = nbp; t.P = parts;
+        // slot:sb | offset-in-word:5 | rank:4 in the 32-bit index stream. (1 << sb) is strictly larger than the slots of a
+        // partition, so the all-ones word (kNoSlot) is never a valid record even when all 32 bits are in use (48 MB partitions: sb = 23)
         uint32_t sb = 1;
-        while ((1ull << sb) < nbp * 4) sb++;
-        t.sb = sb + 9 <= 31 ? sb : 0;
+        while ((1ull << sb) <= nbp * 4) sb++;
+        t.sb = sb + 9 <= 32 ? sb : 0;
         return t;
     }
     uint64_t *d_ovf_keys = nullptr; unsigned long long *d_ovf_wraps = nullptr;
@@ -1127,6 +1129,12 @@ static int adjacency_long(struct p3_ctx *c, const uint64_t *d_words, uint64_t n,
 static const uint64_t *long_words(struct p3_ctx *c);
 static int long_batch(struct p3_ctx *c, int op, uint32_t k, const uint64_t *h_kmers, uint64_t n, void *h_out);
 template <typename T> static void dfree(T *&p) { if (p) { cudaFree((void *)p); p = nullptr; } }
+// device temporaries of the batch entry points: released on EVERY return path (CU() returns early on an error)
+struct TmpFree {
+    void **slot[6]; int n = 0;
+    template <typename T> void own(T **pp) { slot[n++] = reinterpret_cast<void **>(pp); }
+    ~TmpFree() { for (int i = 0; i < n; i++) if (*slot[i]) { cudaFree(*slot[i]); *slot[i] = nullptr; } }
+};
 // grow-only device buffer: reallocates only when the request exceeds the capacity, so repeated
 // runs on same-sized inputs never touch cudaMalloc/cudaFree (both synchronise the device)
 template <typename T> static cudaError_t ensure(T *&p, uint64_t &cap_bytes, uint64_t need_bytes) {
@@ -1578,6 +1586,7 @@ int p3_short_kmer_export(p3_ctx *c, uint64_t *h_keys, uint64_t *h_counts, uint64
     if (cap < nd) return fail(P3_ERR_ARG, "p3_short_kmer_export: capacity too small");
     if (nd == 0) return P3_OK;
     uint64_t *dk = nullptr, *dc = nullptr;
+    TmpFree tmp; tmp.own(&dk); tmp.own(&dc);
     CU(cudaMalloc(&dk, sizeof(uint64_t) * nd));
     CU(cudaMalloc(&dc, sizeof(uint64_t) * nd));
     CU(cudaMemsetAsync(&c->d_stats->n_export, 0, sizeof(unsigned long long), c->stream));
@@ -1586,7 +1595,6 @@ int p3_short_kmer_export(p3_ctx *c, uint64_t *h_keys, uint64_t *h_counts, uint64
     CU(cudaMemcpyAsync(h_keys, dk, sizeof(uint64_t) * nd, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaMemcpyAsync(h_counts, dc, sizeof(uint64_t) * nd, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    cudaFree(dk); cudaFree(dc);
     return P3_OK;
 }
 
@@ -1595,6 +1603,7 @@ int p3_short_kmer_lookup(p3_ctx *c, const uint64_t *h_keys, uint64_t n, uint64_t
     if (n == 0) return P3_OK;
     CU(cudaSetDevice(c->device));
     uint64_t *dk = nullptr, *dc = nullptr;
+    TmpFree tmp; tmp.own(&dk); tmp.own(&dc);
     CU(cudaMalloc(&dk, sizeof(uint64_t) * n));
     CU(cudaMalloc(&dc, sizeof(uint64_t) * n));
     CU(cudaMemcpyAsync(dk, h_keys, sizeof(uint64_t) * n, cudaMemcpyHostToDevice, c->stream));
@@ -1602,7 +1611,6 @@ int p3_short_kmer_lookup(p3_ctx *c, const uint64_t *h_keys, uint64_t n, uint64_t
     c->launches++;
     CU(cudaMemcpyAsync(h_counts, dc, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    cudaFree(dk); cudaFree(dc);
     return P3_OK;
 }
 
@@ -1901,12 +1909,12 @@ int p3_bf_add(p3_ctx *c, const uint64_t *h_kmers, uint64_t n) {
     if (c->k > 32) return long_batch(c, 0, c->k, h_kmers, n, nullptr);
     CU(cudaSetDevice(c->device));
     uint64_t *dk = nullptr;
+    TmpFree tmp; tmp.own(&dk);
     int rc = with_kmers(c, h_kmers, n, &dk);
     if (rc) return rc;
     bf_add_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->bloom(), dk, n);
     c->launches++;
     CU(cudaStreamSynchronize(c->stream));
-    cudaFree(dk);
     return P3_OK;
 }
 
@@ -1916,6 +1924,7 @@ int p3_bf_possibly_contains(p3_ctx *c, const uint64_t *h_kmers, uint64_t n, uint
     if (c->k > 32) return long_batch(c, 1, c->k, h_kmers, n, h_out);
     CU(cudaSetDevice(c->device));
     uint64_t *dk = nullptr; uint8_t *dout = nullptr;
+    TmpFree tmp; tmp.own(&dk); tmp.own(&dout);
     int rc = with_kmers(c, h_kmers, n, &dk);
     if (rc) return rc;
     CU(cudaMalloc(&dout, n));
@@ -1923,7 +1932,6 @@ int p3_bf_possibly_contains(p3_ctx *c, const uint64_t *h_kmers, uint64_t n, uint
     c->launches++;
     CU(cudaMemcpyAsync(h_out, dout, n, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    cudaFree(dk); cudaFree(dout);
     return P3_OK;
 }
 
@@ -1934,6 +1942,7 @@ int p3_double_hash(p3_ctx *c, uint32_t k, const uint64_t *h_kmers, uint64_t n, u
     if (k > 32) return long_batch(c, 2, k, h_kmers, n, h_out);
     CU(cudaSetDevice(c->device));
     uint64_t *dk = nullptr, *dout = nullptr;
+    TmpFree tmp; tmp.own(&dk); tmp.own(&dout);
     int rc = with_kmers(c, h_kmers, n, &dk);
     if (rc) return rc;
     CU(cudaMalloc(&dout, sizeof(uint64_t) * 2 * n));
@@ -1941,7 +1950,6 @@ int p3_double_hash(p3_ctx *c, uint32_t k, const uint64_t *h_kmers, uint64_t n, u
     c->launches++;
     CU(cudaMemcpyAsync(h_out, dout, sizeof(uint64_t) * 2 * n, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    cudaFree(dk); cudaFree(dout);
     return P3_OK;
 }
 
@@ -2008,12 +2016,12 @@ int p3_dbg_close(p3_ctx *c, const uint64_t *h_roots, uint64_t n_roots, uint64_t 
     uint64_t hi = c->n_closed;
     if (h_roots && n_roots) {
         uint64_t *dr = nullptr;
+        TmpFree tmp; tmp.own(&dr);
         CU(cudaMalloc(&dr, sizeof(uint64_t) * n_roots));
         CU(cudaMemcpyAsync(dr, h_roots, sizeof(uint64_t) * n_roots, cudaMemcpyHostToDevice, c->stream));
         roots_kernel<<<(unsigned)((n_roots + 255) / 256), 256, 0, c->stream>>>(dr, n_roots, (int)c->k, c->kset(), c->d_list, c->list_cap, c->d_stats);
         c->launches++;
         int rc = pull_stats(c);
-        cudaFree(dr);
         if (rc) return rc;
         uint64_t n1 = c->h_stats.n_distinct_solid;
         if ((rc = check_full(n1))) return rc;
@@ -2069,6 +2077,7 @@ int p3_check_directions(p3_ctx *c, const uint64_t *h_kmers, uint64_t n, uint8_t 
     if (c->k > 32) return long_batch(c, 3, c->k, h_kmers, n, h_mask);
     CU(cudaSetDevice(c->device));
     uint64_t *dk = nullptr; uint8_t *dout = nullptr;
+    TmpFree tmp; tmp.own(&dk); tmp.own(&dout);
     int rc = with_kmers(c, h_kmers, n, &dk);
     if (rc) return rc;
     CU(cudaMalloc(&dout, n));
@@ -2078,7 +2087,6 @@ int p3_check_directions(p3_ctx *c, const uint64_t *h_kmers, uint64_t n, uint8_t 
     c->launches++;
     CU(cudaMemcpyAsync(h_mask, dout, n, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    cudaFree(dk); cudaFree(dout);
     return P3_OK;
 }
 

@@ -398,6 +398,7 @@ static int long_batch(p3_ctx *c, int op, uint32_t k, const uint64_t *h_kmers, ui
     CU(cudaSetDevice(c->device));
     LongK L = make_longk(k);
     uint64_t *dk = nullptr; void *dout = nullptr;
+    TmpFree tmp; tmp.own(&dk); tmp.own(&dout);
     CU(cudaMalloc(&dk, sizeof(uint64_t) * n * L.W));
     CU(cudaMemcpyAsync(dk, h_kmers, sizeof(uint64_t) * n * L.W, cudaMemcpyHostToDevice, c->stream));
     const unsigned nblk = (unsigned)((n + 255) / 256);
@@ -419,6 +420,5 @@ static int long_batch(p3_ctx *c, int op, uint32_t k, const uint64_t *h_kmers, ui
     CU(cudaGetLastError());
     if (out_bytes) CU(cudaMemcpyAsync(h_out, dout, out_bytes, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    cudaFree(dk); if (dout) cudaFree(dout);
     return P3_OK;
 }

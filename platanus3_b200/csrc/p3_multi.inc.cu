@@ -55,6 +55,14 @@ __global__ void stage_counts_kernel(unsigned long long *dst, const unsigned long
     if (j < n) dst[j] = sent[j];
 }
 
+// records in the fixed-capacity bins (sum over the partitions), added to st->owned_pos: the owner's position
+// total when the insert runs in several rounds over re-used bins
+__global__ void accum_cursors_kernel(const unsigned long long *__restrict__ cursor, uint32_t P, uint64_t cap, Stats *st) {
+    unsigned long long mine = 0;
+    for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) mine += min(cursor[i] - (unsigned long long)i * cap, (unsigned long long)cap);
+    if (mine) atomicAdd(&st->owned_pos, mine);     // one block, at most 256 adds
+}
+
 // tile sort of a position list by source rank (the top byte) into the ranks' regions
 __global__ void __launch_bounds__(kScatterThreads, 3)
 scatter_pos_peer_kernel(const uint64_t *__restrict__ in, uint64_t n, const unsigned long long *__restrict__ n_dev, uint32_t P,
@@ -121,6 +129,7 @@ struct MgState {   // per-context state of the multi-GPU path
     unsigned long long *d_sent = nullptr;                               // [kMaxParts + 1] per-destination cursors of the current send
     // A
     uint64_t chunk_words = 0, n_chunks = 0, capA = 0, part_cap = 0;
+    bool multi_round = false;    // the owner inserted in several rounds: the bins hold the last round only (human-scale inputs)
     // B1
     uint64_t *d_sing = nullptr; uint64_t cap_sing = 0; uint64_t capB = 0; uint32_t n_slices = 0;
     // B2
@@ -130,6 +139,21 @@ struct MgState {   // per-context state of the multi-GPU path
     PeerCtl *ctl() const { return reinterpret_cast<PeerCtl *>(arena); }
 };
 static CtxStates<MgState> g_mg;
+// multi-word k-mers (see the end of this file)
+struct LongMg {
+    uint64_t *d_store = nullptr; uint64_t cap_store = 0;    // bytes
+    unsigned long long *d_store_n = nullptr;                // records in the store (device)
+    uint64_t store_records = 0;                             // capacity in records
+    uint64_t chunk_words = 0, capL = 0; int W = 0;
+};
+static CtxStates<LongMg> g_longmg;
+static void longmg_release(p3_ctx *c) {
+    LongMg *l = g_longmg.find(c);
+    if (!l) return;
+    dfree(l->d_store); dfree(l->d_store_n);
+    g_longmg.erase(c);
+}
+
 
 static void mg_release(p3_ctx *c) {
     MgState *mp = g_mg.find(c);
@@ -138,6 +162,7 @@ static void mg_release(p3_ctx *c) {
     dfree(m.arena); dfree(m.staging); dfree(m.d_stage_cnt); dfree(m.d_sent); dfree(m.d_sing);
     for (void *p : m.graveyard) cudaFree(p);
     g_mg.erase(c);
+    longmg_release(c);
 }
 static int mg_ready(p3_ctx *c, MgState **out, const char *who) {
     if (!c) return fail(P3_ERR_ARG, "null ctx");
@@ -246,7 +271,7 @@ int p3_mg_sync(p3_ctx *c) {
     return P3_OK;
 }
 // staged transport: what the caller's all-to-all has to move for receive set `set` of a stage (0 = A count records,
-// 1 = B1 positions, 2 = B2 k-mers). out[0..2] = send block, receive block, bytes per rank of the 8-byte records;
+// 1 = B1 positions, 2 = B2 k-mers, 3 = B2 multi-word k-mers). out[0..2] = send block, receive block, bytes per rank of the 8-byte records;
 // out[3..5] the same for the auxiliary block (bytes per rank 0 = none); out[6..7] = send / receive counts (n_ranks uint64 each).
 int p3_mg_staged_buffers(p3_ctx *c, int stage, int set, uint64_t out[8]) {
     MgState *m;
@@ -254,7 +279,12 @@ int p3_mg_staged_buffers(p3_ctx *c, int stage, int set, uint64_t out[8]) {
     if (rc) return rc;
     if (m->transport != 1 || set < 0 || set > 1 || !out) return fail(P3_ERR_ARG, "p3_mg_staged_buffers: staged transport only");
     const uint64_t auxb = stage == 0 ? 4 : stage == 2 ? 1 : 0;
-    const uint64_t cap = stage == 0 ? m->capA : stage == 1 ? m->capB : m->capK;
+    uint64_t cap = stage == 0 ? m->capA : stage == 1 ? m->capB : m->capK;
+    if (stage == 3) {    // multi-word k-mer records: W words each, counted here in 8-byte units
+        LongMg *lm = g_longmg.find(c);
+        if (!lm || !lm->W) return fail(P3_ERR_STATE, "p3_mg_staged_buffers: run p3_mg_long_begin first");
+        cap = lm->capL * (uint64_t)lm->W;
+    }
     unsigned char *recv = m->set_ptr(m->my_rank, set);
     out[0] = (uint64_t)(uintptr_t)m->staging; out[1] = (uint64_t)(uintptr_t)recv; out[2] = cap * 8;
     out[3] = (uint64_t)(uintptr_t)(m->staging + (uint64_t)m->n_ranks * cap * 8); out[4] = (uint64_t)(uintptr_t)(recv + (uint64_t)m->n_ranks * cap * 8); out[5] = cap * auxb;
@@ -300,6 +330,7 @@ int p3_mg_count_begin(p3_ctx *c, uint64_t table_slots, uint64_t owner_positions,
     c->launches++;
     CU(cudaEventRecord(c->ev[0], c->stream));
     c->bins_valid = false; c->have_counts = false; c->pos_on_host = true; c->binned_pos = 0; c->n_chunks = 0;
+    m.multi_round = false;
     return P3_OK;
 }
 // bin chunk `ch` of this rank's reads by owner, straight into the owners' receive set ch % 2 (peer stores)
@@ -366,6 +397,22 @@ int p3_mg_count_finish(p3_ctx *c) {
     CU(cudaEventRecord(c->ev[1], c->stream));
     return P3_OK;
 }
+// Human-scale inputs: the owner cannot hold every received record until one insert sweep (16 B per record). The
+// count then runs in ROUNDS of chunks — p3_mg_count_finish after the last chunk of every round, this call between two
+// rounds: the inserted records are forgotten (only their total is kept) and the bins start empty again. The table pays
+// one pass through L2 per round; the verdict stage re-bins the reads round by round (p3_mg_cover_rebin_*).
+int p3_mg_count_next_round(p3_ctx *c) {
+    MgState *mp;
+    int rc = mg_ready(c, &mp, "p3_mg_count_next_round");
+    if (rc) return rc;
+    MgState &m = *mp;
+    accum_cursors_kernel<<<1, 256, 0, c->stream>>>(c->d_cursor, c->parts, m.part_cap, c->d_stats);
+    init_cursors_kernel<<<1, 256, 0, c->stream>>>(c->d_cursor, c->parts, m.part_cap);
+    c->launches += 2;
+    CU(cudaGetLastError());
+    m.multi_round = true;
+    return P3_OK;
+}
 // waits for the stage and checks it; the counts of the owned keys are final afterwards
 int p3_mg_count_end(p3_ctx *c) {
     MgState *mp;
@@ -379,13 +426,13 @@ int p3_mg_count_end(p3_ctx *c) {
     if (c->h_stats.err_bin_overflow) return fail(P3_ERR_TABLE_FULL, "multi-GPU count: a receive region or partition bin overflowed (skewed keys: raise set_bytes / owner_positions)");
     if (c->h_stats.err_table_full) return fail(P3_ERR_TABLE_FULL, "21-mer count table full: raise table_slots");
     if (c->h_stats.err_ovf_full) return fail(P3_ERR_TABLE_FULL, "count overflow side table full");
-    c->binned_pos = 0;
+    c->binned_pos = c->h_stats.owned_pos;     // earlier rounds (p3_mg_count_next_round)
     for (uint32_t p = 0; p < c->parts; p++) c->binned_pos += ends[p] - (unsigned long long)p * mp->part_cap;
     c->h_stats.n_pos21 = c->binned_pos;
     CU(cudaEventElapsedTime(&c->ms[0], c->ev[0], c->ev[1]));
     CU(cudaEventElapsedTime(&c->ms_sub[2], c->ev[10], c->ev[1]));
     c->ms_sub[0] = 0; c->ms_sub[1] = c->ms[0] - c->ms_sub[2];
-    c->bins_valid = true;
+    c->bins_valid = !mp->multi_round;   // several rounds: the verdict stage bins the records again, round by round
     c->have_counts = true;
     c->have_bf = c->have_solid = c->have_adj = false;
     return P3_OK;
@@ -411,7 +458,7 @@ int p3_mg_cover_begin(p3_ctx *c, uint32_t cov_threshold, uint64_t owner_distinct
     int rc = mg_ready(c, &mp, "p3_mg_cover_begin");
     if (rc) return rc;
     MgState &m = *mp;
-    if (!c->have_counts || !c->bins_valid) return fail(P3_ERR_STATE, "p3_mg_cover_begin: run the count stage first");
+    if (!c->have_counts || (!c->bins_valid && !m.multi_round)) return fail(P3_ERR_STATE, "p3_mg_cover_begin: run the count stage first");
     rc = ensure_planes(c);
     if (rc) return rc;
     CU(cudaMemcpyAsync(c->d_good21, c->d_valid, sizeof(uint32_t) * c->n_words, cudaMemcpyDeviceToDevice, c->stream));
@@ -426,10 +473,36 @@ int p3_mg_cover_begin(p3_ctx *c, uint32_t cov_threshold, uint64_t owner_distinct
     m.n_slices = (uint32_t)std::min<uint64_t>(want_slices, c->parts);
     CU(ensure(m.d_sing, m.cap_sing, sizeof(uint64_t) * std::min<uint64_t>(worst / m.n_slices * 5 / 4 + (1u << 20), m.capB * m.n_ranks)));
     if (n_slices) *n_slices = m.n_slices;
-    rc = below_bits(c, cov_threshold);      // "count < threshold" of every owned slot as one bit: what the verdict sweep asks
-    if (rc) return rc;
+    if (c->bins_valid) {
+        rc = below_bits(c, cov_threshold);      // "count < threshold" of every owned slot as one bit: what the verdict sweep asks
+        if (rc) return rc;
+    }
     CU(cudaMemsetAsync(&c->d_stats->err_bin_overflow, 0, sizeof(unsigned), c->stream));
     CU(cudaEventRecord(c->ev[2], c->stream));
+    return P3_OK;
+}
+// Several insert rounds (p3_mg_count_next_round): the bins no longer hold the records, so every round of chunks is sent
+// and sorted into the bins AGAIN (p3_mg_count_send / _recv between these two calls), and the round's verdict slices
+// (p3_mg_cover_send / _recv) look the keys up in the finished table instead of following the insert's index stream.
+int p3_mg_cover_rebin_begin(p3_ctx *c) {
+    MgState *mp;
+    int rc = mg_ready(c, &mp, "p3_mg_cover_rebin_begin");
+    if (rc) return rc;
+    if (!c->have_counts || !mp->multi_round) return fail(P3_ERR_STATE, "p3_mg_cover_rebin_begin: only after a count in several rounds");
+    init_cursors_kernel<<<1, 256, 0, c->stream>>>(c->d_cursor, c->parts, mp->part_cap);
+    c->launches++;
+    CU(cudaGetLastError());
+    return P3_OK;
+}
+int p3_mg_cover_rebin_end(p3_ctx *c) {
+    MgState *mp;
+    int rc = mg_ready(c, &mp, "p3_mg_cover_rebin_end");
+    if (rc) return rc;
+    if (!c->have_counts || !mp->multi_round) return fail(P3_ERR_STATE, "p3_mg_cover_rebin_end: only after a count in several rounds");
+    check_cursors_kernel<<<1, 256, 0, c->stream>>>(c->d_cursor, c->parts, mp->part_cap, c->d_stats);
+    CU(cudaMemcpyAsync(c->d_binmeta, c->d_cursor, sizeof(unsigned long long) * c->parts, cudaMemcpyDeviceToDevice, c->stream));
+    c->launches++;
+    CU(cudaGetLastError());
     return P3_OK;
 }
 // owner side, round `slice`: sweep the bins of its share of the table partitions; the positions of keys whose
@@ -453,8 +526,12 @@ int p3_mg_cover_send(p3_ctx *c, uint32_t cov_threshold, uint32_t slice) {
         const size_t smem = (size_t)kBinThreads * kPosKpt * 6 + 20;
         const uint64_t T = (uint64_t)kBinThreads * kPosKpt;
         unsigned blocks = (unsigned)std::min<uint64_t>((n_end - first + T - 1) / T, (uint64_t)c->n_sm * 4);
-        pos_bin_kernel<0, true><<<blocks, kBinThreads, smem, c->stream>>>(c->table(), c->d_bkeys, c->d_bword, c->d_bidx, c->d_below, n_end, m.part_cap, c->d_binmeta, nullptr,
-                                                                   cov_threshold, c->ovf(), c->d_stats, 27, 1, nullptr, m.cap_sing / sizeof(uint64_t), nullptr, m.d_sing);
+        if (c->bins_valid)
+            pos_bin_kernel<0, true><<<blocks, kBinThreads, smem, c->stream>>>(c->table(), c->d_bkeys, c->d_bword, c->d_bidx, c->d_below, n_end, m.part_cap, c->d_binmeta, nullptr,
+                                                                       cov_threshold, c->ovf(), c->d_stats, 27, 1, nullptr, m.cap_sing / sizeof(uint64_t), nullptr, m.d_sing);
+        else   // re-binned round: no index stream, the keys are looked up in the table
+            pos_bin_kernel<0, false><<<blocks, kBinThreads, smem, c->stream>>>(c->table(), c->d_bkeys, c->d_bword, nullptr, nullptr, n_end, m.part_cap, c->d_binmeta, nullptr,
+                                                                        cov_threshold, c->ovf(), c->d_stats, 27, 1, nullptr, m.cap_sing / sizeof(uint64_t), nullptr, m.d_sing);
         PeerOut64 po;
         for (uint32_t j = 0; j < (uint32_t)kMaxPeers; j++)
             po.p[j] = j < m.n_ranks ? reinterpret_cast<uint64_t *>(dest_block(m, j, set)) + dest_region(m, j) * m.capB : nullptr;
@@ -493,7 +570,7 @@ int p3_mg_solid_begin(p3_ctx *c, uint32_t k, uint64_t owned_slots) {
     if (rc) return rc;
     MgState &m = *mp;
     if (!c->d_good21) return fail(P3_ERR_STATE, "p3_mg_solid_begin: run the coverage stage first");
-    if (k < P3_MIN_K || k > 32) return fail(P3_ERR_ARG, "multi-GPU path: k outside [21,32] is not supported");
+    if (k < P3_MIN_K || k > 32) return fail(P3_ERR_ARG, "p3_mg_solid_begin: k outside [21,32] (multi-word k-mers: p3_mg_long_*)");
     c->k = k; m.k = k; c->set_valid = false; c->hints_valid = false; c->d_set_b = nullptr; c->nbs_b = 0; c->parts_b = 1;
     CU(cudaEventRecord(c->ev[4], c->stream));
     CU(cudaMemsetAsync(&c->d_stats->n_adds, 0, sizeof(unsigned long long) * 5, c->stream));
@@ -578,6 +655,23 @@ int p3_mg_solid_recv(p3_ctx *c, uint64_t ch) {
     CU(cudaGetLastError());
     return P3_OK;
 }
+// between two rounds of chunks (human-scale inputs: the k-mer bins live in the count bins, which hold one round): the
+// round's occurrences are de-duplicated into the owned set and the bins start empty again
+int p3_mg_solid_next_round(p3_ctx *c) {
+    MgState *mp;
+    int rc = mg_ready(c, &mp, "p3_mg_solid_next_round");
+    if (rc) return rc;
+    MgState &m = *mp;
+    const uint32_t P = c->set_parts;
+    check_cursors_kernel<<<1, 256, 0, c->stream>>>(c->d_cursor, P, m.kpart_cap, c->d_stats);
+    CU(cudaMemsetAsync(&c->d_stats->work, 0, sizeof(unsigned long long), c->stream));
+    set_sweep_kernel<<<c->grid(), 256, 0, c->stream>>>(c->d_bkeys, reinterpret_cast<const uint8_t *>(c->d_bword), (uint64_t)P * m.kpart_cap, m.kpart_cap,
+                                                      c->d_cursor, c->kset(), c->d_hint, c->d_stats);
+    init_cursors_kernel<<<1, 256, 0, c->stream>>>(c->d_cursor, P, m.kpart_cap);
+    c->launches += 3;
+    CU(cudaGetLastError());
+    return P3_OK;
+}
 // after the last chunk: one L2-resident de-duplication sweep (hints OR-ed per k-mer), then set -> list + hint bytes
 int p3_mg_solid_finish(p3_ctx *c) {
     MgState *mp;
@@ -612,7 +706,8 @@ int p3_mg_solid_end(p3_ctx *c, uint64_t filter_size, uint32_t num_hashes, uint64
     CU(cudaMemsetAsync(c->d_bloom, 0, sizeof(uint32_t) * c->bloom_words, c->stream));
     CU(cudaEventRecord(c->ev[5], c->stream));
     CU(cudaEventRecord(c->ev[14], c->stream));
-    c->have_bf = true; c->have_solid = true; c->have_adj = false; c->set_valid = true; c->hints_valid = true;
+    c->have_bf = true; c->have_solid = true; c->have_adj = false;
+    c->set_valid = c->hints_valid = mp->k <= 32;     // multi-word k-mers: the set holds store indices, there are no hints
     if (n_adds) *n_adds = c->h_stats.n_adds;
     if (n_owned) *n_owned = c->h_stats.n_distinct_solid;
     return P3_OK;
@@ -642,15 +737,22 @@ int p3_mg_bloom_buffer(p3_ctx *c, uint64_t n_u32, uint32_t **d_buf) {
 // h_segbase[s] (device addresses, possibly peer memory; cap records each). h_counts[s] = records
 // written (a count above cap means that segment overflowed: use p3_mg_bloom_direct on all ranks).
 int p3_mg_bloom_bin(p3_ctx *c, uint32_t n_seg, const uint64_t *h_segbase, uint64_t cap, uint64_t *h_counts) {
+    return p3_mg_bloom_bin_range(c, n_seg, h_segbase, cap, h_counts, 0, ~0ULL);
+}
+// the same for k-mers [first, first + count) of the owned list only: the shard owners' buffers then need room for one
+// PASS over the list at a time (human scale: 19 indices of 3.2 G k-mers are 240 GB over all ranks when binned at once)
+int p3_mg_bloom_bin_range(p3_ctx *c, uint32_t n_seg, const uint64_t *h_segbase, uint64_t cap, uint64_t *h_counts, uint64_t first, uint64_t count) {
     if (!c || !c->have_bf || !h_segbase || !h_counts) return fail(P3_ERR_STATE, "p3_mg_bloom_bin: run p3_mg_solid_end first");
     if (n_seg == 0 || n_seg > (uint32_t)kMaxParts || c->num_hashes > (uint32_t)kBinMaxHashes)
         return fail(P3_ERR_ARG, "p3_mg_bloom_bin: too many segments / hash functions for the binned path");
     CU(cudaSetDevice(c->device));
-    uint64_t n = c->h_stats.n_distinct_solid;
+    const uint64_t n = c->h_stats.n_distinct_solid;
+    first = std::min(first, n);
+    count = std::min(count, n - first);
     uint64_t *d_hh = nullptr;
     int rc = bloom_hash_list(c, n, &d_hh);
     if (rc) return rc;
-    rc = bloom_bin_launch(c, d_hh, n, n_seg, bloom_seg_shift(), h_segbase, cap, h_counts);
+    rc = bloom_bin_launch(c, d_hh + 2 * first, count, n_seg, bloom_seg_shift(), h_segbase, cap, h_counts);
     CU(cudaMemsetAsync(&c->d_stats->err_bin_overflow, 0, sizeof(unsigned), c->stream));   // the caller judges overflow from the counts
     return rc;
 }
@@ -697,6 +799,269 @@ uint64_t p3_device_mem_used(p3_ctx *c) {
     size_t fr = 0, tot = 0;
     if (cudaSetDevice(c->device) != cudaSuccess || cudaMemGetInfo(&fr, &tot) != cudaSuccess) { cudaGetLastError(); return 0; }
     return (uint64_t)(tot - fr);
+}
+
+}  // extern "C"
+
+// ---- B2 for multi-word k-mers (33 <= k <= 3001, W = ceil(2k/64) words), reference src/MakeBloomFilter.cpp:60-83 with
+// std::bitset<2k> k-mers (src/Assemble.cpp:30-53) ---------------------------------------------------------------------
+// A solid occurrence travels as its W canonical words (8W bytes; the owner is a hash of std::hash(k-mer), the value the
+// Bloom hashes start from). The owner appends what arrives to a STORE of W-word records and, after the last chunk,
+// de-duplicates the store the way the single-GPU path de-duplicates read positions (p3_long.inc.cu): set slots hold
+// [hash tag:24 | store index:40]; a tag hit is verified by comparing the two records' words — exact. The distinct
+// k-mers become the context's n x W word array, on which the sharded BF.add (its (h1, h2) pairs) and CheckDirections
+// run unchanged. No adjacency hints for multi-word k-mers.
+// source side: every solid occurrence of words [w0, w1) -> W canonical words into region `me` of its owner's receive
+// set. One word per thread; a block counts its occurrences per destination, claims room once per destination, then
+// writes (the canonical choice and the hash are computed in both passes: nothing per occurrence is kept in registers).
+__global__ void __launch_bounds__(256)
+long_scatter_kernel(Stream2 st, const uint32_t *__restrict__ solid, uint64_t w0, uint64_t w1, LongK L, uint32_t n_ranks,
+                    unsigned long long *sent, PeerOut64 out, uint64_t cap, Stats *stt) {
+    __shared__ unsigned s_cnt[kMaxPeers];
+    __shared__ unsigned long long s_base[kMaxPeers];
+    const int tid = threadIdx.x;
+    const uint64_t n_tiles = (w1 - w0 + 255) / 256;
+    bool over = false;
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        if (tid < kMaxPeers) s_cnt[tid] = 0;
+        __syncthreads();
+        const uint64_t w = w0 + tile * 256 + tid;
+        const uint32_t sbits = w < w1 ? __ldg(solid + w) : 0u;
+        for (uint32_t s = sbits; s;) {
+            const int o = __clz(s);
+            s &= ~(0x80000000u >> o);
+            const uint64_t p = w * 32 + o;
+            const bool rc = occ_use_rc(st, p, L);
+            const uint64_t h0 = hash_words(L, [&](int j) { return occ_word(st, p, L, j, rc); });
+            atomicAdd(&s_cnt[owner_of(h0, n_ranks)], 1u);
+        }
+        __syncthreads();
+        if (tid < (int)n_ranks) {
+            const unsigned cnt = s_cnt[tid];
+            s_base[tid] = cnt ? atomicAdd(&sent[tid], (unsigned long long)cnt) : 0ULL;
+            s_cnt[tid] = 0;
+        }
+        __syncthreads();
+        for (uint32_t s = sbits; s;) {
+            const int o = __clz(s);
+            s &= ~(0x80000000u >> o);
+            const uint64_t p = w * 32 + o;
+            const bool rc = occ_use_rc(st, p, L);
+            const uint64_t h0 = hash_words(L, [&](int j) { return occ_word(st, p, L, j, rc); });
+            const uint32_t dst = owner_of(h0, n_ranks);
+            const unsigned long long slot = s_base[dst] + atomicAdd(&s_cnt[dst], 1u);
+            if (slot < cap) {
+                uint64_t *q = out.p[dst] + slot * (uint64_t)L.W;
+                for (int j = 0; j < L.W; j++) q[j] = occ_word(st, p, L, j, rc);
+            } else over = true;
+        }
+        __syncthreads();
+    }
+    if (over) atomicExch(&stt->err_bin_overflow, 1u);
+}
+
+// owner side: append the records of the n_ranks regions (cap records of W words each, counts[r] filled) to the store.
+// Every block reads the store size as it was when the kernel started; long_advance_kernel adds the total afterwards.
+__global__ void __launch_bounds__(256)
+long_gather_kernel(const uint64_t *__restrict__ recv, uint64_t cap, int W, int n_ranks, const unsigned long long *__restrict__ counts,
+                   uint64_t *__restrict__ store, const unsigned long long *__restrict__ store_n, uint64_t store_cap, Stats *stt) {
+    const uint64_t base = *store_n;
+    const uint64_t stride = gridDim.x * (uint64_t)blockDim.x, t0 = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    uint64_t pre = 0;
+    bool over = false;
+    for (int r = 0; r < n_ranks; r++) {
+        const uint64_t n = min((uint64_t)__ldcg(counts + r), cap);
+        const uint64_t room = base + pre < store_cap ? store_cap - (base + pre) : 0;
+        const uint64_t m = min(n, room);
+        if (m < n) over = true;
+        const uint64_t *src = recv + (uint64_t)r * cap * W;
+        uint64_t *dst = store + (base + pre) * W;
+        for (uint64_t i = t0; i < m * W; i += stride) dst[i] = __ldcs(src + i);
+        pre += n;
+    }
+    if (over && t0 == 0) atomicExch(&stt->err_bin_overflow, 1u);
+}
+__global__ void long_advance_kernel(int n_ranks, uint64_t cap, const unsigned long long *__restrict__ counts, unsigned long long *store_n, uint64_t store_cap) {
+    unsigned long long tot = *store_n;
+    for (int r = 0; r < n_ranks; r++) tot += min((unsigned long long)counts[r], (unsigned long long)cap);
+    *store_n = min(tot, (unsigned long long)store_cap);
+}
+
+// de-duplication of the store: slot = [tag:24 | record index:40]
+__global__ void __launch_bounds__(256)
+long_dedupe_store_kernel(const uint64_t *__restrict__ store, const unsigned long long *__restrict__ n_dev, LongK L, uint64_t *set, uint64_t nbs, Stats *stt) {
+    const uint64_t n = *n_dev;
+    const uint64_t stride = gridDim.x * (uint64_t)blockDim.x;
+    bool full = false;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint64_t *kw = store + i * L.W;
+        const uint64_t h0 = hash_words(L, [&](int j) { return __ldg(kw + j); });
+        const uint64_t tag = h0 >> 40;
+        const uint64_t val = (tag << 40) | i;
+        uint64_t b = __umul64hi(fmix64(h0), nbs);
+        bool done = false;
+        for (uint64_t probe = 0; probe < nbs && probe < kMaxProbe && !done; probe++) {
+            uint64_t *bp = set + 4 * b;
+            uint64_t sl[4];
+            ld_bucket(bp, sl);
+#pragma unroll
+            for (int q = 0; q < 4 && !done; q++) {
+                uint64_t v = sl[q];
+                if (v == kEmpty) {
+                    v = atomicCAS(ull(bp + q), kEmpty, val);
+                    if (v == kEmpty) { done = true; break; }
+                }
+                if ((v >> 40) == tag) {
+                    const uint64_t *ow = store + (v & kPos40) * L.W;
+                    bool eq = true;
+                    for (int j = 0; j < L.W && eq; j++) eq = __ldg(kw + j) == __ldg(ow + j);
+                    if (eq) done = true;
+                }
+            }
+            b = (b + 1 == nbs) ? 0 : b + 1;
+        }
+        if (!done) full = true;
+    }
+    if (full) atomicExch(&stt->err_table_full, 1u);
+}
+__global__ void long_materialise_store_kernel(const uint64_t *__restrict__ store, int W, const uint64_t *__restrict__ list, const unsigned long long *__restrict__ n_dev,
+                                              uint64_t n_cap, uint64_t *__restrict__ words) {
+    const uint64_t n = min((uint64_t)*n_dev, n_cap);
+    const uint64_t stride = gridDim.x * (uint64_t)blockDim.x;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n * W; i += stride) {
+        const uint64_t r = i / W, j = i - r * W;
+        words[i] = __ldg(store + (list[r] & kPos40) * W + j);
+    }
+}
+
+extern "C" {
+
+// local part of B2 for k > 32: solid plane (window of k-20 set coverage bits) and seeds; *n_adds = this rank's solid
+// occurrences = the BF.add calls the reference would make for its reads (sizes the owners' stores: sum over ranks / n_ranks)
+int p3_mg_long_solid(p3_ctx *c, uint32_t k, uint64_t *n_adds) {
+    MgState *mp;
+    int rc = mg_ready(c, &mp, "p3_mg_long_solid");
+    if (rc) return rc;
+    if (!c->d_good21) return fail(P3_ERR_STATE, "p3_mg_long_solid: run the coverage stage first");
+    if (k <= 32 || k > P3_MAX_K) return fail(P3_ERR_ARG, "p3_mg_long_solid: 33 <= k <= 3001");
+    if (c->total_bases >= kPos40) return fail(P3_ERR_ARG, "k > 32 supports up to 2^40 bases per context");
+    c->k = k; mp->k = k; c->set_valid = false; c->hints_valid = false; c->d_set_b = nullptr; c->nbs_b = 0; c->parts_b = 1;
+    CU(cudaEventRecord(c->ev[4], c->stream));
+    CU(cudaMemsetAsync(&c->d_stats->n_adds, 0, sizeof(unsigned long long) * 5, c->stream));
+    CU(cudaMemsetAsync(&c->d_stats->err_table_full, 0, sizeof(unsigned), c->stream));
+    CU(cudaMemsetAsync(&c->d_stats->err_bin_overflow, 0, sizeof(unsigned), c->stream));
+    solid_long_kernel<<<c->grid(), 256, 0, c->stream>>>(c->d_good21, c->n_words, (int)k - kShortK + 1, c->d_solid, c->d_stats);
+    seeds_kernel<<<c->grid(4), 256, 0, c->stream>>>(c->d_off, c->n_reads, c->d_solid, (int)k, c->d_seed);
+    c->launches += 2;
+    CU(cudaGetLastError());
+    rc = pull_stats(c);
+    if (rc) return rc;
+    if (n_adds) *n_adds = c->h_stats.n_adds;
+    return P3_OK;
+}
+// sizes the owner's store (owner_occurrences records) and its set (owned_slots), and fixes the chunking of the sends:
+// occ_per_word = upper estimate of the solid occurrences per packed word of any rank (<= 32). *chunk_words / *n_chunks:
+// what p3_mg_long_send takes (the same on every rank when max_words is the largest n_words of any rank).
+int p3_mg_long_begin(p3_ctx *c, uint64_t owned_slots, uint64_t owner_occurrences, double occ_per_word, uint64_t max_words,
+                     uint64_t *chunk_words, uint64_t *n_chunks) {
+    MgState *mp;
+    int rc = mg_ready(c, &mp, "p3_mg_long_begin");
+    if (rc) return rc;
+    MgState &m = *mp;
+    if (m.k <= 32) return fail(P3_ERR_STATE, "p3_mg_long_begin: run p3_mg_long_solid first");
+    LongK L = make_longk(m.k);
+    LongMg &lm = g_longmg.get(c);
+    lm.W = L.W;
+    lm.capL = m.set_bytes / m.n_ranks / (8ull * L.W);
+    if (lm.capL < 64) return fail(P3_ERR_ARG, "p3_mg_long_begin: receive set too small for k-mers of this length (raise set_bytes)");
+    // a chunk's occurrences spread evenly over the owners (a hash): a region must hold its share + 10 % + slack
+    occ_per_word = std::min(32.0, std::max(occ_per_word, 0.001));
+    const double room = (double)lm.capL - std::min<double>(8192.0, (double)lm.capL / 4);
+    uint64_t cw = (uint64_t)(room * m.n_ranks / (occ_per_word * 1.10));
+    if (cw < 32) return fail(P3_ERR_ARG, "p3_mg_long_begin: receive set too small for k-mers of this length (raise set_bytes)");
+    cw = cw >= 256 ? cw / 256 * 256 : cw / 32 * 32;
+    cw = std::min<uint64_t>(cw, std::max<uint64_t>((max_words + 255) / 256 * 256, 256));
+    lm.chunk_words = cw;
+    if (chunk_words) *chunk_words = cw;
+    if (n_chunks) *n_chunks = std::max<uint64_t>((max_words + cw - 1) / cw, 1);
+    lm.store_records = std::max<uint64_t>(owner_occurrences, 1024);
+    CU(ensure(lm.d_store, lm.cap_store, lm.store_records * 8ull * L.W));
+    if (!lm.d_store_n) CU(cudaMalloc(&lm.d_store_n, sizeof(unsigned long long)));
+    CU(cudaMemsetAsync(lm.d_store_n, 0, sizeof(unsigned long long), c->stream));
+    uint64_t nbs = (std::max<uint64_t>(owned_slots, 1024) + 3) / 4;
+    if (!c->d_set || c->nbs != nbs) {
+        dfree(c->d_set); dfree(c->d_list);
+        if (cudaMalloc(&c->d_set, nbs * 32) != cudaSuccess || cudaMalloc(&c->d_list, nbs * 32) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(P3_ERR_NOMEM, "owned k-mer set allocation failed");
+        }
+        c->nbs = nbs; c->list_cap = nbs * 4;
+    }
+    c->set_parts = 1;
+    CU(cudaMemsetAsync(c->d_set, 0xFF, nbs * 32, c->stream));
+    c->bins_valid = false;
+    return P3_OK;
+}
+int p3_mg_long_send(p3_ctx *c, uint64_t ch) {
+    MgState *mp;
+    int rc = mg_ready(c, &mp, "p3_mg_long_send");
+    if (rc) return rc;
+    MgState &m = *mp;
+    LongMg *lm = g_longmg.find(c);
+    if (!lm || !lm->chunk_words) return fail(P3_ERR_STATE, "p3_mg_long_send: run p3_mg_long_begin first");
+    const int set = (int)(ch & 1);
+    LongK L = make_longk(m.k);
+    const uint64_t w0 = std::min<uint64_t>(ch * lm->chunk_words, c->n_words), w1 = std::min<uint64_t>((ch + 1) * lm->chunk_words, c->n_words);
+    CU(cudaMemsetAsync(m.d_sent, 0, sizeof(unsigned long long) * (kMaxParts + 1), c->stream));
+    if (w1 > w0) {
+        PeerOut64 po;
+        for (uint32_t j = 0; j < (uint32_t)kMaxPeers; j++)
+            po.p[j] = j < m.n_ranks ? reinterpret_cast<uint64_t *>(dest_block(m, j, set)) + dest_region(m, j) * lm->capL * L.W : nullptr;
+        Stream2 st; st.packed = c->d_packed; st.nmask = c->d_nmask;
+        const unsigned blocks = (unsigned)std::min<uint64_t>((w1 - w0 + 255) / 256, (uint64_t)c->grid());
+        long_scatter_kernel<<<blocks, 256, 0, c->stream>>>(st, c->d_solid, w0, w1, L, m.n_ranks, m.d_sent, po, lm->capL, c->d_stats);
+        c->launches++;
+        CU(cudaGetLastError());
+    }
+    return mg_publish(c, m, set);
+}
+int p3_mg_long_recv(p3_ctx *c, uint64_t ch) {
+    MgState *mp;
+    int rc = mg_ready(c, &mp, "p3_mg_long_recv");
+    if (rc) return rc;
+    MgState &m = *mp;
+    LongMg *lm = g_longmg.find(c);
+    if (!lm || !lm->chunk_words) return fail(P3_ERR_STATE, "p3_mg_long_recv: run p3_mg_long_begin first");
+    const int set = (int)(ch & 1);
+    const uint64_t *recv = reinterpret_cast<const uint64_t *>(m.set_ptr(m.my_rank, set));
+    const unsigned long long *counts = &m.ctl()->count[set][0];
+    long_gather_kernel<<<c->grid(4), 256, 0, c->stream>>>(recv, lm->capL, lm->W, (int)m.n_ranks, counts, lm->d_store, lm->d_store_n, lm->store_records, c->d_stats);
+    long_advance_kernel<<<1, 1, 0, c->stream>>>((int)m.n_ranks, lm->capL, counts, lm->d_store_n, lm->store_records);
+    c->launches += 2;
+    CU(cudaGetLastError());
+    return P3_OK;
+}
+// after the last chunk: de-duplicate the store, materialise the distinct k-mers as this context's n x W word array
+// (enqueue only; p3_mg_solid_end waits, checks and leaves the empty filter)
+int p3_mg_long_finish(p3_ctx *c) {
+    MgState *mp;
+    int rc = mg_ready(c, &mp, "p3_mg_long_finish");
+    if (rc) return rc;
+    MgState &m = *mp;
+    LongMg *lm = g_longmg.find(c);
+    if (!lm || !lm->d_store) return fail(P3_ERR_STATE, "p3_mg_long_finish: run p3_mg_long_begin first");
+    LongK L = make_longk(m.k);
+    long_dedupe_store_kernel<<<c->grid(), 256, 0, c->stream>>>(lm->d_store, lm->d_store_n, L, c->d_set, c->nbs, c->d_stats);
+    CU(cudaMemsetAsync(&c->d_stats->n_distinct_solid, 0, sizeof(unsigned long long), c->stream));
+    compact_set_kernel<<<c->grid(), 256, 0, c->stream>>>(c->d_set, c->nbs * 4, c->d_list, c->list_cap, c->d_stats);
+    LongState &ls = g_long.get(c);
+    // the distinct k-mers are at most the store's records and at most the list's capacity
+    CU(ensure(ls.d_words, ls.cap_words, sizeof(uint64_t) * std::max<uint64_t>(std::min<uint64_t>(lm->store_records, c->list_cap) * L.W, 1)));
+    long_materialise_store_kernel<<<c->grid(), 256, 0, c->stream>>>(lm->d_store, L.W, c->d_list, &c->d_stats->n_distinct_solid,
+                                                                   std::min<uint64_t>(lm->store_records, c->list_cap), ls.d_words);
+    c->launches += 3;
+    CU(cudaGetLastError());
+    return P3_OK;
 }
 
 }  // extern "C"

@@ -227,7 +227,7 @@ class EmulatedComm:
 # ---------------------------------------------------------------------------- driver
 def default_set_bytes(chunk_words, world):
     """receive set for one chunk of 21-mer records (12 B each): expected share + 3 % + slack per region"""
-    per_region = int(chunk_words * 32 / world * 1.03) + 8192 + 4096
+    per_region = int(chunk_words * 32 / world * 1.03) + 8192 + 2 * 4096    # the library rounds a region DOWN to whole sort tiles (4096 records)
     return per_region * 12 * world
 
 
@@ -250,13 +250,25 @@ def _setup(ctxs, comm, set_bytes, transport, dev_index):
     comm._p3_setup = key
 
 
+def plan_rounds(n_chunks, owner_total, bin_budget_bytes):
+    """how many insert rounds keep the owner's bins (16 B per received record + slack) inside the budget -> (n_rounds, chunks per round)"""
+    want = max(1, -(-int(owner_total * 16.5) // max(int(bin_budget_bytes), 1)))
+    n_rounds = max(1, min(n_chunks, want))
+    cpr = -(-n_chunks // n_rounds)
+    return -(-n_chunks // cpr), cpr
+
+
 def run_hot_path(ctxs, comm, k, filter_size, num_hashes, table_slots, solid_slots=0, owned_slots=0,
-                 chunk_words=None, device=None, set_bytes=None, cov_threshold=2):
+                 chunk_words=None, device=None, set_bytes=None, cov_threshold=2, bin_budget_bytes=None, bloom_budget_bytes=None):
     """ctxs: the Context of every LOCAL rank (reads already attached/uploaded, all contexts of one process on
     the current torch stream), in comm.local_ranks order. table_slots / owned_slots: per-rank capacities of
     the count table and of the owned solid k-mer set. Returns one stats dict per local rank; the results
     stay in the contexts (owned 21-mer counts, owned k-mers + adjacency, local seeds, the complete filter).
-    solid_slots is accepted for compatibility and unused (there is no local k-mer set any more)."""
+    solid_slots is accepted for compatibility and unused (there is no local k-mer set any more).
+    bin_budget_bytes (default 80 GB, env P3_MG_BIN_BUDGET): when an owner's partition bins for ALL its records would not fit,
+    the count, the verdicts and the de-duplication run in rounds of chunks over bins sized for one round (human-scale
+    inputs, BASELINE.json configs[3]); bloom_budget_bytes (default 16 GB, env P3_MG_BLOOM_BUDGET) bounds the shard owners'
+    bit-index buffers the same way (several passes over the owned k-mer lists). Results do not depend on either."""
     L = _lib.lib()
     w = comm.world
     device = device or torch.device("cuda", torch.cuda.current_device())
@@ -277,13 +289,23 @@ def run_hot_path(ctxs, comm, k, filter_size, num_hashes, table_slots, solid_slot
     peer = os.environ.get("P3_MG_EXCHANGE", "peer") != "nccl"
     transport = 0 if peer else 1
     n_words = [(c.total_bases + 31) // 32 for c in ctxs]
-    cw = chunk_words or max(max(n_words), 128)
-    cw = (cw + 127) // 128 * 128
     pos_upper = [max(c.total_bases - 20 * c.n_reads, 0) for c in ctxs]
-    n_chunks, = comm.all_max([[max((nw + cw - 1) // cw, 1)] for nw in n_words])
     total_pos, = comm.all_sum([[p] for p in pos_upper])
-    owner_positions = int(total_pos / w * 1.02) + 65536
-    set_bytes = set_bytes or default_set_bytes(min(cw, max(comm.all_max([[nw] for nw in n_words])[0], 128)), w)
+    max_words, ppw_e6 = comm.all_max([[nw, min(32_000_000, -(-p * 1_000_000 // max(nw, 1)))] for nw, p in zip(n_words, pos_upper)])
+    owner_total = int(total_pos / w * 1.02) + 65536
+    bin_budget = int(bin_budget_bytes or float(os.environ.get("P3_MG_BIN_BUDGET", 80e9)))
+    cw = chunk_words
+    if not cw:     # one chunk per round
+        cw = -(-max(max_words, 128) // plan_rounds(1 << 30, owner_total, bin_budget)[0])
+    cw = (cw + 127) // 128 * 128
+    n_chunks, = comm.all_max([[max((nw + cw - 1) // cw, 1)] for nw in n_words])
+    n_rounds, cpr = plan_rounds(n_chunks, owner_total, bin_budget)
+    rounds = [range(r * cpr, min((r + 1) * cpr, n_chunks)) for r in range(n_rounds)]
+    # what one round can bring an owner: every rank's chunks of the round, spread evenly over the owners (a hash)
+    owner_positions = owner_total if n_rounds == 1 else min(owner_total, int(cpr * cw * (ppw_e6 / 1e6) * 1.02) + 65536)
+    set_bytes = set_bytes or default_set_bytes(min(cw, max_words + 128), w)
+    if k > 32:      # a region must hold a useful number of W-word k-mer records
+        set_bytes = max(set_bytes, w * 8 * ((2 * k + 63) // 64) * 8192)
     _setup(ctxs, comm, set_bytes, transport, dev_index)
 
     def sync(stage, rset):
@@ -302,14 +324,22 @@ def run_hot_path(ctxs, comm, k, filter_size, num_hashes, table_slots, solid_slot
     for c in ctxs:
         _check(L.p3_mg_count_begin(c.h, table_slots, owner_positions, cw, n_chunks))
     stage_start()
-    for ch in range(n_chunks):
+
+    def count_chunks(chs):
+        for ch in chs:
+            for c in ctxs:
+                _check(L.p3_mg_count_send(c.h, ch))
+            sync(0, ch & 1)
+            for c in ctxs:
+                _check(L.p3_mg_count_recv(c.h, ch))
+
+    for r, chs in enumerate(rounds):
+        if r:
+            for c in ctxs:
+                _check(L.p3_mg_count_next_round(c.h))
+        count_chunks(chs)
         for c in ctxs:
-            _check(L.p3_mg_count_send(c.h, ch))
-        sync(0, ch & 1)
-        for c in ctxs:
-            _check(L.p3_mg_count_recv(c.h, ch))
-    for c in ctxs:
-        _check(L.p3_mg_count_finish(c.h))
+            _check(L.p3_mg_count_finish(c.h))
     mark("count")
     for c, st in zip(ctxs, stats):
         _check(L.p3_mg_count_end(c.h))
@@ -324,26 +354,72 @@ def run_hot_path(ctxs, comm, k, filter_size, num_hashes, table_slots, solid_slot
         ns = C.c_uint32()
         _check(L.p3_mg_cover_begin(c.h, cov_threshold, owner_distinct, C.byref(ns)))
         n_slices = ns.value
-    stage_start()
-    for sl in range(n_slices):
-        for c in ctxs:
-            _check(L.p3_mg_cover_send(c.h, cov_threshold, sl))
-        sync(1, sl & 1)
-        for c in ctxs:
-            _check(L.p3_mg_cover_recv(c.h, sl))
+    def cover_slices():
+        stage_start()
+        for sl in range(n_slices):
+            for c in ctxs:
+                _check(L.p3_mg_cover_send(c.h, cov_threshold, sl))
+            sync(1, sl & 1)
+            for c in ctxs:
+                _check(L.p3_mg_cover_recv(c.h, sl))
+
+    if n_rounds == 1:
+        cover_slices()
+    else:       # the bins hold one round: send and sort every round's records again, then that round's verdicts
+        for chs in rounds:
+            for c in ctxs:
+                _check(L.p3_mg_cover_rebin_begin(c.h))
+            stage_start()
+            count_chunks(chs)
+            for c in ctxs:
+                _check(L.p3_mg_cover_rebin_end(c.h))
+            cover_slices()
     mark("coverage")
     # ---- B2: solid occurrences to their owners ---------------------------------------------------------
-    for c in ctxs:     # default capacity: a rank owns about 1/w of all k-mers, whatever share of the reads it parsed
-        _check(L.p3_mg_solid_begin(c.h, k, owned_slots or max(2 * total_pos // w + 4096, 4096)))
-    stage_start()
-    for ch in range(n_chunks):
+    n_long_chunks = 0
+    if k > 32:
+        # multi-word k-mers: every solid occurrence travels as its W canonical words; the owner stores what arrives and
+        # de-duplicates the store after the last chunk (csrc/p3_multi.inc.cu, p3_mg_long_*)
+        local_adds = []
         for c in ctxs:
-            _check(L.p3_mg_solid_send(c.h, ch))
-        sync(2, ch & 1)
+            na = C.c_uint64()
+            _check(L.p3_mg_long_solid(c.h, k, C.byref(na)))
+            local_adds.append(na.value)
+        total_adds, = comm.all_sum([[a] for a in local_adds])
+        opw_e6, = comm.all_max([[-(-a * 1_000_000 // max(nw, 1))] for a, nw in zip(local_adds, n_words)])
+        owner_occ = int(total_adds / w * 1.05) + 65536
+        cwl = nchl = 0
         for c in ctxs:
-            _check(L.p3_mg_solid_recv(c.h, ch))
-    for c in ctxs:
-        _check(L.p3_mg_solid_finish(c.h))
+            a, b = C.c_uint64(), C.c_uint64()
+            _check(L.p3_mg_long_begin(c.h, owned_slots or max(2 * owner_occ, 4096), owner_occ, min(32.0, opw_e6 / 1e6 * 1.4 + 0.5), max_words,
+                                      C.byref(a), C.byref(b)))
+            cwl, nchl = a.value, b.value
+        n_long_chunks = nchl if total_adds else 0
+        stage_start()
+        for ch in range(n_long_chunks):
+            for c in ctxs:
+                _check(L.p3_mg_long_send(c.h, ch))
+            sync(3, ch & 1)
+            for c in ctxs:
+                _check(L.p3_mg_long_recv(c.h, ch))
+        for c in ctxs:
+            _check(L.p3_mg_long_finish(c.h))
+    else:
+        for c in ctxs:     # default capacity: a rank owns about 1/w of all k-mers, whatever share of the reads it parsed
+            _check(L.p3_mg_solid_begin(c.h, k, owned_slots or max(2 * total_pos // w + 4096, 4096)))
+        stage_start()
+        for r, chs in enumerate(rounds):
+            if r:
+                for c in ctxs:
+                    _check(L.p3_mg_solid_next_round(c.h))
+            for ch in chs:
+                for c in ctxs:
+                    _check(L.p3_mg_solid_send(c.h, ch))
+                sync(2, ch & 1)
+                for c in ctxs:
+                    _check(L.p3_mg_solid_recv(c.h, ch))
+        for c in ctxs:
+            _check(L.p3_mg_solid_finish(c.h))
     mark("dedupe")
     # the filter: sharded, binned adds (each rank owns a contiguous run of 16 MB segments and receives
     # the bit indices that fall into them) or, as fallback, adds into replicated copies + OR-reduce
@@ -367,14 +443,20 @@ def run_hot_path(ctxs, comm, k, filter_size, num_hashes, table_slots, solid_slot
         return out
 
     binned = False
+    n_pass = 1
+    n_all = [row[0] for row in comm.all_gather([[st["owned_solid"]] for st in stats])]
     if sharded:
-        n_all = [row[0] for row in comm.all_gather([[st["owned_solid"]] for st in stats])]
         force = os.environ.get("P3_BLOOM_BINNED")
         binned = (force != "0") if force is not None else (nseg >= 2 and sum(n_all) * num_hashes >= (1 << 22))
     if binned:
-        # hashed indices are uniform: a full segment gets seg_bits / filter_size of a source's indices
+        # hashed indices are uniform: a full segment gets seg_bits / filter_size of a source's indices. The shard owners'
+        # buffers hold one PASS over the sources' k-mer lists; several passes when all indices at once exceed the budget
         share = min(1.0, seg_bits / filter_size)
-        cap_src = [int(n * num_hashes * share * 1.05) + 65536 for n in n_all]
+        bloom_budget = int(bloom_budget_bytes or float(os.environ.get("P3_MG_BLOOM_BUDGET", 16e9)))
+        full = 4 * spr * sum(int(n * num_hashes * share * 1.05) + 65536 for n in n_all)
+        n_pass = max(1, min(-(-full // max(bloom_budget, 1)), max(max(n_all), 1)))
+        per_pass = [-(-n // n_pass) for n in n_all]
+        cap_src = [int(n * num_hashes * share * 1.05) + 65536 for n in per_pass]
         prefix = [sum(cap_src[:r]) for r in range(w)]
         tot_cap = sum(cap_src)
         # the buffers only ever grow, and their size is the same function of the same numbers on every rank:
@@ -391,29 +473,35 @@ def run_hot_path(ctxs, comm, k, filter_size, num_hashes, table_slots, solid_slot
             table = comm.share(ptr_rows, dev_index)
             comm.barrier()
             comm._p3_bloom = (tuple(c.h for c in ctxs), spr * tot_cap, ptr_rows, table)
-        count_rows = []
-        for c, r in zip(ctxs, comm.local_ranks):
-            base = (C.c_uint64 * nseg)(*[table[s // spr][0] + 4 * ((s % spr) * tot_cap + prefix[r]) for s in range(nseg)])
-            counts = (C.c_uint64 * nseg)()
-            _check(L.p3_mg_bloom_bin(c.h, nseg, base, cap_src[r], counts))
-            count_rows.append([int(x) for x in counts])
-        cnt = np.array(comm.all_gather(count_rows), dtype=np.int64).reshape(w, nseg)
-        binned = bool((cnt <= np.array(cap_src)[:, None]).all())     # the same verdict on every rank
-        stage_start()       # every source's stores have landed
+        for ps in range(n_pass):
+            count_rows = []
+            for c, r in zip(ctxs, comm.local_ranks):
+                base = (C.c_uint64 * nseg)(*[table[s // spr][0] + 4 * ((s % spr) * tot_cap + prefix[r]) for s in range(nseg)])
+                counts = (C.c_uint64 * nseg)()
+                _check(L.p3_mg_bloom_bin_range(c.h, nseg, base, cap_src[r], counts, ps * per_pass[r], per_pass[r]))
+                count_rows.append([int(x) for x in counts])
+            cnt = np.array(comm.all_gather(count_rows), dtype=np.int64).reshape(w, nseg)
+            binned = bool((cnt <= np.array(cap_src)[:, None]).all())     # the same verdict on every rank
+            stage_start()       # every source's stores have landed
+            if not binned:      # a segment outgrew its share: every rank adds directly (from scratch) and the copies are OR-reduced
+                break
+            for c, r, row in zip(ctxs, comm.local_ranks, ptr_rows):
+                first = r * spr
+                nloc = max(0, min(spr, nseg - first))
+                if nloc:
+                    hp = (C.c_uint64 * (nloc * w))(*[row[0] + 4 * (sl * tot_cap + prefix[src]) for sl in range(nloc) for src in range(w)])
+                    hn = (C.c_uint64 * (nloc * w))(*[int(cnt[src, first + sl]) for sl in range(nloc) for src in range(w)])
+                    _check(L.p3_mg_bloom_apply(c.h, first, nloc, w, hp, hn))
+            if ps + 1 < n_pass:
+                stage_start()   # nobody overwrites a buffer of the next pass before it has been applied
     if binned:
-        for c, r, row in zip(ctxs, comm.local_ranks, ptr_rows):
-            first = r * spr
-            nloc = max(0, min(spr, nseg - first))
-            if nloc:
-                hp = (C.c_uint64 * (nloc * w))(*[row[0] + 4 * (sl * tot_cap + prefix[src]) for sl in range(nloc) for src in range(w)])
-                hn = (C.c_uint64 * (nloc * w))(*[int(cnt[src, first + sl]) for sl in range(nloc) for src in range(w)])
-                _check(L.p3_mg_bloom_apply(c.h, first, nloc, w, hp, hn))
         comm.all_gather_shards(filter_tensors(), spr * seg_words)
         stage_start()       # nobody overwrites a bloom buffer of the next step before it has been applied
-    else:
+    elif sum(n_all):
         for c in ctxs:
             _check(L.p3_mg_bloom_direct(c.h))
         comm.or_reduce([f[: (filter_size + 31) // 32] for f in filter_tensors()])
+    # (no solid k-mer anywhere: every copy of the filter is empty already)
     for c, st in zip(ctxs, stats):
         st["filter"] = "sharded" if binned else "replicated"
         _check(L.p3_mg_makebf_done(c.h))
@@ -432,4 +520,5 @@ def run_hot_path(ctxs, comm, k, filter_size, num_hashes, table_slots, solid_slot
         st["lap_ms"] = {"owner_" + kk: v for kk, v in st.get("owner_count_ms", {}).items()}
         st["hbm_used_peak_bytes"] = mem_peak[0]
         st["n_chunks"], st["cover_slices"], st["set_bytes"] = n_chunks, n_slices, set_bytes
+        st["insert_rounds"], st["bloom_passes"], st["long_chunks"] = n_rounds, n_pass, n_long_chunks
     return stats

@@ -275,3 +275,126 @@ def test_distributed_hot_path_two_real_gpus(oracle, tmp_path, exchange):
     assert np.array_equal(kmers, osolid)
     for i in range(0, len(osolid), max(1, len(osolid) // 500)):
         assert adj[i] == oracle.check_directions(obits, fs, nh, osolid[i:i + 1], k)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world,exchange", [(1, "peer"), (3, "peer-sharded-filter"), (4, "nccl")])
+def test_distributed_insert_rounds_and_bloom_passes(oracle, world, exchange, monkeypatch):
+    """human-scale schedule at test size: the owners' bins are too small for all records, so the count, the verdicts
+    (records sent and sorted a second time, keys looked up in the finished table) and the de-duplication run in several
+    rounds of chunks, and the sharded Bloom adds in several passes — same results as the one-round schedule"""
+    want_filter = "replicated"
+    if exchange == "peer-sharded-filter":
+        exchange, want_filter = "peer", "sharded"
+        monkeypatch.setenv("P3_BLOOM_BINNED", "1")
+        monkeypatch.setenv("P3_BLOOM_SEG_BITS", "4096")
+        monkeypatch.setenv("P3_BINNED_CLEARS", "1")
+    monkeypatch.setenv("P3_MG_EXCHANGE", exchange)
+    monkeypatch.setenv("P3_PARTS", "5")
+    monkeypatch.setenv("P3_MG_COVER_SLICES", "2")
+    k = 32
+    g = synth.random_genome(12000, 41)
+    reads = synth.reads_as_bytes(synth.simulate_reads(g, 30, 120, 0.01, 42))
+    reads += [b"T" * 200, b"A" * 64 + b"C" * 64]
+    seq, off = reads_to_arrays(reads)
+    fs, nh = _lib.estimate_bloomfilter(int(off[-1]), k)
+    n_keys = len(oracle.count_short_kmers(seq, off)[0])
+    bounds = np.linspace(0, len(reads), world + 1).astype(int)
+    stream = torch.cuda.Stream()
+    ctxs = []
+    with torch.cuda.stream(stream):
+        for r in range(world):
+            s, o = reads_to_arrays(reads[bounds[r]:bounds[r + 1]])
+            c = _lib.Context(0, C.c_void_p(stream.cuda_stream))
+            c.load_ascii(s, o)
+            ctxs.append(c)
+        try:
+            comm = pdist.EmulatedComm(world)
+            for _ in range(2):
+                stats = pdist.run_hot_path(ctxs, comm, k, fs, nh, table_slots=max(2 * n_keys // world, 4096), chunk_words=384,
+                                           set_bytes=1536 * 1024, bin_budget_bytes=1_000_000, bloom_budget_bytes=3_000_000)
+            assert all(s["exchange"] == exchange and s["filter"] == want_filter for s in stats)
+            assert stats[0]["insert_rounds"] >= 3 and stats[0]["n_chunks"] > stats[0]["insert_rounds"]
+            if want_filter == "sharded":
+                assert stats[0]["bloom_passes"] >= 2
+            _check_distributed(oracle, ctxs, stats, reads, bounds, world, k, fs, nh)
+            # and the one-round schedule on the same contexts afterwards (bins grow, state is reset)
+            stats = pdist.run_hot_path(ctxs, comm, k, fs, nh, table_slots=max(2 * n_keys // world, 4096), chunk_words=384, set_bytes=1536 * 1024)
+            assert stats[0]["insert_rounds"] == 1
+            _check_distributed(oracle, ctxs, stats, reads, bounds, world, k, fs, nh)
+        finally:
+            for c in ctxs:
+                c.close()
+
+
+def _check_distributed_long(oracle, ctxs, stats, reads, bounds, k, fs, nh):
+    """multi-word k: counts, filter bits, seeds, the union of the owned k-mer lists (n x W words, no k-mer twice) and
+    sampled adjacency bytes against the oracle"""
+    seq, off = reads_to_arrays(reads)
+    okeys, ocounts = oracle.count_short_kmers(seq, off)
+    obits, oseeds, _, oadds = oracle.make_bf(seq, off, k, okeys, ocounts, fs, nh)
+    osolid = oracle.solid_kmers(seq, off, k, okeys, ocounts)
+    W = osolid.shape[1]
+    assert sum(s["n_adds"] for s in stats) == oadds
+    assert sum(s["owned_solid"] for s in stats) == len(osolid)
+    for r, c in enumerate(ctxs):
+        assert np.array_equal(c.bf_export(), obits)
+        assert np.array_equal(c.seed_export(), oseeds[bounds[r]:bounds[r + 1]])
+    dbg = [c.dbg_export(sort=False) for c in ctxs]
+    kmers = np.concatenate([d[0].reshape(-1, W) for d in dbg])
+    adj = np.concatenate([d[1] for d in dbg])
+    assert sum(s["owned_edges"] for s in stats) == int(np.unpackbits(adj).sum())
+    o = np.lexsort(tuple(kmers[:, j] for j in range(W)))
+    kmers, adj = kmers[o], adj[o]
+    assert kmers.shape == osolid.shape and np.array_equal(kmers, osolid)
+    for i in range(0, len(osolid), max(1, len(osolid) // 300)):
+        assert adj[i] == oracle.check_directions(obits, fs, nh, osolid[i], k), (k, i)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world,exchange,k,rl,set_kb", [(1, "peer", 63, 150, None), (2, "peer", 63, 150, None), (3, "peer-sharded-filter", 47, 120, 900),
+                                                        (4, "nccl", 101, 250, 1024), (8, "peer", 33, 100, None), (2, "peer-sharded-filter", 3001, 6000, None)])
+def test_distributed_long_k_emulated(oracle, world, exchange, k, rl, set_kb, monkeypatch):
+    """multi-word k-mers (the reference's std::bitset<2k>, up to its largest k = 3001) over R emulated ranks: the solid
+    occurrences travel as W-word records to the owner of their hash, the owner de-duplicates its store; filter, seeds,
+    k-mer lists and adjacency equal the single-node oracle. Small receive sets force several chunks."""
+    want_filter = "replicated"
+    if exchange == "peer-sharded-filter":
+        exchange, want_filter = "peer", "sharded"
+        monkeypatch.setenv("P3_BLOOM_BINNED", "1")
+        monkeypatch.setenv("P3_BLOOM_SEG_BITS", "4096")
+        monkeypatch.setenv("P3_BINNED_CLEARS", "1")
+    monkeypatch.setenv("P3_MG_EXCHANGE", exchange)
+    if k > 1000:
+        g = synth.random_genome(9000, 21)
+        reads = synth.reads_as_bytes(synth.simulate_reads(g, 12, rl, 0.0, 22 + k))
+        fs, nh = 200003, 10
+    else:
+        g = synth.random_genome(6000, 300 + k)
+        reads = synth.reads_as_bytes(synth.simulate_reads(g, 40, rl, 0.003, 301 + k))
+        reads[5] = reads[5][:70] + b"N" + reads[5][71:]
+        reads += [b"A" * (2 * k + 40), b"T" * (k + 30), b"AC" * (k + 5)]
+        fs, nh = _lib.estimate_bloomfilter(sum(len(r) for r in reads), k)
+    seq, off = reads_to_arrays(reads)
+    n_keys = len(oracle.count_short_kmers(seq, off)[0])
+    bounds = np.linspace(0, len(reads), world + 1).astype(int)
+    stream = torch.cuda.Stream()
+    ctxs = []
+    with torch.cuda.stream(stream):
+        for r in range(world):
+            s, o = reads_to_arrays(reads[bounds[r]:bounds[r + 1]])
+            c = _lib.Context(0, C.c_void_p(stream.cuda_stream))
+            c.load_ascii(s, o)
+            ctxs.append(c)
+        try:
+            comm = pdist.EmulatedComm(world)
+            for _ in range(2):
+                stats = pdist.run_hot_path(ctxs, comm, k, fs, nh, table_slots=max(2 * n_keys // world, 4096), chunk_words=512 if set_kb else None,
+                                           set_bytes=set_kb * 1024 if set_kb else None)
+            assert all(s["exchange"] == exchange and s["filter"] == want_filter for s in stats)
+            if set_kb:
+                assert stats[0]["long_chunks"] > 1
+            _check_distributed_long(oracle, ctxs, stats, reads, bounds, k, fs, nh)
+        finally:
+            for c in ctxs:
+                c.close()

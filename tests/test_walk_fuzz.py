@@ -5,8 +5,10 @@ palindromes (cycles, k-mers equal to their own reverse complement), low coverage
 substitution errors (bubbles), non-ACGT bytes, tight `-m` filters (Bloom false positives on the
 walk) — for single-word and multi-word k. The CheckDirections table handed to the walk comes from
 the oracle, so the test needs no GPU. Skipped where the reference is not compiled (the GPU box)."""
-import multiprocessing as mp
 import os
+import pickle
+import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -42,7 +44,7 @@ def _reads(rng, k):
     return [bytes(r) for r in reads]
 
 
-def _reference_run(path, k, m, q):
+def _reference_run(path, k, m, out_path):
     from _checkers import Ref
     import tempfile
     ref = Ref(k, readfile=path, m=m, threads=1)
@@ -54,13 +56,30 @@ def _reference_run(path, k, m, q):
     ref.count_node_coverage()
     with tempfile.TemporaryDirectory() as td:
         gfa = sorted(ref.print_graph(td))
-    q.put(dict(k=k, filter_size=ref.filter_size, num_hashes=ref.num_hashes, keys=keys, counts=counts, bloom=bloom,
-               seeds=np.array(seeds), gfa=gfa, nodes=ref.counts()))
+    with open(out_path, "wb") as f:
+        pickle.dump(dict(k=k, filter_size=ref.filter_size, num_hashes=ref.num_hashes, keys=keys, counts=counts, bloom=bloom,
+                         seeds=np.array(seeds), gfa=gfa, nodes=ref.counts()), f)
+
+
+def _reference_in_fresh_process(path, k, m, out_path, timeout=30):
+    """the reference loops forever on a saturated filter, so it runs in its own process under a timeout — a FRESH
+    interpreter, not a fork: by the time this test runs the pytest process has OpenMP / torch threads, and a forked
+    child that enters libgomp deadlocks"""
+    here = os.path.dirname(os.path.abspath(__file__))
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([here, os.path.dirname(here), os.environ.get("PYTHONPATH", "")]))
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), path, str(k), str(m), out_path], env=env, timeout=timeout,
+                           stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
+    except subprocess.TimeoutExpired:
+        return None
+    if r.returncode != 0:
+        raise RuntimeError("reference run failed: " + r.stderr.decode(errors="replace")[-2000:])
+    with open(out_path, "rb") as f:
+        return pickle.load(f)
 
 
 @pytest.mark.parametrize("k", [21, 25, 32, 33, 63])
 def test_host_walk_matches_reference_on_awkward_graphs(oracle, tmp_path, k):
-    ctx = mp.get_context("fork")
     done = 0
     for trial in range(9):
         rng = np.random.default_rng(7919 * k + trial)
@@ -70,15 +89,9 @@ def test_host_walk_matches_reference_on_awkward_graphs(oracle, tmp_path, k):
         n_kmers = sum(max(0, len(r) - k + 1) for r in reads)
         # explicit filter: large enough that the reference's walk terminates, small enough for false positives
         m = int(n_kmers * float(rng.choice([1.5, 3, 8]))) + 1009
-        q = ctx.Queue()
-        p = ctx.Process(target=_reference_run, args=(path, k, m, q))   # the reference loops forever on a saturated filter
-        p.start()
-        try:
-            g = q.get(timeout=20)
-        except Exception:
-            p.kill()
+        g = _reference_in_fresh_process(path, k, m, str(tmp_path / "ref.pkl"))
+        if g is None:
             continue
-        p.join(10)
         kk, aa, ss, n_solid = _closed_table_from_oracle(oracle, g, path)
         gfa = str(tmp_path / "fz.gfa")
         st = _lib.walk_table(path, k, kk, aa, ss, gfa_path=gfa)
@@ -86,3 +99,7 @@ def test_host_walk_matches_reference_on_awkward_graphs(oracle, tmp_path, k):
         assert sorted(open(gfa).read().splitlines()) == g["gfa"], (k, trial)
         done += 1
     assert done >= 5      # the odd non-terminating reference run is skipped, not most of them
+
+
+if __name__ == "__main__":
+    _reference_run(sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), sys.argv[4])
