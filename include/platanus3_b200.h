@@ -204,6 +204,18 @@ int p3_mg_count_end(p3_ctx *ctx);   /* then p3_short_kmer_stats / _export / _loo
  * _end (p3_mg_count_send / _recv), followed by that round's slices; the solid stage de-duplicates per round
  * (p3_mg_solid_next_round between two rounds). Results are identical to the one-round schedule. */
 int p3_mg_count_next_round(p3_ctx *ctx);
+/* The better schedule for the same inputs: rounds over KEY RANGES (groups of table partitions) instead of read chunks.
+ * Every round the sources scan all their reads and send only the records of that round's partitions, so an owner sees
+ * all occurrences of a key in one round: its counts are final when the round's insert ends, the round's verdicts follow
+ * the insert's index stream at once, nothing is sent twice and the table passes through L2 once.
+ *   p3_mg_count_begin_keyed (owner_positions = the estimate for ALL rounds), p3_mg_sync; per round r:
+ *   p3_mg_key_round_begin(r); every chunk: p3_mg_count_send, sync, p3_mg_count_recv; p3_mg_count_finish;
+ *   [r == 0: p3_mg_cover_begin_keyed]; p3_mg_cover_key_round; p3_mg_sync; per slice: p3_mg_cover_send, sync, _recv;
+ *   p3_mg_count_next_round before the next round; p3_mg_count_end after the last. */
+int p3_mg_count_begin_keyed(p3_ctx *ctx, uint64_t table_slots, uint64_t owner_positions, uint64_t chunk_words, uint64_t n_chunks, uint32_t n_rounds);
+int p3_mg_key_round_begin(p3_ctx *ctx, uint32_t round);
+int p3_mg_cover_begin_keyed(p3_ctx *ctx, uint32_t cov_threshold, uint64_t owner_distinct, uint32_t *n_slices);
+int p3_mg_cover_key_round(p3_ctx *ctx, uint32_t cov_threshold);
 int p3_mg_cover_rebin_begin(p3_ctx *ctx);
 int p3_mg_cover_rebin_end(p3_ctx *ctx);
 int p3_mg_solid_next_round(p3_ctx *ctx);
@@ -304,6 +316,8 @@ int p3_count_substage_ms(p3_ctx *ctx, float ms[4], uint32_t *parts, uint64_t *ch
  * environment variable P3_PROBE_STATS set, else 0); out[2], out[3] = the same for a lookup of every distinct solid k-mer
  * in the solid set. p3_table_capacity: count table slots and partitions, solid set slots and partitions. */
 int p3_probe_stats(p3_ctx *ctx, double out[4]);
+/* number of partitions the binned count table of this capacity is cut into (what the multi-GPU driver plans key-range rounds with) */
+uint32_t p3_table_partitions(uint64_t table_slots);
 int p3_table_capacity(p3_ctx *ctx, uint64_t out[4]);
 /* kernels launched by this context since creation (for bench.py's gpu_launches) */
 uint64_t p3_launch_count(p3_ctx *ctx);

@@ -27,10 +27,11 @@ SYMBOLS = [
     "p3_mg_bloom_buffer", "p3_mg_bloom_bin", "p3_mg_bloom_apply", "p3_mg_bloom_direct", "p3_mg_filter",
     "p3_mg_makebf_done", "p3_device_mem_used",
     "p3_mg_count_next_round", "p3_mg_cover_rebin_begin", "p3_mg_cover_rebin_end", "p3_mg_solid_next_round", "p3_mg_bloom_bin_range",
+    "p3_mg_count_begin_keyed", "p3_mg_key_round_begin", "p3_mg_cover_begin_keyed", "p3_mg_cover_key_round",
     "p3_mg_long_solid", "p3_mg_long_begin", "p3_mg_long_send", "p3_mg_long_recv", "p3_mg_long_finish",
     "p3_load_file", "p3_reads_free", "p3_reads_count", "p3_reads_all_bases", "p3_reads_total_bases",
     "p3_reads_offsets", "p3_reads_packed", "p3_reads_nmask", "p3_reads_ascii", "p3_assemble_file", "p3_walk_table", "p3_node_coverage",
-    "p3_assemble_hot_path", "p3_assemble_hot_path_to_host", "p3_stage_ms", "p3_count_substage_ms", "p3_launch_count", "p3_bf_params", "p3_probe_stats", "p3_table_capacity",
+    "p3_assemble_hot_path", "p3_assemble_hot_path_to_host", "p3_stage_ms", "p3_count_substage_ms", "p3_launch_count", "p3_bf_params", "p3_probe_stats", "p3_table_capacity", "p3_table_partitions",
 ]
 
 
@@ -114,6 +115,12 @@ def lib():
         L.p3_mg_bloom_buffer.argtypes = [vp, u64, C.POINTER(vp)]
         L.p3_mg_bloom_bin.argtypes = [vp, u32, vp, u64, vp]
         L.p3_mg_bloom_bin_range.argtypes = [vp, u32, vp, u64, vp, u64, u64]
+        L.p3_table_partitions.restype = u32
+        L.p3_table_partitions.argtypes = [u64]
+        L.p3_mg_count_begin_keyed.argtypes = [vp, u64, u64, u64, u64, u32]
+        L.p3_mg_key_round_begin.argtypes = [vp, u32]
+        L.p3_mg_cover_begin_keyed.argtypes = [vp, u32, u64, C.POINTER(u32)]
+        L.p3_mg_cover_key_round.argtypes = [vp, u32]
         L.p3_mg_long_solid.argtypes = [vp, u32, C.POINTER(u64)]
         L.p3_mg_long_begin.argtypes = [vp, u64, u64, C.c_double, u64, C.POINTER(u64), C.POINTER(u64)]
         L.p3_mg_long_send.argtypes = [vp, u64]

@@ -244,7 +244,10 @@ __global__ void __launch_bounds__(kScatterThreads, 3)
 scatter21_kernel(const uint64_t *__restrict__ packed, const uint32_t *__restrict__ rend,
                  const uint32_t *__restrict__ nmask, uint64_t w0, uint64_t w1, uint32_t P,
                  unsigned long long *cursor, uint64_t *__restrict__ bkeys, uint32_t *__restrict__ bword,
-                 uint32_t *__restrict__ valid_plane, uint64_t tag, Stats *st, PeerOut peer = PeerOut(), uint64_t cap = 0) {
+                 uint32_t *__restrict__ valid_plane, uint64_t tag, Stats *st, PeerOut peer = PeerOut(), uint64_t cap = 0,
+                 uint32_t flt_lo = 0, uint32_t flt_hi = 0, uint32_t flt_P = 0) {
+    // flt_hi > 0 (multi-GPU key-range rounds): only the keys whose TABLE partition (of flt_P) lies in [flt_lo, flt_hi)
+    // are binned in this pass; the valid plane is written for every position as always
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ScatterSmem21 &sm = *reinterpret_cast<ScatterSmem21 *>(smem_raw);
     const uint64_t W21 = ~0ULL << (64 - (kShortK - 1));
@@ -283,6 +286,10 @@ scatter21_kernel(const uint64_t *__restrict__ packed, const uint32_t *__restrict
                 const uint64_t f = window(hi, lo, o) >> (64 - 2 * kShortK);
                 const uint64_t r = (o ? ((rlo >> (2 * o)) | (rhi << (64 - 2 * o))) : rlo) & kKey42;
                 const uint64_t key = f <= r ? f : r;
+                if (PEER && flt_hi) {
+                    const uint32_t tp = part_of(fmix64(key), flt_P);
+                    if (tp < flt_lo || tp >= flt_hi) continue;
+                }
                 const uint32_t pt = pid_of<PMODE>(key, P);
                 kp[q] = key | ((uint64_t)pt << kSmPtShift);
                 rk[q >> 1] |= atomicAdd(&sm.hist[pt], 1u) << (16 * (q & 1));
@@ -1348,24 +1355,32 @@ static void launch_scatter21_local(p3_ctx *c, unsigned sblocks, uint64_t w0, uin
         c->d_packed, c->d_rend, HAS_MASK ? c->d_nmask : nullptr, w0, w1, P, c->d_cursor, c->d_bkeys, c->d_bword, c->d_valid, 0, c->d_stats, PeerOut(), cap);
 }
 }  // extern "C++"
+// bidx (optional): index stream to use instead of c->d_bidx; first: where the sweep starts in the bins' index space
+// (multi-GPU key-range rounds: the bins of partitions [p_lo, p_hi) only, addressed with their absolute indices)
 static int launch_insert_bins(p3_ctx *c, const uint64_t *keys, uint64_t n, uint64_t cap,
-                              const unsigned long long *bin_end, const unsigned long long *n_dev) {
-    CU(cudaMemsetAsync(&c->d_stats->work, 0, sizeof(unsigned long long), c->stream));
+                              const unsigned long long *bin_end, const unsigned long long *n_dev,
+                              uint32_t *bidx = nullptr, unsigned long long first = 0) {
+    if (!bidx) bidx = c->d_bidx;
+    auto set_work = [&]() -> cudaError_t {
+        return first ? cudaMemcpyAsync(&c->d_stats->work, &first, sizeof(first), cudaMemcpyHostToDevice, c->stream)
+                     : cudaMemsetAsync(&c->d_stats->work, 0, sizeof(unsigned long long), c->stream);
+    };
+    CU(set_work());
     if (c->probe_stats) {
-        if (cap) insert_find_kernel<true, false><<<c->grid(8), 256, 0, c->stream>>>(keys, n, c->table(), c->d_stats, c->d_bidx, cap, bin_end, n_dev);
-        else insert_find_kernel<true, true><<<c->grid(8), 256, 0, c->stream>>>(keys, n, c->table(), c->d_stats, c->d_bidx, cap, bin_end, n_dev);
+        if (cap) insert_find_kernel<true, false><<<c->grid(8), 256, 0, c->stream>>>(keys, n, c->table(), c->d_stats, bidx, cap, bin_end, n_dev);
+        else insert_find_kernel<true, true><<<c->grid(8), 256, 0, c->stream>>>(keys, n, c->table(), c->d_stats, bidx, cap, bin_end, n_dev);
     } else if (cap) {
         static const int variant = getenv("P3_FIND_BATCH") ? atoi(getenv("P3_FIND_BATCH")) : kSweepBatch;   // experiment knob
-        if (variant == 8) insert_find_kernel<false, false, 8><<<c->grid(2), 256, 0, c->stream>>>(keys, n, c->table(), c->d_stats, c->d_bidx, cap, bin_end, n_dev);
-        else if (variant == 2) insert_find_kernel<false, false, 2><<<c->grid(6), 256, 0, c->stream>>>(keys, n, c->table(), c->d_stats, c->d_bidx, cap, bin_end, n_dev);
-        else if (variant == 4) insert_find_kernel<false, false, 4><<<c->grid(4), 256, 0, c->stream>>>(keys, n, c->table(), c->d_stats, c->d_bidx, cap, bin_end, n_dev);
-        else insert_find_kernel<false, false><<<c->grid(8), 256, 0, c->stream>>>(keys, n, c->table(), c->d_stats, c->d_bidx, cap, bin_end, n_dev);
+        if (variant == 8) insert_find_kernel<false, false, 8><<<c->grid(2), 256, 0, c->stream>>>(keys, n, c->table(), c->d_stats, bidx, cap, bin_end, n_dev);
+        else if (variant == 2) insert_find_kernel<false, false, 2><<<c->grid(6), 256, 0, c->stream>>>(keys, n, c->table(), c->d_stats, bidx, cap, bin_end, n_dev);
+        else if (variant == 4) insert_find_kernel<false, false, 4><<<c->grid(4), 256, 0, c->stream>>>(keys, n, c->table(), c->d_stats, bidx, cap, bin_end, n_dev);
+        else insert_find_kernel<false, false><<<c->grid(8), 256, 0, c->stream>>>(keys, n, c->table(), c->d_stats, bidx, cap, bin_end, n_dev);
     } else {
-        insert_find_kernel<false, true><<<c->grid(8), 256, 0, c->stream>>>(keys, n, c->table(), c->d_stats, c->d_bidx, cap, bin_end, n_dev);
+        insert_find_kernel<false, true><<<c->grid(8), 256, 0, c->stream>>>(keys, n, c->table(), c->d_stats, bidx, cap, bin_end, n_dev);
     }
-    CU(cudaMemsetAsync(&c->d_stats->work, 0, sizeof(unsigned long long), c->stream));
-    if (cap) insert_add_kernel<false><<<c->grid(8), 256, 0, c->stream>>>(c->d_bidx, keys, n, c->table(), c->ovf(), c->d_stats, cap, bin_end, n_dev);
-    else insert_add_kernel<true><<<c->grid(8), 256, 0, c->stream>>>(c->d_bidx, keys, n, c->table(), c->ovf(), c->d_stats, cap, bin_end, n_dev);
+    CU(set_work());
+    if (cap) insert_add_kernel<false><<<c->grid(8), 256, 0, c->stream>>>(bidx, keys, n, c->table(), c->ovf(), c->d_stats, cap, bin_end, n_dev);
+    else insert_add_kernel<true><<<c->grid(8), 256, 0, c->stream>>>(bidx, keys, n, c->table(), c->ovf(), c->d_stats, cap, bin_end, n_dev);
     c->launches += 2;
     CU(cudaGetLastError());
     return P3_OK;
@@ -1501,18 +1516,19 @@ static void count_binned_times(p3_ctx *c) {
 
 // allocate (or reuse) and clear the count table: partitions of ~24 MB each in binned mode so that
 // one partition plus the streaming bins stay in L2
+// partitions of the binned count table for a given capacity (also what p3_table_partitions tells the multi-GPU driver)
+static uint32_t table_partitions(uint64_t table_slots) {
+    // ~48 MB per partition: the insert sweep is insensitive to the partition size between 17 and 50 MB (measured), while
+    // every tile sort pays a scan + one global claim per partition and tile (scatter21: 33 / 42 / 53 / 72 ms at 350 / 520 /
+    // 696 / 1000 partitions)
+    uint64_t part_bytes = 48ull << 20;
+    if (const char *e = getenv("P3_PART_MB")) part_bytes = std::max<uint64_t>(strtoull(e, nullptr, 10), 1) << 20;
+    uint64_t want = (table_slots * 8 + part_bytes - 1) / part_bytes;
+    if (const char *e = getenv("P3_PARTS")) want = strtoull(e, nullptr, 10);
+    return (uint32_t)std::min<uint64_t>(std::max<uint64_t>(want, 1), kMaxParts);
+}
 static int setup_table(p3_ctx *c, uint64_t table_slots) {
-    uint32_t P = 1;
-    if (c->binned) {
-        // ~48 MB per partition: the insert sweep is insensitive to the partition size between 17 and 50 MB (measured), while
-        // every tile sort pays a scan + one global claim per partition and tile (scatter21: 33 / 42 / 53 / 72 ms at 350 / 520 /
-        // 696 / 1000 partitions)
-        uint64_t part_bytes = 48ull << 20;
-        if (const char *e = getenv("P3_PART_MB")) part_bytes = std::max<uint64_t>(strtoull(e, nullptr, 10), 1) << 20;
-        uint64_t want = (table_slots * 8 + part_bytes - 1) / part_bytes;
-        if (const char *e = getenv("P3_PARTS")) want = strtoull(e, nullptr, 10);
-        P = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(want, 1), kMaxParts);
-    }
+    uint32_t P = c->binned ? table_partitions(table_slots) : 1;
     uint64_t nbp = ((table_slots + 3) / 4 + P - 1) / P;
     if (nbp == 0) nbp = 1;
     if (nbp >= (1ull << 32)) return fail(P3_ERR_ARG, "count table partition too large");
@@ -2198,6 +2214,7 @@ int p3_probe_stats(p3_ctx *c, double out[4]) {
     return P3_OK;
 }
 // out[0..3] = count table slots, count table partitions, solid set slots, solid set partitions
+uint32_t p3_table_partitions(uint64_t table_slots) { return table_partitions(table_slots); }
 int p3_table_capacity(p3_ctx *c, uint64_t out[4]) {
     if (!c || !out) return fail(P3_ERR_ARG, "p3_table_capacity: null argument");
     out[0] = c->nb * 4; out[1] = c->parts; out[2] = c->nbs * 4; out[3] = c->set_parts;

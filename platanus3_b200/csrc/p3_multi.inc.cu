@@ -130,6 +130,13 @@ struct MgState {   // per-context state of the multi-GPU path
     // A
     uint64_t chunk_words = 0, n_chunks = 0, capA = 0, part_cap = 0;
     bool multi_round = false;    // the owner inserted in several rounds: the bins hold the last round only (human-scale inputs)
+    // key-range rounds: round r counts the keys of table partitions [p_lo, p_hi) only — ALL their occurrences, so the counts
+    // of those partitions are final when the round's insert ends and its verdicts can follow at once. The bins hold the
+    // partitions of one round and are addressed with absolute indices through pointers shifted back by p_lo * part_cap.
+    uint32_t key_rounds = 1, p_lo = 0, p_hi = 0; bool round_bins_valid = false;
+    uint64_t *bk(const p3_ctx *c) const;   // partition bins as the kernels of the current round see them
+    uint32_t *bw(const p3_ctx *c) const;
+    uint32_t *bi(const p3_ctx *c) const;
     // B1
     uint64_t *d_sing = nullptr; uint64_t cap_sing = 0; uint64_t capB = 0; uint32_t n_slices = 0;
     // B2
@@ -139,6 +146,9 @@ struct MgState {   // per-context state of the multi-GPU path
     PeerCtl *ctl() const { return reinterpret_cast<PeerCtl *>(arena); }
 };
 static CtxStates<MgState> g_mg;
+uint64_t *MgState::bk(const p3_ctx *c) const { return key_rounds > 1 ? c->d_bkeys - (uint64_t)p_lo * part_cap : c->d_bkeys; }
+uint32_t *MgState::bw(const p3_ctx *c) const { return key_rounds > 1 ? c->d_bword - (uint64_t)p_lo * part_cap : c->d_bword; }
+uint32_t *MgState::bi(const p3_ctx *c) const { return key_rounds > 1 ? c->d_bidx - (uint64_t)p_lo * part_cap : c->d_bidx; }
 // multi-word k-mers (see the end of this file)
 struct LongMg {
     uint64_t *d_store = nullptr; uint64_t cap_store = 0;    // bytes
@@ -304,7 +314,7 @@ static int mg_publish(p3_ctx *c, MgState &m, int set) {
 // will own (all ranks' positions / n_ranks for a hash partition) — sizes the partition bins, which hold every
 // received record until the one insert sweep. n_chunks / chunk_words: the same on every rank (ranks with fewer words
 // send empty chunks).
-int p3_mg_count_begin(p3_ctx *c, uint64_t table_slots, uint64_t owner_positions, uint64_t chunk_words, uint64_t n_chunks) {
+static int mg_count_begin(p3_ctx *c, uint64_t table_slots, uint64_t owner_positions, uint64_t chunk_words, uint64_t n_chunks, uint32_t key_rounds) {
     MgState *mp;
     int rc = mg_ready(c, &mp, "p3_mg_count_begin");
     if (rc) return rc;
@@ -322,15 +332,45 @@ int p3_mg_count_begin(p3_ctx *c, uint64_t table_slots, uint64_t owner_positions,
     if (m.capA < per_region) return fail(P3_ERR_ARG, "p3_mg_count_begin: receive set too small for this chunk size (raise set_bytes or lower chunk_words)");
     const uint32_t P = c->parts;
     m.part_cap = ((uint64_t)((double)owner_positions / P * 1.03) + 8192 + kSweepChunk - 1) / kSweepChunk * kSweepChunk;
-    CU(ensure(c->d_bkeys, c->cap_bkeys, sizeof(uint64_t) * m.part_cap * P));
-    CU(ensure(c->d_bword, c->cap_bword, sizeof(uint32_t) * m.part_cap * P));
-    CU(ensure(c->d_bidx, c->cap_bidx, sizeof(uint32_t) * m.part_cap * P));
+    m.key_rounds = std::max<uint32_t>(std::min<uint32_t>(key_rounds, P), 1);
+    m.p_lo = 0; m.p_hi = P; m.round_bins_valid = false;
+    const uint64_t P_bins = m.key_rounds > 1 ? (P + m.key_rounds - 1) / m.key_rounds + 1 : P;   // partitions whose bins exist at a time
+    CU(ensure(c->d_bkeys, c->cap_bkeys, sizeof(uint64_t) * m.part_cap * P_bins));
+    CU(ensure(c->d_bword, c->cap_bword, sizeof(uint32_t) * m.part_cap * P_bins));
+    CU(ensure(c->d_bidx, c->cap_bidx, sizeof(uint32_t) * m.part_cap * P_bins));
     CU(ensure(c->d_valid, c->cap_valid, sizeof(uint32_t) * (c->n_words + 1)));
     init_cursors_kernel<<<1, 256, 0, c->stream>>>(c->d_cursor, P, m.part_cap);   // the bins persist over the chunks
     c->launches++;
     CU(cudaEventRecord(c->ev[0], c->stream));
     c->bins_valid = false; c->have_counts = false; c->pos_on_host = true; c->binned_pos = 0; c->n_chunks = 0;
-    m.multi_round = false;
+    m.multi_round = m.key_rounds > 1;
+    return P3_OK;
+}
+int p3_mg_count_begin(p3_ctx *c, uint64_t table_slots, uint64_t owner_positions, uint64_t chunk_words, uint64_t n_chunks) {
+    return mg_count_begin(c, table_slots, owner_positions, chunk_words, n_chunks, 1);
+}
+// Key-range rounds for inputs whose records an owner cannot hold at once: owner_positions is the estimate for ALL rounds
+// (a partition's bin must hold all occurrences of its keys), the bins exist for one round's partitions at a time. Per
+// round r: p3_mg_key_round_begin(r); every chunk: p3_mg_count_send (only the keys of the round's partitions travel), sync,
+// p3_mg_count_recv; p3_mg_count_finish; then the round's verdicts (p3_mg_cover_begin_keyed once, p3_mg_cover_key_round,
+// slices of p3_mg_cover_send / _recv); p3_mg_count_next_round before the next round; p3_mg_count_end after the last.
+int p3_mg_count_begin_keyed(p3_ctx *c, uint64_t table_slots, uint64_t owner_positions, uint64_t chunk_words, uint64_t n_chunks, uint32_t n_rounds) {
+    if (n_rounds < 2) return fail(P3_ERR_ARG, "p3_mg_count_begin_keyed: at least 2 rounds (one round: p3_mg_count_begin)");
+    return mg_count_begin(c, table_slots, owner_positions, chunk_words, n_chunks, n_rounds);
+}
+int p3_mg_key_round_begin(p3_ctx *c, uint32_t round) {
+    MgState *mp;
+    int rc = mg_ready(c, &mp, "p3_mg_key_round_begin");
+    if (rc) return rc;
+    MgState &m = *mp;
+    if (m.key_rounds < 2 || round >= m.key_rounds) return fail(P3_ERR_ARG, "p3_mg_key_round_begin: round out of range");
+    const uint32_t P = c->parts;
+    m.p_lo = (uint32_t)((uint64_t)P * round / m.key_rounds);
+    m.p_hi = (uint32_t)((uint64_t)P * (round + 1) / m.key_rounds);
+    m.round_bins_valid = false;
+    init_cursors_kernel<<<1, 256, 0, c->stream>>>(c->d_cursor, P, m.part_cap);   // absolute: partitions outside the round stay empty
+    c->launches++;
+    CU(cudaGetLastError());
     return P3_OK;
 }
 // bin chunk `ch` of this rank's reads by owner, straight into the owners' receive set ch % 2 (peer stores)
@@ -355,8 +395,9 @@ int p3_mg_count_send(p3_ctx *c, uint64_t ch) {
         }
         const unsigned sblocks = (unsigned)std::min<uint64_t>((w1 - w0 + kTileWords - 1) / kTileWords, (uint64_t)c->n_sm * 3);
         const uint64_t tag = (uint64_t)m.my_rank << kRecRankShift;
-        if (c->d_nmask) scatter21_kernel<true, 1, true><<<sblocks, kScatterThreads, kSmem21, c->stream>>>(c->d_packed, c->d_rend, c->d_nmask, w0, w1, m.n_ranks, m.d_sent, nullptr, nullptr, c->d_valid, tag, c->d_stats, po, m.capA);
-        else scatter21_kernel<false, 1, true><<<sblocks, kScatterThreads, kSmem21, c->stream>>>(c->d_packed, c->d_rend, nullptr, w0, w1, m.n_ranks, m.d_sent, nullptr, nullptr, c->d_valid, tag, c->d_stats, po, m.capA);
+        const uint32_t flo = m.key_rounds > 1 ? m.p_lo : 0, fhi = m.key_rounds > 1 ? m.p_hi : 0;   // key-range rounds: this round's partitions only
+        if (c->d_nmask) scatter21_kernel<true, 1, true><<<sblocks, kScatterThreads, kSmem21, c->stream>>>(c->d_packed, c->d_rend, c->d_nmask, w0, w1, m.n_ranks, m.d_sent, nullptr, nullptr, c->d_valid, tag, c->d_stats, po, m.capA, flo, fhi, c->parts);
+        else scatter21_kernel<false, 1, true><<<sblocks, kScatterThreads, kSmem21, c->stream>>>(c->d_packed, c->d_rend, nullptr, w0, w1, m.n_ranks, m.d_sent, nullptr, nullptr, c->d_valid, tag, c->d_stats, po, m.capA, flo, fhi, c->parts);
         c->launches++;
         CU(cudaGetLastError());
     }
@@ -373,7 +414,7 @@ int p3_mg_count_recv(p3_ctx *c, uint64_t ch) {
     const uint64_t n = (uint64_t)m.n_ranks * m.capA;
     const unsigned sblocks = (unsigned)std::min<uint64_t>((n + kTilePos - 1) / kTilePos, (uint64_t)c->n_sm * 3);
     scatter_rec_kernel<0, 4><<<sblocks, kScatterThreads, kSmemA4, c->stream>>>(
-        reinterpret_cast<const uint64_t *>(blk), blk + n * 8, n, c->parts, c->d_cursor, c->d_bkeys, c->d_bword, m.part_cap, nullptr,
+        reinterpret_cast<const uint64_t *>(blk), blk + n * 8, n, c->parts, c->d_cursor, m.bk(c), m.bw(c), m.part_cap, nullptr,
         m.capA, &m.ctl()->count[set][0], c->d_stats);
     c->launches++;
     CU(cudaGetLastError());
@@ -391,7 +432,8 @@ int p3_mg_count_finish(p3_ctx *c) {
     CU(cudaMemcpyAsync(c->d_binmeta, c->d_cursor, sizeof(unsigned long long) * P, cudaMemcpyDeviceToDevice, c->stream));
     CU(cudaEventRecord(c->ev[10], c->stream));
     c->bin_cap = m.part_cap; c->bin_n = (uint64_t)P * m.part_cap;
-    rc = launch_insert_bins(c, c->d_bkeys, c->bin_n, c->bin_cap, c->d_binmeta, nullptr);
+    if (m.key_rounds > 1) rc = launch_insert_bins(c, m.bk(c), (uint64_t)m.p_hi * m.part_cap, c->bin_cap, c->d_binmeta, nullptr, m.bi(c), (unsigned long long)m.p_lo * m.part_cap);
+    else rc = launch_insert_bins(c, c->d_bkeys, c->bin_n, c->bin_cap, c->d_binmeta, nullptr);
     if (rc) return rc;
     c->launches++;
     CU(cudaEventRecord(c->ev[1], c->stream));
@@ -406,11 +448,12 @@ int p3_mg_count_next_round(p3_ctx *c) {
     int rc = mg_ready(c, &mp, "p3_mg_count_next_round");
     if (rc) return rc;
     MgState &m = *mp;
-    accum_cursors_kernel<<<1, 256, 0, c->stream>>>(c->d_cursor, c->parts, m.part_cap, c->d_stats);
+    // the bin ends as p3_mg_count_finish saved them (d_cursor itself is scratch of the verdict stage's clears in between)
+    accum_cursors_kernel<<<1, 256, 0, c->stream>>>(c->d_binmeta, c->parts, m.part_cap, c->d_stats);
     init_cursors_kernel<<<1, 256, 0, c->stream>>>(c->d_cursor, c->parts, m.part_cap);
     c->launches += 2;
     CU(cudaGetLastError());
-    m.multi_round = true;
+    m.multi_round = true; m.round_bins_valid = false;
     return P3_OK;
 }
 // waits for the stage and checks it; the counts of the owned keys are final afterwards
@@ -453,12 +496,12 @@ static int ensure_planes(p3_ctx *c) {
 // coverage plane := every valid 21-mer position. The owners send their verdicts in *n_slices rounds so that a round
 // fits the receive regions; owner_distinct = the largest number of distinct owned 21-mers of any rank (so that every
 // rank computes the same number of rounds).
-int p3_mg_cover_begin(p3_ctx *c, uint32_t cov_threshold, uint64_t owner_distinct, uint32_t *n_slices) {
+static int mg_cover_begin(p3_ctx *c, uint32_t cov_threshold, uint64_t owner_distinct, uint32_t *n_slices, bool keyed) {
     MgState *mp;
     int rc = mg_ready(c, &mp, "p3_mg_cover_begin");
     if (rc) return rc;
     MgState &m = *mp;
-    if (!c->have_counts || (!c->bins_valid && !m.multi_round)) return fail(P3_ERR_STATE, "p3_mg_cover_begin: run the count stage first");
+    if (keyed ? m.key_rounds < 2 : (!c->have_counts || (!c->bins_valid && !m.multi_round))) return fail(P3_ERR_STATE, "p3_mg_cover_begin: run the count stage first");
     rc = ensure_planes(c);
     if (rc) return rc;
     CU(cudaMemcpyAsync(c->d_good21, c->d_valid, sizeof(uint32_t) * c->n_words, cudaMemcpyDeviceToDevice, c->stream));
@@ -470,15 +513,35 @@ int p3_mg_cover_begin(p3_ctx *c, uint32_t cov_threshold, uint64_t owner_distinct
     uint64_t want_slices = std::max<uint64_t>((worst + per_slice - 1) / per_slice, 1);
     want_slices = std::max<uint64_t>(want_slices, (worst + (1ull << 28) - 1) >> 28);   // the owner's verdict list stays below 2^28 records (2 GB)
     if (const char *e = getenv("P3_MG_COVER_SLICES")) want_slices = std::max<uint64_t>(want_slices, strtoull(e, nullptr, 10));   // test knob
-    m.n_slices = (uint32_t)std::min<uint64_t>(want_slices, c->parts);
+    m.n_slices = (uint32_t)std::min<uint64_t>(want_slices, keyed ? std::max<uint32_t>(c->parts / m.key_rounds, 1) : c->parts);
     CU(ensure(m.d_sing, m.cap_sing, sizeof(uint64_t) * std::min<uint64_t>(worst / m.n_slices * 5 / 4 + (1u << 20), m.capB * m.n_ranks)));
     if (n_slices) *n_slices = m.n_slices;
     if (c->bins_valid) {
         rc = below_bits(c, cov_threshold);      // "count < threshold" of every owned slot as one bit: what the verdict sweep asks
         if (rc) return rc;
     }
-    CU(cudaMemsetAsync(&c->d_stats->err_bin_overflow, 0, sizeof(unsigned), c->stream));
+    if (!keyed) CU(cudaMemsetAsync(&c->d_stats->err_bin_overflow, 0, sizeof(unsigned), c->stream));   // keyed: the count is still running, p3_mg_count_end reads the flag
     CU(cudaEventRecord(c->ev[2], c->stream));
+    return P3_OK;
+}
+int p3_mg_cover_begin(p3_ctx *c, uint32_t cov_threshold, uint64_t owner_distinct, uint32_t *n_slices) {
+    return mg_cover_begin(c, cov_threshold, owner_distinct, n_slices, false);
+}
+// key-range rounds: once, after the FIRST round's p3_mg_count_finish (the valid plane is complete then: every round scans
+// all reads). owner_distinct = upper estimate of the distinct keys ONE round inserts on any rank.
+int p3_mg_cover_begin_keyed(p3_ctx *c, uint32_t cov_threshold, uint64_t owner_distinct, uint32_t *n_slices) {
+    return mg_cover_begin(c, cov_threshold, owner_distinct, n_slices, true);
+}
+// key-range rounds, after every round's p3_mg_count_finish: the counts of the round's partitions are final; their
+// "count < threshold" bits are taken and the round's bins (records + index stream) feed the verdict slices
+int p3_mg_cover_key_round(p3_ctx *c, uint32_t cov_threshold) {
+    MgState *mp;
+    int rc = mg_ready(c, &mp, "p3_mg_cover_key_round");
+    if (rc) return rc;
+    if (mp->key_rounds < 2) return fail(P3_ERR_STATE, "p3_mg_cover_key_round: key-range rounds only");
+    rc = below_bits(c, cov_threshold);
+    if (rc) return rc;
+    mp->round_bins_valid = true;
     return P3_OK;
 }
 // Several insert rounds (p3_mg_count_next_round): the bins no longer hold the records, so every round of chunks is sent
@@ -514,8 +577,9 @@ int p3_mg_cover_send(p3_ctx *c, uint32_t cov_threshold, uint32_t slice) {
     MgState &m = *mp;
     if (slice >= m.n_slices) return fail(P3_ERR_ARG, "p3_mg_cover_send: slice out of range");
     const int set = (int)(slice & 1);
-    const uint32_t P = c->parts;
-    const uint32_t p0 = (uint32_t)((uint64_t)P * slice / m.n_slices), p1 = (uint32_t)((uint64_t)P * (slice + 1) / m.n_slices);
+    // the slice's share of the partitions whose bins are there: all of them, or the current key-range round's
+    const uint32_t pa = m.key_rounds > 1 ? m.p_lo : 0, pn = m.key_rounds > 1 ? m.p_hi - m.p_lo : c->parts;
+    const uint32_t p0 = pa + (uint32_t)((uint64_t)pn * slice / m.n_slices), p1 = pa + (uint32_t)((uint64_t)pn * (slice + 1) / m.n_slices);
     CU(cudaMemsetAsync(m.d_sent, 0, sizeof(unsigned long long) * (kMaxParts + 1), c->stream));
     CU(cudaMemsetAsync(&c->d_stats->n_export, 0, sizeof(unsigned long long), c->stream));
     if (p1 > p0) {
@@ -526,8 +590,8 @@ int p3_mg_cover_send(p3_ctx *c, uint32_t cov_threshold, uint32_t slice) {
         const size_t smem = (size_t)kBinThreads * kPosKpt * 6 + 20;
         const uint64_t T = (uint64_t)kBinThreads * kPosKpt;
         unsigned blocks = (unsigned)std::min<uint64_t>((n_end - first + T - 1) / T, (uint64_t)c->n_sm * 4);
-        if (c->bins_valid)
-            pos_bin_kernel<0, true><<<blocks, kBinThreads, smem, c->stream>>>(c->table(), c->d_bkeys, c->d_bword, c->d_bidx, c->d_below, n_end, m.part_cap, c->d_binmeta, nullptr,
+        if (c->bins_valid || m.round_bins_valid)
+            pos_bin_kernel<0, true><<<blocks, kBinThreads, smem, c->stream>>>(c->table(), m.bk(c), m.bw(c), m.bi(c), c->d_below, n_end, m.part_cap, c->d_binmeta, nullptr,
                                                                        cov_threshold, c->ovf(), c->d_stats, 27, 1, nullptr, m.cap_sing / sizeof(uint64_t), nullptr, m.d_sing);
         else   // re-binned round: no index stream, the keys are looked up in the table
             pos_bin_kernel<0, false><<<blocks, kBinThreads, smem, c->stream>>>(c->table(), c->d_bkeys, c->d_bword, nullptr, nullptr, n_end, m.part_cap, c->d_binmeta, nullptr,
@@ -554,7 +618,10 @@ int p3_mg_cover_recv(p3_ctx *c, uint32_t slice) {
     in.rec = reinterpret_cast<const uint64_t *>(m.set_ptr(m.my_rank, set));
     in.n = (uint64_t)m.n_ranks * m.capB; in.in_cap = m.capB; in.in_end = &m.ctl()->count[set][0];
     // what a round may deliver: the regions' capacity at most, normally this rank's share of the owners' verdicts
-    const uint64_t n_expect = std::min<uint64_t>(in.n, (c->h_stats.n_cand / std::max<uint32_t>(m.n_slices, 1)) * 3 / 2 + (1u << 20));
+    // distinct keys the verdicts can come from: known after the count, or (key-range rounds: the count is still running) what one
+    // round's share of the table can hold
+    const uint64_t n_keys = m.key_rounds > 1 ? (uint64_t)((double)c->nb * 4 * 0.7 / m.key_rounds) : c->h_stats.n_cand;
+    const uint64_t n_expect = std::min<uint64_t>(in.n, (n_keys / std::max<uint32_t>(m.n_slices, 1)) * 3 / 2 + (1u << 20));
     rc = plane_clear_job<1>(c, in, n_expect, 0, c->d_good21, c->n_words * 32, false, nullptr);
     if (rc) return rc;
     CU(cudaEventRecord(c->ev[3], c->stream));

@@ -321,8 +321,13 @@ def run_hot_path(ctxs, comm, k, filter_size, num_hashes, table_slots, solid_slot
 
     mark("start")
     # ---- A: count ------------------------------------------------------------------------------
+    # rounds over key ranges need at least one table partition per round; otherwise (tiny tables) rounds of read chunks
+    keyed = n_rounds > 1 and os.environ.get("P3_MG_ROUNDS", "keys") != "chunks" and int(L.p3_table_partitions(table_slots)) >= n_rounds
     for c in ctxs:
-        _check(L.p3_mg_count_begin(c.h, table_slots, owner_positions, cw, n_chunks))
+        if keyed:
+            _check(L.p3_mg_count_begin_keyed(c.h, table_slots, owner_total, cw, n_chunks, n_rounds))
+        else:
+            _check(L.p3_mg_count_begin(c.h, table_slots, owner_positions, cw, n_chunks))
     stage_start()
 
     def count_chunks(chs):
@@ -333,27 +338,9 @@ def run_hot_path(ctxs, comm, k, filter_size, num_hashes, table_slots, solid_slot
             for c in ctxs:
                 _check(L.p3_mg_count_recv(c.h, ch))
 
-    for r, chs in enumerate(rounds):
-        if r:
-            for c in ctxs:
-                _check(L.p3_mg_count_next_round(c.h))
-        count_chunks(chs)
-        for c in ctxs:
-            _check(L.p3_mg_count_finish(c.h))
-    mark("count")
-    for c, st in zip(ctxs, stats):
-        _check(L.p3_mg_count_end(c.h))
-        a, b = C.c_uint64(), C.c_uint64()
-        _check(L.p3_short_kmer_stats(c.h, C.byref(a), C.byref(b)))
-        st.update(owned_positions=a.value, owned_distinct21=b.value, exchange="peer" if peer else "nccl")
-        st["owner_count_ms"] = {kk: v for kk, v in c.count_substage_ms().items() if kk in ("scatter", "insert")}
-    # ---- B1: verdicts back to the reads ---------------------------------------------------------------
-    owner_distinct, = comm.all_max([[st["owned_distinct21"]] for st in stats])
     n_slices = 1
-    for c in ctxs:
-        ns = C.c_uint32()
-        _check(L.p3_mg_cover_begin(c.h, cov_threshold, owner_distinct, C.byref(ns)))
-        n_slices = ns.value
+    cover_ms_events = []
+
     def cover_slices():
         stage_start()
         for sl in range(n_slices):
@@ -363,17 +350,63 @@ def run_hot_path(ctxs, comm, k, filter_size, num_hashes, table_slots, solid_slot
             for c in ctxs:
                 _check(L.p3_mg_cover_recv(c.h, sl))
 
-    if n_rounds == 1:
-        cover_slices()
-    else:       # the bins hold one round: send and sort every round's records again, then that round's verdicts
-        for chs in rounds:
+    if keyed:
+        # rounds over key ranges: every round scans all reads, only the keys of the round's table partitions travel; their
+        # counts are final when the round's insert ends, so the round's verdicts follow at once (nothing is sent twice)
+        for r in range(n_rounds):
+            if r:
+                for c in ctxs:
+                    _check(L.p3_mg_count_next_round(c.h))
+                stage_start()
             for c in ctxs:
-                _check(L.p3_mg_cover_rebin_begin(c.h))
-            stage_start()
+                _check(L.p3_mg_key_round_begin(c.h, r))
+            count_chunks(range(n_chunks))
+            for c in ctxs:
+                _check(L.p3_mg_count_finish(c.h))
+            e0 = torch.cuda.Event(enable_timing=True); e0.record()
+            if r == 0:
+                for c in ctxs:
+                    ns = C.c_uint32()
+                    _check(L.p3_mg_cover_begin_keyed(c.h, cov_threshold, int(table_slots * 0.7 / n_rounds) + 4096, C.byref(ns)))
+                    n_slices = ns.value
+            for c in ctxs:
+                _check(L.p3_mg_cover_key_round(c.h, cov_threshold))
+            cover_slices()
+            e1 = torch.cuda.Event(enable_timing=True); e1.record()
+            cover_ms_events.append((e0, e1))
+    else:
+        for r, chs in enumerate(rounds):
+            if r:
+                for c in ctxs:
+                    _check(L.p3_mg_count_next_round(c.h))
             count_chunks(chs)
             for c in ctxs:
-                _check(L.p3_mg_cover_rebin_end(c.h))
+                _check(L.p3_mg_count_finish(c.h))
+    mark("count")
+    for c, st in zip(ctxs, stats):
+        _check(L.p3_mg_count_end(c.h))
+        a, b = C.c_uint64(), C.c_uint64()
+        _check(L.p3_short_kmer_stats(c.h, C.byref(a), C.byref(b)))
+        st.update(owned_positions=a.value, owned_distinct21=b.value, exchange="peer" if peer else "nccl")
+        st["owner_count_ms"] = {kk: v for kk, v in c.count_substage_ms().items() if kk in ("scatter", "insert")}
+    # ---- B1: verdicts back to the reads ---------------------------------------------------------------
+    if not keyed:
+        owner_distinct, = comm.all_max([[st["owned_distinct21"]] for st in stats])
+        for c in ctxs:
+            ns = C.c_uint32()
+            _check(L.p3_mg_cover_begin(c.h, cov_threshold, owner_distinct, C.byref(ns)))
+            n_slices = ns.value
+        if n_rounds == 1:
             cover_slices()
+        else:       # rounds of read chunks (P3_MG_ROUNDS=chunks): send and sort every round's records again, then that round's verdicts
+            for chs in rounds:
+                for c in ctxs:
+                    _check(L.p3_mg_cover_rebin_begin(c.h))
+                stage_start()
+                count_chunks(chs)
+                for c in ctxs:
+                    _check(L.p3_mg_cover_rebin_end(c.h))
+                cover_slices()
     mark("coverage")
     # ---- B2: solid occurrences to their owners ---------------------------------------------------------
     n_long_chunks = 0
@@ -514,6 +547,10 @@ def run_hot_path(ctxs, comm, k, filter_size, num_hashes, table_slots, solid_slot
     mark("adjacency")
     torch.cuda.synchronize()
     ms = {marks[i][0]: marks[i - 1][1].elapsed_time(marks[i][1]) for i in range(1, len(marks))}
+    if cover_ms_events:      # key-range rounds interleave the verdicts with the count: book them where they belong
+        cov = sum(a.elapsed_time(b) for a, b in cover_ms_events)
+        ms["count"] -= cov
+        ms["coverage"] += cov
     ms["makebf"] = ms["dedupe"] + ms["bloom"]
     for st in stats:
         st["stage_ms"] = ms
@@ -521,4 +558,5 @@ def run_hot_path(ctxs, comm, k, filter_size, num_hashes, table_slots, solid_slot
         st["hbm_used_peak_bytes"] = mem_peak[0]
         st["n_chunks"], st["cover_slices"], st["set_bytes"] = n_chunks, n_slices, set_bytes
         st["insert_rounds"], st["bloom_passes"], st["long_chunks"] = n_rounds, n_pass, n_long_chunks
+        st["round_mode"] = "one round" if n_rounds == 1 else ("key ranges" if keyed else "read chunks")
     return stats

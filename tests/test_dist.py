@@ -278,11 +278,15 @@ def test_distributed_hot_path_two_real_gpus(oracle, tmp_path, exchange):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("world,exchange", [(1, "peer"), (3, "peer-sharded-filter"), (4, "nccl")])
-def test_distributed_insert_rounds_and_bloom_passes(oracle, world, exchange, monkeypatch):
-    """human-scale schedule at test size: the owners' bins are too small for all records, so the count, the verdicts
-    (records sent and sorted a second time, keys looked up in the finished table) and the de-duplication run in several
-    rounds of chunks, and the sharded Bloom adds in several passes — same results as the one-round schedule"""
+@pytest.mark.parametrize("world,exchange,mode", [(1, "peer", "keys"), (3, "peer-sharded-filter", "keys"), (4, "nccl", "keys"), (8, "peer", "keys"),
+                                                 (3, "peer-sharded-filter", "chunks"), (4, "nccl", "chunks")])
+def test_distributed_insert_rounds_and_bloom_passes(oracle, world, exchange, mode, monkeypatch):
+    """human-scale schedules at test size: the owners' bins are too small for all records, so the count and the verdicts
+    run in several rounds — over key ranges (every round scans all reads and moves the keys of a group of table
+    partitions, whose verdicts follow at once) or over read chunks (the records travel a second time for the verdicts,
+    keys looked up in the finished table) — the de-duplication in rounds of chunks and the sharded Bloom adds in several
+    passes: same results as the one-round schedule"""
+    monkeypatch.setenv("P3_MG_ROUNDS", mode)
     want_filter = "replicated"
     if exchange == "peer-sharded-filter":
         exchange, want_filter = "peer", "sharded"
@@ -290,7 +294,7 @@ def test_distributed_insert_rounds_and_bloom_passes(oracle, world, exchange, mon
         monkeypatch.setenv("P3_BLOOM_SEG_BITS", "4096")
         monkeypatch.setenv("P3_BINNED_CLEARS", "1")
     monkeypatch.setenv("P3_MG_EXCHANGE", exchange)
-    monkeypatch.setenv("P3_PARTS", "5")
+    monkeypatch.setenv("P3_PARTS", "12")
     monkeypatch.setenv("P3_MG_COVER_SLICES", "2")
     k = 32
     g = synth.random_genome(12000, 41)
@@ -314,7 +318,8 @@ def test_distributed_insert_rounds_and_bloom_passes(oracle, world, exchange, mon
                 stats = pdist.run_hot_path(ctxs, comm, k, fs, nh, table_slots=max(2 * n_keys // world, 4096), chunk_words=384,
                                            set_bytes=1536 * 1024, bin_budget_bytes=1_000_000, bloom_budget_bytes=3_000_000)
             assert all(s["exchange"] == exchange and s["filter"] == want_filter for s in stats)
-            assert stats[0]["insert_rounds"] >= 3 and stats[0]["n_chunks"] > stats[0]["insert_rounds"]
+            assert stats[0]["insert_rounds"] >= (3 if world < 8 else 2) and stats[0]["n_chunks"] > stats[0]["insert_rounds"]
+            assert stats[0]["round_mode"] == ("key ranges" if mode == "keys" else "read chunks")
             if want_filter == "sharded":
                 assert stats[0]["bloom_passes"] >= 2
             _check_distributed(oracle, ctxs, stats, reads, bounds, world, k, fs, nh)
