@@ -146,9 +146,12 @@ struct MgState {   // per-context state of the multi-GPU path
     PeerCtl *ctl() const { return reinterpret_cast<PeerCtl *>(arena); }
 };
 static CtxStates<MgState> g_mg;
-uint64_t *MgState::bk(const p3_ctx *c) const { return key_rounds > 1 ? c->d_bkeys - (uint64_t)p_lo * part_cap : c->d_bkeys; }
-uint32_t *MgState::bw(const p3_ctx *c) const { return key_rounds > 1 ? c->d_bword - (uint64_t)p_lo * part_cap : c->d_bword; }
-uint32_t *MgState::bi(const p3_ctx *c) const { return key_rounds > 1 ? c->d_bidx - (uint64_t)p_lo * part_cap : c->d_bidx; }
+// (device addresses are plain integers to the host: the shifted base lies before the allocation, only indices of the current
+// round's partitions are ever added to it)
+template <typename T> static T *shifted_base(T *p, uint64_t elems) { return reinterpret_cast<T *>(reinterpret_cast<uintptr_t>(p) - elems * sizeof(T)); }
+uint64_t *MgState::bk(const p3_ctx *c) const { return key_rounds > 1 ? shifted_base(c->d_bkeys, (uint64_t)p_lo * part_cap) : c->d_bkeys; }
+uint32_t *MgState::bw(const p3_ctx *c) const { return key_rounds > 1 ? shifted_base(c->d_bword, (uint64_t)p_lo * part_cap) : c->d_bword; }
+uint32_t *MgState::bi(const p3_ctx *c) const { return key_rounds > 1 ? shifted_base(c->d_bidx, (uint64_t)p_lo * part_cap) : c->d_bidx; }
 // multi-word k-mers (see the end of this file)
 struct LongMg {
     uint64_t *d_store = nullptr; uint64_t cap_store = 0;    // bytes

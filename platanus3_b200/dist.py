@@ -16,6 +16,12 @@ P3_MG_EXCHANGE=nccl selects the staged transport: the same regions are filled in
 with all_to_all_single (the baseline the fused path is measured against). The same driver runs over an
 emulated communicator (several contexts of one process on one GPU and one stream), which is how the
 parity tests exercise the distributed algorithm on a single-GPU box.
+
+Inputs whose records an owner cannot hold at once (BASELINE.json configs[3]) run A and B1 in rounds — over key
+ranges (every round scans all reads and moves the keys of a group of table partitions, whose verdicts follow at once)
+or, with P3_MG_ROUNDS=chunks, over read chunks (the records travel a second time for the verdicts) — B2 in rounds
+of chunks and the sharded Bloom adds in passes (plan_rounds, bin_budget_bytes, bloom_budget_bytes).
+Multi-word k-mers (k > 32) take B2 as W-word records to the owner of their std::hash (p3_mg_long_*).
 """
 import ctypes as C
 import os

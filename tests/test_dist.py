@@ -26,6 +26,19 @@ def test_owner_function_is_a_stable_uniform_partition():
     assert L.p3_owner_of_key(12345, 1) == 0
 
 
+def test_round_planning():
+    """insert rounds: one round while the owner's bins fit the budget, otherwise the fewest rounds of whole chunks that do"""
+    assert pdist.plan_rounds(19, 4_420_000_000, 80e9) == (1, 19)                 # configs[1]: 73 GB of bins, one round
+    n_rounds, cpr = pdist.plan_rounds(44, 10_276_565_536, 45e9)                  # configs[3]: 170 GB of bins
+    assert (n_rounds, cpr) == (4, 11) and n_rounds * cpr >= 44
+    assert pdist.plan_rounds(3, 10 ** 12, 1) == (3, 1)                           # never more rounds than chunks
+    assert pdist.plan_rounds(1, 10 ** 12, 1) == (1, 1)
+    for n_chunks in range(1, 40):
+        for want in (1, 2, 3, 5, 8, 100):
+            r, c = pdist.plan_rounds(n_chunks, want * 1000, 16500)
+            assert 1 <= r <= n_chunks and (r - 1) * c < n_chunks <= r * c
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
