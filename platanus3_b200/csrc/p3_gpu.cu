@@ -239,15 +239,16 @@ struct PeerOut { uint64_t *keys[kMaxPeers]; uint32_t *words[kMaxPeers]; };
 // forward k-mer is a funnel shift of (hi, lo) — no per-position bit reversal.
 constexpr int kScatterThreads = 4 * kTileWords;
 constexpr int kScatterPer = kTilePos / kScatterThreads;   // 8
-template <bool HAS_MASK, int PMODE, bool PEER = false>
+template <bool HAS_MASK, int PMODE, bool PEER = false, bool FILTER = false>
 __global__ void __launch_bounds__(kScatterThreads, 3)
 scatter21_kernel(const uint64_t *__restrict__ packed, const uint32_t *__restrict__ rend,
                  const uint32_t *__restrict__ nmask, uint64_t w0, uint64_t w1, uint32_t P,
                  unsigned long long *cursor, uint64_t *__restrict__ bkeys, uint32_t *__restrict__ bword,
                  uint32_t *__restrict__ valid_plane, uint64_t tag, Stats *st, PeerOut peer = PeerOut(), uint64_t cap = 0,
                  uint32_t flt_lo = 0, uint32_t flt_hi = 0, uint32_t flt_P = 0) {
-    // flt_hi > 0 (multi-GPU key-range rounds): only the keys whose TABLE partition (of flt_P) lies in [flt_lo, flt_hi)
-    // are binned in this pass; the valid plane is written for every position as always
+    // FILTER (multi-GPU key-range rounds; its own instantiation so that the unfiltered kernels keep their register budget): only the
+    // keys whose TABLE partition (of flt_P) lies in [flt_lo, flt_hi) are binned in this pass; the valid plane is written for every
+    // position as always
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ScatterSmem21 &sm = *reinterpret_cast<ScatterSmem21 *>(smem_raw);
     const uint64_t W21 = ~0ULL << (64 - (kShortK - 1));
@@ -286,7 +287,7 @@ scatter21_kernel(const uint64_t *__restrict__ packed, const uint32_t *__restrict
                 const uint64_t f = window(hi, lo, o) >> (64 - 2 * kShortK);
                 const uint64_t r = (o ? ((rlo >> (2 * o)) | (rhi << (64 - 2 * o))) : rlo) & kKey42;
                 const uint64_t key = f <= r ? f : r;
-                if (PEER && flt_hi) {
+                if (FILTER) {
                     const uint32_t tp = part_of(fmix64(key), flt_P);
                     if (tp < flt_lo || tp >= flt_hi) continue;
                 }
@@ -1323,6 +1324,8 @@ static int scatter_attrs(p3_ctx *c) {
     CU(cudaFuncSetAttribute(scatter21_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, s21));
     CU(cudaFuncSetAttribute(scatter21_kernel<true, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s21));
     CU(cudaFuncSetAttribute(scatter21_kernel<false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s21));
+    CU(cudaFuncSetAttribute(scatter21_kernel<true, 1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s21));
+    CU(cudaFuncSetAttribute(scatter21_kernel<false, 1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s21));
     CU(cudaFuncSetAttribute(scatter_kmer_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sPL));
     CU(cudaFuncSetAttribute(scatter_kmer_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sPL));
     CU(cudaFuncSetAttribute(scatter_kmer_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sPL));

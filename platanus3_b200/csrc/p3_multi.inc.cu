@@ -398,9 +398,11 @@ int p3_mg_count_send(p3_ctx *c, uint64_t ch) {
         }
         const unsigned sblocks = (unsigned)std::min<uint64_t>((w1 - w0 + kTileWords - 1) / kTileWords, (uint64_t)c->n_sm * 3);
         const uint64_t tag = (uint64_t)m.my_rank << kRecRankShift;
-        const uint32_t flo = m.key_rounds > 1 ? m.p_lo : 0, fhi = m.key_rounds > 1 ? m.p_hi : 0;   // key-range rounds: this round's partitions only
-        if (c->d_nmask) scatter21_kernel<true, 1, true><<<sblocks, kScatterThreads, kSmem21, c->stream>>>(c->d_packed, c->d_rend, c->d_nmask, w0, w1, m.n_ranks, m.d_sent, nullptr, nullptr, c->d_valid, tag, c->d_stats, po, m.capA, flo, fhi, c->parts);
-        else scatter21_kernel<false, 1, true><<<sblocks, kScatterThreads, kSmem21, c->stream>>>(c->d_packed, c->d_rend, nullptr, w0, w1, m.n_ranks, m.d_sent, nullptr, nullptr, c->d_valid, tag, c->d_stats, po, m.capA, flo, fhi, c->parts);
+        if (m.key_rounds > 1) {   // key-range rounds: this round's partitions only
+            if (c->d_nmask) scatter21_kernel<true, 1, true, true><<<sblocks, kScatterThreads, kSmem21, c->stream>>>(c->d_packed, c->d_rend, c->d_nmask, w0, w1, m.n_ranks, m.d_sent, nullptr, nullptr, c->d_valid, tag, c->d_stats, po, m.capA, m.p_lo, m.p_hi, c->parts);
+            else scatter21_kernel<false, 1, true, true><<<sblocks, kScatterThreads, kSmem21, c->stream>>>(c->d_packed, c->d_rend, nullptr, w0, w1, m.n_ranks, m.d_sent, nullptr, nullptr, c->d_valid, tag, c->d_stats, po, m.capA, m.p_lo, m.p_hi, c->parts);
+        } else if (c->d_nmask) scatter21_kernel<true, 1, true><<<sblocks, kScatterThreads, kSmem21, c->stream>>>(c->d_packed, c->d_rend, c->d_nmask, w0, w1, m.n_ranks, m.d_sent, nullptr, nullptr, c->d_valid, tag, c->d_stats, po, m.capA);
+        else scatter21_kernel<false, 1, true><<<sblocks, kScatterThreads, kSmem21, c->stream>>>(c->d_packed, c->d_rend, nullptr, w0, w1, m.n_ranks, m.d_sent, nullptr, nullptr, c->d_valid, tag, c->d_stats, po, m.capA);
         c->launches++;
         CU(cudaGetLastError());
     }
